@@ -1,0 +1,155 @@
+/*
+ * starr_b200.h -- C ABI of libstarr_b200.so: a device-resident sum tree for NVIDIA B200
+ * (sm_100a) that replaces the reference kernel module `starr._cython`
+ * (reference: starr/src/_sumtree_array.pyx, built by setup.py:50-55 and re-exported at
+ * starr/__init__.py:1-5).
+ *
+ * The reference module is stateless: every call receives the caller's NumPy buffers
+ * (array[n], sumtree[n]) and works on them in place.  The device replacement is stateful:
+ * one opaque handle owns (or borrows) ONE device buffer `heap[2n]` of the element type,
+ *
+ *      heap[0]        = 0                       (sumtree[0], never read)
+ *      heap[h], 1<=h<n = internal node h        (sumtree[h]);  children 2h, 2h+1
+ *      heap[n + i]    = leaf i                  (array[i])
+ *
+ * so the reference's two-array child lookup (_sumtree_array.pyx:15-20) is one load.
+ *
+ * Conventions: every function returns an st_status (0 = ok).  `stream` is a
+ * cudaStream_t passed as void* (NULL = legacy default stream).  *_device entry points
+ * take device pointers and only enqueue work; *_host entry points take host pointers,
+ * copy through the same stream and return after the stream has drained.  No torch
+ * types, no C++ types, plain pointers and sizes only.  Nothing here falls back to the
+ * CPU: if there is no usable CUDA device every call returns ST_ERR_CUDA.
+ */
+#ifndef STARR_B200_H
+#define STARR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define ST_API __attribute__((visibility("default")))
+#else
+#define ST_API
+#endif
+
+typedef struct st_tree st_tree; /* opaque */
+
+/* element types = the members of the reference's fused ARRAY_TYPE
+ * (_sumtree_array.pyx:4-11) that exist on the GPU (no 80-bit long double). */
+typedef enum st_dtype {
+    ST_I16 = 0,
+    ST_I32 = 1,
+    ST_I64 = 2,
+    ST_U8 = 3,
+    ST_U16 = 4,
+    ST_U32 = 5,
+    ST_U64 = 6,
+    ST_F32 = 7,
+    ST_F64 = 8
+} st_dtype;
+
+/* status codes; the Python layer maps them 1:1 onto the reference's exceptions */
+typedef enum st_status {
+    ST_OK = 0,
+    ST_ERR_NEGATIVE_VALS = 1,  /* ValueError "vals must be non-negative"            pyx:37-39 */
+    ST_ERR_NEGATIVE_ARRAY = 2, /* ValueError "array elements must be non-negative"  pyx:58-59 */
+    ST_ERR_INDEX = 3,          /* IndexError (Cython boundscheck)                   pyx:41-49 */
+    ST_ERR_EMPTY_VALS = 4,     /* ZeroDivisionError (i % nv with nv == 0)           pyx:44    */
+    ST_ERR_SIZE = 5,           /* TypeError "... must have the same size" / "invalid output size" */
+    ST_ERR_DTYPE = 6,          /* TypeError "No matching signature found"           pyx:4-11  */
+    ST_ERR_ARG = 7,            /* ValueError: bad argument (n < 2, null pointer, ...)         */
+    ST_ERR_CUDA = 8,           /* RuntimeError: CUDA runtime failure (see st_last_error)      */
+    ST_ERR_TOO_LARGE = 9       /* n beyond the 32-bit heap-index limit (n <= 2^31 - 1)        */
+} st_status;
+
+/* flags for st_update_device */
+#define ST_UPDATE_DEFAULT 0
+#define ST_UPDATE_SYNC_CHECK 1 /* wait for the batch and return its validation status */
+
+ST_API int st_abi_version(void);
+ST_API const char *st_status_string(int status);
+ST_API const char *st_last_error(void); /* detail of the last failure on this thread */
+ST_API int st_dtype_size(int dtype);     /* bytes, or -1 */
+
+/* ---- lifetime -------------------------------------------------------------------- */
+/* Create a tree of n >= 2 zero leaves on CUDA device `device`.  If external_heap is not
+ * NULL it must be a device buffer of 2n elements that outlives the handle (e.g. a torch
+ * tensor); otherwise the library allocates it.  The tree starts all-zero (consistent). */
+ST_API int st_create(int64_t n, int dtype, int device, void *external_heap, st_tree **out);
+ST_API int st_destroy(st_tree *t);
+ST_API int64_t st_size(const st_tree *t);
+ST_API int st_dtype_of(const st_tree *t);
+ST_API int st_device_of(const st_tree *t);
+ST_API void *st_heap_ptr(const st_tree *t); /* device pointer to heap[2n] */
+/* Pre-size the update workspace for batches of up to max_batch updates (so that no
+ * allocation happens later, e.g. inside CUDA-graph capture). */
+ST_API int st_reserve(st_tree *t, int64_t max_batch);
+
+/* ---- raw state transfer (what the stateless reference functions need) ------------ */
+/* leaves -> heap[n..2n), tree -> heap[0..n); either may be NULL.  No validation, no build:
+ * replaces handing (array, sumtree) to the module, _sumtree_array.pyx:22-26. */
+ST_API int st_load_host(st_tree *t, const void *leaves, const void *tree);
+ST_API int st_store_host(const st_tree *t, void *leaves, void *tree);
+ST_API int st_gather_leaves_host(const st_tree *t, const int64_t *idx_host, int64_t m, void *out_host);
+ST_API int st_gather_leaves_device(const st_tree *t, const int64_t *idx_dev, int64_t m, void *out_dev,
+                            void *stream);
+
+/* ---- build: replaces build_sumtree_from_array, _sumtree_array.pyx:51-64 ---------- */
+/* Reject any negative leaf BEFORE touching the tree (ST_ERR_NEGATIVE_ARRAY), then
+ * node = left + right for h = n-1 .. 1 (pairwise, level by level). */
+ST_API int st_build(st_tree *t, void *stream);                 /* from the resident leaves; waits */
+ST_API int st_build_from_host(st_tree *t, const void *leaves); /* H2D leaves, then st_build */
+ST_API int st_build_from_device(st_tree *t, const void *leaves_dev, void *stream);
+
+/* ---- update: replaces update_sumtree, _sumtree_array.pyx:22-49 ------------------- */
+/* For j = 0..ni-1 in batch order: d = vals[j % nv] - leaf; leaf += d; every ancestor += d.
+ * Bit-exact with the sequential reference for every dtype (floats: ordered per-node folds).
+ * Validation (negative vals over ALL nv entries, index range) happens before any write. */
+ST_API int st_update_device(st_tree *t, const int64_t *idx_dev, int64_t ni, const void *vals_dev,
+                     int64_t nv, void *stream, int flags);
+ST_API int st_update_host(st_tree *t, const int64_t *idx_host, int64_t ni, const void *vals_host,
+                   int64_t nv);
+
+/* ---- prefix-sum search: replaces get_prefix_sum_idx, _sumtree_array.pyx:66-122 --- */
+ST_API int st_search_device(const st_tree *t, const void *vals_dev, int64_t m, int64_t *out_dev,
+                     void *stream);
+ST_API int st_search_host(const st_tree *t, const void *vals_host, int64_t m, int64_t *out_host);
+/* sample(): vals = (T)(double(root) * u) then search; replaces sumtree_array.py:417-421.
+ * prio_out (nullable) receives the sampled leaves' values (same dtype as the tree). */
+ST_API int st_sample_uniform_device(const st_tree *t, const double *u_dev, int64_t m, int64_t *out_dev,
+                             void *prio_out_dev, void *stream);
+ST_API int st_sample_uniform_host(const st_tree *t, const double *u_host, int64_t m, int64_t *out_host);
+
+/* ---- sums: replace sum_over / strided_sum, _sumtree_array.pyx:131-194 ------------ */
+ST_API int st_root_host(const st_tree *t, void *out_scalar); /* sumtree[1], sumtree_array.py:503 */
+ST_API int st_sum_over_host(const st_tree *t, int64_t index_from, int64_t index_to, void *out_scalar);
+/* nout must be ceil(n/stride) (ST_ERR_SIZE otherwise, pyx:178-179) */
+ST_API int st_strided_sum_device(const st_tree *t, int64_t stride, void *out_dev, int64_t nout,
+                          void *stream);
+ST_API int st_strided_sum_host(const st_tree *t, int64_t stride, void *out_host, int64_t nout);
+/* Non-contiguous axis sum (replaces the ndarray.sum fallback, sumtree_array.py:514):
+ * leaves viewed as [A][R][C]; out[a][c] = ((x[a][0][c] + x[a][1][c]) + ...) in row order.
+ * Output element type: the tree dtype for f32/f64, int64 for signed and uint64 for unsigned
+ * integers (NumPy's default accumulator).  Requires A*R*C == n. */
+ST_API int st_axis_fold_device(const st_tree *t, int64_t A, int64_t R, int64_t C, void *out_dev,
+                        void *stream);
+ST_API int st_axis_fold_host(const st_tree *t, int64_t A, int64_t R, int64_t C, void *out_host);
+
+/* ---- deferred validation status of *_device calls -------------------------------- */
+/* Waits for `stream`, returns the first validation error recorded since the last clear
+ * (ST_OK if none) and optionally clears it. A failed batch is skipped as a whole. */
+ST_API int st_poll_status(st_tree *t, void *stream, int clear);
+
+/* statistics of the most recent float update (for profiling; all zeros for int trees):
+ * out[0]=segments resolved by the exact order-independent fast path,
+ * out[1]=segments folded sequentially, out[2]=elements in those, out[3]=longest chain */
+ST_API int st_update_stats(st_tree *t, void *stream, int64_t out[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STARR_B200_H */

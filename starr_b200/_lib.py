@@ -1,0 +1,266 @@
+"""ctypes binding of ``libstarr_b200.so`` (C ABI declared in ``include/starr_b200.h``).
+
+This module is the only place that touches the shared library.  There is no CPU fallback:
+if the library is missing it raises at import of the first symbol, and if there is no CUDA
+device ``st_create`` fails with ``ST_ERR_CUDA`` and we raise ``RuntimeError``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_int, c_int64, c_void_p
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libstarr_b200.so")
+
+# st_dtype codes (include/starr_b200.h) <-> NumPy dtypes: the members of the reference's fused
+# ARRAY_TYPE (starr/src/_sumtree_array.pyx:4-11) that exist on the GPU.
+DTYPE_CODES = {
+    np.dtype(np.int16): 0,
+    np.dtype(np.int32): 1,
+    np.dtype(np.int64): 2,
+    np.dtype(np.uint8): 3,
+    np.dtype(np.uint16): 4,
+    np.dtype(np.uint32): 5,
+    np.dtype(np.uint64): 6,
+    np.dtype(np.float32): 7,
+    np.dtype(np.float64): 8,
+}
+# NumPy's default accumulator of ndarray.sum, which st_axis_fold_* mirrors
+FOLD_DTYPES = {0: np.int64, 1: np.int64, 2: np.int64, 3: np.uint64, 4: np.uint64, 5: np.uint64,
+               6: np.uint64, 7: np.float32, 8: np.float64}
+
+ST_OK = 0
+ST_ERR_NEGATIVE_VALS = 1
+ST_ERR_NEGATIVE_ARRAY = 2
+ST_ERR_INDEX = 3
+ST_ERR_EMPTY_VALS = 4
+ST_ERR_SIZE = 5
+ST_ERR_DTYPE = 6
+ST_ERR_ARG = 7
+ST_ERR_CUDA = 8
+ST_ERR_TOO_LARGE = 9
+
+ST_UPDATE_SYNC_CHECK = 1
+
+# status -> (exception type, message of the reference where it has one)
+_EXC = {
+    ST_ERR_NEGATIVE_VALS: (ValueError, "vals must be non-negative"),
+    ST_ERR_NEGATIVE_ARRAY: (ValueError, "array elements must be non-negative"),
+    ST_ERR_INDEX: (IndexError, "Out of bounds on buffer access (axis 0)"),
+    ST_ERR_EMPTY_VALS: (ZeroDivisionError, "integer division or modulo by zero"),
+    ST_ERR_SIZE: (TypeError, None),
+    ST_ERR_DTYPE: (TypeError, "No matching signature found"),
+    ST_ERR_ARG: (ValueError, None),
+    ST_ERR_CUDA: (RuntimeError, None),
+    ST_ERR_TOO_LARGE: (ValueError, None),
+}
+
+_SIGNATURES = {
+    "st_abi_version": (c_int, []),
+    "st_status_string": (c_char_p, [c_int]),
+    "st_last_error": (c_char_p, []),
+    "st_dtype_size": (c_int, [c_int]),
+    "st_create": (c_int, [c_int64, c_int, c_int, c_void_p, POINTER(c_void_p)]),
+    "st_destroy": (c_int, [c_void_p]),
+    "st_size": (c_int64, [c_void_p]),
+    "st_dtype_of": (c_int, [c_void_p]),
+    "st_device_of": (c_int, [c_void_p]),
+    "st_heap_ptr": (c_void_p, [c_void_p]),
+    "st_reserve": (c_int, [c_void_p, c_int64]),
+    "st_load_host": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "st_store_host": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "st_gather_leaves_host": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "st_gather_leaves_device": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "st_build": (c_int, [c_void_p, c_void_p]),
+    "st_build_from_host": (c_int, [c_void_p, c_void_p]),
+    "st_build_from_device": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "st_update_device": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int]),
+    "st_update_host": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64]),
+    "st_search_device": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "st_search_host": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "st_sample_uniform_device": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "st_sample_uniform_host": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "st_root_host": (c_int, [c_void_p, c_void_p]),
+    "st_sum_over_host": (c_int, [c_void_p, c_int64, c_int64, c_void_p]),
+    "st_strided_sum_device": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
+    "st_strided_sum_host": (c_int, [c_void_p, c_int64, c_void_p, c_int64]),
+    "st_axis_fold_device": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
+    "st_axis_fold_host": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p]),
+    "st_poll_status": (c_int, [c_void_p, c_void_p, c_int]),
+    "st_update_stats": (c_int, [c_void_p, c_void_p, c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    """Load the shared library (once).  Raises ``ImportError`` if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -m starr_b200._build` "
+                "(or __graft_entry__.build()).  starr_b200 has no CPU fallback.")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(status: int, size_message: str | None = None) -> None:
+    """Raise the reference's exception for a non-zero st_status."""
+    if status == ST_OK:
+        return
+    exc, msg = _EXC.get(status, (RuntimeError, None))
+    detail = lib().st_last_error().decode("utf-8", "replace")
+    if status == ST_ERR_SIZE and size_message:
+        msg = size_message
+    raise exc(msg if msg is not None else detail)
+
+
+def dtype_code(dtype) -> int:
+    try:
+        return DTYPE_CODES[np.dtype(dtype)]
+    except (KeyError, TypeError):
+        # same failure the reference's fused-type dispatch produces (pyx:4-11)
+        raise TypeError("No matching signature found") from None
+
+
+def host_ptr(a: np.ndarray) -> c_void_p:
+    return c_void_p(a.ctypes.data)
+
+
+class TreeHandle:
+    """Owner of one ``st_tree*``.  Thin: argument marshalling and status -> exception only."""
+
+    def __init__(self, n: int, dtype, device: int = 0, external_heap: int | None = None):
+        self.dtype = np.dtype(dtype)
+        self.code = dtype_code(self.dtype)
+        self.n = int(n)
+        self.device = int(device)
+        out = c_void_p()
+        check(lib().st_create(self.n, self.code, self.device,
+                              c_void_p(external_heap) if external_heap else None,
+                              ctypes.byref(out)))
+        self._h = out
+
+    # -- lifetime ---------------------------------------------------------------------------
+    def close(self) -> None:
+        h, self._h = getattr(self, "_h", None), None
+        if h and _lib is not None:
+            _lib.st_destroy(h)
+
+    def __del__(self):  # noqa: D401
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def ptr(self) -> c_void_p:
+        if not self._h:
+            raise RuntimeError("tree handle is closed")
+        return self._h
+
+    @property
+    def heap_ptr(self) -> int:
+        return int(lib().st_heap_ptr(self.ptr))
+
+    def reserve(self, max_batch: int) -> None:
+        check(lib().st_reserve(self.ptr, int(max_batch)))
+
+    # -- host entry points (NumPy buffers) ---------------------------------------------------
+    def load_host(self, leaves: np.ndarray | None, tree: np.ndarray | None) -> None:
+        check(lib().st_load_host(self.ptr, host_ptr(leaves) if leaves is not None else None,
+                                 host_ptr(tree) if tree is not None else None))
+
+    def store_host(self, leaves: np.ndarray | None, tree: np.ndarray | None) -> None:
+        check(lib().st_store_host(self.ptr, host_ptr(leaves) if leaves is not None else None,
+                                  host_ptr(tree) if tree is not None else None))
+
+    def gather_leaves_host(self, idx: np.ndarray) -> np.ndarray:
+        out = np.empty(idx.size, dtype=self.dtype)
+        check(lib().st_gather_leaves_host(self.ptr, host_ptr(idx), idx.size, host_ptr(out)))
+        return out
+
+    def build(self, stream: int = 0) -> None:
+        check(lib().st_build(self.ptr, c_void_p(stream)))
+
+    def build_from_host(self, leaves: np.ndarray) -> None:
+        check(lib().st_build_from_host(self.ptr, host_ptr(leaves)))
+
+    def update_host(self, idx: np.ndarray, vals: np.ndarray) -> None:
+        check(lib().st_update_host(self.ptr, host_ptr(idx), idx.size, host_ptr(vals), vals.size))
+
+    def search_host(self, vals: np.ndarray, out: np.ndarray) -> None:
+        check(lib().st_search_host(self.ptr, host_ptr(vals), vals.size, host_ptr(out)))
+
+    def sample_uniform_host(self, u: np.ndarray, out: np.ndarray) -> None:
+        check(lib().st_sample_uniform_host(self.ptr, host_ptr(u), u.size, host_ptr(out)))
+
+    def root(self):
+        out = np.zeros(1, dtype=self.dtype)
+        check(lib().st_root_host(self.ptr, host_ptr(out)))
+        return out[0]
+
+    def sum_over(self, a: int, b: int):
+        out = np.zeros(1, dtype=self.dtype)
+        check(lib().st_sum_over_host(self.ptr, int(a), int(b), host_ptr(out)))
+        return out[0]
+
+    def strided_sum_host(self, stride: int) -> np.ndarray:
+        stride = int(stride)
+        nout = self.n // stride + (1 if self.n % stride else 0)
+        out = np.empty(nout, dtype=self.dtype)
+        check(lib().st_strided_sum_host(self.ptr, stride, host_ptr(out), nout), "invalid output size")
+        return out
+
+    def axis_fold_host(self, A: int, R: int, C: int) -> np.ndarray:
+        out = np.empty((A, C), dtype=FOLD_DTYPES[self.code])
+        check(lib().st_axis_fold_host(self.ptr, int(A), int(R), int(C), host_ptr(out)))
+        return out
+
+    # -- device entry points (raw device pointers + stream) ------------------------------------
+    def build_from_device(self, leaves_ptr: int, stream: int = 0) -> None:
+        check(lib().st_build_from_device(self.ptr, c_void_p(leaves_ptr), c_void_p(stream)))
+
+    def update_device(self, idx_ptr: int, ni: int, vals_ptr: int, nv: int, stream: int = 0,
+                      sync_check: bool = False) -> None:
+        check(lib().st_update_device(self.ptr, c_void_p(idx_ptr), int(ni), c_void_p(vals_ptr), int(nv),
+                                     c_void_p(stream), ST_UPDATE_SYNC_CHECK if sync_check else 0))
+
+    def search_device(self, vals_ptr: int, m: int, out_ptr: int, stream: int = 0) -> None:
+        check(lib().st_search_device(self.ptr, c_void_p(vals_ptr), int(m), c_void_p(out_ptr), c_void_p(stream)))
+
+    def sample_uniform_device(self, u_ptr: int, m: int, out_ptr: int, prio_ptr: int = 0,
+                              stream: int = 0) -> None:
+        check(lib().st_sample_uniform_device(self.ptr, c_void_p(u_ptr), int(m), c_void_p(out_ptr),
+                                             c_void_p(prio_ptr) if prio_ptr else None, c_void_p(stream)))
+
+    def gather_leaves_device(self, idx_ptr: int, m: int, out_ptr: int, stream: int = 0) -> None:
+        check(lib().st_gather_leaves_device(self.ptr, c_void_p(idx_ptr), int(m), c_void_p(out_ptr),
+                                            c_void_p(stream)))
+
+    def strided_sum_device(self, stride: int, out_ptr: int, nout: int, stream: int = 0) -> None:
+        check(lib().st_strided_sum_device(self.ptr, int(stride), c_void_p(out_ptr), int(nout),
+                                          c_void_p(stream)), "invalid output size")
+
+    def axis_fold_device(self, A: int, R: int, C: int, out_ptr: int, stream: int = 0) -> None:
+        check(lib().st_axis_fold_device(self.ptr, int(A), int(R), int(C), c_void_p(out_ptr), c_void_p(stream)))
+
+    def poll_status(self, stream: int = 0, clear: bool = True) -> None:
+        check(lib().st_poll_status(self.ptr, c_void_p(stream), 1 if clear else 0))
+
+    def update_stats(self, stream: int = 0) -> dict:
+        out = (c_int64 * 4)()
+        check(lib().st_update_stats(self.ptr, c_void_p(stream), out))
+        return {"fast_segments": out[0], "chain_segments": out[1], "chain_elements": out[2],
+                "longest_chain": out[3]}

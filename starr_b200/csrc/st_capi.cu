@@ -1,0 +1,434 @@
+// st_capi.cu -- the extern "C" surface declared in include/starr_b200.h: handle lifetime,
+// host<->device staging for the *_host entry points, and status plumbing.  No kernels here.
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "st_common.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int status, const char *fmt, const char *detail = "")
+{
+    snprintf(g_err, sizeof(g_err), fmt, detail);
+    return status;
+}
+
+int cuda_fail(cudaError_t e, const char *where)
+{
+    snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+    return ST_ERR_CUDA;
+}
+
+#define CU(call)                                                \
+    do {                                                        \
+        cudaError_t e__ = (call);                               \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call);   \
+    } while (0)
+
+const int kSizes[9] = {2, 4, 8, 1, 2, 4, 8, 4, 8};
+
+int status_from_flags(unsigned int f)
+{
+    if (f & STF_NEG_VALS) return ST_ERR_NEGATIVE_VALS;
+    if (f & STF_NEG_ARRAY) return ST_ERR_NEGATIVE_ARRAY;
+    if (f & STF_INDEX) return ST_ERR_INDEX;
+    return ST_OK;
+}
+
+struct device_guard {
+    int prev = -1;
+    bool ok = true;
+    explicit device_guard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~device_guard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// wait for the stream, fetch the status word, optionally clear it on the device
+int fetch_status(st_tree *t, cudaStream_t s, bool clear)
+{
+    CU(cudaMemcpyAsync(t->h_status, t->d_status, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    const unsigned int f = t->h_status[0];
+    if (f && clear) {
+        CU(cudaMemsetAsync(t->d_status, 0, sizeof(unsigned int), s));
+        CU(cudaStreamSynchronize(s));
+    }
+    return status_from_flags(f);
+}
+
+// scratch device buffer for the *_host entry points (freed on scope exit)
+struct dev_buf {
+    void *p = nullptr;
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+    ~dev_buf()
+    {
+        if (p) cudaFree(p);
+    }
+};
+
+}  // namespace
+
+extern "C" {
+
+int st_abi_version(void) { return 1; }
+
+const char *st_status_string(int status)
+{
+    switch (status) {
+        case ST_OK: return "ok";
+        case ST_ERR_NEGATIVE_VALS: return "vals must be non-negative";
+        case ST_ERR_NEGATIVE_ARRAY: return "array elements must be non-negative";
+        case ST_ERR_INDEX: return "index out of bounds";
+        case ST_ERR_EMPTY_VALS: return "integer division or modulo by zero";
+        case ST_ERR_SIZE: return "size mismatch";
+        case ST_ERR_DTYPE: return "No matching signature found";
+        case ST_ERR_ARG: return "invalid argument";
+        case ST_ERR_CUDA: return "CUDA error";
+        case ST_ERR_TOO_LARGE: return "tree too large";
+        default: return "unknown status";
+    }
+}
+
+const char *st_last_error(void) { return g_err; }
+
+int st_dtype_size(int dtype) { return (dtype >= 0 && dtype < 9) ? kSizes[dtype] : -1; }
+
+int st_create(int64_t n, int dtype, int device, void *external_heap, st_tree **out)
+{
+    if (!out) return fail(ST_ERR_ARG, "st_create: out is NULL");
+    *out = nullptr;
+    if (dtype < 0 || dtype >= 9) return fail(ST_ERR_DTYPE, "st_create: unsupported dtype");
+    if (n < 2) return fail(ST_ERR_ARG, "input to SumTreeArray must have shape with at least 2 elements");
+    if (n > 0x7fffffffLL) return fail(ST_ERR_TOO_LARGE, "st_create: n exceeds 2^31-1 (32-bit heap index)");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(ST_ERR_CUDA, "st_create: no CUDA device available (%s); this library has no CPU path",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= count) return fail(ST_ERR_ARG, "st_create: bad device ordinal");
+    device_guard g(device);
+    if (!g.ok) return fail(ST_ERR_CUDA, "st_create: cudaSetDevice failed");
+
+    st_tree *t = new (std::nothrow) st_tree();
+    if (!t) return fail(ST_ERR_ARG, "st_create: out of host memory");
+    t->n = n;
+    t->dtype = dtype;
+    t->device = device;
+    t->esize = kSizes[dtype];
+    t->depth = st::heap_level((uint32_t)(2 * n - 1));
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) {
+        t->sm_count = prop.multiProcessorCount;
+        t->coop_ok = prop.cooperativeLaunch;
+    }
+    const size_t heap_bytes = (size_t)(2 * n) * t->esize;
+    if (external_heap) {
+        t->heap = external_heap;
+        t->owns_heap = false;
+    } else {
+        e = cudaMalloc(&t->heap, heap_bytes);
+        if (e != cudaSuccess) { delete t; return cuda_fail(e, "cudaMalloc(heap)"); }
+        t->owns_heap = true;
+    }
+    e = cudaMalloc((void **)&t->d_status, 64 * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMallocHost((void **)&t->h_status, 64 * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMemset(t->d_status, 0, 64 * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMemset(t->heap, 0, heap_bytes);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        st_destroy(t);
+        return cuda_fail(e, "st_create");
+    }
+    *out = t;
+    return ST_OK;
+}
+
+int st_destroy(st_tree *t)
+{
+    if (!t) return ST_OK;
+    device_guard g(t->device);
+    if (t->owns_heap && t->heap) cudaFree(t->heap);
+    if (t->d_status) cudaFree(t->d_status);
+    if (t->h_status) cudaFreeHost(t->h_status);
+    if (t->ws.base) cudaFree(t->ws.base);
+    delete t;
+    return ST_OK;
+}
+
+int64_t st_size(const st_tree *t) { return t ? t->n : -1; }
+int st_dtype_of(const st_tree *t) { return t ? t->dtype : -1; }
+int st_device_of(const st_tree *t) { return t ? t->device : -1; }
+void *st_heap_ptr(const st_tree *t) { return t ? t->heap : nullptr; }
+
+int st_reserve(st_tree *t, int64_t max_batch)
+{
+    if (!t || max_batch < 1) return fail(ST_ERR_ARG, "st_reserve: bad argument");
+    device_guard g(t->device);
+    if (max_batch > st::update_max_chunk()) max_batch = st::update_max_chunk();
+    if (max_batch <= t->reserved_batch && t->ws.base) return ST_OK;
+    const size_t need = st::update_workspace_bytes(t, max_batch);
+    CU(cudaDeviceSynchronize());
+    if (t->ws.base) cudaFree(t->ws.base);
+    t->ws.base = nullptr;
+    t->ws.bytes = 0;
+    CU(cudaMalloc(&t->ws.base, need));
+    t->ws.bytes = need;
+    t->reserved_batch = max_batch;
+    return ST_OK;
+}
+
+// ---- raw state transfer ------------------------------------------------------------------
+int st_load_host(st_tree *t, const void *leaves, const void *tree)
+{
+    if (!t) return fail(ST_ERR_ARG, "st_load_host: NULL tree");
+    device_guard g(t->device);
+    const size_t half = (size_t)t->n * t->esize;
+    if (tree) CU(cudaMemcpy(t->heap, tree, half, cudaMemcpyHostToDevice));
+    if (leaves) CU(cudaMemcpy((char *)t->heap + half, leaves, half, cudaMemcpyHostToDevice));
+    return ST_OK;
+}
+
+int st_store_host(const st_tree *t, void *leaves, void *tree)
+{
+    if (!t) return fail(ST_ERR_ARG, "st_store_host: NULL tree");
+    device_guard g(t->device);
+    const size_t half = (size_t)t->n * t->esize;
+    if (tree) CU(cudaMemcpy(tree, t->heap, half, cudaMemcpyDeviceToHost));
+    if (leaves) CU(cudaMemcpy(leaves, (const char *)t->heap + half, half, cudaMemcpyDeviceToHost));
+    return ST_OK;
+}
+
+int st_gather_leaves_device(const st_tree *t, const int64_t *idx_dev, int64_t m, void *out_dev, void *stream)
+{
+    if (!t || m < 0) return fail(ST_ERR_ARG, "st_gather_leaves_device: bad argument");
+    device_guard g(t->device);
+    CU(st::launch_gather(t, idx_dev, m, out_dev, (cudaStream_t)stream));
+    return ST_OK;
+}
+
+int st_gather_leaves_host(const st_tree *t, const int64_t *idx_host, int64_t m, void *out_host)
+{
+    if (!t || m < 0) return fail(ST_ERR_ARG, "st_gather_leaves_host: bad argument");
+    if (m == 0) return ST_OK;
+    device_guard g(t->device);
+    dev_buf di, dout;
+    CU(di.alloc(m * sizeof(int64_t)));
+    CU(dout.alloc(m * t->esize));
+    CU(cudaMemcpy(di.p, idx_host, m * sizeof(int64_t), cudaMemcpyHostToDevice));
+    CU(st::launch_gather(t, (const int64_t *)di.p, m, dout.p, 0));
+    CU(cudaMemcpy(out_host, dout.p, m * t->esize, cudaMemcpyDeviceToHost));
+    return ST_OK;
+}
+
+// ---- build ---------------------------------------------------------------------------------
+int st_build(st_tree *t, void *stream)
+{
+    if (!t) return fail(ST_ERR_ARG, "st_build: NULL tree");
+    device_guard g(t->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    CU(st::launch_check_leaves(t, s));
+    CU(st::launch_build(t, s));
+    const int st = fetch_status(t, s, true);
+    if (st != ST_OK) return fail(st, "%s", st_status_string(st));
+    return ST_OK;
+}
+
+int st_build_from_host(st_tree *t, const void *leaves)
+{
+    if (!t || !leaves) return fail(ST_ERR_ARG, "st_build_from_host: NULL argument");
+    device_guard g(t->device);
+    const size_t half = (size_t)t->n * t->esize;
+    CU(cudaMemcpy((char *)t->heap + half, leaves, half, cudaMemcpyHostToDevice));
+    return st_build(t, nullptr);
+}
+
+int st_build_from_device(st_tree *t, const void *leaves_dev, void *stream)
+{
+    if (!t || !leaves_dev) return fail(ST_ERR_ARG, "st_build_from_device: NULL argument");
+    device_guard g(t->device);
+    const size_t half = (size_t)t->n * t->esize;
+    void *dst = (char *)t->heap + half;
+    if (dst != leaves_dev)
+        CU(cudaMemcpyAsync(dst, leaves_dev, half, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return st_build(t, stream);
+}
+
+// ---- update --------------------------------------------------------------------------------
+int st_update_device(st_tree *t, const int64_t *idx_dev, int64_t ni, const void *vals_dev, int64_t nv,
+                     void *stream, int flags)
+{
+    if (!t || ni < 0 || nv < 0) return fail(ST_ERR_ARG, "st_update_device: bad argument");
+    if (ni > 0 && nv == 0) return fail(ST_ERR_EMPTY_VALS, "%s", st_status_string(ST_ERR_EMPTY_VALS));
+    device_guard g(t->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (ni == 0 && nv == 0) return ST_OK;
+    CU(st::launch_update(t, idx_dev, ni, vals_dev, nv, s));
+    if (flags & ST_UPDATE_SYNC_CHECK) {
+        const int st = fetch_status(t, s, true);
+        if (st != ST_OK) return fail(st, "%s", st_status_string(st));
+    }
+    return ST_OK;
+}
+
+int st_update_host(st_tree *t, const int64_t *idx_host, int64_t ni, const void *vals_host, int64_t nv)
+{
+    if (!t || ni < 0 || nv < 0) return fail(ST_ERR_ARG, "st_update_host: bad argument");
+    if (ni > 0 && nv == 0) return fail(ST_ERR_EMPTY_VALS, "%s", st_status_string(ST_ERR_EMPTY_VALS));
+    if (ni == 0 && nv == 0) return ST_OK;
+    device_guard g(t->device);
+    dev_buf di, dv;
+    CU(di.alloc(ni * sizeof(int64_t)));
+    CU(dv.alloc(nv * t->esize));
+    CU(cudaMemcpy(di.p, idx_host, ni * sizeof(int64_t), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dv.p, vals_host, nv * t->esize, cudaMemcpyHostToDevice));
+    return st_update_device(t, (const int64_t *)di.p, ni, dv.p, nv, nullptr, ST_UPDATE_SYNC_CHECK);
+}
+
+// ---- search / sample -----------------------------------------------------------------------
+int st_search_device(const st_tree *t, const void *vals_dev, int64_t m, int64_t *out_dev, void *stream)
+{
+    if (!t || m < 0) return fail(ST_ERR_ARG, "st_search_device: bad argument");
+    device_guard g(t->device);
+    CU(st::launch_search(t, vals_dev, m, out_dev, (cudaStream_t)stream));
+    return ST_OK;
+}
+
+int st_search_host(const st_tree *t, const void *vals_host, int64_t m, int64_t *out_host)
+{
+    if (!t || m < 0) return fail(ST_ERR_ARG, "st_search_host: bad argument");
+    if (m == 0) return ST_OK;
+    device_guard g(t->device);
+    dev_buf dv, dout;
+    CU(dv.alloc(m * t->esize));
+    CU(dout.alloc(m * sizeof(int64_t)));
+    CU(cudaMemcpy(dv.p, vals_host, m * t->esize, cudaMemcpyHostToDevice));
+    CU(st::launch_search(t, dv.p, m, (int64_t *)dout.p, 0));
+    CU(cudaMemcpy(out_host, dout.p, m * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    return ST_OK;
+}
+
+int st_sample_uniform_device(const st_tree *t, const double *u_dev, int64_t m, int64_t *out_dev,
+                             void *prio_out_dev, void *stream)
+{
+    if (!t || m < 0) return fail(ST_ERR_ARG, "st_sample_uniform_device: bad argument");
+    device_guard g(t->device);
+    CU(st::launch_sample(t, u_dev, m, out_dev, prio_out_dev, (cudaStream_t)stream));
+    return ST_OK;
+}
+
+int st_sample_uniform_host(const st_tree *t, const double *u_host, int64_t m, int64_t *out_host)
+{
+    if (!t || m < 0) return fail(ST_ERR_ARG, "st_sample_uniform_host: bad argument");
+    if (m == 0) return ST_OK;
+    device_guard g(t->device);
+    dev_buf du, dout;
+    CU(du.alloc(m * sizeof(double)));
+    CU(dout.alloc(m * sizeof(int64_t)));
+    CU(cudaMemcpy(du.p, u_host, m * sizeof(double), cudaMemcpyHostToDevice));
+    CU(st::launch_sample(t, (const double *)du.p, m, (int64_t *)dout.p, nullptr, 0));
+    CU(cudaMemcpy(out_host, dout.p, m * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    return ST_OK;
+}
+
+// ---- sums ----------------------------------------------------------------------------------
+int st_root_host(const st_tree *t, void *out_scalar)
+{
+    if (!t || !out_scalar) return fail(ST_ERR_ARG, "st_root_host: bad argument");
+    device_guard g(t->device);
+    CU(cudaMemcpy(out_scalar, (const char *)t->heap + t->esize, t->esize, cudaMemcpyDeviceToHost));
+    return ST_OK;
+}
+
+int st_sum_over_host(const st_tree *t, int64_t index_from, int64_t index_to, void *out_scalar)
+{
+    if (!t || !out_scalar) return fail(ST_ERR_ARG, "st_sum_over_host: bad argument");
+    // Cython boundscheck: the reference raises IndexError for positions outside the array
+    if (index_from < 0 || index_from > t->n || index_to < 0 || index_to > t->n)
+        return fail(ST_ERR_INDEX, "%s", st_status_string(ST_ERR_INDEX));
+    if (index_to - 1 == index_from && index_from >= t->n) return fail(ST_ERR_INDEX, "%s", st_status_string(ST_ERR_INDEX));
+    device_guard g(t->device);
+    dev_buf d;
+    CU(d.alloc(8));
+    CU(st::launch_sum_over(t, index_from, index_to, d.p, 0));
+    CU(cudaMemcpy(out_scalar, d.p, t->esize, cudaMemcpyDeviceToHost));
+    return ST_OK;
+}
+
+static int64_t strided_len(int64_t n, int64_t stride) { return n / stride + (n % stride ? 1 : 0); }
+
+int st_strided_sum_device(const st_tree *t, int64_t stride, void *out_dev, int64_t nout, void *stream)
+{
+    if (!t || stride < 1) return fail(ST_ERR_ARG, "st_strided_sum_device: bad argument");
+    if (nout != strided_len(t->n, stride)) return fail(ST_ERR_SIZE, "invalid output size");
+    device_guard g(t->device);
+    CU(st::launch_strided_sum(t, stride, out_dev, nout, (cudaStream_t)stream));
+    return ST_OK;
+}
+
+int st_strided_sum_host(const st_tree *t, int64_t stride, void *out_host, int64_t nout)
+{
+    if (!t || stride < 1) return fail(ST_ERR_ARG, "st_strided_sum_host: bad argument");
+    if (nout != strided_len(t->n, stride)) return fail(ST_ERR_SIZE, "invalid output size");
+    device_guard g(t->device);
+    dev_buf d;
+    CU(d.alloc(nout * t->esize));
+    CU(st::launch_strided_sum(t, stride, d.p, nout, 0));
+    CU(cudaMemcpy(out_host, d.p, nout * t->esize, cudaMemcpyDeviceToHost));
+    return ST_OK;
+}
+
+static int fold_out_size(const st_tree *t) { return (t->dtype == ST_F32) ? 4 : 8; }
+
+int st_axis_fold_device(const st_tree *t, int64_t A, int64_t R, int64_t C, void *out_dev, void *stream)
+{
+    if (!t || A < 1 || R < 1 || C < 1) return fail(ST_ERR_ARG, "st_axis_fold_device: bad argument");
+    if (A * R * C != t->n) return fail(ST_ERR_SIZE, "axis fold shape does not match the tree size");
+    device_guard g(t->device);
+    CU(st::launch_axis_fold(t, A, R, C, out_dev, (cudaStream_t)stream));
+    return ST_OK;
+}
+
+int st_axis_fold_host(const st_tree *t, int64_t A, int64_t R, int64_t C, void *out_host)
+{
+    if (!t || A < 1 || R < 1 || C < 1) return fail(ST_ERR_ARG, "st_axis_fold_host: bad argument");
+    if (A * R * C != t->n) return fail(ST_ERR_SIZE, "axis fold shape does not match the tree size");
+    device_guard g(t->device);
+    dev_buf d;
+    const size_t bytes = (size_t)A * C * fold_out_size(t);
+    CU(d.alloc(bytes));
+    CU(st::launch_axis_fold(t, A, R, C, d.p, 0));
+    CU(cudaMemcpy(out_host, d.p, bytes, cudaMemcpyDeviceToHost));
+    return ST_OK;
+}
+
+// ---- deferred status -----------------------------------------------------------------------
+int st_poll_status(st_tree *t, void *stream, int clear)
+{
+    if (!t) return fail(ST_ERR_ARG, "st_poll_status: NULL tree");
+    device_guard g(t->device);
+    const int st = fetch_status(t, (cudaStream_t)stream, clear != 0);
+    if (st != ST_OK) return fail(st, "%s", st_status_string(st));
+    return ST_OK;
+}
+
+int st_update_stats(st_tree *t, void *stream, int64_t out[4])
+{
+    if (!t || !out) return fail(ST_ERR_ARG, "st_update_stats: bad argument");
+    device_guard g(t->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    CU(cudaMemcpyAsync(t->h_status, t->d_status, 64 * sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    for (int i = 0; i < 4; ++i) out[i] = t->h_status[4 + i];
+    return ST_OK;
+}
+
+}  // extern "C"

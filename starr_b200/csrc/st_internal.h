@@ -1,0 +1,53 @@
+// st_internal.h -- shared between the translation units of libstarr_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/starr_b200.h"
+
+// Device-side status word bits (written by validation kernels, read by every later kernel
+// of the same batch: a failed batch is skipped as a whole, see DESIGN.md "error atomicity").
+#define STF_NEG_VALS 1u
+#define STF_NEG_ARRAY 2u
+#define STF_INDEX 4u
+
+struct st_workspace {
+    void *base = nullptr;  // one cudaMalloc, carved up per batch
+    size_t bytes = 0;
+};
+
+struct st_tree {
+    int64_t n = 0;
+    int dtype = 0;
+    int device = 0;
+    int esize = 0;
+    int depth = 0;        // level of the deepest heap node: floor(log2(2n-1))
+    void *heap = nullptr; // device, 2n elements
+    bool owns_heap = false;
+    unsigned int *d_status = nullptr;  // device status word (+ spare counters), 64 words
+    unsigned int *h_status = nullptr;  // pinned host mirror, 64 words
+    st_workspace ws;
+    int64_t reserved_batch = 0;
+    int sm_count = 148;
+    int coop_ok = 0;
+};
+
+// launchers implemented in the .cu files; every one only enqueues on `s`
+namespace st {
+
+cudaError_t launch_check_leaves(st_tree *t, cudaStream_t s);  // sets STF_NEG_ARRAY
+cudaError_t launch_build(st_tree *t, cudaStream_t s);         // skipped on device if status != 0
+cudaError_t launch_search(const st_tree *t, const void *vals, int64_t m, int64_t *out, cudaStream_t s);
+cudaError_t launch_sample(const st_tree *t, const double *u, int64_t m, int64_t *out, void *prio,
+                          cudaStream_t s);
+cudaError_t launch_gather(const st_tree *t, const int64_t *idx, int64_t m, void *out, cudaStream_t s);
+cudaError_t launch_sum_over(const st_tree *t, int64_t a, int64_t b, void *out_dev, cudaStream_t s);
+cudaError_t launch_strided_sum(const st_tree *t, int64_t stride, void *out, int64_t nout, cudaStream_t s);
+cudaError_t launch_axis_fold(const st_tree *t, int64_t A, int64_t R, int64_t C, void *out, cudaStream_t s);
+
+size_t update_workspace_bytes(const st_tree *t, int64_t batch);
+cudaError_t launch_update(st_tree *t, const int64_t *idx, int64_t ni, const void *vals, int64_t nv,
+                          cudaStream_t s);
+int64_t update_max_chunk();
+
+}  // namespace st

@@ -1,0 +1,431 @@
+// st_tree_kernels.cu -- build, prefix-sum search / sampling, range sums, axis fold.
+//
+// Hand-written sm_100a kernels that replace (reference file:line)
+//   build_sumtree_from_array   starr/src/_sumtree_array.pyx:51-64
+//   get_prefix_sum_idx         starr/src/_sumtree_array.pyx:66-122
+//   sum_over / strided_sum     starr/src/_sumtree_array.pyx:131-194
+//   the ndarray.sum fallback   starr/sumtree_array.py:514
+// on the single device buffer heap[2n] described in include/starr_b200.h.
+// All of them are HBM/L2 latency- or bandwidth-bound gathers and streams; there is no
+// contraction anywhere, so no tensor cores.
+#include "st_common.cuh"
+
+namespace st {
+
+// =========================================================================================
+// leaf validation (pyx:58-59: min(array) < 0 -> ValueError before any write)
+// =========================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256) check_leaves_kernel(const T *__restrict__ leaves, int64_t n,
+                                                           unsigned int *status)
+{
+    if constexpr (!is_signed_t<T>::value) {
+        return;
+    } else {
+        bool bad = false;
+        const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+        int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        // 8 independent loads in flight per thread
+        for (; i + 7 * stride < n; i += 8 * stride) {
+            T v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = __ldg(leaves + i + k * stride);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) bad |= (v[k] < T(0));
+        }
+        for (; i < n; i += stride) bad |= (__ldg(leaves + i) < T(0));
+        if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(status, STF_NEG_ARRAY);
+    }
+}
+
+cudaError_t launch_check_leaves(st_tree *t, cudaStream_t s)
+{
+    ST_DISPATCH(t->dtype, {
+        const T *leaves = (const T *)t->heap + t->n;
+        unsigned g = grid_for(t->n, 256 * 8, (int64_t)t->sm_count * 8);
+        check_leaves_kernel<T><<<g, 256, 0, s>>>(leaves, t->n, t->d_status);
+    });
+    return cudaGetLastError();
+}
+
+// =========================================================================================
+// build: node = left + right, bottom-up, K levels per pass inside shared memory
+// =========================================================================================
+// One CTA owns the subtree rooted at node r of level `root_level` and computes its levels
+// root_level+k-1 .. root_level from the already-final level root_level+k.  A node h >= n is
+// a leaf (loaded, never computed); h >= 2n does not exist.  Pairwise left+right is exactly
+// the reference's loop order-independent result (every node is one add of its two children).
+template <typename T> struct alignas(2 * sizeof(T)) pair_t { T l, r; };
+
+constexpr int BUILD_K = 11;        // levels per pass
+constexpr int BUILD_THREADS = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(BUILD_THREADS)
+build_pass_kernel(T *__restrict__ H, uint32_t n, int root_level, int k, const unsigned int *status)
+{
+    if (*status) return;  // failed validation: leave the tree untouched (pyx:58-59)
+    __shared__ T buf[2][1 << (BUILD_K - 1)];
+    const uint32_t r = (1u << root_level) + blockIdx.x;
+    const uint64_t two_n = 2ull * n;
+
+    // level root_level + k - 1, children read from global as aligned pairs
+    int lev = k - 1;
+    {
+        const uint32_t cnt = 1u << lev;
+        const uint64_t base = (uint64_t)r << lev;
+        for (uint32_t i = threadIdx.x; i < cnt; i += BUILD_THREADS) {
+            const uint64_t h = base + i;
+            T v = T(0);
+            if (h < n) {
+                pair_t<T> c = *reinterpret_cast<const pair_t<T> *>(H + 2 * h);
+                v = t_add<T>(c.l, c.r);
+                H[h] = v;
+            } else if (h < two_n) {
+                v = H[h];
+            }
+            buf[0][i] = v;
+        }
+    }
+    int cur = 0;
+    while (lev > 0) {
+        __syncthreads();
+        --lev;
+        const uint32_t cnt = 1u << lev;
+        const uint64_t base = (uint64_t)r << lev;
+        for (uint32_t i = threadIdx.x; i < cnt; i += BUILD_THREADS) {
+            const uint64_t h = base + i;
+            T v = T(0);
+            if (h < n) {
+                v = t_add<T>(buf[cur][2 * i], buf[cur][2 * i + 1]);
+                H[h] = v;
+            } else if (h < two_n) {
+                v = H[h];
+            }
+            buf[cur ^ 1][i] = v;
+        }
+        cur ^= 1;
+    }
+}
+
+cudaError_t launch_build(st_tree *t, cudaStream_t s)
+{
+    const uint32_t n = (uint32_t)t->n;
+    int top = t->depth;  // deepest level, already final (leaves)
+    ST_DISPATCH(t->dtype, {
+        T *H = (T *)t->heap;
+        while (top > 0) {
+            int root_level = top - BUILD_K;
+            if (root_level < 0) root_level = 0;
+            int k = top - root_level;
+            uint64_t first = 1ull << root_level;
+            uint64_t last = first * 2 < n ? first * 2 : n;  // roots r >= n have nothing to compute
+            if (last > first)
+                build_pass_kernel<T><<<(unsigned)(last - first), BUILD_THREADS, 0, s>>>(
+                    H, n, root_level, k, t->d_status);
+            top = root_level;
+        }
+    });
+    return cudaGetLastError();
+}
+
+// =========================================================================================
+// prefix-sum search (pyx:84-120) and sampling (sumtree_array.py:417-421)
+// =========================================================================================
+// Each thread walks Q independent queries in lock step so that Q dependent-load chains are
+// in flight per thread.  The top of the tree (heap[0 .. stage_nodes)) is staged once per
+// CTA into shared memory with a TMA bulk copy (cp.async.bulk + mbarrier); deeper levels are
+// read-only gathers through L1/L2 (ld.global.nc).
+constexpr int SEARCH_THREADS = 512;
+constexpr int SEARCH_Q = 4;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// Stage `bytes` (multiple of 16) from global to shared with the TMA engine; all threads
+// return once the data has landed.
+__device__ __forceinline__ void tma_stage(void *smem_dst, const void *gsrc, uint32_t bytes,
+                                          uint64_t *bar)
+{
+    const uint32_t bar_a = smem_u32(bar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes)
+                     : "memory");
+        const uint32_t CH = 32768;
+        for (uint32_t off = 0; off < bytes; off += CH) {
+            uint32_t sz = bytes - off < CH ? bytes - off : CH;
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+                    "r"(smem_u32((const char *)smem_dst + off)),
+                "l"((const char *)gsrc + off), "r"(sz), "r"(bar_a)
+                : "memory");
+        }
+    }
+    // every thread waits on phase 0
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar_a)
+            : "memory");
+    }
+}
+
+template <typename T> __device__ __forceinline__ T scale_uniform(T root, double u)
+{
+    // (root * u).astype(dtype): float64 multiply, then one conversion (sumtree_array.py:420)
+    if constexpr (sizeof(T) == 4 && is_float_t<T>::value) {
+        return __double2float_rn(__dmul_rn((double)root, u));
+    } else if constexpr (is_float_t<T>::value) {
+        return __dmul_rn(root, u);
+    } else {
+        return (T)__dmul_rn((double)root, u);  // C truncation toward zero
+    }
+}
+
+template <typename T, bool STAGE, bool UNIFORM>
+__global__ void __launch_bounds__(SEARCH_THREADS)
+search_kernel(const T *__restrict__ H, uint32_t n, int depth, const void *__restrict__ in,
+              int64_t m, int64_t *__restrict__ out, T *__restrict__ prio, uint32_t stage_nodes)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    T *top = reinterpret_cast<T *>(smem_raw);
+    __shared__ __align__(8) uint64_t bar;
+    if constexpr (STAGE) {
+        tma_stage(top, H, stage_nodes * (uint32_t)sizeof(T), &bar);
+    } else {
+        stage_nodes = 0;
+    }
+    T root = T(0);
+    if constexpr (UNIFORM) root = STAGE ? top[1] : __ldg(H + 1);
+
+    const int64_t per_block = (int64_t)SEARCH_THREADS * SEARCH_Q;
+    for (int64_t base = (int64_t)blockIdx.x * per_block; base < m; base += (int64_t)gridDim.x * per_block) {
+        uint32_t h[SEARCH_Q];
+        T p[SEARCH_Q];
+#pragma unroll
+        for (int q = 0; q < SEARCH_Q; ++q) {
+            const int64_t i = base + threadIdx.x + (int64_t)q * SEARCH_THREADS;
+            h[q] = 1;
+            p[q] = T(0);
+            if (i < m) {
+                if constexpr (UNIFORM) p[q] = scale_uniform<T>(root, __ldg((const double *)in + i));
+                else p[q] = __ldg((const T *)in + i);
+            } else {
+                h[q] = n;  // inactive: already "at a leaf"
+            }
+        }
+        for (int lev = 0; lev < depth; ++lev) {
+            T lv[SEARCH_Q];
+#pragma unroll
+            for (int q = 0; q < SEARCH_Q; ++q) {
+                const uint32_t c = 2u * h[q];
+                lv[q] = T(0);
+                if (h[q] < n) lv[q] = (c < stage_nodes) ? top[c] : __ldg(H + c);
+            }
+#pragma unroll
+            for (int q = 0; q < SEARCH_Q; ++q) {
+                if (h[q] < n) {
+                    const uint32_t c = 2u * h[q];
+                    if (p[q] >= lv[q]) {  // pyx:107: ties go right
+                        p[q] = t_sub<T>(p[q], lv[q]);
+                        h[q] = c + 1;
+                    } else {
+                        h[q] = c;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < SEARCH_Q; ++q) {
+            const int64_t i = base + threadIdx.x + (int64_t)q * SEARCH_THREADS;
+            if (i < m) {
+                out[i] = (int64_t)h[q] - (int64_t)n;
+                if (prio) prio[i] = __ldg(H + h[q]);
+            }
+        }
+    }
+}
+
+template <typename T, bool UNIFORM>
+static cudaError_t launch_search_t(const st_tree *t, const void *in, int64_t m, int64_t *out, void *prio,
+                                   cudaStream_t s)
+{
+    if (m <= 0) return cudaSuccess;
+    const uint32_t n = (uint32_t)t->n;
+    const T *H = (const T *)t->heap;
+    const int64_t per_block = (int64_t)SEARCH_THREADS * SEARCH_Q;
+    // stage the top 64 KiB of the heap when there are enough queries to amortise it
+    uint32_t stage_nodes = 65536u / (uint32_t)sizeof(T);
+    const uint64_t two_n = 2ull * n;
+    bool stage = m >= 16 * per_block;
+    if (two_n < stage_nodes) {
+        // whole heap fits: round down to a multiple of 16 bytes (the tail is read from global)
+        stage_nodes = (uint32_t)(two_n * sizeof(T) / 16 * 16 / sizeof(T));
+        if (stage_nodes < 4) stage = false;
+    }
+    if (stage) {
+        const size_t smem = (size_t)stage_nodes * sizeof(T);
+        auto kern = search_kernel<T, true, UNIFORM>;
+        static bool attr_done = false;
+        if (!attr_done) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+            if (e != cudaSuccess) return e;
+            attr_done = true;
+        }
+        unsigned g = grid_for(m, (int)per_block, (int64_t)t->sm_count * 3);
+        kern<<<g, SEARCH_THREADS, smem, s>>>(H, n, t->depth, in, m, out, (T *)prio, stage_nodes);
+    } else {
+        unsigned g = grid_for(m, (int)per_block, (int64_t)t->sm_count * 4);
+        search_kernel<T, false, UNIFORM><<<g, SEARCH_THREADS, 0, s>>>(H, n, t->depth, in, m, out, (T *)prio, 0);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_search(const st_tree *t, const void *vals, int64_t m, int64_t *out, cudaStream_t s)
+{
+    ST_DISPATCH(t->dtype, return (launch_search_t<T, false>(t, vals, m, out, nullptr, s)));
+    return cudaSuccess;
+}
+
+cudaError_t launch_sample(const st_tree *t, const double *u, int64_t m, int64_t *out, void *prio,
+                          cudaStream_t s)
+{
+    ST_DISPATCH(t->dtype, return (launch_search_t<T, true>(t, u, m, out, prio, s)));
+    return cudaSuccess;
+}
+
+// =========================================================================================
+// leaf gather
+// =========================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256) gather_kernel(const T *__restrict__ leaves, int64_t n,
+                                                     const int64_t *__restrict__ idx, int64_t m,
+                                                     T *__restrict__ out)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t l = idx[i];
+        out[i] = (l >= 0 && l < n) ? __ldg(leaves + l) : T(0);
+    }
+}
+
+cudaError_t launch_gather(const st_tree *t, const int64_t *idx, int64_t m, void *out, cudaStream_t s)
+{
+    if (m <= 0) return cudaSuccess;
+    ST_DISPATCH(t->dtype, {
+        gather_kernel<T><<<grid_for(m, 256, (int64_t)t->sm_count * 8), 256, 0, s>>>(
+            (const T *)t->heap + t->n, t->n, idx, m, (T *)out);
+    });
+    return cudaGetLastError();
+}
+
+// =========================================================================================
+// range sums (pyx:131-170) -- the reference's exact subtraction sequence, one thread per output
+// =========================================================================================
+template <typename T> __device__ __forceinline__ T range_sum(const T *__restrict__ H, int64_t n, int64_t a, int64_t b)
+{
+    b -= 1;
+    if (a == b) return __ldg(H + n + a);
+    if (a > b) return T(0);
+    a += n;
+    b += n;
+    T sub = T(0);
+    const bool wrapped = a < (a ^ b);  // ends at different depths (pyx:144)
+    if (wrapped) {
+        if ((b & 1) == 0) sub = t_add<T>(sub, __ldg(H + b + 1));
+        b >>= 1;
+    }
+    while ((a >> 1) != (b >> 1)) {
+        if (a & 1) sub = t_add<T>(sub, __ldg(H + a - 1));
+        if ((b & 1) == 0) sub = t_add<T>(sub, __ldg(H + b + 1));
+        a >>= 1;
+        b >>= 1;
+    }
+    const T cover = wrapped ? __ldg(H + 1) : __ldg(H + (a >> 1));
+    return t_sub<T>(cover, sub);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) strided_sum_kernel(const T *__restrict__ H, int64_t n, int64_t stride,
+                                                          T *__restrict__ out, int64_t nout)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nout; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t lo = stride * i;
+        int64_t hi = lo + stride;
+        if (hi > n) hi = n;
+        out[i] = range_sum<T>(H, n, lo, hi);
+    }
+}
+
+template <typename T>
+__global__ void sum_over_kernel(const T *__restrict__ H, int64_t n, int64_t a, int64_t b, T *out)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) *out = range_sum<T>(H, n, a, b);
+}
+
+cudaError_t launch_sum_over(const st_tree *t, int64_t a, int64_t b, void *out_dev, cudaStream_t s)
+{
+    ST_DISPATCH(t->dtype, { sum_over_kernel<T><<<1, 32, 0, s>>>((const T *)t->heap, t->n, a, b, (T *)out_dev); });
+    return cudaGetLastError();
+}
+
+cudaError_t launch_strided_sum(const st_tree *t, int64_t stride, void *out, int64_t nout, cudaStream_t s)
+{
+    if (nout <= 0) return cudaSuccess;
+    ST_DISPATCH(t->dtype, {
+        strided_sum_kernel<T><<<grid_for(nout, 256, (int64_t)t->sm_count * 8), 256, 0, s>>>(
+            (const T *)t->heap, t->n, stride, (T *)out, nout);
+    });
+    return cudaGetLastError();
+}
+
+// =========================================================================================
+// non-contiguous axis sum: sequential row-order fold (the order NumPy uses)
+// =========================================================================================
+template <typename T>
+__global__ void __launch_bounds__(128)
+axis_fold_kernel(const T *__restrict__ x, int64_t A, int64_t R, int64_t C,
+                 typename fold_acc<T>::type *__restrict__ out)
+{
+    using ACC = typename fold_acc<T>::type;
+    const int64_t total = A * C;
+    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t a = o / C, c = o - a * C;
+        const T *p = x + a * R * C + c;
+        ACC acc = (ACC)__ldg(p);
+        int64_t r = 1;
+        constexpr int U = 16;
+        for (; r + U <= R; r += U) {
+            T v[U];
+#pragma unroll
+            for (int k = 0; k < U; ++k) v[k] = __ldg(p + (r + k) * C);
+#pragma unroll
+            for (int k = 0; k < U; ++k) acc = t_add<ACC>(acc, (ACC)v[k]);
+        }
+        for (; r < R; ++r) acc = t_add<ACC>(acc, (ACC)__ldg(p + r * C));
+        out[o] = acc;
+    }
+}
+
+cudaError_t launch_axis_fold(const st_tree *t, int64_t A, int64_t R, int64_t C, void *out, cudaStream_t s)
+{
+    if (A * C <= 0) return cudaSuccess;
+    ST_DISPATCH(t->dtype, {
+        using ACC = typename fold_acc<T>::type;
+        axis_fold_kernel<T><<<grid_for(A * C, 128, (int64_t)t->sm_count * 16), 128, 0, s>>>(
+            (const T *)t->heap + t->n, A, R, C, (ACC *)out);
+    });
+    return cudaGetLastError();
+}
+
+}  // namespace st

@@ -1,0 +1,423 @@
+// st_update.cu -- batched leaf update with exact ancestor propagation.
+//
+// Replaces update_sumtree (reference starr/src/_sumtree_array.pyx:22-49):
+//
+//     for j in 0..ni-1:  d = vals[j % nv] - leaf[idx[j]];  leaf += d;  every ancestor += d
+//
+// The reference applies the updates one after another, so for floating point the result at
+// every node is the ORDERED fold  T = (((T + d_a) + d_b) + ...)  over the updates below
+// that node in batch order.  Nodes decouple, which gives the exact parallel
+// form used here:
+//
+//   1. normalised heap keys (leaf position left-aligned to `depth` bits) + stable radix sort
+//      by key with the batch position j as payload  -> duplicates of one leaf are adjacent
+//      and in batch order;
+//   2. leaf pass: one thread per run of equal leaves walks the run sequentially and emits
+//      every d_j (this is where `leaf = fl(leaf + fl(val - leaf))` happens);
+//   3a. integer dtypes: adds are modular, so order is irrelevant -> every element walks to the
+//      root; lanes that share an ancestor are merged with a segmented warp scan and one
+//      atomic add per (warp, node) is issued.
+//   3b. float dtypes: top-down, one level at a time, the batch is kept ordered by
+//      (ancestor at that level, j) -- a stable MSD split -- so every node's updates are one
+//      contiguous, batch-ordered segment; segments are folded in order.
+//
+// Everything is enqueued on one stream; validation failures set the device status word and
+// every later kernel of the batch returns immediately (nothing is written).
+#include <cub/device/device_radix_sort.cuh>
+
+#include "st_common.cuh"
+
+namespace st {
+
+constexpr int64_t UPDATE_MAX_CHUNK = 1 << 20;
+constexpr int SHORT_SEG = 32;  // segments up to this length are folded by their head thread
+
+int64_t update_max_chunk() { return UPDATE_MAX_CHUNK; }
+
+struct seg_entry {
+    int level;
+    int start;
+    int len;
+    uint32_t node;
+};
+
+// status-word layout (unsigned int[64])
+enum { SW_STATUS = 0, SW_QCOUNT = 1, SW_QTAKE = 2, SW_STAT_FAST = 4, SW_STAT_CHAINS = 5, SW_STAT_CHAIN_ELEMS = 6, SW_STAT_LONGEST = 7 };
+
+// -----------------------------------------------------------------------------------------
+// workspace carving
+// -----------------------------------------------------------------------------------------
+struct update_ws {
+    uint32_t *keys_a, *keys_b, *kj;
+    int *j_a, *j_b;
+    void *dj, *ds, *lev_d;  // T-typed
+    seg_entry *queue;
+    void *cub_tmp;
+    size_t cub_bytes;
+    size_t total;
+};
+
+static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static update_ws carve(const st_tree *t, int64_t B, char *base)
+{
+    update_ws w{};
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        char *p = base ? base + off : nullptr;
+        off += align_up(bytes);
+        return (void *)p;
+    };
+    const size_t es = (size_t)t->esize;
+    const bool is_f = (t->dtype == ST_F32 || t->dtype == ST_F64);
+    w.keys_a = (uint32_t *)take(B * 4);
+    w.keys_b = (uint32_t *)take(B * 4);
+    w.kj = (uint32_t *)take(B * 4);
+    w.j_a = (int *)take(B * 4);
+    w.j_b = (int *)take(B * 4);
+    w.dj = take(B * es);
+    w.ds = take(B * es);
+    w.lev_d = is_f ? take((size_t)(t->depth + 1) * B * es) : nullptr;
+    w.queue = is_f ? (seg_entry *)take((size_t)(t->depth + 1) * (B / (SHORT_SEG + 1) + 2) * sizeof(seg_entry)) : nullptr;
+    size_t cb1 = 0, cb2 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, cb1, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+                                    (const int *)nullptr, (int *)nullptr, (int)B, 0, 32, (cudaStream_t)0);
+    if (t->dtype == ST_F64)
+        cub::DeviceRadixSort::SortPairs(nullptr, cb2, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+                                        (const double *)nullptr, (double *)nullptr, (int)B, 0, 32, (cudaStream_t)0);
+    else if (t->dtype == ST_F32)
+        cub::DeviceRadixSort::SortPairs(nullptr, cb2, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+                                        (const float *)nullptr, (float *)nullptr, (int)B, 0, 32, (cudaStream_t)0);
+    w.cub_bytes = cb1 > cb2 ? cb1 : cb2;
+    w.cub_tmp = take(w.cub_bytes);
+    w.total = off;
+    return w;
+}
+
+size_t update_workspace_bytes(const st_tree *t, int64_t batch)
+{
+    if (batch > UPDATE_MAX_CHUNK) batch = UPDATE_MAX_CHUNK;
+    if (batch < 1) batch = 1;
+    return carve(t, batch, nullptr).total;
+}
+
+// -----------------------------------------------------------------------------------------
+// key helpers.  key = heap index of the leaf, shifted left so that its top bit sits at bit
+// `depth`; sorting by key is the tree's left-to-right leaf order (the rotated order of
+// non-power-of-two trees).  Ancestor at level l (root = 0) is key >> (depth - l),
+// valid for l < leaf level.
+// -----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t key_to_heap(uint32_t key, uint64_t two_n) { return key < two_n ? key : key >> 1; }
+__device__ __forceinline__ int key_leaf_level(uint32_t key, uint64_t two_n, int depth) { return key < two_n ? depth : depth - 1; }
+
+// -----------------------------------------------------------------------------------------
+// 0. validation (pyx:37-39 negative scan over ALL vals; Cython boundscheck on idx)
+// -----------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) validate_kernel(const int64_t *__restrict__ idx, int64_t ni,
+                                                       const T *__restrict__ vals, int64_t nv, int64_t n,
+                                                       unsigned int *status)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned int bad = 0;
+    if constexpr (is_signed_t<T>::value)
+        for (int64_t i = tid; i < nv; i += stride)
+            if (vals[i] < T(0)) bad |= STF_NEG_VALS;
+    for (int64_t i = tid; i < ni; i += stride) {
+        const int64_t l = idx[i];
+        if (l < 0 || l >= n) bad |= STF_INDEX;
+    }
+    if (bad) atomicOr(status + SW_STATUS, bad);
+}
+
+__global__ void __launch_bounds__(256) make_keys_kernel(const int64_t *__restrict__ idx, int m, uint32_t n,
+                                                        int depth, uint32_t *__restrict__ keys,
+                                                        uint32_t *__restrict__ kj, int *__restrict__ jj,
+                                                        unsigned int *status)
+{
+    if (status[SW_STATUS]) return;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j == 0) { status[SW_QCOUNT] = 0; status[SW_QTAKE] = 0; }
+    if (j >= m) return;
+    const uint32_t h = (uint32_t)idx[j] + n;
+    const uint32_t key = h << (depth - heap_level(h));
+    keys[j] = key;
+    kj[j] = key;
+    jj[j] = j;
+}
+
+// -----------------------------------------------------------------------------------------
+// 2. leaf pass: sequential chain per leaf (pyx:43-45), emits d in batch order and sorted order
+// -----------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) leaf_pass_kernel(T *__restrict__ H, uint32_t n, const uint32_t *__restrict__ keys,
+                                                        const int *__restrict__ js, int m,
+                                                        const T *__restrict__ vals, uint64_t nv, uint64_t j0,
+                                                        T *__restrict__ dj, T *__restrict__ ds,
+                                                        const unsigned int *status)
+{
+    if (status[SW_STATUS]) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const uint32_t key = keys[i];
+    if (i > 0 && keys[i - 1] == key) return;  // not the head of its run
+    const uint64_t two_n = 2ull * n;
+    const uint32_t h = key_to_heap(key, two_n);
+    T cur = H[h];
+    int e = i;
+    do {
+        const uint32_t j = (uint32_t)js[e];
+        const uint64_t g = j0 + j;  // position in the whole batch (pyx:44: vals[i % nv])
+        const T v = vals[g < nv ? g : g % nv];
+        const T d = t_sub<T>(v, cur);
+        cur = t_add<T>(cur, d);
+        dj[j] = d;
+        ds[e] = d;
+        ++e;
+    } while (e < m && keys[e] == key);
+    H[h] = cur;
+}
+
+// -----------------------------------------------------------------------------------------
+// 3a. integer propagation: segmented warp scan over equal ancestors + one atomic per segment
+// -----------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ void atomic_add_wrap(T *p, T v)
+{
+    if constexpr (sizeof(T) == 4) {
+        atomicAdd(reinterpret_cast<unsigned int *>(p), (unsigned int)v);
+    } else if constexpr (sizeof(T) == 8) {
+        atomicAdd(reinterpret_cast<unsigned long long *>(p), (unsigned long long)v);
+    } else {
+        // 8/16-bit lanes inside an aligned 32-bit word: CAS loop
+        const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+        unsigned int *w = reinterpret_cast<unsigned int *>(a & ~(uintptr_t)3);
+        const unsigned int sh = (unsigned int)(a & 3) * 8;
+        const unsigned int mask = (sizeof(T) == 1 ? 0xffu : 0xffffu) << sh;
+        unsigned int old = *w, assumed;
+        do {
+            assumed = old;
+            const unsigned int field = (assumed & mask) >> sh;
+            const unsigned int nf = ((field + (unsigned int)(typename std::make_unsigned<T>::type)v) << sh) & mask;
+            old = atomicCAS(w, assumed, (assumed & ~mask) | nf);
+        } while (old != assumed);
+    }
+}
+
+template <typename T> __device__ __forceinline__ T shfl_up_t(T v, int off)
+{
+    if constexpr (sizeof(T) == 8) {
+        return (T)__shfl_up_sync(0xffffffffu, (unsigned long long)v, off);
+    } else {
+        return (T)__shfl_up_sync(0xffffffffu, (unsigned int)v, off);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) int_propagate_kernel(T *__restrict__ H, uint32_t n, int depth,
+                                                            const uint32_t *__restrict__ keys,
+                                                            const T *__restrict__ ds, int m,
+                                                            const unsigned int *status)
+{
+    if (status[SW_STATUS]) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // blockDim multiple of 32; whole warps stay
+    const int lane = threadIdx.x & 31;
+    const uint64_t two_n = 2ull * n;
+    const bool live = i < m;
+    const uint32_t key = live ? keys[i] : 0u;
+    const T d = live ? ds[i] : T(0);
+    const int leaf_level = live ? key_leaf_level(key, two_n, depth) : 0;
+    for (int l = depth - 1; l >= 0; --l) {
+        const uint32_t node = (l < leaf_level) ? (key >> (depth - l)) : 0u;  // 0 = no ancestor here
+        T sum = node ? d : T(0);
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const T up = shfl_up_t<T>(sum, off);
+            const uint32_t nup = __shfl_up_sync(0xffffffffu, node, off);
+            if (lane >= off && nup == node) sum = (T)(sum + up);
+        }
+        const uint32_t nnext = __shfl_down_sync(0xffffffffu, node, 1);
+        const bool tail = (lane == 31) || (nnext != node);
+        if (node && tail && sum != T(0)) atomic_add_wrap<T>(H + node, sum);
+    }
+}
+
+// -----------------------------------------------------------------------------------------
+// 3b. float propagation: per-level ordered segment folds
+// -----------------------------------------------------------------------------------------
+// Level l of the pass sees the batch ordered by (key >> (depth-l), j).  The head thread of each
+// segment folds short segments itself and queues long ones for the warp-cooperative kernel.
+template <typename T>
+__global__ void __launch_bounds__(256) fold_level_kernel(T *__restrict__ H, uint32_t n, int depth, int level,
+                                                         const uint32_t *__restrict__ keys,
+                                                         const T *__restrict__ d, int m,
+                                                         seg_entry *__restrict__ queue, unsigned int *status)
+{
+    if (status[SW_STATUS]) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const int sh = depth - level;
+    const uint32_t key = keys[i];
+    const uint32_t node = key >> sh;
+    if (i > 0 && (keys[i - 1] >> sh) == node) return;  // not a segment head
+    if (level >= key_leaf_level(key, 2ull * n, depth)) return;  // `node` is the leaf itself
+    int e = i + 1;
+    while (e < m && e - i <= SHORT_SEG && (keys[e] >> sh) == node) ++e;
+    if (e - i <= SHORT_SEG) {
+        T acc = H[node];
+        for (int x = i; x < e; ++x) acc = t_add<T>(acc, d[x]);
+        H[node] = acc;
+    } else {
+        // upper bound of `node` in the level-sorted keys
+        int lo = e, hi = m;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if ((keys[mid] >> sh) <= node) lo = mid + 1; else hi = mid;
+        }
+        const unsigned int slot = atomicAdd(status + SW_QCOUNT, 1u);
+        queue[slot] = seg_entry{level, i, lo - i, node};
+    }
+}
+
+// Warp-cooperative ordered fold of one long segment: the warp streams the segment with
+// coalesced loads (4 x 32 elements in flight) and every lane replays the same dependent add
+// chain from shuffled values, so the critical path is one FADD per element.
+template <typename T>
+__global__ void __launch_bounds__(128) fold_long_kernel(T *__restrict__ H, const T *__restrict__ lev_d,
+                                                        int64_t level_stride,
+                                                        const seg_entry *__restrict__ queue,
+                                                        unsigned int *status)
+{
+    if (status[SW_STATUS]) return;
+    const int lane = threadIdx.x & 31;
+    const unsigned int total = status[SW_QCOUNT];
+    for (;;) {
+        unsigned int slot = 0;
+        if (lane == 0) slot = atomicAdd(status + SW_QTAKE, 1u);
+        slot = __shfl_sync(0xffffffffu, slot, 0);
+        if (slot >= total) break;
+        const seg_entry s = queue[slot];
+        const T *src = lev_d + (int64_t)s.level * level_stride + s.start;
+        const uint32_t node = s.node;
+        T acc = H[node];
+        int x = 0;
+        constexpr int U = 4;
+        for (; x + 32 * U <= s.len; x += 32 * U) {
+            T v[U];
+#pragma unroll
+            for (int k = 0; k < U; ++k) v[k] = src[x + k * 32 + lane];
+#pragma unroll
+            for (int k = 0; k < U; ++k)
+#pragma unroll
+                for (int l = 0; l < 32; ++l) {
+                    T w;
+                    if constexpr (sizeof(T) == 8) w = __longlong_as_double(__shfl_sync(0xffffffffu, __double_as_longlong(v[k]), l));
+                    else w = __shfl_sync(0xffffffffu, v[k], l);
+                    acc = t_add<T>(acc, w);
+                }
+        }
+        for (; x < s.len; x += 32) {
+            const int rem = s.len - x < 32 ? s.len - x : 32;
+            T v = (lane < rem) ? src[x + lane] : T(0);
+            for (int l = 0; l < rem; ++l) {
+                T w;
+                if constexpr (sizeof(T) == 8) w = __longlong_as_double(__shfl_sync(0xffffffffu, __double_as_longlong(v), l));
+                else w = __shfl_sync(0xffffffffu, v, l);
+                acc = t_add<T>(acc, w);
+            }
+        }
+        if (lane == 0) H[node] = acc;
+    }
+}
+
+// -----------------------------------------------------------------------------------------
+// host driver
+// -----------------------------------------------------------------------------------------
+template <typename T>
+static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *idx, int m, const T *vals,
+                                int64_t nv, int64_t j0, int64_t B, cudaStream_t s)
+{
+    const uint32_t n = (uint32_t)t->n;
+    const int depth = t->depth;
+    T *H = (T *)t->heap;
+    unsigned int *status = t->d_status;
+    const unsigned g = (unsigned)((m + 255) / 256);
+
+    make_keys_kernel<<<g, 256, 0, s>>>(idx, m, n, depth, w.keys_a, w.kj, w.j_a, status);
+    size_t cb = w.cub_bytes;
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(w.cub_tmp, cb, w.keys_a, w.keys_b, w.j_a, w.j_b, m, 0,
+                                                    depth + 1, s);
+    if (e != cudaSuccess) return e;
+    leaf_pass_kernel<T><<<g, 256, 0, s>>>(H, n, w.keys_b, w.j_b, m, vals, (uint64_t)nv, (uint64_t)j0,
+                                          (T *)w.dj, (T *)w.ds, status);
+
+    if constexpr (!is_float_t<T>::value) {
+        int_propagate_kernel<T><<<g, 256, 0, s>>>(H, n, depth, w.keys_b, (const T *)w.ds, m, status);
+        return cudaGetLastError();
+    } else {
+        // Level 0 order = batch order: (kj, dj).  Level l+1 order = stable sort of level l by
+        // the top l+1 key bits.  lev_d[l] keeps every level's ordered d for the long folds.
+        T *lev = (T *)w.lev_d;
+        e = cudaMemcpyAsync(lev, w.dj, (size_t)m * sizeof(T), cudaMemcpyDeviceToDevice, s);
+        if (e != cudaSuccess) return e;
+        uint32_t *kcur = w.kj, *knext = w.keys_a, *kspare = w.keys_b;
+        for (int l = 0; l < depth; ++l) {
+            fold_level_kernel<T><<<g, 256, 0, s>>>(H, n, depth, l, kcur, lev + (int64_t)l * B, m, w.queue, status);
+            if (l + 1 < depth) {
+                cb = w.cub_bytes;
+                e = cub::DeviceRadixSort::SortPairs(w.cub_tmp, cb, kcur, knext, lev + (int64_t)l * B,
+                                                    lev + (int64_t)(l + 1) * B, m, depth - l - 1, depth + 1, s);
+                if (e != cudaSuccess) return e;
+                if (l == 0) { kcur = knext; knext = kspare; }  // never overwrite kj
+                else { uint32_t *tmp = kcur; kcur = knext; knext = tmp; }
+            }
+        }
+        fold_long_kernel<T><<<t->sm_count * 2, 128, 0, s>>>(H, lev, B, w.queue, status);
+        return cudaGetLastError();
+    }
+}
+
+cudaError_t launch_update(st_tree *t, const int64_t *idx, int64_t ni, const void *vals, int64_t nv,
+                          cudaStream_t s)
+{
+    if (ni <= 0 && nv <= 0) return cudaSuccess;
+    if (ni <= 0) {
+        // nothing to apply, but the reference still scans ALL vals for negatives (pyx:37-39)
+        ST_DISPATCH(t->dtype, {
+            validate_kernel<T><<<grid_for(nv, 256, (int64_t)t->sm_count * 8), 256, 0, s>>>(
+                idx, 0, (const T *)vals, nv, t->n, t->d_status);
+        });
+        return cudaGetLastError();
+    }
+    // chunk capacity: the (grow-only) reserved batch size, capped at UPDATE_MAX_CHUNK.  Larger
+    // batches are applied chunk after chunk, which is exact because the reference itself is
+    // sequential in the batch position.
+    int64_t cap = ni > t->reserved_batch ? ni : t->reserved_batch;
+    if (cap > UPDATE_MAX_CHUNK) cap = UPDATE_MAX_CHUNK;
+    const size_t need = carve(t, cap, nullptr).total;
+    if (need > t->ws.bytes) {
+        // never happens once st_reserve() covered the batch size (e.g. before graph capture)
+        cudaError_t e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) return e;
+        if (t->ws.base) cudaFree(t->ws.base);
+        t->ws.base = nullptr;
+        t->ws.bytes = 0;
+        e = cudaMalloc(&t->ws.base, need);
+        if (e != cudaSuccess) return e;
+        t->ws.bytes = need;
+    }
+    t->reserved_batch = cap;
+    ST_DISPATCH(t->dtype, {
+        validate_kernel<T><<<grid_for(ni > nv ? ni : nv, 256, (int64_t)t->sm_count * 8), 256, 0, s>>>(
+            idx, ni, (const T *)vals, nv, t->n, t->d_status);
+        update_ws w = carve(t, cap, (char *)t->ws.base);
+        for (int64_t j0 = 0; j0 < ni; j0 += cap) {
+            const int m = (int)(ni - j0 < cap ? ni - j0 : cap);
+            cudaError_t e = update_chunk<T>(t, w, idx + j0, m, (const T *)vals, nv, j0, cap, s);
+            if (e != cudaSuccess) return e;
+        }
+    });
+    return cudaGetLastError();
+}
+
+}  // namespace st

@@ -1,0 +1,184 @@
+"""``DeviceSumTree``: the batched device entry point for Prioritized-Experience-Replay loops.
+
+Torch tensors in, torch tensors out, everything enqueued on the current CUDA stream, no host
+synchronisation unless asked for.  torch is plumbing only (device memory + streams): the tensors'
+raw pointers go straight into the C ABI of ``libstarr_b200.so``.
+
+It replaces the same reference call sites as ``SumTreeArray`` (``starr/sumtree_array.py:185,
+233, 354, 508`` and ``sample`` ``:417-421``) for callers whose indices / priorities / uniforms
+already live on the GPU.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_TORCH_TO_NP = {
+    torch.int16: np.int16, torch.int32: np.int32, torch.int64: np.int64, torch.uint8: np.uint8,
+    torch.float32: np.float32, torch.float64: np.float64,
+}
+for _n, _np in (("uint16", np.uint16), ("uint32", np.uint32), ("uint64", np.uint64)):
+    if hasattr(torch, _n):
+        _TORCH_TO_NP[getattr(torch, _n)] = _np
+_NP_TO_TORCH = {np.dtype(v): k for k, v in _TORCH_TO_NP.items()}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class DeviceSumTree:
+    """A sum tree over ``n`` leaves resident on one GPU.
+
+    ``heap`` is one tensor of ``2n`` elements: ``heap[:n]`` is the tree in the reference's layout
+    (``[0, root, node 2, ...]``, what ``SumTreeArray.sumtree()`` returns) and ``heap[n:]`` are
+    the leaves.  Both are exposed as zero-copy views (``tree`` / ``leaves``).
+    """
+
+    def __init__(self, n_or_leaves, dtype=None, device=None):
+        if isinstance(n_or_leaves, torch.Tensor):
+            init = n_or_leaves
+            n = init.numel()
+            dtype = dtype or init.dtype
+            device = device if device is not None else (init.device if init.is_cuda else None)
+        else:
+            init, n = None, int(n_or_leaves)
+            dtype = dtype or torch.float32
+        if dtype not in _TORCH_TO_NP:
+            raise TypeError("No matching signature found")
+        if not torch.cuda.is_available():
+            raise RuntimeError("DeviceSumTree needs a CUDA device; starr_b200 has no CPU fallback")
+        self.device = torch.device(device if device is not None else torch.cuda.current_device())
+        if self.device.type != "cuda":
+            raise RuntimeError("DeviceSumTree needs a CUDA device; starr_b200 has no CPU fallback")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.n = n
+        self.dtype = dtype
+        with torch.cuda.device(self.device):
+            self.heap = torch.zeros(2 * n, dtype=dtype, device=self.device)
+            torch.cuda.current_stream().synchronize()
+            self._h = _lib.TreeHandle(n, _TORCH_TO_NP[dtype], self.device.index,
+                                      external_heap=self.heap.data_ptr())
+        if init is not None:
+            self.build_(init)
+
+    # ---- views ------------------------------------------------------------------------------
+    @property
+    def leaves(self) -> torch.Tensor:
+        return self.heap[self.n:]
+
+    @property
+    def tree(self) -> torch.Tensor:
+        return self.heap[:self.n]
+
+    def total(self) -> torch.Tensor:
+        """0-d view of the root (``sumtree[1]``); stays on the device."""
+        return self.heap[1]
+
+    @property
+    def handle(self) -> _lib.TreeHandle:
+        return self._h
+
+    def reserve(self, max_batch: int) -> None:
+        """Pre-allocate the update workspace (call before CUDA-graph capture)."""
+        self._h.reserve(max_batch)
+
+    def _chk(self, t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.device == self.device):
+            raise ValueError(f"{name} must be a CUDA tensor on {self.device}")
+        if t.dtype != dtype:
+            raise TypeError(f"{name} must have dtype {dtype}, got {t.dtype}")
+        return t.contiguous()
+
+    # ---- build ------------------------------------------------------------------------------
+    def build_(self, leaves: torch.Tensor | None = None) -> "DeviceSumTree":
+        """Validate (no negative leaf) and rebuild every node pairwise.  Synchronises once to
+        report the validation result (``ValueError`` like the reference)."""
+        with torch.cuda.device(self.device):
+            if leaves is not None:
+                if leaves.numel() != self.n:
+                    raise TypeError("array and sumtree must have the same size")
+                src = leaves.to(device=self.device, dtype=self.dtype).reshape(-1).contiguous()
+                self._h.build_from_device(src.data_ptr(), _stream())
+            else:
+                self._h.build(_stream())
+        return self
+
+    # ---- update -----------------------------------------------------------------------------
+    def update_(self, idx: torch.Tensor, vals: torch.Tensor, check: bool = False) -> "DeviceSumTree":
+        """``leaves[idx[j]] = vals[j % len(vals)]`` for j in batch order, exact reference
+        semantics (duplicates apply sequentially; float ancestors are ordered folds).
+
+        Asynchronous by default: a batch that fails validation (negative value, index out of
+        range) is skipped as a whole on the device and reported by the next ``poll()``.
+        ``check=True`` waits and raises immediately."""
+        idx = self._chk(idx.reshape(-1), torch.int64, "idx")
+        vals = self._chk(vals.reshape(-1), self.dtype, "vals")
+        with torch.cuda.device(self.device):
+            self._h.update_device(idx.data_ptr(), idx.numel(), vals.data_ptr(), vals.numel(),
+                                  _stream(), sync_check=check)
+        return self
+
+    def poll(self) -> None:
+        """Wait for the current stream and raise the first deferred validation error."""
+        with torch.cuda.device(self.device):
+            self._h.poll_status(_stream(), clear=True)
+
+    # ---- search / sample --------------------------------------------------------------------
+    def search(self, prefix_sums: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        vals = self._chk(prefix_sums.reshape(-1), self.dtype, "prefix_sums")
+        if out is None:
+            out = torch.empty(vals.numel(), dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            self._h.search_device(vals.data_ptr(), vals.numel(), out.data_ptr(), _stream())
+        return out.reshape(prefix_sums.shape)
+
+    def sample_uniform(self, u: torch.Tensor, out: torch.Tensor | None = None,
+                       return_priorities: bool = False):
+        """Indices for injected uniforms ``u`` (float64 in [0, 1)): identical to the reference's
+        ``get_prefix_sum_id((root * u).astype(dtype))`` (``sumtree_array.py:420-421``).  The root
+        is read on the device, so nothing synchronises."""
+        u = self._chk(u.reshape(-1), torch.float64, "u")
+        m = u.numel()
+        if out is None:
+            out = torch.empty(m, dtype=torch.int64, device=self.device)
+        prio = torch.empty(m, dtype=self.dtype, device=self.device) if return_priorities else None
+        with torch.cuda.device(self.device):
+            self._h.sample_uniform_device(u.data_ptr(), m, out.data_ptr(),
+                                          prio.data_ptr() if prio is not None else 0, _stream())
+        return (out, prio) if return_priorities else out
+
+    def sample(self, nsamples: int, generator: torch.Generator | None = None,
+               return_priorities: bool = False):
+        u = torch.rand(nsamples, dtype=torch.float64, device=self.device, generator=generator)
+        return self.sample_uniform(u, return_priorities=return_priorities)
+
+    def gather(self, idx: torch.Tensor) -> torch.Tensor:
+        idx = self._chk(idx.reshape(-1), torch.int64, "idx")
+        out = torch.empty(idx.numel(), dtype=self.dtype, device=self.device)
+        with torch.cuda.device(self.device):
+            self._h.gather_leaves_device(idx.data_ptr(), idx.numel(), out.data_ptr(), _stream())
+        return out
+
+    # ---- sums -------------------------------------------------------------------------------
+    def strided_sum(self, stride: int) -> torch.Tensor:
+        stride = int(stride)
+        nout = self.n // stride + (1 if self.n % stride else 0)
+        out = torch.empty(nout, dtype=self.dtype, device=self.device)
+        with torch.cuda.device(self.device):
+            self._h.strided_sum_device(stride, out.data_ptr(), nout, _stream())
+        return out
+
+    def axis_fold(self, A: int, R: int, C: int) -> torch.Tensor:
+        out_np = _lib.FOLD_DTYPES[self._h.code]
+        out = torch.empty((A, C), dtype=_NP_TO_TORCH[np.dtype(out_np)], device=self.device)
+        with torch.cuda.device(self.device):
+            self._h.axis_fold_device(A, R, C, out.data_ptr(), _stream())
+        return out
+
+    def sum_over(self, index_from: int, index_to: int):
+        torch.cuda.current_stream(self.device).synchronize()
+        return self._h.sum_over(index_from, index_to)

@@ -1,0 +1,262 @@
+"""GPU parity tests of the five kernel entry points (through the C ABI) against the oracle.
+
+Bit-exact for every dtype: tree contents and leaves after build / update batches, sampled
+indices, range and strided sums.  Mirrors reference tests/test_cython_sumtree_array.py and adds
+randomised differential cases (duplicates, cycling vals, non-power-of-two n, fresh zero tree,
+log-uniform magnitudes that exercise float rounding order).
+"""
+import numpy as np
+import pytest
+from cases import KERNEL_BATCHES, KERNEL_SPECS, KERNEL_STRIDES
+from conftest import assert_bits_equal
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sb():
+    import starr_b200
+    return starr_b200
+
+
+def _state(h):
+    leaves = np.empty(h.n, h.dtype)
+    tree = np.empty(h.n, h.dtype)
+    h.store_host(leaves, tree)
+    return leaves, tree
+
+
+# ---- the reference's own kernel tests, run against the CUDA path ------------------------------
+def test_sum_tree_reference_vectors(sb):
+    # reference tests/test_cython_sumtree_array.py:11-79
+    idx = np.array([0, 1, 2, 3, 4], dtype=np.intp)
+    values = np.array([3, 4, 5, 6, 7], dtype=float)
+    base = np.zeros_like(values)
+    tree = np.zeros_like(values)
+    sb.update_sumtree(idx, np.random.randint(1, 10, 5).astype(float), base, tree)
+    sb.update_sumtree(idx, values, base, tree)
+    assert list(base) == list(values)
+    assert tree[0] == 0 and tree[1] == values.sum()
+    assert tree[1] == tree[2] + tree[3] and tree[2] == tree[4] + values[0]
+    assert tree[3] == values[1] + values[2] and tree[4] == values[3] + values[4]
+    q = np.array([0, 5, 6, 12, 13, 15, 16, 19, 20, 24, 25], dtype=float)
+    out = np.zeros_like(q).astype(int)
+    sb.get_prefix_sum_idx(out, q, base, tree)
+    assert list(out) == [3, 3, 4, 4, 0, 0, 1, 1, 2, 2, 2]
+    for i in range(5):
+        for j in range(i, 6):
+            assert sb.sum_over(base, tree, i, j) == values[i:j].sum()
+    assert list(sb.strided_sum(base, tree, 1)) == list(values)
+    assert list(sb.strided_sum(base, tree, 2)) == [7, 11, 7]
+    assert list(sb.strided_sum(base, tree, 3)) == [12, 13]
+    assert list(sb.strided_sum(base, tree, 4)) == [18, 7]
+    assert list(sb.strided_sum(base, tree, 5)) == [25]
+
+
+def test_valid_types(sb):
+    # reference :81-108 (float128 has no GPU representation and is rejected instead)
+    N, K = 100, 10
+    idx = np.random.choice(N, size=K).astype(np.intp)
+    vals = np.random.choice(10, size=K).astype(float)
+    for at in (np.int16, np.int32, np.int64, np.float32, np.float64, np.uint8, np.uint16, np.uint32, np.uint64):
+        base = np.zeros(N).astype(at)
+        tree = np.zeros(N).astype(at)
+        sb.update_sumtree(idx, vals.astype(at), base, tree)
+        assert tree[1] == base.sum()
+        out = np.zeros(K).astype(np.intp)
+        sb.get_prefix_sum_idx(out, np.random.choice(int(vals.sum()), size=K).astype(at), base, tree)
+    with pytest.raises(TypeError):
+        b = np.zeros(N, np.float128)
+        sb.update_sumtree(idx, vals.astype(np.float128), b, b.copy())
+
+
+def test_build_equals_updates(sb):
+    # reference :166-184
+    for n in range(2, 16):
+        vals = np.arange(1, n + 1).astype(float)
+        a1, t1, t2 = np.zeros(n), np.zeros(n), np.zeros(n)
+        sb.update_sumtree(np.arange(n).astype(np.intp), vals, a1, t1)
+        sb.build_sumtree_from_array(vals, t2)
+        assert t1[1] == vals.sum() and t2[1] == vals.sum()
+        assert np.abs(t1 - t2).max() == 0
+
+
+def test_error_contract(sb):
+    # reference :137-164, :186-191 -- and nothing may be written when validation fails
+    base, tree = np.arange(10.0), np.zeros(10)
+    sb.build_sumtree_from_array(base, tree)
+    b0, t0 = base.copy(), tree.copy()
+    with pytest.raises(ValueError, match="vals must be non-negative"):
+        sb.update_sumtree(np.arange(4, dtype=np.intp), -np.arange(4.0), base, tree)
+    with pytest.raises(ValueError, match="vals must be non-negative"):   # unused trailing val still counts
+        sb.update_sumtree(np.arange(2, dtype=np.intp), np.array([1.0, 2.0, -1.0]), base, tree)
+    assert np.array_equal(base, b0) and np.array_equal(tree, t0)
+    with pytest.raises(ValueError, match="array elements must be non-negative"):
+        sb.build_sumtree_from_array(-np.arange(10.0), tree)
+    assert np.array_equal(tree, t0)
+    with pytest.raises(IndexError):
+        sb.update_sumtree(np.array([3, 10], dtype=np.intp), np.ones(2), base, tree)
+    assert np.array_equal(base, b0) and np.array_equal(tree, t0)
+    with pytest.raises(ZeroDivisionError):
+        sb.update_sumtree(np.arange(4, dtype=np.intp), np.zeros(0), base, tree)
+    # a failed call must not poison the next one
+    sb.update_sumtree(np.array([1], dtype=np.intp), np.array([5.0]), base, tree)
+    assert base[1] == 5 and tree[1] == b0.sum() + 4
+
+
+# ---- golden fixtures generated from the unmodified reference ----------------------------------
+@pytest.mark.parametrize("spec", KERNEL_SPECS, ids=[s[0] for s in KERNEL_SPECS])
+def test_golden_fixtures(sb, golden_kernel, spec):
+    from starr_b200 import _lib
+    g = golden_kernel
+    name, dt, n, _ = spec
+    h = _lib.TreeHandle(n, dt)
+    h.build_from_host(g[f"{name}/leaves0"])
+    leaves, tree = _state(h)
+    assert_bits_equal(tree, g[f"{name}/tree0"], "build")
+    for b in range(KERNEL_BATCHES):
+        h.update_host(g[f"{name}/b{b}/idx"], g[f"{name}/b{b}/vals"])
+        leaves, tree = _state(h)
+        assert_bits_equal(leaves, g[f"{name}/b{b}/leaves"], f"leaves after batch {b}")
+        assert_bits_equal(tree, g[f"{name}/b{b}/tree"], f"tree after batch {b}")
+    found = np.zeros(512, np.intp)
+    h.search_host(g[f"{name}/queries"], found)
+    assert np.array_equal(found, g[f"{name}/found"])
+    # sample(): (root * u).astype(dtype) evaluated on the device == NumPy's host arithmetic
+    u = g[f"{name}/u"]
+    q_host = (tree[1] * u).astype(dt)
+    want = np.zeros(512, np.intp)
+    h.search_host(q_host, want)
+    got = np.zeros(512, np.intp)
+    h.sample_uniform_host(u, got)
+    assert np.array_equal(got, want)
+    for s in KERNEL_STRIDES + (n,):
+        assert_bits_equal(h.strided_sum_host(s), g[f"{name}/strided{s}"], f"strided {s}")
+    sums = np.array([h.sum_over(int(a), int(b)) for a, b in g[f"{name}/ranges"]], dtype=dt)
+    assert_bits_equal(sums, g[f"{name}/range_sums"], "sum_over")
+    h.close()
+
+
+# ---- randomised differential tests against the oracle -----------------------------------------
+def _draw(rng, k, dt, kind):
+    if np.issubdtype(dt, np.floating):
+        if kind == "log":
+            return np.exp(rng.uniform(-8, 8, k)).astype(dt)
+        if kind == "mixed":   # zeros, tiny, huge: absorption and binade crossings
+            v = np.exp(rng.uniform(-20, 20, k))
+            v[rng.random(k) < 0.2] = 0
+            return v.astype(dt)
+        return rng.random(k).astype(dt)
+    return rng.integers(0, 1000, k).astype(dt)
+
+
+CASES = [
+    (np.float32, 2, "uni"), (np.float32, 3, "log"), (np.float32, 6, "log"), (np.float32, 37, "log"),
+    (np.float32, 1000, "uni"), (np.float32, 1000, "mixed"), (np.float32, 1024, "log"),
+    (np.float32, 65536, "uni"), (np.float32, 100003, "log"), (np.float32, 1 << 20, "uni"),
+    (np.float64, 5, "log"), (np.float64, 1000, "mixed"), (np.float64, 40000, "uni"),
+    (np.int32, 7, "uni"), (np.int32, 1000, "uni"), (np.int32, 1 << 18, "uni"),
+    (np.int64, 999, "uni"), (np.int16, 300, "uni"), (np.uint8, 77, "uni"), (np.uint16, 513, "uni"),
+    (np.uint32, 4097, "uni"), (np.uint64, 1025, "uni"),
+]
+
+
+@pytest.mark.parametrize("dt,n,kind", CASES, ids=[f"{np.dtype(c[0]).name}-{c[1]}-{c[2]}" for c in CASES])
+def test_differential_vs_oracle(oracle_mod, dt, n, kind):
+    from starr_b200 import _lib
+    C = oracle_mod.c
+    rng = np.random.default_rng(n * 31 + np.dtype(dt).itemsize)
+    leaves = _draw(rng, n, dt, kind)
+    tree = np.zeros(n, dt)
+    C.build_sumtree_from_array(leaves, tree)
+    h = _lib.TreeHandle(n, dt)
+    h.build_from_host(leaves)
+    gl, gt = _state(h)
+    assert_bits_equal(gt, tree, "build")
+    batch_sizes = [1, 2, 33, min(4096, 4 * n), min(1 << 17, 8 * n)]
+    for bi, m in enumerate(batch_sizes):
+        nv = m if bi % 2 == 0 else int(rng.integers(1, m + 1))
+        if bi == 3:     # skewed: many duplicates
+            idx = rng.integers(0, max(1, n // 8), m).astype(np.intp)
+        elif bi == 4 and n > 64:   # a contiguous run plus random
+            idx = np.concatenate([np.arange(m // 2) % n, rng.integers(0, n, m - m // 2)]).astype(np.intp)
+        else:
+            idx = rng.integers(0, n, m).astype(np.intp)
+        vals = _draw(rng, nv, dt, kind)
+        C.update_sumtree(idx, vals, leaves, tree)
+        h.update_host(idx, vals)
+        gl, gt = _state(h)
+        assert_bits_equal(gl, leaves, f"leaves after batch {bi} (m={m}, nv={nv})")
+        assert_bits_equal(gt, tree, f"tree after batch {bi} (m={m}, nv={nv})")
+    m = 5000
+    q = (rng.random(m) * float(tree[1]) * 1.05).astype(dt)
+    want = np.zeros(m, np.intp)
+    C.get_prefix_sum_idx(want, q, leaves, tree)
+    got = np.zeros(m, np.intp)
+    h.search_host(q, got)
+    assert np.array_equal(got, want)
+    for s in (1, 2, 3, 5, 8, 100, 4096, n):
+        assert_bits_equal(h.strided_sum_host(s), C.strided_sum(leaves, tree, s), f"strided {s}")
+    h.close()
+
+
+def test_update_from_fresh_zero_tree(oracle_mod):
+    """PER start-up: all-zero tree filled by updates (every node starts at 0: no float shortcut
+    applies, everything goes through the ordered folds)."""
+    from starr_b200 import _lib
+    C = oracle_mod.c
+    for dt in (np.float32, np.float64):
+        n = 50000
+        rng = np.random.default_rng(9)
+        leaves, tree = np.zeros(n, dt), np.zeros(n, dt)
+        h = _lib.TreeHandle(n, dt)
+        for m in (100, 20000, 100000):
+            idx = rng.integers(0, n, m).astype(np.intp)
+            vals = np.exp(rng.uniform(-6, 6, m)).astype(dt)
+            C.update_sumtree(idx, vals, leaves, tree)
+            h.update_host(idx, vals)
+            gl, gt = _state(h)
+            assert_bits_equal(gl, leaves, "leaves")
+            assert_bits_equal(gt, tree, "tree")
+        h.close()
+
+
+def test_batch_order_matters_and_is_respected(oracle_mod):
+    """Same multiset of updates, different order -> different float tree; we must follow each."""
+    from starr_b200 import _lib
+    C = oracle_mod.c
+    n, m = 1 << 14, 8192
+    rng = np.random.default_rng(4)
+    base = rng.random(n).astype(np.float32)
+    idx = rng.integers(0, n, m).astype(np.intp)
+    vals = np.exp(rng.uniform(-8, 8, m)).astype(np.float32)
+    trees = []
+    for perm in (np.arange(m), rng.permutation(m)):
+        leaves, tree = base.copy(), np.zeros(n, np.float32)
+        C.build_sumtree_from_array(leaves, tree)
+        C.update_sumtree(idx[perm], vals[perm], leaves, tree)
+        h = _lib.TreeHandle(n, np.float32)
+        h.build_from_host(base)
+        h.update_host(idx[perm], vals[perm])
+        gl, gt = _state(h)
+        assert_bits_equal(gt, tree, "tree")
+        trees.append(tree)
+        h.close()
+    assert (trees[0].view(np.uint32) != trees[1].view(np.uint32)).any()
+
+
+def test_axis_fold_matches_numpy(oracle_mod):
+    from starr_b200 import _lib
+    rng = np.random.default_rng(8)
+    for dt in (np.float32, np.float64, np.int32, np.uint8, np.int64):
+        for shape, lo, hi in (((64, 48), 0, 0), ((5, 40, 7), 1, 1), ((3, 4, 5, 6), 0, 1), ((300, 257), 0, 0)):
+            x = _draw(rng, int(np.prod(shape)), dt, "log").reshape(shape)
+            if np.dtype(dt).itemsize == 1:
+                x = (x % 5).astype(dt)
+            A = int(np.prod(shape[:lo])); R = int(np.prod(shape[lo:hi + 1])); Cc = int(np.prod(shape[hi + 1:]))
+            h = _lib.TreeHandle(x.size, dt)
+            h.build_from_host(x.ravel())
+            got = h.axis_fold_host(A, R, Cc)
+            want = x.sum(axis=tuple(range(lo, hi + 1)))
+            assert_bits_equal(got.reshape(want.shape), want, f"{np.dtype(dt).name} {shape}")
+            h.close()
