@@ -74,6 +74,8 @@ ST_API int st_abi_version(void);
 ST_API const char *st_status_string(int status);
 ST_API const char *st_last_error(void); /* detail of the last failure on this thread */
 ST_API int st_dtype_size(int dtype);     /* bytes, or -1 */
+/* number of kernels of this library launched by this process so far (profiling aid) */
+ST_API unsigned long long st_kernel_launches(void);
 
 /* ---- lifetime -------------------------------------------------------------------- */
 /* Create a tree of n >= 2 zero leaves on CUDA device `device`.  If external_heap is not

@@ -63,6 +63,7 @@ _SIGNATURES = {
     "st_status_string": (c_char_p, [c_int]),
     "st_last_error": (c_char_p, []),
     "st_dtype_size": (c_int, [c_int]),
+    "st_kernel_launches": (ctypes.c_ulonglong, []),
     "st_create": (c_int, [c_int64, c_int, c_int, c_void_p, POINTER(c_void_p)]),
     "st_destroy": (c_int, [c_void_p]),
     "st_size": (c_int64, [c_void_p]),

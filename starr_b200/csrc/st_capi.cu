@@ -77,9 +77,13 @@ struct dev_buf {
 
 }  // namespace
 
+namespace st { unsigned long long g_kernel_launches = 0; }
+
 extern "C" {
 
 int st_abi_version(void) { return 1; }
+
+unsigned long long st_kernel_launches(void) { return st::g_kernel_launches; }
 
 const char *st_status_string(int status)
 {

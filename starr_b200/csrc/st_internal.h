@@ -35,6 +35,9 @@ struct st_tree {
 // launchers implemented in the .cu files; every one only enqueues on `s`
 namespace st {
 
+// process-wide count of kernels of THIS library that were launched (bench.py's gpu_launches)
+extern unsigned long long g_kernel_launches;
+
 cudaError_t launch_check_leaves(st_tree *t, cudaStream_t s);  // sets STF_NEG_ARRAY
 cudaError_t launch_build(st_tree *t, cudaStream_t s);         // skipped on device if status != 0
 cudaError_t launch_search(const st_tree *t, const void *vals, int64_t m, int64_t *out, cudaStream_t s);

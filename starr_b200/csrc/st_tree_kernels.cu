@@ -43,6 +43,7 @@ cudaError_t launch_check_leaves(st_tree *t, cudaStream_t s)
     ST_DISPATCH(t->dtype, {
         const T *leaves = (const T *)t->heap + t->n;
         unsigned g = grid_for(t->n, 256 * 8, (int64_t)t->sm_count * 8);
+        ++g_kernel_launches;
         check_leaves_kernel<T><<<g, 256, 0, s>>>(leaves, t->n, t->d_status);
     });
     return cudaGetLastError();
@@ -120,9 +121,11 @@ cudaError_t launch_build(st_tree *t, cudaStream_t s)
             int k = top - root_level;
             uint64_t first = 1ull << root_level;
             uint64_t last = first * 2 < n ? first * 2 : n;  // roots r >= n have nothing to compute
-            if (last > first)
+            if (last > first) {
+                ++g_kernel_launches;
                 build_pass_kernel<T><<<(unsigned)(last - first), BUILD_THREADS, 0, s>>>(
                     H, n, root_level, k, t->d_status);
+            }
             top = root_level;
         }
     });
@@ -284,9 +287,11 @@ static cudaError_t launch_search_t(const st_tree *t, const void *in, int64_t m, 
             attr_done = true;
         }
         unsigned g = grid_for(m, (int)per_block, (int64_t)t->sm_count * 3);
+        ++g_kernel_launches;
         kern<<<g, SEARCH_THREADS, smem, s>>>(H, n, t->depth, in, m, out, (T *)prio, stage_nodes);
     } else {
         unsigned g = grid_for(m, (int)per_block, (int64_t)t->sm_count * 4);
+        ++g_kernel_launches;
         search_kernel<T, false, UNIFORM><<<g, SEARCH_THREADS, 0, s>>>(H, n, t->depth, in, m, out, (T *)prio, 0);
     }
     return cudaGetLastError();
@@ -323,6 +328,7 @@ cudaError_t launch_gather(const st_tree *t, const int64_t *idx, int64_t m, void 
 {
     if (m <= 0) return cudaSuccess;
     ST_DISPATCH(t->dtype, {
+        ++g_kernel_launches;
         gather_kernel<T><<<grid_for(m, 256, (int64_t)t->sm_count * 8), 256, 0, s>>>(
             (const T *)t->heap + t->n, t->n, idx, m, (T *)out);
     });
@@ -375,6 +381,7 @@ __global__ void sum_over_kernel(const T *__restrict__ H, int64_t n, int64_t a, i
 
 cudaError_t launch_sum_over(const st_tree *t, int64_t a, int64_t b, void *out_dev, cudaStream_t s)
 {
+    ++g_kernel_launches;
     ST_DISPATCH(t->dtype, { sum_over_kernel<T><<<1, 32, 0, s>>>((const T *)t->heap, t->n, a, b, (T *)out_dev); });
     return cudaGetLastError();
 }
@@ -383,6 +390,7 @@ cudaError_t launch_strided_sum(const st_tree *t, int64_t stride, void *out, int6
 {
     if (nout <= 0) return cudaSuccess;
     ST_DISPATCH(t->dtype, {
+        ++g_kernel_launches;
         strided_sum_kernel<T><<<grid_for(nout, 256, (int64_t)t->sm_count * 8), 256, 0, s>>>(
             (const T *)t->heap, t->n, stride, (T *)out, nout);
     });
@@ -422,6 +430,7 @@ cudaError_t launch_axis_fold(const st_tree *t, int64_t A, int64_t R, int64_t C, 
     if (A * C <= 0) return cudaSuccess;
     ST_DISPATCH(t->dtype, {
         using ACC = typename fold_acc<T>::type;
+        ++g_kernel_launches;
         axis_fold_kernel<T><<<grid_for(A * C, 128, (int64_t)t->sm_count * 16), 128, 0, s>>>(
             (const T *)t->heap + t->n, A, R, C, (ACC *)out);
     });

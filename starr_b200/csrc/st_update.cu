@@ -343,15 +343,18 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
     unsigned int *status = t->d_status;
     const unsigned g = (unsigned)((m + 255) / 256);
 
+    ++g_kernel_launches;
     make_keys_kernel<<<g, 256, 0, s>>>(idx, m, n, depth, w.keys_a, w.kj, w.j_a, status);
     size_t cb = w.cub_bytes;
     cudaError_t e = cub::DeviceRadixSort::SortPairs(w.cub_tmp, cb, w.keys_a, w.keys_b, w.j_a, w.j_b, m, 0,
                                                     depth + 1, s);
     if (e != cudaSuccess) return e;
+    ++g_kernel_launches;
     leaf_pass_kernel<T><<<g, 256, 0, s>>>(H, n, w.keys_b, w.j_b, m, vals, (uint64_t)nv, (uint64_t)j0,
                                           (T *)w.dj, (T *)w.ds, status);
 
     if constexpr (!is_float_t<T>::value) {
+        ++g_kernel_launches;
         int_propagate_kernel<T><<<g, 256, 0, s>>>(H, n, depth, w.keys_b, (const T *)w.ds, m, status);
         return cudaGetLastError();
     } else {
@@ -362,6 +365,7 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
         if (e != cudaSuccess) return e;
         uint32_t *kcur = w.kj, *knext = w.keys_a, *kspare = w.keys_b;
         for (int l = 0; l < depth; ++l) {
+            ++g_kernel_launches;
             fold_level_kernel<T><<<g, 256, 0, s>>>(H, n, depth, l, kcur, lev + (int64_t)l * B, m, w.queue, status);
             if (l + 1 < depth) {
                 cb = w.cub_bytes;
@@ -372,6 +376,7 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
                 else { uint32_t *tmp = kcur; kcur = knext; knext = tmp; }
             }
         }
+        ++g_kernel_launches;
         fold_long_kernel<T><<<t->sm_count * 2, 128, 0, s>>>(H, lev, B, w.queue, status);
         return cudaGetLastError();
     }
@@ -384,6 +389,7 @@ cudaError_t launch_update(st_tree *t, const int64_t *idx, int64_t ni, const void
     if (ni <= 0) {
         // nothing to apply, but the reference still scans ALL vals for negatives (pyx:37-39)
         ST_DISPATCH(t->dtype, {
+            ++g_kernel_launches;
             validate_kernel<T><<<grid_for(nv, 256, (int64_t)t->sm_count * 8), 256, 0, s>>>(
                 idx, 0, (const T *)vals, nv, t->n, t->d_status);
         });
@@ -408,6 +414,7 @@ cudaError_t launch_update(st_tree *t, const int64_t *idx, int64_t ni, const void
     }
     t->reserved_batch = cap;
     ST_DISPATCH(t->dtype, {
+        ++g_kernel_launches;
         validate_kernel<T><<<grid_for(ni > nv ? ni : nv, 256, (int64_t)t->sm_count * 8), 256, 0, s>>>(
             idx, ni, (const T *)vals, nv, t->n, t->d_status);
         update_ws w = carve(t, cap, (char *)t->ws.base);
