@@ -116,6 +116,22 @@ ST_API int st_update_device(st_tree *t, const int64_t *idx_dev, int64_t ni, cons
 ST_API int st_update_host(st_tree *t, const int64_t *idx_host, int64_t ni, const void *vals_host,
                    int64_t nv);
 
+/* ---- building blocks of the subtree-sharded tree (no reference counterpart: the reference is
+ * single-process; these keep the sharded result bit-identical to ONE reference tree) -------- */
+/* st_update_device that also returns every update's applied difference d_j (batch order,
+ * tree dtype) -- the quantity the reference adds to each ancestor (pyx:43-48). */
+ST_API int st_update_deltas_device(st_tree *t, const int64_t *idx_dev, int64_t ni, const void *vals_dev,
+                            int64_t nv, void *delta_out_dev, void *stream);
+/* For j in batch order: every PROPER ancestor of leaf idx[j] += deltas[j] (ordered fold for
+ * floats); leaves are not touched.  Used on the replicated top tree whose leaves are the
+ * shard roots. */
+ST_API int st_apply_deltas_device(st_tree *t, const int64_t *idx_dev, int64_t ni, const void *deltas_dev,
+                           void *stream);
+/* sample() descent that also returns the prefix left over at the leaf that was reached:
+ * on the top tree this is (owning shard, query to continue with inside that shard). */
+ST_API int st_route_uniform_device(const st_tree *t, const double *u_dev, int64_t m, int64_t *leaf_out_dev,
+                            void *residual_out_dev, void *stream);
+
 /* ---- prefix-sum search: replaces get_prefix_sum_idx, _sumtree_array.pyx:66-122 --- */
 ST_API int st_search_device(const st_tree *t, const void *vals_dev, int64_t m, int64_t *out_dev,
                      void *stream);

@@ -80,6 +80,9 @@ _SIGNATURES = {
     "st_build_from_device": (c_int, [c_void_p, c_void_p, c_void_p]),
     "st_update_device": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int]),
     "st_update_host": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64]),
+    "st_update_deltas_device": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
+    "st_apply_deltas_device": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "st_route_uniform_device": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "st_search_device": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "st_search_host": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "st_sample_uniform_device": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
@@ -237,6 +240,20 @@ class TreeHandle:
                       sync_check: bool = False) -> None:
         check(lib().st_update_device(self.ptr, c_void_p(idx_ptr), int(ni), c_void_p(vals_ptr), int(nv),
                                      c_void_p(stream), ST_UPDATE_SYNC_CHECK if sync_check else 0))
+
+    def update_deltas_device(self, idx_ptr: int, ni: int, vals_ptr: int, nv: int, delta_out_ptr: int,
+                             stream: int = 0) -> None:
+        check(lib().st_update_deltas_device(self.ptr, c_void_p(idx_ptr), int(ni), c_void_p(vals_ptr), int(nv),
+                                            c_void_p(delta_out_ptr), c_void_p(stream)))
+
+    def apply_deltas_device(self, idx_ptr: int, ni: int, deltas_ptr: int, stream: int = 0) -> None:
+        check(lib().st_apply_deltas_device(self.ptr, c_void_p(idx_ptr), int(ni), c_void_p(deltas_ptr),
+                                           c_void_p(stream)))
+
+    def route_uniform_device(self, u_ptr: int, m: int, leaf_out_ptr: int, resid_out_ptr: int,
+                             stream: int = 0) -> None:
+        check(lib().st_route_uniform_device(self.ptr, c_void_p(u_ptr), int(m), c_void_p(leaf_out_ptr),
+                                            c_void_p(resid_out_ptr), c_void_p(stream)))
 
     def search_device(self, vals_ptr: int, m: int, out_ptr: int, stream: int = 0) -> None:
         check(lib().st_search_device(self.ptr, c_void_p(vals_ptr), int(m), c_void_p(out_ptr), c_void_p(stream)))

@@ -275,7 +275,7 @@ int st_update_device(st_tree *t, const int64_t *idx_dev, int64_t ni, const void 
     device_guard g(t->device);
     cudaStream_t s = (cudaStream_t)stream;
     if (ni == 0 && nv == 0) return ST_OK;
-    CU(st::launch_update(t, idx_dev, ni, vals_dev, nv, s));
+    CU(st::launch_update(t, idx_dev, ni, vals_dev, nv, nullptr, nullptr, s));
     if (flags & ST_UPDATE_SYNC_CHECK) {
         const int st = fetch_status(t, s, true);
         if (st != ST_OK) return fail(st, "%s", st_status_string(st));
@@ -295,6 +295,36 @@ int st_update_host(st_tree *t, const int64_t *idx_host, int64_t ni, const void *
     CU(cudaMemcpy(di.p, idx_host, ni * sizeof(int64_t), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(dv.p, vals_host, nv * t->esize, cudaMemcpyHostToDevice));
     return st_update_device(t, (const int64_t *)di.p, ni, dv.p, nv, nullptr, ST_UPDATE_SYNC_CHECK);
+}
+
+// ---- sharded-tree helpers ------------------------------------------------------
+int st_update_deltas_device(st_tree *t, const int64_t *idx_dev, int64_t ni, const void *vals_dev, int64_t nv,
+                            void *delta_out_dev, void *stream)
+{
+    if (!t || ni < 0 || nv < 0) return fail(ST_ERR_ARG, "st_update_deltas_device: bad argument");
+    if (ni > 0 && nv == 0) return fail(ST_ERR_EMPTY_VALS, "%s", st_status_string(ST_ERR_EMPTY_VALS));
+    if (ni == 0 && nv == 0) return ST_OK;
+    device_guard g(t->device);
+    CU(st::launch_update(t, idx_dev, ni, vals_dev, nv, delta_out_dev, nullptr, (cudaStream_t)stream));
+    return ST_OK;
+}
+
+int st_apply_deltas_device(st_tree *t, const int64_t *idx_dev, int64_t ni, const void *deltas_dev, void *stream)
+{
+    if (!t || ni < 0 || (ni > 0 && !deltas_dev)) return fail(ST_ERR_ARG, "st_apply_deltas_device: bad argument");
+    if (ni == 0) return ST_OK;
+    device_guard g(t->device);
+    CU(st::launch_update(t, idx_dev, ni, nullptr, 0, nullptr, deltas_dev, (cudaStream_t)stream));
+    return ST_OK;
+}
+
+int st_route_uniform_device(const st_tree *t, const double *u_dev, int64_t m, int64_t *leaf_out_dev,
+                            void *residual_out_dev, void *stream)
+{
+    if (!t || m < 0) return fail(ST_ERR_ARG, "st_route_uniform_device: bad argument");
+    device_guard g(t->device);
+    CU(st::launch_sample(t, u_dev, m, leaf_out_dev, nullptr, residual_out_dev, (cudaStream_t)stream));
+    return ST_OK;
 }
 
 // ---- search / sample -----------------------------------------------------------------------
@@ -325,7 +355,7 @@ int st_sample_uniform_device(const st_tree *t, const double *u_dev, int64_t m, i
 {
     if (!t || m < 0) return fail(ST_ERR_ARG, "st_sample_uniform_device: bad argument");
     device_guard g(t->device);
-    CU(st::launch_sample(t, u_dev, m, out_dev, prio_out_dev, (cudaStream_t)stream));
+    CU(st::launch_sample(t, u_dev, m, out_dev, prio_out_dev, nullptr, (cudaStream_t)stream));
     return ST_OK;
 }
 
@@ -338,7 +368,7 @@ int st_sample_uniform_host(const st_tree *t, const double *u_host, int64_t m, in
     CU(du.alloc(m * sizeof(double)));
     CU(dout.alloc(m * sizeof(int64_t)));
     CU(cudaMemcpy(du.p, u_host, m * sizeof(double), cudaMemcpyHostToDevice));
-    CU(st::launch_sample(t, (const double *)du.p, m, (int64_t *)dout.p, nullptr, 0));
+    CU(st::launch_sample(t, (const double *)du.p, m, (int64_t *)dout.p, nullptr, nullptr, 0));
     CU(cudaMemcpy(out_host, dout.p, m * sizeof(int64_t), cudaMemcpyDeviceToHost));
     return ST_OK;
 }

@@ -42,15 +42,17 @@ cudaError_t launch_check_leaves(st_tree *t, cudaStream_t s);  // sets STF_NEG_AR
 cudaError_t launch_build(st_tree *t, cudaStream_t s);         // skipped on device if status != 0
 cudaError_t launch_search(const st_tree *t, const void *vals, int64_t m, int64_t *out, cudaStream_t s);
 cudaError_t launch_sample(const st_tree *t, const double *u, int64_t m, int64_t *out, void *prio,
-                          cudaStream_t s);
+                          void *resid, cudaStream_t s);
 cudaError_t launch_gather(const st_tree *t, const int64_t *idx, int64_t m, void *out, cudaStream_t s);
 cudaError_t launch_sum_over(const st_tree *t, int64_t a, int64_t b, void *out_dev, cudaStream_t s);
 cudaError_t launch_strided_sum(const st_tree *t, int64_t stride, void *out, int64_t nout, cudaStream_t s);
 cudaError_t launch_axis_fold(const st_tree *t, int64_t A, int64_t R, int64_t C, void *out, cudaStream_t s);
 
 size_t update_workspace_bytes(const st_tree *t, int64_t batch);
+// delta_out (nullable): receives d_j in batch order.  deltas_in (nullable): apply the given
+// per-update differences to the proper ancestors only (vals ignored, leaves untouched).
 cudaError_t launch_update(st_tree *t, const int64_t *idx, int64_t ni, const void *vals, int64_t nv,
-                          cudaStream_t s);
+                          void *delta_out, const void *deltas_in, cudaStream_t s);
 int64_t update_max_chunk();
 
 }  // namespace st

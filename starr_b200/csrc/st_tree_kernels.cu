@@ -199,7 +199,8 @@ template <typename T> __device__ __forceinline__ T scale_uniform(T root, double 
 template <typename T, bool STAGE, bool UNIFORM>
 __global__ void __launch_bounds__(SEARCH_THREADS)
 search_kernel(const T *__restrict__ H, uint32_t n, int depth, const void *__restrict__ in,
-              int64_t m, int64_t *__restrict__ out, T *__restrict__ prio, uint32_t stage_nodes)
+              int64_t m, int64_t *__restrict__ out, T *__restrict__ prio, T *__restrict__ resid,
+              uint32_t stage_nodes)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     T *top = reinterpret_cast<T *>(smem_raw);
@@ -255,6 +256,7 @@ search_kernel(const T *__restrict__ H, uint32_t n, int depth, const void *__rest
             if (i < m) {
                 out[i] = (int64_t)h[q] - (int64_t)n;
                 if (prio) prio[i] = __ldg(H + h[q]);
+                if (resid) resid[i] = p[q];   // prefix left over inside the found leaf's subtree
             }
         }
     }
@@ -262,7 +264,7 @@ search_kernel(const T *__restrict__ H, uint32_t n, int depth, const void *__rest
 
 template <typename T, bool UNIFORM>
 static cudaError_t launch_search_t(const st_tree *t, const void *in, int64_t m, int64_t *out, void *prio,
-                                   cudaStream_t s)
+                                   void *resid, cudaStream_t s)
 {
     if (m <= 0) return cudaSuccess;
     const uint32_t n = (uint32_t)t->n;
@@ -288,25 +290,26 @@ static cudaError_t launch_search_t(const st_tree *t, const void *in, int64_t m, 
         }
         unsigned g = grid_for(m, (int)per_block, (int64_t)t->sm_count * 3);
         ++g_kernel_launches;
-        kern<<<g, SEARCH_THREADS, smem, s>>>(H, n, t->depth, in, m, out, (T *)prio, stage_nodes);
+        kern<<<g, SEARCH_THREADS, smem, s>>>(H, n, t->depth, in, m, out, (T *)prio, (T *)resid, stage_nodes);
     } else {
         unsigned g = grid_for(m, (int)per_block, (int64_t)t->sm_count * 4);
         ++g_kernel_launches;
-        search_kernel<T, false, UNIFORM><<<g, SEARCH_THREADS, 0, s>>>(H, n, t->depth, in, m, out, (T *)prio, 0);
+        search_kernel<T, false, UNIFORM><<<g, SEARCH_THREADS, 0, s>>>(H, n, t->depth, in, m, out, (T *)prio,
+                                                                      (T *)resid, 0);
     }
     return cudaGetLastError();
 }
 
 cudaError_t launch_search(const st_tree *t, const void *vals, int64_t m, int64_t *out, cudaStream_t s)
 {
-    ST_DISPATCH(t->dtype, return (launch_search_t<T, false>(t, vals, m, out, nullptr, s)));
+    ST_DISPATCH(t->dtype, return (launch_search_t<T, false>(t, vals, m, out, nullptr, nullptr, s)));
     return cudaSuccess;
 }
 
 cudaError_t launch_sample(const st_tree *t, const double *u, int64_t m, int64_t *out, void *prio,
-                          cudaStream_t s)
+                          void *resid, cudaStream_t s)
 {
-    ST_DISPATCH(t->dtype, return (launch_search_t<T, true>(t, u, m, out, prio, s)));
+    ST_DISPATCH(t->dtype, return (launch_search_t<T, true>(t, u, m, out, prio, resid, s)));
     return cudaSuccess;
 }
 

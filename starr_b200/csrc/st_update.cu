@@ -335,8 +335,11 @@ __global__ void __launch_bounds__(128) fold_long_kernel(T *__restrict__ H, const
 // -----------------------------------------------------------------------------------------
 template <typename T>
 static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *idx, int m, const T *vals,
-                                int64_t nv, int64_t j0, int64_t B, cudaStream_t s)
+                                int64_t nv, int64_t j0, int64_t B, T *delta_out, const T *deltas_in,
+                                cudaStream_t s)
 {
+    // deltas_in != nullptr: "apply deltas" mode (sharded top tree): the per-update
+    // differences are given, the leaves are not touched, only proper ancestors are folded.
     const uint32_t n = (uint32_t)t->n;
     const int depth = t->depth;
     T *H = (T *)t->heap;
@@ -346,22 +349,33 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
     ++g_kernel_launches;
     make_keys_kernel<<<g, 256, 0, s>>>(idx, m, n, depth, w.keys_a, w.kj, w.j_a, status);
     size_t cb = w.cub_bytes;
-    cudaError_t e = cub::DeviceRadixSort::SortPairs(w.cub_tmp, cb, w.keys_a, w.keys_b, w.j_a, w.j_b, m, 0,
-                                                    depth + 1, s);
-    if (e != cudaSuccess) return e;
-    ++g_kernel_launches;
-    leaf_pass_kernel<T><<<g, 256, 0, s>>>(H, n, w.keys_b, w.j_b, m, vals, (uint64_t)nv, (uint64_t)j0,
-                                          (T *)w.dj, (T *)w.ds, status);
+    cudaError_t e = cudaSuccess;
+    const T *d_batch = deltas_in;           // d in batch order
+    if (!deltas_in) {
+        e = cub::DeviceRadixSort::SortPairs(w.cub_tmp, cb, w.keys_a, w.keys_b, w.j_a, w.j_b, m, 0, depth + 1, s);
+        if (e != cudaSuccess) return e;
+        ++g_kernel_launches;
+        leaf_pass_kernel<T><<<g, 256, 0, s>>>(H, n, w.keys_b, w.j_b, m, vals, (uint64_t)nv, (uint64_t)j0,
+                                              (T *)w.dj, (T *)w.ds, status);
+        d_batch = (const T *)w.dj;
+        if (delta_out) {
+            e = cudaMemcpyAsync(delta_out, w.dj, (size_t)m * sizeof(T), cudaMemcpyDeviceToDevice, s);
+            if (e != cudaSuccess) return e;
+        }
+    }
 
     if constexpr (!is_float_t<T>::value) {
         ++g_kernel_launches;
-        int_propagate_kernel<T><<<g, 256, 0, s>>>(H, n, depth, w.keys_b, (const T *)w.ds, m, status);
+        if (deltas_in)   // unsorted keys: adjacent equal ancestors still merge, the rest use separate atomics
+            int_propagate_kernel<T><<<g, 256, 0, s>>>(H, n, depth, w.kj, deltas_in, m, status);
+        else
+            int_propagate_kernel<T><<<g, 256, 0, s>>>(H, n, depth, w.keys_b, (const T *)w.ds, m, status);
         return cudaGetLastError();
     } else {
         // Level 0 order = batch order: (kj, dj).  Level l+1 order = stable sort of level l by
         // the top l+1 key bits.  lev_d[l] keeps every level's ordered d for the long folds.
         T *lev = (T *)w.lev_d;
-        e = cudaMemcpyAsync(lev, w.dj, (size_t)m * sizeof(T), cudaMemcpyDeviceToDevice, s);
+        e = cudaMemcpyAsync(lev, d_batch, (size_t)m * sizeof(T), cudaMemcpyDeviceToDevice, s);
         if (e != cudaSuccess) return e;
         uint32_t *kcur = w.kj, *knext = w.keys_a, *kspare = w.keys_b;
         for (int l = 0; l < depth; ++l) {
@@ -383,7 +397,7 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
 }
 
 cudaError_t launch_update(st_tree *t, const int64_t *idx, int64_t ni, const void *vals, int64_t nv,
-                          cudaStream_t s)
+                          void *delta_out, const void *deltas_in, cudaStream_t s)
 {
     if (ni <= 0 && nv <= 0) return cudaSuccess;
     if (ni <= 0) {
@@ -416,11 +430,13 @@ cudaError_t launch_update(st_tree *t, const int64_t *idx, int64_t ni, const void
     ST_DISPATCH(t->dtype, {
         ++g_kernel_launches;
         validate_kernel<T><<<grid_for(ni > nv ? ni : nv, 256, (int64_t)t->sm_count * 8), 256, 0, s>>>(
-            idx, ni, (const T *)vals, nv, t->n, t->d_status);
+            idx, ni, (const T *)vals, deltas_in ? 0 : nv, t->n, t->d_status);
         update_ws w = carve(t, cap, (char *)t->ws.base);
         for (int64_t j0 = 0; j0 < ni; j0 += cap) {
             const int m = (int)(ni - j0 < cap ? ni - j0 : cap);
-            cudaError_t e = update_chunk<T>(t, w, idx + j0, m, (const T *)vals, nv, j0, cap, s);
+            cudaError_t e = update_chunk<T>(t, w, idx + j0, m, (const T *)vals, nv, j0, cap,
+                                            delta_out ? (T *)delta_out + j0 : nullptr,
+                                            deltas_in ? (const T *)deltas_in + j0 : nullptr, s);
             if (e != cudaSuccess) return e;
         }
     });

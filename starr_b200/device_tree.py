@@ -122,6 +122,38 @@ class DeviceSumTree:
                                   _stream(), sync_check=check)
         return self
 
+    # ---- building blocks of the sharded tree (starr_b200/sharded.py) ----------------------------
+    def update_with_deltas_(self, idx: torch.Tensor, vals: torch.Tensor) -> torch.Tensor:
+        """``update_`` that also returns every update's applied difference d_j (batch order)."""
+        idx = self._chk(idx.reshape(-1), torch.int64, "idx")
+        vals = self._chk(vals.reshape(-1), self.dtype, "vals")
+        d = torch.empty(idx.numel(), dtype=self.dtype, device=self.device)
+        with torch.cuda.device(self.device):
+            self._h.update_deltas_device(idx.data_ptr(), idx.numel(), vals.data_ptr(), vals.numel(),
+                                         d.data_ptr(), _stream())
+        return d
+
+    def apply_deltas_(self, idx: torch.Tensor, deltas: torch.Tensor) -> "DeviceSumTree":
+        """For j in batch order add ``deltas[j]`` to every proper ancestor of leaf ``idx[j]``
+        (ordered folds for floats); the leaves themselves are not touched."""
+        idx = self._chk(idx.reshape(-1), torch.int64, "idx")
+        deltas = self._chk(deltas.reshape(-1), self.dtype, "deltas")
+        if idx.numel() != deltas.numel():
+            raise TypeError("idx and deltas must have the same size")
+        with torch.cuda.device(self.device):
+            self._h.apply_deltas_device(idx.data_ptr(), idx.numel(), deltas.data_ptr(), _stream())
+        return self
+
+    def route_uniform(self, u: torch.Tensor):
+        """``sample_uniform`` that also returns the prefix left over at the leaf reached."""
+        u = self._chk(u.reshape(-1), torch.float64, "u")
+        m = u.numel()
+        leaf = torch.empty(m, dtype=torch.int64, device=self.device)
+        resid = torch.empty(m, dtype=self.dtype, device=self.device)
+        with torch.cuda.device(self.device):
+            self._h.route_uniform_device(u.data_ptr(), m, leaf.data_ptr(), resid.data_ptr(), _stream())
+        return leaf, resid
+
     def poll(self) -> None:
         """Wait for the current stream and raise the first deferred validation error."""
         with torch.cuda.device(self.device):
