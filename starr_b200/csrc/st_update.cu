@@ -26,6 +26,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include "st_common.cuh"
+#include "st_ordered_fold.cuh"
 
 namespace st {
 
@@ -279,54 +280,30 @@ __global__ void __launch_bounds__(256) fold_level_kernel(T *__restrict__ H, uint
     }
 }
 
-// Warp-cooperative ordered fold of one long segment: the warp streams the segment with
-// coalesced loads (4 x 32 elements in flight) and every lane replays the same dependent add
-// chain from shuffled values, so the critical path is one FADD per element.
+// Long segments: one CTA per queued segment, exact parallel ordered fold (st_ordered_fold.cuh).
 template <typename T>
-__global__ void __launch_bounds__(128) fold_long_kernel(T *__restrict__ H, const T *__restrict__ lev_d,
-                                                        int64_t level_stride,
-                                                        const seg_entry *__restrict__ queue,
-                                                        unsigned int *status)
+__global__ void __launch_bounds__(FOLD_THREADS) fold_scan_kernel(T *__restrict__ H, const T *__restrict__ lev_d,
+                                                                 int64_t level_stride,
+                                                                 const seg_entry *__restrict__ queue,
+                                                                 unsigned int *status)
 {
     if (status[SW_STATUS]) return;
-    const int lane = threadIdx.x & 31;
+    using I = typename fp_bits<T>::I;
+    __shared__ T s_d[FOLD_CHUNK];
+    __shared__ I s_wtot[FOLD_THREADS / 32][2];
+    __shared__ T s_acc;
+    __shared__ fold_smem_ctl ctl;
     const unsigned int total = status[SW_QCOUNT];
     for (;;) {
-        unsigned int slot = 0;
-        if (lane == 0) slot = atomicAdd(status + SW_QTAKE, 1u);
-        slot = __shfl_sync(0xffffffffu, slot, 0);
+        __syncthreads();
+        if (threadIdx.x == 0) ctl.slot = atomicAdd(status + SW_QTAKE, 1u);
+        __syncthreads();
+        const unsigned int slot = ctl.slot;
         if (slot >= total) break;
         const seg_entry s = queue[slot];
         const T *src = lev_d + (int64_t)s.level * level_stride + s.start;
-        const uint32_t node = s.node;
-        T acc = H[node];
-        int x = 0;
-        constexpr int U = 4;
-        for (; x + 32 * U <= s.len; x += 32 * U) {
-            T v[U];
-#pragma unroll
-            for (int k = 0; k < U; ++k) v[k] = src[x + k * 32 + lane];
-#pragma unroll
-            for (int k = 0; k < U; ++k)
-#pragma unroll
-                for (int l = 0; l < 32; ++l) {
-                    T w;
-                    if constexpr (sizeof(T) == 8) w = __longlong_as_double(__shfl_sync(0xffffffffu, __double_as_longlong(v[k]), l));
-                    else w = __shfl_sync(0xffffffffu, v[k], l);
-                    acc = t_add<T>(acc, w);
-                }
-        }
-        for (; x < s.len; x += 32) {
-            const int rem = s.len - x < 32 ? s.len - x : 32;
-            T v = (lane < rem) ? src[x + lane] : T(0);
-            for (int l = 0; l < rem; ++l) {
-                T w;
-                if constexpr (sizeof(T) == 8) w = __longlong_as_double(__shfl_sync(0xffffffffu, __double_as_longlong(v), l));
-                else w = __shfl_sync(0xffffffffu, v, l);
-                acc = t_add<T>(acc, w);
-            }
-        }
-        if (lane == 0) H[node] = acc;
+        const T r = ordered_fold_cta<T>(H[s.node], src, s.len, s_d, s_wtot, &s_acc, &ctl);
+        if (threadIdx.x == 0) H[s.node] = r;
     }
 }
 
@@ -391,7 +368,7 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
             }
         }
         ++g_kernel_launches;
-        fold_long_kernel<T><<<t->sm_count * 2, 128, 0, s>>>(H, lev, B, w.queue, status);
+        fold_scan_kernel<T><<<t->sm_count * 4, FOLD_THREADS, 0, s>>>(H, lev, B, w.queue, status);
         return cudaGetLastError();
     }
 }

@@ -260,3 +260,46 @@ def test_axis_fold_matches_numpy(oracle_mod):
             want = x.sum(axis=tuple(range(lo, hi + 1)))
             assert_bits_equal(got.reshape(want.shape), want, f"{np.dtype(dt).name} {shape}")
             h.close()
+
+
+# ---- the exact parallel ordered fold (st_ordered_fold.cuh) under adversarial inputs ------------
+def _adversarial_batches(rng, n, m, dt, kind):
+    idx = rng.integers(0, n, m).astype(np.intp)
+    if kind == "ties":            # multiples of a small power of two: exact half-ulp ties everywhere
+        vals = (rng.integers(0, 1 << 12, m) * 2.0 ** -9).astype(dt)
+    elif kind == "boundary":      # total hovers around a power of two and hops across it
+        vals = np.where(rng.random(m) < 0.5, 1.0, 1.0 + 2.0 ** -10).astype(dt)
+        idx = rng.integers(0, 4, m).astype(np.intp)
+    elif kind == "range":         # 60 orders of magnitude, zeros and subnormals
+        vals = (10.0 ** rng.uniform(-44 if dt == np.float32 else -320, 30, m)).astype(dt)
+        vals[rng.random(m) < 0.1] = 0
+    elif kind == "grow":          # monotone growth from zero: a binade crossing per doubling
+        vals = (np.arange(m) % 1000 + rng.random(m)).astype(dt)
+    else:                         # "same": one leaf hammered
+        vals = rng.random(m).astype(dt)
+        idx[:] = n // 3
+    return idx, vals
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64], ids=["f32", "f64"])
+@pytest.mark.parametrize("kind", ["ties", "boundary", "range", "grow", "same"])
+def test_ordered_fold_adversarial(oracle_mod, dt, kind):
+    """Few leaves, many updates: every node sees a long ordered segment, so the result depends
+    on the parity-map scan, its restarts at binade crossings and the sequential fallbacks."""
+    from starr_b200 import _lib
+    C = oracle_mod.c
+    rng = np.random.default_rng(hash(kind) % 1000)
+    for n, m in ((64, 200_000), (5, 40_000), (4096, 300_000)):
+        leaves = np.zeros(n, dt) if kind in ("grow", "range") else np.full(n, (1 << 20) / n, dt)
+        tree = np.zeros(n, dt)
+        C.build_sumtree_from_array(leaves, tree)
+        h = _lib.TreeHandle(n, dt)
+        h.build_from_host(leaves)
+        for rep in range(2):
+            idx, vals = _adversarial_batches(rng, n, m, dt, kind)
+            C.update_sumtree(idx, vals, leaves, tree)
+            h.update_host(idx, vals)
+            gl, gt = _state(h)
+            assert_bits_equal(gl, leaves, f"{kind} n={n} rep={rep} leaves")
+            assert_bits_equal(gt, tree, f"{kind} n={n} rep={rep} tree")
+        h.close()
