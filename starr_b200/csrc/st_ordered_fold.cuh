@@ -20,7 +20,8 @@
 // real FADD, and the scan restarts behind it in the new binade.  Nothing here is approximate:
 // every path reproduces the sequential IEEE result bit for bit.
 //
-// One CTA of FOLD_THREADS threads processes one segment chunk by chunk (FOLD_CHUNK elements).
+// Two drivers share the arithmetic: a warp folds medium segments (256-element chunks, registers
+// and shuffles only) and a CTA folds long ones (1024-element chunks, two barriers per chunk).
 #pragma once
 #include "st_common.cuh"
 
@@ -156,166 +157,239 @@ template <typename T> __device__ __forceinline__ T value_of(int eT, typename fp_
     return F::from_bits((U(eT) << F::MB) + ((U)m - (U(1) << F::MB)));
 }
 
+// ---------------------------------------------------------------------------------------------
+// shared pieces
+// ---------------------------------------------------------------------------------------------
+template <typename I> __device__ __forceinline__ pmap<I> pmap_shfl_up(const pmap<I> v, int off)
+{
+    pmap<I> o;
+    if constexpr (sizeof(I) == 8) {
+        o.a0 = (I)__shfl_up_sync(0xffffffffu, (long long)v.a0, off);
+        o.a1 = (I)__shfl_up_sync(0xffffffffu, (long long)v.a1, off);
+    } else {
+        o.a0 = __shfl_up_sync(0xffffffffu, v.a0, off);
+        o.a1 = __shfl_up_sync(0xffffffffu, v.a1, off);
+    }
+    return o;
+}
+template <typename I> __device__ __forceinline__ I shfl_i(I v, int src)
+{
+    if constexpr (sizeof(I) == 8) return (I)__shfl_sync(0xffffffffu, (long long)v, src);
+    else return __shfl_sync(0xffffffffu, v, src);
+}
+
+// inclusive scan of parity maps across the 32 lanes of a warp
+template <typename I> __device__ __forceinline__ pmap<I> pmap_warp_scan(pmap<I> v, int lane)
+{
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const pmap<I> o = pmap_shfl_up<I>(v, off);
+        if (lane >= off) v = pmap_then<I>(o, v);
+    }
+    return v;
+}
+
+constexpr int NO_VIOL = 0x7fffffff;
+
+// Walk E consecutive pending updates starting from the exact integer m.  Returns the index of
+// the first update the binade identity does not cover (NO_VIOL if none); m is left at the value
+// BEFORE that update (or after the last one).
+template <typename T, int E>
+__device__ __forceinline__ int walk_updates(const upd_map<T> (&um)[E], int first_idx, int pos, int nc,
+                                            typename fp_bits<T>::I &m)
+{
+    using I = typename fp_bits<T>::I;
+    constexpr I LO = I(1) << fp_bits<T>::MB;
+    constexpr I HI = I(1) << (fp_bits<T>::MB + 1);
+    int viol = NO_VIOL;
+#pragma unroll
+    for (int k = 0; k < E; ++k) {
+        const int i = first_idx + k;
+        if (i >= pos && i < nc && viol == NO_VIOL) {
+            const I v = m + um[k].flo;
+            if (um[k].big || m < LO || m >= HI || v < LO || v >= HI) viol = i;
+            else m += (m & 1) ? um[k].map.a1 : um[k].map.a0;
+        }
+    }
+    return viol;
+}
+
+// plain sequential adds from `p` while the value is not a positive normal number (at least one)
+template <typename T, typename LOAD>
+__device__ __forceinline__ T seq_until_ready(T cur, int &p, int nc, LOAD load)
+{
+    int e2;
+    typename fp_bits<T>::I m2;
+    do {
+        cur = t_add<T>(cur, load(p));
+        ++p;
+    } while (p < nc && !scan_ready<T>(cur, e2, m2));
+    return cur;
+}
+
+// ---------------------------------------------------------------------------------------------
+// warp driver: one warp folds src[0..len) into acc; every lane returns the same result.
+// s_w: this warp's private shared staging buffer of FOLDW_PAD elements.
+// ---------------------------------------------------------------------------------------------
+constexpr int FOLDW_E = 8;
+constexpr int FOLDW_CHUNK = 32 * FOLDW_E;                    // 256
+constexpr int FOLDW_PAD = FOLDW_CHUNK + FOLDW_CHUNK / 8;     // one pad word per 8: conflict-free
+
+__device__ __forceinline__ int foldw_at(int i) { return i + (i >> 3); }
+
+template <typename T>
+__device__ T ordered_fold_warp(T cur, const T *__restrict__ src, int len, T *s_w)
+{
+    using I = typename fp_bits<T>::I;
+    const int lane = threadIdx.x & 31;
+    for (int base = 0; base < len; base += FOLDW_CHUNK) {
+        const int nc = len - base < FOLDW_CHUNK ? len - base : FOLDW_CHUNK;
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < FOLDW_E; ++k) {
+            const int i = lane + 32 * k;
+            s_w[foldw_at(i)] = (i < nc) ? src[base + i] : T(0);
+        }
+        __syncwarp();
+        T dreg[FOLDW_E];
+#pragma unroll
+        for (int k = 0; k < FOLDW_E; ++k) dreg[k] = s_w[foldw_at(lane * FOLDW_E + k)];
+        auto load = [&](int p) { return s_w[foldw_at(p)]; };
+        int pos = 0;
+        while (pos < nc) {
+            int eT;
+            I m0;
+            if (!scan_ready<T>(cur, eT, m0)) {
+                cur = seq_until_ready<T>(cur, pos, nc, load);   // identical in every lane
+                continue;
+            }
+            upd_map<T> um[FOLDW_E];
+            pmap<I> local{0, 0};
+#pragma unroll
+            for (int k = 0; k < FOLDW_E; ++k) {
+                const int i = lane * FOLDW_E + k;
+                if (i >= pos && i < nc) um[k] = decompose<T>(dreg[k], eT);
+                else um[k] = upd_map<T>{{0, 0}, 0, false};
+                local = pmap_then<I>(local, um[k].map);
+            }
+            const pmap<I> incl = pmap_warp_scan<I>(local, lane);
+            pmap<I> excl = pmap_shfl_up<I>(incl, 1);
+            if (lane == 0) excl = pmap<I>{0, 0};
+            I m = m0 + ((m0 & 1) ? excl.a1 : excl.a0);
+            const int viol = walk_updates<T, FOLDW_E>(um, lane * FOLDW_E, pos, nc, m);
+            const int fv = __reduce_min_sync(0xffffffffu, viol);
+            if (fv == NO_VIOL) {
+                const I t0 = shfl_i<I>(incl.a0, 31), t1 = shfl_i<I>(incl.a1, 31);
+                cur = value_of<T>(eT, m0 + ((m0 & 1) ? t1 : t0));
+                pos = nc;
+            } else {
+                const I mv = shfl_i<I>(m, fv / FOLDW_E);   // exact m just before update fv
+                cur = t_add<T>(value_of<T>(eT, mv), load(fv));
+                int p = fv + 1;
+                const int stop = (p + FOLD_SEQ_RUN < nc) ? p + FOLD_SEQ_RUN : nc;
+                for (; p < stop; ++p) cur = t_add<T>(cur, load(p));
+                pos = p;
+            }
+        }
+    }
+    return cur;
+}
+
+// ---------------------------------------------------------------------------------------------
+// CTA driver: FOLD_THREADS threads fold src[0..len) into acc; every thread returns the result.
+// Each thread owns FOLD_E consecutive updates of a chunk (loaded straight from global, next
+// chunk prefetched); two barriers per chunk.
+// ---------------------------------------------------------------------------------------------
 struct fold_smem_ctl {
     int first_viol;
-    int pos;
+    int owner_set;
     unsigned int slot;
     int pad;
 };
 
-// Fold `len` ordered updates src[0..len) into `acc` (exactly as a sequential FADD chain would).
-// Must be called by all FOLD_THREADS threads of the CTA; returns the result in every thread.
 template <typename T>
-__device__ T ordered_fold_cta(T acc, const T *__restrict__ src, int len, T *s_d,
-                              typename fp_bits<T>::I (*s_wtot)[2], T *s_acc, fold_smem_ctl *ctl)
+__device__ T ordered_fold_cta(T cur, const T *__restrict__ src, int len,
+                              typename fp_bits<T>::I (*s_wtot)[2], typename fp_bits<T>::I *s_mviol,
+                              fold_smem_ctl *ctl)
 {
-    using F = fp_bits<T>;
-    using I = typename F::I;
-    constexpr I LO = I(1) << F::MB;
-    constexpr I HI = I(1) << (F::MB + 1);
+    using I = typename fp_bits<T>::I;
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = FOLD_THREADS / 32;
+    auto load = [&](int p) { return src[p]; };   // sequential paths read global/L1 directly
 
-    if (tid == 0) *s_acc = acc;
+    T nxt[FOLD_E];
+#pragma unroll
+    for (int k = 0; k < FOLD_E; ++k) {
+        const int i = tid * FOLD_E + k;
+        nxt[k] = (i < len) ? src[i] : T(0);
+    }
     for (int base = 0; base < len; base += FOLD_CHUNK) {
         const int nc = len - base < FOLD_CHUNK ? len - base : FOLD_CHUNK;
-        __syncthreads();  // previous chunk fully consumed
-#pragma unroll
-        for (int k = 0; k < FOLD_E; ++k) {
-            const int i = tid + k * FOLD_THREADS;
-            s_d[i] = (i < nc) ? src[base + i] : T(0);
-        }
-        if (tid == 0) ctl->pos = 0;
-        __syncthreads();
         T dreg[FOLD_E];
 #pragma unroll
-        for (int k = 0; k < FOLD_E; ++k) dreg[k] = s_d[tid * FOLD_E + k];
-
-        for (;;) {
-            const int pos = ctl->pos;
-            if (pos >= nc) break;
-            T cur = *s_acc;
+        for (int k = 0; k < FOLD_E; ++k) dreg[k] = nxt[k];
+#pragma unroll
+        for (int k = 0; k < FOLD_E; ++k) {   // prefetch the next chunk
+            const int i = base + FOLD_CHUNK + tid * FOLD_E + k;
+            nxt[k] = (i < len) ? src[i] : T(0);
+        }
+        auto loadc = [&](int p) { return load(base + p); };
+        int pos = 0;
+        while (pos < nc) {                    // pos, cur are uniform across the CTA
             int eT;
             I m0;
             if (!scan_ready<T>(cur, eT, m0)) {
-                // zero / negative / subnormal / inf / nan: plain sequential adds until usable again
-                __syncthreads();
-                if (tid == 0) {
-                    int p = pos;
-                    int e2;
-                    I m2;
-                    do {
-                        cur = t_add<T>(cur, s_d[p]);
-                        ++p;
-                    } while (p < nc && !scan_ready<T>(cur, e2, m2));
-                    *s_acc = cur;
-                    ctl->pos = p;
-                }
-                __syncthreads();
+                cur = seq_until_ready<T>(cur, pos, nc, loadc);   // identical in every thread
                 continue;
             }
-            // ---- per-thread maps of the still-pending elements ---------------------------------
             upd_map<T> um[FOLD_E];
-            pmap<I> local;
-            local.a0 = 0;
-            local.a1 = 0;
+            pmap<I> local{0, 0};
 #pragma unroll
             for (int k = 0; k < FOLD_E; ++k) {
                 const int i = tid * FOLD_E + k;
-                if (i >= pos && i < nc) {
-                    um[k] = decompose<T>(dreg[k], eT);
-                } else {
-                    um[k].map.a0 = 0;
-                    um[k].map.a1 = 0;
-                    um[k].flo = 0;
-                    um[k].big = false;
-                }
+                if (i >= pos && i < nc) um[k] = decompose<T>(dreg[k], eT);
+                else um[k] = upd_map<T>{{0, 0}, 0, false};
                 local = pmap_then<I>(local, um[k].map);
             }
-            // ---- exclusive scan of the maps over the CTA -----------------------------------------
-            pmap<I> incl = local;
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                pmap<I> o;
-                if constexpr (sizeof(I) == 8) {
-                    o.a0 = (I)__shfl_up_sync(0xffffffffu, (long long)incl.a0, off);
-                    o.a1 = (I)__shfl_up_sync(0xffffffffu, (long long)incl.a1, off);
-                } else {
-                    o.a0 = __shfl_up_sync(0xffffffffu, incl.a0, off);
-                    o.a1 = __shfl_up_sync(0xffffffffu, incl.a1, off);
-                }
-                if (lane >= off) incl = pmap_then<I>(o, incl);
-            }
+            const pmap<I> incl = pmap_warp_scan<I>(local, lane);
+            pmap<I> excl = pmap_shfl_up<I>(incl, 1);
+            if (lane == 0) excl = pmap<I>{0, 0};
             if (lane == 31) {
                 s_wtot[warp][0] = incl.a0;
                 s_wtot[warp][1] = incl.a1;
             }
-            pmap<I> excl;  // maps of all earlier lanes of this warp
-            if constexpr (sizeof(I) == 8) {
-                excl.a0 = (I)__shfl_up_sync(0xffffffffu, (long long)incl.a0, 1);
-                excl.a1 = (I)__shfl_up_sync(0xffffffffu, (long long)incl.a1, 1);
-            } else {
-                excl.a0 = __shfl_up_sync(0xffffffffu, incl.a0, 1);
-                excl.a1 = __shfl_up_sync(0xffffffffu, incl.a1, 1);
-            }
-            if (lane == 0) {
-                excl.a0 = 0;
-                excl.a1 = 0;
-            }
-            if (tid == 0) ctl->first_viol = 0x7fffffff;
-            __syncthreads();
-            pmap<I> pre;
-            pre.a0 = 0;
-            pre.a1 = 0;
-            for (int w = 0; w < warp; ++w) {
-                pmap<I> t;
-                t.a0 = s_wtot[w][0];
-                t.a1 = s_wtot[w][1];
-                pre = pmap_then<I>(pre, t);
+            if (tid == 0) ctl->first_viol = NO_VIOL;
+            __syncthreads();                                           // barrier 1: warp totals
+            pmap<I> pre{0, 0}, tot{0, 0};
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                const pmap<I> t{s_wtot[w][0], s_wtot[w][1]};
+                if (w < warp) pre = pmap_then<I>(pre, t);
+                tot = pmap_then<I>(tot, t);
             }
             pre = pmap_then<I>(pre, excl);
-            // ---- walk my elements with the real m, find the first one the identity does not cover --
             I m = m0 + ((m0 & 1) ? pre.a1 : pre.a0);
-            int viol = 0x7fffffff;
-            I m_at_viol = 0;
-#pragma unroll
-            for (int k = 0; k < FOLD_E; ++k) {
-                const int i = tid * FOLD_E + k;
-                if (i >= pos && i < nc && viol == 0x7fffffff) {
-                    const I v = m + um[k].flo;
-                    if (um[k].big || m < LO || m >= HI || v < LO || v >= HI) {
-                        viol = i;
-                        m_at_viol = m;
-                    } else {
-                        m += (m & 1) ? um[k].map.a1 : um[k].map.a0;
-                    }
-                }
+            const int viol = walk_updates<T, FOLD_E>(um, tid * FOLD_E, pos, nc, m);
+            if (!__syncthreads_or(viol != NO_VIOL)) {                  // barrier 2: any violation?
+                cur = value_of<T>(eT, m0 + ((m0 & 1) ? tot.a1 : tot.a0));
+                pos = nc;
+                continue;
             }
-            if (viol != 0x7fffffff) atomicMin(&ctl->first_viol, viol);
+            if (viol != NO_VIOL) atomicMin(&ctl->first_viol, viol);
             __syncthreads();
             const int fv = ctl->first_viol;
-            if (fv == 0x7fffffff) {
-                // whole rest of the chunk stayed inside the binade: the owner of the last element
-                // holds the final m
-                if (tid == (nc - 1) / FOLD_E) {
-                    *s_acc = value_of<T>(eT, m);
-                    ctl->pos = nc;
-                }
-            } else if (viol == fv) {
-                // every element before fv is exact; apply fv with a real add, then a short
-                // sequential run so that boundary-hopping inputs stay cheap
-                T v = t_add<T>(value_of<T>(eT, m_at_viol), s_d[fv]);
-                int p = fv + 1;
-                const int stop = (p + FOLD_SEQ_RUN < nc) ? p + FOLD_SEQ_RUN : nc;
-                for (; p < stop; ++p) v = t_add<T>(v, s_d[p]);
-                *s_acc = v;
-                ctl->pos = p;
-            }
+            if (viol == fv) *s_mviol = m;      // exact m just before update fv
             __syncthreads();
+            cur = t_add<T>(value_of<T>(eT, *s_mviol), loadc(fv));
+            int p = fv + 1;
+            const int stop = (p + FOLD_SEQ_RUN < nc) ? p + FOLD_SEQ_RUN : nc;
+            for (; p < stop; ++p) cur = t_add<T>(cur, loadc(p));
+            pos = p;
+            __syncthreads();                   // everyone has read s_mviol / first_viol
         }
     }
-    __syncthreads();
-    return *s_acc;
+    return cur;
 }
 
 }  // namespace st

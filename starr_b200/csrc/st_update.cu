@@ -23,27 +23,18 @@
 //
 // Everything is enqueued on one stream; validation failures set the device status word and
 // every later kernel of the batch returns immediately (nothing is written).
+#include <cstdlib>
+
 #include <cub/device/device_radix_sort.cuh>
 
 #include "st_common.cuh"
+#include "st_update_defs.cuh"
 #include "st_ordered_fold.cuh"
+#include "st_partition.cuh"
 
 namespace st {
 
-constexpr int64_t UPDATE_MAX_CHUNK = 1 << 20;
-constexpr int SHORT_SEG = 32;  // segments up to this length are folded by their head thread
-
 int64_t update_max_chunk() { return UPDATE_MAX_CHUNK; }
-
-struct seg_entry {
-    int level;
-    int start;
-    int len;
-    uint32_t node;
-};
-
-// status-word layout (unsigned int[64])
-enum { SW_STATUS = 0, SW_QCOUNT = 1, SW_QTAKE = 2, SW_STAT_FAST = 4, SW_STAT_CHAINS = 5, SW_STAT_CHAIN_ELEMS = 6, SW_STAT_LONGEST = 7 };
 
 // -----------------------------------------------------------------------------------------
 // workspace carving
@@ -52,7 +43,9 @@ struct update_ws {
     uint32_t *keys_a, *keys_b, *kj;
     int *j_a, *j_b;
     void *dj, *ds, *lev_d;  // T-typed
-    seg_entry *queue;
+    seg_entry *queue, *queue_med;
+    int *seg_sa, *seg_ea, *seg_sb, *seg_eb, *zcount;
+    unsigned int *tilesum;
     void *cub_tmp;
     size_t cub_bytes;
     size_t total;
@@ -79,7 +72,16 @@ static update_ws carve(const st_tree *t, int64_t B, char *base)
     w.dj = take(B * es);
     w.ds = take(B * es);
     w.lev_d = is_f ? take((size_t)(t->depth + 1) * B * es) : nullptr;
-    w.queue = is_f ? (seg_entry *)take((size_t)(t->depth + 1) * (B / (SHORT_SEG + 1) + 2) * sizeof(seg_entry)) : nullptr;
+    w.queue = is_f ? (seg_entry *)take((size_t)(t->depth + 1) * (B / (MEDIUM_SEG + 1) + 2) * sizeof(seg_entry)) : nullptr;
+    w.queue_med = is_f ? (seg_entry *)take((size_t)(t->depth + 1) * (B / (SHORT_SEG + 1) + 2) * sizeof(seg_entry)) : nullptr;
+    if (is_f) {
+        w.seg_sa = (int *)take(B * 4);
+        w.seg_ea = (int *)take(B * 4);
+        w.seg_sb = (int *)take(B * 4);
+        w.seg_eb = (int *)take(B * 4);
+        w.zcount = (int *)take(B * 4);
+        w.tilesum = (unsigned int *)take(2 * PART_MAX_TILES * sizeof(unsigned int));
+    }
     size_t cb1 = 0, cb2 = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, cb1, (const uint32_t *)nullptr, (uint32_t *)nullptr,
                                     (const int *)nullptr, (int *)nullptr, (int)B, 0, 32, (cudaStream_t)0);
@@ -101,15 +103,6 @@ size_t update_workspace_bytes(const st_tree *t, int64_t batch)
     if (batch < 1) batch = 1;
     return carve(t, batch, nullptr).total;
 }
-
-// -----------------------------------------------------------------------------------------
-// key helpers.  key = heap index of the leaf, shifted left so that its top bit sits at bit
-// `depth`; sorting by key is the tree's left-to-right leaf order (the rotated order of
-// non-power-of-two trees).  Ancestor at level l (root = 0) is key >> (depth - l),
-// valid for l < leaf level.
-// -----------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t key_to_heap(uint32_t key, uint64_t two_n) { return key < two_n ? key : key >> 1; }
-__device__ __forceinline__ int key_leaf_level(uint32_t key, uint64_t two_n, int depth) { return key < two_n ? depth : depth - 1; }
 
 // -----------------------------------------------------------------------------------------
 // 0. validation (pyx:37-39 negative scan over ALL vals; Cython boundscheck on idx)
@@ -139,7 +132,7 @@ __global__ void __launch_bounds__(256) make_keys_kernel(const int64_t *__restric
 {
     if (status[SW_STATUS]) return;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j == 0) { status[SW_QCOUNT] = 0; status[SW_QTAKE] = 0; }
+    if (j == 0) { status[SW_QCOUNT] = 0; status[SW_QTAKE] = 0; status[SW_QCOUNT_MED] = 0; status[SW_QTAKE_MED] = 0; }
     if (j >= m) return;
     const uint32_t h = (uint32_t)idx[j] + n;
     const uint32_t key = h << (depth - heap_level(h));
@@ -252,7 +245,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) fold_level_kernel(T *__restrict__ H, uint32_t n, int depth, int level,
                                                          const uint32_t *__restrict__ keys,
                                                          const T *__restrict__ d, int m,
-                                                         seg_entry *__restrict__ queue, unsigned int *status)
+                                                         seg_entry *__restrict__ queue_long,
+                                                         seg_entry *__restrict__ queue_med, unsigned int *status)
 {
     if (status[SW_STATUS]) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -275,35 +269,56 @@ __global__ void __launch_bounds__(256) fold_level_kernel(T *__restrict__ H, uint
             const int mid = (lo + hi) >> 1;
             if ((keys[mid] >> sh) <= node) lo = mid + 1; else hi = mid;
         }
-        const unsigned int slot = atomicAdd(status + SW_QCOUNT, 1u);
-        queue[slot] = seg_entry{level, i, lo - i, node};
+        const int len = lo - i;
+        if (len > MEDIUM_SEG) {
+            const unsigned int slot = atomicAdd(status + SW_QCOUNT, 1u);
+            queue_long[slot] = seg_entry{level, i, len, node};
+        } else {
+            const unsigned int slot = atomicAdd(status + SW_QCOUNT_MED, 1u);
+            queue_med[slot] = seg_entry{level, i, len, node};
+        }
     }
 }
 
-// Long segments: one CTA per queued segment, exact parallel ordered fold (st_ordered_fold.cuh).
+// Queued segments: exact parallel ordered folds (st_ordered_fold.cuh).  CTAs first drain the
+// queue of long segments (one CTA each), then their warps drain the queue of medium segments
+// (one warp each).
 template <typename T>
 __global__ void __launch_bounds__(FOLD_THREADS) fold_scan_kernel(T *__restrict__ H, const T *__restrict__ lev_d,
                                                                  int64_t level_stride,
-                                                                 const seg_entry *__restrict__ queue,
+                                                                 const seg_entry *__restrict__ queue_long,
+                                                                 const seg_entry *__restrict__ queue_med,
                                                                  unsigned int *status)
 {
     if (status[SW_STATUS]) return;
     using I = typename fp_bits<T>::I;
-    __shared__ T s_d[FOLD_CHUNK];
     __shared__ I s_wtot[FOLD_THREADS / 32][2];
-    __shared__ T s_acc;
+    __shared__ I s_mviol;
     __shared__ fold_smem_ctl ctl;
-    const unsigned int total = status[SW_QCOUNT];
+    __shared__ T s_stage[FOLD_THREADS / 32][FOLDW_PAD];
+    const unsigned int n_long = status[SW_QCOUNT];
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) ctl.slot = atomicAdd(status + SW_QTAKE, 1u);
         __syncthreads();
         const unsigned int slot = ctl.slot;
-        if (slot >= total) break;
-        const seg_entry s = queue[slot];
+        if (slot >= n_long) break;
+        const seg_entry s = queue_long[slot];
         const T *src = lev_d + (int64_t)s.level * level_stride + s.start;
-        const T r = ordered_fold_cta<T>(H[s.node], src, s.len, s_d, s_wtot, &s_acc, &ctl);
+        const T r = ordered_fold_cta<T>(H[s.node], src, s.len, s_wtot, &s_mviol, &ctl);
         if (threadIdx.x == 0) H[s.node] = r;
+    }
+    const unsigned int n_med = status[SW_QCOUNT_MED];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (;;) {
+        unsigned int slot = 0;
+        if (lane == 0) slot = atomicAdd(status + SW_QTAKE_MED, 1u);
+        slot = __shfl_sync(0xffffffffu, slot, 0);
+        if (slot >= n_med) break;
+        const seg_entry s = queue_med[slot];
+        const T *src = lev_d + (int64_t)s.level * level_stride + s.start;
+        const T r = ordered_fold_warp<T>(H[s.node], src, s.len, s_stage[warp]);
+        if (lane == 0) H[s.node] = r;
     }
 }
 
@@ -354,21 +369,48 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
         T *lev = (T *)w.lev_d;
         e = cudaMemcpyAsync(lev, d_batch, (size_t)m * sizeof(T), cudaMemcpyDeviceToDevice, s);
         if (e != cudaSuccess) return e;
-        uint32_t *kcur = w.kj, *knext = w.keys_a, *kspare = w.keys_b;
-        for (int l = 0; l < depth; ++l) {
-            ++g_kernel_launches;
-            fold_level_kernel<T><<<g, 256, 0, s>>>(H, n, depth, l, kcur, lev + (int64_t)l * B, m, w.queue, status);
-            if (l + 1 < depth) {
-                cb = w.cub_bytes;
-                e = cub::DeviceRadixSort::SortPairs(w.cub_tmp, cb, kcur, knext, lev + (int64_t)l * B,
-                                                    lev + (int64_t)(l + 1) * B, m, depth - l - 1, depth + 1, s);
+        static const bool use_v1 = getenv("ST_UPDATE_V1") != nullptr;   // A/B switch: per-level cub sorts
+        if (!use_v1) {
+            if (!t->coop_ok) return cudaErrorCooperativeLaunchTooLarge;
+            part_params<T> pp;
+            pp.H = H; pp.n = n; pp.depth = depth; pp.m = m;
+            pp.ntiles = (m + PART_TILE - 1) / PART_TILE;
+            pp.key0 = w.kj; pp.keyA = w.keys_a; pp.keyB = w.keys_b;
+            pp.lev_d = lev; pp.lev_stride = B;
+            pp.sA = w.seg_sa; pp.eA = w.seg_ea; pp.sB = w.seg_sb; pp.eB = w.seg_eb;
+            pp.Z = w.zcount; pp.tilesum = w.tilesum;
+            pp.qlong = w.queue; pp.qmed = w.queue_med; pp.status = status;
+            static int occ = 0;
+            if (!occ) {
+                e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, partition_levels_kernel<T>, PART_THREADS, 0);
                 if (e != cudaSuccess) return e;
-                if (l == 0) { kcur = knext; knext = kspare; }  // never overwrite kj
-                else { uint32_t *tmp = kcur; kcur = knext; knext = tmp; }
+                if (occ < 1) return cudaErrorCooperativeLaunchTooLarge;
+            }
+            int grid = occ * t->sm_count;
+            if (grid > pp.ntiles) grid = pp.ntiles;
+            void *args[] = {&pp};
+            ++g_kernel_launches;
+            e = cudaLaunchCooperativeKernel((const void *)partition_levels_kernel<T>, dim3(grid), dim3(PART_THREADS),
+                                            args, 0, s);
+            if (e != cudaSuccess) return e;
+        } else {
+        uint32_t *kcur = w.kj, *knext = w.keys_a, *kspare = w.keys_b;
+            for (int l = 0; l < depth; ++l) {
+                ++g_kernel_launches;
+                fold_level_kernel<T><<<g, 256, 0, s>>>(H, n, depth, l, kcur, lev + (int64_t)l * B, m, w.queue, w.queue_med,
+                                                       status);
+                if (l + 1 < depth) {
+                    cb = w.cub_bytes;
+                    e = cub::DeviceRadixSort::SortPairs(w.cub_tmp, cb, kcur, knext, lev + (int64_t)l * B,
+                                                        lev + (int64_t)(l + 1) * B, m, depth - l - 1, depth + 1, s);
+                    if (e != cudaSuccess) return e;
+                    if (l == 0) { kcur = knext; knext = kspare; }  // never overwrite kj
+                    else { uint32_t *tmp = kcur; kcur = knext; knext = tmp; }
+                }
             }
         }
         ++g_kernel_launches;
-        fold_scan_kernel<T><<<t->sm_count * 4, FOLD_THREADS, 0, s>>>(H, lev, B, w.queue, status);
+        fold_scan_kernel<T><<<t->sm_count * 8, FOLD_THREADS, 0, s>>>(H, lev, B, w.queue, w.queue_med, status);
         return cudaGetLastError();
     }
 }
