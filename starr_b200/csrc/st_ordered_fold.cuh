@@ -178,6 +178,12 @@ template <typename I> __device__ __forceinline__ I shfl_i(I v, int src)
     else return __shfl_sync(0xffffffffu, v, src);
 }
 
+template <typename I> __device__ __forceinline__ I shfl_xor_i(I v, int mask)
+{
+    if constexpr (sizeof(I) == 8) return (I)__shfl_xor_sync(0xffffffffu, (long long)v, mask);
+    else return __shfl_xor_sync(0xffffffffu, v, mask);
+}
+
 // inclusive scan of parity maps across the 32 lanes of a warp
 template <typename I> __device__ __forceinline__ pmap<I> pmap_warp_scan(pmap<I> v, int lane)
 {
@@ -225,6 +231,116 @@ __device__ __forceinline__ T seq_until_ready(T cur, int &p, int nc, LOAD load)
         ++p;
     } while (p < nc && !scan_ready<T>(cur, e2, m2));
     return cur;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Huge segments (one node with tens of thousands of updates, e.g. the root): two phases so that
+// all SMs work on one segment.
+//   phase A (all CTAs): every 1024-update chunk is summarised, relative to the exponent eT of the
+//       node's CURRENT value, as a parity map plus the extreme excursions of its exact partial
+//       sums for either start parity.  A chunk is "safe" for an incoming m if those excursions keep
+//       every intermediate value inside the binade -- then its whole effect is m += a[parity(m)].
+//   phase B (one CTA per segment): walks the chunk summaries in order (a few integer ops per
+//       chunk); an unsafe chunk, or any chunk after the exponent has changed, is folded exactly
+//       by the CTA driver above.
+// ---------------------------------------------------------------------------------------------
+template <typename I> struct chunk_rec {
+    I a0, a1;        // parity map of the whole chunk
+    I min0, max0;    // extremes of (m_k - m_in) and (m_k + floor(x_k) - m_in), start parity even
+    I min1, max1;    // ... start parity odd
+    int ok;          // 0: contains an update the identity never covers, or magnitudes too large
+    int pad;
+};
+
+template <typename T>
+__device__ void chunk_summary_cta(const T *__restrict__ src, int nc, int eT, chunk_rec<typename fp_bits<T>::I> *out,
+                                  typename fp_bits<T>::I (*s_wtot)[2], typename fp_bits<T>::I (*s_red)[4],
+                                  float *s_abs)
+{
+    using I = typename fp_bits<T>::I;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = FOLD_THREADS / 32;
+    upd_map<T> um[FOLD_E];
+    pmap<I> local{0, 0};
+    bool anybig = false;
+    float mag = 0.f;
+#pragma unroll
+    for (int k = 0; k < FOLD_E; ++k) {
+        const int i = tid * FOLD_E + k;
+        if (i < nc) um[k] = decompose<T>(src[i], eT);
+        else um[k] = upd_map<T>{{0, 0}, 0, false};
+        anybig |= um[k].big;
+        const I a = um[k].map.a0 < 0 ? -um[k].map.a0 : um[k].map.a0;
+        mag += (float)a + 2.f;
+        local = pmap_then<I>(local, um[k].map);
+    }
+    const pmap<I> incl = pmap_warp_scan<I>(local, lane);
+    pmap<I> excl = pmap_shfl_up<I>(incl, 1);
+    if (lane == 0) excl = pmap<I>{0, 0};
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) mag += __shfl_xor_sync(0xffffffffu, mag, off);
+    __syncthreads();   // shared buffers free
+    if (lane == 31) {
+        s_wtot[warp][0] = incl.a0;
+        s_wtot[warp][1] = incl.a1;
+    }
+    if (lane == 0) s_abs[warp] = mag;
+    __syncthreads();
+    pmap<I> pre{0, 0}, tot{0, 0};
+    float magt = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+        const pmap<I> t{s_wtot[w][0], s_wtot[w][1]};
+        if (w < warp) pre = pmap_then<I>(pre, t);
+        tot = pmap_then<I>(tot, t);
+        magt += s_abs[w];
+    }
+    pre = pmap_then<I>(pre, excl);
+    // trajectories for both start parities, as offsets from the incoming m
+    I off0 = pre.a0, off1 = pre.a1;
+    I mn0 = 0, mx0 = 0, mn1 = 0, mx1 = 0;
+#pragma unroll
+    for (int k = 0; k < FOLD_E; ++k) {
+        const int i = tid * FOLD_E + k;
+        if (i < nc) {
+            const I f = um[k].flo;
+            const I lo0 = f < 0 ? off0 + f : off0, hi0 = f > 0 ? off0 + f : off0;
+            const I lo1 = f < 0 ? off1 + f : off1, hi1 = f > 0 ? off1 + f : off1;
+            mn0 = lo0 < mn0 ? lo0 : mn0;  mx0 = hi0 > mx0 ? hi0 : mx0;
+            mn1 = lo1 < mn1 ? lo1 : mn1;  mx1 = hi1 > mx1 ? hi1 : mx1;
+            off0 += (off0 & 1) ? um[k].map.a1 : um[k].map.a0;          // start parity even: m = m_in + off0
+            off1 += ((off1 + 1) & 1) ? um[k].map.a1 : um[k].map.a0;    // start parity odd
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const I a = shfl_xor_i<I>(mn0, off), b = shfl_xor_i<I>(mx0, off);
+        const I c = shfl_xor_i<I>(mn1, off), d = shfl_xor_i<I>(mx1, off);
+        mn0 = a < mn0 ? a : mn0;  mx0 = b > mx0 ? b : mx0;
+        mn1 = c < mn1 ? c : mn1;  mx1 = d > mx1 ? d : mx1;
+    }
+    const int bigs = __syncthreads_or(anybig);
+    if (lane == 0) {
+        s_red[warp][0] = mn0; s_red[warp][1] = mx0; s_red[warp][2] = mn1; s_red[warp][3] = mx1;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        chunk_rec<I> r;
+        r.a0 = tot.a0; r.a1 = tot.a1;
+        r.min0 = s_red[0][0]; r.max0 = s_red[0][1]; r.min1 = s_red[0][2]; r.max1 = s_red[0][3];
+        for (int w = 1; w < NW; ++w) {
+            r.min0 = s_red[w][0] < r.min0 ? s_red[w][0] : r.min0;
+            r.max0 = s_red[w][1] > r.max0 ? s_red[w][1] : r.max0;
+            r.min1 = s_red[w][2] < r.min1 ? s_red[w][2] : r.min1;
+            r.max1 = s_red[w][3] > r.max1 ? s_red[w][3] : r.max1;
+        }
+        // total magnitude below 2^(MB-1): no integer in the scan can have overflowed
+        r.ok = (!bigs && magt < (float)(I(1) << (fp_bits<T>::MB - 1))) ? 1 : 0;
+        r.pad = 0;
+        *out = r;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -41,7 +41,8 @@ template <typename T> struct part_params {
     int *sA, *eA, *sB, *eB;  // segment [s, e) of every element, ping-pong (level 0: [0, m))
     int *Z;                  // exclusive count of zero-bit elements before i
     unsigned int *tilesum;   // [2][PART_MAX_TILES] zero-bit counts per tile
-    seg_entry *qlong, *qmed;
+    seg_entry *qlong, *qmed, *qhuge;
+    int *huge_off;   // first chunk record of every huge segment
     unsigned int *status;
 };
 
@@ -149,6 +150,11 @@ __global__ void __launch_bounds__(PART_THREADS) partition_levels_kernel(part_par
                             T acc = p.H[node];
                             for (int x = s; x < e; ++x) acc = t_add<T>(acc, dC[x]);
                             p.H[node] = acc;
+                        } else if (len > HUGE_SEG) {
+                            const unsigned int slot = atomicAdd(p.status + SW_QCOUNT_HUGE, 1u);
+                            p.qhuge[slot] = seg_entry{l, s, len, node};
+                            p.huge_off[slot] = (int)atomicAdd(p.status + SW_HUGE_CHUNKS,
+                                                              (unsigned int)((len + 1023) / 1024));
                         } else if (len > MEDIUM_SEG) {
                             p.qlong[atomicAdd(p.status + SW_QCOUNT, 1u)] = seg_entry{l, s, len, node};
                         } else {

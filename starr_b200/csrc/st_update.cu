@@ -43,7 +43,9 @@ struct update_ws {
     uint32_t *keys_a, *keys_b, *kj;
     int *j_a, *j_b;
     void *dj, *ds, *lev_d;  // T-typed
-    seg_entry *queue, *queue_med;
+    seg_entry *queue, *queue_med, *queue_huge;
+    int *huge_off;
+    void *huge_recs;
     int *seg_sa, *seg_ea, *seg_sb, *seg_eb, *zcount;
     unsigned int *tilesum;
     void *cub_tmp;
@@ -75,6 +77,9 @@ static update_ws carve(const st_tree *t, int64_t B, char *base)
     w.queue = is_f ? (seg_entry *)take((size_t)(t->depth + 1) * (B / (MEDIUM_SEG + 1) + 2) * sizeof(seg_entry)) : nullptr;
     w.queue_med = is_f ? (seg_entry *)take((size_t)(t->depth + 1) * (B / (SHORT_SEG + 1) + 2) * sizeof(seg_entry)) : nullptr;
     if (is_f) {
+        w.queue_huge = (seg_entry *)take((size_t)(t->depth + 1) * (B / (HUGE_SEG + 1) + 2) * sizeof(seg_entry));
+        w.huge_off = (int *)take((size_t)(t->depth + 1) * (B / (HUGE_SEG + 1) + 2) * sizeof(int));
+        w.huge_recs = take((size_t)(t->depth + 1) * (B / FOLD_CHUNK + 2) * 64);
         w.seg_sa = (int *)take(B * 4);
         w.seg_ea = (int *)take(B * 4);
         w.seg_sb = (int *)take(B * 4);
@@ -132,7 +137,8 @@ __global__ void __launch_bounds__(256) make_keys_kernel(const int64_t *__restric
 {
     if (status[SW_STATUS]) return;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j == 0) { status[SW_QCOUNT] = 0; status[SW_QTAKE] = 0; status[SW_QCOUNT_MED] = 0; status[SW_QTAKE_MED] = 0; }
+    if (j == 0) { status[SW_QCOUNT] = 0; status[SW_QTAKE] = 0; status[SW_QCOUNT_MED] = 0; status[SW_QTAKE_MED] = 0;
+                  status[SW_QCOUNT_HUGE] = 0; status[SW_HUGE_CHUNKS] = 0; status[SW_QTAKE_HUGE] = 0; }
     if (j >= m) return;
     const uint32_t h = (uint32_t)idx[j] + n;
     const uint32_t key = h << (depth - heap_level(h));
@@ -322,6 +328,106 @@ __global__ void __launch_bounds__(FOLD_THREADS) fold_scan_kernel(T *__restrict__
     }
 }
 
+// Huge segments, phase A: every CTA summarises chunks (see st_ordered_fold.cuh).
+template <typename T>
+__global__ void __launch_bounds__(FOLD_THREADS) fold_huge_maps_kernel(const T *__restrict__ H, const T *__restrict__ lev_d,
+                                                                      int64_t level_stride,
+                                                                      const seg_entry *__restrict__ qhuge,
+                                                                      const int *__restrict__ huge_off,
+                                                                      chunk_rec<typename fp_bits<T>::I> *__restrict__ recs,
+                                                                      const unsigned int *status)
+{
+    if (status[SW_STATUS]) return;
+    using I = typename fp_bits<T>::I;
+    __shared__ I s_wtot[FOLD_THREADS / 32][2];
+    __shared__ I s_red[FOLD_THREADS / 32][4];
+    __shared__ float s_abs[FOLD_THREADS / 32];
+    __shared__ int s_entry;
+    const unsigned int n_huge = status[SW_QCOUNT_HUGE];
+    const int total_chunks = (int)status[SW_HUGE_CHUNKS];
+    for (int g = blockIdx.x; g < total_chunks; g += gridDim.x) {
+        __syncthreads();
+        for (unsigned int e = threadIdx.x; e < n_huge; e += FOLD_THREADS) {
+            const int off = huge_off[e];
+            if (g >= off && g < off + (qhuge[e].len + FOLD_CHUNK - 1) / FOLD_CHUNK) s_entry = (int)e;
+        }
+        __syncthreads();
+        const int e = s_entry;
+        const seg_entry s = qhuge[e];
+        const int c = g - huge_off[e];
+        const int nc = s.len - c * FOLD_CHUNK < FOLD_CHUNK ? s.len - c * FOLD_CHUNK : FOLD_CHUNK;
+        int eT;
+        I m0;
+        if (!scan_ready<T>(H[s.node], eT, m0)) {
+            if (threadIdx.x == 0) recs[g].ok = 0;
+            continue;
+        }
+        chunk_summary_cta<T>(lev_d + (int64_t)s.level * level_stride + s.start + (int64_t)c * FOLD_CHUNK, nc, eT,
+                             recs + g, s_wtot, s_red, s_abs);
+    }
+}
+
+// Huge segments, phase B: one CTA per segment walks the chunk summaries in order.
+template <typename T>
+__global__ void __launch_bounds__(FOLD_THREADS) fold_huge_apply_kernel(T *__restrict__ H, const T *__restrict__ lev_d,
+                                                                       int64_t level_stride,
+                                                                       const seg_entry *__restrict__ qhuge,
+                                                                       const int *__restrict__ huge_off,
+                                                                       const chunk_rec<typename fp_bits<T>::I> *__restrict__ recs,
+                                                                       unsigned int *status)
+{
+    if (status[SW_STATUS]) return;
+    using I = typename fp_bits<T>::I;
+    constexpr I LO = I(1) << fp_bits<T>::MB;
+    constexpr I HI = I(1) << (fp_bits<T>::MB + 1);
+    __shared__ I s_wtot[FOLD_THREADS / 32][2];
+    __shared__ I s_mviol;
+    __shared__ fold_smem_ctl ctl;
+    __shared__ chunk_rec<I> s_rec[FOLD_THREADS];
+    const unsigned int n_huge = status[SW_QCOUNT_HUGE];
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) ctl.slot = atomicAdd(status + SW_QTAKE_HUGE, 1u);
+        __syncthreads();
+        const unsigned int slot = ctl.slot;
+        if (slot >= n_huge) break;
+        const seg_entry s = qhuge[slot];
+        const T *src = lev_d + (int64_t)s.level * level_stride + s.start;
+        const chunk_rec<I> *rec = recs + huge_off[slot];
+        const int nchunks = (s.len + FOLD_CHUNK - 1) / FOLD_CHUNK;
+        T cur = H[s.node];
+        int eT0;
+        I m;
+        bool stale = !scan_ready<T>(cur, eT0, m);   // summaries were made for eT0 (phase A saw the same value)
+        for (int cb = 0; cb < nchunks; cb += FOLD_THREADS) {
+            __syncthreads();
+            if (cb + (int)threadIdx.x < nchunks) s_rec[threadIdx.x] = rec[cb + threadIdx.x];
+            __syncthreads();
+            const int lim = nchunks - cb < FOLD_THREADS ? nchunks - cb : FOLD_THREADS;
+            for (int k = 0; k < lim; ++k) {   // uniform over the CTA
+                if (!stale) {
+                    const chunk_rec<I> r = s_rec[k];
+                    const bool odd = (m & 1) != 0;
+                    const I mn = odd ? r.min1 : r.min0, mx = odd ? r.max1 : r.max0;
+                    if (r.ok && m + mn >= LO && m + mx < HI) {
+                        m += odd ? r.a1 : r.a0;
+                        continue;
+                    }
+                    cur = value_of<T>(eT0, m);
+                }
+                const int c = cb + k;
+                const int nc = s.len - c * FOLD_CHUNK < FOLD_CHUNK ? s.len - c * FOLD_CHUNK : FOLD_CHUNK;
+                cur = ordered_fold_cta<T>(cur, src + (int64_t)c * FOLD_CHUNK, nc, s_wtot, &s_mviol, &ctl);
+                int e2;
+                I m2;
+                stale = !(scan_ready<T>(cur, e2, m2) && e2 == eT0);
+                if (!stale) m = m2;
+            }
+        }
+        if (threadIdx.x == 0) H[s.node] = stale ? cur : value_of<T>(eT0, m);
+    }
+}
+
 // -----------------------------------------------------------------------------------------
 // host driver
 // -----------------------------------------------------------------------------------------
@@ -379,7 +485,8 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
             pp.lev_d = lev; pp.lev_stride = B;
             pp.sA = w.seg_sa; pp.eA = w.seg_ea; pp.sB = w.seg_sb; pp.eB = w.seg_eb;
             pp.Z = w.zcount; pp.tilesum = w.tilesum;
-            pp.qlong = w.queue; pp.qmed = w.queue_med; pp.status = status;
+            pp.qlong = w.queue; pp.qmed = w.queue_med; pp.qhuge = w.queue_huge; pp.huge_off = w.huge_off;
+            pp.status = status;
             static int occ = 0;
             if (!occ) {
                 e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, partition_levels_kernel<T>, PART_THREADS, 0);
@@ -409,7 +516,12 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
                 }
             }
         }
-        ++g_kernel_launches;
+        using REC = chunk_rec<typename fp_bits<T>::I>;
+        g_kernel_launches += 3;
+        fold_huge_maps_kernel<T><<<t->sm_count * 2, FOLD_THREADS, 0, s>>>(H, lev, B, w.queue_huge, w.huge_off,
+                                                                         (REC *)w.huge_recs, status);
+        fold_huge_apply_kernel<T><<<t->sm_count, FOLD_THREADS, 0, s>>>(H, lev, B, w.queue_huge, w.huge_off,
+                                                                      (const REC *)w.huge_recs, status);
         fold_scan_kernel<T><<<t->sm_count * 8, FOLD_THREADS, 0, s>>>(H, lev, B, w.queue, w.queue_med, status);
         return cudaGetLastError();
     }

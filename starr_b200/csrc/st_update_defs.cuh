@@ -7,6 +7,7 @@ namespace st {
 constexpr int64_t UPDATE_MAX_CHUNK = 1 << 20;
 constexpr int SHORT_SEG = 32;    // segments up to this length are folded by their head thread
 constexpr int MEDIUM_SEG = 2048;  // up to this length by one warp, longer ones by one CTA
+constexpr int HUGE_SEG = 16384;   // longer than this: all CTAs summarise chunks, one CTA stitches them
 
 struct seg_entry {
     int level;
@@ -16,7 +17,7 @@ struct seg_entry {
 };
 
 // status-word layout (unsigned int[64])
-enum { SW_STATUS = 0, SW_QCOUNT = 1, SW_QTAKE = 2, SW_QCOUNT_MED = 8, SW_QTAKE_MED = 9, SW_STAT_FAST = 4, SW_STAT_CHAINS = 5, SW_STAT_CHAIN_ELEMS = 6, SW_STAT_LONGEST = 7 };
+enum { SW_STATUS = 0, SW_QCOUNT = 1, SW_QTAKE = 2, SW_QCOUNT_MED = 8, SW_QTAKE_MED = 9, SW_QCOUNT_HUGE = 10, SW_HUGE_CHUNKS = 11, SW_QTAKE_HUGE = 12, SW_STAT_FAST = 4, SW_STAT_CHAINS = 5, SW_STAT_CHAIN_ELEMS = 6, SW_STAT_LONGEST = 7 };
 
 // -----------------------------------------------------------------------------------------
 // key helpers.  key = heap index of the leaf, shifted left so that its top bit sits at bit
