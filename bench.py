@@ -63,6 +63,15 @@ def measured_hbm_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return {k: v["dram_bytes_per_launch"] for k, v in json.load(f)["kernels"].items()}
+    except Exception:
+        return {}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -75,7 +84,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except Exception:
@@ -83,12 +92,15 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
 
-    def stop(self):
+    def mark(self):
+        return time.time()
+
+    def stop(self, windows=()):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.12)
+        time.sleep(0.06)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -96,7 +108,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        inside = [r for ts, r in self.rows if any(a - 0.03 <= ts <= b + 0.03 for a, b in windows)]
+        scope = "timed regions" if inside else "whole run (timed regions shorter than the sampling period)"
+        for r in (inside or [r for _, r in self.rows]):
             parts = [x.strip() for x in r.split(",")]
             if len(parts) < 6:
                 continue
@@ -108,7 +122,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "scope": scope, "period_ms": 20}
 
 
 def make_batches(rng, n_leaves_global, m_global):
@@ -194,7 +208,7 @@ def run_reference(args):
 def workload_config(world):
     return {
         "workload": f"SumTreeArray float32, 2^{LOG2_LEAVES} leaves per GPU ({world} GPU: 2^{LOG2_LEAVES + (world - 1).bit_length()} "
-                    f"leaves sharded by subtree), per step 2^{LOG2_BATCH} leaf updates + 2^{LOG2_BATCH} prefix-search samples per GPU "
+                    f"leaves{' sharded by subtree' if world > 1 else ''}), per step 2^{LOG2_BATCH} leaf updates + 2^{LOG2_BATCH} prefix-search samples per GPU "
                     f"(BASELINE config #3; config #4 at 8 GPUs)",
         "leaves_per_gpu": 1 << LOG2_LEAVES, "updates_per_step_per_gpu": 1 << LOG2_BATCH,
         "samples_per_step_per_gpu": 1 << LOG2_BATCH,
@@ -258,14 +272,16 @@ def run_ours(args):
         return tree.sample_uniform(u, out=out)
 
     # ---- device-resident timing ---------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for w in range(warmup):
         step(*dbatches[w % N_BATCHES])
     tree.poll()
     barrier()
     launches0 = int(_lib.lib().st_kernel_launches())
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    windows = []
+    t_w0 = time.time()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * steps + 1)]
     ev[0].record()
     for k in range(steps):
@@ -276,7 +292,7 @@ def run_ours(args):
         ev[2 * k + 2].record()
     barrier()
     launches = int(_lib.lib().st_kernel_launches()) - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    windows.append((t_w0, time.time()))
     total_ms = ev[0].elapsed_time(ev[-1])
     upd_ms = sum(ev[2 * k].elapsed_time(ev[2 * k + 1]) for k in range(steps))
     smp_ms = sum(ev[2 * k + 1].elapsed_time(ev[2 * k + 2]) for k in range(steps))
@@ -297,13 +313,27 @@ def run_ours(args):
         e2e_step(w)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_w0 = time.time()
     e0.record()
     for k in range(steps):
         e2e_step(k)
     e1.record()
     barrier()
+    windows.append((t_w0, time.time()))
     e2e_ms = e0.elapsed_time(e1)
     tree.poll()
+    clocks = sampler.stop(windows) if rank == 0 else None
+
+    # ---- per-kernel durations of the update pipeline (CUDA events on the launching stream) -------
+    breakdown = None
+    if world == 1:
+        tree.handle.set_profiling(True)
+        for k in range(min(steps, 10)):
+            i, v, u = dbatches[k % N_BATCHES]
+            tree.update_(i, v)
+        torch.cuda.synchronize()
+        breakdown = tree.handle.update_breakdown()
+        tree.handle.set_profiling(False)
 
     times = torch.tensor([total_ms, upd_ms, smp_ms, e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -323,9 +353,23 @@ def run_ours(args):
                     "traffic": None, "algorithmic_bytes_per_unit": per_unit, "peak_source": peak_src,
                     "ms_per_launch": ms_per_launch}
 
-        r_upd = roof("update pipeline (sort + leaf pass + ordered per-level folds)", bu, m_local, upd_ms / steps)
+        r_upd = roof("update pipeline, all kernels (sort + leaf pass + partition + ordered folds)", bu, m_local,
+                     upd_ms / steps)
         r_smp = roof("search_kernel<float, staged, uniform>", bs, m_local, smp_ms / steps)
+        traffic = ncu_traffic()
+        r_smp["traffic"] = traffic.get("search_kernel")
         dominant = r_upd if upd_ms >= smp_ms else r_smp
+        if breakdown and breakdown["calls"]:
+            phases = {"partition_levels_kernel": breakdown["partition_ms"], "fold_scan_kernel": breakdown["fold_scan_ms"],
+                      "fold_huge_maps_kernel": breakdown["huge_maps_ms"], "fold_huge_apply_kernel": breakdown["huge_apply_ms"],
+                      "leaf_pass_kernel": breakdown["leaf_pass_ms"], "search_kernel": smp_ms / steps}
+            top = max(phases, key=phases.get)
+            if top != "search_kernel":
+                # the update's algorithmic bytes (236 B/update) are charged to its dominant kernel
+                dominant = roof(f"{top}<float> (dominant kernel of the update; all 236 B/update charged to it)", bu,
+                                m_local, phases[top])
+                dominant["traffic"] = traffic.get(top)
+                dominant["share_of_step"] = phases[top] / (total_ms / steps)
         line = {
             "metric": METRIC, "value": ops_per_step * steps / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": steps, "warmup": warmup, "ms_per_step": total_ms / steps, "higher_is_better": True,
@@ -337,7 +381,7 @@ def run_ours(args):
             "e2e": {"value": ops_per_step * steps / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": m_global * (8 + 4 + 8), "d2h_bytes_per_step": m_global * 8,
                     "ms_per_step": e2e_ms / steps},
-            "gpu_launches": launches, "clocks": clocks,
+            "gpu_launches": launches, "clocks": clocks, "update_breakdown_ms": breakdown,
         }
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_arm(leaves_host, batches_host, steps=3, warmup=1)
@@ -352,7 +396,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -162,6 +162,14 @@ ST_API int st_axis_fold_host(const st_tree *t, int64_t A, int64_t R, int64_t C, 
  * (ST_OK if none) and optionally clears it. A failed batch is skipped as a whole. */
 ST_API int st_poll_status(st_tree *t, void *stream, int clear);
 
+/* Per-phase timing of the float update pipeline, measured with CUDA events on the launching
+ * stream.  While enabled every update call waits for its own completion (profiling only).
+ * out_ms[0..5] = accumulated milliseconds of: key build + leaf-order sort, leaf pass, top-down
+ * partition kernel, huge-segment summaries, huge-segment stitch, ordered-fold kernel;
+ * out_ms[7] = number of update chunks accumulated. */
+ST_API int st_set_profiling(st_tree *t, int enable);
+ST_API int st_update_breakdown(const st_tree *t, double out_ms[8]);
+
 /* statistics of the most recent float update (for profiling; all zeros for int trees):
  * out[0]=segments resolved by the exact order-independent fast path,
  * out[1]=segments folded sequentially, out[2]=elements in those, out[3]=longest chain */

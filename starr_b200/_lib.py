@@ -95,6 +95,8 @@ _SIGNATURES = {
     "st_axis_fold_host": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p]),
     "st_poll_status": (c_int, [c_void_p, c_void_p, c_int]),
     "st_update_stats": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "st_set_profiling": (c_int, [c_void_p, c_int]),
+    "st_update_breakdown": (c_int, [c_void_p, c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
@@ -276,6 +278,18 @@ class TreeHandle:
 
     def poll_status(self, stream: int = 0, clear: bool = True) -> None:
         check(lib().st_poll_status(self.ptr, c_void_p(stream), 1 if clear else 0))
+
+    def set_profiling(self, enable: bool) -> None:
+        check(lib().st_set_profiling(self.ptr, 1 if enable else 0))
+
+    def update_breakdown(self) -> dict:
+        out = (ctypes.c_double * 8)()
+        check(lib().st_update_breakdown(self.ptr, out))
+        names = ("sort_ms", "leaf_pass_ms", "partition_ms", "huge_maps_ms", "huge_apply_ms", "fold_scan_ms")
+        calls = max(out[7], 1.0)
+        d = {n: out[i] / calls for i, n in enumerate(names)}
+        d["calls"] = int(out[7])
+        return d
 
     def update_stats(self, stream: int = 0) -> dict:
         out = (c_int64 * 4)()

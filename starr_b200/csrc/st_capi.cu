@@ -164,6 +164,8 @@ int st_destroy(st_tree *t)
     if (t->d_status) cudaFree(t->d_status);
     if (t->h_status) cudaFreeHost(t->h_status);
     if (t->ws.base) cudaFree(t->ws.base);
+    for (int k = 0; k < 8; ++k)
+        if (t->prof_ev[k]) cudaEventDestroy(t->prof_ev[k]);
     delete t;
     return ST_OK;
 }
@@ -451,6 +453,24 @@ int st_poll_status(st_tree *t, void *stream, int clear)
     device_guard g(t->device);
     const int st = fetch_status(t, (cudaStream_t)stream, clear != 0);
     if (st != ST_OK) return fail(st, "%s", st_status_string(st));
+    return ST_OK;
+}
+
+int st_set_profiling(st_tree *t, int enable)
+{
+    if (!t) return fail(ST_ERR_ARG, "st_set_profiling: NULL tree");
+    device_guard g(t->device);
+    if (enable && !t->prof_ev[0])
+        for (int k = 0; k < 8; ++k) CU(cudaEventCreate(&t->prof_ev[k]));
+    t->profile = enable ? 1 : 0;
+    for (int k = 0; k < 8; ++k) t->prof_ms[k] = 0.0;
+    return ST_OK;
+}
+
+int st_update_breakdown(const st_tree *t, double out_ms[8])
+{
+    if (!t || !out_ms) return fail(ST_ERR_ARG, "st_update_breakdown: bad argument");
+    for (int k = 0; k < 8; ++k) out_ms[k] = t->prof_ms[k];
     return ST_OK;
 }
 

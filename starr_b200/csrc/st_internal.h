@@ -30,6 +30,10 @@ struct st_tree {
     int64_t reserved_batch = 0;
     int sm_count = 148;
     int coop_ok = 0;
+    // optional per-phase timing of the update pipeline (st_set_profiling)
+    int profile = 0;
+    cudaEvent_t prof_ev[8] = {};
+    double prof_ms[8] = {};   // sort, leaf pass, partition, huge maps, huge apply, fold scan, (spare), calls
 };
 
 // launchers implemented in the .cu files; every one only enqueues on `s`

@@ -444,6 +444,8 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
     unsigned int *status = t->d_status;
     const unsigned g = (unsigned)((m + 255) / 256);
 
+    auto mark = [&](int k) { if (t->profile) cudaEventRecord(t->prof_ev[k], s); };
+    mark(0);
     ++g_kernel_launches;
     make_keys_kernel<<<g, 256, 0, s>>>(idx, m, n, depth, w.keys_a, w.kj, w.j_a, status);
     size_t cb = w.cub_bytes;
@@ -452,6 +454,7 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
     if (!deltas_in) {
         e = cub::DeviceRadixSort::SortPairs(w.cub_tmp, cb, w.keys_a, w.keys_b, w.j_a, w.j_b, m, 0, depth + 1, s);
         if (e != cudaSuccess) return e;
+        mark(1);
         ++g_kernel_launches;
         leaf_pass_kernel<T><<<g, 256, 0, s>>>(H, n, w.keys_b, w.j_b, m, vals, (uint64_t)nv, (uint64_t)j0,
                                               (T *)w.dj, (T *)w.ds, status);
@@ -473,6 +476,7 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
         // Level 0 order = batch order: (kj, dj).  Level l+1 order = stable sort of level l by
         // the top l+1 key bits.  lev_d[l] keeps every level's ordered d for the long folds.
         T *lev = (T *)w.lev_d;
+        mark(2);
         e = cudaMemcpyAsync(lev, d_batch, (size_t)m * sizeof(T), cudaMemcpyDeviceToDevice, s);
         if (e != cudaSuccess) return e;
         static const bool use_v1 = getenv("ST_UPDATE_V1") != nullptr;   // A/B switch: per-level cub sorts
@@ -518,11 +522,25 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
         }
         using REC = chunk_rec<typename fp_bits<T>::I>;
         g_kernel_launches += 3;
+        mark(3);
         fold_huge_maps_kernel<T><<<t->sm_count * 2, FOLD_THREADS, 0, s>>>(H, lev, B, w.queue_huge, w.huge_off,
                                                                          (REC *)w.huge_recs, status);
+        mark(4);
         fold_huge_apply_kernel<T><<<t->sm_count, FOLD_THREADS, 0, s>>>(H, lev, B, w.queue_huge, w.huge_off,
                                                                       (const REC *)w.huge_recs, status);
+        mark(5);
         fold_scan_kernel<T><<<t->sm_count * 8, FOLD_THREADS, 0, s>>>(H, lev, B, w.queue, w.queue_med, status);
+        mark(6);
+        if (t->profile) {
+            // profiling mode is synchronous by design (bench.py's roofline leg only)
+            cudaEventSynchronize(t->prof_ev[6]);
+            for (int k = 0; k < 6; ++k) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, t->prof_ev[k], t->prof_ev[k + 1]);
+                t->prof_ms[k] += ms;
+            }
+            t->prof_ms[7] += 1.0;
+        }
         return cudaGetLastError();
     }
 }
