@@ -235,6 +235,8 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # keep stdout to the single JSON line (the box may export NCCL_DEBUG=VERSION, which prints there)
+        os.environ["NCCL_DEBUG"] = os.environ.get("ST_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=dev)
 
     n_local = 1 << LOG2_LEAVES
