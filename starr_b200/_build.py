@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libstarr_b200.so")
 SOURCES = ["st_tree_kernels.cu", "st_update.cu", "st_capi.cu"]
-HEADERS = ["st_common.cuh", "st_internal.h", "st_ordered_fold.cuh", "st_partition.cuh", "st_update_defs.cuh", os.path.join("..", "..", "include", "starr_b200.h")]
+HEADERS = ["st_common.cuh", "st_internal.h", "st_ordered_fold.cuh", "st_partition.cuh", "st_update_defs.cuh", "st_update_small.cuh", os.path.join("..", "..", "include", "starr_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -19,6 +19,7 @@ FLAGS = [
     "-fmad=false",            # float parity: never contract a*b+c
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
     "--expt-relaxed-constexpr",
+    *(["-DST_SMALL_TIMING"] if os.environ.get("ST_SMALL_TIMING") else []),
     "-Xptxas", "-v" if os.environ.get("ST_PTXAS_V") else "-O3",
 ]
 

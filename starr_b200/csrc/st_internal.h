@@ -28,6 +28,8 @@ struct st_tree {
     unsigned int *h_status = nullptr;  // pinned host mirror, 64 words
     st_workspace ws;
     int64_t reserved_batch = 0;
+    int64_t cub_cap = -1;      // batch capacity for which cub_bytes was queried
+    size_t cub_bytes = 0;
     int sm_count = 148;
     int coop_ok = 0;
     // optional per-phase timing of the update pipeline (st_set_profiling)

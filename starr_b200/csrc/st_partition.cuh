@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(PART_THREADS) partition_levels_kernel(part_par
     // ---- P0: zero counts of the first split bit per tile; clear the other counter set -----------
     for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
         unsigned int z = 0;
-        if (depth >= 2) {
+        if (depth >= 2 && m > SHORT_SEG) {
 #pragma unroll
             for (int k = 0; k < PART_E; ++k) {
                 const int i = t * PART_TILE + tid * PART_E + k;
@@ -132,7 +132,8 @@ __global__ void __launch_bounds__(PART_THREADS) partition_levels_kernel(part_par
             __syncthreads();
         }
 
-        // ---- P1: folds by segment heads; publish Z --------------------------------------------------
+        // ---- P1: segment heads fold / retire / queue; publish Z ------------------------------------------
+        if (blockIdx.x == 0 && tid == 0) p.status[SW_ANYLONG + ((l + 1) & 1)] = 0;
         for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
             unsigned int zloc[PART_E], zsum = 0;
 #pragma unroll
@@ -140,28 +141,34 @@ __global__ void __launch_bounds__(PART_THREADS) partition_levels_kernel(part_par
                 const int i = t * PART_TILE + tid * PART_E + k;
                 zloc[k] = 0;
                 if (i < m) {
-                    const uint32_t ky = key[i];
-                    const int s = (l == 0) ? 0 : sC[i];
-                    if (i == s && l < key_leaf_level(ky, two_n, depth)) {
-                        const int e = (l == 0) ? m : eC[i];
+                    const int eraw = (l == 0) ? m : eC[i];
+                    if (!(eraw & SEG_DONE)) {
+                        const int s = (l == 0) ? 0 : sC[i];
+                        const int e = eraw;
                         const int len = e - s;
-                        const uint32_t node = ky >> sh;
+                        const uint32_t ky = key[i];
                         if (len <= SHORT_SEG) {
-                            T acc = p.H[node];
-                            for (int x = s; x < e; ++x) acc = t_add<T>(acc, dC[x]);
-                            p.H[node] = acc;
-                        } else if (len > HUGE_SEG) {
-                            const unsigned int slot = atomicAdd(p.status + SW_QCOUNT_HUGE, 1u);
-                            p.qhuge[slot] = seg_entry{l, s, len, node};
-                            p.huge_off[slot] = (int)atomicAdd(p.status + SW_HUGE_CHUNKS,
-                                                              (unsigned int)((len + 1023) / 1024));
-                        } else if (len > MEDIUM_SEG) {
-                            p.qlong[atomicAdd(p.status + SW_QCOUNT, 1u)] = seg_entry{l, s, len, node};
+                            if (i == s)
+                                retire_segment<T>(p.H, s, e, l, depth, two_n, [&](int x) { return key[x]; },
+                                                  [&](int x) { return dC[x]; });
                         } else {
-                            p.qmed[atomicAdd(p.status + SW_QCOUNT_MED, 1u)] = seg_entry{l, s, len, node};
+                            if (i == s && l < key_leaf_level(ky, two_n, depth)) {
+                                const uint32_t node = ky >> sh;
+                                if (len > HUGE_SEG) {
+                                    const unsigned int slot = atomicAdd(p.status + SW_QCOUNT_HUGE, 1u);
+                                    p.qhuge[slot] = seg_entry{l, s, len, node};
+                                    p.huge_off[slot] = (int)atomicAdd(p.status + SW_HUGE_CHUNKS,
+                                                                      (unsigned int)((len + 1023) / 1024));
+                                } else if (len > MEDIUM_SEG) {
+                                    p.qlong[atomicAdd(p.status + SW_QCOUNT, 1u)] = seg_entry{l, s, len, node};
+                                } else {
+                                    p.qmed[atomicAdd(p.status + SW_QCOUNT_MED, 1u)] = seg_entry{l, s, len, node};
+                                }
+                            }
+                            if (i == s) p.status[SW_ANYLONG + (l & 1)] = 1;   // another split is needed
+                            if (!last) zloc[k] = ((ky >> (sh - 1)) & 1u) ^ 1u;
                         }
                     }
-                    if (!last) zloc[k] = ((ky >> (sh - 1)) & 1u) ^ 1u;
                 }
                 zsum += zloc[k];
             }
@@ -179,9 +186,10 @@ __global__ void __launch_bounds__(PART_THREADS) partition_levels_kernel(part_par
         }
         if (last) break;
         grid.sync();
+        if (((volatile unsigned int *)p.status)[SW_ANYLONG + (l & 1)] == 0) break;   // only retired segments are left (grid-uniform)
 
-        // ---- P2: stable split of every segment by the next key bit ----------------------------------
-        const bool need_next = (l + 1 < depth - 1);   // level l+1 will split again by bit sh-2
+        // ---- P2: stable split of every long segment by the next key bit ------------------------------------
+        const bool need_next = (l + 1 < depth - 1);   // level l+1 may split again by bit sh-2
         for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
 #pragma unroll
             for (int k = 0; k < PART_E; ++k) {
@@ -190,28 +198,36 @@ __global__ void __launch_bounds__(PART_THREADS) partition_levels_kernel(part_par
                 int np = 0;
                 unsigned int znext = 0;
                 if (live) {
-                    const uint32_t ky = key[i];
+                    const int eraw = (l == 0) ? m : eC[i];
                     const int s = (l == 0) ? 0 : sC[i];
-                    const int e = (l == 0) ? m : eC[i];
-                    const int zs = p.Z[s];
-                    const int ze = (e < m) ? p.Z[e] : (int)ztotal;
-                    const int zb = p.Z[i] - zs;      // zero-bit elements of my segment before me
-                    const int nz = ze - zs;          // zero-bit elements of my segment
-                    int s2, e2;
-                    if (((ky >> (sh - 1)) & 1u) == 0) {
-                        np = s + zb;
-                        s2 = s;
-                        e2 = s + nz;
+                    const int e = eraw & ~SEG_DONE;
+                    if ((eraw & SEG_DONE) || e - s <= SHORT_SEG) {
+                        // retired: stays where it is, nobody reads its key / difference again
+                        np = i;
+                        sN[i] = s;
+                        eN[i] = e | SEG_DONE;
                     } else {
-                        np = s + nz + (i - s - zb);
-                        s2 = s + nz;
-                        e2 = e;
+                        const uint32_t ky = key[i];
+                        const int zs = p.Z[s];
+                        const int ze = (e < m) ? p.Z[e] : (int)ztotal;
+                        const int zb = p.Z[i] - zs;      // zero-bit elements of my segment before me
+                        const int nz = ze - zs;          // zero-bit elements of my segment
+                        int s2, e2;
+                        if (((ky >> (sh - 1)) & 1u) == 0) {
+                            np = s + zb;
+                            s2 = s;
+                            e2 = s + nz;
+                        } else {
+                            np = s + nz + (i - s - zb);
+                            s2 = s + nz;
+                            e2 = e;
+                        }
+                        keyN[np] = ky;
+                        dN[np] = dC[i];
+                        sN[np] = s2;
+                        eN[np] = e2;
+                        if (need_next && e2 - s2 > SHORT_SEG) znext = ((ky >> (sh - 2)) & 1u) ^ 1u;
                     }
-                    keyN[np] = ky;
-                    dN[np] = dC[i];
-                    sN[np] = s2;
-                    eN[np] = e2;
-                    if (need_next) znext = ((ky >> (sh - 2)) & 1u) ^ 1u;
                 }
                 if (need_next) {
                     // one atomic per (warp, destination tile)

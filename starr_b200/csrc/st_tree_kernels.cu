@@ -139,8 +139,10 @@ cudaError_t launch_build(st_tree *t, cudaStream_t s)
 // in flight per thread.  The top of the tree (heap[0 .. stage_nodes)) is staged once per
 // CTA into shared memory with a TMA bulk copy (cp.async.bulk + mbarrier); deeper levels are
 // read-only gathers through L1/L2 (ld.global.nc).
-constexpr int SEARCH_THREADS = 512;
-constexpr int SEARCH_Q = 4;
+// large batches: 512 threads x 4 queries per thread; small batches: 128 threads x 1 query so that
+// a 4096-query PER step still spreads over 32 SMs
+constexpr int SEARCH_THREADS_BIG = 512, SEARCH_Q_BIG = 4;
+constexpr int SEARCH_THREADS_SMALL = 128, SEARCH_Q_SMALL = 1;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
 {
@@ -196,7 +198,7 @@ template <typename T> __device__ __forceinline__ T scale_uniform(T root, double 
     }
 }
 
-template <typename T, bool STAGE, bool UNIFORM>
+template <typename T, bool STAGE, bool UNIFORM, int SEARCH_THREADS, int SEARCH_Q>
 __global__ void __launch_bounds__(SEARCH_THREADS)
 search_kernel(const T *__restrict__ H, uint32_t n, int depth, const void *__restrict__ in,
               int64_t m, int64_t *__restrict__ out, T *__restrict__ prio, T *__restrict__ resid,
@@ -262,18 +264,17 @@ search_kernel(const T *__restrict__ H, uint32_t n, int depth, const void *__rest
     }
 }
 
-template <typename T, bool UNIFORM>
-static cudaError_t launch_search_t(const st_tree *t, const void *in, int64_t m, int64_t *out, void *prio,
-                                   void *resid, cudaStream_t s)
+template <typename T, bool UNIFORM, int THREADS, int Q>
+static cudaError_t launch_search_cfg(const st_tree *t, const void *in, int64_t m, int64_t *out, void *prio,
+                                     void *resid, cudaStream_t s)
 {
-    if (m <= 0) return cudaSuccess;
     const uint32_t n = (uint32_t)t->n;
     const T *H = (const T *)t->heap;
-    const int64_t per_block = (int64_t)SEARCH_THREADS * SEARCH_Q;
-    // stage the top 64 KiB of the heap when there are enough queries to amortise it
+    const int64_t per_block = (int64_t)THREADS * Q;
+    // stage the top 64 KiB of the heap (TMA bulk copy) when every CTA has enough queries to amortise it
     uint32_t stage_nodes = 65536u / (uint32_t)sizeof(T);
     const uint64_t two_n = 2ull * n;
-    bool stage = m >= 16 * per_block;
+    bool stage = m >= 2048;
     if (two_n < stage_nodes) {
         // whole heap fits: round down to a multiple of 16 bytes (the tail is read from global)
         stage_nodes = (uint32_t)(two_n * sizeof(T) / 16 * 16 / sizeof(T));
@@ -281,7 +282,7 @@ static cudaError_t launch_search_t(const st_tree *t, const void *in, int64_t m, 
     }
     if (stage) {
         const size_t smem = (size_t)stage_nodes * sizeof(T);
-        auto kern = search_kernel<T, true, UNIFORM>;
+        auto kern = search_kernel<T, true, UNIFORM, THREADS, Q>;
         static bool attr_done = false;
         if (!attr_done) {
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
@@ -290,14 +291,24 @@ static cudaError_t launch_search_t(const st_tree *t, const void *in, int64_t m, 
         }
         unsigned g = grid_for(m, (int)per_block, (int64_t)t->sm_count * 3);
         ++g_kernel_launches;
-        kern<<<g, SEARCH_THREADS, smem, s>>>(H, n, t->depth, in, m, out, (T *)prio, (T *)resid, stage_nodes);
+        kern<<<g, THREADS, smem, s>>>(H, n, t->depth, in, m, out, (T *)prio, (T *)resid, stage_nodes);
     } else {
         unsigned g = grid_for(m, (int)per_block, (int64_t)t->sm_count * 4);
         ++g_kernel_launches;
-        search_kernel<T, false, UNIFORM><<<g, SEARCH_THREADS, 0, s>>>(H, n, t->depth, in, m, out, (T *)prio,
-                                                                      (T *)resid, 0);
+        search_kernel<T, false, UNIFORM, THREADS, Q><<<g, THREADS, 0, s>>>(H, n, t->depth, in, m, out, (T *)prio,
+                                                                          (T *)resid, 0);
     }
     return cudaGetLastError();
+}
+
+template <typename T, bool UNIFORM>
+static cudaError_t launch_search_t(const st_tree *t, const void *in, int64_t m, int64_t *out, void *prio,
+                                   void *resid, cudaStream_t s)
+{
+    if (m <= 0) return cudaSuccess;
+    if (m >= (int64_t)t->sm_count * SEARCH_THREADS_BIG * SEARCH_Q_BIG / 4)
+        return launch_search_cfg<T, UNIFORM, SEARCH_THREADS_BIG, SEARCH_Q_BIG>(t, in, m, out, prio, resid, s);
+    return launch_search_cfg<T, UNIFORM, SEARCH_THREADS_SMALL, SEARCH_Q_SMALL>(t, in, m, out, prio, resid, s);
 }
 
 cudaError_t launch_search(const st_tree *t, const void *vals, int64_t m, int64_t *out, cudaStream_t s)

@@ -31,6 +31,7 @@
 #include "st_update_defs.cuh"
 #include "st_ordered_fold.cuh"
 #include "st_partition.cuh"
+#include "st_update_small.cuh"
 
 namespace st {
 
@@ -47,6 +48,7 @@ struct update_ws {
     int *huge_off;
     void *huge_recs;
     int *seg_sa, *seg_ea, *seg_sb, *seg_eb, *zcount;
+    uint32_t *ret_key, *ret_se;
     unsigned int *tilesum;
     void *cub_tmp;
     size_t cub_bytes;
@@ -85,18 +87,25 @@ static update_ws carve(const st_tree *t, int64_t B, char *base)
         w.seg_sb = (int *)take(B * 4);
         w.seg_eb = (int *)take(B * 4);
         w.zcount = (int *)take(B * 4);
+        w.ret_key = (uint32_t *)take((size_t)(t->depth + 1) * SMALL_M * 4);
+        w.ret_se = (uint32_t *)take((size_t)(t->depth + 1) * SMALL_M * 4);
         w.tilesum = (unsigned int *)take(2 * PART_MAX_TILES * sizeof(unsigned int));
     }
-    size_t cb1 = 0, cb2 = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, cb1, (const uint32_t *)nullptr, (uint32_t *)nullptr,
-                                    (const int *)nullptr, (int *)nullptr, (int)B, 0, 32, (cudaStream_t)0);
-    if (t->dtype == ST_F64)
-        cub::DeviceRadixSort::SortPairs(nullptr, cb2, (const uint32_t *)nullptr, (uint32_t *)nullptr,
-                                        (const double *)nullptr, (double *)nullptr, (int)B, 0, 32, (cudaStream_t)0);
-    else if (t->dtype == ST_F32)
-        cub::DeviceRadixSort::SortPairs(nullptr, cb2, (const uint32_t *)nullptr, (uint32_t *)nullptr,
-                                        (const float *)nullptr, (float *)nullptr, (int)B, 0, 32, (cudaStream_t)0);
-    w.cub_bytes = cb1 > cb2 ? cb1 : cb2;
+    if (t->cub_cap != B) {
+        // temp-storage queries are host-side work: do them once per capacity, not once per call
+        size_t cb1 = 0, cb2 = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, cb1, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+                                        (const int *)nullptr, (int *)nullptr, (int)B, 0, 32, (cudaStream_t)0);
+        if (t->dtype == ST_F64)
+            cub::DeviceRadixSort::SortPairs(nullptr, cb2, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+                                            (const double *)nullptr, (double *)nullptr, (int)B, 0, 32, (cudaStream_t)0);
+        else if (t->dtype == ST_F32)
+            cub::DeviceRadixSort::SortPairs(nullptr, cb2, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+                                            (const float *)nullptr, (float *)nullptr, (int)B, 0, 32, (cudaStream_t)0);
+        const_cast<st_tree *>(t)->cub_bytes = cb1 > cb2 ? cb1 : cb2;
+        const_cast<st_tree *>(t)->cub_cap = B;
+    }
+    w.cub_bytes = t->cub_bytes;
     w.cub_tmp = take(w.cub_bytes);
     w.total = off;
     return w;
@@ -138,7 +147,8 @@ __global__ void __launch_bounds__(256) make_keys_kernel(const int64_t *__restric
     if (status[SW_STATUS]) return;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j == 0) { status[SW_QCOUNT] = 0; status[SW_QTAKE] = 0; status[SW_QCOUNT_MED] = 0; status[SW_QTAKE_MED] = 0;
-                  status[SW_QCOUNT_HUGE] = 0; status[SW_HUGE_CHUNKS] = 0; status[SW_QTAKE_HUGE] = 0; }
+                  status[SW_QCOUNT_HUGE] = 0; status[SW_HUGE_CHUNKS] = 0; status[SW_QTAKE_HUGE] = 0;
+                  status[SW_ANYLONG] = 0; status[SW_ANYLONG + 1] = 0; }
     if (j >= m) return;
     const uint32_t h = (uint32_t)idx[j] + n;
     const uint32_t key = h << (depth - heap_level(h));
@@ -294,7 +304,7 @@ __global__ void __launch_bounds__(FOLD_THREADS) fold_scan_kernel(T *__restrict__
                                                                  int64_t level_stride,
                                                                  const seg_entry *__restrict__ queue_long,
                                                                  const seg_entry *__restrict__ queue_med,
-                                                                 unsigned int *status)
+                                                                 unsigned int *status, retire_params<T> ret)
 {
     if (status[SW_STATUS]) return;
     using I = typename fp_bits<T>::I;
@@ -302,6 +312,23 @@ __global__ void __launch_bounds__(FOLD_THREADS) fold_scan_kernel(T *__restrict__
     __shared__ I s_mviol;
     __shared__ fold_smem_ctl ctl;
     __shared__ T s_stage[FOLD_THREADS / 32][FOLDW_PAD];
+    if (ret.key) {
+        // small-batch path: retire the short segments the single-CTA kernel marked (st_update_small.cuh)
+        const unsigned int mask = status[SW_RETIRE_MASK];
+        const uint64_t two_n = 2ull * ret.n;
+        for (int l = 0; l < ret.depth; ++l) {
+            if (!((mask >> l) & 1u)) continue;
+            const uint32_t *kl = ret.key + (size_t)l * ret.stride, *sl = ret.se + (size_t)l * ret.stride;
+            const T *dl = lev_d + (int64_t)l * level_stride;
+            for (int i = blockIdx.x * FOLD_THREADS + threadIdx.x; i < ret.m; i += gridDim.x * FOLD_THREADS) {
+                const uint32_t se = sl[i];
+                const int s = (int)(se & 0xffffu), e = (int)((se >> 16) & 0x7fffu);
+                if (!(se & 0x80000000u) && i == s && e - s <= SHORT_SEG)
+                    retire_segment<T>(H, s, e, l, ret.depth, two_n, [&](int x) { return kl[x]; },
+                                      [&](int x) { return dl[x]; });
+            }
+        }
+    }
     const unsigned int n_long = status[SW_QCOUNT];
     for (;;) {
         __syncthreads();
@@ -434,7 +461,7 @@ __global__ void __launch_bounds__(FOLD_THREADS) fold_huge_apply_kernel(T *__rest
 template <typename T>
 static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *idx, int m, const T *vals,
                                 int64_t nv, int64_t j0, int64_t B, T *delta_out, const T *deltas_in,
-                                cudaStream_t s)
+                                bool small, cudaStream_t s)
 {
     // deltas_in != nullptr: "apply deltas" mode (sharded top tree): the per-update
     // differences are given, the leaves are not touched, only proper ancestors are folded.
@@ -445,6 +472,29 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
     const unsigned g = (unsigned)((m + 255) / 256);
 
     auto mark = [&](int k) { if (t->profile) cudaEventRecord(t->prof_ev[k], s); };
+    if constexpr (is_float_t<T>::value) {
+        if (small) {
+            // one CTA does validation, sort, leaf pass and the whole ordered partition (st_update_small.cuh)
+            small_params<T> sp;
+            sp.H = H; sp.n = n; sp.depth = depth; sp.m = m; sp.idx = idx; sp.vals = vals;
+            sp.nv = (uint64_t)nv; sp.j0 = (uint64_t)j0; sp.deltas_in = deltas_in; sp.delta_out = delta_out;
+            sp.lev_d = (T *)w.lev_d; sp.lev_stride = B; sp.qlong = w.queue; sp.qmed = w.queue_med; sp.status = status;
+            static bool attr_done = false;
+            if (!attr_done) {
+                cudaError_t ea = cudaFuncSetAttribute(update_small_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                      (int)small_smem_bytes<T>());
+                if (ea != cudaSuccess) return ea;
+                attr_done = true;
+            }
+            g_kernel_launches += 2;
+            sp.ret_key = w.ret_key; sp.ret_se = w.ret_se;
+            update_small_kernel<T><<<1, SMALL_THREADS, small_smem_bytes<T>(), s>>>(sp);
+            retire_params<T> rp{w.ret_key, w.ret_se, m, depth, SMALL_M, n};
+            fold_scan_kernel<T><<<t->sm_count, FOLD_THREADS, 0, s>>>(H, (const T *)w.lev_d, B, w.queue, w.queue_med,
+                                                                    status, rp);
+            return cudaGetLastError();
+        }
+    }
     mark(0);
     ++g_kernel_launches;
     make_keys_kernel<<<g, 256, 0, s>>>(idx, m, n, depth, w.keys_a, w.kj, w.j_a, status);
@@ -529,7 +579,8 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
         fold_huge_apply_kernel<T><<<t->sm_count, FOLD_THREADS, 0, s>>>(H, lev, B, w.queue_huge, w.huge_off,
                                                                       (const REC *)w.huge_recs, status);
         mark(5);
-        fold_scan_kernel<T><<<t->sm_count * 8, FOLD_THREADS, 0, s>>>(H, lev, B, w.queue, w.queue_med, status);
+        fold_scan_kernel<T><<<t->sm_count * 8, FOLD_THREADS, 0, s>>>(H, lev, B, w.queue, w.queue_med, status,
+                                                                        retire_params<T>{nullptr, nullptr, 0, 0, 0, 0});
         mark(6);
         if (t->profile) {
             // profiling mode is synchronous by design (bench.py's roofline leg only)
@@ -577,15 +628,18 @@ cudaError_t launch_update(st_tree *t, const int64_t *idx, int64_t ni, const void
     }
     t->reserved_batch = cap;
     ST_DISPATCH(t->dtype, {
-        ++g_kernel_launches;
-        validate_kernel<T><<<grid_for(ni > nv ? ni : nv, 256, (int64_t)t->sm_count * 8), 256, 0, s>>>(
-            idx, ni, (const T *)vals, deltas_in ? 0 : nv, t->n, t->d_status);
+        const bool small = is_float_t<T>::value && !t->profile && ni <= SMALL_M && (deltas_in || nv <= SMALL_M);
+        if (!small) {
+            ++g_kernel_launches;
+            validate_kernel<T><<<grid_for(ni > nv ? ni : nv, 256, (int64_t)t->sm_count * 8), 256, 0, s>>>(
+                idx, ni, (const T *)vals, deltas_in ? 0 : nv, t->n, t->d_status);
+        }
         update_ws w = carve(t, cap, (char *)t->ws.base);
         for (int64_t j0 = 0; j0 < ni; j0 += cap) {
             const int m = (int)(ni - j0 < cap ? ni - j0 : cap);
             cudaError_t e = update_chunk<T>(t, w, idx + j0, m, (const T *)vals, nv, j0, cap,
                                             delta_out ? (T *)delta_out + j0 : nullptr,
-                                            deltas_in ? (const T *)deltas_in + j0 : nullptr, s);
+                                            deltas_in ? (const T *)deltas_in + j0 : nullptr, small, s);
             if (e != cudaSuccess) return e;
         }
     });

@@ -17,7 +17,7 @@ struct seg_entry {
 };
 
 // status-word layout (unsigned int[64])
-enum { SW_STATUS = 0, SW_QCOUNT = 1, SW_QTAKE = 2, SW_QCOUNT_MED = 8, SW_QTAKE_MED = 9, SW_QCOUNT_HUGE = 10, SW_HUGE_CHUNKS = 11, SW_QTAKE_HUGE = 12, SW_STAT_FAST = 4, SW_STAT_CHAINS = 5, SW_STAT_CHAIN_ELEMS = 6, SW_STAT_LONGEST = 7 };
+enum { SW_STATUS = 0, SW_QCOUNT = 1, SW_QTAKE = 2, SW_QCOUNT_MED = 8, SW_QTAKE_MED = 9, SW_QCOUNT_HUGE = 10, SW_HUGE_CHUNKS = 11, SW_QTAKE_HUGE = 12, SW_ANYLONG = 14 /* and 15 */, SW_RETIRE_MASK = 16, SW_STAT_FAST = 4, SW_STAT_CHAINS = 5, SW_STAT_CHAIN_ELEMS = 6, SW_STAT_LONGEST = 7 };
 
 // -----------------------------------------------------------------------------------------
 // key helpers.  key = heap index of the leaf, shifted left so that its top bit sits at bit
@@ -27,5 +27,57 @@ enum { SW_STATUS = 0, SW_QCOUNT = 1, SW_QTAKE = 2, SW_QCOUNT_MED = 8, SW_QTAKE_M
 // -----------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t key_to_heap(uint32_t key, uint64_t two_n) { return key < two_n ? key : key >> 1; }
 __device__ __forceinline__ int key_leaf_level(uint32_t key, uint64_t two_n, int depth) { return key < two_n ? depth : depth - 1; }
+
+
+// One ordered add into a tree node: same-address atomics of ONE thread are performed in program
+// order and each is a single IEEE round-to-nearest add at the L2, so a thread that issues its adds
+// in batch order reproduces (((T + d0) + d1) + ...) exactly without ever waiting for T.
+// float32 global atomic adds flush subnormals (PTX atom.add.f32 / SASS REDG...FTZ): they are used
+// only for |d| >= 2^-100, where a subnormal T is absorbed identically and no subnormal result can
+// arise (both operands are then multiples of >= 2^-124); smaller non-zero d take an atomic CAS
+// (still ordered with the other atomics of this thread); d == 0 changes nothing and is skipped.
+template <typename T> __device__ __forceinline__ void ordered_add(T *ptr, T d)
+{
+    if (d == T(0)) return;
+    if constexpr (sizeof(T) == 4) {
+        if (fabsf(d) < 7.888609052210118e-31f) {  // 2^-100
+            unsigned int *u = reinterpret_cast<unsigned int *>(ptr);
+            unsigned int old = atomicOr(u, 0u), assumed;
+            do {
+                assumed = old;
+                old = atomicCAS(u, assumed, __float_as_uint(__fadd_rn(__uint_as_float(assumed), d)));
+            } while (old != assumed);
+            return;
+        }
+    }
+    atomicAdd(ptr, d);
+}
+
+// A segment of at most SHORT_SEG updates (in batch order) is finished by its head thread for
+// its node at level l AND every deeper level: the thread walks the updates in batch order and adds
+// each one to all of its remaining ancestors, so every node still sees its updates in batch order
+// and no further partitioning of this segment is needed.
+template <typename T, typename KEYAT, typename DAT>
+__device__ __forceinline__ void retire_segment(T *H, int s, int e, int l, int depth, uint64_t two_n, KEYAT keyat,
+                                               DAT dat)
+{
+    for (int x = s; x < e; ++x) {
+        const uint32_t kx = keyat(x);
+        const T dx = dat(x);
+        const int ll = key_leaf_level(kx, two_n, depth);
+        for (int l2 = l; l2 < ll; ++l2) ordered_add<T>(H + (kx >> (depth - l2)), dx);
+    }
+}
+
+constexpr int SEG_DONE = 1 << 30;
+
+// small-batch path: levels whose short segments are retired by the follow-up kernel (spread over
+// all SMs instead of one) keep their ordered keys / differences / segment bounds in global memory
+template <typename T> struct retire_params {
+    const uint32_t *key;   // [level][SMALL stride]
+    const uint32_t *se;    // packed s | e << 16 | done << 31
+    int m, depth, stride;
+    uint32_t n;
+};   // flag in the stored segment end: the segment has been retired
 
 }  // namespace st
