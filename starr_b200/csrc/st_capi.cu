@@ -316,6 +316,13 @@ int st_apply_deltas_device(st_tree *t, const int64_t *idx_dev, int64_t ni, const
     if (!t || ni < 0 || (ni > 0 && !deltas_dev)) return fail(ST_ERR_ARG, "st_apply_deltas_device: bad argument");
     if (ni == 0) return ST_OK;
     device_guard g(t->device);
+    const bool is_float = (t->dtype == ST_F32 || t->dtype == ST_F64);
+    if (is_float && t->n <= 64 && (t->n & (t->n - 1)) == 0 && ni > 4096) {
+        // tiny tree, big batch (the sharded top tree): masked ordered fold per node, no sort / partition.
+        // Indices are trusted to be in range here (they are shard ids computed by the caller).
+        CU(st::launch_fold_by_leaf(t, idx_dev, deltas_dev, ni, (cudaStream_t)stream));
+        return ST_OK;
+    }
     CU(st::launch_update(t, idx_dev, ni, nullptr, 0, nullptr, deltas_dev, (cudaStream_t)stream));
     return ST_OK;
 }

@@ -60,5 +60,7 @@ size_t update_workspace_bytes(const st_tree *t, int64_t batch);
 cudaError_t launch_update(st_tree *t, const int64_t *idx, int64_t ni, const void *vals, int64_t nv,
                           void *delta_out, const void *deltas_in, cudaStream_t s);
 int64_t update_max_chunk();
+// tiny power-of-two float tree: ordered fold of all m differences into the ancestors of leaf[j]
+cudaError_t launch_fold_by_leaf(st_tree *t, const int64_t *leaf, const void *deltas, int64_t m, cudaStream_t s);
 
 }  // namespace st

@@ -245,6 +245,29 @@ __device__ __forceinline__ T seq_until_ready(T cur, int &p, int nc, LOAD load)
 //       chunk); an unsafe chunk, or any chunk after the exponent has changed, is folded exactly
 //       by the CTA driver above.
 // ---------------------------------------------------------------------------------------------
+// Update stream of one node of a tiny (power-of-two) tree seen through a membership mask:
+// element i counts for `node` iff node is an ancestor of leaf[i]; everything else reads as 0,
+// which is the identity of the fold (T + 0 == T).  Used for the replicated top tree of the
+// subtree-sharded layout, where all ranks' differences arrive as ONE batch-ordered vector.
+template <typename T> struct masked_src {
+    const T *d;
+    const int64_t *leaf;
+    int64_t nleaves;
+    uint32_t node;
+    int rshift;   // leaf level - level(node)
+    __device__ __forceinline__ T operator[](int64_t i) const
+    {
+        return ((uint32_t)((leaf[i] + nleaves) >> rshift) == node) ? d[i] : T(0);
+    }
+    __device__ __forceinline__ masked_src operator+(int64_t off) const
+    {
+        masked_src r = *this;
+        r.d += off;
+        r.leaf += off;
+        return r;
+    }
+};
+
 template <typename I> struct chunk_rec {
     I a0, a1;        // parity map of the whole chunk
     I min0, max0;    // extremes of (m_k - m_in) and (m_k + floor(x_k) - m_in), start parity even
@@ -253,8 +276,8 @@ template <typename I> struct chunk_rec {
     int pad;
 };
 
-template <typename T>
-__device__ void chunk_summary_cta(const T *__restrict__ src, int nc, int eT, chunk_rec<typename fp_bits<T>::I> *out,
+template <typename T, typename SRC>
+__device__ void chunk_summary_cta(SRC src, int nc, int eT, chunk_rec<typename fp_bits<T>::I> *out,
                                   typename fp_bits<T>::I (*s_wtot)[2], typename fp_bits<T>::I (*s_red)[4],
                                   float *s_abs)
 {
@@ -423,8 +446,8 @@ struct fold_smem_ctl {
     int pad;
 };
 
-template <typename T>
-__device__ T ordered_fold_cta(T cur, const T *__restrict__ src, int len,
+template <typename T, typename SRC>
+__device__ T ordered_fold_cta(T cur, SRC src, int len,
                               typename fp_bits<T>::I (*s_wtot)[2], typename fp_bits<T>::I *s_mviol,
                               fold_smem_ctl *ctl)
 {

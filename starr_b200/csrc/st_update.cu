@@ -356,13 +356,15 @@ __global__ void __launch_bounds__(FOLD_THREADS) fold_scan_kernel(T *__restrict__
 }
 
 // Huge segments, phase A: every CTA summarises chunks (see st_ordered_fold.cuh).
-template <typename T>
+template <typename T, bool MASKED>
 __global__ void __launch_bounds__(FOLD_THREADS) fold_huge_maps_kernel(const T *__restrict__ H, const T *__restrict__ lev_d,
                                                                       int64_t level_stride,
                                                                       const seg_entry *__restrict__ qhuge,
                                                                       const int *__restrict__ huge_off,
                                                                       chunk_rec<typename fp_bits<T>::I> *__restrict__ recs,
-                                                                      const unsigned int *status)
+                                                                      const unsigned int *status,
+                                                                      const int64_t *__restrict__ mleaf, int64_t mnleaves,
+                                                                      int mleaf_level)
 {
     if (status[SW_STATUS]) return;
     using I = typename fp_bits<T>::I;
@@ -389,19 +391,26 @@ __global__ void __launch_bounds__(FOLD_THREADS) fold_huge_maps_kernel(const T *_
             if (threadIdx.x == 0) recs[g].ok = 0;
             continue;
         }
-        chunk_summary_cta<T>(lev_d + (int64_t)s.level * level_stride + s.start + (int64_t)c * FOLD_CHUNK, nc, eT,
-                             recs + g, s_wtot, s_red, s_abs);
+        if constexpr (MASKED) {
+            const masked_src<T> ms{lev_d, mleaf, mnleaves, s.node, mleaf_level - s.level};
+            chunk_summary_cta<T>(ms + (int64_t)c * FOLD_CHUNK, nc, eT, recs + g, s_wtot, s_red, s_abs);
+        } else {
+            chunk_summary_cta<T>(lev_d + (int64_t)s.level * level_stride + s.start + (int64_t)c * FOLD_CHUNK, nc, eT,
+                                 recs + g, s_wtot, s_red, s_abs);
+        }
     }
 }
 
 // Huge segments, phase B: one CTA per segment walks the chunk summaries in order.
-template <typename T>
+template <typename T, bool MASKED>
 __global__ void __launch_bounds__(FOLD_THREADS) fold_huge_apply_kernel(T *__restrict__ H, const T *__restrict__ lev_d,
                                                                        int64_t level_stride,
                                                                        const seg_entry *__restrict__ qhuge,
                                                                        const int *__restrict__ huge_off,
                                                                        const chunk_rec<typename fp_bits<T>::I> *__restrict__ recs,
-                                                                       unsigned int *status)
+                                                                       unsigned int *status,
+                                                                       const int64_t *__restrict__ mleaf, int64_t mnleaves,
+                                                                       int mleaf_level)
 {
     if (status[SW_STATUS]) return;
     using I = typename fp_bits<T>::I;
@@ -444,7 +453,12 @@ __global__ void __launch_bounds__(FOLD_THREADS) fold_huge_apply_kernel(T *__rest
                 }
                 const int c = cb + k;
                 const int nc = s.len - c * FOLD_CHUNK < FOLD_CHUNK ? s.len - c * FOLD_CHUNK : FOLD_CHUNK;
-                cur = ordered_fold_cta<T>(cur, src + (int64_t)c * FOLD_CHUNK, nc, s_wtot, &s_mviol, &ctl);
+                if constexpr (MASKED) {
+                    const masked_src<T> ms{lev_d, mleaf, mnleaves, s.node, mleaf_level - s.level};
+                    cur = ordered_fold_cta<T>(cur, ms + (int64_t)c * FOLD_CHUNK, nc, s_wtot, &s_mviol, &ctl);
+                } else {
+                    cur = ordered_fold_cta<T>(cur, src + (int64_t)c * FOLD_CHUNK, nc, s_wtot, &s_mviol, &ctl);
+                }
                 int e2;
                 I m2;
                 stale = !(scan_ready<T>(cur, e2, m2) && e2 == eT0);
@@ -573,11 +587,11 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
         using REC = chunk_rec<typename fp_bits<T>::I>;
         g_kernel_launches += 3;
         mark(3);
-        fold_huge_maps_kernel<T><<<t->sm_count * 2, FOLD_THREADS, 0, s>>>(H, lev, B, w.queue_huge, w.huge_off,
-                                                                         (REC *)w.huge_recs, status);
+        fold_huge_maps_kernel<T, false><<<t->sm_count * 2, FOLD_THREADS, 0, s>>>(H, lev, B, w.queue_huge, w.huge_off,
+                                                                                (REC *)w.huge_recs, status, nullptr, 0, 0);
         mark(4);
-        fold_huge_apply_kernel<T><<<t->sm_count, FOLD_THREADS, 0, s>>>(H, lev, B, w.queue_huge, w.huge_off,
-                                                                      (const REC *)w.huge_recs, status);
+        fold_huge_apply_kernel<T, false><<<t->sm_count, FOLD_THREADS, 0, s>>>(H, lev, B, w.queue_huge, w.huge_off,
+                                                                             (const REC *)w.huge_recs, status, nullptr, 0, 0);
         mark(5);
         fold_scan_kernel<T><<<t->sm_count * 8, FOLD_THREADS, 0, s>>>(H, lev, B, w.queue, w.queue_med, status,
                                                                         retire_params<T>{nullptr, nullptr, 0, 0, 0, 0});
@@ -594,6 +608,62 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
         }
         return cudaGetLastError();
     }
+}
+
+// Tiny power-of-two tree (the replicated top tree of the sharded layout): fold ALL m differences, in
+// batch order, into every internal node that is an ancestor of their leaf.  Every node is one
+// "huge segment" over the whole vector with non-members masked to 0 -- no sort, no partition.
+__global__ void top_entries_kernel(seg_entry *q, int *off, unsigned int *status, int n, int m, int nchunks)
+{
+    const int h = blockIdx.x * blockDim.x + threadIdx.x;   // node 1 .. n-1
+    if (h == 0) {
+        status[SW_QCOUNT_HUGE] = (unsigned int)(n - 1);
+        status[SW_HUGE_CHUNKS] = (unsigned int)((n - 1) * nchunks);
+        status[SW_QTAKE_HUGE] = 0;
+    }
+    if (h >= 1 && h < n) {
+        q[h - 1] = seg_entry{heap_level((uint32_t)h), 0, m, (uint32_t)h};
+        off[h - 1] = (h - 1) * nchunks;
+    }
+}
+
+template <typename T>
+static void fold_by_leaf_launch(st_tree *t, seg_entry *q, int *off, void *recs, const int64_t *leaf, const void *deltas,
+                                cudaStream_t s)
+{
+    using REC = chunk_rec<typename fp_bits<T>::I>;
+    fold_huge_maps_kernel<T, true><<<t->sm_count * 2, FOLD_THREADS, 0, s>>>(
+        (const T *)t->heap, (const T *)deltas, 0, q, off, (REC *)recs, t->d_status, leaf, t->n, t->depth);
+    fold_huge_apply_kernel<T, true><<<(unsigned)(t->n - 1), FOLD_THREADS, 0, s>>>(
+        (T *)t->heap, (const T *)deltas, 0, q, off, (const REC *)recs, t->d_status, leaf, t->n, t->depth);
+}
+
+cudaError_t launch_fold_by_leaf(st_tree *t, const int64_t *leaf, const void *deltas, int64_t m, cudaStream_t s)
+{
+    if (m <= 0) return cudaSuccess;
+    if (t->dtype != ST_F32 && t->dtype != ST_F64) return cudaErrorInvalidValue;
+    if (t->n > 64 || (t->n & (t->n - 1)) || m > 0x7fffffffLL) return cudaErrorInvalidValue;
+    const int nchunks = (int)((m + FOLD_CHUNK - 1) / FOLD_CHUNK);
+    // workspace: entries, offsets, chunk records for n-1 nodes
+    const size_t need = 256 * 3 + (size_t)(t->n) * (sizeof(seg_entry) + sizeof(int)) + (size_t)(t->n) * nchunks * 64;
+    if (need > t->ws.bytes) {
+        cudaError_t e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) return e;
+        if (t->ws.base) cudaFree(t->ws.base);
+        t->ws.base = nullptr; t->ws.bytes = 0; t->reserved_batch = 0; t->cub_cap = -1;
+        e = cudaMalloc(&t->ws.base, need);
+        if (e != cudaSuccess) return e;
+        t->ws.bytes = need;
+    }
+    char *base = (char *)t->ws.base;
+    seg_entry *q = (seg_entry *)base;
+    int *off = (int *)(base + align_up((size_t)t->n * sizeof(seg_entry)));
+    void *recs = base + align_up((size_t)t->n * sizeof(seg_entry)) + align_up((size_t)t->n * sizeof(int));
+    g_kernel_launches += 3;
+    top_entries_kernel<<<1, 64, 0, s>>>(q, off, t->d_status, (int)t->n, (int)m, nchunks);
+    if (t->dtype == ST_F32) fold_by_leaf_launch<float>(t, q, off, recs, leaf, deltas, s);
+    else fold_by_leaf_launch<double>(t, q, off, recs, leaf, deltas, s);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_update(st_tree *t, const int64_t *idx, int64_t ni, const void *vals, int64_t nv,

@@ -131,3 +131,27 @@ def test_full_size_config3(torch_mod, oracle_mod):
     C.update_sumtree(idx, vals, leaves, tree)
     dev.update_(torch.from_numpy(idx).cuda(), torch.from_numpy(vals).cuda())
     assert_bits_equal(_np(dev.tree), tree, "tree after re-applying the batch")
+
+
+@pytest.mark.parametrize("dt_name", ["float32", "float64"])
+def test_apply_deltas_tiny_tree(torch_mod, dt_name):
+    """The sharded layout's replicated top tree: every internal node of a tiny tree folds ALL the
+    differences below it in batch order (masked ordered fold, no sort / partition)."""
+    torch = torch_mod
+    from starr_b200 import DeviceSumTree
+    dt = np.dtype(dt_name)
+    rng = np.random.default_rng(11)
+    for G in (2, 4, 8):
+        for m in (100, 5000, 300_000):
+            t = DeviceSumTree(torch.from_numpy(np.exp(rng.uniform(-3, 12, G)).astype(dt)).cuda())
+            heap0 = _np(t.heap).copy()
+            leaf = rng.integers(0, G, m).astype(np.int64)
+            d = (np.exp(rng.uniform(-12, 6, m)) * rng.choice([-1.0, 1.0], m)).astype(dt)
+            t.apply_deltas_(torch.from_numpy(leaf).cuda(), torch.from_numpy(d).cuda())
+            want = heap0.copy()
+            for h in range(1, G):
+                lvl = h.bit_length() - 1
+                member = ((leaf + G) >> (int(np.log2(G)) - lvl)) == h
+                seq = np.concatenate([[heap0[h]], d[member]]).astype(dt)
+                want[h] = np.add.accumulate(seq, dtype=dt)[-1]        # sequential fold in dtype
+            assert_bits_equal(_np(t.heap), want, f"G={G} m={m}")
