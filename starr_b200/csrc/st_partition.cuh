@@ -23,10 +23,12 @@ namespace st {
 
 namespace cg = cooperative_groups;
 
+constexpr int FOLD_CHUNK_ELEMS = 1024;   // == FOLD_CHUNK of st_ordered_fold.cuh (chunk records of huge segments)
+
 constexpr int PART_THREADS = 256;
-constexpr int PART_E = 4;
-constexpr int PART_TILE = PART_THREADS * PART_E;  // 1024
-constexpr int PART_MAX_TILES = 1024;              // UPDATE_MAX_CHUNK / PART_TILE
+constexpr int PART_E = 8;
+constexpr int PART_TILE = PART_THREADS * PART_E;                       // 2048
+constexpr int PART_MAX_TILES = (int)(UPDATE_MAX_CHUNK / PART_TILE);    // 512: one tile per co-resident CTA
 
 template <typename T> struct part_params {
     T *H;
@@ -70,13 +72,25 @@ __device__ __forceinline__ unsigned int block_excl_scan(unsigned int v, unsigned
     return pre + inc - v;
 }
 
+#ifdef ST_SMALL_TIMING
+__device__ unsigned long long g_part_ticks[256];
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define PT_TICK(k) if (blockIdx.x == 0 && threadIdx.x == 0 && (k) < 256) g_part_ticks[(k)] = gtime()
+#else
+#define PT_TICK(k)
+#endif
+
 template <typename T>
 __global__ void __launch_bounds__(PART_THREADS) partition_levels_kernel(part_params<T> p)
 {
     cg::grid_group grid = cg::this_grid();
+    PT_TICK(0);
     if (p.status[SW_STATUS]) return;  // uniform over the grid: a failed batch is skipped as a whole
     __shared__ unsigned int s_tpre[PART_MAX_TILES + 1];
     __shared__ unsigned int s_warp[PART_THREADS / 32];
+    __shared__ unsigned int s_wk[PART_E * (PART_THREADS / 32)];
+    __shared__ unsigned int s_hist[PART_MAX_TILES];
+    for (int j = threadIdx.x; j < PART_MAX_TILES; j += PART_THREADS) s_hist[j] = 0;
     const int tid = threadIdx.x;
     const int m = p.m, depth = p.depth;
     const uint64_t two_n = 2ull * p.n;
@@ -87,7 +101,7 @@ __global__ void __launch_bounds__(PART_THREADS) partition_levels_kernel(part_par
         if (depth >= 2 && m > SHORT_SEG) {
 #pragma unroll
             for (int k = 0; k < PART_E; ++k) {
-                const int i = t * PART_TILE + tid * PART_E + k;
+                const int i = t * PART_TILE + k * PART_THREADS + tid;
                 if (i < m) z += ((p.key0[i] >> (depth - 1)) & 1u) ^ 1u;
             }
         }
@@ -99,6 +113,7 @@ __global__ void __launch_bounds__(PART_THREADS) partition_levels_kernel(part_par
         }
     }
     grid.sync();
+    PT_TICK(1);
 
     for (int l = 0; l < depth; ++l) {
         const int cur = l & 1;
@@ -116,17 +131,18 @@ __global__ void __launch_bounds__(PART_THREADS) partition_levels_kernel(part_par
         // tile prefix of the zero counts (every CTA scans the <= 1024 tile sums itself)
         unsigned int ztotal = 0;
         if (!last) {
-            unsigned int v[PART_E], run = 0;
+            constexpr int TPT = (PART_MAX_TILES + PART_THREADS - 1) / PART_THREADS;   // tile sums per thread
+            unsigned int v[TPT], run = 0;
 #pragma unroll
-            for (int k = 0; k < PART_E; ++k) {
-                const int t = tid * PART_E + k;
+            for (int k = 0; k < TPT; ++k) {
+                const int t = tid * TPT + k;
                 v[k] = (t < p.ntiles) ? tsC[t] : 0u;
                 run += v[k];
             }
             unsigned int pre = block_excl_scan(run, s_warp, &ztotal);
 #pragma unroll
-            for (int k = 0; k < PART_E; ++k) {
-                s_tpre[tid * PART_E + k] = pre;
+            for (int k = 0; k < TPT; ++k) {
+                if (tid * TPT + k <= PART_MAX_TILES) s_tpre[tid * TPT + k] = pre;
                 pre += v[k];
             }
             __syncthreads();
@@ -135,113 +151,179 @@ __global__ void __launch_bounds__(PART_THREADS) partition_levels_kernel(part_par
         // ---- P1: segment heads fold / retire / queue; publish Z ------------------------------------------
         if (blockIdx.x == 0 && tid == 0) p.status[SW_ANYLONG + ((l + 1) & 1)] = 0;
         for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
-            unsigned int zloc[PART_E], zsum = 0;
+            // striped ownership: element (k, tid) = tile base + k * 256 + tid, so that every load / store of
+            // a warp covers 32 consecutive elements (coalesced) and a split sends them to two dense runs
+            unsigned int zloc[PART_E];
+            const int i0 = t * PART_TILE + tid;
+            uint32_t kyv[PART_E];
+            int sv[PART_E], ev[PART_E];
 #pragma unroll
             for (int k = 0; k < PART_E; ++k) {
-                const int i = t * PART_TILE + tid * PART_E + k;
-                zloc[k] = 0;
+                const int i = i0 + k * PART_THREADS;
+                kyv[k] = 0; sv[k] = 0; ev[k] = SEG_DONE;
                 if (i < m) {
-                    const int eraw = (l == 0) ? m : eC[i];
-                    if (!(eraw & SEG_DONE)) {
-                        const int s = (l == 0) ? 0 : sC[i];
-                        const int e = eraw;
-                        const int len = e - s;
-                        const uint32_t ky = key[i];
-                        if (len <= SHORT_SEG) {
-                            if (i == s)
-                                retire_segment<T>(p.H, s, e, l, depth, two_n, [&](int x) { return key[x]; },
-                                                  [&](int x) { return dC[x]; });
-                        } else {
-                            if (i == s && l < key_leaf_level(ky, two_n, depth)) {
-                                const uint32_t node = ky >> sh;
-                                if (len > HUGE_SEG) {
-                                    const unsigned int slot = atomicAdd(p.status + SW_QCOUNT_HUGE, 1u);
-                                    p.qhuge[slot] = seg_entry{l, s, len, node};
-                                    p.huge_off[slot] = (int)atomicAdd(p.status + SW_HUGE_CHUNKS,
-                                                                      (unsigned int)((len + 1023) / 1024));
-                                } else if (len > MEDIUM_SEG) {
-                                    p.qlong[atomicAdd(p.status + SW_QCOUNT, 1u)] = seg_entry{l, s, len, node};
-                                } else {
-                                    p.qmed[atomicAdd(p.status + SW_QCOUNT_MED, 1u)] = seg_entry{l, s, len, node};
-                                }
+                    ev[k] = (l == 0) ? m : eC[i];
+                    sv[k] = (l == 0) ? 0 : sC[i];
+                    kyv[k] = key[i];
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < PART_E; ++k) {
+                const int i = i0 + k * PART_THREADS;
+                zloc[k] = 0;
+                if (!(ev[k] & SEG_DONE)) {
+                    const int s = sv[k], e = ev[k];
+                    const int len = e - s;
+                    const uint32_t ky = kyv[k];
+                    if (len <= SHORT_SEG) {
+                        retire_segment_part<T>(p.H, s, e, i - s, l, depth, two_n, [&](int x) { return key[x]; },
+                                               [&](int x) { return dC[x]; });
+                    } else {
+                        if (i == s && l < key_leaf_level(ky, two_n, depth)) {
+                            const uint32_t node = ky >> sh;
+                            if (len > HUGE_SEG) {
+                                const unsigned int slot = atomicAdd(p.status + SW_QCOUNT_HUGE, 1u);
+                                p.qhuge[slot] = seg_entry{l, s, len, node};
+                                p.huge_off[slot] = (int)atomicAdd(p.status + SW_HUGE_CHUNKS,
+                                                                  (unsigned int)((len + FOLD_CHUNK_ELEMS - 1) / FOLD_CHUNK_ELEMS));
+                            } else if (len > MEDIUM_SEG) {
+                                p.qlong[atomicAdd(p.status + SW_QCOUNT, 1u)] = seg_entry{l, s, len, node};
+                            } else {
+                                p.qmed[atomicAdd(p.status + SW_QCOUNT_MED, 1u)] = seg_entry{l, s, len, node};
                             }
-                            if (i == s) p.status[SW_ANYLONG + (l & 1)] = 1;   // another split is needed
-                            if (!last) zloc[k] = ((ky >> (sh - 1)) & 1u) ^ 1u;
                         }
+                        if (i == s) p.status[SW_ANYLONG + (l & 1)] = 1;   // another split is needed
+                        if (!last) zloc[k] = ((ky >> (sh - 1)) & 1u) ^ 1u;
                     }
                 }
-                zsum += zloc[k];
             }
             if (!last) {
-                unsigned int tot;
-                unsigned int pre = block_excl_scan(zsum, s_warp, &tot) + s_tpre[t];
+                // exclusive zero count in element order (k-major, then thread): ballots give the in-warp
+                // rank, one shared table of 8 x 8 warp totals gives the rest (one barrier pair per tile)
+                const int lane = tid & 31, warp = tid >> 5;
+                unsigned int bal[PART_E];
+#pragma unroll
+                for (int k = 0; k < PART_E; ++k) bal[k] = __ballot_sync(0xffffffffu, zloc[k] != 0);
+                __syncthreads();   // s_wk free (previous tile)
+                if (lane < PART_E) s_wk[lane * (PART_THREADS / 32) + warp] = __popc(bal[lane]);
+                __syncthreads();
+                // every warp scans the 64 totals itself: lane holds entries 2*lane, 2*lane+1
+                const unsigned int e0 = s_wk[2 * lane], e1 = s_wk[2 * lane + 1];
+                unsigned int inc = e0 + e1;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const unsigned int o = __shfl_up_sync(0xffffffffu, inc, off);
+                    if (lane >= off) inc += o;
+                }
+                const unsigned int excl_pair = inc - (e0 + e1);   // exclusive prefix of entry 2*lane
+                const unsigned int tbase = s_tpre[t];
 #pragma unroll
                 for (int k = 0; k < PART_E; ++k) {
-                    const int i = t * PART_TILE + tid * PART_E + k;
-                    if (i < m) p.Z[i] = (int)pre;
-                    pre += zloc[k];
+                    const int ent = k * (PART_THREADS / 32) + warp;
+                    unsigned int pre = __shfl_sync(0xffffffffu, excl_pair, ent >> 1);
+                    const unsigned int first = __shfl_sync(0xffffffffu, e0, ent >> 1);
+                    if (ent & 1) pre += first;
+                    const int i = i0 + k * PART_THREADS;
+                    if (i < m) p.Z[i] = (int)(tbase + pre + __popc(bal[k] & ((1u << lane) - 1u)));
                 }
                 if (tid == 0) tsN[t] = 0;   // counters of the level after next start from zero
             }
         }
         if (last) break;
+        PT_TICK(2 + 4 * l);
         grid.sync();
+        PT_TICK(3 + 4 * l);
         if (((volatile unsigned int *)p.status)[SW_ANYLONG + (l & 1)] == 0) break;   // only retired segments are left (grid-uniform)
 
         // ---- P2: stable split of every long segment by the next key bit ------------------------------------
+        // Loads are issued in batches (all keys / bounds, then all zero counts) so that one thread has
+        // 8 independent L2 requests in flight per round trip instead of 8 dependent chains.
         const bool need_next = (l + 1 < depth - 1);   // level l+1 may split again by bit sh-2
         for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+            const int i0 = t * PART_TILE + tid;
+            uint32_t kyv[PART_E];
+            int sv[PART_E], ev[PART_E];
+            bool live[PART_E], moving[PART_E];
 #pragma unroll
             for (int k = 0; k < PART_E; ++k) {
-                const int i = t * PART_TILE + tid * PART_E + k;
-                const bool live = i < m;
-                int np = 0;
-                unsigned int znext = 0;
-                if (live) {
+                const int i = i0 + k * PART_THREADS;
+                live[k] = i < m;
+                kyv[k] = 0; sv[k] = 0; ev[k] = 0;
+                if (live[k]) {
                     const int eraw = (l == 0) ? m : eC[i];
-                    const int s = (l == 0) ? 0 : sC[i];
-                    const int e = eraw & ~SEG_DONE;
-                    if ((eraw & SEG_DONE) || e - s <= SHORT_SEG) {
+                    sv[k] = (l == 0) ? 0 : sC[i];
+                    ev[k] = eraw;
+                    kyv[k] = key[i];
+                }
+            }
+            int zsv[PART_E], zev[PART_E], ziv[PART_E];
+            T dv[PART_E];
+#pragma unroll
+            for (int k = 0; k < PART_E; ++k) {
+                const int i = i0 + k * PART_THREADS;
+                const int e = ev[k] & ~SEG_DONE;
+                moving[k] = live[k] && !(ev[k] & SEG_DONE) && (e - sv[k] > SHORT_SEG);
+                zsv[k] = zev[k] = ziv[k] = 0;
+                dv[k] = T(0);
+                if (moving[k]) {
+                    zsv[k] = p.Z[sv[k]];
+                    zev[k] = (e < m) ? p.Z[e] : (int)ztotal;
+                    ziv[k] = p.Z[i];
+                    dv[k] = dC[i];
+                }
+            }
+            int npv[PART_E];
+            unsigned int znext[PART_E];
+#pragma unroll
+            for (int k = 0; k < PART_E; ++k) {
+                const int i = i0 + k * PART_THREADS;
+                npv[k] = i;
+                znext[k] = 0;
+                if (live[k]) {
+                    const int s = sv[k], e = ev[k] & ~SEG_DONE;
+                    if (!moving[k]) {
                         // retired: stays where it is, nobody reads its key / difference again
-                        np = i;
                         sN[i] = s;
                         eN[i] = e | SEG_DONE;
                     } else {
-                        const uint32_t ky = key[i];
-                        const int zs = p.Z[s];
-                        const int ze = (e < m) ? p.Z[e] : (int)ztotal;
-                        const int zb = p.Z[i] - zs;      // zero-bit elements of my segment before me
-                        const int nz = ze - zs;          // zero-bit elements of my segment
-                        int s2, e2;
+                        const uint32_t ky = kyv[k];
+                        const int zb = ziv[k] - zsv[k];      // zero-bit elements of my segment before me
+                        const int nz = zev[k] - zsv[k];      // zero-bit elements of my segment
+                        int np, s2, e2;
                         if (((ky >> (sh - 1)) & 1u) == 0) {
-                            np = s + zb;
-                            s2 = s;
-                            e2 = s + nz;
+                            np = s + zb; s2 = s; e2 = s + nz;
                         } else {
-                            np = s + nz + (i - s - zb);
-                            s2 = s + nz;
-                            e2 = e;
+                            np = s + nz + (i - s - zb); s2 = s + nz; e2 = e;
                         }
+                        npv[k] = np;
                         keyN[np] = ky;
-                        dN[np] = dC[i];
+                        dN[np] = dv[k];
                         sN[np] = s2;
                         eN[np] = e2;
-                        if (need_next && e2 - s2 > SHORT_SEG) znext = ((ky >> (sh - 2)) & 1u) ^ 1u;
-                    }
-                }
-                if (need_next) {
-                    // one atomic per (warp, destination tile)
-                    const int dt = live ? (np / PART_TILE) : -1;
-                    const unsigned int peers = __match_any_sync(0xffffffffu, dt);
-                    const unsigned int zmask = __ballot_sync(0xffffffffu, znext != 0);
-                    if (live && (threadIdx.x & 31) == (__ffs(peers) - 1)) {
-                        const unsigned int c = __popc(peers & zmask);
-                        if (c) atomicAdd(tsN + dt, c);
+                        if (need_next && e2 - s2 > SHORT_SEG) znext[k] = ((ky >> (sh - 2)) & 1u) ^ 1u;
                     }
                 }
             }
+            if (need_next) {
+                // zero counts of the NEXT split per destination tile: shared-memory histogram first
+#pragma unroll
+                for (int k = 0; k < PART_E; ++k)
+                    if (znext[k]) atomicAdd(&s_hist[npv[k] / PART_TILE], 1u);
+            }
         }
+        if (need_next) {
+            __syncthreads();
+            for (int j = tid; j < p.ntiles; j += PART_THREADS) {
+                const unsigned int v = s_hist[j];
+                if (v) {
+                    atomicAdd(tsN + j, v);
+                    s_hist[j] = 0;
+                }
+            }
+        }
+        PT_TICK(4 + 4 * l);
         grid.sync();
+        PT_TICK(5 + 4 * l);
     }
 }
 

@@ -323,9 +323,9 @@ __global__ void __launch_bounds__(FOLD_THREADS) fold_scan_kernel(T *__restrict__
             for (int i = blockIdx.x * FOLD_THREADS + threadIdx.x; i < ret.m; i += gridDim.x * FOLD_THREADS) {
                 const uint32_t se = sl[i];
                 const int s = (int)(se & 0xffffu), e = (int)((se >> 16) & 0x7fffu);
-                if (!(se & 0x80000000u) && i == s && e - s <= SHORT_SEG)
-                    retire_segment<T>(H, s, e, l, ret.depth, two_n, [&](int x) { return kl[x]; },
-                                      [&](int x) { return dl[x]; });
+                if (!(se & 0x80000000u) && e - s <= SHORT_SEG)
+                    retire_segment_part<T>(H, s, e, i - s, l, ret.depth, two_n, [&](int x) { return kl[x]; },
+                                           [&](int x) { return dl[x]; });
             }
         }
     }
@@ -561,8 +561,11 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
                 if (e != cudaSuccess) return e;
                 if (occ < 1) return cudaErrorCooperativeLaunchTooLarge;
             }
-            int grid = occ * t->sm_count;
-            if (grid > pp.ntiles) grid = pp.ntiles;
+            // balanced persistent grid: every CTA gets the same number of tiles (the grid barriers wait
+            // for the slowest CTA)
+            const int max_res = occ * t->sm_count;
+            const int per_cta = (pp.ntiles + max_res - 1) / max_res;
+            const int grid = (pp.ntiles + per_cta - 1) / per_cta;
             void *args[] = {&pp};
             ++g_kernel_launches;
             e = cudaLaunchCooperativeKernel((const void *)partition_levels_kernel<T>, dim3(grid), dim3(PART_THREADS),
@@ -717,3 +720,10 @@ cudaError_t launch_update(st_tree *t, const int64_t *idx, int64_t ni, const void
 }
 
 }  // namespace st
+
+#ifdef ST_SMALL_TIMING
+extern "C" __attribute__((visibility("default"))) int st_debug_ticks(unsigned long long *out)
+{
+    return (int)cudaMemcpyFromSymbol(out, st::g_part_ticks, 256 * sizeof(unsigned long long));
+}
+#endif

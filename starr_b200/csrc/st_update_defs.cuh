@@ -53,19 +53,23 @@ template <typename T> __device__ __forceinline__ void ordered_add(T *ptr, T d)
     atomicAdd(ptr, d);
 }
 
-// A segment of at most SHORT_SEG updates (in batch order) is finished by its head thread for
-// its node at level l AND every deeper level: the thread walks the updates in batch order and adds
-// each one to all of its remaining ancestors, so every node still sees its updates in batch order
-// and no further partitioning of this segment is needed.
+// A segment of at most SHORT_SEG updates (in batch order) is finished -- "retired" -- for its node
+// at level l AND every deeper level, so it never has to be partitioned again.  The work is spread
+// over the segment's own threads by LEVEL: the thread of the r-th element takes levels
+// l + r, l + r + len, ... and for each of them walks all updates of the segment in batch order,
+// adding each one to its ancestor at that level.  All adds to one node therefore come from one
+// thread in batch order (ordered_add), different levels touch different nodes.
 template <typename T, typename KEYAT, typename DAT>
-__device__ __forceinline__ void retire_segment(T *H, int s, int e, int l, int depth, uint64_t two_n, KEYAT keyat,
-                                               DAT dat)
+__device__ __forceinline__ void retire_segment_part(T *H, int s, int e, int r, int l, int depth, uint64_t two_n,
+                                                    KEYAT keyat, DAT dat)
 {
-    for (int x = s; x < e; ++x) {
-        const uint32_t kx = keyat(x);
-        const T dx = dat(x);
-        const int ll = key_leaf_level(kx, two_n, depth);
-        for (int l2 = l; l2 < ll; ++l2) ordered_add<T>(H + (kx >> (depth - l2)), dx);
+    const int len = e - s;
+    for (int l2 = l + r; l2 < depth; l2 += len) {
+        const int sh = depth - l2;
+        for (int x = s; x < e; ++x) {
+            const uint32_t kx = keyat(x);
+            if (l2 < key_leaf_level(kx, two_n, depth)) ordered_add<T>(H + (kx >> sh), dat(x));
+        }
     }
 }
 
