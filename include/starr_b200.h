@@ -115,6 +115,10 @@ ST_API int st_update_device(st_tree *t, const int64_t *idx_dev, int64_t ni, cons
                      int64_t nv, void *stream, int flags);
 ST_API int st_update_host(st_tree *t, const int64_t *idx_host, int64_t ni, const void *vals_host,
                    int64_t nv);
+/* st_update_host that also returns the resulting leaf values of idx (what SumTreeArray.put needs
+ * for its host mirror: floats store fl(old + fl(val - old)), not val), in one staging round. */
+ST_API int st_update_gather_host(st_tree *t, const int64_t *idx_host, int64_t ni, const void *vals_host,
+                          int64_t nv, void *leaves_out_host);
 
 /* ---- building blocks of the subtree-sharded tree (no reference counterpart: the reference is
  * single-process; these keep the sharded result bit-identical to ONE reference tree) -------- */
@@ -141,6 +145,10 @@ ST_API int st_search_host(const st_tree *t, const void *vals_host, int64_t m, in
 ST_API int st_sample_uniform_device(const st_tree *t, const double *u_dev, int64_t m, int64_t *out_dev,
                              void *prio_out_dev, void *stream);
 ST_API int st_sample_uniform_host(const st_tree *t, const double *u_host, int64_t m, int64_t *out_host);
+/* same plus the root (sumtree[1]) the uniforms were scaled by: sample()'s zero-total check
+ * (sumtree_array.py:417-418) without a second device round trip */
+ST_API int st_sample_root_host(const st_tree *t, const double *u_host, int64_t m, int64_t *out_host,
+                        void *root_out);
 
 /* ---- sums: replace sum_over / strided_sum, _sumtree_array.pyx:131-194 ------------ */
 ST_API int st_root_host(const st_tree *t, void *out_scalar); /* sumtree[1], sumtree_array.py:503 */

@@ -83,6 +83,8 @@ _SIGNATURES = {
     "st_update_deltas_device": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
     "st_apply_deltas_device": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "st_route_uniform_device": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "st_update_gather_host": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
+    "st_sample_root_host": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "st_search_device": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "st_search_host": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "st_sample_uniform_device": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
@@ -205,6 +207,17 @@ class TreeHandle:
 
     def update_host(self, idx: np.ndarray, vals: np.ndarray) -> None:
         check(lib().st_update_host(self.ptr, host_ptr(idx), idx.size, host_ptr(vals), vals.size))
+
+    def update_gather_host(self, idx: np.ndarray, vals: np.ndarray) -> np.ndarray:
+        out = np.empty(idx.size, dtype=self.dtype)
+        check(lib().st_update_gather_host(self.ptr, host_ptr(idx), idx.size, host_ptr(vals), vals.size,
+                                          host_ptr(out)))
+        return out
+
+    def sample_root_host(self, u: np.ndarray, out: np.ndarray):
+        root = np.zeros(1, dtype=self.dtype)
+        check(lib().st_sample_root_host(self.ptr, host_ptr(u), u.size, host_ptr(out), host_ptr(root)))
+        return root[0]
 
     def search_host(self, vals: np.ndarray, out: np.ndarray) -> None:
         check(lib().st_search_host(self.ptr, host_ptr(vals), vals.size, host_ptr(out)))

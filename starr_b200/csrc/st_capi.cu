@@ -65,14 +65,40 @@ int fetch_status(st_tree *t, cudaStream_t s, bool clear)
     return status_from_flags(f);
 }
 
-// scratch device buffer for the *_host entry points (freed on scope exit)
+// Staging area of the *_host entry points: carved out of one grow-only device buffer per tree so
+// that a call costs copies + launches, not cudaMalloc/cudaFree.
 struct dev_buf {
     void *p = nullptr;
-    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
-    ~dev_buf()
+};
+struct scratch_carver {
+    st_tree *t;
+    size_t need = 0;
+    explicit scratch_carver(const st_tree *tree) : t(const_cast<st_tree *>(tree)) {}
+    static size_t up(size_t b) { return (b + 255) & ~(size_t)255; }
+    // first pass: add(bytes) for every buffer; then commit(); then take(bytes) in the same order
+    void add(size_t bytes) { need += up(bytes ? bytes : 1); }
+    cudaError_t commit()
     {
-        if (p) cudaFree(p);
+        off = 0;
+        if (need <= t->scratch.bytes) return cudaSuccess;
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) return e;
+        if (t->scratch.base) cudaFree(t->scratch.base);
+        t->scratch.base = nullptr;
+        t->scratch.bytes = 0;
+        const size_t want = need < (1u << 20) ? (1u << 20) : need;
+        e = cudaMalloc(&t->scratch.base, want);
+        if (e != cudaSuccess) return e;
+        t->scratch.bytes = want;
+        return cudaSuccess;
     }
+    void *take(size_t bytes)
+    {
+        void *p = (char *)t->scratch.base + off;
+        off += up(bytes ? bytes : 1);
+        return p;
+    }
+    size_t off = 0;
 };
 
 }  // namespace
@@ -164,6 +190,7 @@ int st_destroy(st_tree *t)
     if (t->d_status) cudaFree(t->d_status);
     if (t->h_status) cudaFreeHost(t->h_status);
     if (t->ws.base) cudaFree(t->ws.base);
+    if (t->scratch.base) cudaFree(t->scratch.base);
     for (int k = 0; k < 8; ++k)
         if (t->prof_ev[k]) cudaEventDestroy(t->prof_ev[k]);
     delete t;
@@ -227,8 +254,10 @@ int st_gather_leaves_host(const st_tree *t, const int64_t *idx_host, int64_t m, 
     if (m == 0) return ST_OK;
     device_guard g(t->device);
     dev_buf di, dout;
-    CU(di.alloc(m * sizeof(int64_t)));
-    CU(dout.alloc(m * t->esize));
+    scratch_carver sc(t);
+    sc.add(m * sizeof(int64_t)); sc.add(m * t->esize);
+    CU(sc.commit());
+    di.p = sc.take(m * sizeof(int64_t)); dout.p = sc.take(m * t->esize);
     CU(cudaMemcpy(di.p, idx_host, m * sizeof(int64_t), cudaMemcpyHostToDevice));
     CU(st::launch_gather(t, (const int64_t *)di.p, m, dout.p, 0));
     CU(cudaMemcpy(out_host, dout.p, m * t->esize, cudaMemcpyDeviceToHost));
@@ -292,8 +321,10 @@ int st_update_host(st_tree *t, const int64_t *idx_host, int64_t ni, const void *
     if (ni == 0 && nv == 0) return ST_OK;
     device_guard g(t->device);
     dev_buf di, dv;
-    CU(di.alloc(ni * sizeof(int64_t)));
-    CU(dv.alloc(nv * t->esize));
+    scratch_carver sc(t);
+    sc.add(ni * sizeof(int64_t)); sc.add(nv * t->esize);
+    CU(sc.commit());
+    di.p = sc.take(ni * sizeof(int64_t)); dv.p = sc.take(nv * t->esize);
     CU(cudaMemcpy(di.p, idx_host, ni * sizeof(int64_t), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(dv.p, vals_host, nv * t->esize, cudaMemcpyHostToDevice));
     return st_update_device(t, (const int64_t *)di.p, ni, dv.p, nv, nullptr, ST_UPDATE_SYNC_CHECK);
@@ -336,6 +367,57 @@ int st_route_uniform_device(const st_tree *t, const double *u_dev, int64_t m, in
     return ST_OK;
 }
 
+// put(): update, then read back the leaves that were written, one staging round (sumtree_array.py:229-233)
+int st_update_gather_host(st_tree *t, const int64_t *idx_host, int64_t ni, const void *vals_host, int64_t nv,
+                          void *leaves_out_host)
+{
+    if (!t || ni < 0 || nv < 0) return fail(ST_ERR_ARG, "st_update_gather_host: bad argument");
+    if (ni > 0 && nv == 0) return fail(ST_ERR_EMPTY_VALS, "%s", st_status_string(ST_ERR_EMPTY_VALS));
+    if (ni == 0 && nv == 0) return ST_OK;
+    device_guard g(t->device);
+    scratch_carver sc(t);
+    sc.add(ni * sizeof(int64_t)); sc.add(nv * t->esize); sc.add(ni * t->esize);
+    CU(sc.commit());
+    int64_t *di = (int64_t *)sc.take(ni * sizeof(int64_t));
+    void *dv = sc.take(nv * t->esize);
+    void *dl = sc.take(ni * t->esize);
+    if (ni) CU(cudaMemcpyAsync(di, idx_host, ni * sizeof(int64_t), cudaMemcpyHostToDevice, 0));
+    CU(cudaMemcpyAsync(dv, vals_host, nv * t->esize, cudaMemcpyHostToDevice, 0));
+    CU(st::launch_update(t, di, ni, dv, nv, nullptr, nullptr, 0));
+    if (ni && leaves_out_host) CU(st::launch_gather(t, di, ni, dl, 0));
+    CU(cudaMemcpyAsync(t->h_status, t->d_status, sizeof(unsigned int), cudaMemcpyDeviceToHost, 0));
+    if (ni && leaves_out_host) CU(cudaMemcpyAsync(leaves_out_host, dl, ni * t->esize, cudaMemcpyDeviceToHost, 0));
+    CU(cudaStreamSynchronize(0));
+    const unsigned int f = t->h_status[0];
+    if (f) {
+        CU(cudaMemsetAsync(t->d_status, 0, sizeof(unsigned int), 0));
+        CU(cudaStreamSynchronize(0));
+        const int st = status_from_flags(f);
+        return fail(st, "%s", st_status_string(st));
+    }
+    return ST_OK;
+}
+
+// sample(): indices for the uniforms plus the root they were scaled by, one staging round
+int st_sample_root_host(const st_tree *t, const double *u_host, int64_t m, int64_t *out_host, void *root_out)
+{
+    if (!t || m < 0 || !root_out) return fail(ST_ERR_ARG, "st_sample_root_host: bad argument");
+    device_guard g(t->device);
+    scratch_carver sc(t);
+    sc.add(m * sizeof(double)); sc.add(m * sizeof(int64_t));
+    CU(sc.commit());
+    double *du = (double *)sc.take(m * sizeof(double));
+    int64_t *dout = (int64_t *)sc.take(m * sizeof(int64_t));
+    if (m) {
+        CU(cudaMemcpyAsync(du, u_host, m * sizeof(double), cudaMemcpyHostToDevice, 0));
+        CU(st::launch_sample(t, du, m, dout, nullptr, nullptr, 0));
+        CU(cudaMemcpyAsync(out_host, dout, m * sizeof(int64_t), cudaMemcpyDeviceToHost, 0));
+    }
+    CU(cudaMemcpyAsync(root_out, (const char *)t->heap + t->esize, t->esize, cudaMemcpyDeviceToHost, 0));
+    CU(cudaStreamSynchronize(0));
+    return ST_OK;
+}
+
 // ---- search / sample -----------------------------------------------------------------------
 int st_search_device(const st_tree *t, const void *vals_dev, int64_t m, int64_t *out_dev, void *stream)
 {
@@ -351,8 +433,10 @@ int st_search_host(const st_tree *t, const void *vals_host, int64_t m, int64_t *
     if (m == 0) return ST_OK;
     device_guard g(t->device);
     dev_buf dv, dout;
-    CU(dv.alloc(m * t->esize));
-    CU(dout.alloc(m * sizeof(int64_t)));
+    scratch_carver sc(t);
+    sc.add(m * t->esize); sc.add(m * sizeof(int64_t));
+    CU(sc.commit());
+    dv.p = sc.take(m * t->esize); dout.p = sc.take(m * sizeof(int64_t));
     CU(cudaMemcpy(dv.p, vals_host, m * t->esize, cudaMemcpyHostToDevice));
     CU(st::launch_search(t, dv.p, m, (int64_t *)dout.p, 0));
     CU(cudaMemcpy(out_host, dout.p, m * sizeof(int64_t), cudaMemcpyDeviceToHost));
@@ -374,8 +458,10 @@ int st_sample_uniform_host(const st_tree *t, const double *u_host, int64_t m, in
     if (m == 0) return ST_OK;
     device_guard g(t->device);
     dev_buf du, dout;
-    CU(du.alloc(m * sizeof(double)));
-    CU(dout.alloc(m * sizeof(int64_t)));
+    scratch_carver sc(t);
+    sc.add(m * sizeof(double)); sc.add(m * sizeof(int64_t));
+    CU(sc.commit());
+    du.p = sc.take(m * sizeof(double)); dout.p = sc.take(m * sizeof(int64_t));
     CU(cudaMemcpy(du.p, u_host, m * sizeof(double), cudaMemcpyHostToDevice));
     CU(st::launch_sample(t, (const double *)du.p, m, (int64_t *)dout.p, nullptr, nullptr, 0));
     CU(cudaMemcpy(out_host, dout.p, m * sizeof(int64_t), cudaMemcpyDeviceToHost));
@@ -400,7 +486,10 @@ int st_sum_over_host(const st_tree *t, int64_t index_from, int64_t index_to, voi
     if (index_to - 1 == index_from && index_from >= t->n) return fail(ST_ERR_INDEX, "%s", st_status_string(ST_ERR_INDEX));
     device_guard g(t->device);
     dev_buf d;
-    CU(d.alloc(8));
+    scratch_carver sc(t);
+    sc.add(8);
+    CU(sc.commit());
+    d.p = sc.take(8);
     CU(st::launch_sum_over(t, index_from, index_to, d.p, 0));
     CU(cudaMemcpy(out_scalar, d.p, t->esize, cudaMemcpyDeviceToHost));
     return ST_OK;
@@ -423,7 +512,10 @@ int st_strided_sum_host(const st_tree *t, int64_t stride, void *out_host, int64_
     if (nout != strided_len(t->n, stride)) return fail(ST_ERR_SIZE, "invalid output size");
     device_guard g(t->device);
     dev_buf d;
-    CU(d.alloc(nout * t->esize));
+    scratch_carver sc(t);
+    sc.add(nout * t->esize);
+    CU(sc.commit());
+    d.p = sc.take(nout * t->esize);
     CU(st::launch_strided_sum(t, stride, d.p, nout, 0));
     CU(cudaMemcpy(out_host, d.p, nout * t->esize, cudaMemcpyDeviceToHost));
     return ST_OK;
@@ -447,7 +539,10 @@ int st_axis_fold_host(const st_tree *t, int64_t A, int64_t R, int64_t C, void *o
     device_guard g(t->device);
     dev_buf d;
     const size_t bytes = (size_t)A * C * fold_out_size(t);
-    CU(d.alloc(bytes));
+    scratch_carver sc(t);
+    sc.add(bytes);
+    CU(sc.commit());
+    d.p = sc.take(bytes);
     CU(st::launch_axis_fold(t, A, R, C, d.p, 0));
     CU(cudaMemcpy(out_host, d.p, bytes, cudaMemcpyDeviceToHost));
     return ST_OK;

@@ -27,6 +27,7 @@ struct st_tree {
     unsigned int *d_status = nullptr;  // device status word (+ spare counters), 64 words
     unsigned int *h_status = nullptr;  // pinned host mirror, 64 words
     st_workspace ws;
+    st_workspace scratch;   // grow-only staging area of the *_host entry points (no malloc/free per call)
     int64_t reserved_batch = 0;
     int64_t cub_cap = -1;      // batch capacity for which cub_bytes was queried
     size_t cub_bytes = 0;

@@ -493,16 +493,27 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
             sp.H = H; sp.n = n; sp.depth = depth; sp.m = m; sp.idx = idx; sp.vals = vals;
             sp.nv = (uint64_t)nv; sp.j0 = (uint64_t)j0; sp.deltas_in = deltas_in; sp.delta_out = delta_out;
             sp.lev_d = (T *)w.lev_d; sp.lev_stride = B; sp.qlong = w.queue; sp.qmed = w.queue_med; sp.status = status;
-            static bool attr_done = false;
-            if (!attr_done) {
-                cudaError_t ea = cudaFuncSetAttribute(update_small_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                      (int)small_smem_bytes<T>());
-                if (ea != cudaSuccess) return ea;
-                attr_done = true;
-            }
-            g_kernel_launches += 2;
             sp.ret_key = w.ret_key; sp.ret_se = w.ret_se;
-            update_small_kernel<T><<<1, SMALL_THREADS, small_smem_bytes<T>(), s>>>(sp);
+            g_kernel_launches += 2;
+            if (m <= SMALL_THREADS) {
+                static bool attr1 = false;
+                if (!attr1) {
+                    cudaError_t ea = cudaFuncSetAttribute(update_small_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                          (int)small_smem_bytes<T, 1>());
+                    if (ea != cudaSuccess) return ea;
+                    attr1 = true;
+                }
+                update_small_kernel<T, 1><<<1, SMALL_THREADS, small_smem_bytes<T, 1>(), s>>>(sp);
+            } else {
+                static bool attr4 = false;
+                if (!attr4) {
+                    cudaError_t ea = cudaFuncSetAttribute(update_small_kernel<T, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                          (int)small_smem_bytes<T, 4>());
+                    if (ea != cudaSuccess) return ea;
+                    attr4 = true;
+                }
+                update_small_kernel<T, 4><<<1, SMALL_THREADS, small_smem_bytes<T, 4>(), s>>>(sp);
+            }
             retire_params<T> rp{w.ret_key, w.ret_se, m, depth, SMALL_M, n};
             fold_scan_kernel<T><<<t->sm_count, FOLD_THREADS, 0, s>>>(H, (const T *)w.lev_d, B, w.queue, w.queue_med,
                                                                     status, rp);

@@ -13,8 +13,7 @@
 namespace st {
 
 constexpr int SMALL_THREADS = 1024;
-constexpr int SMALL_E = 4;
-constexpr int SMALL_M = SMALL_THREADS * SMALL_E;  // 4096
+constexpr int SMALL_M = SMALL_THREADS * 4;   // 4096: the largest batch of the single-CTA path (4 per thread)
 constexpr int SMALL_MEDIUM_SEG = 256;             // small batches: CTA fold above one warp chunk
 
 template <typename T> struct small_params {
@@ -35,22 +34,24 @@ template <typename T> struct small_params {
     uint32_t *ret_key, *ret_se;   // [level][SMALL_M]: levels with retirements, for the follow-up kernel
 };
 
-template <typename T> struct small_smem {
-    uint32_t key[2][SMALL_M];
-    T d[2][SMALL_M];
-    uint32_t se[2][SMALL_M];   // s | e << 16  (e == SMALL_M is stored as 0xffff + 1 -> use 13-bit fields)
-    uint32_t z[SMALL_M + 1];
+template <typename T, int SMALL_E> struct small_smem {
+    static constexpr int CAP = SMALL_THREADS * SMALL_E;
+    uint32_t key[2][CAP];
+    T d[2][CAP];
+    uint32_t se[2][CAP];   // s | e << 16  (e == SMALL_M is stored as 0xffff + 1 -> use 13-bit fields)
+    uint32_t z[CAP + 1];
     uint32_t wtot[SMALL_THREADS / 32];
     int flag;
     int flag_retire;
 };
 
-using SmallSort = cub::BlockRadixSort<uint32_t, SMALL_THREADS, SMALL_E, int>;
+template <int SMALL_E> using SmallSort = cub::BlockRadixSort<uint32_t, SMALL_THREADS, SMALL_E, int>;
 
-template <typename T> constexpr size_t small_smem_bytes()
+template <typename T, int SMALL_E> constexpr size_t small_smem_bytes()
 {
-    return sizeof(small_smem<T>) > sizeof(typename SmallSort::TempStorage) ? sizeof(small_smem<T>)
-                                                                           : sizeof(typename SmallSort::TempStorage);
+    return sizeof(small_smem<T, SMALL_E>) > sizeof(typename SmallSort<SMALL_E>::TempStorage)
+               ? sizeof(small_smem<T, SMALL_E>)
+               : sizeof(typename SmallSort<SMALL_E>::TempStorage);
 }
 
 __device__ __forceinline__ uint32_t pack_se(int s, int e) { return (uint32_t)s | ((uint32_t)e << 16); }
@@ -81,12 +82,14 @@ __device__ __forceinline__ uint32_t small_block_scan(uint32_t v, uint32_t *s_wto
     return wpre + inc - v;
 }
 
-template <typename T>
+// SMALL_E = updates per thread: 1 (batches <= 1024, a quarter of the instructions) or 4 (<= 4096)
+template <typename T, int SMALL_E>
 __global__ void __launch_bounds__(SMALL_THREADS, 1) update_small_kernel(small_params<T> p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    small_smem<T> &S = *reinterpret_cast<small_smem<T> *>(smem_raw);
-    typename SmallSort::TempStorage &sort_tmp = *reinterpret_cast<typename SmallSort::TempStorage *>(smem_raw);
+    small_smem<T, SMALL_E> &S = *reinterpret_cast<small_smem<T, SMALL_E> *>(smem_raw);
+    using Sort = SmallSort<SMALL_E>;
+    typename Sort::TempStorage &sort_tmp = *reinterpret_cast<typename Sort::TempStorage *>(smem_raw);
     const int tid = threadIdx.x;
     const int m = p.m, depth = p.depth;
     const uint64_t two_n = 2ull * p.n;
@@ -138,7 +141,7 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) update_small_kernel(small_pa
     uint32_t key0[SMALL_E];
 #pragma unroll
     for (int k = 0; k < SMALL_E; ++k) key0[k] = keys[k];
-    SmallSort(sort_tmp).Sort(keys, js, 0, depth + 1);
+    Sort(sort_tmp).Sort(keys, js, 0, depth + 1);
     __syncthreads();   // sort_tmp dead; the arrays below alias it
 #pragma unroll
     for (int k = 0; k < SMALL_E; ++k) {
@@ -222,12 +225,18 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) update_small_kernel(small_pa
         __syncthreads();
         uint32_t zloc[SMALL_E], zsum = 0;
         uint32_t kreg[SMALL_E], sereg[SMALL_E];
-        {
+        if constexpr (SMALL_E == 4) {
             // one 128-bit shared load per array instead of four conflicting 32-bit ones
             const uint4 k4 = *reinterpret_cast<const uint4 *>(&S.key[c][tid * SMALL_E]);
             const uint4 s4 = *reinterpret_cast<const uint4 *>(&S.se[c][tid * SMALL_E]);
             kreg[0] = k4.x; kreg[1] = k4.y; kreg[2] = k4.z; kreg[3] = k4.w;
             sereg[0] = s4.x; sereg[1] = s4.y; sereg[2] = s4.z; sereg[3] = s4.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < SMALL_E; ++k) {
+                kreg[k] = S.key[c][tid * SMALL_E + k];
+                sereg[k] = S.se[c][tid * SMALL_E + k];
+            }
         }
         int anylong = 0;
 #pragma unroll
@@ -263,7 +272,7 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) update_small_kernel(small_pa
             for (int i = tid; i < m; i += SMALL_THREADS) dst[i] = S.d[c][i];
         }
         if (S.flag_retire) {
-            uint32_t *kd = p.ret_key + (size_t)l * SMALL_M, *sd = p.ret_se + (size_t)l * SMALL_M;
+            uint32_t *kd = p.ret_key + (size_t)l * SMALL_M, *sd = p.ret_se + (size_t)l * SMALL_M;   // stride is always SMALL_M
             for (int i = tid; i < m; i += SMALL_THREADS) {
                 kd[i] = S.key[c][i];
                 sd[i] = S.se[c][i];
@@ -280,9 +289,14 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) update_small_kernel(small_pa
             zown[k] = pre;
             pre += zloc[k];
         }
-        *reinterpret_cast<uint4 *>(&S.z[tid * SMALL_E]) = make_uint4(zown[0], zown[1], zown[2], zown[3]);
+        if constexpr (SMALL_E == 4) {
+            *reinterpret_cast<uint4 *>(&S.z[tid * SMALL_E]) = make_uint4(zown[0], zown[1], zown[2], zown[3]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < SMALL_E; ++k) S.z[tid * SMALL_E + k] = zown[k];
+        }
         T dreg[SMALL_E];
-        if constexpr (sizeof(T) == 4) {
+        if constexpr (sizeof(T) == 4 && SMALL_E == 4) {
             const float4 d4 = *reinterpret_cast<const float4 *>(&S.d[c][tid * SMALL_E]);
             dreg[0] = d4.x; dreg[1] = d4.y; dreg[2] = d4.z; dreg[3] = d4.w;
         } else {

@@ -27,7 +27,7 @@ _TOO_SMALL = "input to SumTreeArray must have shape with at least 2 elements"
 class _TreeState:
     """Device tree + host mirrors shared by every view of one SumTreeArray."""
 
-    __slots__ = ("handle", "leaves", "tree", "tree_stale", "leaves_stale", "_index_base", "__weakref__")
+    __slots__ = ("handle", "leaves", "tree", "tree_stale", "leaves_stale", "_index_base", "_root", "__weakref__")
 
     def __init__(self, flat_leaves: np.ndarray, device: int = 0):
         self.leaves = flat_leaves                      # host mirror (a view of the array buffer)
@@ -35,6 +35,7 @@ class _TreeState:
         self.tree_stale = False
         self.leaves_stale = False
         self._index_base = None
+        self._root = None                              # cached sumtree[1]; None = unknown
         self.handle = _lib.TreeHandle(flat_leaves.size, flat_leaves.dtype, device)
 
     # -- mirrors ----------------------------------------------------------------------------
@@ -55,6 +56,20 @@ class _TreeState:
                 self.leaves[...] = tmp
             self.leaves_stale = False
 
+    def root(self):
+        if self._root is None:
+            self._root = self.handle.root()
+        return self._root
+
+    def root_is_zero(self) -> bool:
+        return self.root() == 0
+
+    def note_root(self, value) -> None:
+        self._root = value
+
+    def invalidate_root(self) -> None:
+        self._root = None
+
     def index_base(self) -> np.ndarray:
         if self._index_base is None:
             self._index_base = np.arange(self.leaves.size, dtype=np.intp)
@@ -63,6 +78,7 @@ class _TreeState:
     # -- the four kernel call sites ------------------------------------------------------------
     def rebuild(self) -> None:                       # reference sumtree_array.py:184-185
         self.leaves_stale = False                    # host leaves are the source here
+        self._root = None
         try:
             self.handle.build_from_host(np.ascontiguousarray(self.leaves))
         finally:
@@ -70,11 +86,15 @@ class _TreeState:
 
     def update(self, flat_idx: np.ndarray, values: np.ndarray) -> None:   # :233
         self.sync_leaves()
-        self.handle.update_host(flat_idx, values)
-        self.tree_stale = True
+        self._root = None
+        try:
+            # the device holds fl(old + fl(val - old)), which is not always `val` for floats, so the
+            # host mirror is patched with what the device actually stored (same staging round)
+            written = self.handle.update_gather_host(flat_idx, values)
+        finally:
+            self.tree_stale = True
         if flat_idx.size:
-            # the device holds fl(old + fl(val - old)), which is not always `val` for floats
-            self.leaves[flat_idx] = self.handle.gather_leaves_host(flat_idx)
+            self.leaves[flat_idx] = written
 
     def search(self, flat_vals: np.ndarray) -> np.ndarray:                # :354
         out = np.zeros(flat_vals.size, dtype=np.intp)
@@ -166,6 +186,7 @@ class SumTreeArray(np.ndarray):
         """Tell the host mirrors that the device tree was changed behind their back."""
         self._state.tree_stale = True
         self._state.leaves_stale = True
+        self._state.invalidate_root()
 
     def _nd(self) -> np.ndarray:
         """Plain, read-only ndarray view of the (up-to-date) host leaf mirror."""
@@ -273,13 +294,14 @@ class SumTreeArray(np.ndarray):
 
     def sample(self, nsamples=1, flatten_indices=False):
         """Draw ``nsamples`` indices with probability ``self / self.sum()``."""
-        total = self.sum()
-        if total == 0:
+        if self._state.root_is_zero():
             raise ValueError("array must have at least 1 positive value")
-        # vals = (total * rand).astype(dtype), evaluated on the device with the same roundings
+        # vals = (total * rand).astype(dtype), evaluated on the device with the same roundings; the
+        # call also returns the root it scaled by, which refreshes the cached zero-total check
         u = np.random.rand(nsamples)
         found = np.zeros(u.size, dtype=np.intp)
-        self._state.handle.sample_uniform_host(np.ascontiguousarray(u), found)
+        root = self._state.handle.sample_root_host(np.ascontiguousarray(u), found)
+        self._state.note_root(root)
         if self.ndim <= 1 or flatten_indices:
             return found
         return np.unravel_index(found, self.shape)
@@ -293,7 +315,7 @@ class SumTreeArray(np.ndarray):
         other contiguous axis blocks are folded on the device in row order."""
         axes = self._parse_axis_arg(axis)
         if axes is None:
-            root = self._state.handle.root()
+            root = self._state.root()
             return np.array([root]).reshape([1] * self.ndim) if keepdims else root
         plan = _hostlogic.plan_sum(self.shape, axes)
         if plan[0] == "strided":
