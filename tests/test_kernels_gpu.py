@@ -303,3 +303,60 @@ def test_ordered_fold_adversarial(oracle_mod, dt, kind):
             assert_bits_equal(gl, leaves, f"{kind} n={n} rep={rep} leaves")
             assert_bits_equal(gt, tree, f"{kind} n={n} rep={rep} tree")
         h.close()
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.int32], ids=["f32", "i32"])
+def test_batches_larger_than_one_chunk(oracle_mod, dt):
+    """Batches above 2^20 updates are applied chunk by chunk; `vals` keeps cycling over the position
+    in the WHOLE batch (pyx:44), duplicates may straddle chunk boundaries."""
+    from starr_b200 import _lib
+    C = oracle_mod.c
+    rng = np.random.default_rng(21)
+    n = 1 << 22
+    leaves = _draw(rng, n, dt, "uni")
+    tree = np.zeros(n, dt)
+    C.build_sumtree_from_array(leaves, tree)
+    h = _lib.TreeHandle(n, dt)
+    h.build_from_host(leaves)
+    for m, nv in (((1 << 21) + 12345, 1000003), ((1 << 20) + 1, (1 << 20) + 1), (3 << 20, 7)):
+        idx = rng.integers(0, n, m).astype(np.intp)
+        idx[::5] = idx[0]                      # one leaf hit in every chunk
+        vals = _draw(rng, nv, dt, "log")
+        C.update_sumtree(idx, vals, leaves, tree)
+        h.update_host(idx, vals)
+        gl, gt = _state(h)
+        assert_bits_equal(gl, leaves, f"leaves m={m} nv={nv}")
+        assert_bits_equal(gt, tree, f"tree m={m} nv={nv}")
+    h.close()
+
+
+def test_non_power_of_two_large(oracle_mod):
+    """A large non-power-of-two tree (leaves at two depths, rotated order) through the big-batch path."""
+    from starr_b200 import _lib
+    C = oracle_mod.c
+    rng = np.random.default_rng(22)
+    for n in (3_000_001, (1 << 22) - 1, (1 << 21) + 1):
+        leaves = rng.random(n).astype(np.float32)
+        tree = np.zeros(n, np.float32)
+        C.build_sumtree_from_array(leaves, tree)
+        h = _lib.TreeHandle(n, np.float32)
+        h.build_from_host(leaves)
+        gl, gt = _state(h)
+        assert_bits_equal(gt, tree, f"build n={n}")
+        m = 400_000
+        idx = rng.integers(0, n, m).astype(np.intp)
+        vals = np.exp(rng.uniform(-6, 6, m)).astype(np.float32)
+        C.update_sumtree(idx, vals, leaves, tree)
+        h.update_host(idx, vals)
+        gl, gt = _state(h)
+        assert_bits_equal(gl, leaves, f"leaves n={n}")
+        assert_bits_equal(gt, tree, f"tree n={n}")
+        q = (rng.random(100_000) * float(tree[1])).astype(np.float32)
+        want = np.zeros(q.size, np.intp)
+        C.get_prefix_sum_idx(want, q, leaves, tree)
+        got = np.zeros(q.size, np.intp)
+        h.search_host(q, got)
+        assert np.array_equal(got, want)
+        for s in (1000, 4096, 3):
+            assert_bits_equal(h.strided_sum_host(s), C.strided_sum(leaves, tree, s), f"strided {s} n={n}")
+        h.close()
