@@ -131,6 +131,15 @@ ST_API int st_update_deltas_device(st_tree *t, const int64_t *idx_dev, int64_t n
  * shard roots. */
 ST_API int st_apply_deltas_device(st_tree *t, const int64_t *idx_dev, int64_t ni, const void *deltas_dev,
                            void *stream);
+/* st_apply_deltas_device for a tiny power-of-two float tree (n <= 64) in two phases, so that the
+ * ranks of a sharded tree can split phase A: chunk c covers batch positions [1024c, 1024c+1024);
+ * phase A writes one record per (chunk, internal node) at recs[(c*(n-1) + node-1) * record_bytes]
+ * for chunk_lo <= c < chunk_hi; phase B needs the records of ALL ceil(m/1024) chunks. */
+ST_API int st_top_fold_record_bytes(const st_tree *t);
+ST_API int st_top_fold_maps_device(st_tree *t, const int64_t *leaf_dev, const void *deltas_dev, int64_t m,
+                            int64_t chunk_lo, int64_t chunk_hi, void *recs_dev, void *stream);
+ST_API int st_top_fold_apply_device(st_tree *t, const int64_t *leaf_dev, const void *deltas_dev, int64_t m,
+                             const void *recs_dev, void *stream);
 /* sample() descent that also returns the prefix left over at the leaf that was reached:
  * on the top tree this is (owning shard, query to continue with inside that shard). */
 ST_API int st_route_uniform_device(const st_tree *t, const double *u_dev, int64_t m, int64_t *leaf_out_dev,

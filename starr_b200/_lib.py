@@ -82,6 +82,9 @@ _SIGNATURES = {
     "st_update_host": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64]),
     "st_update_deltas_device": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
     "st_apply_deltas_device": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "st_top_fold_record_bytes": (c_int, [c_void_p]),
+    "st_top_fold_maps_device": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
+    "st_top_fold_apply_device": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "st_route_uniform_device": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "st_update_gather_host": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
     "st_sample_root_host": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
@@ -264,6 +267,18 @@ class TreeHandle:
     def apply_deltas_device(self, idx_ptr: int, ni: int, deltas_ptr: int, stream: int = 0) -> None:
         check(lib().st_apply_deltas_device(self.ptr, c_void_p(idx_ptr), int(ni), c_void_p(deltas_ptr),
                                            c_void_p(stream)))
+
+    def top_fold_record_bytes(self) -> int:
+        return int(lib().st_top_fold_record_bytes(self.ptr))
+
+    def top_fold_maps_device(self, leaf_ptr: int, deltas_ptr: int, m: int, chunk_lo: int, chunk_hi: int,
+                             recs_ptr: int, stream: int = 0) -> None:
+        check(lib().st_top_fold_maps_device(self.ptr, c_void_p(leaf_ptr), c_void_p(deltas_ptr), int(m),
+                                            int(chunk_lo), int(chunk_hi), c_void_p(recs_ptr), c_void_p(stream)))
+
+    def top_fold_apply_device(self, leaf_ptr: int, deltas_ptr: int, m: int, recs_ptr: int, stream: int = 0) -> None:
+        check(lib().st_top_fold_apply_device(self.ptr, c_void_p(leaf_ptr), c_void_p(deltas_ptr), int(m),
+                                             c_void_p(recs_ptr), c_void_p(stream)))
 
     def route_uniform_device(self, u_ptr: int, m: int, leaf_out_ptr: int, resid_out_ptr: int,
                              stream: int = 0) -> None:

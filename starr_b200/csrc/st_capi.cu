@@ -358,6 +358,27 @@ int st_apply_deltas_device(st_tree *t, const int64_t *idx_dev, int64_t ni, const
     return ST_OK;
 }
 
+int st_top_fold_record_bytes(const st_tree *t) { return t ? (int)st::fold_rec_bytes(t) : -1; }
+
+int st_top_fold_maps_device(st_tree *t, const int64_t *leaf_dev, const void *deltas_dev, int64_t m, int64_t chunk_lo,
+                            int64_t chunk_hi, void *recs_dev, void *stream)
+{
+    if (!t || m < 0 || !recs_dev) return fail(ST_ERR_ARG, "st_top_fold_maps_device: bad argument");
+    device_guard g(t->device);
+    CU(st::launch_fold_by_leaf_maps(t, leaf_dev, deltas_dev, m, (int)chunk_lo, (int)chunk_hi, recs_dev,
+                                    (cudaStream_t)stream));
+    return ST_OK;
+}
+
+int st_top_fold_apply_device(st_tree *t, const int64_t *leaf_dev, const void *deltas_dev, int64_t m,
+                             const void *recs_dev, void *stream)
+{
+    if (!t || m < 0 || !recs_dev) return fail(ST_ERR_ARG, "st_top_fold_apply_device: bad argument");
+    device_guard g(t->device);
+    CU(st::launch_fold_by_leaf_apply(t, leaf_dev, deltas_dev, m, recs_dev, (cudaStream_t)stream));
+    return ST_OK;
+}
+
 int st_route_uniform_device(const st_tree *t, const double *u_dev, int64_t m, int64_t *leaf_out_dev,
                             void *residual_out_dev, void *stream)
 {

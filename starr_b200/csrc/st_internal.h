@@ -63,5 +63,11 @@ cudaError_t launch_update(st_tree *t, const int64_t *idx, int64_t ni, const void
 int64_t update_max_chunk();
 // tiny power-of-two float tree: ordered fold of all m differences into the ancestors of leaf[j]
 cudaError_t launch_fold_by_leaf(st_tree *t, const int64_t *leaf, const void *deltas, int64_t m, cudaStream_t s);
+// the same in two phases (chunk summaries for a chunk range, then the stitch); records [chunk][node-1]
+size_t fold_rec_bytes(const st_tree *t);
+cudaError_t launch_fold_by_leaf_maps(st_tree *t, const int64_t *leaf, const void *deltas, int64_t m, int chunk_lo,
+                                     int chunk_hi, void *recs, cudaStream_t s);
+cudaError_t launch_fold_by_leaf_apply(st_tree *t, const int64_t *leaf, const void *deltas, int64_t m, const void *recs,
+                                      cudaStream_t s);
 
 }  // namespace st

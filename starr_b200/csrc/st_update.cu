@@ -401,7 +401,12 @@ __global__ void __launch_bounds__(FOLD_THREADS) fold_huge_maps_kernel(const T *_
     }
 }
 
-// Huge segments, phase B: one CTA per segment walks the chunk summaries in order.
+// Huge segments, phase B: one CTA per segment stitches the chunk summaries.  First a parallel
+// attempt: the chunk maps are composed with a block scan, which gives every chunk's incoming m, and
+// all excursion bounds are checked at once (the common case: nothing leaves the binade).  From the
+// first chunk that fails the check on, the CTA walks sequentially: safe chunks cost a few integer
+// ops, unsafe ones (or any chunk after the exponent changed) are folded exactly.
+// Record of chunk c of this segment: recs[rec_base + c * rec_stride].
 template <typename T, bool MASKED>
 __global__ void __launch_bounds__(FOLD_THREADS) fold_huge_apply_kernel(T *__restrict__ H, const T *__restrict__ lev_d,
                                                                        int64_t level_stride,
@@ -420,24 +425,82 @@ __global__ void __launch_bounds__(FOLD_THREADS) fold_huge_apply_kernel(T *__rest
     __shared__ I s_mviol;
     __shared__ fold_smem_ctl ctl;
     __shared__ chunk_rec<I> s_rec[FOLD_THREADS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned int n_huge = status[SW_QCOUNT_HUGE];
     for (;;) {
         __syncthreads();
-        if (threadIdx.x == 0) ctl.slot = atomicAdd(status + SW_QTAKE_HUGE, 1u);
+        if (tid == 0) ctl.slot = atomicAdd(status + SW_QTAKE_HUGE, 1u);
         __syncthreads();
         const unsigned int slot = ctl.slot;
         if (slot >= n_huge) break;
         const seg_entry s = qhuge[slot];
         const T *src = lev_d + (int64_t)s.level * level_stride + s.start;
-        const chunk_rec<I> *rec = recs + huge_off[slot];
+        const int64_t rec_base = MASKED ? (int64_t)(s.node - 1) : (int64_t)huge_off[slot];
+        const int64_t rec_stride = MASKED ? (int64_t)(mnleaves - 1) : 1;
         const int nchunks = (s.len + FOLD_CHUNK - 1) / FOLD_CHUNK;
         T cur = H[s.node];
         int eT0;
         I m;
         bool stale = !scan_ready<T>(cur, eT0, m);   // summaries were made for eT0 (phase A saw the same value)
-        for (int cb = 0; cb < nchunks; cb += FOLD_THREADS) {
+        int c_start = 0;
+        if (!stale) {
+            // ---- parallel attempt ---------------------------------------------------------------------
+            const int per = (nchunks + FOLD_THREADS - 1) / FOLD_THREADS;
+            const int lo = tid * per < nchunks ? tid * per : nchunks;
+            const int hi = lo + per < nchunks ? lo + per : nchunks;
+            pmap<I> local{0, 0};
+            for (int c = lo; c < hi; ++c) {
+                const chunk_rec<I> r = recs[rec_base + c * rec_stride];
+                local = pmap_then<I>(local, pmap<I>{r.a0, r.a1});
+            }
+            const pmap<I> incl = pmap_warp_scan<I>(local, lane);
+            pmap<I> excl = pmap_shfl_up<I>(incl, 1);
+            if (lane == 0) excl = pmap<I>{0, 0};
+            if (lane == 31) {
+                s_wtot[warp][0] = incl.a0;
+                s_wtot[warp][1] = incl.a1;
+            }
+            if (tid == 0) ctl.first_viol = NO_VIOL;
             __syncthreads();
-            if (cb + (int)threadIdx.x < nchunks) s_rec[threadIdx.x] = rec[cb + threadIdx.x];
+            pmap<I> pre{0, 0}, tot{0, 0};
+#pragma unroll
+            for (int w = 0; w < FOLD_THREADS / 32; ++w) {
+                const pmap<I> t{s_wtot[w][0], s_wtot[w][1]};
+                if (w < warp) pre = pmap_then<I>(pre, t);
+                tot = pmap_then<I>(tot, t);
+            }
+            pre = pmap_then<I>(pre, excl);
+            I mm = m + ((m & 1) ? pre.a1 : pre.a0);
+            int bad = NO_VIOL;
+            I m_bad = 0;
+            for (int c = lo; c < hi; ++c) {
+                const chunk_rec<I> r = recs[rec_base + c * rec_stride];
+                const bool odd = (mm & 1) != 0;
+                const I mn = odd ? r.min1 : r.min0, mx = odd ? r.max1 : r.max0;
+                if (!(r.ok && mm + mn >= LO && mm + mx < HI)) {
+                    bad = c;
+                    m_bad = mm;
+                    break;
+                }
+                mm += odd ? r.a1 : r.a0;
+            }
+            if (bad != NO_VIOL) atomicMin(&ctl.first_viol, bad);
+            __syncthreads();
+            const int fb = ctl.first_viol;
+            if (fb == NO_VIOL) {
+                m += (m & 1) ? tot.a1 : tot.a0;
+                c_start = nchunks;
+            } else {
+                if (bad == fb) s_mviol = m_bad;   // exact m in front of the first chunk that needs care
+                __syncthreads();
+                m = s_mviol;
+                c_start = fb;
+            }
+        }
+        // ---- sequential continuation ---------------------------------------------------------------------
+        for (int cb = c_start; cb < nchunks; cb += FOLD_THREADS) {
+            __syncthreads();
+            if (cb + tid < nchunks) s_rec[tid] = recs[rec_base + (int64_t)(cb + tid) * rec_stride];
             __syncthreads();
             const int lim = nchunks - cb < FOLD_THREADS ? nchunks - cb : FOLD_THREADS;
             for (int k = 0; k < lim; ++k) {   // uniform over the CTA
@@ -465,7 +528,42 @@ __global__ void __launch_bounds__(FOLD_THREADS) fold_huge_apply_kernel(T *__rest
                 if (!stale) m = m2;
             }
         }
-        if (threadIdx.x == 0) H[s.node] = stale ? cur : value_of<T>(eT0, m);
+        if (tid == 0) H[s.node] = stale ? cur : value_of<T>(eT0, m);
+    }
+}
+
+// Masked variant of phase A for the tiny top tree: records laid out [chunk][node-1] so that a rank's
+// chunk range is one contiguous slab (exchanged with one all-gather in the sharded layout).
+template <typename T>
+__global__ void __launch_bounds__(FOLD_THREADS) fold_top_maps_kernel(const T *__restrict__ H, const T *__restrict__ d,
+                                                                     const int64_t *__restrict__ leaf, int64_t nleaves,
+                                                                     int leaf_level, int64_t m, int chunk_lo, int chunk_hi,
+                                                                     chunk_rec<typename fp_bits<T>::I> *__restrict__ recs,
+                                                                     const unsigned int *status)
+{
+    if (status[SW_STATUS]) return;
+    using I = typename fp_bits<T>::I;
+    __shared__ I s_wtot[FOLD_THREADS / 32][2];
+    __shared__ I s_red[FOLD_THREADS / 32][4];
+    __shared__ float s_abs[FOLD_THREADS / 32];
+    const int nodes = (int)nleaves - 1;
+    const int64_t pairs = (int64_t)(chunk_hi - chunk_lo) * nodes;
+    for (int64_t pidx = blockIdx.x; pidx < pairs; pidx += gridDim.x) {
+        const int c = chunk_lo + (int)(pidx / nodes);
+        const uint32_t node = 1u + (uint32_t)(pidx % nodes);
+        chunk_rec<I> *out = recs + (int64_t)c * nodes + (node - 1);
+        const int64_t base = (int64_t)c * FOLD_CHUNK;
+        int64_t rem = m - base;
+        const int nc = rem <= 0 ? 0 : (rem < FOLD_CHUNK ? (int)rem : FOLD_CHUNK);
+        int eT;
+        I m0;
+        __syncthreads();
+        if (!scan_ready<T>(H[node], eT, m0)) {
+            if (threadIdx.x == 0) out->ok = 0;
+            continue;
+        }
+        const masked_src<T> ms{d, leaf, nleaves, node, leaf_level - heap_level(node)};
+        chunk_summary_cta<T>(ms + base, nc, eT, out, s_wtot, s_red, s_abs);
     }
 }
 
@@ -627,57 +725,92 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
 // Tiny power-of-two tree (the replicated top tree of the sharded layout): fold ALL m differences, in
 // batch order, into every internal node that is an ancestor of their leaf.  Every node is one
 // "huge segment" over the whole vector with non-members masked to 0 -- no sort, no partition.
-__global__ void top_entries_kernel(seg_entry *q, int *off, unsigned int *status, int n, int m, int nchunks)
+// Phase A (chunk summaries, any chunk range -> can be split over ranks) and phase B (stitch) are
+// separate entry points; records are [chunk][node-1], 64 bytes apart at most.
+__global__ void top_entries_kernel(seg_entry *q, unsigned int *status, int n, int m)
 {
     const int h = blockIdx.x * blockDim.x + threadIdx.x;   // node 1 .. n-1
     if (h == 0) {
         status[SW_QCOUNT_HUGE] = (unsigned int)(n - 1);
-        status[SW_HUGE_CHUNKS] = (unsigned int)((n - 1) * nchunks);
         status[SW_QTAKE_HUGE] = 0;
     }
-    if (h >= 1 && h < n) {
-        q[h - 1] = seg_entry{heap_level((uint32_t)h), 0, m, (uint32_t)h};
-        off[h - 1] = (h - 1) * nchunks;
-    }
+    if (h >= 1 && h < n) q[h - 1] = seg_entry{heap_level((uint32_t)h), 0, m, (uint32_t)h};
 }
 
-template <typename T>
-static void fold_by_leaf_launch(st_tree *t, seg_entry *q, int *off, void *recs, const int64_t *leaf, const void *deltas,
-                                cudaStream_t s)
+static bool fold_by_leaf_ok(const st_tree *t, int64_t m)
 {
-    using REC = chunk_rec<typename fp_bits<T>::I>;
-    fold_huge_maps_kernel<T, true><<<t->sm_count * 2, FOLD_THREADS, 0, s>>>(
-        (const T *)t->heap, (const T *)deltas, 0, q, off, (REC *)recs, t->d_status, leaf, t->n, t->depth);
-    fold_huge_apply_kernel<T, true><<<(unsigned)(t->n - 1), FOLD_THREADS, 0, s>>>(
-        (T *)t->heap, (const T *)deltas, 0, q, off, (const REC *)recs, t->d_status, leaf, t->n, t->depth);
+    return (t->dtype == ST_F32 || t->dtype == ST_F64) && t->n <= 64 && (t->n & (t->n - 1)) == 0 && m <= 0x7fffffffLL;
 }
 
-cudaError_t launch_fold_by_leaf(st_tree *t, const int64_t *leaf, const void *deltas, int64_t m, cudaStream_t s)
+size_t fold_rec_bytes(const st_tree *t) { return t->dtype == ST_F64 ? sizeof(chunk_rec<int64_t>) : sizeof(chunk_rec<int32_t>); }
+
+cudaError_t launch_fold_by_leaf_maps(st_tree *t, const int64_t *leaf, const void *deltas, int64_t m, int chunk_lo,
+                                     int chunk_hi, void *recs, cudaStream_t s)
 {
+    if (!fold_by_leaf_ok(t, m)) return cudaErrorInvalidValue;
+    if (chunk_hi <= chunk_lo) return cudaSuccess;
+    const int64_t pairs = (int64_t)(chunk_hi - chunk_lo) * (t->n - 1);
+    const unsigned g = (unsigned)(pairs < (int64_t)t->sm_count * 4 ? pairs : (int64_t)t->sm_count * 4);
+    ++g_kernel_launches;
+    if (t->dtype == ST_F32)
+        fold_top_maps_kernel<float><<<g, FOLD_THREADS, 0, s>>>((const float *)t->heap, (const float *)deltas, leaf, t->n,
+                                                               t->depth, m, chunk_lo, chunk_hi,
+                                                               (chunk_rec<int32_t> *)recs, t->d_status);
+    else
+        fold_top_maps_kernel<double><<<g, FOLD_THREADS, 0, s>>>((const double *)t->heap, (const double *)deltas, leaf,
+                                                                t->n, t->depth, m, chunk_lo, chunk_hi,
+                                                                (chunk_rec<int64_t> *)recs, t->d_status);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fold_by_leaf_apply(st_tree *t, const int64_t *leaf, const void *deltas, int64_t m, const void *recs,
+                                      cudaStream_t s)
+{
+    if (!fold_by_leaf_ok(t, m)) return cudaErrorInvalidValue;
     if (m <= 0) return cudaSuccess;
-    if (t->dtype != ST_F32 && t->dtype != ST_F64) return cudaErrorInvalidValue;
-    if (t->n > 64 || (t->n & (t->n - 1)) || m > 0x7fffffffLL) return cudaErrorInvalidValue;
-    const int nchunks = (int)((m + FOLD_CHUNK - 1) / FOLD_CHUNK);
-    // workspace: entries, offsets, chunk records for n-1 nodes
-    const size_t need = 256 * 3 + (size_t)(t->n) * (sizeof(seg_entry) + sizeof(int)) + (size_t)(t->n) * nchunks * 64;
+    const size_t need = 256 + (size_t)t->n * sizeof(seg_entry);
     if (need > t->ws.bytes) {
         cudaError_t e = cudaStreamSynchronize(s);
         if (e != cudaSuccess) return e;
         if (t->ws.base) cudaFree(t->ws.base);
         t->ws.base = nullptr; t->ws.bytes = 0; t->reserved_batch = 0; t->cub_cap = -1;
-        e = cudaMalloc(&t->ws.base, need);
+        e = cudaMalloc(&t->ws.base, need < 4096 ? 4096 : need);
         if (e != cudaSuccess) return e;
-        t->ws.bytes = need;
+        t->ws.bytes = need < 4096 ? 4096 : need;
     }
-    char *base = (char *)t->ws.base;
-    seg_entry *q = (seg_entry *)base;
-    int *off = (int *)(base + align_up((size_t)t->n * sizeof(seg_entry)));
-    void *recs = base + align_up((size_t)t->n * sizeof(seg_entry)) + align_up((size_t)t->n * sizeof(int));
-    g_kernel_launches += 3;
-    top_entries_kernel<<<1, 64, 0, s>>>(q, off, t->d_status, (int)t->n, (int)m, nchunks);
-    if (t->dtype == ST_F32) fold_by_leaf_launch<float>(t, q, off, recs, leaf, deltas, s);
-    else fold_by_leaf_launch<double>(t, q, off, recs, leaf, deltas, s);
+    seg_entry *q = (seg_entry *)t->ws.base;
+    g_kernel_launches += 2;
+    top_entries_kernel<<<1, 64, 0, s>>>(q, t->d_status, (int)t->n, (int)m);
+    if (t->dtype == ST_F32)
+        fold_huge_apply_kernel<float, true><<<(unsigned)(t->n - 1), FOLD_THREADS, 0, s>>>(
+            (float *)t->heap, (const float *)deltas, 0, q, nullptr, (const chunk_rec<int32_t> *)recs, t->d_status, leaf,
+            t->n, t->depth);
+    else
+        fold_huge_apply_kernel<double, true><<<(unsigned)(t->n - 1), FOLD_THREADS, 0, s>>>(
+            (double *)t->heap, (const double *)deltas, 0, q, nullptr, (const chunk_rec<int64_t> *)recs, t->d_status, leaf,
+            t->n, t->depth);
     return cudaGetLastError();
+}
+
+// both phases on this device (single-process use); the records live in the staging area
+cudaError_t launch_fold_by_leaf(st_tree *t, const int64_t *leaf, const void *deltas, int64_t m, cudaStream_t s)
+{
+    if (m <= 0) return cudaSuccess;
+    if (!fold_by_leaf_ok(t, m)) return cudaErrorInvalidValue;
+    const int nchunks = (int)((m + FOLD_CHUNK - 1) / FOLD_CHUNK);
+    const size_t need = (size_t)nchunks * (t->n - 1) * fold_rec_bytes(t);
+    if (need > t->scratch.bytes) {
+        cudaError_t e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) return e;
+        if (t->scratch.base) cudaFree(t->scratch.base);
+        t->scratch.base = nullptr; t->scratch.bytes = 0;
+        e = cudaMalloc(&t->scratch.base, need);
+        if (e != cudaSuccess) return e;
+        t->scratch.bytes = need;
+    }
+    cudaError_t e = launch_fold_by_leaf_maps(t, leaf, deltas, m, 0, nchunks, t->scratch.base, s);
+    if (e != cudaSuccess) return e;
+    return launch_fold_by_leaf_apply(t, leaf, deltas, m, t->scratch.base, s);
 }
 
 cudaError_t launch_update(st_tree *t, const int64_t *idx, int64_t ni, const void *vals, int64_t nv,

@@ -144,6 +144,22 @@ class DeviceSumTree:
             self._h.apply_deltas_device(idx.data_ptr(), idx.numel(), deltas.data_ptr(), _stream())
         return self
 
+    def top_fold_record_bytes(self) -> int:
+        return self._h.top_fold_record_bytes()
+
+    def top_fold_maps_(self, leaf: torch.Tensor, deltas: torch.Tensor, chunk_lo: int, chunk_hi: int,
+                       recs: torch.Tensor) -> None:
+        """Phase A of ``apply_deltas_`` on a tiny tree: summaries of the 1024-update chunks
+        [chunk_lo, chunk_hi) for every internal node, written into ``recs`` ([chunk][node-1] records)."""
+        with torch.cuda.device(self.device):
+            self._h.top_fold_maps_device(leaf.data_ptr(), deltas.data_ptr(), leaf.numel(), chunk_lo, chunk_hi,
+                                         recs.data_ptr(), _stream())
+
+    def top_fold_apply_(self, leaf: torch.Tensor, deltas: torch.Tensor, recs: torch.Tensor) -> None:
+        """Phase B: stitch the chunk summaries of ALL chunks into the internal nodes."""
+        with torch.cuda.device(self.device):
+            self._h.top_fold_apply_device(leaf.data_ptr(), deltas.data_ptr(), leaf.numel(), recs.data_ptr(), _stream())
+
     def route_uniform(self, u: torch.Tensor):
         """``sample_uniform`` that also returns the prefix left over at the leaf reached."""
         u = self._chk(u.reshape(-1), torch.float64, "u")

@@ -109,9 +109,31 @@ class ShardedSumTree:
         if mine.numel():
             d_all[mine] = self.local.update_with_deltas_(loc_idx, loc_vals)
         dist.all_reduce(d_all, op=dist.ReduceOp.SUM, group=self.group)   # one contributor per slot
-        self.top.apply_deltas_(shard, d_all)                            # ordered fold, all ranks alike
+        self._fold_top(shard, d_all)                                    # ordered fold, all ranks alike
         self._gather_roots()
         return self
+
+    def _fold_top(self, shard: torch.Tensor, d_all: torch.Tensor) -> None:
+        """Ordered fold of ALL differences into the replicated top tree.  With the CUDA tree the
+        chunk summaries (the parallel part) are split over the ranks and exchanged with one small
+        all-gather; the stitch is replicated.  Results are identical on every rank."""
+        top = self.top
+        ni = shard.numel()
+        if not hasattr(top, "top_fold_maps_") or ni <= 4096 or not self.dtype.is_floating_point:
+            top.apply_deltas_(shard, d_all)
+            return
+        nodes = self.world - 1
+        rb = top.top_fold_record_bytes()
+        nchunks = (ni + 1023) // 1024
+        per = (nchunks + self.world - 1) // self.world
+        recs = torch.empty(per * self.world * nodes * rb, dtype=torch.uint8, device=shard.device)
+        lo = self.rank * per
+        shard = shard.contiguous()
+        d_all = d_all.contiguous()
+        top.top_fold_maps_(shard, d_all, lo, lo + per, recs)
+        slab = recs[lo * nodes * rb:(lo + per) * nodes * rb].clone()
+        dist.all_gather_into_tensor(recs, slab, group=self.group)
+        top.top_fold_apply_(shard, d_all, recs)
 
     # ---- sample ---------------------------------------------------------------------------------
     def sample_uniform(self, u: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
