@@ -155,3 +155,53 @@ def test_apply_deltas_tiny_tree(torch_mod, dt_name):
                 seq = np.concatenate([[heap0[h]], d[member]]).astype(dt)
                 want[h] = np.add.accumulate(seq, dtype=dt)[-1]        # sequential fold in dtype
             assert_bits_equal(_np(t.heap), want, f"G={G} m={m}")
+
+
+def test_per_step_cuda_graph(torch_mod, oracle_mod):
+    """The PER step (update -> sample with priorities) captured ONCE in a CUDA graph and replayed with
+    new inputs in static buffers: same bits as the oracle, no launches from Python per step."""
+    torch = torch_mod
+    from starr_b200 import DeviceSumTree
+    C = oracle_mod.c
+    n, m = 1 << 20, 4096
+    rng = np.random.default_rng(5)
+    leaves = rng.random(n).astype(np.float32)
+    tree = np.zeros(n, np.float32)
+    C.build_sumtree_from_array(leaves, tree)
+    dev = DeviceSumTree(torch.from_numpy(leaves).cuda())
+    dev.reserve(m)
+    idx_b = torch.zeros(m, dtype=torch.int64, device="cuda")
+    val_b = torch.zeros(m, dtype=torch.float32, device="cuda")
+    u_b = torch.zeros(m, dtype=torch.float64, device="cuda")
+    out_b = torch.zeros(m, dtype=torch.int64, device="cuda")
+
+    def feed(idx, val, u):
+        idx_b.copy_(torch.from_numpy(idx)); val_b.copy_(torch.from_numpy(val)); u_b.copy_(torch.from_numpy(u))
+
+    # warm-up outside capture (first-use attribute setting, workspace), on a side stream as torch requires
+    idx = rng.integers(0, n, m).astype(np.int64); val = rng.random(m).astype(np.float32); u = rng.random(m)
+    feed(idx, val, u)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        dev.update_(idx_b, val_b)
+        _, prio_w = dev.sample_uniform(u_b, out=out_b, return_priorities=True)
+    torch.cuda.current_stream().wait_stream(s)
+    C.update_sumtree(idx.astype(np.intp), val, leaves, tree)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        dev.update_(idx_b, val_b)
+        _, prio_b = dev.sample_uniform(u_b, out=out_b, return_priorities=True)
+    # the capture itself did not run anything; replay with fresh inputs several times
+    for it in range(4):
+        idx = rng.integers(0, n, m).astype(np.int64) if it % 2 == 0 else want.astype(np.int64)
+        val = (rng.random(m) ** 3).astype(np.float32); u = rng.random(m)
+        feed(idx, val, u)
+        graph.replay()
+        C.update_sumtree(idx.astype(np.intp), val, leaves, tree)
+        want = np.zeros(m, np.intp)
+        C.get_prefix_sum_idx(want, (tree[1] * u).astype(np.float32), leaves, tree)
+        assert np.array_equal(_np(out_b), want), f"replay {it}"
+        assert_bits_equal(_np(prio_b), leaves[want], "priorities")
+    dev.poll()
+    assert_bits_equal(_np(dev.tree), tree, "tree after graph replays")

@@ -85,13 +85,24 @@ def main():
         di, dv, du = (torch.from_numpy(a).to(dev) for a in (idx, val, u))
         out = torch.empty(m, dtype=torch.int64, device=dev)
         g_build = gpu_time(lambda: t.build_(), reps=5)
-        g_upd = gpu_time(lambda: t.update_(di, dv))
-        g_smp = gpu_time(lambda: t.sample_uniform(du, out=out))
         arr = leaves.copy()
         c_upd = cpu_time(lambda: REF.update_sumtree(idx.astype(np.intp), val, arr, tree_np))
         q = (tree_np[1] * u).astype(np.float32); o = np.zeros(m, np.intp)
         c_smp = cpu_time(lambda: REF.get_prefix_sum_idx(o, q, arr, tree_np))
+        g_upd = gpu_time(lambda: t.update_(di, dv))
+        g_smp = gpu_time(lambda: t.sample_uniform(du, out=out))
         c_build = cpu_time(lambda: REF.build_sumtree_from_array(arr, tree_np), reps=1) if logn <= 22 else float("nan")
+        if m <= 4096:
+            # the whole PER step as one CUDA graph (static input buffers)
+            st = torch.cuda.Stream(); st.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(st):
+                t.update_(di, dv); t.sample_uniform(du, out=out, return_priorities=True)
+            torch.cuda.current_stream().wait_stream(st)
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                t.update_(di, dv); t.sample_uniform(du, out=out, return_priorities=True)
+            g_graph = gpu_time(lambda: gr.replay())
+            row(f"{label}: update+sample {m} as one CUDA graph replay", g_graph, c_upd + c_smp, 2 * m)
         row(f"{label}: build 2^{logn} f32 (validate + pairwise)", g_build, c_build, n)
         row(f"{label}: update {m} @ 2^{logn} f32", g_upd, c_upd, m)
         row(f"{label}: sample {m} @ 2^{logn} f32", g_smp, c_smp, m)
