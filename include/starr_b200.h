@@ -179,6 +179,10 @@ ST_API int st_axis_fold_host(const st_tree *t, int64_t A, int64_t R, int64_t C, 
  * (ST_OK if none) and optionally clears it. A failed batch is skipped as a whole. */
 ST_API int st_poll_status(st_tree *t, void *stream, int clear);
 
+/* Optional: pin heap[0, bytes) (the upper tree levels) in the persisting part of L2 for work
+ * submitted to `stream` (cudaAccessPolicyWindow).  bytes <= 0 removes the window. */
+ST_API int st_set_l2_persistence(st_tree *t, void *stream, int64_t bytes, int64_t *granted);
+
 /* Per-phase timing of the float update pipeline, measured with CUDA events on the launching
  * stream.  While enabled every update call waits for its own completion (profiling only).
  * out_ms[0..5] = accumulated milliseconds of: key build + leaf-order sort, leaf pass, top-down

@@ -101,6 +101,7 @@ _SIGNATURES = {
     "st_poll_status": (c_int, [c_void_p, c_void_p, c_int]),
     "st_update_stats": (c_int, [c_void_p, c_void_p, c_void_p]),
     "st_set_profiling": (c_int, [c_void_p, c_int]),
+    "st_set_l2_persistence": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "st_update_breakdown": (c_int, [c_void_p, c_void_p]),
 }
 
@@ -306,6 +307,11 @@ class TreeHandle:
 
     def poll_status(self, stream: int = 0, clear: bool = True) -> None:
         check(lib().st_poll_status(self.ptr, c_void_p(stream), 1 if clear else 0))
+
+    def set_l2_persistence(self, nbytes: int, stream: int = 0) -> int:
+        granted = c_int64(0)
+        check(lib().st_set_l2_persistence(self.ptr, c_void_p(stream), int(nbytes), ctypes.byref(granted)))
+        return int(granted.value)
 
     def set_profiling(self, enable: bool) -> None:
         check(lib().st_set_profiling(self.ptr, 1 if enable else 0))

@@ -171,6 +171,11 @@ int st_create(int64_t n, int dtype, int device, void *external_heap, st_tree **o
     }
     e = cudaMalloc((void **)&t->d_status, 64 * sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMallocHost((void **)&t->h_status, 64 * sizeof(unsigned int));
+    if (e == cudaSuccess) {
+        t->pin_bytes = 64 * 1024;
+        e = cudaHostAlloc(&t->h_pin, t->pin_bytes, cudaHostAllocMapped);
+        if (e == cudaSuccess) e = cudaHostGetDevicePointer(&t->d_pin, t->h_pin, 0);
+    }
     if (e == cudaSuccess) e = cudaMemset(t->d_status, 0, 64 * sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMemset(t->heap, 0, heap_bytes);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
@@ -189,6 +194,7 @@ int st_destroy(st_tree *t)
     if (t->owns_heap && t->heap) cudaFree(t->heap);
     if (t->d_status) cudaFree(t->d_status);
     if (t->h_status) cudaFreeHost(t->h_status);
+    if (t->h_pin) cudaFreeHost(t->h_pin);
     if (t->ws.base) cudaFree(t->ws.base);
     if (t->scratch.base) cudaFree(t->scratch.base);
     for (int k = 0; k < 8; ++k)
@@ -396,6 +402,31 @@ int st_update_gather_host(st_tree *t, const int64_t *idx_host, int64_t ni, const
     if (ni > 0 && nv == 0) return fail(ST_ERR_EMPTY_VALS, "%s", st_status_string(ST_ERR_EMPTY_VALS));
     if (ni == 0 && nv == 0) return ST_OK;
     device_guard g(t->device);
+    {
+        // small call: everything through mapped pinned memory, one stream sync, no cudaMemcpy
+        const size_t up = 256;
+        auto rnd = [&](size_t b) { return (b + up - 1) / up * up; };
+        const size_t o_idx = 0, o_val = o_idx + rnd(ni * sizeof(int64_t)), o_leaf = o_val + rnd(nv * t->esize);
+        const size_t o_stat = o_leaf + rnd(ni * t->esize), total = o_stat + up;
+        if (total <= t->pin_bytes) {
+            char *hp = (char *)t->h_pin, *dp = (char *)t->d_pin;
+            memcpy(hp + o_idx, idx_host, ni * sizeof(int64_t));
+            memcpy(hp + o_val, vals_host, nv * t->esize);
+            CU(st::launch_update(t, (const int64_t *)(dp + o_idx), ni, dp + o_val, nv, nullptr, nullptr, 0));
+            if (ni && leaves_out_host) CU(st::launch_gather(t, (const int64_t *)(dp + o_idx), ni, dp + o_leaf, 0));
+            CU(st::launch_publish(t, dp + o_stat, nullptr, 0));
+            CU(cudaStreamSynchronize(0));
+            const unsigned int f = *(volatile unsigned int *)(hp + o_stat);
+            if (f) {
+                CU(cudaMemsetAsync(t->d_status, 0, sizeof(unsigned int), 0));
+                CU(cudaStreamSynchronize(0));
+                const int st = status_from_flags(f);
+                return fail(st, "%s", st_status_string(st));
+            }
+            if (ni && leaves_out_host) memcpy(leaves_out_host, hp + o_leaf, ni * t->esize);
+            return ST_OK;
+        }
+    }
     scratch_carver sc(t);
     sc.add(ni * sizeof(int64_t)); sc.add(nv * t->esize); sc.add(ni * t->esize);
     CU(sc.commit());
@@ -424,6 +455,21 @@ int st_sample_root_host(const st_tree *t, const double *u_host, int64_t m, int64
 {
     if (!t || m < 0 || !root_out) return fail(ST_ERR_ARG, "st_sample_root_host: bad argument");
     device_guard g(t->device);
+    {
+        const size_t up = 256;
+        auto rnd = [&](size_t b) { return (b + up - 1) / up * up; };
+        const size_t o_u = 0, o_out = o_u + rnd(m * sizeof(double)), o_root = o_out + rnd(m * sizeof(int64_t));
+        if (o_root + up <= t->pin_bytes) {
+            char *hp = (char *)t->h_pin, *dp = (char *)t->d_pin;
+            memcpy(hp + o_u, u_host, m * sizeof(double));
+            if (m) CU(st::launch_sample(t, (const double *)(dp + o_u), m, (int64_t *)(dp + o_out), nullptr, nullptr, 0));
+            CU(st::launch_publish(t, nullptr, dp + o_root, 0));
+            CU(cudaStreamSynchronize(0));
+            memcpy(out_host, hp + o_out, m * sizeof(int64_t));
+            memcpy(root_out, hp + o_root, t->esize);
+            return ST_OK;
+        }
+    }
     scratch_carver sc(t);
     sc.add(m * sizeof(double)); sc.add(m * sizeof(int64_t));
     CU(sc.commit());
@@ -453,6 +499,17 @@ int st_search_host(const st_tree *t, const void *vals_host, int64_t m, int64_t *
     if (!t || m < 0) return fail(ST_ERR_ARG, "st_search_host: bad argument");
     if (m == 0) return ST_OK;
     device_guard g(t->device);
+    {
+        const size_t o_out = ((size_t)m * t->esize + 255) / 256 * 256;
+        if (o_out + (size_t)m * sizeof(int64_t) <= t->pin_bytes) {
+            char *hp = (char *)t->h_pin, *dp = (char *)t->d_pin;
+            memcpy(hp, vals_host, (size_t)m * t->esize);
+            CU(st::launch_search(t, dp, m, (int64_t *)(dp + o_out), 0));
+            CU(cudaStreamSynchronize(0));
+            memcpy(out_host, hp + o_out, (size_t)m * sizeof(int64_t));
+            return ST_OK;
+        }
+    }
     dev_buf dv, dout;
     scratch_carver sc(t);
     sc.add(m * t->esize); sc.add(m * sizeof(int64_t));
@@ -494,7 +551,9 @@ int st_root_host(const st_tree *t, void *out_scalar)
 {
     if (!t || !out_scalar) return fail(ST_ERR_ARG, "st_root_host: bad argument");
     device_guard g(t->device);
-    CU(cudaMemcpy(out_scalar, (const char *)t->heap + t->esize, t->esize, cudaMemcpyDeviceToHost));
+    CU(st::launch_publish(t, nullptr, t->d_pin, 0));
+    CU(cudaStreamSynchronize(0));
+    memcpy(out_scalar, t->h_pin, t->esize);
     return ST_OK;
 }
 
@@ -576,6 +635,42 @@ int st_poll_status(st_tree *t, void *stream, int clear)
     device_guard g(t->device);
     const int st = fetch_status(t, (cudaStream_t)stream, clear != 0);
     if (st != ST_OK) return fail(st, "%s", st_status_string(st));
+    return ST_OK;
+}
+
+// Keep the top of the heap (the levels every query and every update walk through) resident in L2:
+// reserve persisting L2 and attach an access-policy window over heap[0, bytes) to `stream`.
+// bytes <= 0 removes the window.  Returns the window size actually set through *granted.
+int st_set_l2_persistence(st_tree *t, void *stream, int64_t bytes, int64_t *granted)
+{
+    if (!t) return fail(ST_ERR_ARG, "st_set_l2_persistence: NULL tree");
+    device_guard g(t->device);
+    if (granted) *granted = 0;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, t->device));
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof(attr));
+    if (bytes <= 0) {
+        attr.accessPolicyWindow.num_bytes = 0;
+        CU(cudaStreamSetAttribute((cudaStream_t)stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+        CU(cudaCtxResetPersistingL2Cache());
+        return ST_OK;
+    }
+    size_t want = (size_t)bytes;
+    const size_t heap_bytes = (size_t)(2 * t->n) * t->esize;
+    if (want > heap_bytes) want = heap_bytes;
+    if (want > (size_t)prop.accessPolicyMaxWindowSize) want = (size_t)prop.accessPolicyMaxWindowSize;
+    size_t carve = want;
+    if (carve > (size_t)prop.persistingL2CacheMaxSize) carve = (size_t)prop.persistingL2CacheMaxSize;
+    if (carve == 0) return fail(ST_ERR_CUDA, "st_set_l2_persistence: device has no persisting L2");
+    CU(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve));
+    attr.accessPolicyWindow.base_ptr = t->heap;
+    attr.accessPolicyWindow.num_bytes = want;
+    attr.accessPolicyWindow.hitRatio = (float)((double)carve / (double)want);
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    CU(cudaStreamSetAttribute((cudaStream_t)stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+    if (granted) *granted = (int64_t)want;
     return ST_OK;
 }
 

@@ -27,7 +27,11 @@ struct st_tree {
     unsigned int *d_status = nullptr;  // device status word (+ spare counters), 64 words
     unsigned int *h_status = nullptr;  // pinned host mirror, 64 words
     st_workspace ws;
-    st_workspace scratch;   // grow-only staging area of the *_host entry points (no malloc/free per call)
+    st_workspace scratch;
+    // small host calls: inputs/outputs go through mapped pinned memory (no cudaMemcpy round trips)
+    void *h_pin = nullptr;   // host address
+    void *d_pin = nullptr;   // device alias of the same memory
+    size_t pin_bytes = 0;   // grow-only staging area of the *_host entry points (no malloc/free per call)
     int64_t reserved_batch = 0;
     int64_t cub_cap = -1;      // batch capacity for which cub_bytes was queried
     size_t cub_bytes = 0;
@@ -50,6 +54,7 @@ cudaError_t launch_build(st_tree *t, cudaStream_t s);         // skipped on devi
 cudaError_t launch_search(const st_tree *t, const void *vals, int64_t m, int64_t *out, cudaStream_t s);
 cudaError_t launch_sample(const st_tree *t, const double *u, int64_t m, int64_t *out, void *prio,
                           void *resid, cudaStream_t s);
+cudaError_t launch_publish(const st_tree *t, void *dst_status, void *dst_root, cudaStream_t s);  // tiny: status word + root
 cudaError_t launch_gather(const st_tree *t, const int64_t *idx, int64_t m, void *out, cudaStream_t s);
 cudaError_t launch_sum_over(const st_tree *t, int64_t a, int64_t b, void *out_dev, cudaStream_t s);
 cudaError_t launch_strided_sum(const st_tree *t, int64_t stride, void *out, int64_t nout, cudaStream_t s);

@@ -283,11 +283,11 @@ static cudaError_t launch_search_cfg(const st_tree *t, const void *in, int64_t m
     if (stage) {
         const size_t smem = (size_t)stage_nodes * sizeof(T);
         auto kern = search_kernel<T, true, UNIFORM, THREADS, Q>;
-        static bool attr_done = false;
-        if (!attr_done) {
+        static int attr_dev = -1;   // function attributes are per device
+        if (attr_dev != t->device) {
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
             if (e != cudaSuccess) return e;
-            attr_done = true;
+            attr_dev = t->device;
         }
         unsigned g = grid_for(m, (int)per_block, (int64_t)t->sm_count * 3);
         ++g_kernel_launches;
@@ -322,6 +322,28 @@ cudaError_t launch_sample(const st_tree *t, const double *u, int64_t m, int64_t 
 {
     ST_DISPATCH(t->dtype, return (launch_search_t<T, true>(t, u, m, out, prio, resid, s)));
     return cudaSuccess;
+}
+
+// =========================================================================================
+// publish the status word and the root into (mapped pinned) memory the host can read after a sync
+// =========================================================================================
+template <typename T>
+__global__ void publish_kernel(const T *__restrict__ H, const unsigned int *__restrict__ status,
+                               unsigned int *dst_status, T *dst_root)
+{
+    if (threadIdx.x == 0) {
+        if (dst_status) *dst_status = *status;
+        if (dst_root) *dst_root = H[1];
+    }
+}
+
+cudaError_t launch_publish(const st_tree *t, void *dst_status, void *dst_root, cudaStream_t s)
+{
+    ST_DISPATCH(t->dtype, {
+        ++g_kernel_launches;
+        publish_kernel<T><<<1, 32, 0, s>>>((const T *)t->heap, t->d_status, (unsigned int *)dst_status, (T *)dst_root);
+    });
+    return cudaGetLastError();
 }
 
 // =========================================================================================

@@ -594,21 +594,21 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
             sp.ret_key = w.ret_key; sp.ret_se = w.ret_se;
             g_kernel_launches += 2;
             if (m <= SMALL_THREADS) {
-                static bool attr1 = false;
-                if (!attr1) {
+                static int attr1 = -1;   // function attributes are per device
+                if (attr1 != t->device) {
                     cudaError_t ea = cudaFuncSetAttribute(update_small_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                           (int)small_smem_bytes<T, 1>());
                     if (ea != cudaSuccess) return ea;
-                    attr1 = true;
+                    attr1 = t->device;
                 }
                 update_small_kernel<T, 1><<<1, SMALL_THREADS, small_smem_bytes<T, 1>(), s>>>(sp);
             } else {
-                static bool attr4 = false;
-                if (!attr4) {
+                static int attr4 = -1;
+                if (attr4 != t->device) {
                     cudaError_t ea = cudaFuncSetAttribute(update_small_kernel<T, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                           (int)small_smem_bytes<T, 4>());
                     if (ea != cudaSuccess) return ea;
-                    attr4 = true;
+                    attr4 = t->device;
                 }
                 update_small_kernel<T, 4><<<1, SMALL_THREADS, small_smem_bytes<T, 4>(), s>>>(sp);
             }
@@ -664,11 +664,12 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
             pp.Z = w.zcount; pp.tilesum = w.tilesum;
             pp.qlong = w.queue; pp.qmed = w.queue_med; pp.qhuge = w.queue_huge; pp.huge_off = w.huge_off;
             pp.status = status;
-            static int occ = 0;
-            if (!occ) {
+            static int occ = 0, occ_dev = -1;
+            if (occ_dev != t->device) {
                 e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, partition_levels_kernel<T>, PART_THREADS, 0);
                 if (e != cudaSuccess) return e;
                 if (occ < 1) return cudaErrorCooperativeLaunchTooLarge;
+                occ_dev = t->device;
             }
             // balanced persistent grid: every CTA gets the same number of tiles (the grid barriers wait
             // for the slowest CTA)
