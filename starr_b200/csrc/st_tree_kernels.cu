@@ -24,16 +24,34 @@ __global__ void __launch_bounds__(256) check_leaves_kernel(const T *__restrict__
     } else {
         bool bad = false;
         const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-        int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-        // 8 independent loads in flight per thread
-        for (; i + 7 * stride < n; i += 8 * stride) {
-            T v[8];
+        const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        // 128-bit streaming loads over the 16-byte aligned middle, scalars for the ragged ends
+        constexpr int VEC = 16 / (int)sizeof(T);
+        const uintptr_t addr = reinterpret_cast<uintptr_t>(leaves);
+        int64_t head = (int64_t)(((16 - (addr & 15)) & 15) / sizeof(T));
+        if (head > n) head = n;
+        const int64_t nvec = (n - head) / VEC;
+        const int4 *v4 = reinterpret_cast<const int4 *>(leaves + head);
+        int64_t i = tid;
+        for (; i + 3 * stride < nvec; i += 4 * stride) {
+            int4 q[4];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = __ldg(leaves + i + k * stride);
+            for (int k = 0; k < 4; ++k) q[k] = __ldg(v4 + i + k * stride);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) bad |= (v[k] < T(0));
+            for (int k = 0; k < 4; ++k) {
+                const T *e = reinterpret_cast<const T *>(&q[k]);
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) bad |= (e[j] < T(0));
+            }
         }
-        for (; i < n; i += stride) bad |= (__ldg(leaves + i) < T(0));
+        for (; i < nvec; i += stride) {
+            const int4 q = __ldg(v4 + i);
+            const T *e = reinterpret_cast<const T *>(&q);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) bad |= (e[j] < T(0));
+        }
+        for (int64_t j = tid; j < head; j += stride) bad |= (leaves[j] < T(0));
+        for (int64_t j = head + nvec * VEC + tid; j < n; j += stride) bad |= (leaves[j] < T(0));
         if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(status, STF_NEG_ARRAY);
     }
 }
@@ -42,7 +60,7 @@ cudaError_t launch_check_leaves(st_tree *t, cudaStream_t s)
 {
     ST_DISPATCH(t->dtype, {
         const T *leaves = (const T *)t->heap + t->n;
-        unsigned g = grid_for(t->n, 256 * 8, (int64_t)t->sm_count * 8);
+        unsigned g = grid_for(t->n, 256 * 16, (int64_t)t->sm_count * 8);
         ++g_kernel_launches;
         check_leaves_kernel<T><<<g, 256, 0, s>>>(leaves, t->n, t->d_status);
     });
@@ -57,6 +75,7 @@ cudaError_t launch_check_leaves(st_tree *t, cudaStream_t s)
 // a leaf (loaded, never computed); h >= 2n does not exist.  Pairwise left+right is exactly
 // the reference's loop order-independent result (every node is one add of its two children).
 template <typename T> struct alignas(2 * sizeof(T)) pair_t { T l, r; };
+template <typename T> struct alignas(4 * sizeof(T)) quad_t { T a, b, c, d; };
 
 constexpr int BUILD_K = 11;        // levels per pass
 constexpr int BUILD_THREADS = 256;
@@ -75,17 +94,31 @@ build_pass_kernel(T *__restrict__ H, uint32_t n, int root_level, int k, const un
     {
         const uint32_t cnt = 1u << lev;
         const uint64_t base = (uint64_t)r << lev;
-        for (uint32_t i = threadIdx.x; i < cnt; i += BUILD_THREADS) {
-            const uint64_t h = base + i;
-            T v = T(0);
-            if (h < n) {
-                pair_t<T> c = *reinterpret_cast<const pair_t<T> *>(H + 2 * h);
-                v = t_add<T>(c.l, c.r);
-                H[h] = v;
-            } else if (h < two_n) {
-                v = H[h];
+        if (lev >= 1 && base + cnt <= n) {
+            // interior tile: two parents per thread from one aligned 4-child vector (16 B for 4-byte T)
+            for (uint32_t i = 2 * threadIdx.x; i < cnt; i += 2 * BUILD_THREADS) {
+                const uint64_t h = base + i;
+                quad_t<T> c = *reinterpret_cast<const quad_t<T> *>(H + 2 * h);
+                pair_t<T> o;
+                o.l = t_add<T>(c.a, c.b);
+                o.r = t_add<T>(c.c, c.d);
+                *reinterpret_cast<pair_t<T> *>(H + h) = o;
+                buf[0][i] = o.l;
+                buf[0][i + 1] = o.r;
             }
-            buf[0][i] = v;
+        } else {
+            for (uint32_t i = threadIdx.x; i < cnt; i += BUILD_THREADS) {
+                const uint64_t h = base + i;
+                T v = T(0);
+                if (h < n) {
+                    pair_t<T> c = *reinterpret_cast<const pair_t<T> *>(H + 2 * h);
+                    v = t_add<T>(c.l, c.r);
+                    H[h] = v;
+                } else if (h < two_n) {
+                    v = H[h];
+                }
+                buf[0][i] = v;
+            }
         }
     }
     int cur = 0;
