@@ -395,7 +395,8 @@ def run_ours(args):
         r_smp["traffic"] = traffic.get("search_kernel")
         dominant = r_upd if upd_ms >= smp_ms else r_smp
         if breakdown and breakdown["calls"]:
-            phases = {"partition_levels_kernel": breakdown["partition_ms"], "fold_scan_kernel": breakdown["fold_scan_ms"],
+            phases = {"partition_levels_kernel": breakdown["partition_ms"], "retire_kernel": breakdown["retire_ms"],
+                      "fold_scan_kernel": breakdown["fold_scan_ms"],
                       "fold_huge_maps_kernel": breakdown["huge_maps_ms"], "fold_huge_apply_kernel": breakdown["huge_apply_ms"],
                       "leaf_pass_kernel": breakdown["leaf_pass_ms"], "search_kernel": smp_ms / steps}
             top = max(phases, key=phases.get)

@@ -185,8 +185,9 @@ ST_API int st_set_l2_persistence(st_tree *t, void *stream, int64_t bytes, int64_
 
 /* Per-phase timing of the float update pipeline, measured with CUDA events on the launching
  * stream.  While enabled every update call waits for its own completion (profiling only).
- * out_ms[0..5] = accumulated milliseconds of: key build + leaf-order sort, leaf pass, top-down
- * partition kernel, huge-segment summaries, huge-segment stitch, ordered-fold kernel;
+ * out_ms[0..6] = accumulated milliseconds of: key build + leaf-order sort, leaf pass, top-down
+ * partition kernel, retirement of short segments, huge-segment summaries, huge-segment stitch,
+ * ordered-fold kernel;
  * out_ms[7] = number of update chunks accumulated. */
 ST_API int st_set_profiling(st_tree *t, int enable);
 ST_API int st_update_breakdown(const st_tree *t, double out_ms[8]);

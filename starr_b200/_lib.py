@@ -319,7 +319,7 @@ class TreeHandle:
     def update_breakdown(self) -> dict:
         out = (ctypes.c_double * 8)()
         check(lib().st_update_breakdown(self.ptr, out))
-        names = ("sort_ms", "leaf_pass_ms", "partition_ms", "huge_maps_ms", "huge_apply_ms", "fold_scan_ms")
+        names = ("sort_ms", "leaf_pass_ms", "partition_ms", "retire_ms", "huge_maps_ms", "huge_apply_ms", "fold_scan_ms")
         calls = max(out[7], 1.0)
         d = {n: out[i] / calls for i, n in enumerate(names)}
         d["calls"] = int(out[7])

@@ -37,13 +37,14 @@ template <typename T> struct part_params {
     int m;
     int ntiles;
     const uint32_t *key0;  // keys in batch order (level 0)
-    uint32_t *keyA, *keyB; // ping-pong for levels >= 1
+    uint32_t *lev_key;     // lev_key[l * lev_stride + i]: keys in level-l order for l >= 1 (kept for the retire kernel)
     T *lev_d;              // lev_d[l * lev_stride + i]: differences in level-l order; level 0 filled by caller
     int64_t lev_stride;
     int *sA, *eA, *sB, *eB;  // segment [s, e) of every element, ping-pong (level 0: [0, m))
     int *Z;                  // exclusive count of zero-bit elements before i
     unsigned int *tilesum;   // [2][PART_MAX_TILES] zero-bit counts per tile
     seg_entry *qlong, *qmed, *qhuge;
+    seg_entry *qret;       // short segments to retire (node unused): finished by retire_kernel after this kernel
     int *huge_off;   // first chunk record of every huge segment
     unsigned int *status;
 };
@@ -119,8 +120,8 @@ __global__ void __launch_bounds__(PART_THREADS) partition_levels_kernel(part_par
         const int cur = l & 1;
         const int sh = depth - l;            // node at this level = key >> sh
         const bool last = (l == depth - 1);
-        const uint32_t *key = (l == 0) ? p.key0 : (cur ? p.keyA : p.keyB);
-        uint32_t *keyN = cur ? p.keyB : p.keyA;   // level l+1 lives in A when l+1 is odd
+        const uint32_t *key = (l == 0) ? p.key0 : p.lev_key + (int64_t)l * p.lev_stride;
+        uint32_t *keyN = p.lev_key + (int64_t)(l + 1) * p.lev_stride;
         const int *sC = cur ? p.sA : p.sB, *eC = cur ? p.eA : p.eB;
         int *sN = cur ? p.sB : p.sA, *eN = cur ? p.eB : p.eA;
         const T *dC = p.lev_d + (int64_t)l * p.lev_stride;
@@ -167,34 +168,65 @@ __global__ void __launch_bounds__(PART_THREADS) partition_levels_kernel(part_par
                     kyv[k] = key[i];
                 }
             }
+            // what each element asks for: 1 = retire queue, 2 = medium queue, 3 = long queue (heads only)
+            int cls[PART_E];
 #pragma unroll
             for (int k = 0; k < PART_E; ++k) {
                 const int i = i0 + k * PART_THREADS;
                 zloc[k] = 0;
+                cls[k] = 0;
                 if (!(ev[k] & SEG_DONE)) {
                     const int s = sv[k], e = ev[k];
                     const int len = e - s;
                     const uint32_t ky = kyv[k];
                     if (len <= SHORT_SEG) {
-                        retire_segment_part<T>(p.H, s, e, i - s, l, depth, two_n, [&](int x) { return key[x]; },
-                                               [&](int x) { return dC[x]; });
+                        if (i == s) cls[k] = 1;   // retire_kernel finishes it on all SMs
                     } else {
                         if (i == s && l < key_leaf_level(ky, two_n, depth)) {
-                            const uint32_t node = ky >> sh;
                             if (len > HUGE_SEG) {
                                 const unsigned int slot = atomicAdd(p.status + SW_QCOUNT_HUGE, 1u);
-                                p.qhuge[slot] = seg_entry{l, s, len, node};
+                                p.qhuge[slot] = seg_entry{l, s, len, ky >> sh};
                                 p.huge_off[slot] = (int)atomicAdd(p.status + SW_HUGE_CHUNKS,
                                                                   (unsigned int)((len + FOLD_CHUNK_ELEMS - 1) / FOLD_CHUNK_ELEMS));
-                            } else if (len > MEDIUM_SEG) {
-                                p.qlong[atomicAdd(p.status + SW_QCOUNT, 1u)] = seg_entry{l, s, len, node};
                             } else {
-                                p.qmed[atomicAdd(p.status + SW_QCOUNT_MED, 1u)] = seg_entry{l, s, len, node};
+                                cls[k] = len > MEDIUM_SEG ? 3 : 2;
                             }
                         }
                         if (i == s) p.status[SW_ANYLONG + (l & 1)] = 1;   // another split is needed
                         if (!last) zloc[k] = ((ky >> (sh - 1)) & 1u) ^ 1u;
                     }
+                }
+            }
+            // queue slots: ONE atomic per warp and queue for the warp's 256 elements (the counters are
+            // single addresses; per-head atomics would serialise hundreds of thousands of them in L2)
+            {
+                const int ln = tid & 31;
+                const unsigned int lt = (1u << ln) - 1u;
+                unsigned int b1[PART_E], b2[PART_E], b3[PART_E];
+                unsigned int c1 = 0, c2 = 0, c3 = 0;
+#pragma unroll
+                for (int k = 0; k < PART_E; ++k) {
+                    b1[k] = __ballot_sync(0xffffffffu, cls[k] == 1);
+                    b2[k] = __ballot_sync(0xffffffffu, cls[k] == 2);
+                    b3[k] = __ballot_sync(0xffffffffu, cls[k] == 3);
+                    c1 += __popc(b1[k]); c2 += __popc(b2[k]); c3 += __popc(b3[k]);
+                }
+                unsigned int q1 = 0, q2 = 0, q3 = 0;
+                if (ln == 0) {
+                    if (c1) q1 = atomicAdd(p.status + SW_QCOUNT_RET, c1);
+                    if (c2) q2 = atomicAdd(p.status + SW_QCOUNT_MED, c2);
+                    if (c3) q3 = atomicAdd(p.status + SW_QCOUNT, c3);
+                }
+                q1 = __shfl_sync(0xffffffffu, q1, 0);
+                q2 = __shfl_sync(0xffffffffu, q2, 0);
+                q3 = __shfl_sync(0xffffffffu, q3, 0);
+#pragma unroll
+                for (int k = 0; k < PART_E; ++k) {
+                    const int len = ev[k] - sv[k];
+                    if (cls[k] == 1) p.qret[q1 + __popc(b1[k] & lt)] = seg_entry{l, sv[k], len, 0u};
+                    if (cls[k] == 2) p.qmed[q2 + __popc(b2[k] & lt)] = seg_entry{l, sv[k], len, kyv[k] >> sh};
+                    if (cls[k] == 3) p.qlong[q3 + __popc(b3[k] & lt)] = seg_entry{l, sv[k], len, kyv[k] >> sh};
+                    q1 += __popc(b1[k]); q2 += __popc(b2[k]); q3 += __popc(b3[k]);
                 }
             }
             if (!last) {

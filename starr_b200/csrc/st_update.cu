@@ -49,6 +49,8 @@ struct update_ws {
     void *huge_recs;
     int *seg_sa, *seg_ea, *seg_sb, *seg_eb, *zcount;
     uint32_t *ret_key, *ret_se;
+    uint32_t *lev_key;
+    seg_entry *queue_ret;
     unsigned int *tilesum;
     void *cub_tmp;
     size_t cub_bytes;
@@ -87,6 +89,8 @@ static update_ws carve(const st_tree *t, int64_t B, char *base)
         w.seg_sb = (int *)take(B * 4);
         w.seg_eb = (int *)take(B * 4);
         w.zcount = (int *)take(B * 4);
+        w.lev_key = (uint32_t *)take((size_t)(t->depth + 1) * B * 4);
+        w.queue_ret = (seg_entry *)take((size_t)(B + 32) * sizeof(seg_entry));
         w.ret_key = (uint32_t *)take((size_t)(t->depth + 1) * SMALL_M * 4);
         w.ret_se = (uint32_t *)take((size_t)(t->depth + 1) * SMALL_M * 4);
         w.tilesum = (unsigned int *)take(2 * PART_MAX_TILES * sizeof(unsigned int));
@@ -148,7 +152,7 @@ __global__ void __launch_bounds__(256) make_keys_kernel(const int64_t *__restric
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j == 0) { status[SW_QCOUNT] = 0; status[SW_QTAKE] = 0; status[SW_QCOUNT_MED] = 0; status[SW_QTAKE_MED] = 0;
                   status[SW_QCOUNT_HUGE] = 0; status[SW_HUGE_CHUNKS] = 0; status[SW_QTAKE_HUGE] = 0;
-                  status[SW_ANYLONG] = 0; status[SW_ANYLONG + 1] = 0; }
+                  status[SW_ANYLONG] = 0; status[SW_ANYLONG + 1] = 0; status[SW_QCOUNT_RET] = 0; }
     if (j >= m) return;
     const uint32_t h = (uint32_t)idx[j] + n;
     const uint32_t key = h << (depth - heap_level(h));
@@ -352,6 +356,50 @@ __global__ void __launch_bounds__(FOLD_THREADS) fold_scan_kernel(T *__restrict__
         const T *src = lev_d + (int64_t)s.level * level_stride + s.start;
         const T r = ordered_fold_warp<T>(H[s.node], src, s.len, s_stage[warp]);
         if (lane == 0) H[s.node] = r;
+    }
+}
+
+// Retirement of short segments (queued by the partition kernel): one warp per segment, lane r holds
+// the r-th update (key, difference) and takes levels l + r, l + r + len, ...; for each of its levels
+// it walks the updates in batch order (register shuffles) and issues the ordered atomic adds.  All
+// adds to one node come from one lane in batch order (ordered_add); the ~12 M random node updates
+// of a 2^20 batch spread over every SM at full occupancy instead of stalling the cooperative kernel.
+template <typename T>
+__global__ void __launch_bounds__(256) retire_kernel(T *__restrict__ H, uint32_t n, int depth,
+                                                     const uint32_t *__restrict__ key0,
+                                                     const uint32_t *__restrict__ lev_key,
+                                                     const T *__restrict__ lev_d, int64_t lev_stride,
+                                                     const seg_entry *__restrict__ qret, const unsigned int *status)
+{
+    if (status[SW_STATUS]) return;
+    const unsigned int total = status[SW_QCOUNT_RET];
+    const uint64_t two_n = 2ull * n;
+    const int lane = threadIdx.x & 31;
+    const unsigned int warps = gridDim.x * (blockDim.x >> 5);
+    for (unsigned int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < total; w += warps) {
+        const seg_entry s = qret[w];
+        const int l = s.level, len = s.len;
+        const uint32_t *kp = (l == 0 ? key0 : lev_key + (int64_t)l * lev_stride) + s.start;
+        const T *dp = lev_d + (int64_t)l * lev_stride + s.start;
+        uint32_t ky = 0;
+        T dv = T(0);
+        if (lane < len) {
+            ky = kp[lane];
+            dv = dp[lane];
+        }
+        const int iters = (depth - l + len - 1) / len;
+        for (int it = 0; it < iters; ++it) {
+            const int l2 = l + lane + it * len;
+            const bool mine = lane < len && l2 < depth;
+            const int sh = depth - l2;
+            for (int x = 0; x < len; ++x) {
+                const uint32_t kx = __shfl_sync(0xffffffffu, ky, x);
+                T dx;
+                if constexpr (sizeof(T) == 8) dx = __longlong_as_double(__shfl_sync(0xffffffffu, __double_as_longlong(dv), x));
+                else dx = __shfl_sync(0xffffffffu, dv, x);
+                if (mine && l2 < key_leaf_level(kx, two_n, depth)) ordered_add<T>(H + (kx >> sh), dx);
+            }
+        }
     }
 }
 
@@ -658,11 +706,12 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
             part_params<T> pp;
             pp.H = H; pp.n = n; pp.depth = depth; pp.m = m;
             pp.ntiles = (m + PART_TILE - 1) / PART_TILE;
-            pp.key0 = w.kj; pp.keyA = w.keys_a; pp.keyB = w.keys_b;
+            pp.key0 = w.kj; pp.lev_key = w.lev_key;
             pp.lev_d = lev; pp.lev_stride = B;
             pp.sA = w.seg_sa; pp.eA = w.seg_ea; pp.sB = w.seg_sb; pp.eB = w.seg_eb;
             pp.Z = w.zcount; pp.tilesum = w.tilesum;
             pp.qlong = w.queue; pp.qmed = w.queue_med; pp.qhuge = w.queue_huge; pp.huge_off = w.huge_off;
+            pp.qret = w.queue_ret;
             pp.status = status;
             static int occ = 0, occ_dev = -1;
             if (occ_dev != t->device) {
@@ -698,21 +747,26 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
             }
         }
         using REC = chunk_rec<typename fp_bits<T>::I>;
-        g_kernel_launches += 3;
         mark(3);
+        if (!use_v1) {
+            ++g_kernel_launches;
+            retire_kernel<T><<<t->sm_count * 8, 256, 0, s>>>(H, n, depth, w.kj, w.lev_key, lev, B, w.queue_ret, status);
+        }
+        g_kernel_launches += 3;
+        mark(4);
         fold_huge_maps_kernel<T, false><<<t->sm_count * 2, FOLD_THREADS, 0, s>>>(H, lev, B, w.queue_huge, w.huge_off,
                                                                                 (REC *)w.huge_recs, status, nullptr, 0, 0);
-        mark(4);
+        mark(5);
         fold_huge_apply_kernel<T, false><<<t->sm_count, FOLD_THREADS, 0, s>>>(H, lev, B, w.queue_huge, w.huge_off,
                                                                              (const REC *)w.huge_recs, status, nullptr, 0, 0);
-        mark(5);
+        mark(6);
         fold_scan_kernel<T><<<t->sm_count * 8, FOLD_THREADS, 0, s>>>(H, lev, B, w.queue, w.queue_med, status,
                                                                         retire_params<T>{nullptr, nullptr, 0, 0, 0, 0});
-        mark(6);
+        mark(7);
         if (t->profile) {
             // profiling mode is synchronous by design (bench.py's roofline leg only)
-            cudaEventSynchronize(t->prof_ev[6]);
-            for (int k = 0; k < 6; ++k) {
+            cudaEventSynchronize(t->prof_ev[7]);
+            for (int k = 0; k < 7; ++k) {
                 float ms = 0.f;
                 cudaEventElapsedTime(&ms, t->prof_ev[k], t->prof_ev[k + 1]);
                 t->prof_ms[k] += ms;
