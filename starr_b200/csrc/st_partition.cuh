@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(PART_THREADS) partition_levels_kernel(part_par
     // ---- P0: zero counts of the first split bit per tile; clear the other counter set -----------
     for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
         unsigned int z = 0;
-        if (depth >= 2 && m > SHORT_SEG) {
+        if (depth >= 2 && m > RETIRE_SEG) {
 #pragma unroll
             for (int k = 0; k < PART_E; ++k) {
                 const int i = t * PART_TILE + k * PART_THREADS + tid;
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(PART_THREADS) partition_levels_kernel(part_par
                     const int s = sv[k], e = ev[k];
                     const int len = e - s;
                     const uint32_t ky = kyv[k];
-                    if (len <= SHORT_SEG) {
+                    if (len <= RETIRE_SEG) {
                         if (i == s) cls[k] = 1;   // retire_kernel finishes it on all SMs
                     } else {
                         if (i == s && l < key_leaf_level(ky, two_n, depth)) {
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(PART_THREADS) partition_levels_kernel(part_par
             for (int k = 0; k < PART_E; ++k) {
                 const int i = i0 + k * PART_THREADS;
                 const int e = ev[k] & ~SEG_DONE;
-                moving[k] = live[k] && !(ev[k] & SEG_DONE) && (e - sv[k] > SHORT_SEG);
+                moving[k] = live[k] && !(ev[k] & SEG_DONE) && (e - sv[k] > RETIRE_SEG);
                 zsv[k] = zev[k] = ziv[k] = 0;
                 dv[k] = T(0);
                 if (moving[k]) {
@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(PART_THREADS) partition_levels_kernel(part_par
                         dN[np] = dv[k];
                         sN[np] = s2;
                         eN[np] = e2;
-                        if (need_next && e2 - s2 > SHORT_SEG) znext[k] = ((ky >> (sh - 2)) & 1u) ^ 1u;
+                        if (need_next && e2 - s2 > RETIRE_SEG) znext[k] = ((ky >> (sh - 2)) & 1u) ^ 1u;
                     }
                 }
             }

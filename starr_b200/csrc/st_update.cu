@@ -48,7 +48,6 @@ struct update_ws {
     int *huge_off;
     void *huge_recs;
     int *seg_sa, *seg_ea, *seg_sb, *seg_eb, *zcount;
-    uint32_t *ret_key, *ret_se;
     uint32_t *lev_key;
     seg_entry *queue_ret;
     unsigned int *tilesum;
@@ -91,8 +90,6 @@ static update_ws carve(const st_tree *t, int64_t B, char *base)
         w.zcount = (int *)take(B * 4);
         w.lev_key = (uint32_t *)take((size_t)(t->depth + 1) * B * 4);
         w.queue_ret = (seg_entry *)take((size_t)(B + 32) * sizeof(seg_entry));
-        w.ret_key = (uint32_t *)take((size_t)(t->depth + 1) * SMALL_M * 4);
-        w.ret_se = (uint32_t *)take((size_t)(t->depth + 1) * SMALL_M * 4);
         w.tilesum = (unsigned int *)take(2 * PART_MAX_TILES * sizeof(unsigned int));
     }
     if (t->cub_cap != B) {
@@ -300,6 +297,12 @@ __global__ void __launch_bounds__(256) fold_level_kernel(T *__restrict__ H, uint
     }
 }
 
+template <typename T>
+__device__ __forceinline__ void retire_warps(T *__restrict__ H, uint32_t n, int depth, const uint32_t *__restrict__ key0,
+                                             const uint32_t *__restrict__ lev_key, const T *__restrict__ lev_d,
+                                             int64_t lev_stride, const seg_entry *__restrict__ qret, unsigned int total,
+                                             unsigned int warp_id, unsigned int warps);
+
 // Queued segments: exact parallel ordered folds (st_ordered_fold.cuh).  CTAs first drain the
 // queue of long segments (one CTA each), then their warps drain the queue of medium segments
 // (one warp each).
@@ -316,22 +319,11 @@ __global__ void __launch_bounds__(FOLD_THREADS) fold_scan_kernel(T *__restrict__
     __shared__ I s_mviol;
     __shared__ fold_smem_ctl ctl;
     __shared__ T s_stage[FOLD_THREADS / 32][FOLDW_PAD];
-    if (ret.key) {
-        // small-batch path: retire the short segments the single-CTA kernel marked (st_update_small.cuh)
-        const unsigned int mask = status[SW_RETIRE_MASK];
-        const uint64_t two_n = 2ull * ret.n;
-        for (int l = 0; l < ret.depth; ++l) {
-            if (!((mask >> l) & 1u)) continue;
-            const uint32_t *kl = ret.key + (size_t)l * ret.stride, *sl = ret.se + (size_t)l * ret.stride;
-            const T *dl = lev_d + (int64_t)l * level_stride;
-            for (int i = blockIdx.x * FOLD_THREADS + threadIdx.x; i < ret.m; i += gridDim.x * FOLD_THREADS) {
-                const uint32_t se = sl[i];
-                const int s = (int)(se & 0xffffu), e = (int)((se >> 16) & 0x7fffu);
-                if (!(se & 0x80000000u) && e - s <= SHORT_SEG)
-                    retire_segment_part<T>(H, s, e, i - s, l, ret.depth, two_n, [&](int x) { return kl[x]; },
-                                           [&](int x) { return dl[x]; });
-            }
-        }
+    if (ret.qret) {
+        // small-batch path: retire the segments the single-CTA kernel queued (st_update_small.cuh)
+        retire_warps<T>(H, ret.n, ret.depth, ret.key0, ret.lev_key, lev_d, level_stride, ret.qret,
+                        status[SW_QCOUNT_RET], blockIdx.x * (FOLD_THREADS >> 5) + (threadIdx.x >> 5),
+                        gridDim.x * (FOLD_THREADS >> 5));
     }
     const unsigned int n_long = status[SW_QCOUNT];
     for (;;) {
@@ -359,11 +351,50 @@ __global__ void __launch_bounds__(FOLD_THREADS) fold_scan_kernel(T *__restrict__
     }
 }
 
-// Retirement of short segments (queued by the partition kernel): one warp per segment, lane r holds
-// the r-th update (key, difference) and takes levels l + r, l + r + len, ...; for each of its levels
-// it walks the updates in batch order (register shuffles) and issues the ordered atomic adds.  All
-// adds to one node come from one lane in batch order (ordered_add); the ~12 M random node updates
-// of a 2^20 batch spread over every SM at full occupancy instead of stalling the cooperative kernel.
+// Retirement (queued by the partition kernel): a segment of <= RETIRE_SEG updates, batch-ordered, is
+// finished for its node AND every deeper level with ordered atomic adds -- no further partitioning,
+// no scan.  One warp per segment, LANE = LEVEL: lane k owns level l + k.  The warp streams the
+// segment 32 updates at a time (coalesced loads), broadcasts them one by one (shuffles), and every
+// lane adds the update to its level's ancestor.  All adds to one node therefore come from one lane
+// in batch order (ordered_add); the random node updates of a 2^20 batch spread over every SM at
+// full occupancy instead of stalling the cooperative kernel.
+template <typename T>
+__device__ __forceinline__ void retire_warps(T *__restrict__ H, uint32_t n, int depth,
+                                             const uint32_t *__restrict__ key0,
+                                             const uint32_t *__restrict__ lev_key,
+                                             const T *__restrict__ lev_d, int64_t lev_stride,
+                                             const seg_entry *__restrict__ qret, unsigned int total,
+                                             unsigned int warp_id, unsigned int warps)
+{
+    const uint64_t two_n = 2ull * n;
+    const int lane = threadIdx.x & 31;
+    for (unsigned int w = warp_id; w < total; w += warps) {
+        const seg_entry s = qret[w];
+        const int l = s.level, len = s.len;
+        const uint32_t *kp = (l == 0 ? key0 : lev_key + (int64_t)l * lev_stride) + s.start;
+        const T *dp = lev_d + (int64_t)l * lev_stride + s.start;
+        const int l2 = l + lane;              // this lane's level
+        const bool have_level = l2 < depth;
+        const int sh = depth - l2;
+        for (int base = 0; base < len; base += 32) {
+            uint32_t ky = 0;
+            T dv = T(0);
+            if (base + lane < len) {
+                ky = kp[base + lane];
+                dv = dp[base + lane];
+            }
+            const int cnt = len - base < 32 ? len - base : 32;
+            for (int x = 0; x < cnt; ++x) {
+                const uint32_t kx = __shfl_sync(0xffffffffu, ky, x);
+                T dx;
+                if constexpr (sizeof(T) == 8) dx = __longlong_as_double(__shfl_sync(0xffffffffu, __double_as_longlong(dv), x));
+                else dx = __shfl_sync(0xffffffffu, dv, x);
+                if (have_level && l2 < key_leaf_level(kx, two_n, depth)) ordered_add<T>(H + (kx >> sh), dx);
+            }
+        }
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) retire_kernel(T *__restrict__ H, uint32_t n, int depth,
                                                      const uint32_t *__restrict__ key0,
@@ -372,35 +403,8 @@ __global__ void __launch_bounds__(256) retire_kernel(T *__restrict__ H, uint32_t
                                                      const seg_entry *__restrict__ qret, const unsigned int *status)
 {
     if (status[SW_STATUS]) return;
-    const unsigned int total = status[SW_QCOUNT_RET];
-    const uint64_t two_n = 2ull * n;
-    const int lane = threadIdx.x & 31;
-    const unsigned int warps = gridDim.x * (blockDim.x >> 5);
-    for (unsigned int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < total; w += warps) {
-        const seg_entry s = qret[w];
-        const int l = s.level, len = s.len;
-        const uint32_t *kp = (l == 0 ? key0 : lev_key + (int64_t)l * lev_stride) + s.start;
-        const T *dp = lev_d + (int64_t)l * lev_stride + s.start;
-        uint32_t ky = 0;
-        T dv = T(0);
-        if (lane < len) {
-            ky = kp[lane];
-            dv = dp[lane];
-        }
-        const int iters = (depth - l + len - 1) / len;
-        for (int it = 0; it < iters; ++it) {
-            const int l2 = l + lane + it * len;
-            const bool mine = lane < len && l2 < depth;
-            const int sh = depth - l2;
-            for (int x = 0; x < len; ++x) {
-                const uint32_t kx = __shfl_sync(0xffffffffu, ky, x);
-                T dx;
-                if constexpr (sizeof(T) == 8) dx = __longlong_as_double(__shfl_sync(0xffffffffu, __double_as_longlong(dv), x));
-                else dx = __shfl_sync(0xffffffffu, dv, x);
-                if (mine && l2 < key_leaf_level(kx, two_n, depth)) ordered_add<T>(H + (kx >> sh), dx);
-            }
-        }
-    }
+    retire_warps<T>(H, n, depth, key0, lev_key, lev_d, lev_stride, qret, status[SW_QCOUNT_RET],
+                    blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), gridDim.x * (blockDim.x >> 5));
 }
 
 // Huge segments, phase A: every CTA summarises chunks (see st_ordered_fold.cuh).
@@ -639,7 +643,7 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
             sp.H = H; sp.n = n; sp.depth = depth; sp.m = m; sp.idx = idx; sp.vals = vals;
             sp.nv = (uint64_t)nv; sp.j0 = (uint64_t)j0; sp.deltas_in = deltas_in; sp.delta_out = delta_out;
             sp.lev_d = (T *)w.lev_d; sp.lev_stride = B; sp.qlong = w.queue; sp.qmed = w.queue_med; sp.status = status;
-            sp.ret_key = w.ret_key; sp.ret_se = w.ret_se;
+            sp.qret = w.queue_ret; sp.key0_out = w.kj; sp.lev_key = w.lev_key;
             g_kernel_launches += 2;
             if (m <= SMALL_THREADS) {
                 static int attr1 = -1;   // function attributes are per device
@@ -660,7 +664,7 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
                 }
                 update_small_kernel<T, 4><<<1, SMALL_THREADS, small_smem_bytes<T, 4>(), s>>>(sp);
             }
-            retire_params<T> rp{w.ret_key, w.ret_se, m, depth, SMALL_M, n};
+            retire_params<T> rp{w.queue_ret, w.kj, w.lev_key, depth, n};
             fold_scan_kernel<T><<<t->sm_count, FOLD_THREADS, 0, s>>>(H, (const T *)w.lev_d, B, w.queue, w.queue_med,
                                                                     status, rp);
             return cudaGetLastError();
@@ -761,7 +765,7 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
                                                                              (const REC *)w.huge_recs, status, nullptr, 0, 0);
         mark(6);
         fold_scan_kernel<T><<<t->sm_count * 8, FOLD_THREADS, 0, s>>>(H, lev, B, w.queue, w.queue_med, status,
-                                                                        retire_params<T>{nullptr, nullptr, 0, 0, 0, 0});
+                                                                        retire_params<T>{nullptr, nullptr, nullptr, 0, 0});
         mark(7);
         if (t->profile) {
             // profiling mode is synchronous by design (bench.py's roofline leg only)

@@ -6,6 +6,10 @@ namespace st {
 
 constexpr int64_t UPDATE_MAX_CHUNK = 1 << 20;
 constexpr int SHORT_SEG = 32;    // segments up to this length are folded by their head thread
+#ifndef ST_RETIRE_SEG
+#define ST_RETIRE_SEG 512
+#endif
+constexpr int RETIRE_SEG = ST_RETIRE_SEG;  // multi-CTA path: segments up to this length are retired with ordered atomics
 constexpr int MEDIUM_SEG = 2048;  // up to this length by one warp, longer ones by one CTA
 constexpr int HUGE_SEG = 16384;   // longer than this: all CTAs summarise chunks, one CTA stitches them
 
@@ -75,13 +79,13 @@ __device__ __forceinline__ void retire_segment_part(T *H, int s, int e, int r, i
 
 constexpr int SEG_DONE = 1 << 30;
 
-// small-batch path: levels whose short segments are retired by the follow-up kernel (spread over
-// all SMs instead of one) keep their ordered keys / differences / segment bounds in global memory
+// small-batch path: the single-CTA kernel queues its retirements for the follow-up kernel
 template <typename T> struct retire_params {
-    const uint32_t *key;   // [level][SMALL stride]
-    const uint32_t *se;    // packed s | e << 16 | done << 31
-    int m, depth, stride;
+    const seg_entry *qret;     // nullptr: nothing to retire in this launch
+    const uint32_t *key0;      // level-0 keys (batch order)
+    const uint32_t *lev_key;   // [level][lev_stride]
+    int depth;
     uint32_t n;
-};   // flag in the stored segment end: the segment has been retired
+};
 
 }  // namespace st

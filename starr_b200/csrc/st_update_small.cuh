@@ -2,7 +2,7 @@
 // BASELINE config #2) in ONE CTA: validation, key build, block radix sort, leaf pass and the whole
 // top-down ordered partition run out of shared memory with __syncthreads instead of grid barriers
 // and extra launches.  Same arithmetic, same order, same results as the multi-CTA pipeline
-// (st_update.cu / st_partition.cuh): segments up to SHORT_SEG are folded inline, longer ones are
+// (st_update.cu / st_partition.cuh): segments up to SMALL_RETIRE_SEG are queued for retirement, longer ones are
 // queued with their level's ordered differences for the exact parallel ordered fold.
 #pragma once
 #include <cub/block/block_radix_sort.cuh>
@@ -14,7 +14,11 @@ namespace st {
 
 constexpr int SMALL_THREADS = 1024;
 constexpr int SMALL_M = SMALL_THREADS * 4;   // 4096: the largest batch of the single-CTA path (4 per thread)
-constexpr int SMALL_MEDIUM_SEG = 256;             // small batches: CTA fold above one warp chunk
+#ifndef ST_SMALL_RETIRE_SEG
+#define ST_SMALL_RETIRE_SEG 64
+#endif
+constexpr int SMALL_RETIRE_SEG = ST_SMALL_RETIRE_SEG;             // small batches: up to this length retired with ordered atomics,
+                                                  // longer segments go to the CTA fold
 
 template <typename T> struct small_params {
     T *H;
@@ -31,7 +35,9 @@ template <typename T> struct small_params {
     int64_t lev_stride;
     seg_entry *qlong, *qmed;
     unsigned int *status;
-    uint32_t *ret_key, *ret_se;   // [level][SMALL_M]: levels with retirements, for the follow-up kernel
+    seg_entry *qret;       // retirements for the follow-up kernel
+    uint32_t *key0_out;    // level-0 keys (batch order) for the follow-up kernel
+    uint32_t *lev_key;     // [level][lev_stride] keys of levels with retirements
 };
 
 template <typename T, int SMALL_E> struct small_smem {
@@ -43,6 +49,7 @@ template <typename T, int SMALL_E> struct small_smem {
     uint32_t wtot[SMALL_THREADS / 32];
     int flag;
     int flag_retire;
+    unsigned int nret;
 };
 
 template <int SMALL_E> using SmallSort = cub::BlockRadixSort<uint32_t, SMALL_THREADS, SMALL_E, int>;
@@ -134,6 +141,7 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) update_small_kernel(small_pa
         p.status[SW_QCOUNT_MED] = 0; p.status[SW_QTAKE_MED] = 0;
         p.status[SW_QCOUNT_HUGE] = 0; p.status[SW_HUGE_CHUNKS] = 0; p.status[SW_QTAKE_HUGE] = 0;
         p.status[SW_RETIRE_MASK] = 0;
+        p.status[SW_QCOUNT_RET] = 0;
     }
 
     ST_TICK(0);
@@ -213,9 +221,11 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) update_small_kernel(small_pa
         for (int j = tid; j < m; j += SMALL_THREADS) p.delta_out[j] = S.d[0][j];
 
     ST_TICK(2);
-    // ---- top-down ordered partition; a segment of <= SHORT_SEG updates is retired by its head for all
-    // remaining levels, and the loop ends as soon as no longer segment is left -----------------------------
+    // ---- top-down ordered partition; a segment of <= SMALL_RETIRE_SEG updates is queued for retirement
+    // (finished for all remaining levels by the follow-up kernel) and the loop ends as soon as no longer
+    // segment is left ------------------------------------------------------------------------------------
     constexpr uint32_t DONE = 0x80000000u;
+    if (tid == 0) S.nret = 0;
     for (int l = 0; l < depth; ++l) {
         const int c = l & 1;
         const int sh = depth - l;
@@ -247,19 +257,19 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) update_small_kernel(small_pa
                 const uint32_t ky = kreg[k];
                 const int s = (int)(sereg[k] & 0xffffu), e = (int)((sereg[k] >> 16) & 0x7fffu);
                 const int len = e - s;
-                if (len <= SHORT_SEG) {
+                if (len <= SMALL_RETIRE_SEG) {
                     // retired here; the adds themselves are issued by the follow-up kernel so that the
                     // random node updates spread over all SMs instead of queueing up on this one
-                    if (i == s) S.flag_retire = 1;
+                    if (i == s) {
+                        S.flag_retire = 1;
+                        p.qret[atomicAdd(&S.nret, 1u)] = seg_entry{l, s, len, 0u};
+                    }
                 } else {
                     anylong = 1;
                     if (i == s && l < key_leaf_level(ky, two_n, depth)) {
                         const uint32_t node = ky >> sh;
                         S.flag = 1;   // this level's ordered differences are needed by the fold kernel
-                        if (len > SMALL_MEDIUM_SEG)
-                            p.qlong[atomicAdd(p.status + SW_QCOUNT, 1u)] = seg_entry{l, s, len, node};
-                        else
-                            p.qmed[atomicAdd(p.status + SW_QCOUNT_MED, 1u)] = seg_entry{l, s, len, node};
+                        p.qlong[atomicAdd(p.status + SW_QCOUNT, 1u)] = seg_entry{l, s, len, node};
                     }
                     if (!last) zloc[k] = ((ky >> (sh - 1)) & 1u) ^ 1u;
                 }
@@ -272,12 +282,8 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) update_small_kernel(small_pa
             for (int i = tid; i < m; i += SMALL_THREADS) dst[i] = S.d[c][i];
         }
         if (S.flag_retire) {
-            uint32_t *kd = p.ret_key + (size_t)l * SMALL_M, *sd = p.ret_se + (size_t)l * SMALL_M;   // stride is always SMALL_M
-            for (int i = tid; i < m; i += SMALL_THREADS) {
-                kd[i] = S.key[c][i];
-                sd[i] = S.se[c][i];
-            }
-            if (tid == 0) atomicOr(p.status + SW_RETIRE_MASK, 1u << l);
+            uint32_t *kd = (l == 0) ? p.key0_out : p.lev_key + (int64_t)l * p.lev_stride;
+            for (int i = tid; i < m; i += SMALL_THREADS) kd[i] = S.key[c][i];
         }
         if (!more) break;    // only retired segments are left
         uint32_t ztotal = 0;
@@ -309,7 +315,7 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) update_small_kernel(small_pa
             const int i = tid * SMALL_E + k;
             if (i < m) {
                 const int s = (int)(sereg[k] & 0xffffu), e = (int)((sereg[k] >> 16) & 0x7fffu);
-                if ((sereg[k] & DONE) || e - s <= SHORT_SEG) {
+                if ((sereg[k] & DONE) || e - s <= SMALL_RETIRE_SEG) {
                     S.se[c ^ 1][i] = pack_se(s, e) | DONE;   // retired: stays put, never read again
                 } else {
                     const uint32_t ky = kreg[k];
@@ -331,6 +337,8 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) update_small_kernel(small_pa
         }
         __syncthreads();
     }
+    __syncthreads();
+    if (tid == 0) p.status[SW_QCOUNT_RET] = S.nret;
 }
 
 }  // namespace st
