@@ -758,7 +758,7 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
         }
         g_kernel_launches += 3;
         mark(4);
-        fold_huge_maps_kernel<T, false><<<t->sm_count * 2, FOLD_THREADS, 0, s>>>(H, lev, B, w.queue_huge, w.huge_off,
+        fold_huge_maps_kernel<T, false><<<t->sm_count * 8, FOLD_THREADS, 0, s>>>(H, lev, B, w.queue_huge, w.huge_off,
                                                                                 (REC *)w.huge_recs, status, nullptr, 0, 0);
         mark(5);
         fold_huge_apply_kernel<T, false><<<t->sm_count, FOLD_THREADS, 0, s>>>(H, lev, B, w.queue_huge, w.huge_off,
@@ -809,7 +809,7 @@ cudaError_t launch_fold_by_leaf_maps(st_tree *t, const int64_t *leaf, const void
     if (!fold_by_leaf_ok(t, m)) return cudaErrorInvalidValue;
     if (chunk_hi <= chunk_lo) return cudaSuccess;
     const int64_t pairs = (int64_t)(chunk_hi - chunk_lo) * (t->n - 1);
-    const unsigned g = (unsigned)(pairs < (int64_t)t->sm_count * 4 ? pairs : (int64_t)t->sm_count * 4);
+    const unsigned g = (unsigned)(pairs < (int64_t)t->sm_count * 8 ? pairs : (int64_t)t->sm_count * 8);
     ++g_kernel_launches;
     if (t->dtype == ST_F32)
         fold_top_maps_kernel<float><<<g, FOLD_THREADS, 0, s>>>((const float *)t->heap, (const float *)deltas, leaf, t->n,

@@ -11,7 +11,10 @@ constexpr int SHORT_SEG = 32;    // segments up to this length are folded by the
 #endif
 constexpr int RETIRE_SEG = ST_RETIRE_SEG;  // multi-CTA path: segments up to this length are retired with ordered atomics
 constexpr int MEDIUM_SEG = 2048;  // up to this length by one warp, longer ones by one CTA
-constexpr int HUGE_SEG = 16384;   // longer than this: all CTAs summarise chunks, one CTA stitches them
+#ifndef ST_HUGE_SEG
+#define ST_HUGE_SEG 16384
+#endif
+constexpr int HUGE_SEG = ST_HUGE_SEG;   // longer than this: all CTAs summarise chunks, one CTA stitches them
 
 struct seg_entry {
     int level;
