@@ -136,10 +136,33 @@ ST_API int st_apply_deltas_device(st_tree *t, const int64_t *idx_dev, int64_t ni
  * phase A writes one record per (chunk, internal node) at recs[(c*(n-1) + node-1) * record_bytes]
  * for chunk_lo <= c < chunk_hi; phase B needs the records of ALL ceil(m/1024) chunks. */
 ST_API int st_top_fold_record_bytes(const st_tree *t);
-ST_API int st_top_fold_maps_device(st_tree *t, const int64_t *leaf_dev, const void *deltas_dev, int64_t m,
-                            int64_t chunk_lo, int64_t chunk_hi, void *recs_dev, void *stream);
-ST_API int st_top_fold_apply_device(st_tree *t, const int64_t *leaf_dev, const void *deltas_dev, int64_t m,
-                             const void *recs_dev, void *stream);
+/* leaf ids: int64 (leaf_itemsize 8) or uint8 (leaf_itemsize 1, as written by st_shard_plan_device) */
+ST_API int st_top_fold_maps_device(st_tree *t, const void *leaf_dev, int leaf_itemsize, const void *deltas_dev,
+                            int64_t m, int64_t chunk_lo, int64_t chunk_hi, void *recs_dev, void *stream);
+ST_API int st_top_fold_apply_device(st_tree *t, const void *leaf_dev, int leaf_itemsize, const void *deltas_dev,
+                             int64_t m, const void *recs_dev, void *stream);
+/* Plan of one replicated batch of the sharded tree.  Element j belongs to shard ids[j] >> shift
+ * (0 <= shard < shards <= 64; anything else flags ST_ERR_INDEX on `local` and, if given, `top`,
+ * so that the whole batch is skipped on every rank alike; with check_negative a negative entry
+ * anywhere in payload flags ST_ERR_NEGATIVE_VALS the same way, pyx:37-39).  Writes
+ *   shard_out[j]   the owning shard (255 for an invalid id),
+ *   slot_out[j]    the stable position of j among the elements of its shard (-1 if invalid),
+ *   own_ids_out[k], own_payload_out[k]   (both nullable) for the k-th element of shard `rank`:
+ *                  ids[j] - (rank << shift) and payload[j % npayload] (tree dtype),
+ *   counts_out_host[s]   the number of elements of every shard -- the call waits for the stream. */
+ST_API int st_shard_plan_device(st_tree *local, st_tree *top, const int64_t *ids_dev, int64_t m, int shift, int shards,
+                         int rank, const void *payload_dev, int64_t npayload, int check_negative,
+                         uint8_t *shard_out_dev, int32_t *slot_out_dev, int64_t *own_ids_out_dev,
+                         void *own_payload_out_dev, int64_t *counts_out_host, void *stream);
+/* Per-shard results come back as slabs (shard s at slabs[s * slab_stride ...], compact, in the
+ * shard's batch order); these put them back into batch order:
+ *   values:  out[j] = slabs[shard[j] * slab_stride + slot[j]]               (tree dtype)
+ *   indices: out[j] = shard[j] * leaves_per_shard + slabs[...]              (int32 slabs -> int64) */
+ST_API int st_shard_expand_values_device(const st_tree *t, const uint8_t *shard_dev, const int32_t *slot_dev, int64_t m,
+                                  const void *slabs_dev, int64_t slab_stride, void *out_dev, void *stream);
+ST_API int st_shard_expand_indices_device(const st_tree *t, const uint8_t *shard_dev, const int32_t *slot_dev,
+                                   int64_t m, const int32_t *slabs_dev, int64_t slab_stride,
+                                   int64_t leaves_per_shard, int64_t *out_dev, void *stream);
 /* sample() descent that also returns the prefix left over at the leaf that was reached:
  * on the top tree this is (owning shard, query to continue with inside that shard). */
 ST_API int st_route_uniform_device(const st_tree *t, const double *u_dev, int64_t m, int64_t *leaf_out_dev,

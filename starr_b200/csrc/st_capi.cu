@@ -107,7 +107,7 @@ namespace st { unsigned long long g_kernel_launches = 0; }
 
 extern "C" {
 
-int st_abi_version(void) { return 1; }
+int st_abi_version(void) { return 2; }
 
 unsigned long long st_kernel_launches(void) { return st::g_kernel_launches; }
 
@@ -366,22 +366,72 @@ int st_apply_deltas_device(st_tree *t, const int64_t *idx_dev, int64_t ni, const
 
 int st_top_fold_record_bytes(const st_tree *t) { return t ? (int)st::fold_rec_bytes(t) : -1; }
 
-int st_top_fold_maps_device(st_tree *t, const int64_t *leaf_dev, const void *deltas_dev, int64_t m, int64_t chunk_lo,
-                            int64_t chunk_hi, void *recs_dev, void *stream)
+int st_top_fold_maps_device(st_tree *t, const void *leaf_dev, int leaf_itemsize, const void *deltas_dev, int64_t m,
+                            int64_t chunk_lo, int64_t chunk_hi, void *recs_dev, void *stream)
 {
-    if (!t || m < 0 || !recs_dev) return fail(ST_ERR_ARG, "st_top_fold_maps_device: bad argument");
+    if (!t || m < 0 || !recs_dev || (leaf_itemsize != 1 && leaf_itemsize != 8))
+        return fail(ST_ERR_ARG, "st_top_fold_maps_device: bad argument");
     device_guard g(t->device);
-    CU(st::launch_fold_by_leaf_maps(t, leaf_dev, deltas_dev, m, (int)chunk_lo, (int)chunk_hi, recs_dev,
+    CU(st::launch_fold_by_leaf_maps(t, leaf_dev, leaf_itemsize, deltas_dev, m, (int)chunk_lo, (int)chunk_hi, recs_dev,
                                     (cudaStream_t)stream));
     return ST_OK;
 }
 
-int st_top_fold_apply_device(st_tree *t, const int64_t *leaf_dev, const void *deltas_dev, int64_t m,
+int st_top_fold_apply_device(st_tree *t, const void *leaf_dev, int leaf_itemsize, const void *deltas_dev, int64_t m,
                              const void *recs_dev, void *stream)
 {
-    if (!t || m < 0 || !recs_dev) return fail(ST_ERR_ARG, "st_top_fold_apply_device: bad argument");
+    if (!t || m < 0 || !recs_dev || (leaf_itemsize != 1 && leaf_itemsize != 8))
+        return fail(ST_ERR_ARG, "st_top_fold_apply_device: bad argument");
     device_guard g(t->device);
-    CU(st::launch_fold_by_leaf_apply(t, leaf_dev, deltas_dev, m, recs_dev, (cudaStream_t)stream));
+    CU(st::launch_fold_by_leaf_apply(t, leaf_dev, leaf_itemsize, deltas_dev, m, recs_dev, (cudaStream_t)stream));
+    return ST_OK;
+}
+
+int st_shard_plan_device(st_tree *local, st_tree *top, const int64_t *ids_dev, int64_t m, int shift, int shards,
+                         int rank, const void *payload_dev, int64_t npayload, int check_negative,
+                         uint8_t *shard_out_dev, int32_t *slot_out_dev, int64_t *own_ids_out_dev,
+                         void *own_payload_out_dev, int64_t *counts_out_host, void *stream)
+{
+    if (!local || m < 0 || shards < 1 || shards > 64 || rank < 0 || rank >= shards || shift < 0 || shift > 62 ||
+        !counts_out_host || (m > 0 && (!ids_dev || !shard_out_dev || !slot_out_dev)) ||
+        (own_payload_out_dev && (!payload_dev || npayload <= 0)))
+        return fail(ST_ERR_ARG, "st_shard_plan_device: bad argument");
+    for (int i = 0; i < shards; ++i) counts_out_host[i] = 0;
+    if (m == 0) return ST_OK;
+    device_guard g(local->device);
+    scratch_carver c(local);
+    const size_t bytes = st::shard_plan_scratch_bytes(m, shards);
+    c.add(bytes);
+    CU(c.commit());
+    void *scratch = c.take(bytes);
+    unsigned int *counts_pin = (unsigned int *)local->h_pin;
+    CU(st::launch_shard_plan(local, top, ids_dev, m, shift, shards, rank, payload_dev, npayload, check_negative,
+                             shard_out_dev, slot_out_dev, own_ids_out_dev, own_payload_out_dev, scratch,
+                             (unsigned int *)local->d_pin, (cudaStream_t)stream));
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    for (int i = 0; i < shards; ++i) counts_out_host[i] = (int64_t)counts_pin[i];
+    return ST_OK;
+}
+
+int st_shard_expand_values_device(const st_tree *t, const uint8_t *shard_dev, const int32_t *slot_dev, int64_t m,
+                                  const void *slabs_dev, int64_t slab_stride, void *out_dev, void *stream)
+{
+    if (!t || m < 0 || slab_stride < 0 || (m > 0 && (!shard_dev || !slot_dev || !slabs_dev || !out_dev)))
+        return fail(ST_ERR_ARG, "st_shard_expand_values_device: bad argument");
+    device_guard g(t->device);
+    CU(st::launch_shard_expand_values(t, shard_dev, slot_dev, m, slabs_dev, slab_stride, out_dev, (cudaStream_t)stream));
+    return ST_OK;
+}
+
+int st_shard_expand_indices_device(const st_tree *t, const uint8_t *shard_dev, const int32_t *slot_dev, int64_t m,
+                                   const int32_t *slabs_dev, int64_t slab_stride, int64_t leaves_per_shard,
+                                   int64_t *out_dev, void *stream)
+{
+    if (!t || m < 0 || slab_stride < 0 || (m > 0 && (!shard_dev || !slot_dev || !slabs_dev || !out_dev)))
+        return fail(ST_ERR_ARG, "st_shard_expand_indices_device: bad argument");
+    device_guard g(t->device);
+    CU(st::launch_shard_expand_indices(t, shard_dev, slot_dev, m, slabs_dev, slab_stride, leaves_per_shard, out_dev,
+                                       (cudaStream_t)stream));
     return ST_OK;
 }
 

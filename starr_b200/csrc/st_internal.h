@@ -70,9 +70,22 @@ int64_t update_max_chunk();
 cudaError_t launch_fold_by_leaf(st_tree *t, const int64_t *leaf, const void *deltas, int64_t m, cudaStream_t s);
 // the same in two phases (chunk summaries for a chunk range, then the stitch); records [chunk][node-1]
 size_t fold_rec_bytes(const st_tree *t);
-cudaError_t launch_fold_by_leaf_maps(st_tree *t, const int64_t *leaf, const void *deltas, int64_t m, int chunk_lo,
-                                     int chunk_hi, void *recs, cudaStream_t s);
-cudaError_t launch_fold_by_leaf_apply(st_tree *t, const int64_t *leaf, const void *deltas, int64_t m, const void *recs,
-                                      cudaStream_t s);
+// leaf ids are int64 (leaf_bytes 8) or uint8 (leaf_bytes 1)
+cudaError_t launch_fold_by_leaf_maps(st_tree *t, const void *leaf, int leaf_bytes, const void *deltas, int64_t m,
+                                     int chunk_lo, int chunk_hi, void *recs, cudaStream_t s);
+cudaError_t launch_fold_by_leaf_apply(st_tree *t, const void *leaf, int leaf_bytes, const void *deltas, int64_t m,
+                                      const void *recs, cudaStream_t s);
+
+// subtree-sharded layout helpers (st_shard.cu)
+size_t shard_plan_scratch_bytes(int64_t m, int shards);
+cudaError_t launch_shard_plan(st_tree *local, st_tree *top, const int64_t *ids, int64_t m, int shift, int shards,
+                              int rank, const void *payload, int64_t npayload, int check_negative, uint8_t *shard_out,
+                              int32_t *slot_out, int64_t *own_ids_out, void *own_payload_out, void *scratch,
+                              unsigned int *counts_out, cudaStream_t s);
+cudaError_t launch_shard_expand_values(const st_tree *t, const uint8_t *shard, const int32_t *slot, int64_t m,
+                                       const void *slabs, int64_t slab_stride, void *out, cudaStream_t s);
+cudaError_t launch_shard_expand_indices(const st_tree *t, const uint8_t *shard, const int32_t *slot, int64_t m,
+                                        const int32_t *slabs, int64_t slab_stride, int64_t leaves_per_shard,
+                                        int64_t *out, cudaStream_t s);
 
 }  // namespace st

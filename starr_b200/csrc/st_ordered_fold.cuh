@@ -251,19 +251,21 @@ __device__ __forceinline__ T seq_until_ready(T cur, int &p, int nc, LOAD load)
 // subtree-sharded layout, where all ranks' differences arrive as ONE batch-ordered vector.
 template <typename T> struct masked_src {
     const T *d;
-    const int64_t *leaf;
+    const void *leaf;   // leaf (shard) id of every element: int64 (leaf_bytes 8) or uint8 (leaf_bytes 1)
+    int leaf_bytes;
     int64_t nleaves;
     uint32_t node;
     int rshift;   // leaf level - level(node)
     __device__ __forceinline__ T operator[](int64_t i) const
     {
-        return ((uint32_t)((leaf[i] + nleaves) >> rshift) == node) ? d[i] : T(0);
+        const int64_t l = leaf_bytes == 1 ? (int64_t)__ldg((const uint8_t *)leaf + i) : __ldg((const int64_t *)leaf + i);
+        return ((uint32_t)((l + nleaves) >> rshift) == node) ? d[i] : T(0);
     }
     __device__ __forceinline__ masked_src operator+(int64_t off) const
     {
         masked_src r = *this;
         r.d += off;
-        r.leaf += off;
+        r.leaf = (const char *)leaf + off * leaf_bytes;
         return r;
     }
 };

@@ -241,11 +241,18 @@ __global__ void __launch_bounds__(256) int_propagate_kernel(T *__restrict__ H, u
     for (int l = depth - 1; l >= 0; --l) {
         const uint32_t node = (l < leaf_level) ? (key >> (depth - l)) : 0u;  // 0 = no ancestor here
         T sum = node ? d : T(0);
+        // segmented inclusive scan over RUNS of equal nodes (keys need not be sorted: in "apply
+        // deltas" mode they arrive in batch order, and equal nodes may be separated by others)
+        const uint32_t nprev = __shfl_up_sync(0xffffffffu, node, 1);
+        unsigned int head = (lane == 0) || (nprev != node);
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
             const T up = shfl_up_t<T>(sum, off);
-            const uint32_t nup = __shfl_up_sync(0xffffffffu, node, off);
-            if (lane >= off && nup == node) sum = (T)(sum + up);
+            const unsigned int hup = __shfl_up_sync(0xffffffffu, head, off);
+            if (lane >= off && !head) {
+                sum = (T)(sum + up);
+                head |= hup;
+            }
         }
         const uint32_t nnext = __shfl_down_sync(0xffffffffu, node, 1);
         const bool tail = (lane == 31) || (nnext != node);
@@ -415,7 +422,7 @@ __global__ void __launch_bounds__(FOLD_THREADS) fold_huge_maps_kernel(const T *_
                                                                       const int *__restrict__ huge_off,
                                                                       chunk_rec<typename fp_bits<T>::I> *__restrict__ recs,
                                                                       const unsigned int *status,
-                                                                      const int64_t *__restrict__ mleaf, int64_t mnleaves,
+                                                                      const void *__restrict__ mleaf, int mleaf_bytes, int64_t mnleaves,
                                                                       int mleaf_level)
 {
     if (status[SW_STATUS]) return;
@@ -444,7 +451,7 @@ __global__ void __launch_bounds__(FOLD_THREADS) fold_huge_maps_kernel(const T *_
             continue;
         }
         if constexpr (MASKED) {
-            const masked_src<T> ms{lev_d, mleaf, mnleaves, s.node, mleaf_level - s.level};
+            const masked_src<T> ms{lev_d, mleaf, mleaf_bytes, mnleaves, s.node, mleaf_level - s.level};
             chunk_summary_cta<T>(ms + (int64_t)c * FOLD_CHUNK, nc, eT, recs + g, s_wtot, s_red, s_abs);
         } else {
             chunk_summary_cta<T>(lev_d + (int64_t)s.level * level_stride + s.start + (int64_t)c * FOLD_CHUNK, nc, eT,
@@ -466,7 +473,7 @@ __global__ void __launch_bounds__(FOLD_THREADS) fold_huge_apply_kernel(T *__rest
                                                                        const int *__restrict__ huge_off,
                                                                        const chunk_rec<typename fp_bits<T>::I> *__restrict__ recs,
                                                                        unsigned int *status,
-                                                                       const int64_t *__restrict__ mleaf, int64_t mnleaves,
+                                                                       const void *__restrict__ mleaf, int mleaf_bytes, int64_t mnleaves,
                                                                        int mleaf_level)
 {
     if (status[SW_STATUS]) return;
@@ -569,7 +576,7 @@ __global__ void __launch_bounds__(FOLD_THREADS) fold_huge_apply_kernel(T *__rest
                 const int c = cb + k;
                 const int nc = s.len - c * FOLD_CHUNK < FOLD_CHUNK ? s.len - c * FOLD_CHUNK : FOLD_CHUNK;
                 if constexpr (MASKED) {
-                    const masked_src<T> ms{lev_d, mleaf, mnleaves, s.node, mleaf_level - s.level};
+                    const masked_src<T> ms{lev_d, mleaf, mleaf_bytes, mnleaves, s.node, mleaf_level - s.level};
                     cur = ordered_fold_cta<T>(cur, ms + (int64_t)c * FOLD_CHUNK, nc, s_wtot, &s_mviol, &ctl);
                 } else {
                     cur = ordered_fold_cta<T>(cur, src + (int64_t)c * FOLD_CHUNK, nc, s_wtot, &s_mviol, &ctl);
@@ -588,8 +595,9 @@ __global__ void __launch_bounds__(FOLD_THREADS) fold_huge_apply_kernel(T *__rest
 // chunk range is one contiguous slab (exchanged with one all-gather in the sharded layout).
 template <typename T>
 __global__ void __launch_bounds__(FOLD_THREADS) fold_top_maps_kernel(const T *__restrict__ H, const T *__restrict__ d,
-                                                                     const int64_t *__restrict__ leaf, int64_t nleaves,
-                                                                     int leaf_level, int64_t m, int chunk_lo, int chunk_hi,
+                                                                     const void *__restrict__ leaf, int leaf_bytes,
+                                                                     int64_t nleaves, int leaf_level, int64_t m,
+                                                                     int chunk_lo, int chunk_hi,
                                                                      chunk_rec<typename fp_bits<T>::I> *__restrict__ recs,
                                                                      const unsigned int *status)
 {
@@ -614,7 +622,7 @@ __global__ void __launch_bounds__(FOLD_THREADS) fold_top_maps_kernel(const T *__
             if (threadIdx.x == 0) out->ok = 0;
             continue;
         }
-        const masked_src<T> ms{d, leaf, nleaves, node, leaf_level - heap_level(node)};
+        const masked_src<T> ms{d, leaf, leaf_bytes, nleaves, node, leaf_level - heap_level(node)};
         chunk_summary_cta<T>(ms + base, nc, eT, out, s_wtot, s_red, s_abs);
     }
 }
@@ -759,10 +767,10 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
         g_kernel_launches += 3;
         mark(4);
         fold_huge_maps_kernel<T, false><<<t->sm_count * 8, FOLD_THREADS, 0, s>>>(H, lev, B, w.queue_huge, w.huge_off,
-                                                                                (REC *)w.huge_recs, status, nullptr, 0, 0);
+                                                                                (REC *)w.huge_recs, status, nullptr, 0, 0, 0);
         mark(5);
         fold_huge_apply_kernel<T, false><<<t->sm_count, FOLD_THREADS, 0, s>>>(H, lev, B, w.queue_huge, w.huge_off,
-                                                                             (const REC *)w.huge_recs, status, nullptr, 0, 0);
+                                                                             (const REC *)w.huge_recs, status, nullptr, 0, 0, 0);
         mark(6);
         fold_scan_kernel<T><<<t->sm_count * 8, FOLD_THREADS, 0, s>>>(H, lev, B, w.queue, w.queue_med, status,
                                                                         retire_params<T>{nullptr, nullptr, nullptr, 0, 0});
@@ -803,29 +811,29 @@ static bool fold_by_leaf_ok(const st_tree *t, int64_t m)
 
 size_t fold_rec_bytes(const st_tree *t) { return t->dtype == ST_F64 ? sizeof(chunk_rec<int64_t>) : sizeof(chunk_rec<int32_t>); }
 
-cudaError_t launch_fold_by_leaf_maps(st_tree *t, const int64_t *leaf, const void *deltas, int64_t m, int chunk_lo,
-                                     int chunk_hi, void *recs, cudaStream_t s)
+cudaError_t launch_fold_by_leaf_maps(st_tree *t, const void *leaf, int leaf_bytes, const void *deltas, int64_t m,
+                                     int chunk_lo, int chunk_hi, void *recs, cudaStream_t s)
 {
-    if (!fold_by_leaf_ok(t, m)) return cudaErrorInvalidValue;
+    if (!fold_by_leaf_ok(t, m) || (leaf_bytes != 1 && leaf_bytes != 8)) return cudaErrorInvalidValue;
     if (chunk_hi <= chunk_lo) return cudaSuccess;
     const int64_t pairs = (int64_t)(chunk_hi - chunk_lo) * (t->n - 1);
     const unsigned g = (unsigned)(pairs < (int64_t)t->sm_count * 8 ? pairs : (int64_t)t->sm_count * 8);
     ++g_kernel_launches;
     if (t->dtype == ST_F32)
-        fold_top_maps_kernel<float><<<g, FOLD_THREADS, 0, s>>>((const float *)t->heap, (const float *)deltas, leaf, t->n,
-                                                               t->depth, m, chunk_lo, chunk_hi,
+        fold_top_maps_kernel<float><<<g, FOLD_THREADS, 0, s>>>((const float *)t->heap, (const float *)deltas, leaf,
+                                                               leaf_bytes, t->n, t->depth, m, chunk_lo, chunk_hi,
                                                                (chunk_rec<int32_t> *)recs, t->d_status);
     else
         fold_top_maps_kernel<double><<<g, FOLD_THREADS, 0, s>>>((const double *)t->heap, (const double *)deltas, leaf,
-                                                                t->n, t->depth, m, chunk_lo, chunk_hi,
+                                                                leaf_bytes, t->n, t->depth, m, chunk_lo, chunk_hi,
                                                                 (chunk_rec<int64_t> *)recs, t->d_status);
     return cudaGetLastError();
 }
 
-cudaError_t launch_fold_by_leaf_apply(st_tree *t, const int64_t *leaf, const void *deltas, int64_t m, const void *recs,
-                                      cudaStream_t s)
+cudaError_t launch_fold_by_leaf_apply(st_tree *t, const void *leaf, int leaf_bytes, const void *deltas, int64_t m,
+                                      const void *recs, cudaStream_t s)
 {
-    if (!fold_by_leaf_ok(t, m)) return cudaErrorInvalidValue;
+    if (!fold_by_leaf_ok(t, m) || (leaf_bytes != 1 && leaf_bytes != 8)) return cudaErrorInvalidValue;
     if (m <= 0) return cudaSuccess;
     const size_t need = 256 + (size_t)t->n * sizeof(seg_entry);
     if (need > t->ws.bytes) {
@@ -843,11 +851,11 @@ cudaError_t launch_fold_by_leaf_apply(st_tree *t, const int64_t *leaf, const voi
     if (t->dtype == ST_F32)
         fold_huge_apply_kernel<float, true><<<(unsigned)(t->n - 1), FOLD_THREADS, 0, s>>>(
             (float *)t->heap, (const float *)deltas, 0, q, nullptr, (const chunk_rec<int32_t> *)recs, t->d_status, leaf,
-            t->n, t->depth);
+            leaf_bytes, t->n, t->depth);
     else
         fold_huge_apply_kernel<double, true><<<(unsigned)(t->n - 1), FOLD_THREADS, 0, s>>>(
             (double *)t->heap, (const double *)deltas, 0, q, nullptr, (const chunk_rec<int64_t> *)recs, t->d_status, leaf,
-            t->n, t->depth);
+            leaf_bytes, t->n, t->depth);
     return cudaGetLastError();
 }
 
@@ -867,9 +875,9 @@ cudaError_t launch_fold_by_leaf(st_tree *t, const int64_t *leaf, const void *del
         if (e != cudaSuccess) return e;
         t->scratch.bytes = need;
     }
-    cudaError_t e = launch_fold_by_leaf_maps(t, leaf, deltas, m, 0, nchunks, t->scratch.base, s);
+    cudaError_t e = launch_fold_by_leaf_maps(t, leaf, 8, deltas, m, 0, nchunks, t->scratch.base, s);
     if (e != cudaSuccess) return e;
-    return launch_fold_by_leaf_apply(t, leaf, deltas, m, t->scratch.base, s);
+    return launch_fold_by_leaf_apply(t, leaf, 8, deltas, m, t->scratch.base, s);
 }
 
 cudaError_t launch_update(st_tree *t, const int64_t *idx, int64_t ni, const void *vals, int64_t nv,

@@ -123,11 +123,16 @@ class DeviceSumTree:
         return self
 
     # ---- building blocks of the sharded tree (starr_b200/sharded.py) ----------------------------
-    def update_with_deltas_(self, idx: torch.Tensor, vals: torch.Tensor) -> torch.Tensor:
+    def update_with_deltas_(self, idx: torch.Tensor, vals: torch.Tensor,
+                            out: torch.Tensor | None = None) -> torch.Tensor:
         """``update_`` that also returns every update's applied difference d_j (batch order)."""
         idx = self._chk(idx.reshape(-1), torch.int64, "idx")
         vals = self._chk(vals.reshape(-1), self.dtype, "vals")
-        d = torch.empty(idx.numel(), dtype=self.dtype, device=self.device)
+        if out is None:
+            out = torch.empty(idx.numel(), dtype=self.dtype, device=self.device)
+        d = self._chk(out, self.dtype, "out")
+        if d.numel() != idx.numel() or not out.is_contiguous():
+            raise TypeError("out must be contiguous and have the size of idx")
         with torch.cuda.device(self.device):
             self._h.update_deltas_device(idx.data_ptr(), idx.numel(), vals.data_ptr(), vals.numel(),
                                          d.data_ptr(), _stream())
@@ -150,15 +155,64 @@ class DeviceSumTree:
     def top_fold_maps_(self, leaf: torch.Tensor, deltas: torch.Tensor, chunk_lo: int, chunk_hi: int,
                        recs: torch.Tensor) -> None:
         """Phase A of ``apply_deltas_`` on a tiny tree: summaries of the 1024-update chunks
-        [chunk_lo, chunk_hi) for every internal node, written into ``recs`` ([chunk][node-1] records)."""
+        [chunk_lo, chunk_hi) for every internal node, written into ``recs`` ([chunk][node-1] records).
+        ``leaf`` is int64 or uint8."""
+        if leaf.dtype not in (torch.int64, torch.uint8) or not leaf.is_contiguous():
+            raise TypeError("leaf must be a contiguous int64 or uint8 tensor")
         with torch.cuda.device(self.device):
-            self._h.top_fold_maps_device(leaf.data_ptr(), deltas.data_ptr(), leaf.numel(), chunk_lo, chunk_hi,
-                                         recs.data_ptr(), _stream())
+            self._h.top_fold_maps_device(leaf.data_ptr(), leaf.element_size(), deltas.data_ptr(), leaf.numel(),
+                                         chunk_lo, chunk_hi, recs.data_ptr(), _stream())
 
     def top_fold_apply_(self, leaf: torch.Tensor, deltas: torch.Tensor, recs: torch.Tensor) -> None:
         """Phase B: stitch the chunk summaries of ALL chunks into the internal nodes."""
+        if leaf.dtype not in (torch.int64, torch.uint8) or not leaf.is_contiguous():
+            raise TypeError("leaf must be a contiguous int64 or uint8 tensor")
         with torch.cuda.device(self.device):
-            self._h.top_fold_apply_device(leaf.data_ptr(), deltas.data_ptr(), leaf.numel(), recs.data_ptr(), _stream())
+            self._h.top_fold_apply_device(leaf.data_ptr(), leaf.element_size(), deltas.data_ptr(), leaf.numel(),
+                                          recs.data_ptr(), _stream())
+
+    def shard_plan(self, top: "DeviceSumTree | None", ids: torch.Tensor, shift: int, shards: int, rank: int,
+                   payload: torch.Tensor, check_negative: bool, want_ids: bool = True):
+        """Plan of one replicated batch of a sharded tree (``st_shard_plan_device``): returns
+        ``(shard uint8[m], slot int32[m], own_ids int64[m] | None, own_payload dtype[m], counts)``;
+        only the first ``counts[rank]`` entries of the ``own_*`` tensors are meaningful.  Waits for
+        the stream (the counts are needed on the host)."""
+        ids = self._chk(ids.reshape(-1), torch.int64, "ids")
+        payload = self._chk(payload.reshape(-1), self.dtype, "payload")
+        m = ids.numel()
+        shard = torch.empty(m, dtype=torch.uint8, device=self.device)
+        slot = torch.empty(m, dtype=torch.int32, device=self.device)
+        own_ids = torch.empty(m, dtype=torch.int64, device=self.device) if want_ids else None
+        own_payload = torch.empty(m, dtype=self.dtype, device=self.device)
+        with torch.cuda.device(self.device):
+            counts = self._h.shard_plan_device(top._h if top is not None else None, ids.data_ptr(), m, shift, shards,
+                                               rank, payload.data_ptr(), payload.numel(), check_negative,
+                                               shard.data_ptr(), slot.data_ptr(),
+                                               own_ids.data_ptr() if want_ids else 0, own_payload.data_ptr(),
+                                               _stream())
+        return shard, slot, own_ids, own_payload, counts
+
+    def shard_expand_values(self, shard: torch.Tensor, slot: torch.Tensor, slabs: torch.Tensor) -> torch.Tensor:
+        """``out[j] = slabs[shard[j], slot[j]]`` for 2-D ``slabs`` of the tree's dtype."""
+        slabs = self._chk(slabs, self.dtype, "slabs")
+        out = torch.empty(shard.numel(), dtype=self.dtype, device=self.device)
+        with torch.cuda.device(self.device):
+            self._h.shard_expand_values_device(shard.data_ptr(), slot.data_ptr(), shard.numel(), slabs.data_ptr(),
+                                               slabs.shape[1], out.data_ptr(), _stream())
+        return out
+
+    def shard_expand_indices(self, shard: torch.Tensor, slot: torch.Tensor, slabs: torch.Tensor,
+                             leaves_per_shard: int, out: torch.Tensor | None = None) -> torch.Tensor:
+        """``out[j] = shard[j] * leaves_per_shard + slabs[shard[j], slot[j]]`` (int32 slabs, int64 out)."""
+        slabs = self._chk(slabs, torch.int32, "slabs")
+        if out is None:
+            out = torch.empty(shard.numel(), dtype=torch.int64, device=self.device)
+        if self._chk(out, torch.int64, "out") is not out or out.numel() != shard.numel():
+            raise TypeError("out must be a contiguous int64 tensor of the batch size")
+        with torch.cuda.device(self.device):
+            self._h.shard_expand_indices_device(shard.data_ptr(), slot.data_ptr(), shard.numel(), slabs.data_ptr(),
+                                                slabs.shape[1], leaves_per_shard, out.data_ptr(), _stream())
+        return out
 
     def route_uniform(self, u: torch.Tensor):
         """``sample_uniform`` that also returns the prefix left over at the leaf reached."""

@@ -13,14 +13,20 @@ global heap index h.
 
 Per batch (inputs are replicated on every rank, as a PER learner broadcasts them):
   build   local pairwise build -> all-gather of the G shard roots -> pairwise top build.
-  update  every rank applies the updates it owns (batch order preserved) and gets their
-          differences d_j; the d_j are exchanged (sum all-reduce of a zero-filled vector: one
-          non-zero contributor per slot, hence exact); every rank folds all d_j into the top tree
-          in batch order (the reference adds EVERY update's d to the top nodes in order, so
-          roots alone are not enough for floats); shard roots are re-gathered.
+  plan    every rank computes, for EVERY element of the batch, the owning shard and the stable
+          position ("slot") of the element among those of its shard, and compacts its own
+          elements in batch order (three streaming kernels, st_shard.cu).  All ranks therefore
+          know where each shard's results will sit in that shard's compact slab.
+  update  every rank applies the updates it owns (batch order preserved) and writes their
+          differences d_j, followed by its new shard root, into its slab; ONE all-gather of the
+          slabs moves everything (each d_j crosses NVLink once, no zero-filled all-reduce); the
+          d_j are put back into batch order and every rank folds them into the top tree (the
+          reference adds EVERY update's d to the top nodes in order, so roots alone are not
+          enough for floats).
   sample  every rank routes all queries through the top tree (same compares / subtractions as
           the first g levels of the reference descent), finishes the ones it owns locally with
-          the left-over prefix, and the global indices are combined with one all-reduce.
+          the left-over prefix, and the local leaf ids (int32) are all-gathered as slabs and
+          expanded to global indices in batch order.
 """
 from __future__ import annotations
 
@@ -56,6 +62,7 @@ class ShardedSumTree:
         self.local = factory(self.n_local, dtype, self.device)
         self.top = factory(self.world, dtype, self.device)
         self.offset = self.rank * self.n_local
+        self._marks = None     # diagnostics: list of (label, cuda event) while phase_times() runs
         if local_leaves is not None:
             self.build_(local_leaves)
 
@@ -64,11 +71,44 @@ class ShardedSumTree:
         self.local.reserve(max_global_batch)
         self.top.reserve(max_global_batch)
 
-    def poll(self) -> None:
-        self.local.poll()
-        self.top.poll()
+    def _mark(self, label: str) -> None:
+        if self._marks is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self._marks.append((label, ev))
 
-    def _gather_roots(self) -> None:
+    def phase_times(self, next_batch, reps: int = 10):
+        """Diagnostics (tools/sharded_breakdown.py): median device time in microseconds of every
+        phase of ``update_`` and ``sample_uniform``; ``next_batch()`` returns ``(idx, vals, u)``."""
+        import statistics
+        acc: dict[str, list[float]] = {}
+        for _ in range(reps):
+            idx, vals, u = next_batch()
+            dist.barrier(group=self.group)
+            torch.cuda.synchronize()
+            self._marks = []
+            self._mark("start")
+            self.update_(idx, vals)
+            self._mark("update: done")
+            self.sample_uniform(u)
+            torch.cuda.synchronize()
+            marks, self._marks = self._marks, None
+            for (_, a), (label, b) in zip(marks, marks[1:]):
+                acc.setdefault(label, []).append(a.elapsed_time(b) * 1e3)
+        return [(k, statistics.median(v)) for k, v in acc.items()]
+
+    def poll(self) -> None:
+        """Raise the first deferred validation error; both trees' status words are cleared."""
+        first = None
+        for tree in (self.local, self.top):
+            try:
+                tree.poll()
+            except (ValueError, IndexError) as e:
+                first = first or e
+        if first is not None:
+            raise first
+
+    def _gather_roots(self) -> None:  # build only; updates carry the roots in the delta slabs
         """All-gather of the G shard roots (G elements) into the top tree's leaves."""
         root = self.local.heap[1:2].contiguous()
         roots = torch.empty(self.world, dtype=self.dtype, device=root.device)
@@ -86,9 +126,16 @@ class ShardedSumTree:
         return self
 
     # ---- update ---------------------------------------------------------------------------------
+    @staticmethod
+    def _slab_capacity(counts) -> int:
+        """Common slab length of one exchange: the largest per-shard count (every rank computes
+        the same counts from the replicated batch), rounded up so that slabs stay 256-byte aligned."""
+        return max(64, (max(counts) + 63) // 64 * 64)
+
     def update_(self, idx: torch.Tensor, vals: torch.Tensor, check: bool = False) -> "ShardedSumTree":
         """Replicated batch: ``idx`` are GLOBAL leaf ids, ``vals`` cycles over the global batch
-        position (reference pyx:44)."""
+        position (reference pyx:44).  Validation is deferred like ``DeviceSumTree.update_`` (a bad
+        batch is skipped on every rank alike; ``poll()`` raises) unless ``check=True``."""
         idx = idx.reshape(-1)
         vals = vals.reshape(-1)
         ni, nv = idx.numel(), vals.numel()
@@ -101,16 +148,25 @@ class ShardedSumTree:
             return self
         if nv == 0:
             raise ZeroDivisionError("integer division or modulo by zero")
-        shard = idx >> self.shift
-        mine = torch.nonzero(shard == self.rank).reshape(-1)        # batch order preserved
-        loc_idx = idx[mine] - self.offset
-        loc_vals = vals[mine] if nv >= ni else vals[mine % nv]
-        d_all = torch.zeros(ni, dtype=self.dtype, device=idx.device)
-        if mine.numel():
-            d_all[mine] = self.local.update_with_deltas_(loc_idx, loc_vals)
-        dist.all_reduce(d_all, op=dist.ReduceOp.SUM, group=self.group)   # one contributor per slot
+        # who owns what: shard and stable slot of EVERY element, this rank's elements compacted
+        shard, slot, own_idx, own_vals, counts = self.local.shard_plan(
+            self.top, idx, self.shift, self.world, self.rank, vals, check_negative=True)
+        self._mark("update: plan (owner, slot, compaction)")
+        c, cap = counts[self.rank], self._slab_capacity(counts)
+        # slab of this rank: its differences d_j in batch order, then (last entry) its new shard root
+        mine = torch.empty(cap + 1, dtype=self.dtype, device=idx.device)
+        if c:
+            self.local.update_with_deltas_(own_idx[:c], own_vals[:c], out=mine[:c])
+        mine[cap:].copy_(self.local.heap[1:2])
+        self._mark("update: local update")
+        slabs = torch.empty((self.world, cap + 1), dtype=self.dtype, device=idx.device)
+        dist.all_gather_into_tensor(slabs.view(-1), mine, group=self.group)
+        self._mark("update: exchange deltas + roots")
+        d_all = self.local.shard_expand_values(shard, slot, slabs)      # batch order again
+        self._mark("update: deltas to batch order")
         self._fold_top(shard, d_all)                                    # ordered fold, all ranks alike
-        self._gather_roots()
+        self.top.leaves.copy_(slabs[:, cap])
+        self._mark("update: top fold")
         return self
 
     def _fold_top(self, shard: torch.Tensor, d_all: torch.Tensor) -> None:
@@ -120,7 +176,7 @@ class ShardedSumTree:
         top = self.top
         ni = shard.numel()
         if not hasattr(top, "top_fold_maps_") or ni <= 4096 or not self.dtype.is_floating_point:
-            top.apply_deltas_(shard, d_all)
+            top.apply_deltas_(shard.to(torch.int64), d_all)
             return
         nodes = self.world - 1
         rb = top.top_fold_record_bytes()
@@ -128,11 +184,11 @@ class ShardedSumTree:
         per = (nchunks + self.world - 1) // self.world
         recs = torch.empty(per * self.world * nodes * rb, dtype=torch.uint8, device=shard.device)
         lo = self.rank * per
-        shard = shard.contiguous()
-        d_all = d_all.contiguous()
         top.top_fold_maps_(shard, d_all, lo, lo + per, recs)
+        self._mark("update: top fold summaries")
         slab = recs[lo * nodes * rb:(lo + per) * nodes * rb].clone()
         dist.all_gather_into_tensor(recs, slab, group=self.group)
+        self._mark("update: top fold all-gather")
         top.top_fold_apply_(shard, d_all, recs)
 
     # ---- sample ---------------------------------------------------------------------------------
@@ -140,14 +196,26 @@ class ShardedSumTree:
         """Global leaf indices for replicated uniforms ``u`` (float64), identical to the
         reference's ``get_prefix_sum_id((root * u).astype(dtype))`` on the whole tree."""
         u = u.reshape(-1)
-        shard, resid = self.top.route_uniform(u)
-        mine = torch.nonzero(shard == self.rank).reshape(-1)
+        m = u.numel()
         if out is None:
-            out = torch.empty(u.numel(), dtype=torch.int64, device=u.device)
-        out.zero_()
-        if mine.numel():
-            out[mine] = self.local.search(resid[mine]) + self.offset
-        dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self.group)
+            out = torch.empty(m, dtype=torch.int64, device=u.device)
+        if m == 0:
+            return out
+        owner, resid = self.top.route_uniform(u)
+        self._mark("sample: route")
+        shard, slot, _, own_resid, counts = self.local.shard_plan(
+            None, owner, 0, self.world, self.rank, resid, check_negative=False, want_ids=False)
+        self._mark("sample: plan (slot, compaction)")
+        c, cap = counts[self.rank], self._slab_capacity(counts)
+        mine = torch.empty(cap, dtype=torch.int32, device=u.device)
+        if c:
+            mine[:c].copy_(self.local.search(own_resid[:c]))             # local leaf ids fit 31 bits
+        self._mark("sample: local search")
+        slabs = torch.empty((self.world, cap), dtype=torch.int32, device=u.device)
+        dist.all_gather_into_tensor(slabs.view(-1), mine, group=self.group)
+        self._mark("sample: exchange indices")
+        self.local.shard_expand_indices(shard, slot, slabs, self.n_local, out=out)
+        self._mark("sample: indices to batch order")
         return out
 
     # ---- inspection -------------------------------------------------------------------------------

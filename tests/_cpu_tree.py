@@ -33,7 +33,35 @@ class CpuTree:
         oracle.c.build_sumtree_from_array(self._np[self.n:], self._np[:self.n])
         return self
 
-    def update_with_deltas_(self, idx, vals):
+    def shard_plan(self, top, ids, shift, shards, rank, payload, check_negative, want_ids=True):
+        ids = ids.reshape(-1)
+        payload = payload.reshape(-1)
+        owner = ids >> shift
+        if bool(((ids < 0) | (owner >= shards)).any()):
+            raise IndexError("Out of bounds on buffer access (axis 0)")
+        if check_negative and bool((payload < 0).any()):
+            raise ValueError("vals must be non-negative")
+        slot = torch.empty(ids.numel(), dtype=torch.int32)
+        counts = []
+        for s in range(shards):
+            pos = torch.nonzero(owner == s).reshape(-1)
+            slot[pos] = torch.arange(pos.numel(), dtype=torch.int32)
+            counts.append(int(pos.numel()))
+        mine = torch.nonzero(owner == rank).reshape(-1)
+        own_ids = (ids[mine] - (rank << shift)) if want_ids else None
+        return owner.to(torch.uint8), slot, own_ids, payload[mine % payload.numel()], counts
+
+    def shard_expand_values(self, shard, slot, slabs):
+        return slabs[shard.long(), slot.long()]
+
+    def shard_expand_indices(self, shard, slot, slabs, leaves_per_shard, out=None):
+        res = shard.long() * leaves_per_shard + slabs[shard.long(), slot.long()].long()
+        if out is None:
+            return res
+        out.copy_(res)
+        return out
+
+    def update_with_deltas_(self, idx, vals, out=None):
         idx_np = idx.numpy().astype(np.intp)
         vals_np = vals.numpy()
         before = self._np[self.n:].copy()
@@ -43,6 +71,9 @@ class CpuTree:
             before[l] = before[l] + d[j]
         oracle.c.update_sumtree(idx_np, np.ascontiguousarray(vals_np), self._np[self.n:], self._np[:self.n])
         assert before.tobytes() == self._np[self.n:].tobytes()
+        if out is not None:
+            out.copy_(torch.from_numpy(d))
+            return out
         return torch.from_numpy(d)
 
     def apply_deltas_(self, idx, deltas):

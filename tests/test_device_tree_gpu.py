@@ -157,6 +157,30 @@ def test_apply_deltas_tiny_tree(torch_mod, dt_name):
             assert_bits_equal(_np(t.heap), want, f"G={G} m={m}")
 
 
+@pytest.mark.parametrize("dt_name", ["int32", "int64", "uint8", "int16"])
+def test_apply_deltas_integer_trees_unsorted_ids(torch_mod, dt_name):
+    """Integer ``apply_deltas_``: ids arrive in batch order, so equal ancestors are NOT adjacent."""
+    torch = torch_mod
+    from starr_b200 import DeviceSumTree
+    dt = np.dtype(dt_name)
+    rng = np.random.default_rng(19)
+    for n in (2, 4, 8, 64, 1000):
+        for m in (1, 37, 5000, 100_000):
+            leaves = rng.integers(0, 50, n).astype(dt)
+            t = DeviceSumTree(torch.from_numpy(leaves).cuda())
+            want = _np(t.heap).copy()
+            leaf = rng.integers(0, n, m).astype(np.int64)
+            d = rng.integers(-3 if dt.kind == "i" else 0, 4, m).astype(dt)
+            t.apply_deltas_(torch.from_numpy(leaf).cuda(), torch.from_numpy(d).cuda())
+            for j in range(m):                       # wrap-around arithmetic in the dtype, like C
+                h = (int(leaf[j]) + n) // 2
+                while h > 0:
+                    want[h] = (want[h].astype(np.int64) + d[j].astype(np.int64)).astype(dt) if dt.itemsize < 8 \
+                        else want[h] + d[j]
+                    h //= 2
+            assert_bits_equal(_np(t.heap), want, f"{dt_name} n={n} m={m}")
+
+
 def test_per_step_cuda_graph(torch_mod, oracle_mod):
     """The PER step (update -> sample with priorities) captured ONCE in a CUDA graph and replayed with
     new inputs in static buffers: same bits as the oracle, no launches from Python per step."""

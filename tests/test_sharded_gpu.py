@@ -69,3 +69,172 @@ def test_sharded_nccl_equals_single_tree(dt_name):
         p.join(timeout=60)
     assert all(p.exitcode == 0 for p in procs)
     assert all(ok for _, ok in results), results
+
+
+# ---- single-GPU coverage of the sharded building blocks --------------------------------------
+def _plan_reference(ids, shift, shards, rank, payload):
+    owner = ids >> shift
+    slot = np.full(ids.size, -1, np.int32)
+    counts = []
+    for s in range(shards):
+        pos = np.flatnonzero(owner == s)
+        slot[pos] = np.arange(pos.size, dtype=np.int32)
+        counts.append(int(pos.size))
+    mine = np.flatnonzero(owner == rank)
+    return owner.astype(np.uint8), slot, ids[mine] - (rank << shift), payload[mine % payload.size], counts
+
+
+@pytest.mark.parametrize("shards,rank,m,npay,skew", [
+    (2, 1, 1, 1, False), (8, 3, 2047, 2047, False), (8, 0, 2049, 5, False), (64, 63, 100_003, 100_003, False),
+    (4, 2, 1 << 20, 1 << 20, True), (8, 7, 300_000, 1000, True)])
+def test_shard_plan_matches_numpy(shards, rank, m, npay, skew):
+    from starr_b200 import DeviceSumTree
+    dev = torch.device("cuda", 0)
+    shift = 10
+    rng = np.random.default_rng(m + shards)
+    ids = rng.integers(0, shards << shift, m).astype(np.int64)
+    if skew:                                             # most of the batch lands in one shard
+        ids[rng.random(m) < 0.9] = (rank << shift) + 5
+    payload = rng.random(npay).astype(np.float32)
+    tree = DeviceSumTree(1 << shift, dtype=torch.float32, device=dev)
+    shard, slot, own_ids, own_pay, counts = tree.shard_plan(
+        None, torch.from_numpy(ids).to(dev), shift, shards, rank, torch.from_numpy(payload).to(dev), True)
+    w_shard, w_slot, w_ids, w_pay, w_counts = _plan_reference(ids, shift, shards, rank, payload)
+    assert counts == w_counts
+    c = counts[rank]
+    assert np.array_equal(shard.cpu().numpy(), w_shard)
+    assert np.array_equal(slot.cpu().numpy(), w_slot)
+    assert np.array_equal(own_ids[:c].cpu().numpy(), w_ids)
+    assert own_pay[:c].cpu().numpy().tobytes() == w_pay.tobytes()
+    tree.poll()
+    # expansion of per-shard slabs back to batch order
+    cap = max(counts) + 3
+    slabs = torch.from_numpy(rng.random((shards, cap)).astype(np.float32)).to(dev)
+    got = tree.shard_expand_values(shard, slot, slabs).cpu().numpy()
+    assert got.tobytes() == slabs.cpu().numpy()[w_shard, w_slot].tobytes()
+    islabs = torch.from_numpy(rng.integers(0, 1 << shift, (shards, cap)).astype(np.int32)).to(dev)
+    goti = tree.shard_expand_indices(shard, slot, islabs, 1 << shift).cpu().numpy()
+    assert np.array_equal(goti, w_shard.astype(np.int64) * (1 << shift) + islabs.cpu().numpy()[w_shard, w_slot])
+
+
+def test_shard_plan_flags_bad_batches_on_both_trees():
+    from starr_b200 import DeviceSumTree
+    dev = torch.device("cuda", 0)
+    local = DeviceSumTree(1 << 10, dtype=torch.float32, device=dev)
+    top = DeviceSumTree(4, dtype=torch.float32, device=dev)
+    ids = torch.arange(5000, dtype=torch.int64, device=dev) % (4 << 10)
+    pay = torch.ones(5000, dtype=torch.float32, device=dev)
+    bad_ids = ids.clone()
+    bad_ids[4321] = 4 << 10
+    local.shard_plan(top, bad_ids, 10, 4, 1, pay, True)
+    for t in (local, top):
+        with pytest.raises(IndexError):
+            t.poll()
+    bad_ids[4321] = -1
+    local.shard_plan(top, bad_ids, 10, 4, 1, pay, True)
+    for t in (local, top):
+        with pytest.raises(IndexError):
+            t.poll()
+    bad_pay = pay.clone()
+    bad_pay[77] = -1.0
+    local.shard_plan(top, ids, 10, 4, 1, bad_pay, True)
+    for t in (local, top):
+        with pytest.raises(ValueError):
+            t.poll()
+    local.shard_plan(top, ids, 10, 4, 1, bad_pay, False)      # residuals are not vals: no sign check
+    local.poll()
+    top.poll()
+
+
+@pytest.mark.parametrize("dt_name", ["float32", "float64"])
+def test_top_fold_uint8_ids_equal_int64_ids(dt_name):
+    from starr_b200 import DeviceSumTree
+    dev = torch.device("cuda", 0)
+    dt = np.dtype(dt_name)
+    rng = np.random.default_rng(3)
+    m, g = 50_000, 8
+    roots = np.exp(rng.uniform(-2, 12, g)).astype(dt)
+    shard = rng.integers(0, g, m)
+    d = (np.exp(rng.uniform(-8, 8, m)) * rng.choice([-1, 1], m)).astype(dt)
+    heaps = []
+    for ids in (torch.from_numpy(shard.astype(np.int64)), torch.from_numpy(shard.astype(np.uint8))):
+        top = DeviceSumTree(torch.from_numpy(roots).to(dev))
+        recs = torch.empty(((m + 1023) // 1024) * (g - 1) * top.top_fold_record_bytes(), dtype=torch.uint8, device=dev)
+        top.top_fold_maps_(ids.to(dev), torch.from_numpy(d).to(dev), 0, (m + 1023) // 1024, recs)
+        top.top_fold_apply_(ids.to(dev), torch.from_numpy(d).to(dev), recs)
+        top.poll()
+        heaps.append(top.heap.cpu().numpy().tobytes())
+    assert heaps[0] == heaps[1]
+    # and both equal the sequential statement: every ancestor += d in batch order
+    tree = np.zeros(g, dt)
+    oracle_leaves = roots.copy()
+    import oracle
+    oracle.c.build_sumtree_from_array(oracle_leaves, tree)
+    for j in range(m):
+        h = (int(shard[j]) + g) // 2
+        while h > 0:
+            tree[h] = tree[h] + d[j]
+            h //= 2
+    assert np.frombuffer(heaps[0], dt)[:g].tobytes() == tree.tobytes()
+
+
+@pytest.mark.parametrize("world,dt_name", [(2, "float32"), (8, "float32"), (4, "float64"), (4, "int32")])
+def test_sharded_cuda_path_on_one_gpu(world, dt_name, monkeypatch):
+    """All ranks as threads on cuda:0 (tests/_thread_group.py): the complete CUDA path of the
+    sharded tree against ONE oracle tree, on a box with a single GPU."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle
+    from _thread_group import ThreadGroup
+
+    import starr_b200.sharded as sharded
+    group = ThreadGroup(world)
+    monkeypatch.setattr(sharded, "dist", group)
+    dev = torch.device("cuda", 0)
+    dt, tdt = np.dtype(dt_name), getattr(torch, dt_name)
+    n = 1 << 16
+    rng = np.random.default_rng(11)
+    draw = (lambda k: np.exp(rng.uniform(-8, 8, k)).astype(dt)) if dt.kind == "f" else \
+        (lambda k: rng.integers(0, 1000, k).astype(dt))
+    leaves = draw(n)
+    ref_leaves, ref_tree = leaves.copy(), np.zeros(n, dt)
+    oracle.c.build_sumtree_from_array(ref_leaves, ref_tree)
+    nl = n // world
+    batches = []
+    for m, nv in ((1, 1), (4096, 4096), (20_000, 333), (70_000, 70_000)):
+        idx = rng.integers(0, n, m).astype(np.int64)
+        if m == 20_000:
+            idx[rng.random(m) < 0.7] = rng.integers(0, 64, 1)[0]        # skewed: duplicates in one shard
+        vals, u = draw(nv), rng.random(10_000)
+        oracle.c.update_sumtree(idx.astype(np.intp), vals, ref_leaves, ref_tree)
+        want = np.zeros(u.size, np.intp)
+        oracle.c.get_prefix_sum_idx(want, (ref_tree[1] * u).astype(dt), ref_leaves, ref_tree)
+        batches.append((idx, vals, u, ref_tree.copy(), ref_leaves.copy(), want))
+
+    def rank_body(r):
+        torch.cuda.set_device(0)
+        st = sharded.ShardedSumTree(n, tdt, local_leaves=torch.from_numpy(leaves[r * nl:(r + 1) * nl].copy()).to(dev))
+        bad_steps = []
+        for b, (idx, vals, u, tree_after, leaves_after, want) in enumerate(batches):
+            st.update_(torch.from_numpy(idx).to(dev), torch.from_numpy(vals).to(dev))
+            if st.gather_sumtree().cpu().numpy().tobytes() != tree_after.tobytes():
+                bad_steps.append((b, "tree"))
+            if st.gather_leaves().cpu().numpy().tobytes() != leaves_after.tobytes():
+                bad_steps.append((b, "leaves"))
+            if not np.array_equal(st.sample_uniform(torch.from_numpy(u).to(dev)).cpu().numpy(), want):
+                bad_steps.append((b, "sample"))
+        st.poll()
+        # a bad batch is skipped on every rank alike and reported by poll()
+        before = st.gather_sumtree().cpu().numpy().tobytes()
+        bad = torch.from_numpy(batches[1][0]).to(dev).clone()
+        bad[17] = n
+        st.update_(bad, torch.from_numpy(batches[1][1]).to(dev))
+        try:
+            st.poll()
+            bad_steps.append(("bad batch", "not reported"))
+        except IndexError:
+            pass
+        if st.gather_sumtree().cpu().numpy().tobytes() != before:
+            bad_steps.append(("bad batch", "tree modified"))
+        return bad_steps
+
+    assert group.run(rank_body) == [[]] * world
