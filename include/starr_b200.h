@@ -149,7 +149,8 @@ ST_API int st_top_fold_apply_device(st_tree *t, const void *leaf_dev, int leaf_i
  *   slot_out[j]    the stable position of j among the elements of its shard (-1 if invalid),
  *   own_ids_out[k], own_payload_out[k]   (both nullable) for the k-th element of shard `rank`:
  *                  ids[j] - (rank << shift) and payload[j % npayload] (tree dtype),
- *   counts_out_host[s]   the number of elements of every shard -- the call waits for the stream. */
+ *   counts_out_host[s]   the number of elements of every shard -- the call waits for the stream.
+ * shard_out must be 8-byte aligned and slot_out 16-byte aligned (vector stores). */
 ST_API int st_shard_plan_device(st_tree *local, st_tree *top, const int64_t *ids_dev, int64_t m, int shift, int shards,
                          int rank, const void *payload_dev, int64_t npayload, int check_negative,
                          uint8_t *shard_out_dev, int32_t *slot_out_dev, int64_t *own_ids_out_dev,

@@ -396,6 +396,8 @@ int st_shard_plan_device(st_tree *local, st_tree *top, const int64_t *ids_dev, i
         !counts_out_host || (m > 0 && (!ids_dev || !shard_out_dev || !slot_out_dev)) ||
         (own_payload_out_dev && (!payload_dev || npayload <= 0)))
         return fail(ST_ERR_ARG, "st_shard_plan_device: bad argument");
+    if (((uintptr_t)shard_out_dev & 7) || ((uintptr_t)slot_out_dev & 15))
+        return fail(ST_ERR_ARG, "st_shard_plan_device: shard_out must be 8-byte and slot_out 16-byte aligned");
     for (int i = 0; i < shards; ++i) counts_out_host[i] = 0;
     if (m == 0) return ST_OK;
     device_guard g(local->device);

@@ -21,6 +21,38 @@ constexpr int SH_MAX = 64;          // shards (the top tree is limited to 64 lea
 constexpr int SH_WARPS = SH_THREADS / 32;
 constexpr uint8_t SH_NONE = 255;    // id outside every shard (the batch is flagged and skipped)
 
+// Eight 16-bit counters (one per shard of the current group of eight shards) packed in 128 bits:
+// a tile holds 2048 elements, so no field can overflow into its neighbour.
+struct pk128 {
+    unsigned long long lo, hi;
+};
+struct pk_add {
+    __device__ __forceinline__ pk128 operator()(const pk128 &a, const pk128 &b) const
+    {
+        return pk128{a.lo + b.lo, a.hi + b.hi};
+    }
+};
+__device__ __forceinline__ void pk_inc(pk128 &v, int k)   // k in 0..7
+{
+    const unsigned long long one = 1ull << (16 * (k & 3));
+    if (k < 4) v.lo += one; else v.hi += one;
+}
+__device__ __forceinline__ unsigned int pk_get(const pk128 &v, int k)
+{
+    return (unsigned int)(((k < 4 ? v.lo : v.hi) >> (16 * (k & 3))) & 0xffffu);
+}
+
+// Thread t of a tile owns the SH_E = 8 consecutive elements [tile*2048 + 8t, +8): their shard ids
+// travel as one packed 64-bit word.
+__device__ __forceinline__ unsigned long long load_shard8(const uint8_t *__restrict__ shard8, int64_t j0, int64_t m)
+{
+    if (j0 + SH_E <= m) return *(const unsigned long long *)(shard8 + j0);   // 8-byte aligned: j0 % 8 == 0
+    unsigned long long w = 0;
+    for (int k = 0; k < SH_E; ++k)
+        w |= (unsigned long long)(j0 + k < m ? shard8[j0 + k] : SH_NONE) << (8 * k);
+    return w;
+}
+
 template <typename T, bool CHECK_NEG>
 __global__ void __launch_bounds__(SH_THREADS) shard_count_kernel(const int64_t *__restrict__ ids, int64_t m, int shift,
                                                                  int shards, const T *__restrict__ payload,
@@ -28,29 +60,38 @@ __global__ void __launch_bounds__(SH_THREADS) shard_count_kernel(const int64_t *
                                                                  unsigned int *__restrict__ tile_counts, int64_t ntiles,
                                                                  unsigned int *status_a, unsigned int *status_b)
 {
-    __shared__ unsigned int hist[SH_MAX];
-    const int tid = threadIdx.x, lane = tid & 31;
-    if (tid < SH_MAX) hist[tid] = 0;
-    __syncthreads();
-    const int64_t base = (int64_t)blockIdx.x * SH_TILE;
+    __shared__ pk128 s_warp[SH_WARPS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t j0 = (int64_t)blockIdx.x * SH_TILE + (int64_t)tid * SH_E;
     unsigned int bad = 0;
+    unsigned long long word = 0;
+    int64_t id[SH_E];
+    if (j0 + SH_E <= m && ((uintptr_t)ids & 15) == 0) {
+        const longlong2 *p = (const longlong2 *)(ids + j0);
 #pragma unroll
-    for (int r = 0; r < SH_E; ++r) {
-        const int64_t j = base + r * SH_THREADS + tid;
-        int key = 0x100 + lane;   // unique: matches nobody
-        if (j < m) {
-            const int64_t id = ids[j];
-            const int64_t q = id >> shift;
-            if (id < 0 || q >= shards) {
-                bad |= STF_INDEX;
-                shard_out[j] = SH_NONE;
-            } else {
-                shard_out[j] = (uint8_t)q;
-                key = (int)q;
-            }
+        for (int k = 0; k < SH_E / 2; ++k) {
+            const longlong2 v = p[k];
+            id[2 * k] = v.x;
+            id[2 * k + 1] = v.y;
         }
-        const unsigned int peers = __match_any_sync(0xffffffffu, key);
-        if (key < 0x100 && (peers & ((1u << lane) - 1)) == 0) atomicAdd(&hist[key], __popc(peers));
+    } else {
+#pragma unroll
+        for (int k = 0; k < SH_E; ++k) id[k] = j0 + k < m ? ids[j0 + k] : 0;
+    }
+#pragma unroll
+    for (int k = 0; k < SH_E; ++k) {
+        unsigned long long b = SH_NONE;
+        if (j0 + k < m) {
+            const int64_t q = id[k] >> shift;
+            if (id[k] < 0 || q >= shards) bad |= STF_INDEX;
+            else b = (unsigned long long)q;
+        }
+        word |= b << (8 * k);
+    }
+    if (j0 + SH_E <= m) {
+        *(unsigned long long *)(shard_out + j0) = word;
+    } else {
+        for (int k = 0; k < SH_E && j0 + k < m; ++k) shard_out[j0 + k] = (uint8_t)(word >> (8 * k));
     }
     if constexpr (CHECK_NEG && is_signed_t<T>::value) {
         // the reference rejects a negative entry anywhere in vals, used or not (pyx:37-39)
@@ -62,8 +103,28 @@ __global__ void __launch_bounds__(SH_THREADS) shard_count_kernel(const int64_t *
         atomicOr(status_a + SW_STATUS, bad);
         if (status_b) atomicOr(status_b + SW_STATUS, bad);
     }
-    __syncthreads();
-    if (tid < shards) tile_counts[(int64_t)tid * ntiles + blockIdx.x] = hist[tid];
+    for (int g0 = 0; g0 < shards; g0 += 8) {
+        pk128 c{0, 0};
+#pragma unroll
+        for (int k = 0; k < SH_E; ++k) {
+            const int b = (int)((word >> (8 * k)) & 0xff) - g0;
+            if (b >= 0 && b < 8) pk_inc(c, b);
+        }
+#pragma unroll
+        for (int off = 16; off; off >>= 1) {
+            c.lo += __shfl_xor_sync(0xffffffffu, c.lo, off);
+            c.hi += __shfl_xor_sync(0xffffffffu, c.hi, off);
+        }
+        if (lane == 0) s_warp[warp] = c;
+        __syncthreads();
+        if (tid < 8 && g0 + tid < shards) {
+            unsigned int sum = 0;
+#pragma unroll
+            for (int w = 0; w < SH_WARPS; ++w) sum += pk_get(s_warp[w], tid);
+            tile_counts[(int64_t)(g0 + tid) * ntiles + blockIdx.x] = sum;
+        }
+        __syncthreads();
+    }
 }
 
 // one CTA per shard: exclusive scan of its per-tile counts, total -> counts[shard]
@@ -73,68 +134,81 @@ __global__ void __launch_bounds__(SH_THREADS) shard_scan_kernel(unsigned int *__
     typedef cub::BlockScan<unsigned int, SH_THREADS> scan_t;
     __shared__ typename scan_t::TempStorage tmp;
     unsigned int *row = tile_counts + (int64_t)blockIdx.x * ntiles;
-    const int64_t per = (ntiles + SH_THREADS - 1) / SH_THREADS;
-    const int64_t lo = per * threadIdx.x;
-    const int64_t hi = lo + per < ntiles ? lo + per : ntiles;
-    unsigned int sum = 0;
-    for (int64_t i = lo; i < hi; ++i) sum += row[i];
-    unsigned int off, total;
-    scan_t(tmp).ExclusiveSum(sum, off, total);
-    for (int64_t i = lo; i < hi; ++i) {
-        const unsigned int c = row[i];
-        row[i] = off;
-        off += c;
+    unsigned int running = 0;
+    for (int64_t b = 0; b < ntiles; b += SH_THREADS * 4) {
+        const int64_t i0 = b + threadIdx.x * 4;
+        unsigned int v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = i0 + k < ntiles ? row[i0 + k] : 0u;
+        unsigned int total;
+        scan_t(tmp).ExclusiveSum(v, v, total);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (i0 + k < ntiles) row[i0 + k] = v[k] + running;
+        running += total;
+        __syncthreads();
     }
-    if (threadIdx.x == 0) counts[blockIdx.x] = total;
+    if (threadIdx.x == 0) counts[blockIdx.x] = running;
 }
 
 template <typename T>
-__global__ void __launch_bounds__(SH_THREADS) shard_slot_kernel(const int64_t *__restrict__ ids, int64_t m, int shift,
-                                                                int shards, int rank, const T *__restrict__ payload,
-                                                                int64_t npayload, const uint8_t *__restrict__ shard8,
-                                                                const unsigned int *__restrict__ tile_off,
-                                                                int64_t ntiles, int32_t *__restrict__ slot_out,
-                                                                int64_t *__restrict__ own_ids, T *__restrict__ own_payload)
+__global__ void __launch_bounds__(SH_THREADS, 3) shard_slot_kernel(const int64_t *__restrict__ ids, int64_t m, int shift,
+                                                                   int shards, int rank, const T *__restrict__ payload,
+                                                                   int64_t npayload, const uint8_t *__restrict__ shard8,
+                                                                   const unsigned int *__restrict__ tile_off,
+                                                                   int64_t ntiles, int32_t *__restrict__ slot_out,
+                                                                   int64_t *__restrict__ own_ids, T *__restrict__ own_payload)
 {
-    __shared__ unsigned int s_base[SH_MAX];           // elements of each shard before the current row
-    __shared__ unsigned int s_wc[SH_WARPS][SH_MAX];   // per-warp counts of the current row
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid < SH_MAX) s_base[tid] = tid < shards ? tile_off[(int64_t)tid * ntiles + blockIdx.x] : 0u;
-    for (int i = tid; i < SH_WARPS * SH_MAX; i += SH_THREADS) (&s_wc[0][0])[i] = 0;
-    __syncthreads();
-    const int64_t base = (int64_t)blockIdx.x * SH_TILE;
-    const int64_t origin = (int64_t)rank << shift;
-    for (int r = 0; r < SH_E; ++r) {
-        const int64_t j = base + r * SH_THREADS + tid;
-        const int sh = j < m ? (int)shard8[j] : (int)SH_NONE;
-        const bool valid = sh < shards;
-        const unsigned int peers = __match_any_sync(0xffffffffu, valid ? sh : 0x100 + lane);
-        const int within = __popc(peers & ((1u << lane) - 1));
-        if (valid && within == 0) s_wc[warp][sh] = __popc(peers);
-        __syncthreads();
-        if (valid) {
-            unsigned int before = s_base[sh];
-            for (int w = 0; w < warp; ++w) before += s_wc[w][sh];
-            const unsigned int slot = before + within;
-            slot_out[j] = (int32_t)slot;
-            if (sh == rank) {
-                if (own_ids) own_ids[slot] = ids[j] - origin;
-                if (own_payload) own_payload[slot] = payload[j < npayload ? j : j % npayload];
-            }
-        } else if (j < m) {
-            slot_out[j] = -1;
-        }
-        __syncthreads();
-        if (tid < shards) {
-            unsigned int sum = 0;
+    typedef cub::BlockScan<pk128, SH_THREADS> scan_t;
+    __shared__ typename scan_t::TempStorage tmp;
+    __shared__ unsigned int s_off[SH_MAX];            // elements of each shard before this tile
+    __shared__ int32_t s_slot[SH_TILE];               // staged so that the global stores are coalesced
+    __shared__ unsigned short s_own[SH_TILE];         // this rank's elements of the tile, in slot order
+    __shared__ unsigned int s_nown;
+    const int tid = threadIdx.x;
+    if (tid < SH_MAX) s_off[tid] = tid < shards ? tile_off[(int64_t)tid * ntiles + blockIdx.x] : 0u;
+    const int64_t tile0 = (int64_t)blockIdx.x * SH_TILE;
+    const int64_t j0 = tile0 + (int64_t)tid * SH_E;
+    const unsigned long long word = load_shard8(shard8, j0, m);
+    // ids outside every shard (and the padding of a ragged last tile) keep slot -1
 #pragma unroll
-            for (int w = 0; w < SH_WARPS; ++w) {
-                sum += s_wc[w][tid];
-                s_wc[w][tid] = 0;
-            }
-            s_base[tid] += sum;
+    for (int k = 0; k < SH_E; ++k) s_slot[k * SH_THREADS + tid] = -1;
+    __syncthreads();
+    for (int g0 = 0; g0 < shards; g0 += 8) {
+        pk128 c{0, 0};
+#pragma unroll
+        for (int k = 0; k < SH_E; ++k) {
+            const int b = (int)((word >> (8 * k)) & 0xff) - g0;
+            if (b >= 0 && b < 8) pk_inc(c, b);
         }
-        __syncthreads();
+        pk128 pre, total;
+        scan_t(tmp).ExclusiveScan(c, pre, pk128{0, 0}, pk_add(), total);
+        if (tid == 0 && rank >= g0 && rank < g0 + 8) s_nown = pk_get(total, rank - g0);
+#pragma unroll
+        for (int k = 0; k < SH_E; ++k) {
+            const int b = (int)((word >> (8 * k)) & 0xff) - g0;
+            if (b >= 0 && b < 8) {
+                const unsigned int within = pk_get(pre, b);
+                s_slot[tid * SH_E + k] = (int32_t)(s_off[b + g0] + within);
+                if (b + g0 == rank) s_own[within] = (unsigned short)(tid * SH_E + k);
+                pk_inc(pre, b);
+            }
+        }
+        __syncthreads();   // tmp is reused by the next group; s_slot / s_own / s_nown are complete after the last one
+    }
+#pragma unroll
+    for (int r = 0; r < SH_E; ++r) {
+        const int i = r * SH_THREADS + tid;
+        if (tile0 + i < m) slot_out[tile0 + i] = s_slot[i];
+    }
+    // compaction of this rank's elements: consecutive threads write consecutive slots
+    if (!own_ids && !own_payload) return;
+    const int64_t origin = (int64_t)rank << shift;
+    const unsigned int nown = s_nown, first = s_off[rank];
+    for (unsigned int i = tid; i < nown; i += SH_THREADS) {
+        const int64_t j = tile0 + s_own[i];
+        if (own_ids) own_ids[first + i] = ids[j] - origin;
+        if (own_payload) own_payload[first + i] = payload[j < npayload ? j : j % npayload];
     }
 }
 
