@@ -285,11 +285,21 @@ def run_ours(args):
     windows = []
     t_w0 = time.time()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * steps + 1)]
+    # Sharded runs plan ahead: owner / slot / compaction of batch k+1 (it reads nothing of the tree) is
+    # computed on a side stream while batch k is applied.  One plan per step inside the timed region.
+    s_plan = torch.cuda.Stream() if world > 1 else None
+    plan = tree.plan_update(*dbatches[warmup % N_BATCHES][:2], stream=s_plan) if world > 1 else None
+    barrier()
     ev[0].record()
     for k in range(steps):
         i, v, u = dbatches[(warmup + k) % N_BATCHES]
-        tree.update_(i, v)
-        ev[2 * k + 1].record()
+        if world > 1:
+            tree.update_(plan=plan)
+            ev[2 * k + 1].record()
+            plan = tree.plan_update(*dbatches[(warmup + k + 1) % N_BATCHES][:2], stream=s_plan)
+        else:
+            tree.update_(i, v)
+            ev[2 * k + 1].record()
         tree.sample_uniform(u, out=out)
         ev[2 * k + 2].record()
     barrier()
@@ -329,6 +339,10 @@ def run_ours(args):
             ev_free[slot].record(s_main)
             ev_read[slot].record(s_main)
         prefetch(0)
+        plan = None
+        if world > 1:
+            s_plan.wait_event(ev_in[0])
+            plan = tree.plan_update(*dbuf[0][:2], stream=s_plan)
         for k in range(nsteps):
             slot = k % 2
             if k + 1 < nsteps:
@@ -336,7 +350,13 @@ def run_ours(args):
             s_main.wait_event(ev_in[slot])
             s_main.wait_event(ev_read[slot])            # previous results of this slot are on the host
             di, dv, du = dbuf[slot]
-            tree.update_(di, dv)
+            if world > 1:
+                tree.update_(plan=plan)
+                if k + 1 < nsteps:                      # plan of the next batch as soon as its inputs have landed
+                    s_plan.wait_event(ev_in[(k + 1) % 2])
+                    plan = tree.plan_update(*dbuf[(k + 1) % 2][:2], stream=s_plan)
+            else:
+                tree.update_(di, dv)
             tree.sample_uniform(du, out=obuf[slot])
             ev_free[slot].record(s_main)
             ev_done[slot].record(s_main)

@@ -141,20 +141,21 @@ ST_API int st_top_fold_maps_device(st_tree *t, const void *leaf_dev, int leaf_it
                             int64_t m, int64_t chunk_lo, int64_t chunk_hi, void *recs_dev, void *stream);
 ST_API int st_top_fold_apply_device(st_tree *t, const void *leaf_dev, int leaf_itemsize, const void *deltas_dev,
                              int64_t m, const void *recs_dev, void *stream);
-/* Plan of one replicated batch of the sharded tree.  Element j belongs to shard ids[j] >> shift
- * (0 <= shard < shards <= 64; anything else flags ST_ERR_INDEX on `local` and, if given, `top`,
- * so that the whole batch is skipped on every rank alike; with check_negative a negative entry
- * anywhere in payload flags ST_ERR_NEGATIVE_VALS the same way, pyx:37-39).  Writes
- *   shard_out[j]   the owning shard (255 for an invalid id),
+/* Plan of one replicated batch of the sharded tree.  Element j belongs to shard ids[j] >> shift.
+ * Synchronous (waits for `stream`, because the per-shard counts are needed on the host), and
+ * reads nothing of the tree, so it may run on a side stream ahead of the batch it plans.  Writes
+ *   shard_out[j]   the owning shard (255 for an id outside [0, shards << shift)),
  *   slot_out[j]    the stable position of j among the elements of its shard (-1 if invalid),
  *   own_ids_out[k], own_payload_out[k]   (both nullable) for the k-th element of shard `rank`:
  *                  ids[j] - (rank << shift) and payload[j % npayload] (tree dtype),
- *   counts_out_host[s]   the number of elements of every shard -- the call waits for the stream.
- * shard_out must be 8-byte aligned and slot_out 16-byte aligned (vector stores). */
-ST_API int st_shard_plan_device(st_tree *local, st_tree *top, const int64_t *ids_dev, int64_t m, int shift, int shards,
-                         int rank, const void *payload_dev, int64_t npayload, int check_negative,
-                         uint8_t *shard_out_dev, int32_t *slot_out_dev, int64_t *own_ids_out_dev,
-                         void *own_payload_out_dev, int64_t *counts_out_host, void *stream);
+ *   counts_out_host[s]   the number of elements of every shard (shards <= 64).
+ * Returns ST_ERR_INDEX for an id outside every shard and, with check_negative, ST_ERR_NEGATIVE_VALS
+ * for a negative entry anywhere in payload (pyx:37-39) -- the same verdict on every rank, before
+ * anything was modified.  shard_out must be 8-byte and slot_out 16-byte aligned (vector stores). */
+ST_API int st_shard_plan_device(st_tree *t, const int64_t *ids_dev, int64_t m, int shift, int shards, int rank,
+                         const void *payload_dev, int64_t npayload, int check_negative, uint8_t *shard_out_dev,
+                         int32_t *slot_out_dev, int64_t *own_ids_out_dev, void *own_payload_out_dev,
+                         int64_t *counts_out_host, void *stream);
 /* Per-shard results come back as slabs (shard s at slabs[s * slab_stride ...], compact, in the
  * shard's batch order); these put them back into batch order:
  *   values:  out[j] = slabs[shard[j] * slab_stride + slot[j]]               (tree dtype)

@@ -85,7 +85,7 @@ _SIGNATURES = {
     "st_top_fold_record_bytes": (c_int, [c_void_p]),
     "st_top_fold_maps_device": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
     "st_top_fold_apply_device": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_void_p]),
-    "st_shard_plan_device": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_int64, c_int,
+    "st_shard_plan_device": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_int64, c_int,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "st_shard_expand_values_device": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
     "st_shard_expand_indices_device": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p,
@@ -288,16 +288,14 @@ class TreeHandle:
         check(lib().st_top_fold_apply_device(self.ptr, c_void_p(leaf_ptr), int(leaf_itemsize), c_void_p(deltas_ptr),
                                              int(m), c_void_p(recs_ptr), c_void_p(stream)))
 
-    def shard_plan_device(self, top: "TreeHandle | None", ids_ptr: int, m: int, shift: int, shards: int, rank: int,
-                          payload_ptr: int, npayload: int, check_negative: bool, shard_out_ptr: int,
-                          slot_out_ptr: int, own_ids_out_ptr: int, own_payload_out_ptr: int,
-                          stream: int = 0) -> list[int]:
+    def shard_plan_device(self, ids_ptr: int, m: int, shift: int, shards: int, rank: int, payload_ptr: int,
+                          npayload: int, check_negative: bool, shard_out_ptr: int, slot_out_ptr: int,
+                          own_ids_out_ptr: int, own_payload_out_ptr: int, stream: int = 0) -> list[int]:
         counts = (c_int64 * int(shards))()
-        check(lib().st_shard_plan_device(self.ptr, top.ptr if top is not None else None, c_void_p(ids_ptr), int(m),
-                                         int(shift), int(shards), int(rank), c_void_p(payload_ptr), int(npayload),
-                                         int(bool(check_negative)), c_void_p(shard_out_ptr), c_void_p(slot_out_ptr),
-                                         c_void_p(own_ids_out_ptr), c_void_p(own_payload_out_ptr), counts,
-                                         c_void_p(stream)))
+        check(lib().st_shard_plan_device(self.ptr, c_void_p(ids_ptr), int(m), int(shift), int(shards), int(rank),
+                                         c_void_p(payload_ptr), int(npayload), int(bool(check_negative)),
+                                         c_void_p(shard_out_ptr), c_void_p(slot_out_ptr), c_void_p(own_ids_out_ptr),
+                                         c_void_p(own_payload_out_ptr), counts, c_void_p(stream)))
         return list(counts)
 
     def shard_expand_values_device(self, shard_ptr: int, slot_ptr: int, m: int, slabs_ptr: int, slab_stride: int,

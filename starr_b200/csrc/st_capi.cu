@@ -387,32 +387,33 @@ int st_top_fold_apply_device(st_tree *t, const void *leaf_dev, int leaf_itemsize
     return ST_OK;
 }
 
-int st_shard_plan_device(st_tree *local, st_tree *top, const int64_t *ids_dev, int64_t m, int shift, int shards,
-                         int rank, const void *payload_dev, int64_t npayload, int check_negative,
-                         uint8_t *shard_out_dev, int32_t *slot_out_dev, int64_t *own_ids_out_dev,
-                         void *own_payload_out_dev, int64_t *counts_out_host, void *stream)
+int st_shard_plan_device(st_tree *t, const int64_t *ids_dev, int64_t m, int shift, int shards, int rank,
+                         const void *payload_dev, int64_t npayload, int check_negative, uint8_t *shard_out_dev,
+                         int32_t *slot_out_dev, int64_t *own_ids_out_dev, void *own_payload_out_dev,
+                         int64_t *counts_out_host, void *stream)
 {
-    if (!local || m < 0 || shards < 1 || shards > 64 || rank < 0 || rank >= shards || shift < 0 || shift > 62 ||
+    if (!t || m < 0 || shards < 1 || shards > 64 || rank < 0 || rank >= shards || shift < 0 || shift > 62 ||
         !counts_out_host || (m > 0 && (!ids_dev || !shard_out_dev || !slot_out_dev)) ||
-        (own_payload_out_dev && (!payload_dev || npayload <= 0)))
+        ((own_payload_out_dev || check_negative) && (!payload_dev || npayload <= 0)))
         return fail(ST_ERR_ARG, "st_shard_plan_device: bad argument");
     if (((uintptr_t)shard_out_dev & 7) || ((uintptr_t)slot_out_dev & 15))
         return fail(ST_ERR_ARG, "st_shard_plan_device: shard_out must be 8-byte and slot_out 16-byte aligned");
     for (int i = 0; i < shards; ++i) counts_out_host[i] = 0;
     if (m == 0) return ST_OK;
-    device_guard g(local->device);
-    scratch_carver c(local);
+    device_guard g(t->device);
+    scratch_carver c(t);
     const size_t bytes = st::shard_plan_scratch_bytes(m, shards);
     c.add(bytes);
     CU(c.commit());
     void *scratch = c.take(bytes);
-    unsigned int *counts_pin = (unsigned int *)local->h_pin;
-    CU(st::launch_shard_plan(local, top, ids_dev, m, shift, shards, rank, payload_dev, npayload, check_negative,
-                             shard_out_dev, slot_out_dev, own_ids_out_dev, own_payload_out_dev, scratch,
-                             (unsigned int *)local->d_pin, (cudaStream_t)stream));
+    const unsigned int *counts_pin = (const unsigned int *)t->h_pin;
+    CU(st::launch_shard_plan(t, ids_dev, m, shift, shards, rank, payload_dev, npayload, check_negative, shard_out_dev,
+                             slot_out_dev, own_ids_out_dev, own_payload_out_dev, scratch, (unsigned int *)t->d_pin,
+                             (cudaStream_t)stream));
     CU(cudaStreamSynchronize((cudaStream_t)stream));
     for (int i = 0; i < shards; ++i) counts_out_host[i] = (int64_t)counts_pin[i];
-    return ST_OK;
+    const int status = status_from_flags(counts_pin[shards]);
+    return status == ST_OK ? ST_OK : fail(status, "%s", st_status_string(status));
 }
 
 int st_shard_expand_values_device(const st_tree *t, const uint8_t *shard_dev, const int32_t *slot_dev, int64_t m,

@@ -78,8 +78,9 @@ cudaError_t launch_fold_by_leaf_apply(st_tree *t, const void *leaf, int leaf_byt
 
 // subtree-sharded layout helpers (st_shard.cu)
 size_t shard_plan_scratch_bytes(int64_t m, int shards);
-cudaError_t launch_shard_plan(st_tree *local, st_tree *top, const int64_t *ids, int64_t m, int shift, int shards,
-                              int rank, const void *payload, int64_t npayload, int check_negative, uint8_t *shard_out,
+// counts_out: [shards] element counts, then one word of STF_* validation flags
+cudaError_t launch_shard_plan(st_tree *t, const int64_t *ids, int64_t m, int shift, int shards, int rank,
+                              const void *payload, int64_t npayload, int check_negative, uint8_t *shard_out,
                               int32_t *slot_out, int64_t *own_ids_out, void *own_payload_out, void *scratch,
                               unsigned int *counts_out, cudaStream_t s);
 cudaError_t launch_shard_expand_values(const st_tree *t, const uint8_t *shard, const int32_t *slot, int64_t m,

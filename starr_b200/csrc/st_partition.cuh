@@ -28,7 +28,7 @@ constexpr int FOLD_CHUNK_ELEMS = 1024;   // == FOLD_CHUNK of st_ordered_fold.cuh
 constexpr int PART_THREADS = 256;
 constexpr int PART_E = 8;
 constexpr int PART_TILE = PART_THREADS * PART_E;                       // 2048
-constexpr int PART_MAX_TILES = (int)(UPDATE_MAX_CHUNK / PART_TILE);    // 512: one tile per co-resident CTA
+constexpr int PART_MAX_TILES = (int)(UPDATE_MAX_CHUNK / PART_TILE);    // 1024
 
 template <typename T> struct part_params {
     T *H;

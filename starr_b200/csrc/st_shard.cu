@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(SH_THREADS) shard_count_kernel(const int64_t *
                                                                  int shards, const T *__restrict__ payload,
                                                                  int64_t npayload, uint8_t *__restrict__ shard_out,
                                                                  unsigned int *__restrict__ tile_counts, int64_t ntiles,
-                                                                 unsigned int *status_a, unsigned int *status_b)
+                                                                 unsigned int *flags)
 {
     __shared__ pk128 s_warp[SH_WARPS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -99,10 +99,7 @@ __global__ void __launch_bounds__(SH_THREADS) shard_count_kernel(const int64_t *
         for (int64_t k = (int64_t)blockIdx.x * SH_THREADS + tid; k < npayload; k += stride)
             if (payload[k] < T(0)) bad |= STF_NEG_VALS;
     }
-    if (bad) {
-        atomicOr(status_a + SW_STATUS, bad);
-        if (status_b) atomicOr(status_b + SW_STATUS, bad);
-    }
+    if (bad) atomicOr(flags, bad);
     for (int g0 = 0; g0 < shards; g0 += 8) {
         pk128 c{0, 0};
 #pragma unroll
@@ -127,10 +124,13 @@ __global__ void __launch_bounds__(SH_THREADS) shard_count_kernel(const int64_t *
     }
 }
 
-// one CTA per shard: exclusive scan of its per-tile counts, total -> counts[shard]
+// one CTA per shard: exclusive scan of its per-tile counts, total -> counts[shard];
+// counts[shards] receives the validation flags of the count kernel
 __global__ void __launch_bounds__(SH_THREADS) shard_scan_kernel(unsigned int *__restrict__ tile_counts, int64_t ntiles,
-                                                                unsigned int *__restrict__ counts)
+                                                                unsigned int *__restrict__ counts,
+                                                                const unsigned int *__restrict__ flags)
 {
+    if (blockIdx.x == 0 && threadIdx.x == 0) counts[gridDim.x] = *flags;
     typedef cub::BlockScan<unsigned int, SH_THREADS> scan_t;
     __shared__ typename scan_t::TempStorage tmp;
     unsigned int *row = tile_counts + (int64_t)blockIdx.x * ntiles;
@@ -241,13 +241,13 @@ __global__ void __launch_bounds__(256) shard_expand_indices_kernel(const uint8_t
 // -----------------------------------------------------------------------------------------
 static int64_t shard_tiles(int64_t m) { return (m + SH_TILE - 1) / SH_TILE; }
 
-size_t shard_plan_scratch_bytes(int64_t m, int shards)
+size_t shard_plan_scratch_bytes(int64_t m, int shards)   // per-tile counts of every shard + one flags word
 {
-    return (size_t)shards * (size_t)(shard_tiles(m) > 0 ? shard_tiles(m) : 1) * sizeof(unsigned int);
+    return ((size_t)shards * (size_t)(shard_tiles(m) > 0 ? shard_tiles(m) : 1) + 1) * sizeof(unsigned int);
 }
 
-cudaError_t launch_shard_plan(st_tree *local, st_tree *top, const int64_t *ids, int64_t m, int shift, int shards,
-                              int rank, const void *payload, int64_t npayload, int check_negative, uint8_t *shard_out,
+cudaError_t launch_shard_plan(st_tree *t, const int64_t *ids, int64_t m, int shift, int shards, int rank,
+                              const void *payload, int64_t npayload, int check_negative, uint8_t *shard_out,
                               int32_t *slot_out, int64_t *own_ids_out, void *own_payload_out, void *scratch,
                               unsigned int *counts_out, cudaStream_t s)
 {
@@ -256,18 +256,18 @@ cudaError_t launch_shard_plan(st_tree *local, st_tree *top, const int64_t *ids, 
     const int64_t ntiles = shard_tiles(m);
     if (ntiles <= 0 || ntiles > 0x7fffffffLL) return cudaErrorInvalidValue;
     unsigned int *tile_counts = (unsigned int *)scratch;
-    unsigned int *status_b = top ? top->d_status : nullptr;
+    unsigned int *flags = tile_counts + (size_t)shards * ntiles;
+    cudaError_t e = cudaMemsetAsync(flags, 0, sizeof(unsigned int), s);
+    if (e != cudaSuccess) return e;
     g_kernel_launches += 3;
-    ST_DISPATCH(local->dtype, {
+    ST_DISPATCH(t->dtype, {
         if (check_negative)
             shard_count_kernel<T, true><<<(unsigned)ntiles, SH_THREADS, 0, s>>>(
-                ids, m, shift, shards, (const T *)payload, npayload, shard_out, tile_counts, ntiles, local->d_status,
-                status_b);
+                ids, m, shift, shards, (const T *)payload, npayload, shard_out, tile_counts, ntiles, flags);
         else
             shard_count_kernel<T, false><<<(unsigned)ntiles, SH_THREADS, 0, s>>>(
-                ids, m, shift, shards, (const T *)payload, npayload, shard_out, tile_counts, ntiles, local->d_status,
-                status_b);
-        shard_scan_kernel<<<(unsigned)shards, SH_THREADS, 0, s>>>(tile_counts, ntiles, counts_out);
+                ids, m, shift, shards, (const T *)payload, npayload, shard_out, tile_counts, ntiles, flags);
+        shard_scan_kernel<<<(unsigned)shards, SH_THREADS, 0, s>>>(tile_counts, ntiles, counts_out, flags);
         shard_slot_kernel<T><<<(unsigned)ntiles, SH_THREADS, 0, s>>>(ids, m, shift, shards, rank, (const T *)payload,
                                                                     npayload, shard_out, tile_counts, ntiles, slot_out,
                                                                     own_ids_out, (T *)own_payload_out);

@@ -4,7 +4,7 @@
 
 namespace st {
 
-constexpr int64_t UPDATE_MAX_CHUNK = 1 << 20;
+constexpr int64_t UPDATE_MAX_CHUNK = 1 << 21;
 constexpr int SHORT_SEG = 32;    // segments up to this length are folded by their head thread
 #ifndef ST_RETIRE_SEG
 #define ST_RETIRE_SEG 512

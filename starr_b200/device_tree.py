@@ -171,26 +171,30 @@ class DeviceSumTree:
             self._h.top_fold_apply_device(leaf.data_ptr(), leaf.element_size(), deltas.data_ptr(), leaf.numel(),
                                           recs.data_ptr(), _stream())
 
-    def shard_plan(self, top: "DeviceSumTree | None", ids: torch.Tensor, shift: int, shards: int, rank: int,
-                   payload: torch.Tensor, check_negative: bool, want_ids: bool = True):
+    def shard_plan(self, ids: torch.Tensor, shift: int, shards: int, rank: int, payload: torch.Tensor,
+                   check_negative: bool, want_ids: bool = True, out=None):
         """Plan of one replicated batch of a sharded tree (``st_shard_plan_device``): returns
-        ``(shard uint8[m], slot int32[m], own_ids int64[m] | None, own_payload dtype[m], counts)``;
+        ``(shard uint8[m], slot int32[m], own_ids int64[>=m] | None, own_payload dtype[>=m], counts)``;
         only the first ``counts[rank]`` entries of the ``own_*`` tensors are meaningful.  Waits for
-        the stream (the counts are needed on the host)."""
+        the current stream (the counts are needed on the host) and raises ``IndexError`` /
+        ``ValueError`` for a bad batch.  ``out``: the four tensors to write into (capacity >= m)."""
         ids = self._chk(ids.reshape(-1), torch.int64, "ids")
         payload = self._chk(payload.reshape(-1), self.dtype, "payload")
         m = ids.numel()
-        shard = torch.empty(m, dtype=torch.uint8, device=self.device)
-        slot = torch.empty(m, dtype=torch.int32, device=self.device)
-        own_ids = torch.empty(m, dtype=torch.int64, device=self.device) if want_ids else None
-        own_payload = torch.empty(m, dtype=self.dtype, device=self.device)
+        if out is None:
+            out = (torch.empty(m, dtype=torch.uint8, device=self.device),
+                   torch.empty(m, dtype=torch.int32, device=self.device),
+                   torch.empty(m, dtype=torch.int64, device=self.device) if want_ids else None,
+                   torch.empty(m, dtype=self.dtype, device=self.device))
+        shard, slot, own_ids, own_payload = out
+        if min(shard.numel(), slot.numel(), own_payload.numel()) < m or (want_ids and own_ids.numel() < m):
+            raise TypeError("plan buffers are smaller than the batch")
         with torch.cuda.device(self.device):
-            counts = self._h.shard_plan_device(top._h if top is not None else None, ids.data_ptr(), m, shift, shards,
-                                               rank, payload.data_ptr(), payload.numel(), check_negative,
-                                               shard.data_ptr(), slot.data_ptr(),
+            counts = self._h.shard_plan_device(ids.data_ptr(), m, shift, shards, rank, payload.data_ptr(),
+                                               payload.numel(), check_negative, shard.data_ptr(), slot.data_ptr(),
                                                own_ids.data_ptr() if want_ids else 0, own_payload.data_ptr(),
                                                _stream())
-        return shard, slot, own_ids, own_payload, counts
+        return shard[:m], slot[:m], own_ids, own_payload, counts
 
     def shard_expand_values(self, shard: torch.Tensor, slot: torch.Tensor, slabs: torch.Tensor) -> torch.Tensor:
         """``out[j] = slabs[shard[j], slot[j]]`` for 2-D ``slabs`` of the tree's dtype."""

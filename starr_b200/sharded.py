@@ -36,6 +36,15 @@ import torch.distributed as dist
 from . import _hostlogic
 
 
+class UpdatePlan:
+    """Result of ``ShardedSumTree.plan_update``: who owns which element of the batch."""
+    __slots__ = ("ni", "shard", "slot", "own_idx", "own_vals", "counts", "buf")
+
+    def __init__(self, ni, shard, slot, own_idx, own_vals, counts, buf):
+        self.ni, self.shard, self.slot, self.own_idx, self.own_vals = ni, shard, slot, own_idx, own_vals
+        self.counts, self.buf = counts, buf
+
+
 def _default_factory(n, dtype, device):
     from .device_tree import DeviceSumTree
     return DeviceSumTree(n, dtype=dtype, device=device)
@@ -63,6 +72,8 @@ class ShardedSumTree:
         self.top = factory(self.world, dtype, self.device)
         self.offset = self.rank * self.n_local
         self._marks = None     # diagnostics: list of (label, cuda event) while phase_times() runs
+        self._bufs = [None, None, None]
+        self._turn = 0
         if local_leaves is not None:
             self.build_(local_leaves)
 
@@ -132,40 +143,81 @@ class ShardedSumTree:
         the same counts from the replicated batch), rounded up so that slabs stay 256-byte aligned."""
         return max(64, (max(counts) + 63) // 64 * 64)
 
-    def update_(self, idx: torch.Tensor, vals: torch.Tensor, check: bool = False) -> "ShardedSumTree":
-        """Replicated batch: ``idx`` are GLOBAL leaf ids, ``vals`` cycles over the global batch
-        position (reference pyx:44).  Validation is deferred like ``DeviceSumTree.update_`` (a bad
-        batch is skipped on every rank alike; ``poll()`` raises) unless ``check=True``."""
+    def _plan_buffers(self, which: int, m: int):
+        """Persistent plan buffers (grow-only).  Sets 0 and 1 alternate between update plans, so
+        that the plan of batch k+1 can be computed (on a side stream) while batch k is still
+        being applied from the other set; set 2 belongs to ``sample_uniform``."""
+        buf = self._bufs[which]
+        if buf is None or buf["cap"] < m:
+            if buf is not None and self.device.type == "cuda":
+                torch.cuda.synchronize(self.device)        # nobody may still be reading the old set
+            dev = self.device
+            buf = {"cap": m, "free": None,
+                   "out": (torch.empty(m, dtype=torch.uint8, device=dev), torch.empty(m, dtype=torch.int32, device=dev),
+                           torch.empty(m, dtype=torch.int64, device=dev), torch.empty(m, dtype=self.dtype, device=dev))}
+            self._bufs[which] = buf
+        return buf
+
+    def plan_update(self, idx: torch.Tensor, vals: torch.Tensor, stream=None) -> "UpdatePlan":
+        """Owner, slot and compaction of one update batch (it reads nothing of the tree), ahead of
+        ``update_(idx, vals, plan=...)``.  With ``stream`` (a side stream) the plan runs there and
+        overlaps with whatever the current stream is still doing; the caller then guarantees that
+        ``idx`` and ``vals`` are complete on the device (not produced by work still pending on the
+        current stream).  Raises ``IndexError`` / ``ValueError`` for a bad batch -- on every rank
+        alike, before anything is modified -- and ``ZeroDivisionError`` for empty ``vals``."""
         idx = idx.reshape(-1)
         vals = vals.reshape(-1)
         ni, nv = idx.numel(), vals.numel()
-        if check:
-            if nv and bool((vals < 0).any()):
-                raise ValueError("vals must be non-negative")
-            if ni and (int(idx.min()) < 0 or int(idx.max()) >= self.n):
-                raise IndexError("Out of bounds on buffer access (axis 0)")
-        if ni == 0:
-            return self
-        if nv == 0:
+        if ni and nv == 0:
             raise ZeroDivisionError("integer division or modulo by zero")
-        # who owns what: shard and stable slot of EVERY element, this rank's elements compacted
-        shard, slot, own_idx, own_vals, counts = self.local.shard_plan(
-            self.top, idx, self.shift, self.world, self.rank, vals, check_negative=True)
+        if ni == 0:
+            if nv and bool((vals < 0).any()):              # the reference scans vals even then (pyx:37-39)
+                raise ValueError("vals must be non-negative")
+            return UpdatePlan(0, None, None, None, None, None, None)
+        which = self._turn
+        self._turn ^= 1
+        buf = self._plan_buffers(which, ni)
+        on_cuda = self.device.type == "cuda"
+        if on_cuda and stream is not None:
+            if buf["free"] is not None:
+                stream.wait_event(buf["free"])             # the update that read this set has finished
+            with torch.cuda.stream(stream):
+                res = self.local.shard_plan(idx, self.shift, self.world, self.rank, vals, True, out=buf["out"])
+        else:
+            res = self.local.shard_plan(idx, self.shift, self.world, self.rank, vals, True,
+                                        **({"out": buf["out"]} if on_cuda else {}))
+        return UpdatePlan(ni, *res, buf)
+
+    def update_(self, idx: torch.Tensor | None = None, vals: torch.Tensor | None = None, check: bool = False,
+                plan: "UpdatePlan | None" = None) -> "ShardedSumTree":
+        """Replicated batch: ``idx`` are GLOBAL leaf ids, ``vals`` cycles over the global batch
+        position (reference pyx:44).  A bad batch raises at once on every rank (the plan validates
+        the whole batch and synchronises anyway); ``check`` is kept for compatibility."""
+        if plan is None:
+            plan = self.plan_update(idx, vals)
+        if plan.ni == 0:
+            return self
+        shard, slot, own_idx, own_vals, counts = plan.shard, plan.slot, plan.own_idx, plan.own_vals, plan.counts
         self._mark("update: plan (owner, slot, compaction)")
+        dev = shard.device
         c, cap = counts[self.rank], self._slab_capacity(counts)
         # slab of this rank: its differences d_j in batch order, then (last entry) its new shard root
-        mine = torch.empty(cap + 1, dtype=self.dtype, device=idx.device)
+        mine = torch.empty(cap + 1, dtype=self.dtype, device=dev)
         if c:
             self.local.update_with_deltas_(own_idx[:c], own_vals[:c], out=mine[:c])
         mine[cap:].copy_(self.local.heap[1:2])
         self._mark("update: local update")
-        slabs = torch.empty((self.world, cap + 1), dtype=self.dtype, device=idx.device)
+        slabs = torch.empty((self.world, cap + 1), dtype=self.dtype, device=dev)
         dist.all_gather_into_tensor(slabs.view(-1), mine, group=self.group)
         self._mark("update: exchange deltas + roots")
         d_all = self.local.shard_expand_values(shard, slot, slabs)      # batch order again
         self._mark("update: deltas to batch order")
         self._fold_top(shard, d_all)                                    # ordered fold, all ranks alike
         self.top.leaves.copy_(slabs[:, cap])
+        if plan.buf is not None and dev.type == "cuda":
+            ev = torch.cuda.Event()
+            ev.record()
+            plan.buf["free"] = ev
         self._mark("update: top fold")
         return self
 
@@ -203,8 +255,9 @@ class ShardedSumTree:
             return out
         owner, resid = self.top.route_uniform(u)
         self._mark("sample: route")
+        extra = {"out": self._plan_buffers(2, m)["out"]} if self.device.type == "cuda" else {}
         shard, slot, _, own_resid, counts = self.local.shard_plan(
-            None, owner, 0, self.world, self.rank, resid, check_negative=False, want_ids=False)
+            owner, 0, self.world, self.rank, resid, False, want_ids=False, **extra)
         self._mark("sample: plan (slot, compaction)")
         c, cap = counts[self.rank], self._slab_capacity(counts)
         mine = torch.empty(cap, dtype=torch.int32, device=u.device)

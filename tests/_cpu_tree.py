@@ -33,7 +33,7 @@ class CpuTree:
         oracle.c.build_sumtree_from_array(self._np[self.n:], self._np[:self.n])
         return self
 
-    def shard_plan(self, top, ids, shift, shards, rank, payload, check_negative, want_ids=True):
+    def shard_plan(self, ids, shift, shards, rank, payload, check_negative, want_ids=True):
         ids = ids.reshape(-1)
         payload = payload.reshape(-1)
         owner = ids >> shift

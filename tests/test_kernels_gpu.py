@@ -307,7 +307,7 @@ def test_ordered_fold_adversarial(oracle_mod, dt, kind):
 
 @pytest.mark.parametrize("dt", [np.float32, np.int32], ids=["f32", "i32"])
 def test_batches_larger_than_one_chunk(oracle_mod, dt):
-    """Batches above 2^20 updates are applied chunk by chunk; `vals` keeps cycling over the position
+    """Batches above 2^21 updates are applied chunk by chunk (2^20 + 1 is now ONE ragged chunk); `vals` keeps cycling over the position
     in the WHOLE batch (pyx:44), duplicates may straddle chunk boundaries."""
     from starr_b200 import _lib
     C = oracle_mod.c
@@ -318,7 +318,7 @@ def test_batches_larger_than_one_chunk(oracle_mod, dt):
     C.build_sumtree_from_array(leaves, tree)
     h = _lib.TreeHandle(n, dt)
     h.build_from_host(leaves)
-    for m, nv in (((1 << 21) + 12345, 1000003), ((1 << 20) + 1, (1 << 20) + 1), (3 << 20, 7)):
+    for m, nv in (((1 << 21) + 12345, 1000003), ((1 << 20) + 1, (1 << 20) + 1), (5 << 20, 7)):
         idx = rng.integers(0, n, m).astype(np.intp)
         idx[::5] = idx[0]                      # one leaf hit in every chunk
         vals = _draw(rng, nv, dt, "log")

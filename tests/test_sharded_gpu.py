@@ -98,7 +98,7 @@ def test_shard_plan_matches_numpy(shards, rank, m, npay, skew):
     payload = rng.random(npay).astype(np.float32)
     tree = DeviceSumTree(1 << shift, dtype=torch.float32, device=dev)
     shard, slot, own_ids, own_pay, counts = tree.shard_plan(
-        None, torch.from_numpy(ids).to(dev), shift, shards, rank, torch.from_numpy(payload).to(dev), True)
+        torch.from_numpy(ids).to(dev), shift, shards, rank, torch.from_numpy(payload).to(dev), True)
     w_shard, w_slot, w_ids, w_pay, w_counts = _plan_reference(ids, shift, shards, rank, payload)
     assert counts == w_counts
     c = counts[rank]
@@ -117,33 +117,27 @@ def test_shard_plan_matches_numpy(shards, rank, m, npay, skew):
     assert np.array_equal(goti, w_shard.astype(np.int64) * (1 << shift) + islabs.cpu().numpy()[w_shard, w_slot])
 
 
-def test_shard_plan_flags_bad_batches_on_both_trees():
+def test_shard_plan_rejects_bad_batches():
+    """The plan is synchronous, so a bad batch raises at once (the same verdict on every rank,
+    since the batch is replicated) and nothing has been modified yet."""
     from starr_b200 import DeviceSumTree
     dev = torch.device("cuda", 0)
     local = DeviceSumTree(1 << 10, dtype=torch.float32, device=dev)
-    top = DeviceSumTree(4, dtype=torch.float32, device=dev)
     ids = torch.arange(5000, dtype=torch.int64, device=dev) % (4 << 10)
     pay = torch.ones(5000, dtype=torch.float32, device=dev)
-    bad_ids = ids.clone()
-    bad_ids[4321] = 4 << 10
-    local.shard_plan(top, bad_ids, 10, 4, 1, pay, True)
-    for t in (local, top):
+    for bad_value in (4 << 10, -1, 1 << 40):
+        bad_ids = ids.clone()
+        bad_ids[4321] = bad_value
         with pytest.raises(IndexError):
-            t.poll()
-    bad_ids[4321] = -1
-    local.shard_plan(top, bad_ids, 10, 4, 1, pay, True)
-    for t in (local, top):
-        with pytest.raises(IndexError):
-            t.poll()
+            local.shard_plan(bad_ids, 10, 4, 1, pay, True)
     bad_pay = pay.clone()
     bad_pay[77] = -1.0
-    local.shard_plan(top, ids, 10, 4, 1, bad_pay, True)
-    for t in (local, top):
-        with pytest.raises(ValueError):
-            t.poll()
-    local.shard_plan(top, ids, 10, 4, 1, bad_pay, False)      # residuals are not vals: no sign check
-    local.poll()
-    top.poll()
+    with pytest.raises(ValueError):
+        local.shard_plan(ids, 10, 4, 1, bad_pay, True)
+    with pytest.raises(ValueError):                           # unused entries of vals count too (pyx:37-39)
+        local.shard_plan(ids[:10], 10, 4, 1, bad_pay, True)
+    local.shard_plan(ids, 10, 4, 1, bad_pay, False)           # residuals are not vals: no sign check
+    local.poll()                                              # and nothing was flagged on the tree
 
 
 @pytest.mark.parametrize("dt_name", ["float32", "float64"])
@@ -214,8 +208,14 @@ def test_sharded_cuda_path_on_one_gpu(world, dt_name, monkeypatch):
         torch.cuda.set_device(0)
         st = sharded.ShardedSumTree(n, tdt, local_leaves=torch.from_numpy(leaves[r * nl:(r + 1) * nl].copy()).to(dev))
         bad_steps = []
+        side = torch.cuda.Stream()
         for b, (idx, vals, u, tree_after, leaves_after, want) in enumerate(batches):
-            st.update_(torch.from_numpy(idx).to(dev), torch.from_numpy(vals).to(dev))
+            d_idx, d_vals = torch.from_numpy(idx).to(dev), torch.from_numpy(vals).to(dev)
+            if b % 2:                      # plan ahead on a side stream (inputs are complete: .to() above is synchronous)
+                torch.cuda.current_stream().synchronize()
+                st.update_(plan=st.plan_update(d_idx, d_vals, stream=side))
+            else:
+                st.update_(d_idx, d_vals)
             if st.gather_sumtree().cpu().numpy().tobytes() != tree_after.tobytes():
                 bad_steps.append((b, "tree"))
             if st.gather_leaves().cpu().numpy().tobytes() != leaves_after.tobytes():
@@ -223,16 +223,16 @@ def test_sharded_cuda_path_on_one_gpu(world, dt_name, monkeypatch):
             if not np.array_equal(st.sample_uniform(torch.from_numpy(u).to(dev)).cpu().numpy(), want):
                 bad_steps.append((b, "sample"))
         st.poll()
-        # a bad batch is skipped on every rank alike and reported by poll()
+        # a bad batch raises on every rank alike, before anything is modified
         before = st.gather_sumtree().cpu().numpy().tobytes()
         bad = torch.from_numpy(batches[1][0]).to(dev).clone()
         bad[17] = n
-        st.update_(bad, torch.from_numpy(batches[1][1]).to(dev))
         try:
-            st.poll()
+            st.update_(bad, torch.from_numpy(batches[1][1]).to(dev))
             bad_steps.append(("bad batch", "not reported"))
         except IndexError:
             pass
+        st.poll()
         if st.gather_sumtree().cpu().numpy().tobytes() != before:
             bad_steps.append(("bad batch", "tree modified"))
         return bad_steps
