@@ -311,15 +311,20 @@ def run_ours(args):
     tree.poll()
 
     # ---- end-to-end: pinned host buffers in, sampled indices back on the host -------------------
-    pinned = [(torch.from_numpy(i).pin_memory(), torch.from_numpy(v).pin_memory(), torch.from_numpy(u).pin_memory())
-              for i, v, u in batches_host]
-    host_out = torch.empty(m_global, dtype=torch.int64).pin_memory()
+    # Sharded runs feed the batch the way a data-parallel learner would: every rank holds ITS slice of
+    # the batch in pinned host memory, uploads only that (PCIe carries every byte once, not once per
+    # rank), the slices are all-gathered over NVLink, and every rank reads back its slice of the result.
+    mine = slice(rank * m_local, (rank + 1) * m_local) if world > 1 else slice(0, m_global)
+    pinned = [(torch.from_numpy(i[mine]).pin_memory(), torch.from_numpy(v[mine]).pin_memory(),
+               torch.from_numpy(u[mine]).pin_memory()) for i, v, u in batches_host]
+    host_out = torch.empty(mine.stop - mine.start, dtype=torch.int64).pin_memory()
 
     # Software-pipelined like a real PER loop: the H2D copy of step k+1 and the D2H copy of step k-1
     # run on side streams while step k computes; every step's copies are inside the timed region.
     s_main = torch.cuda.current_stream()
     s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
-    dbuf = [tuple(torch.empty_like(t, device=dev) for t in pinned[0]) for _ in range(2)]
+    dbuf = [tuple(torch.empty(m_global, dtype=t.dtype, device=dev) for t in pinned[0]) for _ in range(2)]
+    stage = [tuple(torch.empty_like(t, device=dev) for t in pinned[0]) for _ in range(2)] if world > 1 else dbuf
     obuf = [torch.empty(m_global, dtype=torch.int64, device=dev) for _ in range(2)]
     ev_in = [torch.cuda.Event() for _ in range(2)]
     ev_free = [torch.cuda.Event() for _ in range(2)]     # inputs of the slot consumed
@@ -330,8 +335,11 @@ def run_ours(args):
         slot = k % 2
         with torch.cuda.stream(s_in):
             s_in.wait_event(ev_free[slot])
-            for dst, src in zip(dbuf[slot], pinned[k % N_BATCHES]):
+            for dst, src in zip(stage[slot], pinned[k % N_BATCHES]):
                 dst.copy_(src, non_blocking=True)
+            if world > 1:
+                for full, part in zip(dbuf[slot], stage[slot]):
+                    dist.all_gather_into_tensor(full, part)
             ev_in[slot].record(s_in)
 
     def e2e_run(nsteps):
@@ -362,7 +370,7 @@ def run_ours(args):
             ev_done[slot].record(s_main)
             with torch.cuda.stream(s_out):
                 s_out.wait_event(ev_done[slot])
-                host_out.copy_(obuf[slot], non_blocking=True)
+                host_out.copy_(obuf[slot][mine], non_blocking=True)
                 ev_read[slot].record(s_out)
         s_main.wait_stream(s_out)
 
@@ -417,7 +425,7 @@ def run_ours(args):
         if breakdown and breakdown["calls"]:
             phases = {"partition_levels_kernel": breakdown["partition_ms"], "retire_kernel": breakdown["retire_ms"],
                       "fold_scan_kernel": breakdown["fold_scan_ms"],
-                      "fold_huge_maps_kernel": breakdown["huge_maps_ms"], "fold_huge_apply_kernel": breakdown["huge_apply_ms"],
+                      "fold_huge_maps_kernel": breakdown["huge_maps_ms"],
                       "leaf_pass_kernel": breakdown["leaf_pass_ms"], "search_kernel": smp_ms / steps}
             top = max(phases, key=phases.get)
             if top != "search_kernel":
@@ -437,7 +445,9 @@ def run_ours(args):
             "e2e": {"value": ops_per_step * steps / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": m_global * (8 + 4 + 8), "d2h_bytes_per_step": m_global * 8,
                     "ms_per_step": e2e_ms / steps,
-                    "note": "pinned host buffers; H2D of step k+1 and D2H of step k-1 overlap step k on side streams"},
+                    "note": "pinned host buffers; H2D of step k+1 and D2H of step k-1 overlap step k on side streams"
+                            + ("; every rank uploads / reads back its 1/N slice of the batch (byte counts are "
+                               "totals over ranks), slices are all-gathered over NVLink" if world > 1 else "")},
             "gpu_launches": launches, "clocks": clocks, "update_breakdown_ms": breakdown,
         }
         if world == 1 and not args.no_cpu_baseline:

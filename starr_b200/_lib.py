@@ -348,7 +348,9 @@ class TreeHandle:
     def update_breakdown(self) -> dict:
         out = (ctypes.c_double * 8)()
         check(lib().st_update_breakdown(self.ptr, out))
-        names = ("sort_ms", "leaf_pass_ms", "partition_ms", "retire_ms", "huge_maps_ms", "huge_apply_ms", "fold_scan_ms")
+        # fold_scan_ms: stitch of the huge segments + long + medium folds (one launch);
+        # huge_redo_ms: second pass for huge segments whose node left its binade (usually two empty launches)
+        names = ("sort_ms", "leaf_pass_ms", "partition_ms", "retire_ms", "huge_maps_ms", "fold_scan_ms", "huge_redo_ms")
         calls = max(out[7], 1.0)
         d = {n: out[i] / calls for i, n in enumerate(names)}
         d["calls"] = int(out[7])
@@ -357,5 +359,6 @@ class TreeHandle:
     def update_stats(self, stream: int = 0) -> dict:
         out = (c_int64 * 4)()
         check(lib().st_update_stats(self.ptr, c_void_p(stream), out))
-        return {"fast_segments": out[0], "chain_segments": out[1], "chain_elements": out[2],
-                "longest_chain": out[3]}
+        # huge segments (more than 16384 updates under one node), cumulative since the tree was created
+        return {"huge_segments_maps_only": out[0], "huge_segments_with_exact_chunks": out[1],
+                "chunks_folded_exactly": out[2], "most_exact_chunks_in_one_segment": out[3]}

@@ -40,7 +40,7 @@ struct st_tree {
     // optional per-phase timing of the update pipeline (st_set_profiling)
     int profile = 0;
     cudaEvent_t prof_ev[8] = {};
-    double prof_ms[8] = {};   // sort, leaf pass, partition, huge maps, huge apply, fold scan, (spare), calls
+    double prof_ms[8] = {};   // sort, leaf pass, partition, retire, huge maps, stitch + folds, second pass, calls
 };
 
 // launchers implemented in the .cu files; every one only enqueues on `s`

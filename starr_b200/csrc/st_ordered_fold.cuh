@@ -451,7 +451,7 @@ struct fold_smem_ctl {
 template <typename T, typename SRC>
 __device__ T ordered_fold_cta(T cur, SRC src, int len,
                               typename fp_bits<T>::I (*s_wtot)[2], typename fp_bits<T>::I *s_mviol,
-                              fold_smem_ctl *ctl)
+                              fold_smem_ctl *ctl, T *s_seq /* FOLD_CHUNK elements of shared memory */)
 {
     using I = typename fp_bits<T>::I;
     const int tid = threadIdx.x;
@@ -470,6 +470,10 @@ __device__ T ordered_fold_cta(T cur, SRC src, int len,
         T dreg[FOLD_E];
 #pragma unroll
         for (int k = 0; k < FOLD_E; ++k) dreg[k] = nxt[k];
+        // staged for the sequential runs after a restart (read only behind barriers 1 and 2 below;
+        // the previous chunk's readers are behind the barrier that ended their round)
+#pragma unroll
+        for (int k = 0; k < FOLD_E; ++k) s_seq[tid * FOLD_E + k] = dreg[k];
 #pragma unroll
         for (int k = 0; k < FOLD_E; ++k) {   // prefetch the next chunk
             const int i = base + FOLD_CHUNK + tid * FOLD_E + k;
@@ -477,6 +481,7 @@ __device__ T ordered_fold_cta(T cur, SRC src, int len,
         }
         auto loadc = [&](int p) { return load(base + p); };
         int pos = 0;
+        int nviol = 0;                        // restarts within this chunk
         while (pos < nc) {                    // pos, cur are uniform across the CTA
             int eT;
             I m0;
@@ -522,14 +527,39 @@ __device__ T ordered_fold_cta(T cur, SRC src, int len,
             const int fv = ctl->first_viol;
             if (viol == fv) *s_mviol = m;      // exact m just before update fv
             __syncthreads();
-            cur = t_add<T>(value_of<T>(eT, *s_mviol), loadc(fv));
+            cur = t_add<T>(value_of<T>(eT, *s_mviol), s_seq[fv]);
             int p = fv + 1;
-            const int stop = (p + FOLD_SEQ_RUN < nc) ? p + FOLD_SEQ_RUN : nc;
-            for (; p < stop; ++p) cur = t_add<T>(cur, loadc(p));
+            // A value hovering at a binade boundary violates again and again, and every restart costs
+            // three barriers: the sequential run grows 32, 128, 512, rest, so a chunk restarts at
+            // most four times and its worst case is one plain sequential pass.
+            const int run = FOLD_SEQ_RUN << (nviol < 3 ? 2 * nviol : 6);
+            ++nviol;
+            const int stop = (p + run < nc) ? p + run : nc;
+#pragma unroll 16
+            for (; p < stop; ++p) cur = t_add<T>(cur, s_seq[p]);   // uniform address: a broadcast, no conflicts
             pos = p;
             __syncthreads();                   // everyone has read s_mviol / first_viol
         }
     }
+    return cur;
+}
+
+// Plain sequential fold of one chunk (every thread computes the same result).  For chunks whose
+// summary says "stays representable but touches the binade boundary": a value hovering there
+// defeats the scan (restart after restart), while the dependent-add chain is ~4 cycles per update.
+template <typename T, typename SRC>
+__device__ T sequential_fold_cta(T cur, SRC src, int nc, T *s_seq)
+{
+    const int tid = threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < FOLD_E; ++k) {
+        const int i = tid * FOLD_E + k;
+        s_seq[i] = (i < nc) ? src[i] : T(0);
+    }
+    __syncthreads();
+#pragma unroll 16
+    for (int p = 0; p < nc; ++p) cur = t_add<T>(cur, s_seq[p]);
+    __syncthreads();
     return cur;
 }
 

@@ -47,6 +47,8 @@ struct update_ws {
     seg_entry *queue, *queue_med, *queue_huge;
     int *huge_off;
     void *huge_recs;
+    void *huge_recs2;   // summaries for the binade a segment moved to (second pass)
+    int *huge_redo;     // [2][slots]: first chunk of the second pass (-1: none), exponent of the first pass
     int *seg_sa, *seg_ea, *seg_sb, *seg_eb, *zcount;
     uint32_t *lev_key;
     seg_entry *queue_ret;
@@ -83,6 +85,8 @@ static update_ws carve(const st_tree *t, int64_t B, char *base)
         w.queue_huge = (seg_entry *)take((size_t)(t->depth + 1) * (B / (HUGE_SEG + 1) + 2) * sizeof(seg_entry));
         w.huge_off = (int *)take((size_t)(t->depth + 1) * (B / (HUGE_SEG + 1) + 2) * sizeof(int));
         w.huge_recs = take((size_t)(t->depth + 1) * (B / FOLD_CHUNK + 2) * 64);
+        w.huge_recs2 = take((size_t)(t->depth + 1) * (B / FOLD_CHUNK + 2) * 64);
+        w.huge_redo = (int *)take(2 * (size_t)(t->depth + 1) * (B / (HUGE_SEG + 1) + 2) * sizeof(int));
         w.seg_sa = (int *)take(B * 4);
         w.seg_ea = (int *)take(B * 4);
         w.seg_sb = (int *)take(B * 4);
@@ -149,7 +153,7 @@ __global__ void __launch_bounds__(256) make_keys_kernel(const int64_t *__restric
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j == 0) { status[SW_QCOUNT] = 0; status[SW_QTAKE] = 0; status[SW_QCOUNT_MED] = 0; status[SW_QTAKE_MED] = 0;
                   status[SW_QCOUNT_HUGE] = 0; status[SW_HUGE_CHUNKS] = 0; status[SW_QTAKE_HUGE] = 0;
-                  status[SW_ANYLONG] = 0; status[SW_ANYLONG + 1] = 0; status[SW_QCOUNT_RET] = 0; }
+                  status[SW_ANYLONG] = 0; status[SW_ANYLONG + 1] = 0; status[SW_QCOUNT_RET] = 0; status[SW_REDO_ANY] = 0; }
     if (j >= m) return;
     const uint32_t h = (uint32_t)idx[j] + n;
     const uint32_t key = h << (depth - heap_level(h));
@@ -313,12 +317,34 @@ __device__ __forceinline__ void retire_warps(T *__restrict__ H, uint32_t n, int 
 // Queued segments: exact parallel ordered folds (st_ordered_fold.cuh).  CTAs first drain the
 // queue of long segments (one CTA each), then their warps drain the queue of medium segments
 // (one warp each).
+template <typename T, bool MASKED, bool REDO>
+__device__ void huge_apply_body(T *__restrict__ H, const T *__restrict__ lev_d, int64_t level_stride,
+                                const seg_entry *__restrict__ qhuge, const int *__restrict__ huge_off,
+                                const chunk_rec<typename fp_bits<T>::I> *__restrict__ recs, unsigned int *status,
+                                const void *__restrict__ mleaf, int mleaf_bytes, int64_t mnleaves, int mleaf_level,
+                                const chunk_rec<typename fp_bits<T>::I> *__restrict__ recs2, int *__restrict__ redo,
+                                int redo_stride, T *s_seq);
+
+// first-pass stitch of the huge segments, done by the same launch as the long / medium folds
+template <typename T> struct huge_params {
+    const seg_entry *qhuge;   // nullptr: no huge phase in this launch
+    const int *huge_off;
+    const chunk_rec<typename fp_bits<T>::I> *recs;
+    int *redo;
+    int redo_stride;
+};
+
+// One launch for everything that is left after partition + retirement.  The CTAs first take the huge
+// segments (stitch of the chunk summaries; a node hovering at a binade boundary makes ONE of them
+// slow), and every CTA that finds none left goes straight on to the long and medium queues, so the
+// slow stitch overlaps with the rest instead of holding up a kernel of its own.
 template <typename T>
 __global__ void __launch_bounds__(FOLD_THREADS) fold_scan_kernel(T *__restrict__ H, const T *__restrict__ lev_d,
                                                                  int64_t level_stride,
                                                                  const seg_entry *__restrict__ queue_long,
                                                                  const seg_entry *__restrict__ queue_med,
-                                                                 unsigned int *status, retire_params<T> ret)
+                                                                 unsigned int *status, retire_params<T> ret,
+                                                                 huge_params<T> hp)
 {
     if (status[SW_STATUS]) return;
     using I = typename fp_bits<T>::I;
@@ -326,6 +352,9 @@ __global__ void __launch_bounds__(FOLD_THREADS) fold_scan_kernel(T *__restrict__
     __shared__ I s_mviol;
     __shared__ fold_smem_ctl ctl;
     __shared__ T s_stage[FOLD_THREADS / 32][FOLDW_PAD];
+    if (hp.qhuge)
+        huge_apply_body<T, false, false>(H, lev_d, level_stride, hp.qhuge, hp.huge_off, hp.recs, status, nullptr, 0, 0, 0,
+                                         nullptr, hp.redo, hp.redo_stride, &s_stage[0][0]);
     if (ret.qret) {
         // small-batch path: retire the segments the single-CTA kernel queued (st_update_small.cuh)
         retire_warps<T>(H, ret.n, ret.depth, ret.key0, ret.lev_key, lev_d, level_stride, ret.qret,
@@ -341,7 +370,7 @@ __global__ void __launch_bounds__(FOLD_THREADS) fold_scan_kernel(T *__restrict__
         if (slot >= n_long) break;
         const seg_entry s = queue_long[slot];
         const T *src = lev_d + (int64_t)s.level * level_stride + s.start;
-        const T r = ordered_fold_cta<T>(H[s.node], src, s.len, s_wtot, &s_mviol, &ctl);
+        const T r = ordered_fold_cta<T>(H[s.node], src, s.len, s_wtot, &s_mviol, &ctl, &s_stage[0][0]);
         if (threadIdx.x == 0) H[s.node] = r;
     }
     const unsigned int n_med = status[SW_QCOUNT_MED];
@@ -423,9 +452,12 @@ __global__ void __launch_bounds__(FOLD_THREADS) fold_huge_maps_kernel(const T *_
                                                                       chunk_rec<typename fp_bits<T>::I> *__restrict__ recs,
                                                                       const unsigned int *status,
                                                                       const void *__restrict__ mleaf, int mleaf_bytes, int64_t mnleaves,
-                                                                      int mleaf_level)
+                                                                      int mleaf_level, const int *__restrict__ redo_from)
 {
+    // redo_from != nullptr: second pass -- only the chunks [redo_from[e], ...) of the segments whose
+    // node left the binade its first-pass summaries were made for (H[node] holds the value reached).
     if (status[SW_STATUS]) return;
+    if (redo_from && !status[SW_REDO_ANY]) return;
     using I = typename fp_bits<T>::I;
     __shared__ I s_wtot[FOLD_THREADS / 32][2];
     __shared__ I s_red[FOLD_THREADS / 32][4];
@@ -443,6 +475,7 @@ __global__ void __launch_bounds__(FOLD_THREADS) fold_huge_maps_kernel(const T *_
         const int e = s_entry;
         const seg_entry s = qhuge[e];
         const int c = g - huge_off[e];
+        if (redo_from && (redo_from[e] < 0 || c < redo_from[e])) continue;
         const int nc = s.len - c * FOLD_CHUNK < FOLD_CHUNK ? s.len - c * FOLD_CHUNK : FOLD_CHUNK;
         int eT;
         I m0;
@@ -466,43 +499,71 @@ __global__ void __launch_bounds__(FOLD_THREADS) fold_huge_maps_kernel(const T *_
 // first chunk that fails the check on, the CTA walks sequentially: safe chunks cost a few integer
 // ops, unsafe ones (or any chunk after the exponent changed) are folded exactly.
 // Record of chunk c of this segment: recs[rec_base + c * rec_stride].
-template <typename T, bool MASKED>
-__global__ void __launch_bounds__(FOLD_THREADS) fold_huge_apply_kernel(T *__restrict__ H, const T *__restrict__ lev_d,
-                                                                       int64_t level_stride,
-                                                                       const seg_entry *__restrict__ qhuge,
-                                                                       const int *__restrict__ huge_off,
-                                                                       const chunk_rec<typename fp_bits<T>::I> *__restrict__ recs,
-                                                                       unsigned int *status,
-                                                                       const void *__restrict__ mleaf, int mleaf_bytes, int64_t mnleaves,
-                                                                       int mleaf_level)
+constexpr int REDO_MIN_CHUNKS = 8;   // a second pass pays off only if this many chunks are left
+
+template <typename T, bool MASKED, bool REDO>
+__device__ void huge_apply_body(T *__restrict__ H, const T *__restrict__ lev_d, int64_t level_stride,
+                                const seg_entry *__restrict__ qhuge, const int *__restrict__ huge_off,
+                                const chunk_rec<typename fp_bits<T>::I> *__restrict__ recs, unsigned int *status,
+                                const void *__restrict__ mleaf, int mleaf_bytes, int64_t mnleaves, int mleaf_level,
+                                const chunk_rec<typename fp_bits<T>::I> *__restrict__ recs2, int *__restrict__ redo,
+                                int redo_stride, T *s_seq /* FOLD_CHUNK elements of shared memory */)
 {
+    // First pass (REDO false): stitch with the summaries made for the binade eA the node started in.
+    // When the node leaves that binade with many chunks to go, the segment is handed to the second
+    // pass (redo != nullptr): H[node] keeps the value reached, redo[slot] the next chunk and
+    // redo[redo_stride + slot] = eA.  The second pass (REDO true) has summaries for the binade eB the
+    // node moved to (recs2) next to the old ones (recs), so hopping between the two costs nothing.
     if (status[SW_STATUS]) return;
+    if (REDO && !status[SW_REDO_ANY]) return;
     using I = typename fp_bits<T>::I;
     constexpr I LO = I(1) << fp_bits<T>::MB;
     constexpr I HI = I(1) << (fp_bits<T>::MB + 1);
+    constexpr int STAGE = FOLD_THREADS / 2;
     __shared__ I s_wtot[FOLD_THREADS / 32][2];
     __shared__ I s_mviol;
     __shared__ fold_smem_ctl ctl;
-    __shared__ chunk_rec<I> s_rec[FOLD_THREADS];
+    __shared__ chunk_rec<I> s_rec[REDO ? 2 : 1][STAGE];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned int n_huge = status[SW_QCOUNT_HUGE];
-    for (;;) {
+    for (unsigned int it = 0;; ++it) {
         __syncthreads();
-        if (tid == 0) ctl.slot = atomicAdd(status + SW_QTAKE_HUGE, 1u);
-        __syncthreads();
-        const unsigned int slot = ctl.slot;
+        unsigned int slot;
+        if constexpr (REDO) {
+            slot = blockIdx.x + it * gridDim.x;
+        } else {
+            if (tid == 0) ctl.slot = atomicAdd(status + SW_QTAKE_HUGE, 1u);
+            __syncthreads();
+            slot = ctl.slot;
+        }
         if (slot >= n_huge) break;
+        int c_start = 0;
+        int eA;
+        if constexpr (REDO) {
+            c_start = redo[slot];
+            if (c_start < 0) continue;
+            eA = redo[redo_stride + slot];
+        }
         const seg_entry s = qhuge[slot];
+#ifdef ST_HUGE_DEBUG
+        unsigned long long t_begin;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
+#endif
         const T *src = lev_d + (int64_t)s.level * level_stride + s.start;
         const int64_t rec_base = MASKED ? (int64_t)(s.node - 1) : (int64_t)huge_off[slot];
         const int64_t rec_stride = MASKED ? (int64_t)(mnleaves - 1) : 1;
         const int nchunks = (s.len + FOLD_CHUNK - 1) / FOLD_CHUNK;
         T cur = H[s.node];
-        int eT0;
+        int e_cur, eB = 0;
         I m;
-        bool stale = !scan_ready<T>(cur, eT0, m);   // summaries were made for eT0 (phase A saw the same value)
-        int c_start = 0;
-        if (!stale) {
+        bool ready = scan_ready<T>(cur, e_cur, m);
+        if constexpr (REDO) {
+            eB = ready ? e_cur : eA;   // recs2 were made for the value found in H[node] (same read in pass A')
+        } else {
+            eA = e_cur;                // summaries were made for this exponent (phase A saw the same value)
+            if (redo && tid == 0) redo[slot] = -1;
+        }
+        if (!REDO && ready) {
             // ---- parallel attempt ---------------------------------------------------------------------
             const int per = (nchunks + FOLD_THREADS - 1) / FOLD_THREADS;
             const int lo = tid * per < nchunks ? tid * per : nchunks;
@@ -557,38 +618,98 @@ __global__ void __launch_bounds__(FOLD_THREADS) fold_huge_apply_kernel(T *__rest
             }
         }
         // ---- sequential continuation ---------------------------------------------------------------------
-        for (int cb = c_start; cb < nchunks; cb += FOLD_THREADS) {
+        bool deferred = false;
+        int exact_chunks = 0;   // statistics (st_update_stats)
+        for (int cb = c_start; cb < nchunks && !deferred; cb += STAGE) {
             __syncthreads();
-            if (cb + tid < nchunks) s_rec[tid] = recs[rec_base + (int64_t)(cb + tid) * rec_stride];
+            if (tid < STAGE && cb + tid < nchunks) {
+                s_rec[0][tid] = recs[rec_base + (int64_t)(cb + tid) * rec_stride];
+                if constexpr (REDO) s_rec[REDO ? 1 : 0][tid] = recs2[rec_base + (int64_t)(cb + tid) * rec_stride];
+            }
             __syncthreads();
-            const int lim = nchunks - cb < FOLD_THREADS ? nchunks - cb : FOLD_THREADS;
+            const int lim = nchunks - cb < STAGE ? nchunks - cb : STAGE;
             for (int k = 0; k < lim; ++k) {   // uniform over the CTA
-                if (!stale) {
-                    const chunk_rec<I> r = s_rec[k];
-                    const bool odd = (m & 1) != 0;
-                    const I mn = odd ? r.min1 : r.min0, mx = odd ? r.max1 : r.max0;
-                    if (r.ok && m + mn >= LO && m + mx < HI) {
-                        m += odd ? r.a1 : r.a0;
-                        continue;
+                bool hovering = false;   // small updates, but the chunk touches the binade boundary
+                if (ready) {
+                    const int which = e_cur == eA ? 0 : ((REDO && e_cur == eB) ? 1 : -1);
+                    if (which >= 0) {
+                        const chunk_rec<I> &r = s_rec[REDO ? which : 0][k];
+                        const bool odd = (m & 1) != 0;
+                        const I mn = odd ? r.min1 : r.min0, mx = odd ? r.max1 : r.max0;
+                        if (r.ok && m + mn >= LO && m + mx < HI) {
+                            m += odd ? r.a1 : r.a0;
+                            continue;
+                        }
+                        hovering = r.ok != 0;
                     }
-                    cur = value_of<T>(eT0, m);
+                    cur = value_of<T>(e_cur, m);
                 }
                 const int c = cb + k;
                 const int nc = s.len - c * FOLD_CHUNK < FOLD_CHUNK ? s.len - c * FOLD_CHUNK : FOLD_CHUNK;
                 if constexpr (MASKED) {
                     const masked_src<T> ms{lev_d, mleaf, mleaf_bytes, mnleaves, s.node, mleaf_level - s.level};
-                    cur = ordered_fold_cta<T>(cur, ms + (int64_t)c * FOLD_CHUNK, nc, s_wtot, &s_mviol, &ctl);
+                    cur = hovering ? sequential_fold_cta<T>(cur, ms + (int64_t)c * FOLD_CHUNK, nc, s_seq)
+                                   : ordered_fold_cta<T>(cur, ms + (int64_t)c * FOLD_CHUNK, nc, s_wtot, &s_mviol, &ctl, s_seq);
                 } else {
-                    cur = ordered_fold_cta<T>(cur, src + (int64_t)c * FOLD_CHUNK, nc, s_wtot, &s_mviol, &ctl);
+                    cur = hovering ? sequential_fold_cta<T>(cur, src + (int64_t)c * FOLD_CHUNK, nc, s_seq)
+                                   : ordered_fold_cta<T>(cur, src + (int64_t)c * FOLD_CHUNK, nc, s_wtot, &s_mviol, &ctl, s_seq);
                 }
-                int e2;
-                I m2;
-                stale = !(scan_ready<T>(cur, e2, m2) && e2 == eT0);
-                if (!stale) m = m2;
+                ready = scan_ready<T>(cur, e_cur, m);
+                ++exact_chunks;
+                if constexpr (!REDO) {
+                    if (redo && ready && e_cur != eA && nchunks - (c + 1) >= REDO_MIN_CHUNKS) {
+                        // left the binade with a long way to go: the second pass takes over from chunk c+1
+                        if (tid == 0) {
+                            H[s.node] = cur;
+                            redo[slot] = c + 1;
+                            redo[redo_stride + slot] = eA;
+                            status[SW_REDO_ANY] = 1u;
+                        }
+                        deferred = true;
+                        break;
+                    }
+                }
             }
         }
-        if (tid == 0) H[s.node] = stale ? cur : value_of<T>(eT0, m);
+        if (!deferred && tid == 0) H[s.node] = ready ? value_of<T>(e_cur, m) : cur;
+#ifdef ST_HUGE_DEBUG
+        if (tid == 0 && !REDO && !MASKED) {
+            unsigned long long t_end;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+            const unsigned int ns = (unsigned int)(t_end - t_begin);
+            if (atomicMax(status + 40, ns) < ns) {
+                status[41] = (unsigned int)s.level; status[42] = (unsigned int)s.len; status[43] = (unsigned int)c_start;
+                status[44] = (unsigned int)exact_chunks; status[45] = deferred ? 1u : 0u; status[46] = (unsigned int)s.node;
+            }
+        }
+#endif
+        if (tid == 0) {
+            if (exact_chunks == 0 && !deferred) {
+                if (!REDO) atomicAdd(status + SW_STAT_FAST, 1u);
+            } else {
+                if (!REDO) atomicAdd(status + SW_STAT_CHAINS, 1u);
+                atomicAdd(status + SW_STAT_CHAIN_ELEMS, (unsigned int)exact_chunks);
+                atomicMax(status + SW_STAT_LONGEST, (unsigned int)exact_chunks);
+            }
+        }
     }
+}
+
+template <typename T, bool MASKED, bool REDO>
+__global__ void __launch_bounds__(FOLD_THREADS) fold_huge_apply_kernel(T *__restrict__ H, const T *__restrict__ lev_d,
+                                                                       int64_t level_stride,
+                                                                       const seg_entry *__restrict__ qhuge,
+                                                                       const int *__restrict__ huge_off,
+                                                                       const chunk_rec<typename fp_bits<T>::I> *__restrict__ recs,
+                                                                       unsigned int *status,
+                                                                       const void *__restrict__ mleaf, int mleaf_bytes, int64_t mnleaves,
+                                                                       int mleaf_level,
+                                                                       const chunk_rec<typename fp_bits<T>::I> *__restrict__ recs2,
+                                                                       int *__restrict__ redo, int redo_stride)
+{
+    __shared__ T s_seq[FOLD_CHUNK];
+    huge_apply_body<T, MASKED, REDO>(H, lev_d, level_stride, qhuge, huge_off, recs, status, mleaf, mleaf_bytes, mnleaves,
+                                     mleaf_level, recs2, redo, redo_stride, s_seq);
 }
 
 // Masked variant of phase A for the tiny top tree: records laid out [chunk][node-1] so that a rank's
@@ -674,7 +795,7 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
             }
             retire_params<T> rp{w.queue_ret, w.kj, w.lev_key, depth, n};
             fold_scan_kernel<T><<<t->sm_count, FOLD_THREADS, 0, s>>>(H, (const T *)w.lev_d, B, w.queue, w.queue_med,
-                                                                    status, rp);
+                                                                    status, rp, huge_params<T>{nullptr, nullptr, nullptr, nullptr, 0});
             return cudaGetLastError();
         }
     }
@@ -766,14 +887,22 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
         }
         g_kernel_launches += 3;
         mark(4);
-        fold_huge_maps_kernel<T, false><<<t->sm_count * 8, FOLD_THREADS, 0, s>>>(H, lev, B, w.queue_huge, w.huge_off,
-                                                                                (REC *)w.huge_recs, status, nullptr, 0, 0, 0);
+        fold_huge_maps_kernel<T, false><<<t->sm_count * 8, FOLD_THREADS, 0, s>>>(
+            H, lev, B, w.queue_huge, w.huge_off, (REC *)w.huge_recs, status, nullptr, 0, 0, 0, nullptr);
         mark(5);
-        fold_huge_apply_kernel<T, false><<<t->sm_count, FOLD_THREADS, 0, s>>>(H, lev, B, w.queue_huge, w.huge_off,
-                                                                             (const REC *)w.huge_recs, status, nullptr, 0, 0, 0);
+        // stitch of the huge segments (first pass) + long + medium folds in one launch; segments whose
+        // node left its binade are finished by the second pass (usually two empty launches)
+        const int redo_stride = (int)((t->depth + 1) * (B / (HUGE_SEG + 1) + 2));
+        fold_scan_kernel<T><<<t->sm_count * 8, FOLD_THREADS, 0, s>>>(
+            H, lev, B, w.queue, w.queue_med, status, retire_params<T>{nullptr, nullptr, nullptr, 0, 0},
+            huge_params<T>{w.queue_huge, w.huge_off, (const REC *)w.huge_recs, w.huge_redo, redo_stride});
         mark(6);
-        fold_scan_kernel<T><<<t->sm_count * 8, FOLD_THREADS, 0, s>>>(H, lev, B, w.queue, w.queue_med, status,
-                                                                        retire_params<T>{nullptr, nullptr, nullptr, 0, 0});
+        g_kernel_launches += 1;
+        fold_huge_maps_kernel<T, false><<<t->sm_count * 8, FOLD_THREADS, 0, s>>>(
+            H, lev, B, w.queue_huge, w.huge_off, (REC *)w.huge_recs2, status, nullptr, 0, 0, 0, w.huge_redo);
+        fold_huge_apply_kernel<T, false, true><<<t->sm_count, FOLD_THREADS, 0, s>>>(
+            H, lev, B, w.queue_huge, w.huge_off, (const REC *)w.huge_recs, status, nullptr, 0, 0, 0,
+            (const REC *)w.huge_recs2, w.huge_redo, redo_stride);
         mark(7);
         if (t->profile) {
             // profiling mode is synchronous by design (bench.py's roofline leg only)
@@ -849,13 +978,13 @@ cudaError_t launch_fold_by_leaf_apply(st_tree *t, const void *leaf, int leaf_byt
     g_kernel_launches += 2;
     top_entries_kernel<<<1, 64, 0, s>>>(q, t->d_status, (int)t->n, (int)m);
     if (t->dtype == ST_F32)
-        fold_huge_apply_kernel<float, true><<<(unsigned)(t->n - 1), FOLD_THREADS, 0, s>>>(
+        fold_huge_apply_kernel<float, true, false><<<(unsigned)(t->n - 1), FOLD_THREADS, 0, s>>>(
             (float *)t->heap, (const float *)deltas, 0, q, nullptr, (const chunk_rec<int32_t> *)recs, t->d_status, leaf,
-            leaf_bytes, t->n, t->depth);
+            leaf_bytes, t->n, t->depth, nullptr, nullptr, 0);
     else
-        fold_huge_apply_kernel<double, true><<<(unsigned)(t->n - 1), FOLD_THREADS, 0, s>>>(
+        fold_huge_apply_kernel<double, true, false><<<(unsigned)(t->n - 1), FOLD_THREADS, 0, s>>>(
             (double *)t->heap, (const double *)deltas, 0, q, nullptr, (const chunk_rec<int64_t> *)recs, t->d_status, leaf,
-            leaf_bytes, t->n, t->depth);
+            leaf_bytes, t->n, t->depth, nullptr, nullptr, 0);
     return cudaGetLastError();
 }
 

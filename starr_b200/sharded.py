@@ -201,13 +201,15 @@ class ShardedSumTree:
         self._mark("update: plan (owner, slot, compaction)")
         dev = shard.device
         c, cap = counts[self.rank], self._slab_capacity(counts)
-        # slab of this rank: its differences d_j in batch order, then (last entry) its new shard root
-        mine = torch.empty(cap + 1, dtype=self.dtype, device=dev)
+        # slab of this rank: its differences d_j in batch order, then (entry `cap`) its new shard root;
+        # the slab length stays a multiple of 64 elements so that every rank's part of the all-gather
+        # is 16-byte aligned (an odd length makes NCCL fall back to its slow unaligned protocol)
+        mine = torch.empty(cap + 64, dtype=self.dtype, device=dev)
         if c:
             self.local.update_with_deltas_(own_idx[:c], own_vals[:c], out=mine[:c])
-        mine[cap:].copy_(self.local.heap[1:2])
+        mine[cap:cap + 1].copy_(self.local.heap[1:2])
         self._mark("update: local update")
-        slabs = torch.empty((self.world, cap + 1), dtype=self.dtype, device=dev)
+        slabs = torch.empty((self.world, cap + 64), dtype=self.dtype, device=dev)
         dist.all_gather_into_tensor(slabs.view(-1), mine, group=self.group)
         self._mark("update: exchange deltas + roots")
         d_all = self.local.shard_expand_values(shard, slot, slabs)      # batch order again
