@@ -18,8 +18,17 @@
 //      root; lanes that share an ancestor are merged with a segmented warp scan and one
 //      atomic add per (warp, node) is issued.
 //   3b. float dtypes: top-down, one level at a time, the batch is kept ordered by
-//      (ancestor at that level, j) -- a stable MSD split -- so every node's updates are one
-//      contiguous, batch-ordered segment; segments are folded in order.
+//      (ancestor at that level, j) -- a stable MSD split (st_partition.cuh, one cooperative
+//      launch) -- so every node's updates are one contiguous, batch-ordered segment.  Segments
+//      are classified by length and queued:
+//        retire (<= 512)   finished for the node AND all deeper levels by ordered atomic adds,
+//                          one warp per segment, lane = level (retire_kernel);
+//        medium / long     exact parallel ordered fold by a warp / a CTA (fold_scan_kernel,
+//                          st_ordered_fold.cuh);
+//        huge (> 16384)    chunk summaries on all CTAs (fold_huge_maps_kernel), stitched per
+//                          segment inside the fold_scan_kernel launch; segments whose node leaves
+//                          its binade get a second pass (two launches, usually empty).
+//      Batches of <= 4096 updates run the whole pipeline in one CTA (st_update_small.cuh).
 //
 // Everything is enqueued on one stream; validation failures set the device status word and
 // every later kernel of the batch returns immediately (nothing is written).

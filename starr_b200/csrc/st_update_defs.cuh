@@ -60,26 +60,6 @@ template <typename T> __device__ __forceinline__ void ordered_add(T *ptr, T d)
     atomicAdd(ptr, d);
 }
 
-// A segment of at most SHORT_SEG updates (in batch order) is finished -- "retired" -- for its node
-// at level l AND every deeper level, so it never has to be partitioned again.  The work is spread
-// over the segment's own threads by LEVEL: the thread of the r-th element takes levels
-// l + r, l + r + len, ... and for each of them walks all updates of the segment in batch order,
-// adding each one to its ancestor at that level.  All adds to one node therefore come from one
-// thread in batch order (ordered_add), different levels touch different nodes.
-template <typename T, typename KEYAT, typename DAT>
-__device__ __forceinline__ void retire_segment_part(T *H, int s, int e, int r, int l, int depth, uint64_t two_n,
-                                                    KEYAT keyat, DAT dat)
-{
-    const int len = e - s;
-    for (int l2 = l + r; l2 < depth; l2 += len) {
-        const int sh = depth - l2;
-        for (int x = s; x < e; ++x) {
-            const uint32_t kx = keyat(x);
-            if (l2 < key_leaf_level(kx, two_n, depth)) ordered_add<T>(H + (kx >> sh), dat(x));
-        }
-    }
-}
-
 constexpr int SEG_DONE = 1 << 30;
 
 // small-batch path: the single-CTA kernel queues its retirements for the follow-up kernel
