@@ -20,7 +20,6 @@ FLAGS = [
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
     "--expt-relaxed-constexpr",
     *(["-DST_SMALL_TIMING"] if os.environ.get("ST_SMALL_TIMING") else []),
-    *(["-DST_HUGE_DEBUG"] if os.environ.get("ST_HUGE_DEBUG") else []),
     *([f"-DST_RETIRE_SEG={os.environ['ST_RETIRE_SEG']}"] if os.environ.get("ST_RETIRE_SEG") else []),
     *([f"-DST_HUGE_SEG={os.environ['ST_HUGE_SEG']}"] if os.environ.get("ST_HUGE_SEG") else []),
     *([f"-DST_SMALL_RETIRE_SEG={os.environ['ST_SMALL_RETIRE_SEG']}"] if os.environ.get("ST_SMALL_RETIRE_SEG") else []),

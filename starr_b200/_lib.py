@@ -348,9 +348,9 @@ class TreeHandle:
     def update_breakdown(self) -> dict:
         out = (ctypes.c_double * 8)()
         check(lib().st_update_breakdown(self.ptr, out))
-        # fold_scan_ms: stitch of the huge segments + long + medium folds (one launch);
-        # huge_redo_ms: second pass for huge segments whose node left its binade (usually two empty launches)
-        names = ("sort_ms", "leaf_pass_ms", "partition_ms", "retire_ms", "huge_maps_ms", "fold_scan_ms", "huge_redo_ms")
+        # huge_stitch_ms: first-pass stitch of the huge segments + summaries for the far side of a binade
+        # boundary (usually nothing to do); fold_scan_ms: second-pass stitch + long + medium folds (one launch)
+        names = ("sort_ms", "leaf_pass_ms", "partition_ms", "retire_ms", "huge_maps_ms", "huge_stitch_ms", "fold_scan_ms")
         calls = max(out[7], 1.0)
         d = {n: out[i] / calls for i, n in enumerate(names)}
         d["calls"] = int(out[7])

@@ -753,11 +753,6 @@ int st_update_stats(st_tree *t, void *stream, int64_t out[4])
     CU(cudaMemcpyAsync(t->h_status, t->d_status, 64 * sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     for (int i = 0; i < 4; ++i) out[i] = t->h_status[4 + i];
-#ifdef ST_HUGE_DEBUG
-    fprintf(stderr, "slowest huge segment: %u ns, level %u, len %u, c_start %u, exact chunks %u, deferred %u, node %u\n",
-            t->h_status[40], t->h_status[41], t->h_status[42], t->h_status[43], t->h_status[44], t->h_status[45],
-            t->h_status[46]);
-#endif
     return ST_OK;
 }
 

@@ -57,7 +57,7 @@ struct update_ws {
     int *huge_off;
     void *huge_recs;
     void *huge_recs2;   // summaries for the binade a segment moved to (second pass)
-    int *huge_redo;     // [2][slots]: first chunk of the second pass (-1: none), exponent of the first pass
+    int *huge_redo;     // [3][slots]: first chunk of the second pass (-1: none), binade of the first pass, other binade
     int *seg_sa, *seg_ea, *seg_sb, *seg_eb, *zcount;
     uint32_t *lev_key;
     seg_entry *queue_ret;
@@ -95,7 +95,7 @@ static update_ws carve(const st_tree *t, int64_t B, char *base)
         w.huge_off = (int *)take((size_t)(t->depth + 1) * (B / (HUGE_SEG + 1) + 2) * sizeof(int));
         w.huge_recs = take((size_t)(t->depth + 1) * (B / FOLD_CHUNK + 2) * 64);
         w.huge_recs2 = take((size_t)(t->depth + 1) * (B / FOLD_CHUNK + 2) * 64);
-        w.huge_redo = (int *)take(2 * (size_t)(t->depth + 1) * (B / (HUGE_SEG + 1) + 2) * sizeof(int));
+        w.huge_redo = (int *)take(3 * (size_t)(t->depth + 1) * (B / (HUGE_SEG + 1) + 2) * sizeof(int));
         w.seg_sa = (int *)take(B * 4);
         w.seg_ea = (int *)take(B * 4);
         w.seg_sb = (int *)take(B * 4);
@@ -334,19 +334,19 @@ __device__ void huge_apply_body(T *__restrict__ H, const T *__restrict__ lev_d, 
                                 const chunk_rec<typename fp_bits<T>::I> *__restrict__ recs2, int *__restrict__ redo,
                                 int redo_stride, T *s_seq);
 
-// first-pass stitch of the huge segments, done by the same launch as the long / medium folds
+// second-pass stitch of the huge segments, done by the same launch as the long / medium folds
 template <typename T> struct huge_params {
     const seg_entry *qhuge;   // nullptr: no huge phase in this launch
     const int *huge_off;
-    const chunk_rec<typename fp_bits<T>::I> *recs;
+    const chunk_rec<typename fp_bits<T>::I> *recs, *recs2;
     int *redo;
     int redo_stride;
 };
 
-// One launch for everything that is left after partition + retirement.  The CTAs first take the huge
-// segments (stitch of the chunk summaries; a node hovering at a binade boundary makes ONE of them
-// slow), and every CTA that finds none left goes straight on to the long and medium queues, so the
-// slow stitch overlaps with the rest instead of holding up a kernel of its own.
+// One launch for everything that is left after partition + retirement + the first-pass stitch.  CTA b
+// first finishes huge segment b if the first pass handed it over (its node sits at a binade boundary:
+// exact folds, the slow part), every other CTA goes straight on to the long and medium queues, so
+// the slow stitch overlaps with the rest instead of holding up a kernel of its own.
 template <typename T>
 __global__ void __launch_bounds__(FOLD_THREADS) fold_scan_kernel(T *__restrict__ H, const T *__restrict__ lev_d,
                                                                  int64_t level_stride,
@@ -362,8 +362,8 @@ __global__ void __launch_bounds__(FOLD_THREADS) fold_scan_kernel(T *__restrict__
     __shared__ fold_smem_ctl ctl;
     __shared__ T s_stage[FOLD_THREADS / 32][FOLDW_PAD];
     if (hp.qhuge)
-        huge_apply_body<T, false, false>(H, lev_d, level_stride, hp.qhuge, hp.huge_off, hp.recs, status, nullptr, 0, 0, 0,
-                                         nullptr, hp.redo, hp.redo_stride, &s_stage[0][0]);
+        huge_apply_body<T, false, true>(H, lev_d, level_stride, hp.qhuge, hp.huge_off, hp.recs, status, nullptr, 0, 0, 0,
+                                        hp.recs2, hp.redo, hp.redo_stride, &s_stage[0][0]);
     if (ret.qret) {
         // small-batch path: retire the segments the single-CTA kernel queued (st_update_small.cuh)
         retire_warps<T>(H, ret.n, ret.depth, ret.key0, ret.lev_key, lev_d, level_stride, ret.qret,
@@ -461,7 +461,8 @@ __global__ void __launch_bounds__(FOLD_THREADS) fold_huge_maps_kernel(const T *_
                                                                       chunk_rec<typename fp_bits<T>::I> *__restrict__ recs,
                                                                       const unsigned int *status,
                                                                       const void *__restrict__ mleaf, int mleaf_bytes, int64_t mnleaves,
-                                                                      int mleaf_level, const int *__restrict__ redo_from)
+                                                                      int mleaf_level, const int *__restrict__ redo_from,
+                                                                      int redo_stride)
 {
     // redo_from != nullptr: second pass -- only the chunks [redo_from[e], ...) of the segments whose
     // node left the binade its first-pass summaries were made for (H[node] holds the value reached).
@@ -484,11 +485,15 @@ __global__ void __launch_bounds__(FOLD_THREADS) fold_huge_maps_kernel(const T *_
         const int e = s_entry;
         const seg_entry s = qhuge[e];
         const int c = g - huge_off[e];
-        if (redo_from && (redo_from[e] < 0 || c < redo_from[e])) continue;
+        if (redo_from && (redo_from[e] < 0 || c < redo_from[e] ||
+                          redo_from[redo_stride + e] == redo_from[2 * redo_stride + e]))
+            continue;   // second pass: only chunks from the hand-over on, and only if there is another binade
         const int nc = s.len - c * FOLD_CHUNK < FOLD_CHUNK ? s.len - c * FOLD_CHUNK : FOLD_CHUNK;
         int eT;
         I m0;
-        if (!scan_ready<T>(H[s.node], eT, m0)) {
+        if (redo_from) {
+            eT = redo_from[2 * redo_stride + e];
+        } else if (!scan_ready<T>(H[s.node], eT, m0)) {
             if (threadIdx.x == 0) recs[g].ok = 0;
             continue;
         }
@@ -508,8 +513,6 @@ __global__ void __launch_bounds__(FOLD_THREADS) fold_huge_maps_kernel(const T *_
 // first chunk that fails the check on, the CTA walks sequentially: safe chunks cost a few integer
 // ops, unsafe ones (or any chunk after the exponent changed) are folded exactly.
 // Record of chunk c of this segment: recs[rec_base + c * rec_stride].
-constexpr int REDO_MIN_CHUNKS = 8;   // a second pass pays off only if this many chunks are left
-
 template <typename T, bool MASKED, bool REDO>
 __device__ void huge_apply_body(T *__restrict__ H, const T *__restrict__ lev_d, int64_t level_stride,
                                 const seg_entry *__restrict__ qhuge, const int *__restrict__ huge_off,
@@ -518,11 +521,14 @@ __device__ void huge_apply_body(T *__restrict__ H, const T *__restrict__ lev_d, 
                                 const chunk_rec<typename fp_bits<T>::I> *__restrict__ recs2, int *__restrict__ redo,
                                 int redo_stride, T *s_seq /* FOLD_CHUNK elements of shared memory */)
 {
-    // First pass (REDO false): stitch with the summaries made for the binade eA the node started in.
-    // When the node leaves that binade with many chunks to go, the segment is handed to the second
-    // pass (redo != nullptr): H[node] keeps the value reached, redo[slot] the next chunk and
-    // redo[redo_stride + slot] = eA.  The second pass (REDO true) has summaries for the binade eB the
-    // node moved to (recs2) next to the old ones (recs), so hopping between the two costs nothing.
+    // First pass (REDO false): stitch with the summaries made for the binade eA the node starts in.
+    //   redo == nullptr (the masked top fold): chunks that fail the check are folded exactly in place.
+    //   redo != nullptr: the first chunk c that fails hands the segment to the second pass -- H[node]
+    //   keeps the value in front of chunk c, redo[slot] = c, redo[stride + slot] = eA and
+    //   redo[2 * stride + slot] = eB, the binade on the other side of the boundary the chunk ran into.
+    // Second pass (REDO true, inside the fold_scan_kernel launch so that its exact folds overlap the
+    // long / medium folds): summaries for eB (recs2) next to the old ones (recs); the node may hop
+    // between the two binades for free, chunks that straddle the boundary are folded exactly.
     if (status[SW_STATUS]) return;
     if (REDO && !status[SW_REDO_ANY]) return;
     using I = typename fp_bits<T>::I;
@@ -547,29 +553,24 @@ __device__ void huge_apply_body(T *__restrict__ H, const T *__restrict__ lev_d, 
         }
         if (slot >= n_huge) break;
         int c_start = 0;
-        int eA;
+        int eA = 0, eB = 0;
         if constexpr (REDO) {
             c_start = redo[slot];
             if (c_start < 0) continue;
             eA = redo[redo_stride + slot];
+            eB = redo[2 * redo_stride + slot];
         }
         const seg_entry s = qhuge[slot];
-#ifdef ST_HUGE_DEBUG
-        unsigned long long t_begin;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
-#endif
         const T *src = lev_d + (int64_t)s.level * level_stride + s.start;
         const int64_t rec_base = MASKED ? (int64_t)(s.node - 1) : (int64_t)huge_off[slot];
         const int64_t rec_stride = MASKED ? (int64_t)(mnleaves - 1) : 1;
         const int nchunks = (s.len + FOLD_CHUNK - 1) / FOLD_CHUNK;
         T cur = H[s.node];
-        int e_cur, eB = 0;
+        int e_cur;
         I m;
         bool ready = scan_ready<T>(cur, e_cur, m);
-        if constexpr (REDO) {
-            eB = ready ? e_cur : eA;   // recs2 were made for the value found in H[node] (same read in pass A')
-        } else {
-            eA = e_cur;                // summaries were made for this exponent (phase A saw the same value)
+        if constexpr (!REDO) {
+            eA = ready ? e_cur : 0;    // summaries were made for this exponent (phase A saw the same value)
             if (redo && tid == 0) redo[slot] = -1;
         }
         if (!REDO && ready) {
@@ -639,6 +640,7 @@ __device__ void huge_apply_body(T *__restrict__ H, const T *__restrict__ lev_d, 
             const int lim = nchunks - cb < STAGE ? nchunks - cb : STAGE;
             for (int k = 0; k < lim; ++k) {   // uniform over the CTA
                 bool hovering = false;   // small updates, but the chunk touches the binade boundary
+                int other = eA;          // the binade on the far side of that boundary
                 if (ready) {
                     const int which = e_cur == eA ? 0 : ((REDO && e_cur == eB) ? 1 : -1);
                     if (which >= 0) {
@@ -650,10 +652,25 @@ __device__ void huge_apply_body(T *__restrict__ H, const T *__restrict__ lev_d, 
                             continue;
                         }
                         hovering = r.ok != 0;
+                        if (hovering) other = (m + mn < LO) ? e_cur - 1 : e_cur + 1;
                     }
-                    cur = value_of<T>(e_cur, m);
                 }
                 const int c = cb + k;
+                if constexpr (!REDO) {
+                    if (redo) {
+                        // hand over to the second pass, which has the time to fold exactly
+                        if (tid == 0) {
+                            H[s.node] = ready ? value_of<T>(e_cur, m) : cur;
+                            redo[slot] = c;
+                            redo[redo_stride + slot] = eA;
+                            redo[2 * redo_stride + slot] = other;
+                            status[SW_REDO_ANY] = 1u;
+                        }
+                        deferred = true;
+                        break;
+                    }
+                }
+                if (ready) cur = value_of<T>(e_cur, m);
                 const int nc = s.len - c * FOLD_CHUNK < FOLD_CHUNK ? s.len - c * FOLD_CHUNK : FOLD_CHUNK;
                 if constexpr (MASKED) {
                     const masked_src<T> ms{lev_d, mleaf, mleaf_bytes, mnleaves, s.node, mleaf_level - s.level};
@@ -665,33 +682,9 @@ __device__ void huge_apply_body(T *__restrict__ H, const T *__restrict__ lev_d, 
                 }
                 ready = scan_ready<T>(cur, e_cur, m);
                 ++exact_chunks;
-                if constexpr (!REDO) {
-                    if (redo && ready && e_cur != eA && nchunks - (c + 1) >= REDO_MIN_CHUNKS) {
-                        // left the binade with a long way to go: the second pass takes over from chunk c+1
-                        if (tid == 0) {
-                            H[s.node] = cur;
-                            redo[slot] = c + 1;
-                            redo[redo_stride + slot] = eA;
-                            status[SW_REDO_ANY] = 1u;
-                        }
-                        deferred = true;
-                        break;
-                    }
-                }
             }
         }
         if (!deferred && tid == 0) H[s.node] = ready ? value_of<T>(e_cur, m) : cur;
-#ifdef ST_HUGE_DEBUG
-        if (tid == 0 && !REDO && !MASKED) {
-            unsigned long long t_end;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
-            const unsigned int ns = (unsigned int)(t_end - t_begin);
-            if (atomicMax(status + 40, ns) < ns) {
-                status[41] = (unsigned int)s.level; status[42] = (unsigned int)s.len; status[43] = (unsigned int)c_start;
-                status[44] = (unsigned int)exact_chunks; status[45] = deferred ? 1u : 0u; status[46] = (unsigned int)s.node;
-            }
-        }
-#endif
         if (tid == 0) {
             if (exact_chunks == 0 && !deferred) {
                 if (!REDO) atomicAdd(status + SW_STAT_FAST, 1u);
@@ -804,7 +797,7 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
             }
             retire_params<T> rp{w.queue_ret, w.kj, w.lev_key, depth, n};
             fold_scan_kernel<T><<<t->sm_count, FOLD_THREADS, 0, s>>>(H, (const T *)w.lev_d, B, w.queue, w.queue_med,
-                                                                    status, rp, huge_params<T>{nullptr, nullptr, nullptr, nullptr, 0});
+                                                                    status, rp, huge_params<T>{nullptr, nullptr, nullptr, nullptr, nullptr, 0});
             return cudaGetLastError();
         }
     }
@@ -894,24 +887,25 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
             ++g_kernel_launches;
             retire_kernel<T><<<t->sm_count * 8, 256, 0, s>>>(H, n, depth, w.kj, w.lev_key, lev, B, w.queue_ret, status);
         }
-        g_kernel_launches += 3;
+        g_kernel_launches += 4;
         mark(4);
-        fold_huge_maps_kernel<T, false><<<t->sm_count * 8, FOLD_THREADS, 0, s>>>(
-            H, lev, B, w.queue_huge, w.huge_off, (REC *)w.huge_recs, status, nullptr, 0, 0, 0, nullptr);
-        mark(5);
-        // stitch of the huge segments (first pass) + long + medium folds in one launch; segments whose
-        // node left its binade are finished by the second pass (usually two empty launches)
+        // huge segments: chunk summaries -> first-pass stitch (pure map composition; a segment whose
+        // node runs into a binade boundary is handed over) -> summaries for the far side of that
+        // boundary (usually nothing to do) -> second-pass stitch inside the fold launch
         const int redo_stride = (int)((t->depth + 1) * (B / (HUGE_SEG + 1) + 2));
+        fold_huge_maps_kernel<T, false><<<t->sm_count * 8, FOLD_THREADS, 0, s>>>(
+            H, lev, B, w.queue_huge, w.huge_off, (REC *)w.huge_recs, status, nullptr, 0, 0, 0, nullptr, 0);
+        mark(5);
+        fold_huge_apply_kernel<T, false, false><<<t->sm_count, FOLD_THREADS, 0, s>>>(
+            H, lev, B, w.queue_huge, w.huge_off, (const REC *)w.huge_recs, status, nullptr, 0, 0, 0, nullptr, w.huge_redo,
+            redo_stride);
+        fold_huge_maps_kernel<T, false><<<t->sm_count * 8, FOLD_THREADS, 0, s>>>(
+            H, lev, B, w.queue_huge, w.huge_off, (REC *)w.huge_recs2, status, nullptr, 0, 0, 0, w.huge_redo, redo_stride);
+        mark(6);
         fold_scan_kernel<T><<<t->sm_count * 8, FOLD_THREADS, 0, s>>>(
             H, lev, B, w.queue, w.queue_med, status, retire_params<T>{nullptr, nullptr, nullptr, 0, 0},
-            huge_params<T>{w.queue_huge, w.huge_off, (const REC *)w.huge_recs, w.huge_redo, redo_stride});
-        mark(6);
-        g_kernel_launches += 1;
-        fold_huge_maps_kernel<T, false><<<t->sm_count * 8, FOLD_THREADS, 0, s>>>(
-            H, lev, B, w.queue_huge, w.huge_off, (REC *)w.huge_recs2, status, nullptr, 0, 0, 0, w.huge_redo);
-        fold_huge_apply_kernel<T, false, true><<<t->sm_count, FOLD_THREADS, 0, s>>>(
-            H, lev, B, w.queue_huge, w.huge_off, (const REC *)w.huge_recs, status, nullptr, 0, 0, 0,
-            (const REC *)w.huge_recs2, w.huge_redo, redo_stride);
+            huge_params<T>{w.queue_huge, w.huge_off, (const REC *)w.huge_recs, (const REC *)w.huge_recs2, w.huge_redo,
+                           redo_stride});
         mark(7);
         if (t->profile) {
             // profiling mode is synchronous by design (bench.py's roofline leg only)

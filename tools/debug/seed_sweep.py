@@ -18,7 +18,7 @@ for seed in [0] + list(range(1000, 1008)):
     torch.cuda.synchronize()
     last = tree.handle.update_breakdown()
     st = tree.handle.update_stats()
-    print(f"seed {seed}: huge_maps {last['huge_maps_ms']*1e3:.0f} us stitch+folds {last['fold_scan_ms']*1e3:.0f} us second pass {last['huge_redo_ms']*1e3:.0f} us "
+    print(f"seed {seed}: huge_maps {last['huge_maps_ms']*1e3:.0f} us first stitch {last['huge_stitch_ms']*1e3:.0f} us second stitch + folds {last['fold_scan_ms']*1e3:.0f} us "
           f"(avg over {last['calls']} calls); 72 calls: {st['huge_segments_with_exact_chunks']} of "
           f"{st['huge_segments_with_exact_chunks'] + st['huge_segments_maps_only']} huge segments needed {st['chunks_folded_exactly']} exact chunk folds")
     del tree
