@@ -203,6 +203,39 @@ __global__ void __launch_bounds__(256) leaf_pass_kernel(T *__restrict__ H, uint3
     H[h] = cur;
 }
 
+// Float path: the sort only has to bring the duplicates of one leaf together in batch order, so the
+// low `gb` key bits may be left unsorted (one radix pass less).  A group = the updates of 2^gb
+// neighbouring leaves, batch-ordered; its head thread walks it and keeps every leaf's running value
+// in memory (its own earlier stores are visible to its later loads).  Used when groups are sparse.
+template <typename T>
+__global__ void __launch_bounds__(256) leaf_pass_grouped_kernel(T *H, uint32_t n, const uint32_t *__restrict__ keys,
+                                                                const int *__restrict__ js, int m,
+                                                                const T *__restrict__ vals, uint64_t nv, uint64_t j0,
+                                                                T *__restrict__ dj, int gb, const unsigned int *status)
+{
+    if (status[SW_STATUS]) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const uint32_t grp = keys[i] >> gb;
+    if (i > 0 && (keys[i - 1] >> gb) == grp) return;  // not the head of its group
+    const uint64_t two_n = 2ull * n;
+    int e = i;
+    uint32_t key = keys[i];
+    do {
+        const uint32_t h = key_to_heap(key, two_n);
+        const uint32_t j = (uint32_t)js[e];
+        const uint64_t g = j0 + j;  // position in the whole batch (pyx:44: vals[i % nv])
+        const T v = vals[g < nv ? g : g % nv];
+        const T cur = H[h];
+        const T d = t_sub<T>(v, cur);
+        H[h] = t_add<T>(cur, d);
+        dj[j] = d;
+        ++e;
+        if (e >= m) break;
+        key = keys[e];
+    } while ((key >> gb) == grp);
+}
+
 // -----------------------------------------------------------------------------------------
 // 3a. integer propagation: segmented warp scan over equal ancestors + one atomic per segment
 // -----------------------------------------------------------------------------------------
@@ -808,12 +841,23 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
     cudaError_t e = cudaSuccess;
     const T *d_batch = deltas_in;           // d in batch order
     if (!deltas_in) {
-        e = cub::DeviceRadixSort::SortPairs(w.cub_tmp, cb, w.keys_a, w.keys_b, w.j_a, w.j_b, m, 0, depth + 1, s);
+        // floats only need the duplicates of a leaf adjacent: drop the partial low radix digit when the
+        // groups this creates (2^gb neighbouring leaves) hold less than one update on average
+        int gb = 0;
+        if constexpr (is_float_t<T>::value) {
+            const int rem = (depth + 1) % 8;
+            if (rem && depth + 1 > 8 && ((int64_t)m << rem) <= (int64_t)n) gb = rem;
+        }
+        e = cub::DeviceRadixSort::SortPairs(w.cub_tmp, cb, w.keys_a, w.keys_b, w.j_a, w.j_b, m, gb, depth + 1, s);
         if (e != cudaSuccess) return e;
         mark(1);
         ++g_kernel_launches;
-        leaf_pass_kernel<T><<<g, 256, 0, s>>>(H, n, w.keys_b, w.j_b, m, vals, (uint64_t)nv, (uint64_t)j0,
-                                              (T *)w.dj, (T *)w.ds, status);
+        if (gb)
+            leaf_pass_grouped_kernel<T><<<g, 256, 0, s>>>(H, n, w.keys_b, w.j_b, m, vals, (uint64_t)nv, (uint64_t)j0,
+                                                         (T *)w.dj, gb, status);
+        else
+            leaf_pass_kernel<T><<<g, 256, 0, s>>>(H, n, w.keys_b, w.j_b, m, vals, (uint64_t)nv, (uint64_t)j0,
+                                                  (T *)w.dj, (T *)w.ds, status);
         d_batch = (const T *)w.dj;
         if (delta_out) {
             e = cudaMemcpyAsync(delta_out, w.dj, (size_t)m * sizeof(T), cudaMemcpyDeviceToDevice, s);

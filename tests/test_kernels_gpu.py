@@ -330,6 +330,35 @@ def test_batches_larger_than_one_chunk(oracle_mod, dt):
     h.close()
 
 
+@pytest.mark.parametrize("dt,n", [(np.float32, 1 << 22), (np.float64, 1 << 22), (np.float32, (1 << 22) + 12345),
+                                  (np.float32, 3_000_001)], ids=["f32", "f64", "f32-odd", "f32-3M"])
+def test_sparse_float_batches_sort_fewer_bits(oracle_mod, dt, n):
+    """Sparse float batches leave the low key bits unsorted (one radix pass less): a group then holds
+    the updates of up to 128 neighbouring leaves, interleaved in batch order.  Crowd a few groups with
+    duplicates of several neighbouring leaves; everything else stays sparse."""
+    from starr_b200 import _lib
+    C = oracle_mod.c
+    rng = np.random.default_rng(23)
+    leaves = _draw(rng, n, dt, "log")
+    tree = np.zeros(n, dt)
+    C.build_sumtree_from_array(leaves, tree)
+    h = _lib.TreeHandle(n, dt)
+    h.build_from_host(leaves)
+    for m in (5000, 20_000, 32_768):
+        idx = rng.integers(0, n, m).astype(np.intp)
+        for base in rng.integers(0, n - 256, 6):              # crowded neighbourhoods, duplicates interleaved
+            where = rng.integers(0, m, 300)
+            idx[where] = base + rng.integers(0, 200, 300)
+        idx[rng.integers(0, m, 50)] = n - 1                   # and the last leaf, repeatedly
+        vals = _draw(rng, m // 3, dt, "log")                  # cycling vals
+        C.update_sumtree(idx, vals, leaves, tree)
+        h.update_host(idx, vals)
+        gl, gt = _state(h)
+        assert_bits_equal(gl, leaves, f"leaves n={n} m={m}")
+        assert_bits_equal(gt, tree, f"tree n={n} m={m}")
+    h.close()
+
+
 def test_non_power_of_two_large(oracle_mod):
     """A large non-power-of-two tree (leaves at two depths, rotated order) through the big-batch path."""
     from starr_b200 import _lib
