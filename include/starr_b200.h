@@ -141,21 +141,32 @@ ST_API int st_top_fold_maps_device(st_tree *t, const void *leaf_dev, int leaf_it
                             int64_t m, int64_t chunk_lo, int64_t chunk_hi, void *recs_dev, void *stream);
 ST_API int st_top_fold_apply_device(st_tree *t, const void *leaf_dev, int leaf_itemsize, const void *deltas_dev,
                              int64_t m, const void *recs_dev, void *stream);
-/* Plan of one replicated batch of the sharded tree.  Element j belongs to shard ids[j] >> shift.
- * Synchronous (waits for `stream`, because the per-shard counts are needed on the host), and
- * reads nothing of the tree, so it may run on a side stream ahead of the batch it plans.  Writes
+/* Plan of one replicated batch of the sharded tree (m > 0).  Element j belongs to shard
+ * ids[j] >> shift.  Reads nothing of the tree, so it may run on a side stream ahead of the batch it
+ * plans.  Writes
  *   shard_out[j]   the owning shard (255 for an id outside [0, shards << shift)),
  *   slot_out[j]    the stable position of j among the elements of its shard (-1 if invalid),
  *   own_ids_out[k], own_payload_out[k]   (both nullable) for the k-th element of shard `rank`:
  *                  ids[j] - (rank << shift) and payload[j % npayload] (tree dtype),
- *   counts_out_host[s]   the number of elements of every shard (shards <= 64).
- * Returns ST_ERR_INDEX for an id outside every shard and, with check_negative, ST_ERR_NEGATIVE_VALS
- * for a negative entry anywhere in payload (pyx:37-39) -- the same verdict on every rank, before
- * anything was modified.  shard_out must be 8-byte and slot_out 16-byte aligned (vector stores). */
+ * and, into result slot `result_slot` (0..3; a slot is overwritten by the next plan that names it),
+ * the number of elements of every shard (shards <= 64).
+ * counts_out_host != NULL: synchronous -- waits for the plan, fills counts_out_host[shards] and
+ * returns ST_ERR_INDEX for an id outside every shard or, with check_negative, ST_ERR_NEGATIVE_VALS for
+ * a negative entry anywhere in payload (pyx:37-39): the same verdict on every rank, before anything
+ * was modified.  counts_out_host == NULL: only enqueues; st_shard_plan_wait() collects the same result
+ * later and waits for the plan's kernels only, so work that needs nothing but the DEVICE-side counts
+ * (st_shard_plan_counts_device, st_search_counted_device) can be enqueued in between.
+ * shard_out must be 8-byte and slot_out 16-byte aligned (vector stores). */
 ST_API int st_shard_plan_device(st_tree *t, const int64_t *ids_dev, int64_t m, int shift, int shards, int rank,
                          const void *payload_dev, int64_t npayload, int check_negative, uint8_t *shard_out_dev,
-                         int32_t *slot_out_dev, int64_t *own_ids_out_dev, void *own_payload_out_dev,
+                         int32_t *slot_out_dev, int64_t *own_ids_out_dev, void *own_payload_out_dev, int result_slot,
                          int64_t *counts_out_host, void *stream);
+ST_API int st_shard_plan_wait(st_tree *t, int result_slot, int shards, int64_t *counts_out_host);
+/* device address of result slot `result_slot`: uint32 counts[shards] (valid in stream order behind the plan) */
+ST_API const uint32_t *st_shard_plan_counts_device(const st_tree *t, int result_slot);
+/* st_search_device over min(m_max, *m_dev) queries: the count is read on the device at launch time */
+ST_API int st_search_counted_device(const st_tree *t, const void *vals_dev, int64_t m_max, const uint32_t *m_dev,
+                             int64_t *out_dev, void *stream);
 /* Per-shard results come back as slabs (shard s at slabs[s * slab_stride ...], compact, in the
  * shard's batch order); these put them back into batch order:
  *   values:  out[j] = slabs[shard[j] * slab_stride + slot[j]]               (tree dtype)

@@ -86,7 +86,10 @@ _SIGNATURES = {
     "st_top_fold_maps_device": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
     "st_top_fold_apply_device": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_void_p]),
     "st_shard_plan_device": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_int64, c_int,
-                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                     c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "st_shard_plan_wait": (c_int, [c_void_p, c_int, c_int, c_void_p]),
+    "st_shard_plan_counts_device": (c_void_p, [c_void_p, c_int]),
+    "st_search_counted_device": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "st_shard_expand_values_device": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
     "st_shard_expand_indices_device": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p,
                                                c_void_p]),
@@ -290,13 +293,27 @@ class TreeHandle:
 
     def shard_plan_device(self, ids_ptr: int, m: int, shift: int, shards: int, rank: int, payload_ptr: int,
                           npayload: int, check_negative: bool, shard_out_ptr: int, slot_out_ptr: int,
-                          own_ids_out_ptr: int, own_payload_out_ptr: int, stream: int = 0) -> list[int]:
-        counts = (c_int64 * int(shards))()
+                          own_ids_out_ptr: int, own_payload_out_ptr: int, result_slot: int = 0,
+                          stream: int = 0, wait: bool = True) -> list[int] | None:
+        """wait=False only enqueues; collect the counts with shard_plan_wait(result_slot, shards)."""
+        counts = (c_int64 * int(shards))() if wait else None
         check(lib().st_shard_plan_device(self.ptr, c_void_p(ids_ptr), int(m), int(shift), int(shards), int(rank),
                                          c_void_p(payload_ptr), int(npayload), int(bool(check_negative)),
                                          c_void_p(shard_out_ptr), c_void_p(slot_out_ptr), c_void_p(own_ids_out_ptr),
-                                         c_void_p(own_payload_out_ptr), counts, c_void_p(stream)))
+                                         c_void_p(own_payload_out_ptr), int(result_slot), counts, c_void_p(stream)))
+        return list(counts) if wait else None
+
+    def shard_plan_wait(self, result_slot: int, shards: int) -> list[int]:
+        counts = (c_int64 * int(shards))()
+        check(lib().st_shard_plan_wait(self.ptr, int(result_slot), int(shards), counts))
         return list(counts)
+
+    def shard_plan_counts_ptr(self, result_slot: int) -> int:
+        return int(lib().st_shard_plan_counts_device(self.ptr, int(result_slot)) or 0)
+
+    def search_counted_device(self, vals_ptr: int, m_max: int, m_dev_ptr: int, out_ptr: int, stream: int = 0) -> None:
+        check(lib().st_search_counted_device(self.ptr, c_void_p(vals_ptr), int(m_max), c_void_p(m_dev_ptr),
+                                             c_void_p(out_ptr), c_void_p(stream)))
 
     def shard_expand_values_device(self, shard_ptr: int, slot_ptr: int, m: int, slabs_ptr: int, slab_stride: int,
                                    out_ptr: int, stream: int = 0) -> None:

@@ -29,6 +29,8 @@ int cuda_fail(cudaError_t e, const char *where)
     } while (0)
 
 const int kSizes[9] = {2, 4, 8, 1, 2, 4, 8, 4, 8};
+constexpr int kPlanSlots = 4;            // result slots of st_shard_plan_device behind the pinned staging area
+constexpr size_t kPlanSlotBytes = 1024;  // 64 per-shard counts + one flags word
 
 int status_from_flags(unsigned int f)
 {
@@ -173,8 +175,9 @@ int st_create(int64_t n, int dtype, int device, void *external_heap, st_tree **o
     if (e == cudaSuccess) e = cudaMallocHost((void **)&t->h_status, 64 * sizeof(unsigned int));
     if (e == cudaSuccess) {
         t->pin_bytes = 64 * 1024;
-        e = cudaHostAlloc(&t->h_pin, t->pin_bytes, cudaHostAllocMapped);
+        e = cudaHostAlloc(&t->h_pin, t->pin_bytes + kPlanSlots * kPlanSlotBytes, cudaHostAllocMapped);
         if (e == cudaSuccess) e = cudaHostGetDevicePointer(&t->d_pin, t->h_pin, 0);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t->plan_ev, cudaEventDisableTiming);
     }
     if (e == cudaSuccess) e = cudaMemset(t->d_status, 0, 64 * sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMemset(t->heap, 0, heap_bytes);
@@ -195,6 +198,7 @@ int st_destroy(st_tree *t)
     if (t->d_status) cudaFree(t->d_status);
     if (t->h_status) cudaFreeHost(t->h_status);
     if (t->h_pin) cudaFreeHost(t->h_pin);
+    if (t->plan_ev) cudaEventDestroy(t->plan_ev);
     if (t->ws.base) cudaFree(t->ws.base);
     if (t->scratch.base) cudaFree(t->scratch.base);
     for (int k = 0; k < 8; ++k)
@@ -387,33 +391,72 @@ int st_top_fold_apply_device(st_tree *t, const void *leaf_dev, int leaf_itemsize
     return ST_OK;
 }
 
+namespace {
+int plan_result(st_tree *t, int slot, int shards, int64_t *counts_out_host)
+{
+    const unsigned int *pin = (const unsigned int *)((const char *)t->h_pin + t->pin_bytes + slot * kPlanSlotBytes);
+    for (int i = 0; i < shards; ++i) counts_out_host[i] = (int64_t)pin[i];
+    const int status = status_from_flags(pin[shards]);
+    return status == ST_OK ? ST_OK : fail(status, "%s", st_status_string(status));
+}
+}  // namespace
+
 int st_shard_plan_device(st_tree *t, const int64_t *ids_dev, int64_t m, int shift, int shards, int rank,
                          const void *payload_dev, int64_t npayload, int check_negative, uint8_t *shard_out_dev,
-                         int32_t *slot_out_dev, int64_t *own_ids_out_dev, void *own_payload_out_dev,
+                         int32_t *slot_out_dev, int64_t *own_ids_out_dev, void *own_payload_out_dev, int result_slot,
                          int64_t *counts_out_host, void *stream)
 {
-    if (!t || m < 0 || shards < 1 || shards > 64 || rank < 0 || rank >= shards || shift < 0 || shift > 62 ||
-        !counts_out_host || (m > 0 && (!ids_dev || !shard_out_dev || !slot_out_dev)) ||
+    if (!t || m <= 0 || shards < 1 || shards > 64 || rank < 0 || rank >= shards || shift < 0 || shift > 62 ||
+        result_slot < 0 || result_slot >= kPlanSlots || !ids_dev || !shard_out_dev || !slot_out_dev ||
         ((own_payload_out_dev || check_negative) && (!payload_dev || npayload <= 0)))
         return fail(ST_ERR_ARG, "st_shard_plan_device: bad argument");
     if (((uintptr_t)shard_out_dev & 7) || ((uintptr_t)slot_out_dev & 15))
         return fail(ST_ERR_ARG, "st_shard_plan_device: shard_out must be 8-byte and slot_out 16-byte aligned");
-    for (int i = 0; i < shards; ++i) counts_out_host[i] = 0;
-    if (m == 0) return ST_OK;
     device_guard g(t->device);
+    if (t->plan_pending) {   // the scratch area belongs to one plan at a time
+        CU(cudaEventSynchronize(t->plan_ev));
+        t->plan_pending = 0;
+    }
     scratch_carver c(t);
     const size_t bytes = st::shard_plan_scratch_bytes(m, shards);
     c.add(bytes);
     CU(c.commit());
     void *scratch = c.take(bytes);
-    const unsigned int *counts_pin = (const unsigned int *)t->h_pin;
+    unsigned int *counts_dev = (unsigned int *)((char *)t->d_pin + t->pin_bytes + result_slot * kPlanSlotBytes);
     CU(st::launch_shard_plan(t, ids_dev, m, shift, shards, rank, payload_dev, npayload, check_negative, shard_out_dev,
-                             slot_out_dev, own_ids_out_dev, own_payload_out_dev, scratch, (unsigned int *)t->d_pin,
+                             slot_out_dev, own_ids_out_dev, own_payload_out_dev, scratch, counts_dev,
                              (cudaStream_t)stream));
-    CU(cudaStreamSynchronize((cudaStream_t)stream));
-    for (int i = 0; i < shards; ++i) counts_out_host[i] = (int64_t)counts_pin[i];
-    const int status = status_from_flags(counts_pin[shards]);
-    return status == ST_OK ? ST_OK : fail(status, "%s", st_status_string(status));
+    CU(cudaEventRecord(t->plan_ev, (cudaStream_t)stream));
+    t->plan_pending = 1;
+    if (!counts_out_host) return ST_OK;   // asynchronous: st_shard_plan_wait collects the result
+    return st_shard_plan_wait(t, result_slot, shards, counts_out_host);
+}
+
+int st_shard_plan_wait(st_tree *t, int result_slot, int shards, int64_t *counts_out_host)
+{
+    if (!t || !counts_out_host || shards < 1 || shards > 64 || result_slot < 0 || result_slot >= kPlanSlots)
+        return fail(ST_ERR_ARG, "st_shard_plan_wait: bad argument");
+    device_guard g(t->device);
+    if (t->plan_pending) {
+        CU(cudaEventSynchronize(t->plan_ev));   // the plan's kernels only, not what was enqueued behind them
+        t->plan_pending = 0;
+    }
+    return plan_result(t, result_slot, shards, counts_out_host);
+}
+
+const uint32_t *st_shard_plan_counts_device(const st_tree *t, int result_slot)
+{
+    if (!t || result_slot < 0 || result_slot >= kPlanSlots) return nullptr;
+    return (const uint32_t *)((const char *)t->d_pin + t->pin_bytes + result_slot * kPlanSlotBytes);
+}
+
+int st_search_counted_device(const st_tree *t, const void *vals_dev, int64_t m_max, const uint32_t *m_dev,
+                             int64_t *out_dev, void *stream)
+{
+    if (!t || m_max < 0 || !m_dev) return fail(ST_ERR_ARG, "st_search_counted_device: bad argument");
+    device_guard g(t->device);
+    CU(st::launch_search(t, vals_dev, m_max, out_dev, (cudaStream_t)stream, m_dev));
+    return ST_OK;
 }
 
 int st_shard_expand_values_device(const st_tree *t, const uint8_t *shard_dev, const int32_t *slot_dev, int64_t m,

@@ -32,6 +32,10 @@ struct st_tree {
     void *h_pin = nullptr;   // host address
     void *d_pin = nullptr;   // device alias of the same memory
     size_t pin_bytes = 0;   // grow-only staging area of the *_host entry points (no malloc/free per call)
+    // sharded plans: 4 result slots (per-shard counts + flags, 1 KiB each) behind the staging area,
+    // and the event that marks the end of the latest plan's kernels
+    cudaEvent_t plan_ev = nullptr;
+    int plan_pending = 0;
     int64_t reserved_batch = 0;
     int64_t cub_cap = -1;      // batch capacity for which cub_bytes was queried
     size_t cub_bytes = 0;
@@ -51,7 +55,9 @@ extern unsigned long long g_kernel_launches;
 
 cudaError_t launch_check_leaves(st_tree *t, cudaStream_t s);  // sets STF_NEG_ARRAY
 cudaError_t launch_build(st_tree *t, cudaStream_t s);         // skipped on device if status != 0
-cudaError_t launch_search(const st_tree *t, const void *vals, int64_t m, int64_t *out, cudaStream_t s);
+// m_dev (nullable): device-side query count, the launch covers min(m, *m_dev) queries
+cudaError_t launch_search(const st_tree *t, const void *vals, int64_t m, int64_t *out, cudaStream_t s,
+                          const unsigned int *m_dev = nullptr);
 cudaError_t launch_sample(const st_tree *t, const double *u, int64_t m, int64_t *out, void *prio,
                           void *resid, cudaStream_t s);
 cudaError_t launch_publish(const st_tree *t, void *dst_status, void *dst_root, cudaStream_t s);  // tiny: status word + root

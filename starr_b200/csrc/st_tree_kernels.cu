@@ -235,8 +235,12 @@ template <typename T, bool STAGE, bool UNIFORM, int SEARCH_THREADS, int SEARCH_Q
 __global__ void __launch_bounds__(SEARCH_THREADS)
 search_kernel(const T *__restrict__ H, uint32_t n, int depth, const void *__restrict__ in,
               int64_t m, int64_t *__restrict__ out, T *__restrict__ prio, T *__restrict__ resid,
-              uint32_t stage_nodes)
+              uint32_t stage_nodes, const unsigned int *__restrict__ m_dev)
 {
+    if (m_dev) {   // the host did not know the count when it launched (sharded sample: st_shard_plan_device)
+        const int64_t md = (int64_t)*m_dev;
+        if (md < m) m = md;
+    }
     extern __shared__ __align__(128) unsigned char smem_raw[];
     T *top = reinterpret_cast<T *>(smem_raw);
     __shared__ __align__(8) uint64_t bar;
@@ -299,7 +303,7 @@ search_kernel(const T *__restrict__ H, uint32_t n, int depth, const void *__rest
 
 template <typename T, bool UNIFORM, int THREADS, int Q>
 static cudaError_t launch_search_cfg(const st_tree *t, const void *in, int64_t m, int64_t *out, void *prio,
-                                     void *resid, cudaStream_t s)
+                                     void *resid, cudaStream_t s, const unsigned int *m_dev)
 {
     const uint32_t n = (uint32_t)t->n;
     const T *H = (const T *)t->heap;
@@ -324,29 +328,30 @@ static cudaError_t launch_search_cfg(const st_tree *t, const void *in, int64_t m
         }
         unsigned g = grid_for(m, (int)per_block, (int64_t)t->sm_count * 3);
         ++g_kernel_launches;
-        kern<<<g, THREADS, smem, s>>>(H, n, t->depth, in, m, out, (T *)prio, (T *)resid, stage_nodes);
+        kern<<<g, THREADS, smem, s>>>(H, n, t->depth, in, m, out, (T *)prio, (T *)resid, stage_nodes, m_dev);
     } else {
         unsigned g = grid_for(m, (int)per_block, (int64_t)t->sm_count * 4);
         ++g_kernel_launches;
         search_kernel<T, false, UNIFORM, THREADS, Q><<<g, THREADS, 0, s>>>(H, n, t->depth, in, m, out, (T *)prio,
-                                                                          (T *)resid, 0);
+                                                                          (T *)resid, 0, m_dev);
     }
     return cudaGetLastError();
 }
 
 template <typename T, bool UNIFORM>
 static cudaError_t launch_search_t(const st_tree *t, const void *in, int64_t m, int64_t *out, void *prio,
-                                   void *resid, cudaStream_t s)
+                                   void *resid, cudaStream_t s, const unsigned int *m_dev = nullptr)
 {
     if (m <= 0) return cudaSuccess;
     if (m >= (int64_t)t->sm_count * SEARCH_THREADS_BIG * SEARCH_Q_BIG / 4)
-        return launch_search_cfg<T, UNIFORM, SEARCH_THREADS_BIG, SEARCH_Q_BIG>(t, in, m, out, prio, resid, s);
-    return launch_search_cfg<T, UNIFORM, SEARCH_THREADS_SMALL, SEARCH_Q_SMALL>(t, in, m, out, prio, resid, s);
+        return launch_search_cfg<T, UNIFORM, SEARCH_THREADS_BIG, SEARCH_Q_BIG>(t, in, m, out, prio, resid, s, m_dev);
+    return launch_search_cfg<T, UNIFORM, SEARCH_THREADS_SMALL, SEARCH_Q_SMALL>(t, in, m, out, prio, resid, s, m_dev);
 }
 
-cudaError_t launch_search(const st_tree *t, const void *vals, int64_t m, int64_t *out, cudaStream_t s)
+cudaError_t launch_search(const st_tree *t, const void *vals, int64_t m, int64_t *out, cudaStream_t s,
+                          const unsigned int *m_dev)
 {
-    ST_DISPATCH(t->dtype, return (launch_search_t<T, false>(t, vals, m, out, nullptr, nullptr, s)));
+    ST_DISPATCH(t->dtype, return (launch_search_t<T, false>(t, vals, m, out, nullptr, nullptr, s, m_dev)));
     return cudaSuccess;
 }
 

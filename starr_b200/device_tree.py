@@ -172,12 +172,14 @@ class DeviceSumTree:
                                           recs.data_ptr(), _stream())
 
     def shard_plan(self, ids: torch.Tensor, shift: int, shards: int, rank: int, payload: torch.Tensor,
-                   check_negative: bool, want_ids: bool = True, out=None):
+                   check_negative: bool, want_ids: bool = True, out=None, result_slot: int = 0, wait: bool = True):
         """Plan of one replicated batch of a sharded tree (``st_shard_plan_device``): returns
         ``(shard uint8[m], slot int32[m], own_ids int64[>=m] | None, own_payload dtype[>=m], counts)``;
         only the first ``counts[rank]`` entries of the ``own_*`` tensors are meaningful.  Waits for
-        the current stream (the counts are needed on the host) and raises ``IndexError`` /
-        ``ValueError`` for a bad batch.  ``out``: the four tensors to write into (capacity >= m)."""
+        the current stream's plan kernels (the counts are needed on the host) and raises
+        ``IndexError`` / ``ValueError`` for a bad batch.  ``out``: the four tensors to write into
+        (capacity >= m).  ``wait=False`` only enqueues (``counts`` is None): collect the counts with
+        ``shard_plan_wait`` after enqueuing whatever needs only the device-side counts."""
         ids = self._chk(ids.reshape(-1), torch.int64, "ids")
         payload = self._chk(payload.reshape(-1), self.dtype, "payload")
         m = ids.numel()
@@ -193,8 +195,23 @@ class DeviceSumTree:
             counts = self._h.shard_plan_device(ids.data_ptr(), m, shift, shards, rank, payload.data_ptr(),
                                                payload.numel(), check_negative, shard.data_ptr(), slot.data_ptr(),
                                                own_ids.data_ptr() if want_ids else 0, own_payload.data_ptr(),
-                                               _stream())
+                                               result_slot, _stream(), wait)
         return shard[:m], slot[:m], own_ids, own_payload, counts
+
+    def shard_plan_wait(self, result_slot: int, shards: int) -> list:
+        with torch.cuda.device(self.device):
+            return self._h.shard_plan_wait(result_slot, shards)
+
+    def search_counted(self, prefix_sums: torch.Tensor, result_slot: int, which: int, out: torch.Tensor) -> None:
+        """``search`` over the first ``counts[which]`` entries of ``prefix_sums``, the count being read
+        on the device from plan result slot ``result_slot`` (the host need not know it yet)."""
+        vals = self._chk(prefix_sums, self.dtype, "prefix_sums")
+        if self._chk(out, torch.int64, "out") is not out or out.numel() < vals.numel():
+            raise TypeError("out must be a contiguous int64 tensor at least as long as prefix_sums")
+        with torch.cuda.device(self.device):
+            self._h.search_counted_device(vals.data_ptr(), vals.numel(),
+                                          self._h.shard_plan_counts_ptr(result_slot) + 4 * which, out.data_ptr(),
+                                          _stream())
 
     def shard_expand_values(self, shard: torch.Tensor, slot: torch.Tensor, slabs: torch.Tensor) -> torch.Tensor:
         """``out[j] = slabs[shard[j], slot[j]]`` for 2-D ``slabs`` of the tree's dtype."""

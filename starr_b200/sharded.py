@@ -182,10 +182,11 @@ class ShardedSumTree:
             if buf["free"] is not None:
                 stream.wait_event(buf["free"])             # the update that read this set has finished
             with torch.cuda.stream(stream):
-                res = self.local.shard_plan(idx, self.shift, self.world, self.rank, vals, True, out=buf["out"])
+                res = self.local.shard_plan(idx, self.shift, self.world, self.rank, vals, True, out=buf["out"],
+                                            result_slot=which)
         else:
             res = self.local.shard_plan(idx, self.shift, self.world, self.rank, vals, True,
-                                        **({"out": buf["out"]} if on_cuda else {}))
+                                        **({"out": buf["out"], "result_slot": which} if on_cuda else {}))
         return UpdatePlan(ni, *res, buf)
 
     def update_(self, idx: torch.Tensor | None = None, vals: torch.Tensor | None = None, check: bool = False,
@@ -257,15 +258,28 @@ class ShardedSumTree:
             return out
         owner, resid = self.top.route_uniform(u)
         self._mark("sample: route")
-        extra = {"out": self._plan_buffers(2, m)["out"]} if self.device.type == "cuda" else {}
-        shard, slot, _, own_resid, counts = self.local.shard_plan(
-            owner, 0, self.world, self.rank, resid, False, want_ids=False, **extra)
-        self._mark("sample: plan (slot, compaction)")
-        c, cap = counts[self.rank], self._slab_capacity(counts)
-        mine = torch.empty(cap, dtype=torch.int32, device=u.device)
-        if c:
-            mine[:c].copy_(self.local.search(own_resid[:c]))             # local leaf ids fit 31 bits
-        self._mark("sample: local search")
+        if hasattr(self.local, "search_counted"):
+            # CUDA tree: enqueue the plan, then the local search with the count read on the device, and
+            # only then wait for the plan's counts -- the host round trip hides behind the search
+            bufs = self._plan_buffers(2, m)["out"]
+            shard, slot, _, own_resid, _ = self.local.shard_plan(
+                owner, 0, self.world, self.rank, resid, False, want_ids=False, out=bufs, result_slot=2, wait=False)
+            found = bufs[2]                                              # int64[m], unused by this plan
+            self.local.search_counted(own_resid, 2, self.rank, found)
+            counts = self.local.shard_plan_wait(2, self.world)
+            self._mark("sample: plan + local search")
+            c, cap = counts[self.rank], self._slab_capacity(counts)
+            mine = torch.empty(cap, dtype=torch.int32, device=u.device)
+            if c:
+                mine[:c].copy_(found[:c])                                # local leaf ids fit 31 bits
+        else:
+            shard, slot, _, own_resid, counts = self.local.shard_plan(
+                owner, 0, self.world, self.rank, resid, False, want_ids=False)
+            c, cap = counts[self.rank], self._slab_capacity(counts)
+            mine = torch.empty(cap, dtype=torch.int32, device=u.device)
+            if c:
+                mine[:c].copy_(self.local.search(own_resid[:c]))
+        self._mark("sample: local leaf ids")
         slabs = torch.empty((self.world, cap), dtype=torch.int32, device=u.device)
         dist.all_gather_into_tensor(slabs.view(-1), mine, group=self.group)
         self._mark("sample: exchange indices")

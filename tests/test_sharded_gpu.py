@@ -117,6 +117,37 @@ def test_shard_plan_matches_numpy(shards, rank, m, npay, skew):
     assert np.array_equal(goti, w_shard.astype(np.int64) * (1 << shift) + islabs.cpu().numpy()[w_shard, w_slot])
 
 
+def test_async_plan_and_device_counted_search(oracle_mod=None):
+    """wait=False only enqueues the plan; the local search then reads its count on the device, and the
+    host collects the counts afterwards (what ShardedSumTree.sample_uniform does)."""
+    import oracle
+    from starr_b200 import DeviceSumTree
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(31)
+    n, m, shards, rank = 1 << 12, 50_000, 8, 5
+    leaves = rng.random(n).astype(np.float32)
+    tree_np = np.zeros(n, np.float32)
+    oracle.c.build_sumtree_from_array(leaves, tree_np)
+    tree = DeviceSumTree(torch.from_numpy(leaves).to(dev))
+    owner = rng.integers(0, shards, m).astype(np.int64)
+    resid = (rng.random(m) * tree_np[1]).astype(np.float32)
+    bufs = (torch.empty(m, dtype=torch.uint8, device=dev), torch.empty(m, dtype=torch.int32, device=dev),
+            torch.full((m,), -7, dtype=torch.int64, device=dev), torch.empty(m, dtype=torch.float32, device=dev))
+    shard, slot, _, own, counts = tree.shard_plan(torch.from_numpy(owner).to(dev), 0, shards, rank,
+                                                  torch.from_numpy(resid).to(dev), False, want_ids=False, out=bufs,
+                                                  result_slot=2, wait=False)
+    assert counts is None
+    tree.search_counted(own, 2, rank, bufs[2])
+    counts = tree.shard_plan_wait(2, shards)
+    mine = np.flatnonzero(owner == rank)
+    assert counts == [int((owner == s).sum()) for s in range(shards)]
+    want = np.zeros(mine.size, np.intp)
+    oracle.c.get_prefix_sum_idx(want, resid[mine], leaves, tree_np)
+    got = bufs[2].cpu().numpy()
+    assert np.array_equal(got[:mine.size], want)
+    assert (got[mine.size:] == -7).all()                     # nothing beyond the device-side count was touched
+
+
 def test_shard_plan_rejects_bad_batches():
     """The plan is synchronous, so a bad batch raises at once (the same verdict on every rank,
     since the batch is replicated) and nothing has been modified yet."""
