@@ -52,7 +52,7 @@ def end_of(sub, nth=0):
     hits = [e for e in ev[lo:hi] if sub in e["name"]]
     return (hits[nth]["ts"] + hits[nth]["dur"] - t0, hits[nth]["dur"]) if len(hits) > nth else (float("nan"), float("nan"))
 row = [rank, end_of("partition_levels")[1], end_of("fold_scan_kernel")[0], end_of("AllGather", 0)[1], end_of("AllGather", 0)[0],
-       end_of("AllGather", 1)[1], end_of("fold_huge_apply_kernel<float, true>")[0], end_of("AllGather", 2)[1], ev[hi]["ts"] - t0]
+       end_of("AllGather", 1)[1], end_of("fold_huge_apply_kernel<float, true")[0], end_of("AllGather", 2)[1], ev[hi]["ts"] - t0]
 with open(f"gpurun_out/trace_rank{rank}.txt", "w") as f:
     f.write("rank %d: partition %.0f us | local update ends %.0f | AG(deltas) dur %.0f ends %.0f | AG(recs) dur %.0f | top fold ends %.0f | AG(idx) dur %.0f | step %.0f\n" % tuple(row))
 dist.barrier()
