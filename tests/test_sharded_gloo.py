@@ -51,6 +51,24 @@ def _worker(rank, world, port, dt_name, n, q):
             oracle.c.get_prefix_sum_idx(want, (ref_tree[1] * u).astype(dt), ref_leaves, ref_tree)
             got = st.sample_uniform(torch.from_numpy(u)).numpy()
             ok &= bool(np.array_equal(got, want))
+        # edge cases of the host logic: empty batch, empty vals, empty query set, an explicit plan
+        before = st.gather_sumtree().numpy().tobytes()
+        st.update_(torch.zeros(0, dtype=torch.int64), torch.from_numpy(draw(3)))
+        ok &= st.gather_sumtree().numpy().tobytes() == before
+        try:
+            st.update_(torch.tensor([1, 2]), torch.from_numpy(draw(0)))
+            ok = False
+        except ZeroDivisionError:
+            pass
+        ok &= st.sample_uniform(torch.zeros(0, dtype=torch.float64)).numel() == 0
+        idx = rng.integers(0, n, 100).astype(np.int64)
+        vals = draw(100)
+        oracle.c.update_sumtree(idx.astype(np.intp), vals, ref_leaves, ref_tree)
+        plan = st.plan_update(torch.from_numpy(idx), torch.from_numpy(vals))
+        ok &= sum(plan.counts) == 100 and plan.ni == 100
+        st.update_(plan=plan)
+        ok &= st.gather_sumtree().numpy().tobytes() == ref_tree.tobytes()
+        ok &= float(st.total()) == float(ref_tree[1])
         try:
             st.update_(torch.tensor([0]), torch.from_numpy(np.array([1], dt)) * -1 if dt.kind != "u" else torch.tensor([n]), check=True)
             raised = dt.kind == "u"
