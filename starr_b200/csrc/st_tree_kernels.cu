@@ -274,7 +274,7 @@ search_kernel(const T *__restrict__ H, uint32_t n, int depth, const void *__rest
             for (int q = 0; q < SEARCH_Q; ++q) {
                 const uint32_t c = 2u * h[q];
                 lv[q] = T(0);
-                if (h[q] < n) lv[q] = (c < stage_nodes) ? top[c] : __ldg(H + c);
+                if (h[q] < n) lv[q] = (c < stage_nodes) ? top[c] : __ldcg(H + c);
             }
 #pragma unroll
             for (int q = 0; q < SEARCH_Q; ++q) {
@@ -294,7 +294,7 @@ search_kernel(const T *__restrict__ H, uint32_t n, int depth, const void *__rest
             const int64_t i = base + threadIdx.x + (int64_t)q * SEARCH_THREADS;
             if (i < m) {
                 out[i] = (int64_t)h[q] - (int64_t)n;
-                if (prio) prio[i] = __ldg(H + h[q]);
+                if (prio) prio[i] = __ldcg(H + h[q]);
                 if (resid) resid[i] = p[q];   // prefix left over inside the found leaf's subtree
             }
         }
@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(256) gather_kernel(const T *__restrict__ leave
 {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
         int64_t l = idx[i];
-        out[i] = (l >= 0 && l < n) ? __ldg(leaves + l) : T(0);
+        out[i] = (l >= 0 && l < n) ? __ldcg(leaves + l) : T(0);
     }
 }
 
