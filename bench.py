@@ -37,7 +37,6 @@ sys.path.insert(0, ROOT)
 
 LOG2_LEAVES = int(os.environ.get("ST_BENCH_LOG2_LEAVES", "27"))   # per GPU
 LOG2_BATCH = int(os.environ.get("ST_BENCH_LOG2_BATCH", "20"))     # per GPU
-N_BATCHES = 4                                                      # distinct synthetic batches, cycled
 METRIC = "leaf updates + prefix-search samples per second (2^27 float32 leaves per GPU, 2^20 + 2^20 per step)"
 UNIT = "ops/s"
 
@@ -125,10 +124,12 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "scope": scope, "period_ms": 20}
 
 
-def make_batches(rng, n_leaves_global, m_global):
-    """SURVEY 8(d) synthetic inputs: idx with replacement, uniform priorities, float64 uniforms."""
+def make_batches(rng, n_leaves_global, m_global, count):
+    """SURVEY 8(d) synthetic inputs: idx with replacement, uniform priorities, float64 uniforms.
+    `count` DISTINCT batches: re-applying a batch makes most differences exactly 0, which the update
+    skips -- every timed step therefore gets a batch that has not been applied before."""
     out = []
-    for _ in range(N_BATCHES):
+    for _ in range(count):
         out.append((rng.integers(0, n_leaves_global, m_global).astype(np.int64),
                     rng.random(m_global, dtype=np.float32),
                     rng.random(m_global)))
@@ -138,16 +139,20 @@ def make_batches(rng, n_leaves_global, m_global):
 # --------------------------------------------------------------------------------------------
 # CPU baseline (reference module from oracle/_ref, else the C oracle port)
 # --------------------------------------------------------------------------------------------
-def cpu_arm(leaves, batches, steps, warmup):
-    """Time the reference CPU path: per step update_sumtree(2^20) + get_prefix_sum_idx(2^20)."""
+def cpu_arm(leaves, batches, steps, warmup, keep=False):
+    """Time the reference CPU path: per step update_sumtree(2^20) + get_prefix_sum_idx(2^20), every step on
+    a batch it has not seen.  keep=True also returns the final (leaves, tree) and every step's sampled
+    indices: the in-run parity gate replays the same batches on the GPU and compares bits."""
     import oracle
     oracle.build()
     ref = oracle.ref()
     kind = "reference" if ref is not None else "port"
     K = ref if ref is not None else oracle.c
     avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
+    saved_affinity = None
     try:
-        os.sched_setaffinity(0, {sorted(os.sched_getaffinity(0))[0]})
+        saved_affinity = os.sched_getaffinity(0)
+        os.sched_setaffinity(0, {sorted(saved_affinity)[0]})
     except Exception:
         pass
     n = leaves.size
@@ -155,9 +160,11 @@ def cpu_arm(leaves, batches, steps, warmup):
     tree = np.zeros(n, np.float32)
     oracle.c.build_sumtree_from_array(arr, tree)   # bit-identical to the reference build, 10x faster
     m = batches[0][0].size
+    assert len(batches) >= warmup + steps
     t_upd = t_srch = 0.0
+    sampled = []
     for it in range(warmup + steps):
-        idx, val, u = batches[it % len(batches)]
+        idx, val, u = batches[it]
         idx = idx.astype(np.intp)
         t0 = time.perf_counter()
         K.update_sumtree(idx, val, arr, tree)
@@ -166,18 +173,28 @@ def cpu_arm(leaves, batches, steps, warmup):
         out = np.zeros(m, np.intp)
         K.get_prefix_sum_idx(out, q, arr, tree)
         t2 = time.perf_counter()
+        if keep:
+            sampled.append(out)
         if it >= warmup:
             t_upd += t1 - t0
             t_srch += t2 - t1
     total = t_upd + t_srch
-    return {
+    res = {
         "value": 2 * m * steps / total, "unit": UNIT, "cores": 1, "kind": kind,
-        "sample": f"{steps} full steps (2^{LOG2_BATCH} updates + 2^{LOG2_BATCH} samples each) on one pinned host core; "
-                  f"tree built by the C oracle",
+        "sample": f"{steps} full steps (2^{LOG2_BATCH} updates + 2^{LOG2_BATCH} samples each, a fresh batch per step) "
+                  f"on one pinned host core; tree built by the C oracle",
         "updates_per_s": m * steps / t_upd, "samples_per_s": m * steps / t_srch,
         "host_cores_available": avail,
         "ms_per_step": 1e3 * total / steps,
     }
+    if keep:
+        res["_state"] = (arr, tree, sampled)
+    try:
+        if saved_affinity:
+            os.sched_setaffinity(0, saved_affinity)
+    except Exception:
+        pass
+    return res
 
 
 def run_reference(args):
@@ -188,9 +205,9 @@ def run_reference(args):
     m = 1 << LOG2_BATCH
     rng = np.random.default_rng(0)
     leaves = rng.random(n, dtype=np.float32)
-    batches = make_batches(rng, n, m)
     steps = max(1, min(args.steps, 8))
     warmup = max(1, min(args.warmup, 2))
+    batches = make_batches(rng, n, m, steps + warmup)
     base = cpu_arm(leaves, batches, steps, warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
@@ -212,14 +229,82 @@ def workload_config(world):
                     f"(BASELINE config #3; config #4 at 8 GPUs)",
         "leaves_per_gpu": 1 << LOG2_LEAVES, "updates_per_step_per_gpu": 1 << LOG2_BATCH,
         "samples_per_step_per_gpu": 1 << LOG2_BATCH,
-        "l2_policy": "inputs larger than L2: the tree is 1 GiB per GPU and every step uses a different batch",
+        "l2_policy": "inputs larger than L2: the tree is 1 GiB per GPU; every warm-up and timed step applies a batch "
+                     "(indices, values, uniforms) that has never been applied before (zero_delta_frac reports the share "
+                     "of updates whose difference was exactly 0)",
         "parallelism": "single tree" if world == 1 else f"subtree shards x{world}, NCCL exchange of deltas / roots / results",
     }
 
 
 # --------------------------------------------------------------------------------------------
+# parity gates (SURVEY 8(d) "parity gates in the same run")
+# --------------------------------------------------------------------------------------------
+def parity_single(torch, dev, leaves_host, batches_host, cpu_state):
+    """Replay the CPU arm's batches on a fresh device tree: sumtree() bits, leaf bits and every step's
+    sampled indices must equal the reference's."""
+    from starr_b200 import DeviceSumTree
+    arr, tree, sampled = cpu_state
+    t = DeviceSumTree(torch.from_numpy(leaves_host).to(dev))
+    ok_idx = True
+    for k, want in enumerate(sampled):
+        i, v, u = batches_host[k]
+        t.update_(torch.from_numpy(i).to(dev), torch.from_numpy(v).to(dev))
+        got = t.sample_uniform(torch.from_numpy(u).to(dev))
+        ok_idx = ok_idx and bool(np.array_equal(got.cpu().numpy(), want))
+    t.poll()
+    ok_tree = t.tree.cpu().numpy().tobytes() == tree.tobytes()
+    ok_leaves = t.leaves.cpu().numpy().tobytes() == arr.tobytes()
+    del t
+    return {"checked": True, "batches": len(sampled), "sumtree_bits_equal": bool(ok_tree), "leaves_bits_equal": bool(ok_leaves),
+            "sampled_indices_equal": bool(ok_idx), "ok": bool(ok_tree and ok_leaves and ok_idx)}
+
+
+def parity_sharded(torch, dist, dev, world, rank):
+    """Reduced sharded case against the C oracle on EVERY rank, before the timed region: 2^22 leaves over the
+    ranks, float32 and int32, 3 replicated batches of 2^16 updates (with duplicates) and 50 000 samples."""
+    import oracle
+    from starr_b200 import ShardedSumTree
+    oracle.build()
+    C = oracle.c
+    n, m, q = 1 << 22, 1 << 16, 50000
+    n_local = n // world
+    detail = {}
+    ok = True
+    for name, dt, tdt in (("float32", np.float32, torch.float32), ("int32", np.int32, torch.int32)):
+        rng = np.random.default_rng(77)
+        leaves = rng.random(n).astype(dt) if dt == np.float32 else rng.integers(0, 1000, n).astype(dt)
+        tree = np.zeros(n, dt)
+        C.build_sumtree_from_array(leaves, tree)
+        sh = ShardedSumTree(n, tdt, local_leaves=torch.from_numpy(leaves[rank * n_local:(rank + 1) * n_local].copy()).to(dev))
+        good = True
+        for b in range(3):
+            idx = rng.integers(0, n if b < 2 else n // 64, m).astype(np.int64)
+            val = rng.random(m).astype(dt) if dt == np.float32 else rng.integers(0, 1000, m).astype(dt)
+            u = rng.random(q)
+            C.update_sumtree(idx.astype(np.intp), val, leaves, tree)
+            want = np.zeros(q, np.intp)
+            C.get_prefix_sum_idx(want, (tree[1] * u).astype(dt), leaves, tree)
+            sh.update_(torch.from_numpy(idx).to(dev), torch.from_numpy(val).to(dev))
+            got = sh.sample_uniform(torch.from_numpy(u).to(dev))
+            good = good and bool(np.array_equal(got.cpu().numpy(), want))
+        sh.poll()
+        good = good and sh.gather_sumtree().cpu().numpy().tobytes() == tree.tobytes()
+        good = good and sh.gather_leaves().cpu().numpy().tobytes() == leaves.tobytes()
+        flag = torch.tensor([1 if good else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        detail[name] = bool(flag.item())
+        ok = ok and detail[name]
+        del sh
+    torch.cuda.empty_cache()
+    return ok, {"leaves": n, "batches": 3, "updates_per_batch": m, "samples_per_batch": q, "checked_on": "every rank", **detail}
+
+
+# --------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------
+MAX_DISTINCT_BYTES = 12 << 30    # device memory spent on pre-generated batches before cycling (with fresh values)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -235,8 +320,8 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # keep stdout to the single JSON line (the box may export NCCL_DEBUG=VERSION, which prints there)
-        os.environ["NCCL_DEBUG"] = os.environ.get("ST_NCCL_DEBUG", "WARN")
+        # stdout carries the single JSON line: whatever NCCL_DEBUG level the box exports goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     n_local = 1 << LOG2_LEAVES
@@ -245,164 +330,274 @@ def run_ours(args):
     m_global = m_local * world
     steps, warmup = args.steps, max(3, args.warmup)
 
-    # synthetic priorities: every rank draws its own shard; batches are replicated (same seed)
-    leaves_host = np.random.default_rng(1000 + rank).random(n_local, dtype=np.float32) if world > 1 else \
-        np.random.default_rng(0).random(n_local, dtype=np.float32)
-    rng = np.random.default_rng(0) if world > 1 else np.random.default_rng(0)
-    if world == 1:
-        rng.random(n_local, dtype=np.float32)     # keep the stream identical to the reference arm
-    batches_host = make_batches(rng, n_global, m_global)
-
-    if world == 1:
-        tree = DeviceSumTree(torch.from_numpy(leaves_host).to(dev))
-        tree.reserve(m_local)
-    else:
-        from starr_b200 import ShardedSumTree
-        tree = ShardedSumTree(n_global, torch.float32, local_leaves=torch.from_numpy(leaves_host).to(dev))
-        tree.reserve(m_global)
-    dbatches = [(torch.from_numpy(i).to(dev), torch.from_numpy(v).to(dev), torch.from_numpy(u).to(dev))
-                for i, v, u in batches_host]
-    out = torch.empty(m_global, dtype=torch.int64, device=dev)
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step(i, v, u):
-        tree.update_(i, v)
-        return tree.sample_uniform(u, out=out)
+    # ---- sharded parity gate, before anything is timed -------------------------------------------
+    par_sharded = None
+    if world > 1:
+        ok, par_sharded = parity_sharded(torch, dist, dev, world, rank)
+        if not ok:
+            if rank == 0:
+                print(json.dumps({"metric": METRIC, "parity_sharded": False, "parity_sharded_detail": par_sharded}), flush=True)
+            dist.barrier()
+            dist.destroy_process_group()
+            sys.exit(3)
+
+    # synthetic priorities: every rank draws its own shard
+    leaves_host = np.random.default_rng(1000 + rank).random(n_local, dtype=np.float32) if world > 1 else \
+        np.random.default_rng(0).random(n_local, dtype=np.float32)
+
+    def build_tree(n_loc, leaves_dev, m_res):
+        if world == 1:
+            t = DeviceSumTree(leaves_dev)
+            t.reserve(m_res)
+        else:
+            from starr_b200 import ShardedSumTree
+            t = ShardedSumTree(n_loc * world, torch.float32, local_leaves=leaves_dev)
+            t.reserve(m_res)
+        return t
+
+    tree = build_tree(n_local, torch.from_numpy(leaves_host).to(dev), m_global)
+
+    # Batches are generated on the device with the same seed on every rank (replicated input, as a PER
+    # learner broadcasts it): DISTINCT batches for every warm-up and timed step.
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(20260)
+
+    def gen_batch(n_tot, m_tot):
+        return (torch.randint(0, n_tot, (m_tot,), generator=gen, device=dev, dtype=torch.int64),
+                torch.rand(m_tot, generator=gen, device=dev, dtype=torch.float32),
+                torch.rand(m_tot, generator=gen, device=dev, dtype=torch.float64))
+
+    def counters(t):
+        h = t.handle if world == 1 else t.local.handle
+        return h.update_counters(torch.cuda.current_stream().cuda_stream, reset=True)
+
+    def timed_leg(t, n_tot, m_tot, nsteps, nwarm):
+        """W warm-up + exactly K timed steps on never-applied batches; returns per-rank times (ms)."""
+        per = m_tot * 20
+        distinct = max(2, min(nwarm + nsteps + 1, MAX_DISTINCT_BYTES // per))
+        cycling = distinct < nwarm + nsteps + 1
+        bat = [gen_batch(n_tot, m_tot) for _ in range(distinct)]
+        outb = torch.empty(m_tot, dtype=torch.int64, device=dev)
+        s_plan = torch.cuda.Stream() if world > 1 else None
+
+        def use(k):
+            b = bat[k % distinct]
+            return b
+
+        def refresh(k):
+            if cycling:   # the slot will be reused: give it values it has never had (a few us, inside the region)
+                bat[k % distinct][1].uniform_(0, 1, generator=gen)
+
+        for w in range(nwarm):
+            i, v, u = use(w)
+            t.update_(i, v)
+            t.sample_uniform(u, out=outb)
+            refresh(w)
+        t.poll()
+        barrier()
+        counters(t)
+        launches0 = int(_lib.lib().st_kernel_launches())
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * nsteps + 1)]
+        # Sharded runs plan ahead: owner / slot / compaction of batch k+1 (it reads nothing of the tree) is
+        # computed on a side stream while batch k is applied.  One plan per step inside the timed region.
+        plan = t.plan_update(*use(nwarm)[:2], stream=s_plan) if world > 1 else None
+        barrier()
+        t_w0 = time.time()
+        ev[0].record()
+        for k in range(nsteps):
+            i, v, u = use(nwarm + k)
+            if world > 1:
+                t.update_(plan=plan)
+                ev[2 * k + 1].record()
+                if k + 1 < nsteps:
+                    plan = t.plan_update(*use(nwarm + k + 1)[:2], stream=s_plan)
+            else:
+                t.update_(i, v)
+                ev[2 * k + 1].record()
+            t.sample_uniform(u, out=outb)
+            ev[2 * k + 2].record()
+            refresh(nwarm + k)
+        barrier()
+        window = (t_w0, time.time())
+        launches = int(_lib.lib().st_kernel_launches()) - launches0
+        total_ms = ev[0].elapsed_time(ev[-1])
+        upd_ms = sum(ev[2 * k].elapsed_time(ev[2 * k + 1]) for k in range(nsteps))
+        smp_ms = sum(ev[2 * k + 1].elapsed_time(ev[2 * k + 2]) for k in range(nsteps))
+        t.poll()
+        cnt = counters(t)
+        del bat
+        return total_ms, upd_ms, smp_ms, launches, window, cnt, cycling
 
     # ---- device-resident timing ---------------------------------------------------------------
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    for w in range(warmup):
-        step(*dbatches[w % N_BATCHES])
-    tree.poll()
-    barrier()
-    launches0 = int(_lib.lib().st_kernel_launches())
     windows = []
-    t_w0 = time.time()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * steps + 1)]
-    # Sharded runs plan ahead: owner / slot / compaction of batch k+1 (it reads nothing of the tree) is
-    # computed on a side stream while batch k is applied.  One plan per step inside the timed region.
-    s_plan = torch.cuda.Stream() if world > 1 else None
-    plan = tree.plan_update(*dbatches[warmup % N_BATCHES][:2], stream=s_plan) if world > 1 else None
-    barrier()
-    ev[0].record()
-    for k in range(steps):
-        i, v, u = dbatches[(warmup + k) % N_BATCHES]
-        if world > 1:
-            tree.update_(plan=plan)
-            ev[2 * k + 1].record()
-            plan = tree.plan_update(*dbatches[(warmup + k + 1) % N_BATCHES][:2], stream=s_plan)
-        else:
-            tree.update_(i, v)
-            ev[2 * k + 1].record()
-        tree.sample_uniform(u, out=out)
-        ev[2 * k + 2].record()
-    barrier()
-    launches = int(_lib.lib().st_kernel_launches()) - launches0
-    windows.append((t_w0, time.time()))
-    total_ms = ev[0].elapsed_time(ev[-1])
-    upd_ms = sum(ev[2 * k].elapsed_time(ev[2 * k + 1]) for k in range(steps))
-    smp_ms = sum(ev[2 * k + 1].elapsed_time(ev[2 * k + 2]) for k in range(steps))
-    tree.poll()
+    total_ms, upd_ms, smp_ms, launches, win, cnt_dev, cycling = timed_leg(tree, n_global, m_global, steps, warmup)
+    windows.append(win)
 
-    # ---- end-to-end: pinned host buffers in, sampled indices back on the host -------------------
-    # Sharded runs feed the batch the way a data-parallel learner would: every rank holds ITS slice of
-    # the batch in pinned host memory, uploads only that (PCIe carries every byte once, not once per
-    # rank), the slices are all-gathered over NVLink, and every rank reads back its slice of the result.
-    mine = slice(rank * m_local, (rank + 1) * m_local) if world > 1 else slice(0, m_global)
-    pinned = [(torch.from_numpy(i[mine]).pin_memory(), torch.from_numpy(v[mine]).pin_memory(),
-               torch.from_numpy(u[mine]).pin_memory()) for i, v, u in batches_host]
-    host_out = torch.empty(mine.stop - mine.start, dtype=torch.int64).pin_memory()
+    # ---- end-to-end: HOST buffers in, sampled indices back on the host -----------------------------
+    rng_e = np.random.default_rng(555 + rank)
+    e2e_distinct = min(steps + 2, 64)
+    if world == 1:
+        # through the C ABI: st_per_step_host_submit / st_per_step_host_wait (pinned host buffers from
+        # st_host_alloc; two slots, so the H2D of step k+1 and the D2H of step k-1 overlap the kernels of step k)
+        h = tree.handle
+        pins = []
+        for _ in range(e2e_distinct):
+            pb = _lib.PinnedBuffer(m_local * 20)
+            i = pb.array(np.int64, m_local, 0); v = pb.array(np.float32, m_local, 8 * m_local)
+            u = pb.array(np.float64, m_local, 12 * m_local)
+            i[:] = rng_e.integers(0, n_local, m_local); v[:] = rng_e.random(m_local, dtype=np.float32); u[:] = rng_e.random(m_local)
+            pins.append((pb, i, v, u))
+        outs = []
+        for _ in range(2):
+            pb = _lib.PinnedBuffer(m_local * 8)
+            outs.append((pb, pb.array(np.int64, m_local, 0)))
 
-    # Software-pipelined like a real PER loop: the H2D copy of step k+1 and the D2H copy of step k-1
-    # run on side streams while step k computes; every step's copies are inside the timed region.
-    s_main = torch.cuda.current_stream()
-    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
-    dbuf = [tuple(torch.empty(m_global, dtype=t.dtype, device=dev) for t in pinned[0]) for _ in range(2)]
-    stage = [tuple(torch.empty_like(t, device=dev) for t in pinned[0]) for _ in range(2)] if world > 1 else dbuf
-    obuf = [torch.empty(m_global, dtype=torch.int64, device=dev) for _ in range(2)]
-    ev_in = [torch.cuda.Event() for _ in range(2)]
-    ev_free = [torch.cuda.Event() for _ in range(2)]     # inputs of the slot consumed
-    ev_done = [torch.cuda.Event() for _ in range(2)]     # results of the slot ready
-    ev_read = [torch.cuda.Event() for _ in range(2)]     # results of the slot copied out
+        def e2e_run(first, nsteps):
+            for k in range(nsteps):
+                slot = k % 2
+                if k >= 2:
+                    h.per_step_host_wait(slot)
+                _, i, v, u = pins[(first + k) % e2e_distinct]
+                h.per_step_host_submit(slot, i, v, u, outs[slot][1])
+            for k in range(max(0, nsteps - 2), nsteps):
+                h.per_step_host_wait(k % 2)
 
-    def prefetch(k):
-        slot = k % 2
-        with torch.cuda.stream(s_in):
-            s_in.wait_event(ev_free[slot])
-            for dst, src in zip(stage[slot], pinned[k % N_BATCHES]):
-                dst.copy_(src, non_blocking=True)
-            if world > 1:
+        torch.cuda.synchronize()
+        e2e_run(0, 2)
+        counters(tree)
+        t_w0 = time.time()
+        t0 = time.perf_counter()
+        e2e_run(2, steps)
+        e2e_ms = (time.perf_counter() - t0) * 1e3     # host clock: the call is synchronous at its ends (wait() blocks)
+        windows.append((t_w0, time.time()))
+        cnt_e2e = counters(tree)
+        e2e_how = ("C ABI st_per_step_host_submit/_wait on pinned host buffers (st_host_alloc): every step's indices, "
+                   "values and uniforms are copied H2D and its sampled indices D2H inside the timed region; two slots, "
+                   "so copies of step k+1 / k-1 overlap the kernels of step k; timed with the host clock around the "
+                   "blocking calls")
+        del pins, outs
+    else:
+        # Sharded: every rank holds ITS 1/N slice of the batch in pinned host memory, uploads only that (PCIe
+        # carries every byte once), the slices are all-gathered over NVLink, and every rank reads back its slice.
+        mine = slice(rank * m_local, (rank + 1) * m_local)
+        pinned = [(torch.from_numpy(rng_e.integers(0, n_global, m_local).astype(np.int64)).pin_memory(),
+                   torch.from_numpy(rng_e.random(m_local, dtype=np.float32)).pin_memory(),
+                   torch.from_numpy(rng_e.random(m_local)).pin_memory()) for _ in range(e2e_distinct)]
+        host_out = torch.empty(m_local, dtype=torch.int64).pin_memory()
+        s_main = torch.cuda.current_stream()
+        s_in, s_out, s_plan = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
+        dbuf = [tuple(torch.empty(m_global, dtype=t.dtype, device=dev) for t in pinned[0]) for _ in range(2)]
+        stage = [tuple(torch.empty_like(t, device=dev) for t in pinned[0]) for _ in range(2)]
+        obuf = [torch.empty(m_global, dtype=torch.int64, device=dev) for _ in range(2)]
+        ev_in = [torch.cuda.Event() for _ in range(2)]
+        ev_free = [torch.cuda.Event() for _ in range(2)]
+        ev_done = [torch.cuda.Event() for _ in range(2)]
+        ev_read = [torch.cuda.Event() for _ in range(2)]
+
+        def prefetch(first, k):
+            slot = k % 2
+            with torch.cuda.stream(s_in):
+                s_in.wait_event(ev_free[slot])
+                for dst, src in zip(stage[slot], pinned[(first + k) % e2e_distinct]):
+                    dst.copy_(src, non_blocking=True)
                 for full, part in zip(dbuf[slot], stage[slot]):
                     dist.all_gather_into_tensor(full, part)
-            ev_in[slot].record(s_in)
+                ev_in[slot].record(s_in)
 
-    def e2e_run(nsteps):
-        for slot in range(2):
-            ev_free[slot].record(s_main)
-            ev_read[slot].record(s_main)
-        prefetch(0)
-        plan = None
-        if world > 1:
+        def e2e_run(first, nsteps):
+            for slot in range(2):
+                ev_free[slot].record(s_main)
+                ev_read[slot].record(s_main)
+            prefetch(first, 0)
             s_plan.wait_event(ev_in[0])
             plan = tree.plan_update(*dbuf[0][:2], stream=s_plan)
-        for k in range(nsteps):
-            slot = k % 2
-            if k + 1 < nsteps:
-                prefetch(k + 1)
-            s_main.wait_event(ev_in[slot])
-            s_main.wait_event(ev_read[slot])            # previous results of this slot are on the host
-            di, dv, du = dbuf[slot]
-            if world > 1:
+            for k in range(nsteps):
+                slot = k % 2
+                if k + 1 < nsteps:
+                    prefetch(first, k + 1)
+                s_main.wait_event(ev_in[slot])
+                s_main.wait_event(ev_read[slot])
                 tree.update_(plan=plan)
-                if k + 1 < nsteps:                      # plan of the next batch as soon as its inputs have landed
+                if k + 1 < nsteps:
                     s_plan.wait_event(ev_in[(k + 1) % 2])
                     plan = tree.plan_update(*dbuf[(k + 1) % 2][:2], stream=s_plan)
-            else:
-                tree.update_(di, dv)
-            tree.sample_uniform(du, out=obuf[slot])
-            ev_free[slot].record(s_main)
-            ev_done[slot].record(s_main)
-            with torch.cuda.stream(s_out):
-                s_out.wait_event(ev_done[slot])
-                host_out.copy_(obuf[slot][mine], non_blocking=True)
-                ev_read[slot].record(s_out)
-        s_main.wait_stream(s_out)
+                tree.sample_uniform(dbuf[slot][2], out=obuf[slot])
+                ev_free[slot].record(s_main)
+                ev_done[slot].record(s_main)
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(ev_done[slot])
+                    host_out.copy_(obuf[slot][mine], non_blocking=True)
+                    ev_read[slot].record(s_out)
+            s_main.wait_stream(s_out)
 
-    e2e_run(2)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_w0 = time.time()
-    e0.record()
-    e2e_run(steps)
-    e1.record()
-    barrier()
-    windows.append((t_w0, time.time()))
-    e2e_ms = e0.elapsed_time(e1)
+        e2e_run(0, 2)
+        barrier()
+        counters(tree)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_w0 = time.time()
+        e0.record()
+        e2e_run(2, steps)
+        e1.record()
+        barrier()
+        windows.append((t_w0, time.time()))
+        e2e_ms = e0.elapsed_time(e1)
+        cnt_e2e = counters(tree)
+        e2e_how = ("pinned host buffers; every rank uploads / reads back its 1/N slice of the batch (byte counts are totals "
+                   "over ranks), slices are all-gathered over NVLink; H2D of step k+1 and D2H of step k-1 overlap step k")
+        del pinned, dbuf, stage, obuf
     tree.poll()
     clocks = sampler.stop(windows) if rank == 0 else None
 
     # ---- per-kernel durations of the update pipeline (CUDA events on the launching stream) -------
     breakdown = None
     if world == 1:
+        nb = min(steps, 10)
+        bat = [gen_batch(n_global, m_global) for _ in range(nb)]
         tree.handle.set_profiling(True)
-        for k in range(min(steps, 10)):
-            i, v, u = dbatches[k % N_BATCHES]
+        for i, v, u in bat:
             tree.update_(i, v)
         torch.cuda.synchronize()
         breakdown = tree.handle.update_breakdown()
         tree.handle.set_profiling(False)
+        del bat
+
+    # ---- BASELINE config #4 as stated: a FIXED 2^30 leaves over the N GPUs, 2^20 + 2^20 per step -------------
+    fixed = None
+    if world > 1 and not args.no_fixed:
+        del tree
+        torch.cuda.empty_cache()
+        nl = (1 << 30) // world
+        gen_l = torch.Generator(device=dev)
+        gen_l.manual_seed(4242 + rank)              # every rank its own shard; `gen` stays in lock step for the batches
+        lv = torch.rand(nl, device=dev, dtype=torch.float32, generator=gen_l)
+        tree = build_tree(nl, lv, 1 << LOG2_BATCH)
+        del lv
+        fsteps = max(1, min(steps, 20))
+        f_total, f_upd, f_smp, _, _, f_cnt, _ = timed_leg(tree, 1 << 30, 1 << LOG2_BATCH, fsteps, 3)
+        ft = torch.tensor([f_total, f_upd, f_smp], dtype=torch.float64, device=dev)
+        dist.all_reduce(ft, op=dist.ReduceOp.MAX)
+        f_total, f_upd, f_smp = ft.tolist()
+        mm = 1 << LOG2_BATCH
+        fixed = {"workload": f"BASELINE config #4: 2^30 float32 leaves sharded over {world} GPUs, 2^{LOG2_BATCH} updates + "
+                             f"2^{LOG2_BATCH} samples per step in total (strong scaling)",
+                 "steps": fsteps, "ms_per_step": f_total / fsteps, "value": 2 * mm * fsteps / (f_total * 1e-3), "unit": UNIT,
+                 "updates_per_s": mm * fsteps / (f_upd * 1e-3), "samples_per_s": mm * fsteps / (f_smp * 1e-3),
+                 "zero_delta_frac": f_cnt["zero_delta"] / max(1, f_cnt["updates"])}
 
     times = torch.tensor([total_ms, upd_ms, smp_ms, e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     total_ms, upd_ms, smp_ms, e2e_ms = times.tolist()
 
+    rc = 0
     if rank == 0:
         peak, peak_src = measured_hbm_peak()
         ops_per_step = 2 * m_global
@@ -410,30 +605,20 @@ def run_ours(args):
         smp_rate = m_global * steps / (smp_ms * 1e-3)
         bu, bs = bytes_per_update(n_global), bytes_per_sample(n_global)
 
-        def roof(name, per_unit, units_per_launch, ms_per_launch):
+        def roof(name, per_unit, units_per_launch, ms_per_launch, traffic=None):
             ach = per_unit * units_per_launch / (ms_per_launch * 1e-3) / 1e9
             return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": None, "algorithmic_bytes_per_unit": per_unit, "peak_source": peak_src,
+                    "traffic": traffic, "algorithmic_bytes_per_unit": per_unit, "peak_source": peak_src,
                     "ms_per_launch": ms_per_launch}
 
-        r_upd = roof("update pipeline, all kernels (sort + leaf pass + partition + ordered folds)", bu, m_local,
-                     upd_ms / steps)
-        r_smp = roof("search_kernel<float, staged, uniform>", bs, m_local, smp_ms / steps)
         traffic = ncu_traffic()
-        r_smp["traffic"] = traffic.get("search_kernel")
-        dominant = r_upd if upd_ms >= smp_ms else r_smp
-        if breakdown and breakdown["calls"]:
-            phases = {"partition_levels_kernel": breakdown["partition_ms"], "retire_kernel": breakdown["retire_ms"],
-                      "fold_scan_kernel": breakdown["fold_scan_ms"],
-                      "fold_huge_maps_kernel": breakdown["huge_maps_ms"],
-                      "leaf_pass_kernel": breakdown["leaf_pass_ms"], "search_kernel": smp_ms / steps}
-            top = max(phases, key=phases.get)
-            if top != "search_kernel":
-                # the update's algorithmic bytes (236 B/update) are charged to its dominant kernel
-                dominant = roof(f"{top}<float> (dominant kernel of the update; all 236 B/update charged to it)", bu,
-                                m_local, phases[top])
-                dominant["traffic"] = traffic.get(top)
-                dominant["share_of_step"] = phases[top] / (total_ms / steps)
+        r_upd = roof("update pipeline, all kernels of one batch (leaf pass + ordered partition + retirement + folds); "
+                     "236 B/update is the work of the whole pipeline, so it is charged to the whole pipeline",
+                     bu, m_local, upd_ms / steps, traffic.get("update_pipeline"))
+        r_smp = roof("search_kernel<float, staged, uniform>", bs, m_local, smp_ms / steps, traffic.get("search_kernel"))
+        r_step = roof("whole step (update pipeline + search_kernel)", bu + bs, m_local, total_ms / steps)
+        dominant = dict(r_upd if upd_ms >= smp_ms else r_smp)
+        dominant["share_of_step"] = max(upd_ms, smp_ms) / total_ms
         line = {
             "metric": METRIC, "value": ops_per_step * steps / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": steps, "warmup": warmup, "ms_per_step": total_ms / steps, "higher_is_better": True,
@@ -441,23 +626,43 @@ def run_ours(args):
             "config": workload_config(world),
             "updates_per_s": upd_rate, "samples_per_s": smp_rate,
             "update_ms_per_step": upd_ms / steps, "sample_ms_per_step": smp_ms / steps,
-            "roofline": dominant, "roofline_update": r_upd, "roofline_sample": r_smp,
+            "zero_delta_frac": cnt_dev["zero_delta"] / max(1, cnt_dev["updates"]),
+            "fresh_batches": {"distinct_per_leg": "all" if not cycling else "cycled with regenerated values",
+                              "updates_counted": cnt_dev["updates"]},
+            "roofline": dominant, "roofline_update": r_upd, "roofline_sample": r_smp, "roofline_step": r_step,
             "e2e": {"value": ops_per_step * steps / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": m_global * (8 + 4 + 8), "d2h_bytes_per_step": m_global * 8,
-                    "ms_per_step": e2e_ms / steps,
-                    "note": "pinned host buffers; H2D of step k+1 and D2H of step k-1 overlap step k on side streams"
-                            + ("; every rank uploads / reads back its 1/N slice of the batch (byte counts are "
-                               "totals over ranks), slices are all-gathered over NVLink" if world > 1 else "")},
+                    "ms_per_step": e2e_ms / steps, "zero_delta_frac": cnt_e2e["zero_delta"] / max(1, cnt_e2e["updates"]),
+                    "distinct_batches": e2e_distinct, "note": e2e_how},
             "gpu_launches": launches, "clocks": clocks, "update_breakdown_ms": breakdown,
         }
+        if par_sharded is not None:
+            line["parity_sharded"] = True
+            line["parity_sharded_detail"] = par_sharded
+        if fixed is not None:
+            line["fixed_2p30"] = fixed
         if world == 1 and not args.no_cpu_baseline:
-            cb = cpu_arm(leaves_host, batches_host, steps=3, warmup=1)
+            # CPU leg + parity gate: the reference applies 4 fresh batches; the same batches are replayed on a
+            # fresh device tree and every bit is compared
+            del tree
+            torch.cuda.empty_cache()
+            rng = np.random.default_rng(0)
+            rng.random(n_local, dtype=np.float32)     # leaves_host came from this stream (same as --impl reference)
+            bh = make_batches(rng, n_local, m_local, 4)
+            cb = cpu_arm(leaves_host, bh, steps=3, warmup=1, keep=True)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "updates_per_s",
                                                        "samples_per_s", "host_cores_available")}
+            par = parity_single(torch, dev, leaves_host, bh, cb["_state"])
+            par["oracle"] = cb["kind"]
+            line["parity"] = par
+            if not par["ok"]:
+                rc = 4
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if rc:
+        sys.exit(rc)
 
 
 def main():
@@ -466,7 +671,8 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg and the in-run parity gate (N=1)")
+    ap.add_argument("--no-fixed", action="store_true", help="skip the fixed-2^30-leaf leg (N>1)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -69,6 +69,19 @@ typedef enum st_status {
 /* flags for st_update_device */
 #define ST_UPDATE_DEFAULT 0
 #define ST_UPDATE_SYNC_CHECK 1 /* wait for the batch and return its validation status */
+/* the leaf becomes vals[j] itself instead of fl(leaf + fl(vals[j] - leaf)): the semantics of the
+ * reference's experimental C++ twin (starr/experimental/src/sumtree_array.cpp:19-23); ancestors still
+ * receive the ordered differences */
+#define ST_UPDATE_ASSIGN_LEAF 2
+
+/* in-place leaf arithmetic, st_inplace_device */
+typedef enum st_inplace_op {
+    ST_OP_ADD = 0,  /* x += c   */
+    ST_OP_SUB = 1,  /* x -= c   */
+    ST_OP_MUL = 2,  /* x *= c   */
+    ST_OP_DIV = 3,  /* x /= c   (float trees only, as in NumPy) */
+    ST_OP_FILL = 4  /* x.fill(c) */
+} st_inplace_op;
 
 ST_API int st_abi_version(void);
 ST_API const char *st_status_string(int status);
@@ -115,6 +128,10 @@ ST_API int st_update_device(st_tree *t, const int64_t *idx_dev, int64_t ni, cons
                      int64_t nv, void *stream, int flags);
 ST_API int st_update_host(st_tree *t, const int64_t *idx_host, int64_t ni, const void *vals_host,
                    int64_t nv);
+/* st_update_host with the ST_UPDATE_* flags of st_update_device (ST_UPDATE_ASSIGN_LEAF: the stateless
+ * experimental twin, starr/experimental/src/_sumtree_array.pyx:22-32) */
+ST_API int st_update_host_ex(st_tree *t, const int64_t *idx_host, int64_t ni, const void *vals_host,
+                      int64_t nv, int flags);
 /* st_update_host that also returns the resulting leaf values of idx (what SumTreeArray.put needs
  * for its host mirror: floats store fl(old + fl(val - old)), not val), in one staging round. */
 ST_API int st_update_gather_host(st_tree *t, const int64_t *idx_host, int64_t ni, const void *vals_host,
@@ -210,9 +227,64 @@ ST_API int st_axis_fold_device(const st_tree *t, int64_t A, int64_t R, int64_t C
                         void *stream);
 ST_API int st_axis_fold_host(const st_tree *t, int64_t A, int64_t R, int64_t C, void *out_host);
 
+/* ---- PER step (reference README.md:7, users do this on the host through
+ * sumtree_array.py:229-233, :365-421 and x[idx] / x.sum()) ----------------------------- */
+/* st_sample_uniform_device that also returns, per sample, the leaf's priority (tree dtype) and the
+ * sampling probability priority / total (tree dtype for f32 / f64 -- one IEEE division, as NumPy's
+ * x[idx] / x.sum() -- float64 for integer trees).  Either output may be NULL. */
+ST_API int st_sample_weights_device(const st_tree *t, const double *u_dev, int64_t m, int64_t *out_dev,
+                             void *prio_out_dev, void *prob_out_dev, void *stream);
+/* update -> sample -> priorities -> probabilities as ONE call: enqueues only (capturable in a CUDA
+ * graph after st_reserve); validation is deferred to st_poll_status. */
+ST_API int st_per_step_device(st_tree *t, const int64_t *idx_dev, int64_t ni, const void *vals_dev, int64_t nv,
+                       const double *u_dev, int64_t m, int64_t *out_idx_dev, void *out_prio_dev,
+                       void *out_prob_dev, void *stream);
+/* The same step for HOST buffers, pipelined over two slots: submit(slot) enqueues H2D of
+ * (idx, vals, u) on a copy stream, the step on the compute stream and D2H of the results on a third
+ * stream, and returns; wait(slot) blocks until that slot's results are in the caller's buffers and
+ * returns the batch's validation status.  With both slots in flight the copies of step k+1 / k-1
+ * overlap the kernels of step k.  Buffers must stay valid until wait(); use st_host_alloc (pinned
+ * memory) for truly asynchronous copies.  out_prio_host / out_prob_host may be NULL. */
+ST_API int st_per_step_host_submit(st_tree *t, int slot, const int64_t *idx_host, int64_t ni, const void *vals_host,
+                            int64_t nv, const double *u_host, int64_t m, int64_t *out_idx_host,
+                            void *out_prio_host, void *out_prob_host);
+ST_API int st_per_step_host_wait(st_tree *t, int slot);
+ST_API int st_host_alloc(int64_t bytes, void **out); /* page-locked host memory */
+ST_API int st_host_free(void *p);
+
+/* ---- in-place leaf arithmetic (replaces host ufunc + full rebuild upload,
+ * reference sumtree_array.py:150-173, :202-205) ---------------------------------------- */
+/* leaves = leaves (op) c, c = *scalar_host (one element of the tree dtype) or, if operand_dev is not
+ * NULL, operand_dev[i] (operand_len must be n).  Bit-identical to the NumPy ufunc in the tree dtype.
+ * Does NOT rebuild the tree: follow with st_build (which validates the new leaves, pyx:58-59). */
+ST_API int st_inplace_device(st_tree *t, int op, const void *scalar_host, const void *operand_dev,
+                      int64_t operand_len, void *stream);
+
+/* ---- min tree + ring append (reference starr/experimental/slow.py:53-98) - */
+/* A tree whose internal nodes are min(left, right); unset leaves are +inf (integers: type max).
+ * st_root_host = MinTree.min(); st_store_host / st_gather_leaves_* / st_destroy work as usual; the
+ * sum-tree entry points reject a min tree with ST_ERR_ARG. */
+ST_API int st_min_create(int64_t n, int dtype, int device, void *external_heap, st_tree **out); /* as st_create */
+/* heap[n + idx[j]] = vals[j % nv] for j in batch order (the last write to a leaf wins), then every
+ * ancestor = min(left, right) (slow.py:62-68).  Index range is validated before any write. */
+ST_API int st_min_update_device(st_tree *t, const int64_t *idx_dev, int64_t ni, const void *vals_dev, int64_t nv,
+                         void *stream);
+ST_API int st_min_update_host(st_tree *t, const int64_t *idx_host, int64_t ni, const void *vals_host, int64_t nv);
+ST_API int st_min_build(st_tree *t, void *stream); /* all internal nodes from the resident leaves */
+
+/* ---- bookkeeping -------------------------------------------------------------------- */
+/* out[0] = updates submitted through this handle, out[1] = how many of them had a difference of
+ * exactly 0 (nothing to propagate); cumulative, reset != 0 clears both after reading.  Waits for stream. */
+ST_API int st_update_counters(st_tree *t, void *stream, int64_t out[2], int reset);
+/* st_reserve for the sharded helpers too: sizes the scratch area for st_shard_plan_device and the
+ * top-fold records of batches up to max_batch over `shards` shards, so that none of the stream-ordered
+ * entry points reallocates (or synchronises) later. */
+ST_API int st_reserve_sharded(st_tree *t, int64_t max_batch, int shards);
+
 /* ---- deferred validation status of *_device calls -------------------------------- */
 /* Waits for `stream`, returns the first validation error recorded since the last clear
- * (ST_OK if none) and optionally clears it. A failed batch is skipped as a whole. */
+ * (ST_OK if none) and optionally clears it.  A failed batch is skipped as a whole; batches
+ * enqueued behind it are applied normally (its flags move to a sticky word that this call reports). */
 ST_API int st_poll_status(st_tree *t, void *stream, int clear);
 
 /* Optional: pin heap[0, bytes) (the upper tree levels) in the persisting part of L2 for work

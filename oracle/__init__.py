@@ -56,7 +56,7 @@ def build(force: bool = False) -> None:
     src = os.path.join(_HERE, "sumtree_oracle.c")
     if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
         subprocess.check_call(["make", "-C", _HERE, "-B", "liboracle.so"], stdout=subprocess.DEVNULL)
-    if os.path.exists("/root/reference/starr/src/_sumtree_array.pyx") and (force or not _ref_so()):
+    if os.path.exists("/root/reference/starr/src/_sumtree_array.pyx") and (force or not _ref_so() or not _ref_exp_so()):
         subprocess.check_call(["bash", os.path.join(_HERE, "build_ref.sh")], stdout=subprocess.DEVNULL)
 
 
@@ -177,9 +177,59 @@ class c:
         return out
 
 
+class exp:
+    """``starr.experimental._cython`` (the C++ twin) restated in plain C: float64 / int32, assign-leaf."""
+
+    @staticmethod
+    def update_tree_multi(idxs, vals, array, sumtree):
+        assert idxs.dtype == np.int32 and vals.dtype == array.dtype == sumtree.dtype == np.float64
+        rc = _load().orc_exp_update_tree_multi(_ptr(_c(idxs)), ctypes.c_int32(len(idxs)), _ptr(_c(vals)),
+                                               ctypes.c_int32(len(vals)), _ptr(_c(array)), ctypes.c_int32(len(array)),
+                                               _ptr(_c(sumtree)))
+        if rc == 1:
+            raise ValueError("val must be non-negative")
+
+    @staticmethod
+    def get_prefix_sum_idx_multi(output, vals, array, sumtree):
+        assert output.dtype == np.int32 and vals.dtype == array.dtype == sumtree.dtype == np.float64
+        _load().orc_exp_get_prefix_sum_idx_multi(_ptr(_c(output)), _ptr(_c(vals)), ctypes.c_int32(len(vals)),
+                                                 _ptr(_c(array)), ctypes.c_int32(len(sumtree)), _ptr(_c(sumtree)))
+        return output
+
+
+def min_tree_set(data, idxs, vals):
+    """Sequential ``MinTree.__setitem__`` over a batch on ``data[2n]`` (float64), slow.py:62-68."""
+    assert data.dtype == np.float64 and vals.dtype == np.float64 and idxs.dtype == np.int64
+    _load().orc_min_set_f64(_ptr(_c(data)), ctypes.c_int64(len(data) // 2), _ptr(_c(idxs)), ctypes.c_int64(len(idxs)),
+                            _ptr(_c(vals)), ctypes.c_int64(len(vals)))
+    return data
+
+
 # ----------------------------------------------------------------------------------------
 # the real reference, where available
 # ----------------------------------------------------------------------------------------
+def _ref_exp_so():
+    hits = glob.glob(os.path.join(_HERE, "_ref", "_xcython*.so"))
+    return hits[0] if hits else None
+
+
+_ref_exp_mod = None
+
+
+def ref_exp():
+    """The unmodified reference experimental module (``starr.experimental._cython``), or None."""
+    global _ref_exp_mod
+    if _ref_exp_mod is None:
+        so = _ref_exp_so()
+        if so is None:
+            return None
+        spec = importlib.util.spec_from_file_location("starr.experimental._cython", so)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        _ref_exp_mod = mod
+    return _ref_exp_mod
+
+
 def _ref_so():
     hits = glob.glob(os.path.join(_HERE, "_ref", "_cython*.so"))
     return hits[0] if hits else None

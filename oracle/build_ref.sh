@@ -32,3 +32,15 @@ $py -m cython -3 --module-name starr._cython "$pyx" -o "$tmp/_cython.c" 2>/dev/n
 gcc -shared -fPIC -fno-strict-overflow -fwrapv -DNDEBUG -O2 -w \
     -I"$incpy" -I"$incnp" "$tmp/_cython.c" -o "$out/_cython$suffix"
 echo "build_ref: wrote $out/_cython$suffix"
+
+# The experimental C++ twin (starr/experimental/src/{_sumtree_array.pyx,sumtree_array.cpp}; ext
+# `starr.experimental._cython`, setup.py:56-64): two source files, cython --cplus + one g++ command.
+xpyx="$ref/starr/experimental/src/_sumtree_array.pyx"
+xcpp="$ref/starr/experimental/src/sumtree_array.cpp"
+if [ -f "$xpyx" ] && [ -f "$xcpp" ]; then
+    $py -m cython -3 --cplus --module-name starr.experimental._cython "$xpyx" -o "$tmp/_xcython.cpp" 2>/dev/null
+    g++ -shared -fPIC -fno-strict-overflow -fwrapv -DNDEBUG -O2 -w \
+        -I"$incpy" -I"$incnp" -I"$ref/starr/experimental/src" "$tmp/_xcython.cpp" "$xcpp" \
+        -o "$out/_xcython$suffix"
+    echo "build_ref: wrote $out/_xcython$suffix"
+fi

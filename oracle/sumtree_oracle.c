@@ -169,3 +169,65 @@ DEFINE_FOLD(u32, uint32_t, uint64_t)
 DEFINE_FOLD(u64, uint64_t, uint64_t)
 DEFINE_FOLD(f32, float, float)
 DEFINE_FOLD(f64, double, double)
+
+/* ------------------------------------------------------------------------------------------
+ * starr.experimental: the C++ twin, starr/experimental/src/sumtree_array.cpp.
+ * float64 values, int32 indices.  Differences from orc_update_f64 that are restated here:
+ * the leaf is ASSIGNED (`*array = val`, cpp:23) and the negative check is per element inside
+ * the loop (cpp:15-17) -- updates in front of a negative value stay applied (the reference then
+ * throws through a nogil extern and the process aborts; this restatement returns ORC_NEGATIVE).
+ * `vals` cycles by a wrap-around cursor (cpp:41-50), the same as i % V.
+ * Pinned against the compiled reference module in oracle/_ref (tests/test_oracle.py). */
+int orc_exp_update_tree_multi(const int32_t *idxs, int32_t I, const double *vals, int32_t V,
+                              double *array, int32_t n, double *sumtree)
+{
+    int32_t v = 0;
+    for (int32_t i = 0; i < I; ++i) {
+        const double val = vals[v];
+        if (val < 0) return ORC_NEGATIVE;                 /* cpp:15-17 */
+        int32_t idx = idxs[i];
+        const double diff = val - array[idx];            /* cpp:21 */
+        array[idx] = val;                                /* cpp:22-23 */
+        for (idx = (idx + n) / 2; idx > 0; idx /= 2)     /* cpp:20, 25-29 */
+            sumtree[idx] += diff;
+        if (++v == V) v = 0;                             /* cpp:46-50 */
+    }
+    return ORC_OK;
+}
+
+/* cpp:54-85: the same left-child descent as orc_search_f64 with int32 outputs */
+void orc_exp_get_prefix_sum_idx_multi(int32_t *out, const double *vals, int32_t m, const double *array,
+                                      int32_t n, const double *sumtree)
+{
+    for (int32_t q = 0; q < m; ++q) {
+        double val = vals[q];
+        int32_t i = 1;
+        while (i < n) {
+            const int32_t left = 2 * i;
+            const double left_val = left < n ? sumtree[left] : array[left - n];
+            if (val >= left_val) {
+                i = left + 1;
+                val -= left_val;
+            } else {
+                i = left;
+            }
+        }
+        out[q] = i - n;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * MinTree: starr/experimental/slow.py:53-78.  data[2n], data[idx + n] = val, then
+ * every ancestor = min(left, right) with Python's min (returns the right operand only if it is
+ * smaller).  One call = a batch of sequential __setitem__ (slow.py:62-68). */
+void orc_min_set_f64(double *data, int64_t n, const int64_t *idxs, int64_t ni, const double *vals, int64_t nv)
+{
+    for (int64_t i = 0; i < ni; ++i) {
+        int64_t idx = idxs[i] + n;
+        data[idx] = vals[i % nv];
+        for (idx /= 2; idx > 0; idx /= 2) {
+            const double l = data[2 * idx], r = data[2 * idx + 1];
+            data[idx] = r < l ? r : l;
+        }
+    }
+}

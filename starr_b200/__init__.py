@@ -12,7 +12,7 @@ from .kernels import (build_sumtree_from_array, get_prefix_sum_idx, strided_sum,
 from .sumtree_array import SumTreeArray
 
 __all__ = ["get_prefix_sum_idx", "strided_sum", "sum_over", "build_sumtree_from_array",
-           "update_sumtree", "SumTreeArray", "DeviceSumTree", "ShardedSumTree"]
+           "update_sumtree", "SumTreeArray", "DeviceSumTree", "DeviceMinTree", "ShardedSumTree"]
 
 
 def __getattr__(name):
@@ -20,6 +20,9 @@ def __getattr__(name):
     if name == "DeviceSumTree":
         from .device_tree import DeviceSumTree
         return DeviceSumTree
+    if name == "DeviceMinTree":
+        from .device_tree import DeviceMinTree
+        return DeviceMinTree
     if name == "ShardedSumTree":
         from .sharded import ShardedSumTree
         return ShardedSumTree

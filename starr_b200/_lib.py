@@ -44,6 +44,10 @@ ST_ERR_CUDA = 8
 ST_ERR_TOO_LARGE = 9
 
 ST_UPDATE_SYNC_CHECK = 1
+ST_UPDATE_ASSIGN_LEAF = 2
+ST_OPS = {"add": 0, "subtract": 1, "multiply": 2, "true_divide": 3, "divide": 3, "fill": 4}
+# dtype of st_sample_weights_device's probabilities: the tree dtype for floats, float64 for integers
+PROB_DTYPES = {c: (np.float32 if c == 7 else np.float64) for c in range(9)}
 
 # status -> (exception type, message of the reference where it has one)
 _EXC = {
@@ -80,6 +84,7 @@ _SIGNATURES = {
     "st_build_from_device": (c_int, [c_void_p, c_void_p, c_void_p]),
     "st_update_device": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int]),
     "st_update_host": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64]),
+    "st_update_host_ex": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int]),
     "st_update_deltas_device": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
     "st_apply_deltas_device": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "st_top_fold_record_bytes": (c_int, [c_void_p]),
@@ -111,6 +116,21 @@ _SIGNATURES = {
     "st_set_profiling": (c_int, [c_void_p, c_int]),
     "st_set_l2_persistence": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "st_update_breakdown": (c_int, [c_void_p, c_void_p]),
+    "st_sample_weights_device": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "st_per_step_device": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p,
+                                   c_void_p, c_void_p]),
+    "st_per_step_host_submit": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
+                                        c_void_p, c_void_p]),
+    "st_per_step_host_wait": (c_int, [c_void_p, c_int]),
+    "st_host_alloc": (c_int, [c_int64, POINTER(c_void_p)]),
+    "st_host_free": (c_int, [c_void_p]),
+    "st_inplace_device": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_void_p]),
+    "st_min_create": (c_int, [c_int64, c_int, c_int, c_void_p, POINTER(c_void_p)]),
+    "st_min_update_device": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
+    "st_min_update_host": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64]),
+    "st_min_build": (c_int, [c_void_p, c_void_p]),
+    "st_update_counters": (c_int, [c_void_p, c_void_p, c_void_p, c_int]),
+    "st_reserve_sharded": (c_int, [c_void_p, c_int64, c_int]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
@@ -161,15 +181,20 @@ def host_ptr(a: np.ndarray) -> c_void_p:
 class TreeHandle:
     """Owner of one ``st_tree*``.  Thin: argument marshalling and status -> exception only."""
 
-    def __init__(self, n: int, dtype, device: int = 0, external_heap: int | None = None):
+    def __init__(self, n: int, dtype, device: int = 0, external_heap: int | None = None, kind: str = "sum"):
         self.dtype = np.dtype(dtype)
         self.code = dtype_code(self.dtype)
         self.n = int(n)
         self.device = int(device)
+        self.kind = kind
         out = c_void_p()
-        check(lib().st_create(self.n, self.code, self.device,
-                              c_void_p(external_heap) if external_heap else None,
-                              ctypes.byref(out)))
+        if kind == "min":
+            check(lib().st_min_create(self.n, self.code, self.device,
+                                      c_void_p(external_heap) if external_heap else None, ctypes.byref(out)))
+        else:
+            check(lib().st_create(self.n, self.code, self.device,
+                                  c_void_p(external_heap) if external_heap else None,
+                                  ctypes.byref(out)))
         self._h = out
 
     # -- lifetime ---------------------------------------------------------------------------
@@ -217,8 +242,9 @@ class TreeHandle:
     def build_from_host(self, leaves: np.ndarray) -> None:
         check(lib().st_build_from_host(self.ptr, host_ptr(leaves)))
 
-    def update_host(self, idx: np.ndarray, vals: np.ndarray) -> None:
-        check(lib().st_update_host(self.ptr, host_ptr(idx), idx.size, host_ptr(vals), vals.size))
+    def update_host(self, idx: np.ndarray, vals: np.ndarray, assign_leaf: bool = False) -> None:
+        check(lib().st_update_host_ex(self.ptr, host_ptr(idx), idx.size, host_ptr(vals), vals.size,
+                                      ST_UPDATE_ASSIGN_LEAF if assign_leaf else 0))
 
     def update_gather_host(self, idx: np.ndarray, vals: np.ndarray) -> np.ndarray:
         out = np.empty(idx.size, dtype=self.dtype)
@@ -264,9 +290,58 @@ class TreeHandle:
         check(lib().st_build_from_device(self.ptr, c_void_p(leaves_ptr), c_void_p(stream)))
 
     def update_device(self, idx_ptr: int, ni: int, vals_ptr: int, nv: int, stream: int = 0,
-                      sync_check: bool = False) -> None:
+                      sync_check: bool = False, assign_leaf: bool = False) -> None:
+        flags = (ST_UPDATE_SYNC_CHECK if sync_check else 0) | (ST_UPDATE_ASSIGN_LEAF if assign_leaf else 0)
         check(lib().st_update_device(self.ptr, c_void_p(idx_ptr), int(ni), c_void_p(vals_ptr), int(nv),
-                                     c_void_p(stream), ST_UPDATE_SYNC_CHECK if sync_check else 0))
+                                     c_void_p(stream), flags))
+
+    def sample_weights_device(self, u_ptr: int, m: int, out_ptr: int, prio_ptr: int = 0, prob_ptr: int = 0,
+                              stream: int = 0) -> None:
+        check(lib().st_sample_weights_device(self.ptr, c_void_p(u_ptr), int(m), c_void_p(out_ptr),
+                                             c_void_p(prio_ptr) if prio_ptr else None,
+                                             c_void_p(prob_ptr) if prob_ptr else None, c_void_p(stream)))
+
+    def per_step_device(self, idx_ptr: int, ni: int, vals_ptr: int, nv: int, u_ptr: int, m: int, out_ptr: int,
+                        prio_ptr: int = 0, prob_ptr: int = 0, stream: int = 0) -> None:
+        check(lib().st_per_step_device(self.ptr, c_void_p(idx_ptr), int(ni), c_void_p(vals_ptr), int(nv), c_void_p(u_ptr),
+                                       int(m), c_void_p(out_ptr), c_void_p(prio_ptr) if prio_ptr else None,
+                                       c_void_p(prob_ptr) if prob_ptr else None, c_void_p(stream)))
+
+    def per_step_host_submit(self, slot: int, idx: np.ndarray, vals: np.ndarray, u: np.ndarray, out_idx: np.ndarray,
+                             out_prio: np.ndarray | None = None, out_prob: np.ndarray | None = None) -> None:
+        """Pipelined host step (two slots); the arrays must stay alive and untouched until per_step_host_wait."""
+        check(lib().st_per_step_host_submit(self.ptr, int(slot), host_ptr(idx), idx.size, host_ptr(vals), vals.size,
+                                            host_ptr(u), u.size, host_ptr(out_idx),
+                                            host_ptr(out_prio) if out_prio is not None else None,
+                                            host_ptr(out_prob) if out_prob is not None else None))
+
+    def per_step_host_wait(self, slot: int) -> None:
+        check(lib().st_per_step_host_wait(self.ptr, int(slot)))
+
+    def inplace_device(self, op: str, scalar: np.ndarray | None, operand_ptr: int = 0, operand_len: int = 0,
+                       stream: int = 0) -> None:
+        """leaves = leaves (op) scalar | operand; no rebuild (call build afterwards)."""
+        check(lib().st_inplace_device(self.ptr, ST_OPS[op], host_ptr(scalar) if scalar is not None else None,
+                                      c_void_p(operand_ptr) if operand_ptr else None, int(operand_len),
+                                      c_void_p(stream)))
+
+    def min_update_device(self, idx_ptr: int, ni: int, vals_ptr: int, nv: int, stream: int = 0) -> None:
+        check(lib().st_min_update_device(self.ptr, c_void_p(idx_ptr), int(ni), c_void_p(vals_ptr), int(nv),
+                                         c_void_p(stream)))
+
+    def min_update_host(self, idx: np.ndarray, vals: np.ndarray) -> None:
+        check(lib().st_min_update_host(self.ptr, host_ptr(idx), idx.size, host_ptr(vals), vals.size))
+
+    def min_build(self, stream: int = 0) -> None:
+        check(lib().st_min_build(self.ptr, c_void_p(stream)))
+
+    def update_counters(self, stream: int = 0, reset: bool = False) -> dict:
+        out = (c_int64 * 2)()
+        check(lib().st_update_counters(self.ptr, c_void_p(stream), out, 1 if reset else 0))
+        return {"updates": int(out[0]), "zero_delta": int(out[1])}
+
+    def reserve_sharded(self, max_batch: int, shards: int) -> None:
+        check(lib().st_reserve_sharded(self.ptr, int(max_batch), int(shards)))
 
     def update_deltas_device(self, idx_ptr: int, ni: int, vals_ptr: int, nv: int, delta_out_ptr: int,
                              stream: int = 0) -> None:
@@ -379,3 +454,30 @@ class TreeHandle:
         # huge segments (more than 16384 updates under one node), cumulative since the tree was created
         return {"huge_segments_maps_only": out[0], "huge_segments_with_exact_chunks": out[1],
                 "chunks_folded_exactly": out[2], "most_exact_chunks_in_one_segment": out[3]}
+
+
+class PinnedBuffer:
+    """Page-locked host memory from ``st_host_alloc`` with NumPy views over it (inputs / outputs of the
+    pipelined host step, ``TreeHandle.per_step_host_submit``)."""
+
+    def __init__(self, nbytes: int):
+        self.nbytes = int(nbytes)
+        p = c_void_p()
+        check(lib().st_host_alloc(self.nbytes, ctypes.byref(p)))
+        self._p = p
+        self._raw = (ctypes.c_char * self.nbytes).from_address(p.value)
+
+    def array(self, dtype, count: int, offset: int = 0) -> np.ndarray:
+        return np.frombuffer(self._raw, dtype=dtype, count=count, offset=offset)
+
+    def close(self) -> None:
+        p, self._p = getattr(self, "_p", None), None
+        if p and _lib is not None:
+            self._raw = None
+            _lib.st_host_free(p)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

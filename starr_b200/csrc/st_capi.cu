@@ -54,14 +54,31 @@ struct device_guard {
     }
 };
 
-// wait for the stream, fetch the status word, optionally clear it on the device
-int fetch_status(st_tree *t, cudaStream_t s, bool clear)
+// Serialises the callers of one tree (the reference's functions hold the GIL end to end):
+// staging areas, workspace, status queue and the legacy-stream host paths belong to one call at a time.
+struct tree_lock {
+    std::lock_guard<std::recursive_mutex> g;
+    explicit tree_lock(const st_tree *t) : g(const_cast<st_tree *>(t)->mu) {}
+};
+
+cudaError_t clear_status_words(st_tree *t, cudaStream_t s)
 {
-    CU(cudaMemcpyAsync(t->h_status, t->d_status, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
+    cudaError_t e = cudaMemsetAsync(t->d_status, 0, sizeof(unsigned int), s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(t->d_status + ST_SW_STICKY, 0, sizeof(unsigned int), s);
+    return e;
+}
+
+// Wait for the stream and fetch the validation flags, optionally clearing what was reported.
+// own_only: just the batch that was enqueued last (synchronous calls report their OWN verdict; an
+// earlier asynchronous failure stays in the sticky word for st_poll_status).
+int fetch_status(st_tree *t, cudaStream_t s, bool clear, bool own_only = false)
+{
+    CU(cudaMemcpyAsync(t->h_status, t->d_status, 32 * sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
-    const unsigned int f = t->h_status[0];
+    const unsigned int f = own_only ? t->h_status[0] : (t->h_status[0] | t->h_status[ST_SW_STICKY]);
     if (f && clear) {
-        CU(cudaMemsetAsync(t->d_status, 0, sizeof(unsigned int), s));
+        if (own_only) CU(cudaMemsetAsync(t->d_status, 0, sizeof(unsigned int), s));
+        else CU(clear_status_words(t, s));
         CU(cudaStreamSynchronize(s));
     }
     return status_from_flags(f);
@@ -105,13 +122,13 @@ struct scratch_carver {
 
 }  // namespace
 
-namespace st { unsigned long long g_kernel_launches = 0; }
+namespace st { std::atomic<unsigned long long> g_kernel_launches{0}; }
 
 extern "C" {
 
-int st_abi_version(void) { return 2; }
+int st_abi_version(void) { return 3; }
 
-unsigned long long st_kernel_launches(void) { return st::g_kernel_launches; }
+unsigned long long st_kernel_launches(void) { return st::g_kernel_launches.load(); }
 
 const char *st_status_string(int status)
 {
@@ -201,6 +218,15 @@ int st_destroy(st_tree *t)
     if (t->plan_ev) cudaEventDestroy(t->plan_ev);
     if (t->ws.base) cudaFree(t->ws.base);
     if (t->scratch.base) cudaFree(t->scratch.base);
+    if (t->aux) cudaFree(t->aux);
+    for (auto &h : t->hs) {
+        if (h.dev) cudaFree(h.dev);
+        if (h.h_flag) cudaFreeHost(h.h_flag);
+        for (cudaEvent_t ev : {h.ev_in, h.ev_free, h.ev_done, h.ev_read})
+            if (ev) cudaEventDestroy(ev);
+    }
+    for (cudaStream_t st : {t->hs_in, t->hs_main, t->hs_out})
+        if (st) cudaStreamDestroy(st);
     for (int k = 0; k < 8; ++k)
         if (t->prof_ev[k]) cudaEventDestroy(t->prof_ev[k]);
     delete t;
@@ -215,6 +241,7 @@ void *st_heap_ptr(const st_tree *t) { return t ? t->heap : nullptr; }
 int st_reserve(st_tree *t, int64_t max_batch)
 {
     if (!t || max_batch < 1) return fail(ST_ERR_ARG, "st_reserve: bad argument");
+    tree_lock lk(t);
     device_guard g(t->device);
     if (max_batch > st::update_max_chunk()) max_batch = st::update_max_chunk();
     if (max_batch <= t->reserved_batch && t->ws.base) return ST_OK;
@@ -233,6 +260,7 @@ int st_reserve(st_tree *t, int64_t max_batch)
 int st_load_host(st_tree *t, const void *leaves, const void *tree)
 {
     if (!t) return fail(ST_ERR_ARG, "st_load_host: NULL tree");
+    tree_lock lk(t);
     device_guard g(t->device);
     const size_t half = (size_t)t->n * t->esize;
     if (tree) CU(cudaMemcpy(t->heap, tree, half, cudaMemcpyHostToDevice));
@@ -243,6 +271,7 @@ int st_load_host(st_tree *t, const void *leaves, const void *tree)
 int st_store_host(const st_tree *t, void *leaves, void *tree)
 {
     if (!t) return fail(ST_ERR_ARG, "st_store_host: NULL tree");
+    tree_lock lk(t);
     device_guard g(t->device);
     const size_t half = (size_t)t->n * t->esize;
     if (tree) CU(cudaMemcpy(tree, t->heap, half, cudaMemcpyDeviceToHost));
@@ -253,6 +282,7 @@ int st_store_host(const st_tree *t, void *leaves, void *tree)
 int st_gather_leaves_device(const st_tree *t, const int64_t *idx_dev, int64_t m, void *out_dev, void *stream)
 {
     if (!t || m < 0) return fail(ST_ERR_ARG, "st_gather_leaves_device: bad argument");
+    tree_lock lk(t);
     device_guard g(t->device);
     CU(st::launch_gather(t, idx_dev, m, out_dev, (cudaStream_t)stream));
     return ST_OK;
@@ -262,6 +292,7 @@ int st_gather_leaves_host(const st_tree *t, const int64_t *idx_host, int64_t m, 
 {
     if (!t || m < 0) return fail(ST_ERR_ARG, "st_gather_leaves_host: bad argument");
     if (m == 0) return ST_OK;
+    tree_lock lk(t);
     device_guard g(t->device);
     dev_buf di, dout;
     scratch_carver sc(t);
@@ -277,12 +308,14 @@ int st_gather_leaves_host(const st_tree *t, const int64_t *idx_host, int64_t m, 
 // ---- build ---------------------------------------------------------------------------------
 int st_build(st_tree *t, void *stream)
 {
-    if (!t) return fail(ST_ERR_ARG, "st_build: NULL tree");
+    if (!t || t->kind != 0) return fail(ST_ERR_ARG, "st_build: NULL tree (or a min tree: use st_min_build)");
+    tree_lock lk(t);
     device_guard g(t->device);
     cudaStream_t s = (cudaStream_t)stream;
+    CU(st::launch_batch_begin(t, s));   // an earlier failed batch must not cancel this build
     CU(st::launch_check_leaves(t, s));
     CU(st::launch_build(t, s));
-    const int st = fetch_status(t, s, true);
+    const int st = fetch_status(t, s, true, true);
     if (st != ST_OK) return fail(st, "%s", st_status_string(st));
     return ST_OK;
 }
@@ -290,6 +323,7 @@ int st_build(st_tree *t, void *stream)
 int st_build_from_host(st_tree *t, const void *leaves)
 {
     if (!t || !leaves) return fail(ST_ERR_ARG, "st_build_from_host: NULL argument");
+    tree_lock lk(t);
     device_guard g(t->device);
     const size_t half = (size_t)t->n * t->esize;
     CU(cudaMemcpy((char *)t->heap + half, leaves, half, cudaMemcpyHostToDevice));
@@ -299,6 +333,7 @@ int st_build_from_host(st_tree *t, const void *leaves)
 int st_build_from_device(st_tree *t, const void *leaves_dev, void *stream)
 {
     if (!t || !leaves_dev) return fail(ST_ERR_ARG, "st_build_from_device: NULL argument");
+    tree_lock lk(t);
     device_guard g(t->device);
     const size_t half = (size_t)t->n * t->esize;
     void *dst = (char *)t->heap + half;
@@ -311,14 +346,15 @@ int st_build_from_device(st_tree *t, const void *leaves_dev, void *stream)
 int st_update_device(st_tree *t, const int64_t *idx_dev, int64_t ni, const void *vals_dev, int64_t nv,
                      void *stream, int flags)
 {
-    if (!t || ni < 0 || nv < 0) return fail(ST_ERR_ARG, "st_update_device: bad argument");
+    if (!t || ni < 0 || nv < 0 || t->kind != 0) return fail(ST_ERR_ARG, "st_update_device: bad argument");
     if (ni > 0 && nv == 0) return fail(ST_ERR_EMPTY_VALS, "%s", st_status_string(ST_ERR_EMPTY_VALS));
+    tree_lock lk(t);
     device_guard g(t->device);
     cudaStream_t s = (cudaStream_t)stream;
     if (ni == 0 && nv == 0) return ST_OK;
-    CU(st::launch_update(t, idx_dev, ni, vals_dev, nv, nullptr, nullptr, s));
+    CU(st::launch_update(t, idx_dev, ni, vals_dev, nv, nullptr, nullptr, s, (flags & ST_UPDATE_ASSIGN_LEAF) != 0));
     if (flags & ST_UPDATE_SYNC_CHECK) {
-        const int st = fetch_status(t, s, true);
+        const int st = fetch_status(t, s, true, true);
         if (st != ST_OK) return fail(st, "%s", st_status_string(st));
     }
     return ST_OK;
@@ -326,9 +362,15 @@ int st_update_device(st_tree *t, const int64_t *idx_dev, int64_t ni, const void 
 
 int st_update_host(st_tree *t, const int64_t *idx_host, int64_t ni, const void *vals_host, int64_t nv)
 {
+    return st_update_host_ex(t, idx_host, ni, vals_host, nv, ST_UPDATE_DEFAULT);
+}
+
+int st_update_host_ex(st_tree *t, const int64_t *idx_host, int64_t ni, const void *vals_host, int64_t nv, int flags)
+{
     if (!t || ni < 0 || nv < 0) return fail(ST_ERR_ARG, "st_update_host: bad argument");
     if (ni > 0 && nv == 0) return fail(ST_ERR_EMPTY_VALS, "%s", st_status_string(ST_ERR_EMPTY_VALS));
     if (ni == 0 && nv == 0) return ST_OK;
+    tree_lock lk(t);
     device_guard g(t->device);
     dev_buf di, dv;
     scratch_carver sc(t);
@@ -337,16 +379,17 @@ int st_update_host(st_tree *t, const int64_t *idx_host, int64_t ni, const void *
     di.p = sc.take(ni * sizeof(int64_t)); dv.p = sc.take(nv * t->esize);
     CU(cudaMemcpy(di.p, idx_host, ni * sizeof(int64_t), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(dv.p, vals_host, nv * t->esize, cudaMemcpyHostToDevice));
-    return st_update_device(t, (const int64_t *)di.p, ni, dv.p, nv, nullptr, ST_UPDATE_SYNC_CHECK);
+    return st_update_device(t, (const int64_t *)di.p, ni, dv.p, nv, nullptr, flags | ST_UPDATE_SYNC_CHECK);
 }
 
 // ---- sharded-tree helpers ------------------------------------------------------
 int st_update_deltas_device(st_tree *t, const int64_t *idx_dev, int64_t ni, const void *vals_dev, int64_t nv,
                             void *delta_out_dev, void *stream)
 {
-    if (!t || ni < 0 || nv < 0) return fail(ST_ERR_ARG, "st_update_deltas_device: bad argument");
+    if (!t || ni < 0 || nv < 0 || t->kind != 0) return fail(ST_ERR_ARG, "st_update_deltas_device: bad argument");
     if (ni > 0 && nv == 0) return fail(ST_ERR_EMPTY_VALS, "%s", st_status_string(ST_ERR_EMPTY_VALS));
     if (ni == 0 && nv == 0) return ST_OK;
+    tree_lock lk(t);
     device_guard g(t->device);
     CU(st::launch_update(t, idx_dev, ni, vals_dev, nv, delta_out_dev, nullptr, (cudaStream_t)stream));
     return ST_OK;
@@ -356,6 +399,7 @@ int st_apply_deltas_device(st_tree *t, const int64_t *idx_dev, int64_t ni, const
 {
     if (!t || ni < 0 || (ni > 0 && !deltas_dev)) return fail(ST_ERR_ARG, "st_apply_deltas_device: bad argument");
     if (ni == 0) return ST_OK;
+    tree_lock lk(t);
     device_guard g(t->device);
     const bool is_float = (t->dtype == ST_F32 || t->dtype == ST_F64);
     if (is_float && t->n <= 64 && (t->n & (t->n - 1)) == 0 && ni > 4096) {
@@ -375,6 +419,7 @@ int st_top_fold_maps_device(st_tree *t, const void *leaf_dev, int leaf_itemsize,
 {
     if (!t || m < 0 || !recs_dev || (leaf_itemsize != 1 && leaf_itemsize != 8))
         return fail(ST_ERR_ARG, "st_top_fold_maps_device: bad argument");
+    tree_lock lk(t);
     device_guard g(t->device);
     CU(st::launch_fold_by_leaf_maps(t, leaf_dev, leaf_itemsize, deltas_dev, m, (int)chunk_lo, (int)chunk_hi, recs_dev,
                                     (cudaStream_t)stream));
@@ -386,6 +431,7 @@ int st_top_fold_apply_device(st_tree *t, const void *leaf_dev, int leaf_itemsize
 {
     if (!t || m < 0 || !recs_dev || (leaf_itemsize != 1 && leaf_itemsize != 8))
         return fail(ST_ERR_ARG, "st_top_fold_apply_device: bad argument");
+    tree_lock lk(t);
     device_guard g(t->device);
     CU(st::launch_fold_by_leaf_apply(t, leaf_dev, leaf_itemsize, deltas_dev, m, recs_dev, (cudaStream_t)stream));
     return ST_OK;
@@ -412,6 +458,7 @@ int st_shard_plan_device(st_tree *t, const int64_t *ids_dev, int64_t m, int shif
         return fail(ST_ERR_ARG, "st_shard_plan_device: bad argument");
     if (((uintptr_t)shard_out_dev & 7) || ((uintptr_t)slot_out_dev & 15))
         return fail(ST_ERR_ARG, "st_shard_plan_device: shard_out must be 8-byte and slot_out 16-byte aligned");
+    tree_lock lk(t);
     device_guard g(t->device);
     if (t->plan_pending) {   // the scratch area belongs to one plan at a time
         CU(cudaEventSynchronize(t->plan_ev));
@@ -436,6 +483,7 @@ int st_shard_plan_wait(st_tree *t, int result_slot, int shards, int64_t *counts_
 {
     if (!t || !counts_out_host || shards < 1 || shards > 64 || result_slot < 0 || result_slot >= kPlanSlots)
         return fail(ST_ERR_ARG, "st_shard_plan_wait: bad argument");
+    tree_lock lk(t);
     device_guard g(t->device);
     if (t->plan_pending) {
         CU(cudaEventSynchronize(t->plan_ev));   // the plan's kernels only, not what was enqueued behind them
@@ -454,6 +502,7 @@ int st_search_counted_device(const st_tree *t, const void *vals_dev, int64_t m_m
                              int64_t *out_dev, void *stream)
 {
     if (!t || m_max < 0 || !m_dev) return fail(ST_ERR_ARG, "st_search_counted_device: bad argument");
+    tree_lock lk(t);
     device_guard g(t->device);
     CU(st::launch_search(t, vals_dev, m_max, out_dev, (cudaStream_t)stream, m_dev));
     return ST_OK;
@@ -464,6 +513,7 @@ int st_shard_expand_values_device(const st_tree *t, const uint8_t *shard_dev, co
 {
     if (!t || m < 0 || slab_stride < 0 || (m > 0 && (!shard_dev || !slot_dev || !slabs_dev || !out_dev)))
         return fail(ST_ERR_ARG, "st_shard_expand_values_device: bad argument");
+    tree_lock lk(t);
     device_guard g(t->device);
     CU(st::launch_shard_expand_values(t, shard_dev, slot_dev, m, slabs_dev, slab_stride, out_dev, (cudaStream_t)stream));
     return ST_OK;
@@ -475,6 +525,7 @@ int st_shard_expand_indices_device(const st_tree *t, const uint8_t *shard_dev, c
 {
     if (!t || m < 0 || slab_stride < 0 || (m > 0 && (!shard_dev || !slot_dev || !slabs_dev || !out_dev)))
         return fail(ST_ERR_ARG, "st_shard_expand_indices_device: bad argument");
+    tree_lock lk(t);
     device_guard g(t->device);
     CU(st::launch_shard_expand_indices(t, shard_dev, slot_dev, m, slabs_dev, slab_stride, leaves_per_shard, out_dev,
                                        (cudaStream_t)stream));
@@ -485,6 +536,7 @@ int st_route_uniform_device(const st_tree *t, const double *u_dev, int64_t m, in
                             void *residual_out_dev, void *stream)
 {
     if (!t || m < 0) return fail(ST_ERR_ARG, "st_route_uniform_device: bad argument");
+    tree_lock lk(t);
     device_guard g(t->device);
     CU(st::launch_sample(t, u_dev, m, leaf_out_dev, nullptr, residual_out_dev, (cudaStream_t)stream));
     return ST_OK;
@@ -494,9 +546,10 @@ int st_route_uniform_device(const st_tree *t, const double *u_dev, int64_t m, in
 int st_update_gather_host(st_tree *t, const int64_t *idx_host, int64_t ni, const void *vals_host, int64_t nv,
                           void *leaves_out_host)
 {
-    if (!t || ni < 0 || nv < 0) return fail(ST_ERR_ARG, "st_update_gather_host: bad argument");
+    if (!t || ni < 0 || nv < 0 || t->kind != 0) return fail(ST_ERR_ARG, "st_update_gather_host: bad argument");
     if (ni > 0 && nv == 0) return fail(ST_ERR_EMPTY_VALS, "%s", st_status_string(ST_ERR_EMPTY_VALS));
     if (ni == 0 && nv == 0) return ST_OK;
+    tree_lock lk(t);
     device_guard g(t->device);
     {
         // small call: everything through mapped pinned memory, one stream sync, no cudaMemcpy
@@ -514,7 +567,7 @@ int st_update_gather_host(st_tree *t, const int64_t *idx_host, int64_t ni, const
             CU(cudaStreamSynchronize(0));
             const unsigned int f = *(volatile unsigned int *)(hp + o_stat);
             if (f) {
-                CU(cudaMemsetAsync(t->d_status, 0, sizeof(unsigned int), 0));
+                CU(clear_status_words(t, 0));
                 CU(cudaStreamSynchronize(0));
                 const int st = status_from_flags(f);
                 return fail(st, "%s", st_status_string(st));
@@ -533,12 +586,12 @@ int st_update_gather_host(st_tree *t, const int64_t *idx_host, int64_t ni, const
     CU(cudaMemcpyAsync(dv, vals_host, nv * t->esize, cudaMemcpyHostToDevice, 0));
     CU(st::launch_update(t, di, ni, dv, nv, nullptr, nullptr, 0));
     if (ni && leaves_out_host) CU(st::launch_gather(t, di, ni, dl, 0));
-    CU(cudaMemcpyAsync(t->h_status, t->d_status, sizeof(unsigned int), cudaMemcpyDeviceToHost, 0));
+    CU(cudaMemcpyAsync(t->h_status, t->d_status, 32 * sizeof(unsigned int), cudaMemcpyDeviceToHost, 0));
     if (ni && leaves_out_host) CU(cudaMemcpyAsync(leaves_out_host, dl, ni * t->esize, cudaMemcpyDeviceToHost, 0));
     CU(cudaStreamSynchronize(0));
-    const unsigned int f = t->h_status[0];
+    const unsigned int f = t->h_status[0] | t->h_status[ST_SW_STICKY];
     if (f) {
-        CU(cudaMemsetAsync(t->d_status, 0, sizeof(unsigned int), 0));
+        CU(clear_status_words(t, 0));
         CU(cudaStreamSynchronize(0));
         const int st = status_from_flags(f);
         return fail(st, "%s", st_status_string(st));
@@ -550,6 +603,7 @@ int st_update_gather_host(st_tree *t, const int64_t *idx_host, int64_t ni, const
 int st_sample_root_host(const st_tree *t, const double *u_host, int64_t m, int64_t *out_host, void *root_out)
 {
     if (!t || m < 0 || !root_out) return fail(ST_ERR_ARG, "st_sample_root_host: bad argument");
+    tree_lock lk(t);
     device_guard g(t->device);
     {
         const size_t up = 256;
@@ -585,6 +639,7 @@ int st_sample_root_host(const st_tree *t, const double *u_host, int64_t m, int64
 int st_search_device(const st_tree *t, const void *vals_dev, int64_t m, int64_t *out_dev, void *stream)
 {
     if (!t || m < 0) return fail(ST_ERR_ARG, "st_search_device: bad argument");
+    tree_lock lk(t);
     device_guard g(t->device);
     CU(st::launch_search(t, vals_dev, m, out_dev, (cudaStream_t)stream));
     return ST_OK;
@@ -594,6 +649,7 @@ int st_search_host(const st_tree *t, const void *vals_host, int64_t m, int64_t *
 {
     if (!t || m < 0) return fail(ST_ERR_ARG, "st_search_host: bad argument");
     if (m == 0) return ST_OK;
+    tree_lock lk(t);
     device_guard g(t->device);
     {
         const size_t o_out = ((size_t)m * t->esize + 255) / 256 * 256;
@@ -621,6 +677,7 @@ int st_sample_uniform_device(const st_tree *t, const double *u_dev, int64_t m, i
                              void *prio_out_dev, void *stream)
 {
     if (!t || m < 0) return fail(ST_ERR_ARG, "st_sample_uniform_device: bad argument");
+    tree_lock lk(t);
     device_guard g(t->device);
     CU(st::launch_sample(t, u_dev, m, out_dev, prio_out_dev, nullptr, (cudaStream_t)stream));
     return ST_OK;
@@ -630,6 +687,7 @@ int st_sample_uniform_host(const st_tree *t, const double *u_host, int64_t m, in
 {
     if (!t || m < 0) return fail(ST_ERR_ARG, "st_sample_uniform_host: bad argument");
     if (m == 0) return ST_OK;
+    tree_lock lk(t);
     device_guard g(t->device);
     dev_buf du, dout;
     scratch_carver sc(t);
@@ -646,6 +704,7 @@ int st_sample_uniform_host(const st_tree *t, const double *u_host, int64_t m, in
 int st_root_host(const st_tree *t, void *out_scalar)
 {
     if (!t || !out_scalar) return fail(ST_ERR_ARG, "st_root_host: bad argument");
+    tree_lock lk(t);
     device_guard g(t->device);
     CU(st::launch_publish(t, nullptr, t->d_pin, 0));
     CU(cudaStreamSynchronize(0));
@@ -660,6 +719,7 @@ int st_sum_over_host(const st_tree *t, int64_t index_from, int64_t index_to, voi
     if (index_from < 0 || index_from > t->n || index_to < 0 || index_to > t->n)
         return fail(ST_ERR_INDEX, "%s", st_status_string(ST_ERR_INDEX));
     if (index_to - 1 == index_from && index_from >= t->n) return fail(ST_ERR_INDEX, "%s", st_status_string(ST_ERR_INDEX));
+    tree_lock lk(t);
     device_guard g(t->device);
     dev_buf d;
     scratch_carver sc(t);
@@ -677,6 +737,7 @@ int st_strided_sum_device(const st_tree *t, int64_t stride, void *out_dev, int64
 {
     if (!t || stride < 1) return fail(ST_ERR_ARG, "st_strided_sum_device: bad argument");
     if (nout != strided_len(t->n, stride)) return fail(ST_ERR_SIZE, "invalid output size");
+    tree_lock lk(t);
     device_guard g(t->device);
     CU(st::launch_strided_sum(t, stride, out_dev, nout, (cudaStream_t)stream));
     return ST_OK;
@@ -686,6 +747,7 @@ int st_strided_sum_host(const st_tree *t, int64_t stride, void *out_host, int64_
 {
     if (!t || stride < 1) return fail(ST_ERR_ARG, "st_strided_sum_host: bad argument");
     if (nout != strided_len(t->n, stride)) return fail(ST_ERR_SIZE, "invalid output size");
+    tree_lock lk(t);
     device_guard g(t->device);
     dev_buf d;
     scratch_carver sc(t);
@@ -703,6 +765,7 @@ int st_axis_fold_device(const st_tree *t, int64_t A, int64_t R, int64_t C, void 
 {
     if (!t || A < 1 || R < 1 || C < 1) return fail(ST_ERR_ARG, "st_axis_fold_device: bad argument");
     if (A * R * C != t->n) return fail(ST_ERR_SIZE, "axis fold shape does not match the tree size");
+    tree_lock lk(t);
     device_guard g(t->device);
     CU(st::launch_axis_fold(t, A, R, C, out_dev, (cudaStream_t)stream));
     return ST_OK;
@@ -712,6 +775,7 @@ int st_axis_fold_host(const st_tree *t, int64_t A, int64_t R, int64_t C, void *o
 {
     if (!t || A < 1 || R < 1 || C < 1) return fail(ST_ERR_ARG, "st_axis_fold_host: bad argument");
     if (A * R * C != t->n) return fail(ST_ERR_SIZE, "axis fold shape does not match the tree size");
+    tree_lock lk(t);
     device_guard g(t->device);
     dev_buf d;
     const size_t bytes = (size_t)A * C * fold_out_size(t);
@@ -728,6 +792,7 @@ int st_axis_fold_host(const st_tree *t, int64_t A, int64_t R, int64_t C, void *o
 int st_poll_status(st_tree *t, void *stream, int clear)
 {
     if (!t) return fail(ST_ERR_ARG, "st_poll_status: NULL tree");
+    tree_lock lk(t);
     device_guard g(t->device);
     const int st = fetch_status(t, (cudaStream_t)stream, clear != 0);
     if (st != ST_OK) return fail(st, "%s", st_status_string(st));
@@ -740,6 +805,7 @@ int st_poll_status(st_tree *t, void *stream, int clear)
 int st_set_l2_persistence(st_tree *t, void *stream, int64_t bytes, int64_t *granted)
 {
     if (!t) return fail(ST_ERR_ARG, "st_set_l2_persistence: NULL tree");
+    tree_lock lk(t);
     device_guard g(t->device);
     if (granted) *granted = 0;
     cudaDeviceProp prop;
@@ -773,6 +839,7 @@ int st_set_l2_persistence(st_tree *t, void *stream, int64_t bytes, int64_t *gran
 int st_set_profiling(st_tree *t, int enable)
 {
     if (!t) return fail(ST_ERR_ARG, "st_set_profiling: NULL tree");
+    tree_lock lk(t);
     device_guard g(t->device);
     if (enable && !t->prof_ev[0])
         for (int k = 0; k < 8; ++k) CU(cudaEventCreate(&t->prof_ev[k]));
@@ -791,11 +858,259 @@ int st_update_breakdown(const st_tree *t, double out_ms[8])
 int st_update_stats(st_tree *t, void *stream, int64_t out[4])
 {
     if (!t || !out) return fail(ST_ERR_ARG, "st_update_stats: bad argument");
+    tree_lock lk(t);
     device_guard g(t->device);
     cudaStream_t s = (cudaStream_t)stream;
     CU(cudaMemcpyAsync(t->h_status, t->d_status, 64 * sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     for (int i = 0; i < 4; ++i) out[i] = t->h_status[4 + i];
+    return ST_OK;
+}
+
+// ---- PER step ----------------------------------------------------------------------------------
+int st_sample_weights_device(const st_tree *t, const double *u_dev, int64_t m, int64_t *out_dev,
+                             void *prio_out_dev, void *prob_out_dev, void *stream)
+{
+    if (!t || m < 0 || t->kind != 0) return fail(ST_ERR_ARG, "st_sample_weights_device: bad argument");
+    tree_lock lk(t);
+    device_guard g(t->device);
+    CU(st::launch_sample(t, u_dev, m, out_dev, prio_out_dev, nullptr, (cudaStream_t)stream, prob_out_dev));
+    return ST_OK;
+}
+
+int st_per_step_device(st_tree *t, const int64_t *idx_dev, int64_t ni, const void *vals_dev, int64_t nv,
+                       const double *u_dev, int64_t m, int64_t *out_idx_dev, void *out_prio_dev,
+                       void *out_prob_dev, void *stream)
+{
+    if (!t || ni < 0 || nv < 0 || m < 0 || t->kind != 0) return fail(ST_ERR_ARG, "st_per_step_device: bad argument");
+    if (ni > 0 && nv == 0) return fail(ST_ERR_EMPTY_VALS, "%s", st_status_string(ST_ERR_EMPTY_VALS));
+    tree_lock lk(t);
+    device_guard g(t->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (ni > 0 || nv > 0) CU(st::launch_update(t, idx_dev, ni, vals_dev, nv, nullptr, nullptr, s));
+    CU(st::launch_sample(t, u_dev, m, out_idx_dev, out_prio_dev, nullptr, s, out_prob_dev));
+    return ST_OK;
+}
+
+int st_host_alloc(int64_t bytes, void **out)
+{
+    if (!out || bytes <= 0) return fail(ST_ERR_ARG, "st_host_alloc: bad argument");
+    *out = nullptr;
+    CU(cudaHostAlloc(out, (size_t)bytes, cudaHostAllocPortable));
+    return ST_OK;
+}
+
+int st_host_free(void *p)
+{
+    if (p) CU(cudaFreeHost(p));
+    return ST_OK;
+}
+
+namespace {
+int prob_size(const st_tree *t) { return t->dtype == ST_F32 ? 4 : 8; }
+
+int host_pipeline_init(st_tree *t)
+{
+    if (t->hs_main) return ST_OK;
+    CU(cudaStreamCreateWithFlags(&t->hs_in, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&t->hs_main, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&t->hs_out, cudaStreamNonBlocking));
+    for (auto &h : t->hs) {
+        CU(cudaEventCreateWithFlags(&h.ev_in, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&h.ev_free, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&h.ev_done, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&h.ev_read, cudaEventDisableTiming));
+        CU(cudaMallocHost((void **)&h.h_flag, 32 * sizeof(unsigned int)));
+    }
+    return ST_OK;
+}
+}  // namespace
+
+int st_per_step_host_submit(st_tree *t, int slot, const int64_t *idx_host, int64_t ni, const void *vals_host,
+                            int64_t nv, const double *u_host, int64_t m, int64_t *out_idx_host,
+                            void *out_prio_host, void *out_prob_host)
+{
+    if (!t || slot < 0 || slot > 1 || ni < 0 || nv < 0 || m < 0 || t->kind != 0 || (m > 0 && (!u_host || !out_idx_host)))
+        return fail(ST_ERR_ARG, "st_per_step_host_submit: bad argument");
+    if (ni > 0 && nv == 0) return fail(ST_ERR_EMPTY_VALS, "%s", st_status_string(ST_ERR_EMPTY_VALS));
+    tree_lock lk(t);
+    device_guard g(t->device);
+    { const int st = host_pipeline_init(t); if (st != ST_OK) return st; }
+    st_tree::host_slot &h = t->hs[slot];
+    if (h.busy) {   // the slot's previous step has not been collected: finish it first (its status is dropped)
+        CU(cudaEventSynchronize(h.ev_read));
+        h.busy = 0;
+    }
+    auto rnd = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t es = (size_t)t->esize, ps = (size_t)prob_size(t);
+    const size_t o_idx = 0, o_val = o_idx + rnd(ni * 8), o_u = o_val + rnd(nv * es), o_out = o_u + rnd(m * 8),
+                 o_prio = o_out + rnd(m * 8), o_prob = o_prio + rnd(m * es), total = o_prob + rnd(m * ps);
+    if (total > h.bytes) {
+        CU(cudaDeviceSynchronize());
+        if (h.dev) cudaFree(h.dev);
+        h.dev = nullptr; h.bytes = 0;
+        CU(cudaMalloc(&h.dev, total));
+        h.bytes = total;
+    }
+    // make sure the update workspace never reallocates while the other slot's kernels are in flight
+    if (ni > t->reserved_batch || !t->ws.base) {
+        const int st = st_reserve(t, ni > 0 ? ni : 1);
+        if (st != ST_OK) return st;
+    }
+    char *d = (char *)h.dev;
+    CU(cudaStreamWaitEvent(t->hs_in, h.ev_free, 0));    // the slot's previous inputs have been consumed
+    if (ni) CU(cudaMemcpyAsync(d + o_idx, idx_host, ni * 8, cudaMemcpyHostToDevice, t->hs_in));
+    if (nv) CU(cudaMemcpyAsync(d + o_val, vals_host, nv * es, cudaMemcpyHostToDevice, t->hs_in));
+    if (m) CU(cudaMemcpyAsync(d + o_u, u_host, m * 8, cudaMemcpyHostToDevice, t->hs_in));
+    CU(cudaEventRecord(h.ev_in, t->hs_in));
+    CU(cudaStreamWaitEvent(t->hs_main, h.ev_in, 0));
+    CU(cudaStreamWaitEvent(t->hs_main, h.ev_read, 0));  // the slot's previous results have left the device
+    if (ni > 0 || nv > 0)
+        CU(st::launch_update(t, (const int64_t *)(d + o_idx), ni, d + o_val, nv, nullptr, nullptr, t->hs_main));
+    if (m)
+        CU(st::launch_sample(t, (const double *)(d + o_u), m, (int64_t *)(d + o_out), out_prio_host ? d + o_prio : nullptr,
+                             nullptr, t->hs_main, out_prob_host ? d + o_prob : nullptr));
+    CU(cudaEventRecord(h.ev_free, t->hs_main));
+    CU(cudaEventRecord(h.ev_done, t->hs_main));
+    CU(cudaStreamWaitEvent(t->hs_out, h.ev_done, 0));
+    if (m) {
+        CU(cudaMemcpyAsync(out_idx_host, d + o_out, m * 8, cudaMemcpyDeviceToHost, t->hs_out));
+        if (out_prio_host) CU(cudaMemcpyAsync(out_prio_host, d + o_prio, m * es, cudaMemcpyDeviceToHost, t->hs_out));
+        if (out_prob_host) CU(cudaMemcpyAsync(out_prob_host, d + o_prob, m * ps, cudaMemcpyDeviceToHost, t->hs_out));
+    }
+    CU(cudaMemcpyAsync(h.h_flag, t->d_status, 32 * sizeof(unsigned int), cudaMemcpyDeviceToHost, t->hs_out));
+    CU(cudaEventRecord(h.ev_read, t->hs_out));
+    h.busy = 1;
+    return ST_OK;
+}
+
+int st_per_step_host_wait(st_tree *t, int slot)
+{
+    if (!t || slot < 0 || slot > 1) return fail(ST_ERR_ARG, "st_per_step_host_wait: bad argument");
+    tree_lock lk(t);
+    device_guard g(t->device);
+    st_tree::host_slot &h = t->hs[slot];
+    if (!h.busy) return ST_OK;
+    CU(cudaEventSynchronize(h.ev_read));
+    h.busy = 0;
+    const unsigned int f = h.h_flag[0] | h.h_flag[ST_SW_STICKY];
+    if (f) {
+        CU(cudaStreamSynchronize(t->hs_main));
+        CU(clear_status_words(t, t->hs_main));
+        CU(cudaStreamSynchronize(t->hs_main));
+        const int st = status_from_flags(f);
+        return fail(st, "%s", st_status_string(st));
+    }
+    return ST_OK;
+}
+
+// ---- in-place leaf arithmetic ---------------------------------------------------------------------
+int st_inplace_device(st_tree *t, int op, const void *scalar_host, const void *operand_dev, int64_t operand_len,
+                      void *stream)
+{
+    if (!t || t->kind != 0 || op < ST_OP_ADD || op > ST_OP_FILL || (!scalar_host && !operand_dev))
+        return fail(ST_ERR_ARG, "st_inplace_device: bad argument");
+    if (operand_dev && operand_len != t->n) return fail(ST_ERR_SIZE, "operand must have the size of the array");
+    const bool is_f = (t->dtype == ST_F32 || t->dtype == ST_F64);
+    if (op == ST_OP_DIV && !is_f) return fail(ST_ERR_DTYPE, "in-place true division needs a floating-point tree");
+    if (op == ST_OP_FILL && operand_dev) return fail(ST_ERR_ARG, "st_inplace_device: fill takes a scalar");
+    tree_lock lk(t);
+    device_guard g(t->device);
+    CU(st::launch_inplace(t, op, scalar_host, operand_dev, (cudaStream_t)stream));
+    return ST_OK;
+}
+
+// ---- min tree -------------------------------------------------------------------------------------
+int st_min_create(int64_t n, int dtype, int device, void *external_heap, st_tree **out)
+{
+    const int st = st_create(n, dtype, device, external_heap, out);
+    if (st != ST_OK) return st;
+    st_tree *t = *out;
+    device_guard g(device);
+    t->kind = 1;
+    cudaError_t e = cudaMalloc(&t->aux, (size_t)n * sizeof(int));
+    if (e == cudaSuccess) e = st::launch_min_init(t, 0);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+    if (e != cudaSuccess) {
+        st_destroy(t);
+        *out = nullptr;
+        return cuda_fail(e, "st_min_create");
+    }
+    return ST_OK;
+}
+
+int st_min_update_device(st_tree *t, const int64_t *idx_dev, int64_t ni, const void *vals_dev, int64_t nv, void *stream)
+{
+    if (!t || t->kind != 1 || ni < 0 || nv < 0) return fail(ST_ERR_ARG, "st_min_update_device: bad argument");
+    if (ni > 0 && nv == 0) return fail(ST_ERR_EMPTY_VALS, "%s", st_status_string(ST_ERR_EMPTY_VALS));
+    if (ni > 0x7fffffffLL) return fail(ST_ERR_TOO_LARGE, "st_min_update_device: batch too large");
+    tree_lock lk(t);
+    device_guard g(t->device);
+    CU(st::launch_min_update(t, idx_dev, ni, vals_dev, nv, (cudaStream_t)stream));
+    return ST_OK;
+}
+
+int st_min_update_host(st_tree *t, const int64_t *idx_host, int64_t ni, const void *vals_host, int64_t nv)
+{
+    if (!t || t->kind != 1 || ni < 0 || nv < 0) return fail(ST_ERR_ARG, "st_min_update_host: bad argument");
+    if (ni > 0 && nv == 0) return fail(ST_ERR_EMPTY_VALS, "%s", st_status_string(ST_ERR_EMPTY_VALS));
+    if (ni == 0) return ST_OK;
+    tree_lock lk(t);
+    device_guard g(t->device);
+    scratch_carver sc(t);
+    sc.add(ni * sizeof(int64_t)); sc.add(nv * t->esize);
+    CU(sc.commit());
+    int64_t *di = (int64_t *)sc.take(ni * sizeof(int64_t));
+    void *dv = sc.take(nv * t->esize);
+    CU(cudaMemcpyAsync(di, idx_host, ni * sizeof(int64_t), cudaMemcpyHostToDevice, 0));
+    CU(cudaMemcpyAsync(dv, vals_host, nv * t->esize, cudaMemcpyHostToDevice, 0));
+    CU(st::launch_min_update(t, di, ni, dv, nv, 0));
+    const int st = fetch_status(t, 0, true, true);
+    if (st != ST_OK) return fail(st, "%s", st_status_string(st));
+    return ST_OK;
+}
+
+int st_min_build(st_tree *t, void *stream)
+{
+    if (!t || t->kind != 1) return fail(ST_ERR_ARG, "st_min_build: bad argument");
+    tree_lock lk(t);
+    device_guard g(t->device);
+    CU(st::launch_min_build(t, (cudaStream_t)stream));
+    return ST_OK;
+}
+
+// ---- bookkeeping ------------------------------------------------------------------------------------
+int st_update_counters(st_tree *t, void *stream, int64_t out[2], int reset)
+{
+    if (!t || !out) return fail(ST_ERR_ARG, "st_update_counters: bad argument");
+    tree_lock lk(t);
+    device_guard g(t->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    CU(cudaMemcpyAsync(t->h_status, t->d_status, 32 * sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    out[0] = t->stat_updates;
+    out[1] = (int64_t)t->h_status[ST_SW_ZERO_DELTA];
+    if (reset) {
+        t->stat_updates = 0;
+        CU(cudaMemsetAsync(t->d_status + ST_SW_ZERO_DELTA, 0, sizeof(unsigned int), s));
+        CU(cudaStreamSynchronize(s));
+    }
+    return ST_OK;
+}
+
+int st_reserve_sharded(st_tree *t, int64_t max_batch, int shards)
+{
+    if (!t || max_batch < 1 || shards < 1 || shards > 64) return fail(ST_ERR_ARG, "st_reserve_sharded: bad argument");
+    tree_lock lk(t);
+    device_guard g(t->device);
+    { const int st = st_reserve(t, max_batch); if (st != ST_OK) return st; }
+    size_t need = st::shard_plan_scratch_bytes(max_batch, shards);
+    const size_t nchunks = (size_t)((max_batch + 1023) / 1024);
+    const size_t recs = nchunks * (size_t)(shards > 1 ? shards - 1 : 1) * 64;   // top-fold records (<= 64 B each)
+    if (recs > need) need = recs;
+    scratch_carver c(t);
+    c.add(need);
+    CU(c.commit());
     return ST_OK;
 }
 

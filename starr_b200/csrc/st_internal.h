@@ -3,6 +3,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+#include <mutex>
+
 #include "../../include/starr_b200.h"
 
 // Device-side status word bits (written by validation kernels, read by every later kernel
@@ -10,6 +13,11 @@
 #define STF_NEG_VALS 1u
 #define STF_NEG_ARRAY 2u
 #define STF_INDEX 4u
+// status word 0 holds the flags of the batch IN FLIGHT (every later kernel of that batch returns at once
+// when it is set); the first kernel of the next batch moves them to the sticky word, which st_poll_status
+// reports, so one failed batch does not silently drop the batches behind it.
+#define ST_SW_STICKY 21
+#define ST_SW_ZERO_DELTA 20
 
 struct st_workspace {
     void *base = nullptr;  // one cudaMalloc, carved up per batch
@@ -23,6 +31,8 @@ struct st_tree {
     int esize = 0;
     int depth = 0;        // level of the deepest heap node: floor(log2(2n-1))
     void *heap = nullptr; // device, 2n elements
+    int kind = 0;         // 0 = sum tree, 1 = min tree (st_min_create)
+    void *aux = nullptr;  // min tree: int tag[n] (last-writer claims)
     bool owns_heap = false;
     unsigned int *d_status = nullptr;  // device status word (+ spare counters), 64 words
     unsigned int *h_status = nullptr;  // pinned host mirror, 64 words
@@ -41,6 +51,20 @@ struct st_tree {
     size_t cub_bytes = 0;
     int sm_count = 148;
     int coop_ok = 0;
+    int part_occ = 0;          // resident CTAs per SM of the cooperative partition kernel (0 = not queried yet)
+    // The reference's functions hold the GIL (SURVEY 8b "Threading"); here every entry point that touches the
+    // handle's host-side state or staging areas takes this lock, so concurrent callers on ONE tree serialise.
+    std::recursive_mutex mu;
+    int64_t stat_updates = 0;  // updates submitted since the last st_update_counters(reset)
+    // pipelined host step (st_per_step_host_submit / _wait): two slots of device staging + streams + events
+    struct host_slot {
+        void *dev = nullptr;       // idx | vals | u | out_idx | out_prio | out_prob
+        size_t bytes = 0;
+        cudaEvent_t ev_in = nullptr, ev_free = nullptr, ev_done = nullptr, ev_read = nullptr;
+        unsigned int *h_flag = nullptr;   // pinned: validation flags of the slot's batch
+        int busy = 0;
+    } hs[2];
+    cudaStream_t hs_in = nullptr, hs_main = nullptr, hs_out = nullptr;
     // optional per-phase timing of the update pipeline (st_set_profiling)
     int profile = 0;
     cudaEvent_t prof_ev[8] = {};
@@ -51,26 +75,53 @@ struct st_tree {
 namespace st {
 
 // process-wide count of kernels of THIS library that were launched (bench.py's gpu_launches)
-extern unsigned long long g_kernel_launches;
+extern std::atomic<unsigned long long> g_kernel_launches;
 
+// run `f` once per CUDA device (function attributes are per device); thread-safe
+struct per_device_once {
+    std::atomic<unsigned long long> mask{0};
+    std::mutex mu;
+    template <typename F> cudaError_t run(int dev, F f)
+    {
+        const unsigned long long bit = 1ull << (dev & 63);
+        if (mask.load(std::memory_order_acquire) & bit) return cudaSuccess;
+        std::lock_guard<std::mutex> g(mu);
+        if (mask.load(std::memory_order_relaxed) & bit) return cudaSuccess;
+        cudaError_t e = f();
+        if (e != cudaSuccess) return e;
+        mask.fetch_or(bit, std::memory_order_release);
+        return cudaSuccess;
+    }
+};
+
+cudaError_t launch_batch_begin(st_tree *t, cudaStream_t s);   // flags of the previous batch -> sticky word
 cudaError_t launch_check_leaves(st_tree *t, cudaStream_t s);  // sets STF_NEG_ARRAY
 cudaError_t launch_build(st_tree *t, cudaStream_t s);         // skipped on device if status != 0
 // m_dev (nullable): device-side query count, the launch covers min(m, *m_dev) queries
 cudaError_t launch_search(const st_tree *t, const void *vals, int64_t m, int64_t *out, cudaStream_t s,
                           const unsigned int *m_dev = nullptr);
+// prob (nullable): prio / root in the tree dtype for f32 / f64, in float64 for integer trees
 cudaError_t launch_sample(const st_tree *t, const double *u, int64_t m, int64_t *out, void *prio,
-                          void *resid, cudaStream_t s);
+                          void *resid, cudaStream_t s, void *prob = nullptr);
 cudaError_t launch_publish(const st_tree *t, void *dst_status, void *dst_root, cudaStream_t s);  // tiny: status word + root
 cudaError_t launch_gather(const st_tree *t, const int64_t *idx, int64_t m, void *out, cudaStream_t s);
+// leaves = leaves (op) scalar | operand[n] (st_inplace_op); the tree is NOT rebuilt
+cudaError_t launch_inplace(st_tree *t, int op, const void *scalar_host, const void *operand, cudaStream_t s);
 cudaError_t launch_sum_over(const st_tree *t, int64_t a, int64_t b, void *out_dev, cudaStream_t s);
 cudaError_t launch_strided_sum(const st_tree *t, int64_t stride, void *out, int64_t nout, cudaStream_t s);
 cudaError_t launch_axis_fold(const st_tree *t, int64_t A, int64_t R, int64_t C, void *out, cudaStream_t s);
 
+// min tree (st_mintree.cu)
+cudaError_t launch_min_init(st_tree *t, cudaStream_t s);
+cudaError_t launch_min_build(st_tree *t, cudaStream_t s);
+cudaError_t launch_min_update(st_tree *t, const int64_t *idx, int64_t ni, const void *vals, int64_t nv, cudaStream_t s);
+
 size_t update_workspace_bytes(const st_tree *t, int64_t batch);
 // delta_out (nullable): receives d_j in batch order.  deltas_in (nullable): apply the given
 // per-update differences to the proper ancestors only (vals ignored, leaves untouched).
+// assign: the leaf becomes vals[j] itself instead of fl(leaf + fl(vals[j] - leaf)) (starr.experimental twin)
 cudaError_t launch_update(st_tree *t, const int64_t *idx, int64_t ni, const void *vals, int64_t nv,
-                          void *delta_out, const void *deltas_in, cudaStream_t s);
+                          void *delta_out, const void *deltas_in, cudaStream_t s, bool assign = false);
 int64_t update_max_chunk();
 // tiny power-of-two float tree: ordered fold of all m differences into the ancestors of leaf[j]
 cudaError_t launch_fold_by_leaf(st_tree *t, const int64_t *leaf, const void *deltas, int64_t m, cudaStream_t s);

@@ -8,9 +8,32 @@
 // on the single device buffer heap[2n] described in include/starr_b200.h.
 // All of them are HBM/L2 latency- or bandwidth-bound gathers and streams; there is no
 // contraction anywhere, so no tensor cores.
+#include <cstring>
+
 #include "st_common.cuh"
 
 namespace st {
+
+// =========================================================================================
+// first kernel of a batch: the previous batch's validation flags move to the sticky word
+// =========================================================================================
+__global__ void batch_begin_kernel(unsigned int *status)
+{
+    if (threadIdx.x == 0) {
+        const unsigned int f = status[0];
+        if (f) {
+            status[ST_SW_STICKY] |= f;
+            status[0] = 0;
+        }
+    }
+}
+
+cudaError_t launch_batch_begin(st_tree *t, cudaStream_t s)
+{
+    ++g_kernel_launches;
+    batch_begin_kernel<<<1, 32, 0, s>>>(t->d_status);
+    return cudaGetLastError();
+}
 
 // =========================================================================================
 // leaf validation (pyx:58-59: min(array) < 0 -> ValueError before any write)
@@ -231,11 +254,22 @@ template <typename T> __device__ __forceinline__ T scale_uniform(T root, double 
     }
 }
 
+// NumPy's `x[idx] / x.sum()`: float32 / float32 -> one float32 division, float64 likewise, integer
+// dtypes -> true division in float64 (README.md:7 PER importance weights are built from this ratio)
+template <typename T> struct prob_type { using type = double; };
+template <> struct prob_type<float> { using type = float; };
+template <typename T> __device__ __forceinline__ typename prob_type<T>::type prob_div(T p, T total)
+{
+    if constexpr (sizeof(T) == 4 && is_float_t<T>::value) return __fdiv_rn(p, total);
+    else return __ddiv_rn((double)p, (double)total);
+}
+
 template <typename T, bool STAGE, bool UNIFORM, int SEARCH_THREADS, int SEARCH_Q>
 __global__ void __launch_bounds__(SEARCH_THREADS)
 search_kernel(const T *__restrict__ H, uint32_t n, int depth, const void *__restrict__ in,
               int64_t m, int64_t *__restrict__ out, T *__restrict__ prio, T *__restrict__ resid,
-              uint32_t stage_nodes, const unsigned int *__restrict__ m_dev)
+              uint32_t stage_nodes, const unsigned int *__restrict__ m_dev,
+              typename prob_type<T>::type *__restrict__ prob)
 {
     if (m_dev) {   // the host did not know the count when it launched (sharded sample: st_shard_plan_device)
         const int64_t md = (int64_t)*m_dev;
@@ -294,7 +328,12 @@ search_kernel(const T *__restrict__ H, uint32_t n, int depth, const void *__rest
             const int64_t i = base + threadIdx.x + (int64_t)q * SEARCH_THREADS;
             if (i < m) {
                 out[i] = (int64_t)h[q] - (int64_t)n;
-                if (prio) prio[i] = __ldcg(H + h[q]);
+                if (prio || prob) {
+                    const T pv = __ldcg(H + h[q]);
+                    if (prio) prio[i] = pv;
+                    // importance-sampling probability p_i / total: what `x[idx] / x.sum()` gives on the host
+                    if constexpr (UNIFORM) { if (prob) prob[i] = prob_div<T>(pv, root); }
+                }
                 if (resid) resid[i] = p[q];   // prefix left over inside the found leaf's subtree
             }
         }
@@ -303,7 +342,7 @@ search_kernel(const T *__restrict__ H, uint32_t n, int depth, const void *__rest
 
 template <typename T, bool UNIFORM, int THREADS, int Q>
 static cudaError_t launch_search_cfg(const st_tree *t, const void *in, int64_t m, int64_t *out, void *prio,
-                                     void *resid, cudaStream_t s, const unsigned int *m_dev)
+                                     void *resid, cudaStream_t s, const unsigned int *m_dev, void *prob)
 {
     const uint32_t n = (uint32_t)t->n;
     const T *H = (const T *)t->heap;
@@ -320,32 +359,33 @@ static cudaError_t launch_search_cfg(const st_tree *t, const void *in, int64_t m
     if (stage) {
         const size_t smem = (size_t)stage_nodes * sizeof(T);
         auto kern = search_kernel<T, true, UNIFORM, THREADS, Q>;
-        static int attr_dev = -1;   // function attributes are per device
-        if (attr_dev != t->device) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
-            if (e != cudaSuccess) return e;
-            attr_dev = t->device;
-        }
+        static per_device_once attr_once;   // function attributes are per device
+        cudaError_t ea = attr_once.run(t->device, [&] {
+            return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+        });
+        if (ea != cudaSuccess) return ea;
         unsigned g = grid_for(m, (int)per_block, (int64_t)t->sm_count * 3);
         ++g_kernel_launches;
-        kern<<<g, THREADS, smem, s>>>(H, n, t->depth, in, m, out, (T *)prio, (T *)resid, stage_nodes, m_dev);
+        kern<<<g, THREADS, smem, s>>>(H, n, t->depth, in, m, out, (T *)prio, (T *)resid, stage_nodes, m_dev,
+                                      (typename prob_type<T>::type *)prob);
     } else {
         unsigned g = grid_for(m, (int)per_block, (int64_t)t->sm_count * 4);
         ++g_kernel_launches;
         search_kernel<T, false, UNIFORM, THREADS, Q><<<g, THREADS, 0, s>>>(H, n, t->depth, in, m, out, (T *)prio,
-                                                                          (T *)resid, 0, m_dev);
+                                                                          (T *)resid, 0, m_dev,
+                                                                          (typename prob_type<T>::type *)prob);
     }
     return cudaGetLastError();
 }
 
 template <typename T, bool UNIFORM>
 static cudaError_t launch_search_t(const st_tree *t, const void *in, int64_t m, int64_t *out, void *prio,
-                                   void *resid, cudaStream_t s, const unsigned int *m_dev = nullptr)
+                                   void *resid, cudaStream_t s, const unsigned int *m_dev = nullptr, void *prob = nullptr)
 {
     if (m <= 0) return cudaSuccess;
     if (m >= (int64_t)t->sm_count * SEARCH_THREADS_BIG * SEARCH_Q_BIG / 4)
-        return launch_search_cfg<T, UNIFORM, SEARCH_THREADS_BIG, SEARCH_Q_BIG>(t, in, m, out, prio, resid, s, m_dev);
-    return launch_search_cfg<T, UNIFORM, SEARCH_THREADS_SMALL, SEARCH_Q_SMALL>(t, in, m, out, prio, resid, s, m_dev);
+        return launch_search_cfg<T, UNIFORM, SEARCH_THREADS_BIG, SEARCH_Q_BIG>(t, in, m, out, prio, resid, s, m_dev, prob);
+    return launch_search_cfg<T, UNIFORM, SEARCH_THREADS_SMALL, SEARCH_Q_SMALL>(t, in, m, out, prio, resid, s, m_dev, prob);
 }
 
 cudaError_t launch_search(const st_tree *t, const void *vals, int64_t m, int64_t *out, cudaStream_t s,
@@ -356,9 +396,9 @@ cudaError_t launch_search(const st_tree *t, const void *vals, int64_t m, int64_t
 }
 
 cudaError_t launch_sample(const st_tree *t, const double *u, int64_t m, int64_t *out, void *prio,
-                          void *resid, cudaStream_t s)
+                          void *resid, cudaStream_t s, void *prob)
 {
-    ST_DISPATCH(t->dtype, return (launch_search_t<T, true>(t, u, m, out, prio, resid, s)));
+    ST_DISPATCH(t->dtype, return (launch_search_t<T, true>(t, u, m, out, prio, resid, s, nullptr, prob)));
     return cudaSuccess;
 }
 
@@ -370,7 +410,7 @@ __global__ void publish_kernel(const T *__restrict__ H, const unsigned int *__re
                                unsigned int *dst_status, T *dst_root)
 {
     if (threadIdx.x == 0) {
-        if (dst_status) *dst_status = *status;
+        if (dst_status) *dst_status = status[0] | status[ST_SW_STICKY];
         if (dst_root) *dst_root = H[1];
     }
 }
@@ -407,6 +447,91 @@ cudaError_t launch_gather(const st_tree *t, const int64_t *idx, int64_t m, void 
             (const T *)t->heap + t->n, t->n, idx, m, (T *)out);
     });
     return cudaGetLastError();
+}
+
+// =========================================================================================
+// in-place leaf arithmetic (reference sumtree_array.py:150-173 in-place ufuncs, :202-205 fill):
+// leaves = leaves (op) operand, operand a scalar or an array of n elements of the tree dtype.
+// One IEEE operation per element in the element type (integers wrap like NumPy's), so the leaves
+// are bit-identical to what the host ufunc writes; the caller rebuilds the tree afterwards.
+// =========================================================================================
+template <typename T, int OP> __device__ __forceinline__ T inplace_apply(T a, T b)
+{
+    if constexpr (OP == ST_OP_ADD) return t_add<T>(a, b);
+    else if constexpr (OP == ST_OP_SUB) return t_sub<T>(a, b);
+    else if constexpr (OP == ST_OP_MUL) {
+        if constexpr (sizeof(T) == 4 && is_float_t<T>::value) return __fmul_rn(a, b);
+        else if constexpr (is_float_t<T>::value) return __dmul_rn(a, b);
+        else return (T)(a * b);
+    } else if constexpr (OP == ST_OP_DIV) {
+        if constexpr (sizeof(T) == 4 && is_float_t<T>::value) return __fdiv_rn(a, b);
+        else if constexpr (is_float_t<T>::value) return __ddiv_rn(a, b);
+        else return a;   // integer true_divide does not exist in place (NumPy raises); rejected by the launcher
+    } else return b;     // ST_OP_FILL
+}
+
+template <typename T, int OP, bool ARRAY>
+__global__ void __launch_bounds__(256) inplace_kernel(T *__restrict__ x, int64_t n, T scalar, const T *__restrict__ y)
+{
+    constexpr int VEC = 16 / (int)sizeof(T);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // the leaves start at heap + n: 16-byte aligned only when n * sizeof(T) is; peel to alignment
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(x);
+    int64_t head = (int64_t)(((16 - (addr & 15)) & 15) / sizeof(T));
+    if (head > n) head = n;
+    bool vec_ok = true;
+    if constexpr (ARRAY) vec_ok = ((reinterpret_cast<uintptr_t>(y + head) & 15) == 0);
+    const int64_t nvec = vec_ok ? (n - head) / VEC : 0;
+    int4 *x4 = reinterpret_cast<int4 *>(x + head);
+    const int4 *y4 = reinterpret_cast<const int4 *>(y + head);
+    for (int64_t i = tid; i < nvec; i += stride) {
+        int4 q;
+        if constexpr (OP != ST_OP_FILL) q = x4[i];
+        int4 r;
+        if constexpr (ARRAY) r = __ldg(y4 + i);
+        T *e = reinterpret_cast<T *>(&q);
+        const T *f = reinterpret_cast<const T *>(&r);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) e[j] = inplace_apply<T, OP>(e[j], ARRAY ? f[j] : scalar);
+        x4[i] = q;
+    }
+    for (int64_t j = tid; j < head; j += stride) x[j] = inplace_apply<T, OP>(x[j], ARRAY ? y[j] : scalar);
+    for (int64_t j = head + nvec * VEC + tid; j < n; j += stride) x[j] = inplace_apply<T, OP>(x[j], ARRAY ? y[j] : scalar);
+}
+
+template <typename T, int OP>
+static cudaError_t launch_inplace_op(st_tree *t, const void *scalar_host, const void *operand, cudaStream_t s)
+{
+    T *leaves = (T *)t->heap + t->n;
+    const unsigned g = grid_for(t->n, 256 * (16 / (int)sizeof(T)) * 4, (int64_t)t->sm_count * 16);
+    ++g_kernel_launches;
+    if (operand) {
+        inplace_kernel<T, OP, true><<<g, 256, 0, s>>>(leaves, t->n, T(0), (const T *)operand);
+    } else {
+        T sc;
+        memcpy(&sc, scalar_host, sizeof(T));
+        inplace_kernel<T, OP, false><<<g, 256, 0, s>>>(leaves, t->n, sc, nullptr);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_inplace(st_tree *t, int op, const void *scalar_host, const void *operand, cudaStream_t s)
+{
+    const bool is_f = (t->dtype == ST_F32 || t->dtype == ST_F64);
+    if (op == ST_OP_DIV && !is_f) return cudaErrorInvalidValue;
+    if (op == ST_OP_FILL && operand) return cudaErrorInvalidValue;
+    ST_DISPATCH(t->dtype, {
+        switch (op) {
+            case ST_OP_ADD: return launch_inplace_op<T, ST_OP_ADD>(t, scalar_host, operand, s);
+            case ST_OP_SUB: return launch_inplace_op<T, ST_OP_SUB>(t, scalar_host, operand, s);
+            case ST_OP_MUL: return launch_inplace_op<T, ST_OP_MUL>(t, scalar_host, operand, s);
+            case ST_OP_DIV: return launch_inplace_op<T, ST_OP_DIV>(t, scalar_host, operand, s);
+            case ST_OP_FILL: return launch_inplace_op<T, ST_OP_FILL>(t, scalar_host, operand, s);
+            default: return cudaErrorInvalidValue;
+        }
+    });
+    return cudaSuccess;
 }
 
 // =========================================================================================

@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(256) leaf_pass_kernel(T *__restrict__ H, uint3
                                                         const int *__restrict__ js, int m,
                                                         const T *__restrict__ vals, uint64_t nv, uint64_t j0,
                                                         T *__restrict__ dj, T *__restrict__ ds,
-                                                        const unsigned int *status)
+                                                        unsigned int *status, bool assign)
 {
     if (status[SW_STATUS]) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -190,17 +190,20 @@ __global__ void __launch_bounds__(256) leaf_pass_kernel(T *__restrict__ H, uint3
     const uint32_t h = key_to_heap(key, two_n);
     T cur = H[h];
     int e = i;
+    unsigned int nzero = 0;
     do {
         const uint32_t j = (uint32_t)js[e];
         const uint64_t g = j0 + j;  // position in the whole batch (pyx:44: vals[i % nv])
         const T v = vals[g < nv ? g : g % nv];
         const T d = t_sub<T>(v, cur);
-        cur = t_add<T>(cur, d);
+        cur = assign ? v : t_add<T>(cur, d);   // assign: the experimental C++ twin stores val itself (cpp:22-23)
         dj[j] = d;
         ds[e] = d;
+        nzero += (d == T(0));
         ++e;
     } while (e < m && keys[e] == key);
     H[h] = cur;
+    if (nzero) atomicAdd(status + SW_STAT_ZERO_DELTA, nzero);   // bench.py's zero_delta_frac (rare on real batches)
 }
 
 // Float path: the sort only has to bring the duplicates of one leaf together in batch order, so the
@@ -211,7 +214,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) leaf_pass_grouped_kernel(T *H, uint32_t n, const uint32_t *__restrict__ keys,
                                                                 const int *__restrict__ js, int m,
                                                                 const T *__restrict__ vals, uint64_t nv, uint64_t j0,
-                                                                T *__restrict__ dj, int gb, const unsigned int *status)
+                                                                T *__restrict__ dj, int gb, unsigned int *status,
+                                                                bool assign)
 {
     if (status[SW_STATUS]) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -221,6 +225,7 @@ __global__ void __launch_bounds__(256) leaf_pass_grouped_kernel(T *H, uint32_t n
     const uint64_t two_n = 2ull * n;
     int e = i;
     uint32_t key = keys[i];
+    unsigned int nzero = 0;
     do {
         const uint32_t h = key_to_heap(key, two_n);
         const uint32_t j = (uint32_t)js[e];
@@ -228,12 +233,14 @@ __global__ void __launch_bounds__(256) leaf_pass_grouped_kernel(T *H, uint32_t n
         const T v = vals[g < nv ? g : g % nv];
         const T cur = H[h];
         const T d = t_sub<T>(v, cur);
-        H[h] = t_add<T>(cur, d);
+        H[h] = assign ? v : t_add<T>(cur, d);
         dj[j] = d;
+        nzero += (d == T(0));
         ++e;
         if (e >= m) break;
         key = keys[e];
     } while ((key >> gb) == grp);
+    if (nzero) atomicAdd(status + SW_STAT_ZERO_DELTA, nzero);
 }
 
 // -----------------------------------------------------------------------------------------
@@ -789,7 +796,7 @@ __global__ void __launch_bounds__(FOLD_THREADS) fold_top_maps_kernel(const T *__
 template <typename T>
 static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *idx, int m, const T *vals,
                                 int64_t nv, int64_t j0, int64_t B, T *delta_out, const T *deltas_in,
-                                bool small, cudaStream_t s)
+                                bool small, bool assign, cudaStream_t s)
 {
     // deltas_in != nullptr: "apply deltas" mode (sharded top tree): the per-update
     // differences are given, the leaves are not touched, only proper ancestors are folded.
@@ -807,25 +814,23 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
             sp.H = H; sp.n = n; sp.depth = depth; sp.m = m; sp.idx = idx; sp.vals = vals;
             sp.nv = (uint64_t)nv; sp.j0 = (uint64_t)j0; sp.deltas_in = deltas_in; sp.delta_out = delta_out;
             sp.lev_d = (T *)w.lev_d; sp.lev_stride = B; sp.qlong = w.queue; sp.qmed = w.queue_med; sp.status = status;
-            sp.qret = w.queue_ret; sp.key0_out = w.kj; sp.lev_key = w.lev_key;
+            sp.qret = w.queue_ret; sp.key0_out = w.kj; sp.lev_key = w.lev_key; sp.assign = assign;
             g_kernel_launches += 2;
             if (m <= SMALL_THREADS) {
-                static int attr1 = -1;   // function attributes are per device
-                if (attr1 != t->device) {
-                    cudaError_t ea = cudaFuncSetAttribute(update_small_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                          (int)small_smem_bytes<T, 1>());
-                    if (ea != cudaSuccess) return ea;
-                    attr1 = t->device;
-                }
+                static per_device_once attr1;   // function attributes are per device
+                cudaError_t ea = attr1.run(t->device, [&] {
+                    return cudaFuncSetAttribute(update_small_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)small_smem_bytes<T, 1>());
+                });
+                if (ea != cudaSuccess) return ea;
                 update_small_kernel<T, 1><<<1, SMALL_THREADS, small_smem_bytes<T, 1>(), s>>>(sp);
             } else {
-                static int attr4 = -1;
-                if (attr4 != t->device) {
-                    cudaError_t ea = cudaFuncSetAttribute(update_small_kernel<T, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                          (int)small_smem_bytes<T, 4>());
-                    if (ea != cudaSuccess) return ea;
-                    attr4 = t->device;
-                }
+                static per_device_once attr4;
+                cudaError_t ea = attr4.run(t->device, [&] {
+                    return cudaFuncSetAttribute(update_small_kernel<T, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)small_smem_bytes<T, 4>());
+                });
+                if (ea != cudaSuccess) return ea;
                 update_small_kernel<T, 4><<<1, SMALL_THREADS, small_smem_bytes<T, 4>(), s>>>(sp);
             }
             retire_params<T> rp{w.queue_ret, w.kj, w.lev_key, depth, n};
@@ -854,10 +859,10 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
         ++g_kernel_launches;
         if (gb)
             leaf_pass_grouped_kernel<T><<<g, 256, 0, s>>>(H, n, w.keys_b, w.j_b, m, vals, (uint64_t)nv, (uint64_t)j0,
-                                                         (T *)w.dj, gb, status);
+                                                         (T *)w.dj, gb, status, assign);
         else
             leaf_pass_kernel<T><<<g, 256, 0, s>>>(H, n, w.keys_b, w.j_b, m, vals, (uint64_t)nv, (uint64_t)j0,
-                                                  (T *)w.dj, (T *)w.ds, status);
+                                                  (T *)w.dj, (T *)w.ds, status, assign);
         d_batch = (const T *)w.dj;
         if (delta_out) {
             e = cudaMemcpyAsync(delta_out, w.dj, (size_t)m * sizeof(T), cudaMemcpyDeviceToDevice, s);
@@ -892,13 +897,14 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
             pp.qlong = w.queue; pp.qmed = w.queue_med; pp.qhuge = w.queue_huge; pp.huge_off = w.huge_off;
             pp.qret = w.queue_ret;
             pp.status = status;
-            static int occ = 0, occ_dev = -1;
-            if (occ_dev != t->device) {
+            if (t->part_occ < 1) {   // per tree (one dtype, one device); the caller holds the tree's lock
+                int occ = 0;
                 e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, partition_levels_kernel<T>, PART_THREADS, 0);
                 if (e != cudaSuccess) return e;
                 if (occ < 1) return cudaErrorCooperativeLaunchTooLarge;
-                occ_dev = t->device;
+                t->part_occ = occ;
             }
+            const int occ = t->part_occ;
             // balanced persistent grid: every CTA gets the same number of tiles (the grid barriers wait
             // for the slowest CTA)
             const int max_res = occ * t->sm_count;
@@ -1057,11 +1063,13 @@ cudaError_t launch_fold_by_leaf(st_tree *t, const int64_t *leaf, const void *del
 }
 
 cudaError_t launch_update(st_tree *t, const int64_t *idx, int64_t ni, const void *vals, int64_t nv,
-                          void *delta_out, const void *deltas_in, cudaStream_t s)
+                          void *delta_out, const void *deltas_in, cudaStream_t s, bool assign)
 {
     if (ni <= 0 && nv <= 0) return cudaSuccess;
     if (ni <= 0) {
         // nothing to apply, but the reference still scans ALL vals for negatives (pyx:37-39)
+        cudaError_t eb = launch_batch_begin(t, s);
+        if (eb != cudaSuccess) return eb;
         ST_DISPATCH(t->dtype, {
             ++g_kernel_launches;
             validate_kernel<T><<<grid_for(nv, 256, (int64_t)t->sm_count * 8), 256, 0, s>>>(
@@ -1087,9 +1095,12 @@ cudaError_t launch_update(st_tree *t, const int64_t *idx, int64_t ni, const void
         t->ws.bytes = need;
     }
     t->reserved_batch = cap;
+    t->stat_updates += ni;
     ST_DISPATCH(t->dtype, {
         const bool small = is_float_t<T>::value && !t->profile && ni <= SMALL_M && (deltas_in || nv <= SMALL_M);
         if (!small) {
+            cudaError_t eb = launch_batch_begin(t, s);
+            if (eb != cudaSuccess) return eb;
             ++g_kernel_launches;
             validate_kernel<T><<<grid_for(ni > nv ? ni : nv, 256, (int64_t)t->sm_count * 8), 256, 0, s>>>(
                 idx, ni, (const T *)vals, deltas_in ? 0 : nv, t->n, t->d_status);
@@ -1099,7 +1110,7 @@ cudaError_t launch_update(st_tree *t, const int64_t *idx, int64_t ni, const void
             const int m = (int)(ni - j0 < cap ? ni - j0 : cap);
             cudaError_t e = update_chunk<T>(t, w, idx + j0, m, (const T *)vals, nv, j0, cap,
                                             delta_out ? (T *)delta_out + j0 : nullptr,
-                                            deltas_in ? (const T *)deltas_in + j0 : nullptr, small, s);
+                                            deltas_in ? (const T *)deltas_in + j0 : nullptr, small, assign, s);
             if (e != cudaSuccess) return e;
         }
     });

@@ -35,6 +35,7 @@ template <typename T> struct small_params {
     int64_t lev_stride;
     seg_entry *qlong, *qmed;
     unsigned int *status;
+    bool assign;           // leaf = val instead of fl(leaf + d)
     seg_entry *qret;       // retirements for the follow-up kernel
     uint32_t *key0_out;    // level-0 keys (batch order) for the follow-up kernel
     uint32_t *lev_key;     // [level][lev_stride] keys of levels with retirements
@@ -100,7 +101,16 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) update_small_kernel(small_pa
     const int tid = threadIdx.x;
     const int m = p.m, depth = p.depth;
     const uint64_t two_n = 2ull * p.n;
-    if (p.status[SW_STATUS]) return;
+    {
+        // a new batch: an earlier batch's failure moves to the sticky word (st_poll_status still reports it)
+        // and no longer blocks this one.  One CTA, every thread reads before the barrier: no race.
+        const unsigned int prev = p.status[SW_STATUS];
+        __syncthreads();
+        if (tid == 0 && prev) {
+            p.status[ST_SW_STICKY] |= prev;
+            p.status[SW_STATUS] = 0;
+        }
+    }
 #ifdef ST_SMALL_TIMING
     long long t_start = clock64();
     #define ST_TICK(k) if (tid == 0) p.status[32 + (k)] = (unsigned int)(clock64() - t_start)
@@ -205,13 +215,16 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) update_small_kernel(small_pa
                     const uint32_t ky = S.key[1][i];
                     T cur = hreg[k];
                     int e = i;
+                    unsigned int nzero = 0;
                     do {
                         const T d = t_sub<T>(S.d[1][e], cur);
-                        cur = t_add<T>(cur, d);
+                        cur = p.assign ? S.d[1][e] : t_add<T>(cur, d);
                         S.d[0][(int)S.se[1][e]] = d;
+                        nzero += (d == T(0));
                         ++e;
                     } while (e < m && S.key[1][e] == ky);
                     p.H[key_to_heap(ky, two_n)] = cur;
+                    if (nzero) atomicAdd(p.status + SW_STAT_ZERO_DELTA, nzero);
                 }
             }
         }

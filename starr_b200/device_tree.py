@@ -108,18 +108,55 @@ class DeviceSumTree:
         return self
 
     # ---- update -----------------------------------------------------------------------------
-    def update_(self, idx: torch.Tensor, vals: torch.Tensor, check: bool = False) -> "DeviceSumTree":
+    def update_(self, idx: torch.Tensor, vals: torch.Tensor, check: bool = False,
+                assign_leaf: bool = False) -> "DeviceSumTree":
         """``leaves[idx[j]] = vals[j % len(vals)]`` for j in batch order, exact reference
         semantics (duplicates apply sequentially; float ancestors are ordered folds).
 
         Asynchronous by default: a batch that fails validation (negative value, index out of
         range) is skipped as a whole on the device and reported by the next ``poll()``.
-        ``check=True`` waits and raises immediately."""
+        ``check=True`` waits and raises immediately.  A failed batch does not block the batches
+        enqueued behind it.  ``assign_leaf=True`` stores ``vals[j]`` itself in the leaf (the
+        reference's experimental C++ twin, ``starr/experimental/src/sumtree_array.cpp:19-23``)
+        instead of ``fl(leaf + fl(vals[j] - leaf))``."""
         idx = self._chk(idx.reshape(-1), torch.int64, "idx")
         vals = self._chk(vals.reshape(-1), self.dtype, "vals")
         with torch.cuda.device(self.device):
             self._h.update_device(idx.data_ptr(), idx.numel(), vals.data_ptr(), vals.numel(),
-                                  _stream(), sync_check=check)
+                                  _stream(), sync_check=check, assign_leaf=assign_leaf)
+        return self
+
+    def append_(self, vals: torch.Tensor) -> "DeviceSumTree":
+        """Ring-buffer append (reference ``starr/experimental/slow.py:81-88`` ``CircularSumTree``):
+        ``vals[k]`` goes to leaf ``(cursor + k) % n`` in order, the cursor advances by ``len(vals)``."""
+        vals = self._chk(vals.reshape(-1), self.dtype, "vals")
+        k = vals.numel()
+        if k == 0:
+            return self
+        cursor = getattr(self, "_cursor", 0)
+        idx = (torch.arange(k, dtype=torch.int64, device=self.device) + cursor) % self.n
+        self.update_(idx, vals)
+        self._cursor = (cursor + k) % self.n
+        return self
+
+    # ---- in-place leaf arithmetic (SURVEY 8(f2); reference sumtree_array.py:150-173, :202-205) --------
+    def inplace_(self, op: str, operand, rebuild: bool = True) -> "DeviceSumTree":
+        """``leaves = leaves (op) operand`` on the device, ``op`` in add / subtract / multiply /
+        true_divide / fill, ``operand`` a Python or NumPy scalar or a tensor of ``n`` elements of the
+        tree dtype; then (``rebuild``) validate and rebuild the tree like the reference's in-place
+        ufuncs do (``ValueError`` if a leaf went negative: the leaves stay changed, the tree does not)."""
+        with torch.cuda.device(self.device):
+            if isinstance(operand, torch.Tensor):
+                y = self._chk(operand.reshape(-1), self.dtype, "operand")
+                if y.numel() != self.n:
+                    raise TypeError("operand must have the size of the array")
+                self._h.inplace_device(op, None, y.data_ptr(), y.numel(), _stream())
+            else:
+                sc = np.empty(1, dtype=_TORCH_TO_NP[self.dtype])
+                sc.fill(operand)
+                self._h.inplace_device(op, sc, 0, 0, _stream())
+            if rebuild:
+                self._h.build(_stream())
         return self
 
     # ---- building blocks of the sharded tree (starr_b200/sharded.py) ----------------------------
@@ -251,10 +288,23 @@ class DeviceSumTree:
             self._h.poll_status(_stream(), clear=True)
 
     # ---- search / sample --------------------------------------------------------------------
+    def _chk_out(self, out: torch.Tensor | None, m: int, dtype=torch.int64, name: str = "out") -> torch.Tensor:
+        """A caller-supplied result buffer goes to the kernel as a raw pointer: it must be the right
+        device / dtype, contiguous and long enough."""
+        if out is None:
+            return torch.empty(m, dtype=dtype, device=self.device)
+        if self._chk(out, dtype, name) is not out or out.numel() < m:
+            raise TypeError(f"{name} must be a contiguous {dtype} tensor on {self.device} with at least {m} elements")
+        return out
+
     def search(self, prefix_sums: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
         vals = self._chk(prefix_sums.reshape(-1), self.dtype, "prefix_sums")
-        if out is None:
-            out = torch.empty(vals.numel(), dtype=torch.int64, device=self.device)
+        if out is not None:
+            self._chk_out(out, vals.numel())
+            with torch.cuda.device(self.device):
+                self._h.search_device(vals.data_ptr(), vals.numel(), out.data_ptr(), _stream())
+            return out
+        out = torch.empty(vals.numel(), dtype=torch.int64, device=self.device)
         with torch.cuda.device(self.device):
             self._h.search_device(vals.data_ptr(), vals.numel(), out.data_ptr(), _stream())
         return out.reshape(prefix_sums.shape)
@@ -266,13 +316,48 @@ class DeviceSumTree:
         is read on the device, so nothing synchronises."""
         u = self._chk(u.reshape(-1), torch.float64, "u")
         m = u.numel()
-        if out is None:
-            out = torch.empty(m, dtype=torch.int64, device=self.device)
+        out = self._chk_out(out, m)
         prio = torch.empty(m, dtype=self.dtype, device=self.device) if return_priorities else None
         with torch.cuda.device(self.device):
             self._h.sample_uniform_device(u.data_ptr(), m, out.data_ptr(),
                                           prio.data_ptr() if prio is not None else 0, _stream())
         return (out, prio) if return_priorities else out
+
+    @property
+    def prob_dtype(self) -> torch.dtype:
+        return _NP_TO_TORCH[np.dtype(_lib.PROB_DTYPES[self._h.code])]
+
+    def sample_weights(self, u: torch.Tensor, out=None):
+        """``(indices, priorities, probabilities)`` for injected uniforms: ``priorities = leaves[indices]``,
+        ``probabilities = priorities / total`` exactly as NumPy's ``x[idx] / x.sum()`` computes it (one
+        division in the tree dtype; float64 for integer trees) -- the inputs of the PER importance
+        weights ``(N * P(i)) ** -beta`` (reference ``README.md:7``).  ``out``: optional tuple of three buffers."""
+        u = self._chk(u.reshape(-1), torch.float64, "u")
+        m = u.numel()
+        o_idx, o_prio, o_prob = out if out is not None else (None, None, None)
+        o_idx = self._chk_out(o_idx, m)
+        o_prio = self._chk_out(o_prio, m, self.dtype, "priorities")
+        o_prob = self._chk_out(o_prob, m, self.prob_dtype, "probabilities")
+        with torch.cuda.device(self.device):
+            self._h.sample_weights_device(u.data_ptr(), m, o_idx.data_ptr(), o_prio.data_ptr(), o_prob.data_ptr(), _stream())
+        return o_idx, o_prio, o_prob
+
+    def per_step_(self, idx: torch.Tensor, vals: torch.Tensor, u: torch.Tensor, out=None):
+        """One fused PER step: apply the priority updates, then draw ``len(u)`` samples
+        and return ``(indices, priorities, probabilities)`` -- one library call, nothing synchronises,
+        capturable in a CUDA graph after ``reserve``."""
+        idx = self._chk(idx.reshape(-1), torch.int64, "idx")
+        vals = self._chk(vals.reshape(-1), self.dtype, "vals")
+        u = self._chk(u.reshape(-1), torch.float64, "u")
+        m = u.numel()
+        o_idx, o_prio, o_prob = out if out is not None else (None, None, None)
+        o_idx = self._chk_out(o_idx, m)
+        o_prio = self._chk_out(o_prio, m, self.dtype, "priorities")
+        o_prob = self._chk_out(o_prob, m, self.prob_dtype, "probabilities")
+        with torch.cuda.device(self.device):
+            self._h.per_step_device(idx.data_ptr(), idx.numel(), vals.data_ptr(), vals.numel(), u.data_ptr(), m,
+                                    o_idx.data_ptr(), o_prio.data_ptr(), o_prob.data_ptr(), _stream())
+        return o_idx, o_prio, o_prob
 
     def sample(self, nsamples: int, generator: torch.Generator | None = None,
                return_priorities: bool = False):
@@ -305,3 +390,82 @@ class DeviceSumTree:
     def sum_over(self, index_from: int, index_to: int):
         torch.cuda.current_stream(self.device).synchronize()
         return self._h.sum_over(index_from, index_to)
+
+
+class DeviceMinTree:
+    """Device-resident MIN tree: the reference's ``MinTree`` / ``CircularMinTree``
+    (``starr/experimental/slow.py:53-78, 91-98``) for PER buffers that need ``min(priorities)`` for the
+    importance-weight normalisation.  Same heap layout as ``DeviceSumTree``; unset leaves are ``+inf``
+    (integer dtypes: the largest value of the type)."""
+
+    def __init__(self, n: int, dtype=torch.float32, device=None):
+        if dtype not in _TORCH_TO_NP:
+            raise TypeError("No matching signature found")
+        if not torch.cuda.is_available():
+            raise RuntimeError("DeviceMinTree needs a CUDA device; starr_b200 has no CPU fallback")
+        self.device = torch.device(device if device is not None else torch.cuda.current_device())
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.n, self.dtype = int(n), dtype
+        assert self.n > 0, "size must be greater than 0"
+        self._cursor = 0
+        with torch.cuda.device(self.device):
+            self.heap = torch.empty(2 * self.n, dtype=dtype, device=self.device)
+            torch.cuda.current_stream().synchronize()
+            self._h = _lib.TreeHandle(self.n, _TORCH_TO_NP[dtype], self.device.index,
+                                      external_heap=self.heap.data_ptr(), kind="min")
+
+    def __len__(self) -> int:
+        return self.n
+
+    @property
+    def leaves(self) -> torch.Tensor:
+        return self.heap[self.n:]
+
+    @property
+    def tree(self) -> torch.Tensor:
+        return self.heap[:self.n]
+
+    def min(self) -> torch.Tensor:
+        """0-d device view of the root (``MinTree.min()``, slow.py:77-78)."""
+        return self.heap[1]
+
+    def _chk(self, t, dtype, name):
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.device == self.device):
+            raise ValueError(f"{name} must be a CUDA tensor on {self.device}")
+        if t.dtype != dtype:
+            raise TypeError(f"{name} must have dtype {dtype}, got {t.dtype}")
+        return t.contiguous()
+
+    def update_(self, idx: torch.Tensor, vals: torch.Tensor) -> "DeviceMinTree":
+        """``leaves[idx[j]] = vals[j % len(vals)]`` in batch order (the last write to a leaf wins), every
+        ancestor recomputed as ``min(left, right)`` (slow.py:62-68).  Asynchronous; ``poll()`` reports
+        an out-of-range index (the whole batch is then skipped)."""
+        idx = self._chk(idx.reshape(-1), torch.int64, "idx")
+        vals = self._chk(vals.reshape(-1), self.dtype, "vals")
+        with torch.cuda.device(self.device):
+            self._h.min_update_device(idx.data_ptr(), idx.numel(), vals.data_ptr(), vals.numel(), _stream())
+        return self
+
+    def append_(self, vals: torch.Tensor) -> "DeviceMinTree":
+        """``CircularMinTree.append`` for a batch (slow.py:96-98)."""
+        vals = self._chk(vals.reshape(-1), self.dtype, "vals")
+        k = vals.numel()
+        if k:
+            idx = (torch.arange(k, dtype=torch.int64, device=self.device) + self._cursor) % self.n
+            self.update_(idx, vals)
+            self._cursor = (self._cursor + k) % self.n
+        return self
+
+    def build_(self, leaves: torch.Tensor | None = None) -> "DeviceMinTree":
+        if leaves is not None:
+            if leaves.numel() != self.n:
+                raise TypeError("array and tree must have the same size")
+            self.leaves.copy_(leaves.to(device=self.device, dtype=self.dtype).reshape(-1))
+        with torch.cuda.device(self.device):
+            self._h.min_build(_stream())
+        return self
+
+    def poll(self) -> None:
+        with torch.cuda.device(self.device):
+            self._h.poll_status(_stream(), clear=True)

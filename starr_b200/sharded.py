@@ -79,8 +79,14 @@ class ShardedSumTree:
 
     # ---- helpers --------------------------------------------------------------------------------
     def reserve(self, max_global_batch: int) -> None:
-        self.local.reserve(max_global_batch)
-        self.top.reserve(max_global_batch)
+        """Pre-size every workspace a batch of this size needs (update pipeline, plan scratch, top-fold
+        records), so that no stream-ordered call reallocates or synchronises later."""
+        for tree in (self.local, self.top):
+            h = getattr(tree, "handle", None)
+            if h is not None and hasattr(h, "reserve_sharded"):
+                h.reserve_sharded(max_global_batch, self.world)
+            else:
+                tree.reserve(max_global_batch)
 
     def _mark(self, label: str) -> None:
         if self._marks is not None:

@@ -22,6 +22,7 @@ import numpy as np
 from . import _hostlogic, _lib
 
 _TOO_SMALL = "input to SumTreeArray must have shape with at least 2 elements"
+_DEVICE_UFUNCS = ("add", "subtract", "multiply", "true_divide", "divide")
 
 
 class _TreeState:
@@ -103,6 +104,17 @@ class _TreeState:
 
     def strided_sum(self, stride: int) -> np.ndarray:                     # :508
         return self.handle.strided_sum_host(stride)
+
+    def inplace(self, op: str, scalar: np.ndarray) -> None:               # :150-173, :202-205
+        """In-place leaf arithmetic + rebuild entirely on the device: no host ufunc over
+        the n leaves and no n-element upload.  The host leaf mirror goes stale and is refreshed lazily."""
+        self._root = None
+        try:
+            self.handle.inplace_device(op, scalar)
+            self.leaves_stale = True
+            self.handle.build()          # validates the NEW leaves; on failure the tree stays as it was
+        finally:
+            self.tree_stale = True
 
 
 def _guarded(method):
@@ -204,11 +216,45 @@ class SumTreeArray(np.ndarray):
         out = out_arr.view(np.ndarray)
         return out[()] if return_scalar else out
 
+    def _device_scalar(self, ufunc, method, inputs, kwargs):
+        """The operand of ``self (op)= scalar`` as a 1-element array of this dtype if the device can
+        reproduce NumPy's result bit for bit, else None (-> host ufunc + rebuild, as the reference does).
+        Eligible: add / subtract / multiply / true_divide called in place on self with a Python scalar
+        or a NumPy scalar of the array's own dtype (then NumPy computes in that dtype, one IEEE op)."""
+        if method != "__call__" or ufunc.__name__ not in _DEVICE_UFUNCS or len(inputs) != 2 or inputs[0] is not self:
+            return None
+        if set(kwargs) - {"out"}:
+            return None
+        dt = self.dtype
+        if ufunc.__name__ in ("true_divide", "divide") and dt.kind != "f":
+            return None
+        c = inputs[1]
+        if isinstance(c, (bool, np.bool_)):
+            return None
+        if isinstance(c, np.generic):
+            return np.array([c]) if c.dtype == dt else None
+        if isinstance(c, int):
+            if dt.kind == "f":
+                try:
+                    return np.array([c], dtype=dt)
+                except OverflowError:
+                    return None
+            info = np.iinfo(dt)
+            return np.array([c], dtype=dt) if info.min <= c <= info.max else None
+        if isinstance(c, float) and dt.kind == "f":
+            return np.array([c], dtype=dt)
+        return None
+
     @_guarded
     def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
+        out = kwargs.get("out")
+        if out is not None and len(out) == 1 and out[0] is self:
+            scalar = self._device_scalar(ufunc, method, inputs, kwargs)
+            if scalar is not None:
+                self._state.inplace(ufunc.__name__, scalar)
+                return self
         self._state.sync_leaves()
         plain = tuple(x.view(np.ndarray) if isinstance(x, SumTreeArray) else x for x in inputs)
-        out = kwargs.get("out")
         if out is None:
             return getattr(ufunc, method)(*plain, **kwargs)
         if len(out) == 1 and out[0] is self:
@@ -231,6 +277,12 @@ class SumTreeArray(np.ndarray):
 
     @_guarded
     def fill(self, *args, **kwargs):
+        if len(args) == 1 and not kwargs and isinstance(args[0], (int, float, np.generic)) \
+                and not isinstance(args[0], (bool, np.bool_, complex, np.complexfloating)):
+            sc = np.empty(1, dtype=self.dtype)
+            sc.fill(args[0])             # NumPy's own conversion of the fill value (or its error)
+            self._state.inplace("fill", sc)
+            return
         self._state.sync_leaves()
         super().fill(*args, **kwargs)
         self._rebuild_sumtree()

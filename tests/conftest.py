@@ -45,3 +45,8 @@ def oracle_mod():
     import oracle
     oracle.build()
     return oracle
+
+
+@pytest.fixture(scope="session")
+def golden_next():
+    return np.load(os.path.join(GOLDEN, "next_cases.npz"))

@@ -79,10 +79,59 @@ def api_cases():
     return out
 
 
+def next_cases(reference_root="/root/reference"):
+    """the experimental C++ twin (oracle/_ref/_xcython*.so, unmodified) and the pure-Python
+    MinTree / CircularMinTree / CircularSumTree of starr/experimental/slow.py (imported from the reference tree)."""
+    import importlib.util
+    X = oracle.ref_exp()
+    spec = importlib.util.spec_from_file_location("ref_slow", os.path.join(reference_root, "starr/experimental/slow.py"))
+    slow = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(slow)
+    out = {}
+    for n in (2, 3, 5, 37, 1000, 4096):
+        rng = np.random.default_rng(4000 + n)
+        a = np.exp(rng.uniform(-6, 6, n))
+        t = np.zeros(n)
+        oracle.ref().build_sumtree_from_array(a, t)
+        out[f"exp_n{n}/array0"], out[f"exp_n{n}/tree0"] = a.copy(), t.copy()
+        for b in range(3):
+            m = int(rng.integers(1, 3 * n)); nv = m if b == 0 else int(rng.integers(1, m + 1))
+            idx = rng.integers(0, n if b < 2 else max(2, n // 8), m).astype(np.int32)
+            vals = np.exp(rng.uniform(-6, 6, nv))
+            X.update_tree_multi(idx, vals, a, t)
+            out[f"exp_n{n}/b{b}/idx"], out[f"exp_n{n}/b{b}/vals"] = idx, vals
+            out[f"exp_n{n}/b{b}/array"], out[f"exp_n{n}/b{b}/tree"] = a.copy(), t.copy()
+        q = t[1] * rng.random(200) * 1.05
+        found = np.ones(200, np.int32)
+        X.get_prefix_sum_idx_multi(found, q, a, t)
+        out[f"exp_n{n}/queries"], out[f"exp_n{n}/found"] = q, found
+    for n in (2, 3, 5, 6, 7, 13, 64, 100, 1000):
+        rng = np.random.default_rng(5000 + n)
+        mt = slow.MinTree(n)
+        for b in range(3):
+            m = int(rng.integers(1, 3 * n))
+            idx = rng.integers(0, n, m).astype(np.int64)
+            vals = np.round(np.exp(rng.uniform(-3, 3, m)), 3)
+            for i, v in zip(idx, vals):
+                mt[int(i)] = float(v)
+            out[f"min_n{n}/b{b}/idx"], out[f"min_n{n}/b{b}/vals"] = idx, vals
+            out[f"min_n{n}/b{b}/data"] = np.array(mt._data, dtype=np.float64)
+        cm, cs = slow.CircularMinTree(n), slow.CircularSumTree(n)
+        for b in range(3):
+            vals = np.round(np.exp(rng.uniform(-3, 3, int(rng.integers(1, 2 * n + 2)))), 3)
+            for v in vals:
+                cm.append(float(v)); cs.append(float(v))
+            out[f"ring_n{n}/b{b}/vals"] = vals
+            out[f"ring_n{n}/b{b}/min_data"] = np.array(cm._data, dtype=np.float64)
+            out[f"ring_n{n}/b{b}/sum_data"] = np.array(cs._data, dtype=np.float64)
+    return out
+
+
 if __name__ == "__main__":
     if oracle.ref() is None or oracle.ref_api() is None:
         sys.exit("reference not available: run oracle/build_ref.sh in the build container")
     np.savez_compressed(os.path.join(HERE, "kernel_cases.npz"), **kernel_cases())
     np.savez_compressed(os.path.join(HERE, "api_cases.npz"), **api_cases())
-    for f in ("kernel_cases.npz", "api_cases.npz"):
+    np.savez_compressed(os.path.join(HERE, "next_cases.npz"), **next_cases())
+    for f in ("kernel_cases.npz", "api_cases.npz", "next_cases.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

@@ -128,3 +128,64 @@ def test_axis_fold_is_numpy_order(oracle_mod):
             want = x.sum(axis=tuple(range(lo, hi + 1)))
             got = oracle_mod.c.axis_fold(x.reshape(A, R, Cc)).reshape(want.shape)
             assert_bits_equal(got, want, f"{np.dtype(dt).name} {shape} axes {lo}..{hi}")
+
+
+# ---- experimental twin and MinTree restatements ---------------------------------
+EXP_SIZES = (2, 3, 5, 37, 1000, 4096)
+MIN_SIZES = (2, 3, 5, 6, 7, 13, 64, 100, 1000)
+
+
+@pytest.mark.parametrize("n", EXP_SIZES)
+def test_experimental_oracle_matches_golden(oracle_mod, golden_next, n):
+    """orc_exp_* vs fixtures generated from the unmodified starr.experimental._cython."""
+    g, X = golden_next, oracle_mod.exp
+    a, t = g[f"exp_n{n}/array0"].copy(), g[f"exp_n{n}/tree0"].copy()
+    for b in range(3):
+        X.update_tree_multi(g[f"exp_n{n}/b{b}/idx"], g[f"exp_n{n}/b{b}/vals"], a, t)
+        assert_bits_equal(a, g[f"exp_n{n}/b{b}/array"], f"array after batch {b}")
+        assert_bits_equal(t, g[f"exp_n{n}/b{b}/tree"], f"tree after batch {b}")
+    out = np.ones(200, np.int32)
+    X.get_prefix_sum_idx_multi(out, g[f"exp_n{n}/queries"], a, t)
+    assert np.array_equal(out, g[f"exp_n{n}/found"])
+
+
+def test_experimental_oracle_matches_compiled_reference(oracle_mod):
+    R = oracle_mod.ref_exp()
+    if R is None:
+        pytest.skip("oracle/_ref/_xcython not built (needs the reference tree)")
+    rng = np.random.default_rng(11)
+    for n in (2, 3, 6, 100, 1023):
+        a1 = rng.random(n); t1 = np.zeros(n)
+        oracle_mod.c.build_sumtree_from_array(a1, t1)
+        a2, t2 = a1.copy(), t1.copy()
+        for _ in range(3):
+            m = int(rng.integers(1, 4 * n))
+            idx = rng.integers(0, n, m).astype(np.int32); v = np.exp(rng.uniform(-8, 8, int(rng.integers(1, m + 1))))
+            R.update_tree_multi(idx, v, a1, t1); oracle_mod.exp.update_tree_multi(idx, v, a2, t2)
+            assert_bits_equal(a2, a1, "array"); assert_bits_equal(t2, t1, "tree")
+
+
+def test_experimental_assign_differs_from_main_path(oracle_mod):
+    """The twin ASSIGNS the leaf (cpp:23); the main module stores fl(old + fl(val - old)) (pyx:43-45)."""
+    a1 = np.array([1e8, 1.0]); t1 = np.zeros(2); oracle_mod.c.build_sumtree_from_array(a1, t1)
+    a2, t2 = a1.copy(), t1.copy()
+    v = np.array([0.1])
+    oracle_mod.c.update_sumtree(np.array([0], np.intp), v, a1, t1)
+    oracle_mod.exp.update_tree_multi(np.array([0], np.int32), v, a2, t2)
+    assert a2[0] == 0.1 and a1[0] != 0.1 and t1[1] == t2[1]
+
+
+@pytest.mark.parametrize("n", MIN_SIZES)
+def test_min_oracle_matches_golden(oracle_mod, golden_next, n):
+    """orc_min_set_f64 vs fixtures from the reference's slow.MinTree / CircularMinTree."""
+    g = golden_next
+    data = np.full(2 * n, np.inf)
+    for b in range(3):
+        oracle_mod.min_tree_set(data, g[f"min_n{n}/b{b}/idx"], g[f"min_n{n}/b{b}/vals"])
+        assert_bits_equal(data, g[f"min_n{n}/b{b}/data"], f"min tree after batch {b}")
+    ring, cursor = np.full(2 * n, np.inf), 0
+    for b in range(3):
+        v = g[f"ring_n{n}/b{b}/vals"]
+        oracle_mod.min_tree_set(ring, (np.arange(v.size, dtype=np.int64) + cursor) % n, v)
+        cursor = (cursor + v.size) % n
+        assert_bits_equal(ring, g[f"ring_n{n}/b{b}/min_data"], f"ring min tree after batch {b}")
