@@ -143,6 +143,14 @@ ST_API int st_update_gather_host(st_tree *t, const int64_t *idx_host, int64_t ni
  * tree dtype) -- the quantity the reference adds to each ancestor (pyx:43-48). */
 ST_API int st_update_deltas_device(st_tree *t, const int64_t *idx_dev, int64_t ni, const void *vals_dev,
                             int64_t nv, void *delta_out_dev, void *stream);
+/* st_update_deltas_device in two halves, so that the differences can travel to the other ranks while
+ * the ancestors are still being updated: begin = validation, leaf order, leaf pass (delta_out is complete
+ * in stream order behind it); finish = everything above the leaves, for the batch begin left pending.
+ * Batches the library applies in one piece anyway (<= 4096 updates, or more than one 2^21 chunk) are
+ * applied completely by begin; finish is then a no-op. */
+ST_API int st_update_begin_device(st_tree *t, const int64_t *idx_dev, int64_t ni, const void *vals_dev, int64_t nv,
+                           void *delta_out_dev, void *stream);
+ST_API int st_update_finish_device(st_tree *t, void *stream);
 /* For j in batch order: every PROPER ancestor of leaf idx[j] += deltas[j] (ordered fold for
  * floats); leaves are not touched.  Used on the replicated top tree whose leaves are the
  * shard roots. */
@@ -178,6 +186,12 @@ ST_API int st_shard_plan_device(st_tree *t, const int64_t *ids_dev, int64_t m, i
                          const void *payload_dev, int64_t npayload, int check_negative, uint8_t *shard_out_dev,
                          int32_t *slot_out_dev, int64_t *own_ids_out_dev, void *own_payload_out_dev, int result_slot,
                          int64_t *counts_out_host, void *stream);
+/* the same, additionally writing own_pos_out[k] = batch position j of the k-th element of shard `rank`
+ * (nullable; m < 2^31): where that element's results are stored on every rank by the peer exchange */
+ST_API int st_shard_plan_pos_device(st_tree *t, const int64_t *ids_dev, int64_t m, int shift, int shards, int rank,
+                             const void *payload_dev, int64_t npayload, int check_negative, uint8_t *shard_out_dev,
+                             int32_t *slot_out_dev, int64_t *own_ids_out_dev, void *own_payload_out_dev,
+                             int32_t *own_pos_out_dev, int result_slot, int64_t *counts_out_host, void *stream);
 ST_API int st_shard_plan_wait(st_tree *t, int result_slot, int shards, int64_t *counts_out_host);
 /* device address of result slot `result_slot`: uint32 counts[shards] (valid in stream order behind the plan) */
 ST_API const uint32_t *st_shard_plan_counts_device(const st_tree *t, int result_slot);
@@ -197,6 +211,42 @@ ST_API int st_shard_expand_indices_device(const st_tree *t, const uint8_t *shard
  * on the top tree this is (owning shard, query to continue with inside that shard). */
 ST_API int st_route_uniform_device(const st_tree *t, const double *u_dev, int64_t m, int64_t *leaf_out_dev,
                             void *residual_out_dev, void *stream);
+
+/* ---- peer-memory exchange of the sharded tree (one node, NVLink / NVSwitch peer access) ------------
+ * Every rank owns one device buffer [flag page | payload]; its CUDA IPC handle (st_peer_handle_bytes()
+ * bytes) is exchanged once by the host layer, after which kernels store results straight into the
+ * buffers of all ranks.  All calls are stream-ordered and never synchronise with the host. */
+typedef struct st_peer st_peer; /* opaque */
+ST_API const char *st_peer_last_error(void);
+ST_API int st_peer_handle_bytes(void);
+ST_API int st_peer_create(int device, int rank, int world, int64_t payload_bytes, st_peer **out,
+                   unsigned char *handle_out);
+/* handles: world x st_peer_handle_bytes() bytes, rank-major (this rank's own entry is ignored) */
+ST_API int st_peer_connect(st_peer *p, const unsigned char *handles);
+ST_API int st_peer_destroy(st_peer *p);
+ST_API void *st_peer_payload(const st_peer *p); /* local device pointer of the payload */
+ST_API int64_t st_peer_payload_bytes(const st_peer *p);
+/* payload_q[offset .. offset+bytes) = this rank's payload[offset ..) for every other rank q (multiples of 16) */
+ST_API int st_peer_broadcast(st_peer *p, int64_t offset, int64_t bytes, void *stream);
+/* payload_q[offset + pos[k]*esize] = src[k] on EVERY rank q (this one included), k < min(count, *count_dev);
+ * pos values must lie in [0, span_elems); count_dev may be NULL */
+ST_API int st_peer_scatter(st_peer *p, const void *src_dev, const int32_t *pos_dev, int64_t count,
+                    const uint32_t *count_dev, int esize, int64_t offset, int64_t span_elems, void *stream);
+/* release-store `value` into flags[channel][this rank] of every rank / spin until flags[channel][q] has
+ * reached `value` for every q (wrap-safe compare; gives up after 20 s and records it for st_peer_status) */
+ST_API int st_peer_signal(st_peer *p, int channel, unsigned int value, void *stream);
+ST_API int st_peer_wait(st_peer *p, int channel, unsigned int value, void *stream);
+ST_API int st_peer_status(st_peer *p, void *stream); /* waits for stream; ST_ERR_CUDA after a timed-out wait */
+/* sample() routing on the replicated top tree fused with the selection of this rank's queries: for the
+ * queries whose top-tree descent ends in leaf `rank`, appends (left-over prefix, batch position) to
+ * own_resid_out / own_pos_out (unordered) and counts them in *own_count_out_dev. */
+ST_API int st_route_compact_device(const st_tree *top, const double *u_dev, int64_t m, int rank, void *own_resid_out_dev,
+                            int32_t *own_pos_out_dev, uint32_t *own_count_out_dev, void *stream);
+/* st_search_counted_device whose result for query k -- index_offset + local leaf -- is stored as int64 at
+ * payload_q[payload_offset + 8*pos[k]] on every rank q */
+ST_API int st_search_push_device(const st_tree *t, const void *vals_dev, int64_t m_max, const uint32_t *m_dev,
+                          const int32_t *pos_dev, int64_t index_offset, st_peer *p, int64_t payload_offset,
+                          int64_t span_elems, void *stream);
 
 /* ---- prefix-sum search: replaces get_prefix_sum_idx, _sumtree_array.pyx:66-122 --- */
 ST_API int st_search_device(const st_tree *t, const void *vals_dev, int64_t m, int64_t *out_dev,

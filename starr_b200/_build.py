@@ -8,9 +8,9 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(CSRC, "build")
-LIB = os.path.join(HERE, "libstarr_b200.so")
-SOURCES = ["st_tree_kernels.cu", "st_update.cu", "st_shard.cu", "st_mintree.cu", "st_capi.cu"]
+OBJ = os.environ.get("ST_BUILD_DIR") or os.path.join(CSRC, "build")
+LIB = os.environ.get("ST_BUILD_LIB") or os.path.join(HERE, "libstarr_b200.so")
+SOURCES = ["st_tree_kernels.cu", "st_update.cu", "st_shard.cu", "st_mintree.cu", "st_peer.cu", "st_capi.cu"]
 HEADERS = ["st_common.cuh", "st_internal.h", "st_ordered_fold.cuh", "st_partition.cuh", "st_update_defs.cuh", "st_update_small.cuh", os.path.join("..", "..", "include", "starr_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [

@@ -13,7 +13,7 @@ from ctypes import POINTER, c_char_p, c_int, c_int64, c_void_p
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libstarr_b200.so")
+LIB_PATH = os.environ.get("STARR_B200_LIB") or os.path.join(_HERE, "libstarr_b200.so")   # override: tuning builds only
 
 # st_dtype codes (include/starr_b200.h) <-> NumPy dtypes: the members of the reference's fused
 # ARRAY_TYPE (starr/src/_sumtree_array.pyx:4-11) that exist on the GPU.
@@ -116,6 +116,25 @@ _SIGNATURES = {
     "st_set_profiling": (c_int, [c_void_p, c_int]),
     "st_set_l2_persistence": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "st_update_breakdown": (c_int, [c_void_p, c_void_p]),
+    "st_update_begin_device": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
+    "st_update_finish_device": (c_int, [c_void_p, c_void_p]),
+    "st_shard_plan_pos_device": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_int64, c_int,
+                                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "st_peer_last_error": (c_char_p, []),
+    "st_peer_handle_bytes": (c_int, []),
+    "st_peer_create": (c_int, [c_int, c_int, c_int, c_int64, POINTER(c_void_p), c_void_p]),
+    "st_peer_connect": (c_int, [c_void_p, c_void_p]),
+    "st_peer_destroy": (c_int, [c_void_p]),
+    "st_peer_payload": (c_void_p, [c_void_p]),
+    "st_peer_payload_bytes": (c_int64, [c_void_p]),
+    "st_peer_broadcast": (c_int, [c_void_p, c_int64, c_int64, c_void_p]),
+    "st_peer_scatter": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int64, c_int64, c_void_p]),
+    "st_peer_signal": (c_int, [c_void_p, c_int, ctypes.c_uint, c_void_p]),
+    "st_peer_wait": (c_int, [c_void_p, c_int, ctypes.c_uint, c_void_p]),
+    "st_peer_status": (c_int, [c_void_p, c_void_p]),
+    "st_route_compact_device": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "st_search_push_device": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64,
+                                      c_void_p]),
     "st_sample_weights_device": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "st_per_step_device": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p,
                                    c_void_p, c_void_p]),
@@ -378,6 +397,35 @@ class TreeHandle:
                                          c_void_p(own_payload_out_ptr), int(result_slot), counts, c_void_p(stream)))
         return list(counts) if wait else None
 
+    def shard_plan_pos_device(self, ids_ptr: int, m: int, shift: int, shards: int, rank: int, payload_ptr: int,
+                              npayload: int, check_negative: bool, shard_out_ptr: int, slot_out_ptr: int,
+                              own_ids_out_ptr: int, own_payload_out_ptr: int, own_pos_out_ptr: int, result_slot: int = 0,
+                              stream: int = 0, wait: bool = True) -> list[int] | None:
+        counts = (c_int64 * int(shards))() if wait else None
+        check(lib().st_shard_plan_pos_device(self.ptr, c_void_p(ids_ptr), int(m), int(shift), int(shards), int(rank),
+                                             c_void_p(payload_ptr), int(npayload), int(bool(check_negative)),
+                                             c_void_p(shard_out_ptr), c_void_p(slot_out_ptr), c_void_p(own_ids_out_ptr),
+                                             c_void_p(own_payload_out_ptr), c_void_p(own_pos_out_ptr), int(result_slot),
+                                             counts, c_void_p(stream)))
+        return list(counts) if wait else None
+
+    def update_begin_device(self, idx_ptr: int, ni: int, vals_ptr: int, nv: int, delta_out_ptr: int, stream: int = 0) -> None:
+        check(lib().st_update_begin_device(self.ptr, c_void_p(idx_ptr), int(ni), c_void_p(vals_ptr), int(nv),
+                                           c_void_p(delta_out_ptr), c_void_p(stream)))
+
+    def update_finish_device(self, stream: int = 0) -> None:
+        check(lib().st_update_finish_device(self.ptr, c_void_p(stream)))
+
+    def route_compact_device(self, u_ptr: int, m: int, rank: int, resid_ptr: int, pos_ptr: int, count_ptr: int,
+                             stream: int = 0) -> None:
+        check(lib().st_route_compact_device(self.ptr, c_void_p(u_ptr), int(m), int(rank), c_void_p(resid_ptr),
+                                            c_void_p(pos_ptr), c_void_p(count_ptr), c_void_p(stream)))
+
+    def search_push_device(self, vals_ptr: int, m_max: int, m_dev_ptr: int, pos_ptr: int, index_offset: int, peer: "PeerArea",
+                           payload_offset: int, span_elems: int, stream: int = 0) -> None:
+        check(lib().st_search_push_device(self.ptr, c_void_p(vals_ptr), int(m_max), c_void_p(m_dev_ptr), c_void_p(pos_ptr),
+                                          int(index_offset), peer.ptr, int(payload_offset), int(span_elems), c_void_p(stream)))
+
     def shard_plan_wait(self, result_slot: int, shards: int) -> list[int]:
         counts = (c_int64 * int(shards))()
         check(lib().st_shard_plan_wait(self.ptr, int(result_slot), int(shards), counts))
@@ -475,6 +523,74 @@ class PinnedBuffer:
         if p and _lib is not None:
             self._raw = None
             _lib.st_host_free(p)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class PeerArea:
+    """One rank's side of the peer-memory exchange area (``st_peer_*``): a device buffer whose CUDA IPC
+    handle is exchanged once, after which kernels store into the buffers of all ranks."""
+
+    def __init__(self, device: int, rank: int, world: int, payload_bytes: int):
+        self.rank, self.world, self.device = int(rank), int(world), int(device)
+        self._hb = int(lib().st_peer_handle_bytes())
+        h = (ctypes.c_ubyte * self._hb)()
+        out = c_void_p()
+        self._check(lib().st_peer_create(self.device, self.rank, self.world, int(payload_bytes), ctypes.byref(out), h))
+        self._p = out
+        self.handle = bytes(h)
+
+    @staticmethod
+    def _check(status: int) -> None:
+        if status != ST_OK:
+            raise RuntimeError(lib().st_peer_last_error().decode("utf-8", "replace"))
+
+    @property
+    def ptr(self) -> c_void_p:
+        if not self._p:
+            raise RuntimeError("peer area is closed")
+        return self._p
+
+    def connect(self, handles: list) -> None:
+        blob = b"".join(handles)
+        assert len(blob) == self.world * self._hb
+        buf = (ctypes.c_ubyte * len(blob)).from_buffer_copy(blob)
+        self._check(lib().st_peer_connect(self.ptr, buf))
+
+    @property
+    def payload_ptr(self) -> int:
+        return int(lib().st_peer_payload(self.ptr))
+
+    @property
+    def payload_bytes(self) -> int:
+        return int(lib().st_peer_payload_bytes(self.ptr))
+
+    def broadcast(self, offset: int, nbytes: int, stream: int = 0) -> None:
+        self._check(lib().st_peer_broadcast(self.ptr, int(offset), int(nbytes), c_void_p(stream)))
+
+    def scatter(self, src_ptr: int, pos_ptr: int, count: int, esize: int, offset: int, span_elems: int,
+                count_dev_ptr: int = 0, stream: int = 0) -> None:
+        self._check(lib().st_peer_scatter(self.ptr, c_void_p(src_ptr), c_void_p(pos_ptr), int(count),
+                                          c_void_p(count_dev_ptr) if count_dev_ptr else None, int(esize), int(offset),
+                                          int(span_elems), c_void_p(stream)))
+
+    def signal(self, channel: int, value: int, stream: int = 0) -> None:
+        self._check(lib().st_peer_signal(self.ptr, int(channel), int(value) & 0xffffffff, c_void_p(stream)))
+
+    def wait(self, channel: int, value: int, stream: int = 0) -> None:
+        self._check(lib().st_peer_wait(self.ptr, int(channel), int(value) & 0xffffffff, c_void_p(stream)))
+
+    def status(self, stream: int = 0) -> None:
+        self._check(lib().st_peer_status(self.ptr, c_void_p(stream)))
+
+    def close(self) -> None:
+        p, self._p = getattr(self, "_p", None), None
+        if p and _lib is not None:
+            _lib.st_peer_destroy(p)
 
     def __del__(self):
         try:

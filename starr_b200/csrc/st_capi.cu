@@ -395,6 +395,28 @@ int st_update_deltas_device(st_tree *t, const int64_t *idx_dev, int64_t ni, cons
     return ST_OK;
 }
 
+int st_update_begin_device(st_tree *t, const int64_t *idx_dev, int64_t ni, const void *vals_dev, int64_t nv,
+                           void *delta_out_dev, void *stream)
+{
+    if (!t || ni < 0 || nv < 0 || t->kind != 0) return fail(ST_ERR_ARG, "st_update_begin_device: bad argument");
+    if (ni > 0 && nv == 0) return fail(ST_ERR_EMPTY_VALS, "%s", st_status_string(ST_ERR_EMPTY_VALS));
+    tree_lock lk(t);
+    device_guard g(t->device);
+    t->pending_split = 0;
+    if (ni == 0 && nv == 0) return ST_OK;
+    CU(st::launch_update(t, idx_dev, ni, vals_dev, nv, delta_out_dev, nullptr, (cudaStream_t)stream, false, 1));
+    return ST_OK;
+}
+
+int st_update_finish_device(st_tree *t, void *stream)
+{
+    if (!t || t->kind != 0) return fail(ST_ERR_ARG, "st_update_finish_device: bad argument");
+    tree_lock lk(t);
+    device_guard g(t->device);
+    CU(st::launch_update(t, nullptr, 0, nullptr, 0, nullptr, nullptr, (cudaStream_t)stream, false, 2));
+    return ST_OK;
+}
+
 int st_apply_deltas_device(st_tree *t, const int64_t *idx_dev, int64_t ni, const void *deltas_dev, void *stream)
 {
     if (!t || ni < 0 || (ni > 0 && !deltas_dev)) return fail(ST_ERR_ARG, "st_apply_deltas_device: bad argument");
@@ -452,6 +474,16 @@ int st_shard_plan_device(st_tree *t, const int64_t *ids_dev, int64_t m, int shif
                          int32_t *slot_out_dev, int64_t *own_ids_out_dev, void *own_payload_out_dev, int result_slot,
                          int64_t *counts_out_host, void *stream)
 {
+    return st_shard_plan_pos_device(t, ids_dev, m, shift, shards, rank, payload_dev, npayload, check_negative, shard_out_dev,
+                                    slot_out_dev, own_ids_out_dev, own_payload_out_dev, nullptr, result_slot, counts_out_host,
+                                    stream);
+}
+
+int st_shard_plan_pos_device(st_tree *t, const int64_t *ids_dev, int64_t m, int shift, int shards, int rank,
+                             const void *payload_dev, int64_t npayload, int check_negative, uint8_t *shard_out_dev,
+                             int32_t *slot_out_dev, int64_t *own_ids_out_dev, void *own_payload_out_dev,
+                             int32_t *own_pos_out_dev, int result_slot, int64_t *counts_out_host, void *stream)
+{
     if (!t || m <= 0 || shards < 1 || shards > 64 || rank < 0 || rank >= shards || shift < 0 || shift > 62 ||
         result_slot < 0 || result_slot >= kPlanSlots || !ids_dev || !shard_out_dev || !slot_out_dev ||
         ((own_payload_out_dev || check_negative) && (!payload_dev || npayload <= 0)))
@@ -470,9 +502,10 @@ int st_shard_plan_device(st_tree *t, const int64_t *ids_dev, int64_t m, int shif
     CU(c.commit());
     void *scratch = c.take(bytes);
     unsigned int *counts_dev = (unsigned int *)((char *)t->d_pin + t->pin_bytes + result_slot * kPlanSlotBytes);
+    if (m > 0x7fffffffLL && own_pos_out_dev) return fail(ST_ERR_TOO_LARGE, "st_shard_plan_pos_device: batch positions are 32-bit");
     CU(st::launch_shard_plan(t, ids_dev, m, shift, shards, rank, payload_dev, npayload, check_negative, shard_out_dev,
                              slot_out_dev, own_ids_out_dev, own_payload_out_dev, scratch, counts_dev,
-                             (cudaStream_t)stream));
+                             (cudaStream_t)stream, own_pos_out_dev));
     CU(cudaEventRecord(t->plan_ev, (cudaStream_t)stream));
     t->plan_pending = 1;
     if (!counts_out_host) return ST_OK;   // asynchronous: st_shard_plan_wait collects the result

@@ -55,6 +55,8 @@ struct st_tree {
     // The reference's functions hold the GIL (SURVEY 8b "Threading"); here every entry point that touches the
     // handle's host-side state or staging areas takes this lock, so concurrent callers on ONE tree serialise.
     std::recursive_mutex mu;
+    int64_t pending_ni = 0;    // split update (st_update_begin_device): batch size waiting for st_update_finish_device
+    int pending_split = 0;
     int64_t stat_updates = 0;  // updates submitted since the last st_update_counters(reset)
     // pipelined host step (st_per_step_host_submit / _wait): two slots of device staging + streams + events
     struct host_slot {
@@ -73,6 +75,15 @@ struct st_tree {
 
 // launchers implemented in the .cu files; every one only enqueues on `s`
 namespace st {
+
+// epilogue of the sharded sample (st_peer.cu): instead of out[i], the GLOBAL leaf index of query i is
+// stored at position pos[i] of an int64 array in the exchange buffer of EVERY rank (peer stores)
+struct search_push {
+    char *base[64];
+    int n = 0;                     // 0: no push (plain search)
+    const int32_t *pos = nullptr;
+    int64_t index_offset = 0;
+};
 
 // process-wide count of kernels of THIS library that were launched (bench.py's gpu_launches)
 extern std::atomic<unsigned long long> g_kernel_launches;
@@ -99,7 +110,9 @@ cudaError_t launch_check_leaves(st_tree *t, cudaStream_t s);  // sets STF_NEG_AR
 cudaError_t launch_build(st_tree *t, cudaStream_t s);         // skipped on device if status != 0
 // m_dev (nullable): device-side query count, the launch covers min(m, *m_dev) queries
 cudaError_t launch_search(const st_tree *t, const void *vals, int64_t m, int64_t *out, cudaStream_t s,
-                          const unsigned int *m_dev = nullptr);
+                          const unsigned int *m_dev = nullptr, const search_push *push = nullptr);
+cudaError_t launch_route_compact(const st_tree *top, const double *u, int64_t m, int rank, void *own_resid,
+                                 int32_t *own_pos, unsigned int *own_count, cudaStream_t s);
 // prob (nullable): prio / root in the tree dtype for f32 / f64, in float64 for integer trees
 cudaError_t launch_sample(const st_tree *t, const double *u, int64_t m, int64_t *out, void *prio,
                           void *resid, cudaStream_t s, void *prob = nullptr);
@@ -121,7 +134,7 @@ size_t update_workspace_bytes(const st_tree *t, int64_t batch);
 // per-update differences to the proper ancestors only (vals ignored, leaves untouched).
 // assign: the leaf becomes vals[j] itself instead of fl(leaf + fl(vals[j] - leaf)) (starr.experimental twin)
 cudaError_t launch_update(st_tree *t, const int64_t *idx, int64_t ni, const void *vals, int64_t nv,
-                          void *delta_out, const void *deltas_in, cudaStream_t s, bool assign = false);
+                          void *delta_out, const void *deltas_in, cudaStream_t s, bool assign = false, int phase = 0);
 int64_t update_max_chunk();
 // tiny power-of-two float tree: ordered fold of all m differences into the ancestors of leaf[j]
 cudaError_t launch_fold_by_leaf(st_tree *t, const int64_t *leaf, const void *deltas, int64_t m, cudaStream_t s);
@@ -139,7 +152,7 @@ size_t shard_plan_scratch_bytes(int64_t m, int shards);
 cudaError_t launch_shard_plan(st_tree *t, const int64_t *ids, int64_t m, int shift, int shards, int rank,
                               const void *payload, int64_t npayload, int check_negative, uint8_t *shard_out,
                               int32_t *slot_out, int64_t *own_ids_out, void *own_payload_out, void *scratch,
-                              unsigned int *counts_out, cudaStream_t s);
+                              unsigned int *counts_out, cudaStream_t s, int32_t *own_pos_out = nullptr);
 cudaError_t launch_shard_expand_values(const st_tree *t, const uint8_t *shard, const int32_t *slot, int64_t m,
                                        const void *slabs, int64_t slab_stride, void *out, cudaStream_t s);
 cudaError_t launch_shard_expand_indices(const st_tree *t, const uint8_t *shard, const int32_t *slot, int64_t m,

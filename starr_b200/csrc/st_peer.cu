@@ -1,0 +1,367 @@
+// st_peer.cu -- peer-memory exchange area of the subtree-sharded tree.
+//
+// The reference is single-process (no collective anywhere), so nothing is replaced
+// here; what is pinned is the RESULT: the sharded tree stays bit-identical to one reference tree.
+// This file is only the transport: every rank of one node owns one device buffer
+//
+//     [ flag page: flags[channel][source rank] (uint32) | payload ... ]
+//
+// whose CUDA IPC handle is exchanged once (through torch.distributed, by the Python layer); after
+// st_peer_connect every rank holds a device-visible pointer to every other rank's buffer (NVLink /
+// NVSwitch peer access).  Kernels of rank r then store their results STRAIGHT into the buffers of
+// all ranks at the batch-order position of every element, so no all-gather, no slab layout and no
+// "back to batch order" pass is needed:
+//
+//   scatter    payload_q[off + pos[k]] = src[k]  for every rank q   (update: the differences d_j)
+//   broadcast  payload_q[off .. off+bytes) = payload_r[off ..)      (top-fold records, shard roots)
+//   search     st_search_push_device: the local descent writes the GLOBAL leaf index of query k to
+//              payload_q[off + 8 * pos[k]] on every rank                (sample)
+//   signal / wait   a release store of a step counter into flags[channel][r] of every rank, and a
+//              spin (acquire loads, bounded by a timeout) until all sources reached the step.
+// All of it is stream-ordered; nothing synchronises with the host.
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "st_common.cuh"
+
+namespace st {
+
+constexpr int PEER_MAX = 64;
+constexpr int PEER_CHANNELS = 16;
+constexpr size_t PEER_FLAG_BYTES = 8192;   // 16 channels x 64 sources x 4 B, rounded up
+
+struct peer_ptrs {
+    char *base[PEER_MAX];   // start of every rank's buffer (flag page first)
+    int n;
+};
+
+}  // namespace st
+
+struct st_peer {
+    int device = 0, rank = 0, world = 1;
+    size_t payload_bytes = 0;
+    char *local = nullptr;
+    bool opened[st::PEER_MAX] = {};
+    st::peer_ptrs ptrs{};
+    unsigned int *d_err = nullptr;   // bit 0: a wait timed out
+    unsigned int *h_err = nullptr;
+};
+
+namespace st {
+
+__device__ __forceinline__ unsigned long long gtimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__global__ void peer_signal_kernel(peer_ptrs pp, int rank, int channel, unsigned int value)
+{
+    const int q = threadIdx.x;
+    if (q >= pp.n) return;
+    __threadfence_system();   // everything this stream stored before (earlier kernels) is ordered in front of the flag
+    unsigned int *f = reinterpret_cast<unsigned int *>(pp.base[q]) + channel * PEER_MAX + rank;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(value) : "memory");
+}
+
+__global__ void peer_wait_kernel(const unsigned int *flags, int channel, unsigned int value, int world,
+                                 unsigned long long timeout_ns, unsigned int *err)
+{
+    const int q = threadIdx.x;
+    if (q >= world) return;
+    const unsigned int *f = flags + channel * PEER_MAX + q;
+    const unsigned long long t0 = gtimer_ns();
+    for (;;) {
+        unsigned int v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+        if ((int)(v - value) >= 0) break;
+        if (gtimer_ns() - t0 > timeout_ns) {   // a rank died or never launched: do not hang the GPU
+            atomicOr(err, 1u);
+            break;
+        }
+        __nanosleep(200);
+    }
+}
+
+// payload_q[off .. off + bytes) = local payload[off ..) for every q != rank (16-byte vectors)
+__global__ void __launch_bounds__(256) peer_broadcast_kernel(peer_ptrs pp, int rank, size_t off, size_t bytes)
+{
+    const size_t nvec = bytes / 16;
+    const int4 *src = reinterpret_cast<const int4 *>(pp.base[rank] + off);
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+        const int4 v = src[i];
+        for (int q = 0; q < pp.n; ++q)
+            if (q != rank) reinterpret_cast<int4 *>(pp.base[q] + off)[i] = v;
+    }
+}
+
+// payload_q[off + pos[k] * sizeof(T)] = src[k] for EVERY q (the local copy included)
+template <typename T>
+__global__ void __launch_bounds__(256) peer_scatter_kernel(peer_ptrs pp, size_t off, const T *__restrict__ src,
+                                                           const int32_t *__restrict__ pos, int64_t count,
+                                                           const unsigned int *__restrict__ count_dev)
+{
+    if (count_dev) {
+        const int64_t c = (int64_t)*count_dev;
+        if (c < count) count = c;
+    }
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += stride) {
+        const T v = src[k];
+        const size_t at = off + (size_t)pos[k] * sizeof(T);
+        for (int q = 0; q < pp.n; ++q) *reinterpret_cast<T *>(pp.base[q] + at) = v;
+    }
+}
+
+// Top-tree routing of a replicated query batch (the first g levels of the reference descent,
+// pyx:96-113, on the replicated top tree) fused with the selection of this rank's queries:
+// the queries whose descent ends in top leaf `rank` are appended (any order: every result is
+// addressed by its batch position later) with the prefix that is left over for the local descent.
+template <typename T>
+__global__ void __launch_bounds__(256) route_compact_kernel(const T *__restrict__ H, int nleaves, int depth,
+                                                            const double *__restrict__ u, int64_t m, int rank,
+                                                            T *__restrict__ own_resid, int32_t *__restrict__ own_pos,
+                                                            unsigned int *__restrict__ own_count)
+{
+    __shared__ T top[2 * PEER_MAX];
+    for (int i = threadIdx.x; i < 2 * nleaves; i += blockDim.x) top[i] = H[i];
+    __syncthreads();
+    const T root = top[1];
+    const int lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t rounds = (m + stride - 1) / stride;
+    for (int64_t r = 0; r < rounds; ++r) {
+        const int64_t i = r * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        bool mine = false;
+        T p = T(0);
+        if (i < m) {
+            // (root * u).astype(dtype), sumtree_array.py:420
+            if constexpr (sizeof(T) == 4 && is_float_t<T>::value) p = __double2float_rn(__dmul_rn((double)root, u[i]));
+            else if constexpr (is_float_t<T>::value) p = __dmul_rn(root, u[i]);
+            else p = (T)__dmul_rn((double)root, u[i]);
+            uint32_t h = 1;
+            for (int lev = 0; lev < depth; ++lev) {
+                const T lv = top[2 * h];
+                if (p >= lv) { p = t_sub<T>(p, lv); h = 2 * h + 1; } else { h = 2 * h; }
+            }
+            mine = ((int)h - nleaves == rank);
+        }
+        const unsigned int bal = __ballot_sync(0xffffffffu, mine);
+        if (bal) {
+            unsigned int base = 0;
+            if (lane == (__ffs(bal) - 1)) base = atomicAdd(own_count, (unsigned int)__popc(bal));
+            base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
+            if (mine) {
+                const unsigned int at = base + __popc(bal & ((1u << lane) - 1u));
+                own_resid[at] = p;
+                own_pos[at] = (int32_t)i;
+            }
+        }
+    }
+}
+
+cudaError_t launch_route_compact(const st_tree *top, const double *u, int64_t m, int rank, void *own_resid,
+                                 int32_t *own_pos, unsigned int *own_count, cudaStream_t s)
+{
+    if (top->n > PEER_MAX || (top->n & (top->n - 1))) return cudaErrorInvalidValue;
+    cudaError_t e = cudaMemsetAsync(own_count, 0, sizeof(unsigned int), s);
+    if (e != cudaSuccess || m <= 0) return e;
+    ST_DISPATCH(top->dtype, {
+        ++g_kernel_launches;
+        route_compact_kernel<T><<<grid_for(m, 256 * 4, (int64_t)top->sm_count * 8), 256, 0, s>>>(
+            (const T *)top->heap, (int)top->n, top->depth, u, m, rank, (T *)own_resid, own_pos, own_count);
+    });
+    return cudaGetLastError();
+}
+
+}  // namespace st
+
+namespace {
+thread_local char g_perr[256] = "";
+int pfail(int status, const char *msg, cudaError_t e = cudaSuccess)
+{
+    if (e != cudaSuccess) snprintf(g_perr, sizeof(g_perr), "%s: %s", msg, cudaGetErrorString(e));
+    else snprintf(g_perr, sizeof(g_perr), "%s", msg);
+    return status;
+}
+#define PCU(call)                                                     \
+    do {                                                              \
+        cudaError_t e__ = (call);                                     \
+        if (e__ != cudaSuccess) return pfail(ST_ERR_CUDA, #call, e__); \
+    } while (0)
+
+struct dev_guard {
+    int prev = -1;
+    explicit dev_guard(int dev) { if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) cudaSetDevice(dev); }
+    ~dev_guard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+}  // namespace
+
+extern "C" {
+
+const char *st_peer_last_error(void) { return g_perr; }
+
+int st_peer_handle_bytes(void) { return (int)sizeof(cudaIpcMemHandle_t); }
+
+int st_peer_create(int device, int rank, int world, int64_t payload_bytes, st_peer **out, unsigned char *handle_out)
+{
+    if (!out || !handle_out || world < 1 || world > st::PEER_MAX || rank < 0 || rank >= world || payload_bytes < 0)
+        return pfail(ST_ERR_ARG, "st_peer_create: bad argument");
+    *out = nullptr;
+    dev_guard g(device);
+    st_peer *p = new (std::nothrow) st_peer();
+    if (!p) return pfail(ST_ERR_ARG, "st_peer_create: out of host memory");
+    p->device = device; p->rank = rank; p->world = world;
+    p->payload_bytes = ((size_t)payload_bytes + 255) & ~(size_t)255;
+    const size_t total = st::PEER_FLAG_BYTES + p->payload_bytes;
+    cudaError_t e = cudaMalloc((void **)&p->local, total);      // plain cudaMalloc: IPC-exportable
+    if (e == cudaSuccess) e = cudaMemset(p->local, 0, total);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&p->d_err, sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMemset(p->d_err, 0, sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMallocHost((void **)&p->h_err, sizeof(unsigned int));
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p->local);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        st_peer_destroy(p);
+        return pfail(ST_ERR_CUDA, "st_peer_create", e);
+    }
+    memcpy(handle_out, &h, sizeof(h));
+    p->ptrs.n = world;
+    p->ptrs.base[rank] = p->local;
+    *out = p;
+    return ST_OK;
+}
+
+int st_peer_connect(st_peer *p, const unsigned char *handles)
+{
+    if (!p || !handles) return pfail(ST_ERR_ARG, "st_peer_connect: bad argument");
+    dev_guard g(p->device);
+    for (int q = 0; q < p->world; ++q) {
+        if (q == p->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + (size_t)q * sizeof(h), sizeof(h));
+        void *ptr = nullptr;
+        PCU(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        p->ptrs.base[q] = (char *)ptr;
+        p->opened[q] = true;
+    }
+    return ST_OK;
+}
+
+int st_peer_destroy(st_peer *p)
+{
+    if (!p) return ST_OK;
+    dev_guard g(p->device);
+    cudaDeviceSynchronize();
+    for (int q = 0; q < p->world; ++q)
+        if (p->opened[q]) cudaIpcCloseMemHandle(p->ptrs.base[q]);
+    if (p->local) cudaFree(p->local);
+    if (p->d_err) cudaFree(p->d_err);
+    if (p->h_err) cudaFreeHost(p->h_err);
+    delete p;
+    return ST_OK;
+}
+
+void *st_peer_payload(const st_peer *p) { return p ? p->local + st::PEER_FLAG_BYTES : nullptr; }
+int64_t st_peer_payload_bytes(const st_peer *p) { return p ? (int64_t)p->payload_bytes : -1; }
+
+int st_peer_broadcast(st_peer *p, int64_t offset, int64_t bytes, void *stream)
+{
+    if (!p || offset < 0 || bytes < 0 || (offset & 15) || (bytes & 15) || (size_t)(offset + bytes) > p->payload_bytes)
+        return pfail(ST_ERR_ARG, "st_peer_broadcast: bad argument (offset and size must be multiples of 16 inside the payload)");
+    if (bytes == 0 || p->world == 1) return ST_OK;
+    dev_guard g(p->device);
+    ++st::g_kernel_launches;
+    const unsigned grid = st::grid_for(bytes / 16, 256, 592);
+    st::peer_broadcast_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p->ptrs, p->rank, st::PEER_FLAG_BYTES + (size_t)offset,
+                                                                     (size_t)bytes);
+    PCU(cudaGetLastError());
+    return ST_OK;
+}
+
+int st_peer_scatter(st_peer *p, const void *src_dev, const int32_t *pos_dev, int64_t count, const uint32_t *count_dev,
+                    int esize, int64_t offset, int64_t span_elems, void *stream)
+{
+    if (!p || count < 0 || offset < 0 || (offset % 8) || (esize != 1 && esize != 2 && esize != 4 && esize != 8) ||
+        (count > 0 && (!src_dev || !pos_dev)) || (size_t)(offset + span_elems * esize) > p->payload_bytes)
+        return pfail(ST_ERR_ARG, "st_peer_scatter: bad argument");
+    if (count == 0) return ST_OK;
+    dev_guard g(p->device);
+    ++st::g_kernel_launches;
+    const unsigned grid = st::grid_for(count, 256, 1184);
+    const size_t off = st::PEER_FLAG_BYTES + (size_t)offset;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (esize) {
+    case 1: st::peer_scatter_kernel<uint8_t><<<grid, 256, 0, s>>>(p->ptrs, off, (const uint8_t *)src_dev, pos_dev, count, count_dev); break;
+    case 2: st::peer_scatter_kernel<uint16_t><<<grid, 256, 0, s>>>(p->ptrs, off, (const uint16_t *)src_dev, pos_dev, count, count_dev); break;
+    case 4: st::peer_scatter_kernel<uint32_t><<<grid, 256, 0, s>>>(p->ptrs, off, (const uint32_t *)src_dev, pos_dev, count, count_dev); break;
+    default: st::peer_scatter_kernel<uint64_t><<<grid, 256, 0, s>>>(p->ptrs, off, (const uint64_t *)src_dev, pos_dev, count, count_dev); break;
+    }
+    PCU(cudaGetLastError());
+    return ST_OK;
+}
+
+int st_peer_signal(st_peer *p, int channel, unsigned int value, void *stream)
+{
+    if (!p || channel < 0 || channel >= st::PEER_CHANNELS) return pfail(ST_ERR_ARG, "st_peer_signal: bad argument");
+    dev_guard g(p->device);
+    ++st::g_kernel_launches;
+    st::peer_signal_kernel<<<1, st::PEER_MAX, 0, (cudaStream_t)stream>>>(p->ptrs, p->rank, channel, value);
+    PCU(cudaGetLastError());
+    return ST_OK;
+}
+
+int st_peer_wait(st_peer *p, int channel, unsigned int value, void *stream)
+{
+    if (!p || channel < 0 || channel >= st::PEER_CHANNELS) return pfail(ST_ERR_ARG, "st_peer_wait: bad argument");
+    dev_guard g(p->device);
+    ++st::g_kernel_launches;
+    st::peer_wait_kernel<<<1, st::PEER_MAX, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned int *>(p->local), channel,
+                                                                      value, p->world, 20ull * 1000000000ull, p->d_err);
+    PCU(cudaGetLastError());
+    return ST_OK;
+}
+
+int st_peer_status(st_peer *p, void *stream)
+{
+    if (!p) return pfail(ST_ERR_ARG, "st_peer_status: bad argument");
+    dev_guard g(p->device);
+    PCU(cudaMemcpyAsync(p->h_err, p->d_err, sizeof(unsigned int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    PCU(cudaStreamSynchronize((cudaStream_t)stream));
+    if (*p->h_err) return pfail(ST_ERR_CUDA, "st_peer_wait timed out: a rank of the sharded tree did not reach the exchange");
+    return ST_OK;
+}
+
+int st_route_compact_device(const st_tree *top, const double *u_dev, int64_t m, int rank, void *own_resid_out_dev,
+                            int32_t *own_pos_out_dev, uint32_t *own_count_out_dev, void *stream)
+{
+    if (!top || m < 0 || rank < 0 || !own_count_out_dev || (m > 0 && (!u_dev || !own_resid_out_dev || !own_pos_out_dev)) ||
+        m > 0x7fffffffLL)
+        return pfail(ST_ERR_ARG, "st_route_compact_device: bad argument");
+    dev_guard g(top->device);
+    PCU(st::launch_route_compact(top, u_dev, m, rank, own_resid_out_dev, own_pos_out_dev, own_count_out_dev, (cudaStream_t)stream));
+    return ST_OK;
+}
+
+int st_search_push_device(const st_tree *t, const void *vals_dev, int64_t m_max, const uint32_t *m_dev,
+                          const int32_t *pos_dev, int64_t index_offset, st_peer *p, int64_t payload_offset,
+                          int64_t span_elems, void *stream)
+{
+    if (!t || !p || m_max < 0 || !m_dev || payload_offset < 0 || (payload_offset % 8) ||
+        (size_t)(payload_offset + span_elems * 8) > p->payload_bytes || (m_max > 0 && (!vals_dev || !pos_dev)))
+        return pfail(ST_ERR_ARG, "st_search_push_device: bad argument");
+    dev_guard g(t->device);
+    st::search_push push;
+    push.n = p->ptrs.n;
+    for (int q = 0; q < p->ptrs.n; ++q) push.base[q] = p->ptrs.base[q] + st::PEER_FLAG_BYTES + payload_offset;
+    push.pos = pos_dev;
+    push.index_offset = index_offset;
+    PCU(st::launch_search(t, vals_dev, m_max, nullptr, (cudaStream_t)stream, m_dev, &push));
+    return ST_OK;
+}
+
+}  // extern "C"

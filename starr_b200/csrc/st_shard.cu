@@ -157,7 +157,8 @@ __global__ void __launch_bounds__(SH_THREADS, 3) shard_slot_kernel(const int64_t
                                                                    int64_t npayload, const uint8_t *__restrict__ shard8,
                                                                    const unsigned int *__restrict__ tile_off,
                                                                    int64_t ntiles, int32_t *__restrict__ slot_out,
-                                                                   int64_t *__restrict__ own_ids, T *__restrict__ own_payload)
+                                                                   int64_t *__restrict__ own_ids, T *__restrict__ own_payload,
+                                                                   int32_t *__restrict__ own_pos)
 {
     typedef cub::BlockScan<pk128, SH_THREADS> scan_t;
     __shared__ typename scan_t::TempStorage tmp;
@@ -202,13 +203,14 @@ __global__ void __launch_bounds__(SH_THREADS, 3) shard_slot_kernel(const int64_t
         if (tile0 + i < m) slot_out[tile0 + i] = s_slot[i];
     }
     // compaction of this rank's elements: consecutive threads write consecutive slots
-    if (!own_ids && !own_payload) return;
+    if (!own_ids && !own_payload && !own_pos) return;
     const int64_t origin = (int64_t)rank << shift;
     const unsigned int nown = s_nown, first = s_off[rank];
     for (unsigned int i = tid; i < nown; i += SH_THREADS) {
         const int64_t j = tile0 + s_own[i];
         if (own_ids) own_ids[first + i] = ids[j] - origin;
         if (own_payload) own_payload[first + i] = payload[j < npayload ? j : j % npayload];
+        if (own_pos) own_pos[first + i] = (int32_t)j;   // batch position: where this element's results go on every rank
     }
 }
 
@@ -249,7 +251,7 @@ size_t shard_plan_scratch_bytes(int64_t m, int shards)   // per-tile counts of e
 cudaError_t launch_shard_plan(st_tree *t, const int64_t *ids, int64_t m, int shift, int shards, int rank,
                               const void *payload, int64_t npayload, int check_negative, uint8_t *shard_out,
                               int32_t *slot_out, int64_t *own_ids_out, void *own_payload_out, void *scratch,
-                              unsigned int *counts_out, cudaStream_t s)
+                              unsigned int *counts_out, cudaStream_t s, int32_t *own_pos_out)
 {
     if (shards < 1 || shards > SH_MAX || rank < 0 || rank >= shards || shift < 0 || shift > 62)
         return cudaErrorInvalidValue;
@@ -270,7 +272,7 @@ cudaError_t launch_shard_plan(st_tree *t, const int64_t *ids, int64_t m, int shi
         shard_scan_kernel<<<(unsigned)shards, SH_THREADS, 0, s>>>(tile_counts, ntiles, counts_out, flags);
         shard_slot_kernel<T><<<(unsigned)ntiles, SH_THREADS, 0, s>>>(ids, m, shift, shards, rank, (const T *)payload,
                                                                     npayload, shard_out, tile_counts, ntiles, slot_out,
-                                                                    own_ids_out, (T *)own_payload_out);
+                                                                    own_ids_out, (T *)own_payload_out, own_pos_out);
     });
     return cudaGetLastError();
 }

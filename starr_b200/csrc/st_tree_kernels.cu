@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS)
 search_kernel(const T *__restrict__ H, uint32_t n, int depth, const void *__restrict__ in,
               int64_t m, int64_t *__restrict__ out, T *__restrict__ prio, T *__restrict__ resid,
               uint32_t stage_nodes, const unsigned int *__restrict__ m_dev,
-              typename prob_type<T>::type *__restrict__ prob)
+              typename prob_type<T>::type *__restrict__ prob, const search_push push)
 {
     if (m_dev) {   // the host did not know the count when it launched (sharded sample: st_shard_plan_device)
         const int64_t md = (int64_t)*m_dev;
@@ -327,7 +327,14 @@ search_kernel(const T *__restrict__ H, uint32_t n, int depth, const void *__rest
         for (int q = 0; q < SEARCH_Q; ++q) {
             const int64_t i = base + threadIdx.x + (int64_t)q * SEARCH_THREADS;
             if (i < m) {
-                out[i] = (int64_t)h[q] - (int64_t)n;
+                if (push.n) {
+                    // sharded sample: the global leaf index goes straight into every rank's result buffer
+                    const int64_t g = (int64_t)h[q] - (int64_t)n + push.index_offset;
+                    const int32_t at = push.pos[i];
+                    for (int r = 0; r < push.n; ++r) reinterpret_cast<int64_t *>(push.base[r])[at] = g;
+                } else {
+                    out[i] = (int64_t)h[q] - (int64_t)n;
+                }
                 if (prio || prob) {
                     const T pv = __ldcg(H + h[q]);
                     if (prio) prio[i] = pv;
@@ -342,7 +349,8 @@ search_kernel(const T *__restrict__ H, uint32_t n, int depth, const void *__rest
 
 template <typename T, bool UNIFORM, int THREADS, int Q>
 static cudaError_t launch_search_cfg(const st_tree *t, const void *in, int64_t m, int64_t *out, void *prio,
-                                     void *resid, cudaStream_t s, const unsigned int *m_dev, void *prob)
+                                     void *resid, cudaStream_t s, const unsigned int *m_dev, void *prob,
+                                     const search_push &push)
 {
     const uint32_t n = (uint32_t)t->n;
     const T *H = (const T *)t->heap;
@@ -367,31 +375,34 @@ static cudaError_t launch_search_cfg(const st_tree *t, const void *in, int64_t m
         unsigned g = grid_for(m, (int)per_block, (int64_t)t->sm_count * 3);
         ++g_kernel_launches;
         kern<<<g, THREADS, smem, s>>>(H, n, t->depth, in, m, out, (T *)prio, (T *)resid, stage_nodes, m_dev,
-                                      (typename prob_type<T>::type *)prob);
+                                      (typename prob_type<T>::type *)prob, push);
     } else {
         unsigned g = grid_for(m, (int)per_block, (int64_t)t->sm_count * 4);
         ++g_kernel_launches;
         search_kernel<T, false, UNIFORM, THREADS, Q><<<g, THREADS, 0, s>>>(H, n, t->depth, in, m, out, (T *)prio,
                                                                           (T *)resid, 0, m_dev,
-                                                                          (typename prob_type<T>::type *)prob);
+                                                                          (typename prob_type<T>::type *)prob, push);
     }
     return cudaGetLastError();
 }
 
 template <typename T, bool UNIFORM>
 static cudaError_t launch_search_t(const st_tree *t, const void *in, int64_t m, int64_t *out, void *prio,
-                                   void *resid, cudaStream_t s, const unsigned int *m_dev = nullptr, void *prob = nullptr)
+                                   void *resid, cudaStream_t s, const unsigned int *m_dev = nullptr, void *prob = nullptr,
+                                   const search_push *push = nullptr)
 {
     if (m <= 0) return cudaSuccess;
+    const search_push none{};
+    const search_push &ps = push ? *push : none;
     if (m >= (int64_t)t->sm_count * SEARCH_THREADS_BIG * SEARCH_Q_BIG / 4)
-        return launch_search_cfg<T, UNIFORM, SEARCH_THREADS_BIG, SEARCH_Q_BIG>(t, in, m, out, prio, resid, s, m_dev, prob);
-    return launch_search_cfg<T, UNIFORM, SEARCH_THREADS_SMALL, SEARCH_Q_SMALL>(t, in, m, out, prio, resid, s, m_dev, prob);
+        return launch_search_cfg<T, UNIFORM, SEARCH_THREADS_BIG, SEARCH_Q_BIG>(t, in, m, out, prio, resid, s, m_dev, prob, ps);
+    return launch_search_cfg<T, UNIFORM, SEARCH_THREADS_SMALL, SEARCH_Q_SMALL>(t, in, m, out, prio, resid, s, m_dev, prob, ps);
 }
 
 cudaError_t launch_search(const st_tree *t, const void *vals, int64_t m, int64_t *out, cudaStream_t s,
-                          const unsigned int *m_dev)
+                          const unsigned int *m_dev, const search_push *push)
 {
-    ST_DISPATCH(t->dtype, return (launch_search_t<T, false>(t, vals, m, out, nullptr, nullptr, s, m_dev)));
+    ST_DISPATCH(t->dtype, return (launch_search_t<T, false>(t, vals, m, out, nullptr, nullptr, s, m_dev, nullptr, push)));
     return cudaSuccess;
 }
 

@@ -314,49 +314,8 @@ __global__ void __launch_bounds__(256) int_propagate_kernel(T *__restrict__ H, u
 }
 
 // -----------------------------------------------------------------------------------------
-// 3b. float propagation: per-level ordered segment folds
+// 3b. float propagation: ordered segment folds (segments come from st_partition.cuh)
 // -----------------------------------------------------------------------------------------
-// Level l of the pass sees the batch ordered by (key >> (depth-l), j).  The head thread of each
-// segment folds short segments itself and queues long ones for the warp-cooperative kernel.
-template <typename T>
-__global__ void __launch_bounds__(256) fold_level_kernel(T *__restrict__ H, uint32_t n, int depth, int level,
-                                                         const uint32_t *__restrict__ keys,
-                                                         const T *__restrict__ d, int m,
-                                                         seg_entry *__restrict__ queue_long,
-                                                         seg_entry *__restrict__ queue_med, unsigned int *status)
-{
-    if (status[SW_STATUS]) return;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m) return;
-    const int sh = depth - level;
-    const uint32_t key = keys[i];
-    const uint32_t node = key >> sh;
-    if (i > 0 && (keys[i - 1] >> sh) == node) return;  // not a segment head
-    if (level >= key_leaf_level(key, 2ull * n, depth)) return;  // `node` is the leaf itself
-    int e = i + 1;
-    while (e < m && e - i <= SHORT_SEG && (keys[e] >> sh) == node) ++e;
-    if (e - i <= SHORT_SEG) {
-        T acc = H[node];
-        for (int x = i; x < e; ++x) acc = t_add<T>(acc, d[x]);
-        H[node] = acc;
-    } else {
-        // upper bound of `node` in the level-sorted keys
-        int lo = e, hi = m;
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if ((keys[mid] >> sh) <= node) lo = mid + 1; else hi = mid;
-        }
-        const int len = lo - i;
-        if (len > MEDIUM_SEG) {
-            const unsigned int slot = atomicAdd(status + SW_QCOUNT, 1u);
-            queue_long[slot] = seg_entry{level, i, len, node};
-        } else {
-            const unsigned int slot = atomicAdd(status + SW_QCOUNT_MED, 1u);
-            queue_med[slot] = seg_entry{level, i, len, node};
-        }
-    }
-}
-
 template <typename T>
 __device__ __forceinline__ void retire_warps(T *__restrict__ H, uint32_t n, int depth, const uint32_t *__restrict__ key0,
                                              const uint32_t *__restrict__ lev_key, const T *__restrict__ lev_d,
@@ -796,8 +755,10 @@ __global__ void __launch_bounds__(FOLD_THREADS) fold_top_maps_kernel(const T *__
 template <typename T>
 static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *idx, int m, const T *vals,
                                 int64_t nv, int64_t j0, int64_t B, T *delta_out, const T *deltas_in,
-                                bool small, bool assign, cudaStream_t s)
+                                bool small, bool assign, cudaStream_t s, int phase = 0)
 {
+    // phase 0: the whole update.  phase 1: up to and including the leaf pass (the differences d_j exist and
+    // delta_out is filled); phase 2: the rest (ancestors), for the batch phase 1 left in the workspace.
     // deltas_in != nullptr: "apply deltas" mode (sharded top tree): the per-update
     // differences are given, the leaves are not touched, only proper ancestors are folded.
     const uint32_t n = (uint32_t)t->n;
@@ -808,6 +769,7 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
 
     auto mark = [&](int k) { if (t->profile) cudaEventRecord(t->prof_ev[k], s); };
     if constexpr (is_float_t<T>::value) {
+        if (small && phase == 2) return cudaSuccess;
         if (small) {
             // one CTA does validation, sort, leaf pass and the whole ordered partition (st_update_small.cuh)
             small_params<T> sp;
@@ -839,13 +801,16 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
             return cudaGetLastError();
         }
     }
-    mark(0);
-    ++g_kernel_launches;
-    make_keys_kernel<<<g, 256, 0, s>>>(idx, m, n, depth, w.keys_a, w.kj, w.j_a, status);
     size_t cb = w.cub_bytes;
     cudaError_t e = cudaSuccess;
     const T *d_batch = deltas_in;           // d in batch order
-    if (!deltas_in) {
+    if (phase == 2) d_batch = (const T *)w.dj;
+    if (phase != 2) {
+    mark(0);
+    ++g_kernel_launches;
+    make_keys_kernel<<<g, 256, 0, s>>>(idx, m, n, depth, w.keys_a, w.kj, w.j_a, status);
+    }
+    if (!deltas_in && phase != 2) {
         // floats only need the duplicates of a leaf adjacent: drop the partial low radix digit when the
         // groups this creates (2^gb neighbouring leaves) hold less than one update on average
         int gb = 0;
@@ -869,6 +834,7 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
             if (e != cudaSuccess) return e;
         }
     }
+    if (phase == 1) return cudaGetLastError();
 
     if constexpr (!is_float_t<T>::value) {
         ++g_kernel_launches;
@@ -884,59 +850,39 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
         mark(2);
         e = cudaMemcpyAsync(lev, d_batch, (size_t)m * sizeof(T), cudaMemcpyDeviceToDevice, s);
         if (e != cudaSuccess) return e;
-        static const bool use_v1 = getenv("ST_UPDATE_V1") != nullptr;   // A/B switch: per-level cub sorts
-        if (!use_v1) {
-            if (!t->coop_ok) return cudaErrorCooperativeLaunchTooLarge;
-            part_params<T> pp;
-            pp.H = H; pp.n = n; pp.depth = depth; pp.m = m;
-            pp.ntiles = (m + PART_TILE - 1) / PART_TILE;
-            pp.key0 = w.kj; pp.lev_key = w.lev_key;
-            pp.lev_d = lev; pp.lev_stride = B;
-            pp.sA = w.seg_sa; pp.eA = w.seg_ea; pp.sB = w.seg_sb; pp.eB = w.seg_eb;
-            pp.Z = w.zcount; pp.tilesum = w.tilesum;
-            pp.qlong = w.queue; pp.qmed = w.queue_med; pp.qhuge = w.queue_huge; pp.huge_off = w.huge_off;
-            pp.qret = w.queue_ret;
-            pp.status = status;
-            if (t->part_occ < 1) {   // per tree (one dtype, one device); the caller holds the tree's lock
-                int occ = 0;
-                e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, partition_levels_kernel<T>, PART_THREADS, 0);
-                if (e != cudaSuccess) return e;
-                if (occ < 1) return cudaErrorCooperativeLaunchTooLarge;
-                t->part_occ = occ;
-            }
-            const int occ = t->part_occ;
-            // balanced persistent grid: every CTA gets the same number of tiles (the grid barriers wait
-            // for the slowest CTA)
-            const int max_res = occ * t->sm_count;
-            const int per_cta = (pp.ntiles + max_res - 1) / max_res;
-            const int grid = (pp.ntiles + per_cta - 1) / per_cta;
-            void *args[] = {&pp};
-            ++g_kernel_launches;
-            e = cudaLaunchCooperativeKernel((const void *)partition_levels_kernel<T>, dim3(grid), dim3(PART_THREADS),
-                                            args, 0, s);
+        if (!t->coop_ok) return cudaErrorCooperativeLaunchTooLarge;
+        part_params<T> pp;
+        pp.H = H; pp.n = n; pp.depth = depth; pp.m = m;
+        pp.ntiles = (m + PART_TILE - 1) / PART_TILE;
+        pp.key0 = w.kj; pp.lev_key = w.lev_key;
+        pp.lev_d = lev; pp.lev_stride = B;
+        pp.sA = w.seg_sa; pp.eA = w.seg_ea; pp.sB = w.seg_sb; pp.eB = w.seg_eb;
+        pp.Z = w.zcount; pp.tilesum = w.tilesum;
+        pp.qlong = w.queue; pp.qmed = w.queue_med; pp.qhuge = w.queue_huge; pp.huge_off = w.huge_off;
+        pp.qret = w.queue_ret;
+        pp.status = status;
+        if (t->part_occ < 1) {   // per tree (one dtype, one device); the caller holds the tree's lock
+            int occ = 0;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, partition_levels_kernel<T>, PART_THREADS, 0);
             if (e != cudaSuccess) return e;
-        } else {
-        uint32_t *kcur = w.kj, *knext = w.keys_a, *kspare = w.keys_b;
-            for (int l = 0; l < depth; ++l) {
-                ++g_kernel_launches;
-                fold_level_kernel<T><<<g, 256, 0, s>>>(H, n, depth, l, kcur, lev + (int64_t)l * B, m, w.queue, w.queue_med,
-                                                       status);
-                if (l + 1 < depth) {
-                    cb = w.cub_bytes;
-                    e = cub::DeviceRadixSort::SortPairs(w.cub_tmp, cb, kcur, knext, lev + (int64_t)l * B,
-                                                        lev + (int64_t)(l + 1) * B, m, depth - l - 1, depth + 1, s);
-                    if (e != cudaSuccess) return e;
-                    if (l == 0) { kcur = knext; knext = kspare; }  // never overwrite kj
-                    else { uint32_t *tmp = kcur; kcur = knext; knext = tmp; }
-                }
-            }
+            if (occ < 1) return cudaErrorCooperativeLaunchTooLarge;
+            t->part_occ = occ;
         }
+        const int occ = t->part_occ;
+        // balanced persistent grid: every CTA gets the same number of tiles (the grid barriers wait
+        // for the slowest CTA)
+        const int max_res = occ * t->sm_count;
+        const int per_cta = (pp.ntiles + max_res - 1) / max_res;
+        const int grid = (pp.ntiles + per_cta - 1) / per_cta;
+        void *args[] = {&pp};
+        ++g_kernel_launches;
+        e = cudaLaunchCooperativeKernel((const void *)partition_levels_kernel<T>, dim3(grid), dim3(PART_THREADS),
+                                        args, 0, s);
+        if (e != cudaSuccess) return e;
         using REC = chunk_rec<typename fp_bits<T>::I>;
         mark(3);
-        if (!use_v1) {
-            ++g_kernel_launches;
-            retire_kernel<T><<<t->sm_count * 8, 256, 0, s>>>(H, n, depth, w.kj, w.lev_key, lev, B, w.queue_ret, status);
-        }
+        ++g_kernel_launches;
+        retire_kernel<T><<<t->sm_count * 8, 256, 0, s>>>(H, n, depth, w.kj, w.lev_key, lev, B, w.queue_ret, status);
         g_kernel_launches += 4;
         mark(4);
         // huge segments: chunk summaries -> first-pass stitch (pure map composition; a segment whose
@@ -1063,8 +1009,21 @@ cudaError_t launch_fold_by_leaf(st_tree *t, const int64_t *leaf, const void *del
 }
 
 cudaError_t launch_update(st_tree *t, const int64_t *idx, int64_t ni, const void *vals, int64_t nv,
-                          void *delta_out, const void *deltas_in, cudaStream_t s, bool assign)
+                          void *delta_out, const void *deltas_in, cudaStream_t s, bool assign, int phase)
 {
+    if (phase == 2) {
+        // second half of a split update (st_update_begin_device / st_update_finish_device)
+        if (!t->pending_split) return cudaSuccess;
+        t->pending_split = 0;
+        const int64_t cap2 = t->reserved_batch;
+        const int m2 = (int)t->pending_ni;
+        ST_DISPATCH(t->dtype, {
+            update_ws w = carve(t, cap2, (char *)t->ws.base);
+            return update_chunk<T>(t, w, nullptr, m2, nullptr, 0, 0, cap2, nullptr, nullptr, false, false, s, 2);
+        });
+        return cudaSuccess;
+    }
+    t->pending_split = 0;
     if (ni <= 0 && nv <= 0) return cudaSuccess;
     if (ni <= 0) {
         // nothing to apply, but the reference still scans ALL vals for negatives (pyx:37-39)
@@ -1106,12 +1065,20 @@ cudaError_t launch_update(st_tree *t, const int64_t *idx, int64_t ni, const void
                 idx, ni, (const T *)vals, deltas_in ? 0 : nv, t->n, t->d_status);
         }
         update_ws w = carve(t, cap, (char *)t->ws.base);
+        // a split update (phase 1) covers a batch that is one chunk of the multi-kernel pipeline; anything else
+        // is applied completely now and the second half has nothing left to do
+        const bool split = phase == 1 && !small && ni <= cap && !t->profile;
         for (int64_t j0 = 0; j0 < ni; j0 += cap) {
             const int m = (int)(ni - j0 < cap ? ni - j0 : cap);
             cudaError_t e = update_chunk<T>(t, w, idx + j0, m, (const T *)vals, nv, j0, cap,
                                             delta_out ? (T *)delta_out + j0 : nullptr,
-                                            deltas_in ? (const T *)deltas_in + j0 : nullptr, small, assign, s);
+                                            deltas_in ? (const T *)deltas_in + j0 : nullptr, small, assign, s,
+                                            split ? 1 : 0);
             if (e != cudaSuccess) return e;
+        }
+        if (split) {
+            t->pending_split = 1;
+            t->pending_ni = ni;
         }
     });
     return cudaGetLastError();

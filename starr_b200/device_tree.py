@@ -175,6 +175,42 @@ class DeviceSumTree:
                                          d.data_ptr(), _stream())
         return d
 
+    def update_begin_(self, idx: torch.Tensor, vals: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+        """First half of ``update_with_deltas_``: through the leaf pass -- ``out`` holds every d_j in stream
+        order behind this call, the ancestors are untouched until ``update_finish_``."""
+        idx = self._chk(idx.reshape(-1), torch.int64, "idx")
+        vals = self._chk(vals.reshape(-1), self.dtype, "vals")
+        if self._chk(out, self.dtype, "out") is not out or out.numel() < idx.numel():
+            raise TypeError("out must be contiguous and at least as long as idx")
+        with torch.cuda.device(self.device):
+            self._h.update_begin_device(idx.data_ptr(), idx.numel(), vals.data_ptr(), vals.numel(), out.data_ptr(), _stream())
+        return out
+
+    def update_finish_(self) -> "DeviceSumTree":
+        with torch.cuda.device(self.device):
+            self._h.update_finish_device(_stream())
+        return self
+
+    def route_compact(self, u: torch.Tensor, rank: int, own_resid: torch.Tensor, own_pos: torch.Tensor,
+                      own_count: torch.Tensor) -> None:
+        """On a top tree: route every uniform through the tree and append (left-over prefix, batch position) of
+        the queries that end in leaf ``rank`` to ``own_resid`` / ``own_pos``; ``own_count`` (uint32[1]) counts them."""
+        u = self._chk(u.reshape(-1), torch.float64, "u")
+        if own_resid.dtype != self.dtype or own_pos.dtype != torch.int32 or min(own_resid.numel(), own_pos.numel()) < u.numel():
+            raise TypeError("own_resid / own_pos must have the tree dtype / int32 and the size of u")
+        with torch.cuda.device(self.device):
+            self._h.route_compact_device(u.data_ptr(), u.numel(), rank, own_resid.data_ptr(), own_pos.data_ptr(),
+                                         own_count.data_ptr(), _stream())
+
+    def search_push(self, prefix_sums: torch.Tensor, count: torch.Tensor, pos: torch.Tensor, index_offset: int, peer,
+                    payload_offset: int, span_elems: int) -> None:
+        """``search`` over the first ``count[0]`` prefixes; result k (``index_offset`` + leaf) is stored as int64
+        at element ``pos[k]`` of the region at ``payload_offset`` of EVERY rank's exchange buffer."""
+        vals = self._chk(prefix_sums, self.dtype, "prefix_sums")
+        with torch.cuda.device(self.device):
+            self._h.search_push_device(vals.data_ptr(), vals.numel(), count.data_ptr(), pos.data_ptr(), index_offset, peer,
+                                       payload_offset, span_elems, _stream())
+
     def apply_deltas_(self, idx: torch.Tensor, deltas: torch.Tensor) -> "DeviceSumTree":
         """For j in batch order add ``deltas[j]`` to every proper ancestor of leaf ``idx[j]``
         (ordered folds for floats); the leaves themselves are not touched."""
@@ -209,7 +245,8 @@ class DeviceSumTree:
                                           recs.data_ptr(), _stream())
 
     def shard_plan(self, ids: torch.Tensor, shift: int, shards: int, rank: int, payload: torch.Tensor,
-                   check_negative: bool, want_ids: bool = True, out=None, result_slot: int = 0, wait: bool = True):
+                   check_negative: bool, want_ids: bool = True, out=None, result_slot: int = 0, wait: bool = True,
+                   own_pos: torch.Tensor | None = None):
         """Plan of one replicated batch of a sharded tree (``st_shard_plan_device``): returns
         ``(shard uint8[m], slot int32[m], own_ids int64[>=m] | None, own_payload dtype[>=m], counts)``;
         only the first ``counts[rank]`` entries of the ``own_*`` tensors are meaningful.  Waits for
@@ -228,11 +265,14 @@ class DeviceSumTree:
         shard, slot, own_ids, own_payload = out
         if min(shard.numel(), slot.numel(), own_payload.numel()) < m or (want_ids and own_ids.numel() < m):
             raise TypeError("plan buffers are smaller than the batch")
+        if own_pos is not None and (own_pos.dtype != torch.int32 or own_pos.numel() < m or not own_pos.is_contiguous()):
+            raise TypeError("own_pos must be a contiguous int32 tensor of the batch size")
         with torch.cuda.device(self.device):
-            counts = self._h.shard_plan_device(ids.data_ptr(), m, shift, shards, rank, payload.data_ptr(),
-                                               payload.numel(), check_negative, shard.data_ptr(), slot.data_ptr(),
-                                               own_ids.data_ptr() if want_ids else 0, own_payload.data_ptr(),
-                                               result_slot, _stream(), wait)
+            counts = self._h.shard_plan_pos_device(ids.data_ptr(), m, shift, shards, rank, payload.data_ptr(),
+                                                   payload.numel(), check_negative, shard.data_ptr(), slot.data_ptr(),
+                                                   own_ids.data_ptr() if want_ids else 0, own_payload.data_ptr(),
+                                                   own_pos.data_ptr() if own_pos is not None else 0,
+                                                   result_slot, _stream(), wait)
         return shard[:m], slot[:m], own_ids, own_payload, counts
 
     def shard_plan_wait(self, result_slot: int, shards: int) -> list:
