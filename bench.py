@@ -294,6 +294,7 @@ def parity_sharded(torch, dist, dev, world, rank):
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         detail[name] = bool(flag.item())
         ok = ok and detail[name]
+        sh.close()
         del sh
     torch.cuda.empty_cache()
     return ok, {"leaves": n, "batches": 3, "updates_per_batch": m, "samples_per_batch": q, "checked_on": "every rank", **detail}

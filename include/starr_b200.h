@@ -223,10 +223,18 @@ ST_API int st_peer_create(int device, int rank, int world, int64_t payload_bytes
                    unsigned char *handle_out);
 /* handles: world x st_peer_handle_bytes() bytes, rank-major (this rank's own entry is ignored) */
 ST_API int st_peer_connect(st_peer *p, const unsigned char *handles);
+/* a peer that lives in THIS process (ranks as threads; CUDA IPC cannot open a handle in the process that
+ * exported it): base = st_peer_base() of that rank's area, on a device this one has peer access to.  Call
+ * before st_peer_connect, which skips adopted ranks. */
+ST_API int st_peer_adopt(st_peer *p, int q, void *base);
+ST_API void *st_peer_base(const st_peer *p); /* start of the local buffer (flag page) */
+/* closes the mappings of the other ranks' buffers (every rank calls this, then a host barrier, then destroy:
+ * an exported buffer must not be freed while another process still has it open) */
+ST_API int st_peer_disconnect(st_peer *p);
 ST_API int st_peer_destroy(st_peer *p);
 ST_API void *st_peer_payload(const st_peer *p); /* local device pointer of the payload */
 ST_API int64_t st_peer_payload_bytes(const st_peer *p);
-/* payload_q[offset .. offset+bytes) = this rank's payload[offset ..) for every other rank q (multiples of 16) */
+/* payload_q[offset .. offset+bytes) = this rank's payload[offset ..) for every other rank q (multiples of 4) */
 ST_API int st_peer_broadcast(st_peer *p, int64_t offset, int64_t bytes, void *stream);
 /* payload_q[offset + pos[k]*esize] = src[k] on EVERY rank q (this one included), k < min(count, *count_dev);
  * pos values must lie in [0, span_elems); count_dev may be NULL */

@@ -124,6 +124,9 @@ _SIGNATURES = {
     "st_peer_handle_bytes": (c_int, []),
     "st_peer_create": (c_int, [c_int, c_int, c_int, c_int64, POINTER(c_void_p), c_void_p]),
     "st_peer_connect": (c_int, [c_void_p, c_void_p]),
+    "st_peer_adopt": (c_int, [c_void_p, c_int, c_void_p]),
+    "st_peer_base": (c_void_p, [c_void_p]),
+    "st_peer_disconnect": (c_int, [c_void_p]),
     "st_peer_destroy": (c_int, [c_void_p]),
     "st_peer_payload": (c_void_p, [c_void_p]),
     "st_peer_payload_bytes": (c_int64, [c_void_p]),
@@ -555,8 +558,17 @@ class PeerArea:
             raise RuntimeError("peer area is closed")
         return self._p
 
-    def connect(self, handles: list) -> None:
-        blob = b"".join(handles)
+    def address(self) -> tuple:
+        """What the other ranks need to reach this area: ``(pid, base pointer, CUDA IPC handle)``."""
+        return (os.getpid(), int(lib().st_peer_base(self.ptr)), self.handle)
+
+    def connect(self, addresses: list) -> None:
+        """``addresses[q]`` = ``address()`` of rank q.  Ranks of this process (threads) are adopted by
+        pointer, the others are opened through their IPC handle."""
+        for q, (pid, base, _) in enumerate(addresses):
+            if q != self.rank and pid == os.getpid():
+                self._check(lib().st_peer_adopt(self.ptr, q, c_void_p(base)))
+        blob = b"".join(a[2] for a in addresses)
         assert len(blob) == self.world * self._hb
         buf = (ctypes.c_ubyte * len(blob)).from_buffer_copy(blob)
         self._check(lib().st_peer_connect(self.ptr, buf))
@@ -586,6 +598,10 @@ class PeerArea:
 
     def status(self, stream: int = 0) -> None:
         self._check(lib().st_peer_status(self.ptr, c_void_p(stream)))
+
+    def disconnect(self) -> None:
+        if getattr(self, "_p", None):
+            self._check(lib().st_peer_disconnect(self._p))
 
     def close(self) -> None:
         p, self._p = getattr(self, "_p", None), None

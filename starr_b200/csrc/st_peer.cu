@@ -85,16 +85,17 @@ __global__ void peer_wait_kernel(const unsigned int *flags, int channel, unsigne
     }
 }
 
-// payload_q[off .. off + bytes) = local payload[off ..) for every q != rank (16-byte vectors)
+// payload_q[off .. off + bytes) = local payload[off ..) for every q != rank (V = widest vector the range allows)
+template <typename V>
 __global__ void __launch_bounds__(256) peer_broadcast_kernel(peer_ptrs pp, int rank, size_t off, size_t bytes)
 {
-    const size_t nvec = bytes / 16;
-    const int4 *src = reinterpret_cast<const int4 *>(pp.base[rank] + off);
+    const size_t nvec = bytes / sizeof(V);
+    const V *src = reinterpret_cast<const V *>(pp.base[rank] + off);
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
-        const int4 v = src[i];
+        const V v = src[i];
         for (int q = 0; q < pp.n; ++q)
-            if (q != rank) reinterpret_cast<int4 *>(pp.base[q] + off)[i] = v;
+            if (q != rank) reinterpret_cast<V *>(pp.base[q] + off)[i] = v;
     }
 }
 
@@ -241,7 +242,7 @@ int st_peer_connect(st_peer *p, const unsigned char *handles)
     if (!p || !handles) return pfail(ST_ERR_ARG, "st_peer_connect: bad argument");
     dev_guard g(p->device);
     for (int q = 0; q < p->world; ++q) {
-        if (q == p->rank) continue;
+        if (q == p->rank || p->ptrs.base[q]) continue;   // own buffer / adopted (same-process) peer
         cudaIpcMemHandle_t h;
         memcpy(&h, handles + (size_t)q * sizeof(h), sizeof(h));
         void *ptr = nullptr;
@@ -252,13 +253,33 @@ int st_peer_connect(st_peer *p, const unsigned char *handles)
     return ST_OK;
 }
 
-int st_peer_destroy(st_peer *p)
+int st_peer_adopt(st_peer *p, int q, void *base)
+{
+    if (!p || q < 0 || q >= p->world || q == p->rank || !base) return pfail(ST_ERR_ARG, "st_peer_adopt: bad argument");
+    p->ptrs.base[q] = (char *)base;
+    return ST_OK;
+}
+
+void *st_peer_base(const st_peer *p) { return p ? p->local : nullptr; }
+
+int st_peer_disconnect(st_peer *p)
 {
     if (!p) return ST_OK;
     dev_guard g(p->device);
     cudaDeviceSynchronize();
-    for (int q = 0; q < p->world; ++q)
+    for (int q = 0; q < p->world; ++q) {
         if (p->opened[q]) cudaIpcCloseMemHandle(p->ptrs.base[q]);
+        p->opened[q] = false;
+        if (q != p->rank) p->ptrs.base[q] = nullptr;
+    }
+    return ST_OK;
+}
+
+int st_peer_destroy(st_peer *p)
+{
+    if (!p) return ST_OK;
+    st_peer_disconnect(p);
+    dev_guard g(p->device);
     if (p->local) cudaFree(p->local);
     if (p->d_err) cudaFree(p->d_err);
     if (p->h_err) cudaFreeHost(p->h_err);
@@ -271,14 +292,20 @@ int64_t st_peer_payload_bytes(const st_peer *p) { return p ? (int64_t)p->payload
 
 int st_peer_broadcast(st_peer *p, int64_t offset, int64_t bytes, void *stream)
 {
-    if (!p || offset < 0 || bytes < 0 || (offset & 15) || (bytes & 15) || (size_t)(offset + bytes) > p->payload_bytes)
-        return pfail(ST_ERR_ARG, "st_peer_broadcast: bad argument (offset and size must be multiples of 16 inside the payload)");
+    if (!p || offset < 0 || bytes < 0 || (offset & 3) || (bytes & 3) || (size_t)(offset + bytes) > p->payload_bytes)
+        return pfail(ST_ERR_ARG, "st_peer_broadcast: bad argument (offset and size must be multiples of 4 inside the payload)");
     if (bytes == 0 || p->world == 1) return ST_OK;
     dev_guard g(p->device);
     ++st::g_kernel_launches;
-    const unsigned grid = st::grid_for(bytes / 16, 256, 592);
-    st::peer_broadcast_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p->ptrs, p->rank, st::PEER_FLAG_BYTES + (size_t)offset,
-                                                                     (size_t)bytes);
+    const size_t off = st::PEER_FLAG_BYTES + (size_t)offset;
+    const int64_t both = offset | bytes;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!(both & 15))
+        st::peer_broadcast_kernel<int4><<<st::grid_for(bytes / 16, 256, 592), 256, 0, s>>>(p->ptrs, p->rank, off, (size_t)bytes);
+    else if (!(both & 7))
+        st::peer_broadcast_kernel<int2><<<st::grid_for(bytes / 8, 256, 592), 256, 0, s>>>(p->ptrs, p->rank, off, (size_t)bytes);
+    else
+        st::peer_broadcast_kernel<int><<<st::grid_for(bytes / 4, 256, 592), 256, 0, s>>>(p->ptrs, p->rank, off, (size_t)bytes);
     PCU(cudaGetLastError());
     return ST_OK;
 }

@@ -27,8 +27,21 @@ Per batch (inputs are replicated on every rank, as a PER learner broadcasts them
           the first g levels of the reference descent), finishes the ones it owns locally with
           the left-over prefix, and the local leaf ids (int32) are all-gathered as slabs and
           expanded to global indices in batch order.
+
+Peer exchange (``peer=True``, the default on CUDA when every rank can reach every other rank's memory):
+the three all-gathers and the passes that put slabs back into batch order are replaced by direct stores
+into an exchange buffer of EVERY rank (``csrc/st_peer.cu``, CUDA IPC over NVLink / NVSwitch):
+  update  the leaf pass of the local update emits the d_j, a scatter kernel stores each one at its batch
+          position j of ``d_all`` on every rank WHILE the local ancestors are still being updated
+          (side stream); shard roots and the rank's 1/G of the top-fold records follow the same way;
+          a release flag per rank + a spinning wait kernel replace the collective's implicit barrier.
+  sample  routing on the top tree and the selection of the rank's queries are one kernel
+          (``st_route_compact_device``: no plan, no host round trip); the local descent stores the GLOBAL
+          index of each query at its batch position on every rank (``st_search_push_device``).
 """
 from __future__ import annotations
+
+import os
 
 import torch
 import torch.distributed as dist
@@ -52,7 +65,7 @@ def _default_factory(n, dtype, device):
 
 class ShardedSumTree:
     def __init__(self, n_global: int, dtype=torch.float32, local_leaves: torch.Tensor | None = None,
-                 group=None, device=None, tree_factory=None):
+                 group=None, device=None, tree_factory=None, peer: bool | None = None):
         if not dist.is_initialized():
             raise RuntimeError("ShardedSumTree needs an initialised torch.distributed process group")
         self.group = group
@@ -74,6 +87,14 @@ class ShardedSumTree:
         self._marks = None     # diagnostics: list of (label, cuda event) while phase_times() runs
         self._bufs = [None, None, None]
         self._turn = 0
+        # peer-memory exchange: created by the first batch (a collective: every rank sees the same sizes)
+        if peer is None:     # STARR_B200_PEER=0 keeps the NCCL all-gather exchange (A/B comparisons)
+            peer = self.device.type == "cuda" and tree_factory is None and os.environ.get("STARR_B200_PEER", "1") != "0"
+        self._peer_wanted = bool(peer)
+        self._peer = None
+        self._peer_cap = (0, 0)
+        self._ustep = self._sstep = 0
+        self._side = None
         if local_leaves is not None:
             self.build_(local_leaves)
 
@@ -93,6 +114,73 @@ class ShardedSumTree:
             ev = torch.cuda.Event(enable_timing=True)
             ev.record()
             self._marks.append((label, ev))
+
+    # ---- peer exchange area ---------------------------------------------------------------------
+    CH_DELTAS, CH_RECS, CH_SAMPLE = 0, 1, 2
+
+    def _peer_layout(self, mu: int, ms: int):
+        """Byte offsets of the double-buffered regions for update batches of <= mu and sample batches of <= ms."""
+        es = torch.empty(0, dtype=self.dtype).element_size()
+        al = lambda x: (x + 255) // 256 * 256                                   # noqa: E731
+        nodes = self.world - 1
+        rb = self.top.top_fold_record_bytes() if hasattr(self.top, "top_fold_record_bytes") else 0
+        per = ((mu + 1023) // 1024 + self.world - 1) // self.world
+        sizes = {"d": al(mu * es), "roots": al(self.world * es), "recs": al(per * self.world * nodes * rb), "out": al(ms * 8)}
+        off, lay = 0, {}
+        for name, size in sizes.items():
+            lay[name] = (off, off + size)                                        # parity 0 / parity 1
+            off += 2 * size
+        lay["bytes"] = off
+        return lay
+
+    def _ensure_peer(self, mu: int = 0, ms: int = 0) -> bool:
+        """(Re)create the exchange area when a larger batch arrives.  Collective: batches are replicated, so every
+        rank gets here with the same sizes at the same call."""
+        if not self._peer_wanted:
+            return False
+        cu, cs = self._peer_cap
+        if self._peer is not None and mu <= cu and ms <= cs:
+            return True
+        from . import _lib
+        mu, ms = max(mu, cu, 1024), max(ms, cs, 1024)
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)              # nobody is still storing into the old area
+        self._drop_peer()
+        lay = self._peer_layout(mu, ms)
+        area = _lib.PeerArea(self.device.index, self.rank, self.world, lay["bytes"])
+        addrs = [None] * self.world
+        dist.all_gather_object(addrs, area.address(), group=self.group)
+        area.connect(addrs)
+        dist.barrier(group=self.group)              # every rank has opened every buffer before the first store
+        self._peer, self._peer_cap, self._lay = area, (mu, ms), lay
+        self._ustep = self._sstep = 0
+        self._rank_pos = torch.tensor([self.rank], dtype=torch.int32, device=self.device)
+        self._own_count = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._side = self._side or torch.cuda.Stream(device=self.device)
+        return True
+
+    def _drop_peer(self) -> None:
+        old, self._peer = self._peer, None
+        if old is not None:
+            old.disconnect()
+            dist.barrier(group=self.group)          # an exported buffer is freed only after every importer closed it
+            old.close()
+
+    def close(self) -> None:
+        """Release the peer exchange area (collective; every rank calls it).  Without it the area is freed when the
+        object is collected, which is only safe once every rank has finished with the tree."""
+        if self._peer is not None:
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)
+            self._drop_peer()
+
+    def _region(self, name: str, parity: int, dtype, count: int) -> torch.Tensor:
+        """Zero-copy tensor over a region of the LOCAL exchange buffer."""
+        off = self._lay[name][parity]
+        nbytes = count * torch.empty(0, dtype=dtype).element_size()
+        iface = {"shape": (max(nbytes, 1),), "typestr": "|u1", "version": 3, "data": (self._peer.payload_ptr + off, False)}
+        holder = type("_Region", (), {"__cuda_array_interface__": iface})()
+        return torch.as_tensor(holder, device=self.device)[:nbytes].view(dtype)
 
     def phase_times(self, next_batch, reps: int = 10):
         """Diagnostics (tools/sharded_breakdown.py): median device time in microseconds of every
@@ -124,6 +212,8 @@ class ShardedSumTree:
                 first = first or e
         if first is not None:
             raise first
+        if self._peer is not None:
+            self._peer.status(torch.cuda.current_stream().cuda_stream)
 
     def _gather_roots(self) -> None:  # build only; updates carry the roots in the delta slabs
         """All-gather of the G shard roots (G elements) into the top tree's leaves."""
@@ -160,7 +250,9 @@ class ShardedSumTree:
             dev = self.device
             buf = {"cap": m, "free": None,
                    "out": (torch.empty(m, dtype=torch.uint8, device=dev), torch.empty(m, dtype=torch.int32, device=dev),
-                           torch.empty(m, dtype=torch.int64, device=dev), torch.empty(m, dtype=self.dtype, device=dev))}
+                           torch.empty(m, dtype=torch.int64, device=dev), torch.empty(m, dtype=self.dtype, device=dev)),
+                   "pos": torch.empty(m, dtype=torch.int32, device=dev) if self._peer_wanted else None,
+                   "d_own": torch.empty(m, dtype=self.dtype, device=dev) if self._peer_wanted else None}
             self._bufs[which] = buf
         return buf
 
@@ -184,15 +276,16 @@ class ShardedSumTree:
         self._turn ^= 1
         buf = self._plan_buffers(which, ni)
         on_cuda = self.device.type == "cuda"
+        extra = {"own_pos": buf["pos"]} if buf["pos"] is not None else {}
         if on_cuda and stream is not None:
             if buf["free"] is not None:
                 stream.wait_event(buf["free"])             # the update that read this set has finished
             with torch.cuda.stream(stream):
                 res = self.local.shard_plan(idx, self.shift, self.world, self.rank, vals, True, out=buf["out"],
-                                            result_slot=which)
+                                            result_slot=which, **extra)
         else:
             res = self.local.shard_plan(idx, self.shift, self.world, self.rank, vals, True,
-                                        **({"out": buf["out"], "result_slot": which} if on_cuda else {}))
+                                        **({"out": buf["out"], "result_slot": which, **extra} if on_cuda else {}))
         return UpdatePlan(ni, *res, buf)
 
     def update_(self, idx: torch.Tensor | None = None, vals: torch.Tensor | None = None, check: bool = False,
@@ -206,6 +299,8 @@ class ShardedSumTree:
             return self
         shard, slot, own_idx, own_vals, counts = plan.shard, plan.slot, plan.own_idx, plan.own_vals, plan.counts
         self._mark("update: plan (owner, slot, compaction)")
+        if plan.buf is not None and plan.buf.get("pos") is not None and self._ensure_peer(mu=plan.ni):
+            return self._update_peer(plan)
         dev = shard.device
         c, cap = counts[self.rank], self._slab_capacity(counts)
         # slab of this rank: its differences d_j in batch order, then (entry `cap`) its new shard root;
@@ -230,7 +325,40 @@ class ShardedSumTree:
         self._mark("update: top fold")
         return self
 
-    def _fold_top(self, shard: torch.Tensor, d_all: torch.Tensor) -> None:
+    def _update_peer(self, plan: "UpdatePlan") -> "ShardedSumTree":
+        """``update_`` over the peer exchange area (module docstring): no collective, no slab, no expansion."""
+        peer, ni, buf = self._peer, plan.ni, plan.buf
+        c = plan.counts[self.rank]
+        self._ustep += 1
+        step, par = self._ustep, self._ustep & 1
+        es = self.local.heap.element_size()
+        main = torch.cuda.current_stream()
+        d_own = buf["d_own"]
+        if c:
+            # leaf pass first: the differences exist, and travel (side stream) while the ancestors are updated
+            self.local.update_begin_(plan.own_idx[:c], plan.own_vals[:c], out=d_own)
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                peer.scatter(d_own.data_ptr(), buf["pos"].data_ptr(), c, es, self._lay["d"][par], ni,
+                             stream=self._side.cuda_stream)
+            self.local.update_finish_()
+            main.wait_stream(self._side)
+        self._mark("update: local update (+ deltas to every rank)")
+        peer.scatter(self.local.heap[1:2].data_ptr(), self._rank_pos.data_ptr(), 1, es, self._lay["roots"][par], self.world,
+                     stream=main.cuda_stream)
+        peer.signal(self.CH_DELTAS, step, main.cuda_stream)
+        peer.wait(self.CH_DELTAS, step, main.cuda_stream)
+        self._mark("update: wait for all ranks' deltas + roots")
+        d_all = self._region("d", par, self.dtype, ni)
+        self._fold_top(plan.shard, d_all, peer_step=(step, par))
+        self.top.leaves.copy_(self._region("roots", par, self.dtype, self.world))
+        ev = torch.cuda.Event()
+        ev.record()
+        buf["free"] = ev
+        self._mark("update: top fold")
+        return self
+
+    def _fold_top(self, shard: torch.Tensor, d_all: torch.Tensor, peer_step=None) -> None:
         """Ordered fold of ALL differences into the replicated top tree.  With the CUDA tree the
         chunk summaries (the parallel part) are split over the ranks and exchanged with one small
         all-gather; the stitch is replicated.  Results are identical on every rank."""
@@ -243,8 +371,22 @@ class ShardedSumTree:
         rb = top.top_fold_record_bytes()
         nchunks = (ni + 1023) // 1024
         per = (nchunks + self.world - 1) // self.world
-        recs = torch.empty(per * self.world * nodes * rb, dtype=torch.uint8, device=shard.device)
         lo = self.rank * per
+        if peer_step is not None:
+            # this rank's 1/G of the chunk summaries goes straight into every rank's record array
+            step, par = peer_step
+            recs = self._region("recs", par, torch.uint8, per * self.world * nodes * rb)
+            top.top_fold_maps_(shard, d_all, lo, lo + per, recs)
+            self._mark("update: top fold summaries")
+            s = torch.cuda.current_stream().cuda_stream
+            span = per * nodes * rb
+            self._peer.broadcast(self._lay["recs"][par] + lo * nodes * rb, span, s)
+            self._peer.signal(self.CH_RECS, step, s)
+            self._peer.wait(self.CH_RECS, step, s)
+            self._mark("update: top fold records to every rank")
+            top.top_fold_apply_(shard, d_all, recs)
+            return
+        recs = torch.empty(per * self.world * nodes * rb, dtype=torch.uint8, device=shard.device)
         top.top_fold_maps_(shard, d_all, lo, lo + per, recs)
         self._mark("update: top fold summaries")
         slab = recs[lo * nodes * rb:(lo + per) * nodes * rb].clone()
@@ -262,6 +404,8 @@ class ShardedSumTree:
             out = torch.empty(m, dtype=torch.int64, device=u.device)
         if m == 0:
             return out
+        if self._ensure_peer(ms=m):
+            return self._sample_peer(u, out)
         owner, resid = self.top.route_uniform(u)
         self._mark("sample: route")
         if hasattr(self.local, "search_counted"):
@@ -291,6 +435,26 @@ class ShardedSumTree:
         self._mark("sample: exchange indices")
         self.local.shard_expand_indices(shard, slot, slabs, self.n_local, out=out)
         self._mark("sample: indices to batch order")
+        return out
+
+    def _sample_peer(self, u: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+        """``sample_uniform`` over the peer exchange area: route + select in one kernel, the local descent stores
+        global indices at their batch positions on every rank; no plan, no host round trip, no collective."""
+        m = u.numel()
+        self._sstep += 1
+        step, par = self._sstep, self._sstep & 1
+        bufs = self._plan_buffers(2, m)
+        own_resid, own_pos = bufs["out"][3], bufs["pos"]
+        self.top.route_compact(u, self.rank, own_resid, own_pos, self._own_count)
+        self._mark("sample: route + select")
+        self.local.search_push(own_resid, self._own_count, own_pos, self.offset, self._peer, self._lay["out"][par], m)
+        self._mark("sample: local search (indices to every rank)")
+        s = torch.cuda.current_stream().cuda_stream
+        self._peer.signal(self.CH_SAMPLE, step, s)
+        self._peer.wait(self.CH_SAMPLE, step, s)
+        self._mark("sample: wait for all ranks")
+        out.copy_(self._region("out", par, torch.int64, m))
+        self._mark("sample: copy out")
         return out
 
     # ---- inspection -------------------------------------------------------------------------------

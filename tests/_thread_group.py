@@ -32,12 +32,20 @@ class ThreadGroup:
 
     def all_gather_into_tensor(self, output: torch.Tensor, input: torch.Tensor, group=None) -> None:
         self._slots[self._local.rank] = input
-        self._barrier.wait()                      # every producer kernel is enqueued on the shared stream
+        torch.cuda.current_stream().synchronize()  # ranks may run on streams of their own: the input is complete
+        self._barrier.wait()
         k = input.numel()
         flat = output.view(-1)
         for r in range(self.world):
             flat[r * k:(r + 1) * k].copy_(self._slots[r].reshape(-1))
+        torch.cuda.current_stream().synchronize()
         self._barrier.wait()                      # nobody overwrites its slot before all have copied
+
+    def all_gather_object(self, object_list: list, obj, group=None) -> None:
+        self._slots[self._local.rank] = obj
+        self._barrier.wait()
+        object_list[:] = list(self._slots)
+        self._barrier.wait()
 
     def run(self, fn):
         """fn(rank) on every rank; returns the list of results, re-raises the first exception."""

@@ -203,10 +203,13 @@ def test_top_fold_uint8_ids_equal_int64_ids(dt_name):
     assert np.frombuffer(heaps[0], dt)[:g].tobytes() == tree.tobytes()
 
 
+@pytest.mark.parametrize("peer", [False, True], ids=["allgather", "peer"])
 @pytest.mark.parametrize("world,dt_name", [(2, "float32"), (8, "float32"), (4, "float64"), (4, "int32")])
-def test_sharded_cuda_path_on_one_gpu(world, dt_name, monkeypatch):
+def test_sharded_cuda_path_on_one_gpu(world, dt_name, peer, monkeypatch):
     """All ranks as threads on cuda:0 (tests/_thread_group.py): the complete CUDA path of the
-    sharded tree against ONE oracle tree, on a box with a single GPU."""
+    sharded tree against ONE oracle tree, on a box with a single GPU.  ``peer``: the exchange goes through
+    the peer-memory area (st_peer.cu; ranks of one process adopt each other's buffers by pointer) with every
+    rank on a stream of its own, as separate processes would be."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle
     from _thread_group import ThreadGroup
@@ -237,7 +240,18 @@ def test_sharded_cuda_path_on_one_gpu(world, dt_name, monkeypatch):
 
     def rank_body(r):
         torch.cuda.set_device(0)
-        st = sharded.ShardedSumTree(n, tdt, local_leaves=torch.from_numpy(leaves[r * nl:(r + 1) * nl].copy()).to(dev))
+        if peer:        # a spinning wait kernel must not sit in front of another rank's signal on a shared stream
+            with torch.cuda.stream(torch.cuda.Stream()):
+                try:
+                    return rank_steps(r)
+                finally:
+                    torch.cuda.current_stream().synchronize()
+        return rank_steps(r)
+
+    def rank_steps(r):
+        st = sharded.ShardedSumTree(n, tdt, local_leaves=torch.from_numpy(leaves[r * nl:(r + 1) * nl].copy()).to(dev),
+                                    peer=peer)
+        st.reserve(70_000)   # no workspace growth (cudaFree = device-wide wait) while another rank's wait kernel spins
         bad_steps = []
         side = torch.cuda.Stream()
         for b, (idx, vals, u, tree_after, leaves_after, want) in enumerate(batches):
@@ -266,6 +280,9 @@ def test_sharded_cuda_path_on_one_gpu(world, dt_name, monkeypatch):
         st.poll()
         if st.gather_sumtree().cpu().numpy().tobytes() != before:
             bad_steps.append(("bad batch", "tree modified"))
+        if peer and st._peer is None:
+            bad_steps.append(("peer", "exchange area was not used"))
+        st.close()
         return bad_steps
 
     assert group.run(rank_body) == [[]] * world
