@@ -154,8 +154,8 @@ DEFINE_ORACLE(f64, double, 1)
     {                                                                                      \
         for (int64_t a = 0; a < A; ++a)                                                    \
             for (int64_t c = 0; c < C; ++c) {                                              \
-                ACC acc = (ACC)x[(a * R) * C + c];                                         \
-                for (int64_t r = 1; r < R; ++r) acc = (ACC)(acc + (ACC)x[(a * R + r) * C + c]); \
+                ACC acc = (ACC)0; /* add.reduce starts from the identity: an all -0.0 column gives +0.0 */ \
+                for (int64_t r = 0; r < R; ++r) acc = (ACC)(acc + (ACC)x[(a * R + r) * C + c]); \
                 out[a * C + c] = acc;                                                      \
             }                                                                              \
     }

@@ -10,8 +10,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.environ.get("ST_BUILD_DIR") or os.path.join(CSRC, "build")
 LIB = os.environ.get("ST_BUILD_LIB") or os.path.join(HERE, "libstarr_b200.so")
-SOURCES = ["st_tree_kernels.cu", "st_update.cu", "st_shard.cu", "st_mintree.cu", "st_peer.cu", "st_capi.cu"]
-HEADERS = ["st_common.cuh", "st_internal.h", "st_ordered_fold.cuh", "st_partition.cuh", "st_update_defs.cuh", "st_update_small.cuh", os.path.join("..", "..", "include", "starr_b200.h")]
+SOURCES = ["st_tree_kernels.cu", "st_update.cu", "st_shard.cu", "st_mintree.cu", "st_peer.cu", "st_axis_fold.cu", "st_capi.cu"]
+HEADERS = ["st_common.cuh", "st_internal.h", "st_ordered_fold.cuh", "st_partition.cuh", "st_partition_hybrid.cuh", "st_update_defs.cuh", "st_update_small.cuh", os.path.join("..", "..", "include", "starr_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

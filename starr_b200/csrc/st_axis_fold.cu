@@ -3,14 +3,16 @@
 // Replaces the reference's fallback `return self.view(np.ndarray).sum(axis=..)` (sumtree_array.py:514)
 // for the axis combinations the tree cannot answer (sumtree_array.py:497-512).  NumPy reduces a non-trailing
 // axis row by row -- out[a][c] = (((x[a][0][c] + x[a][1][c]) + x[a][2][c]) + ...) -- so every output column is
-// one SEQUENTIAL chain of R adds; that order is kept for floats (bit-exact with ndarray.sum,
+// one SEQUENTIAL chain of R adds starting from +0; that order is kept for floats (bit-exact with ndarray.sum,
 // tests/test_oracle.py::test_axis_fold_is_numpy_order).  Integer sums are associative (NumPy widens small
 // integers to 64 bit; the 64-bit adds wrap), so their R range is additionally split over CTAs.
 //
-// The kernel is an HBM stream: s*A*R*C bytes in, s_out*A*C out.  Each CTA (one warp) owns a strip of BC
-// columns; lane = column; the strip is pulled through a 16-stage ring of 4-KiB shared-memory tiles by
-// TMA tensor copies (cp.async.bulk.tensor.3d + mbarrier complete_tx; SASS UTMALDG), so 64 KiB per CTA and
-// up to 192 KiB per SM are in flight while the dependent-add chain (4 cycles per row) consumes them.
+// The kernel is an HBM stream: s*A*R*C bytes in, s_out*A*C out.  Each CTA owns a strip of BC columns: a
+// producer thread pulls the strip through a 6-stage ring of 16-KiB shared-memory tiles with TMA tensor
+// copies (cp.async.bulk.tensor.3d + mbarrier complete_tx; SASS UTMALDG; full / empty barriers per slot), a
+// consumer warp (lane = column) runs the dependent-add chains.  96 KiB per CTA, 192 KiB per SM in flight.
+// Measured (tools/debug/axis_probe.cu, 4096 x 4096 float32): the tensor copies alone deliver 4.4 TB/s, the
+// dependent-add chain (~9 cycles per row with the mbarrier wait) is what bounds a float column at ~20 us.
 #include <cuda.h>
 
 #include <mutex>
@@ -19,8 +21,8 @@
 
 namespace st {
 
-constexpr int AF_TILE_BYTES = 4096;
-constexpr int AF_STAGES = 16;
+constexpr int AF_TILE_BYTES = 16384;   // one ring slot (a tile is BC columns x up to 256 rows)
+constexpr int AF_STAGES = 6;          // 96 KiB per CTA, two CTAs per SM
 
 // ---- generic fallback: one thread per output column (any alignment) ---------------------------------
 template <typename T>
@@ -33,8 +35,8 @@ axis_fold_kernel(const T *__restrict__ x, int64_t A, int64_t R, int64_t C,
     for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
         const int64_t a = o / C, c = o - a * C;
         const T *p = x + a * R * C + c;
-        ACC acc = (ACC)__ldg(p);
-        int64_t r = 1;
+        ACC acc = ACC(0);      // NumPy's add.reduce starts from the identity (+0)
+        int64_t r = 0;
         constexpr int U = 16;
         for (; r + U <= R; r += U) {
             T v[U];
@@ -49,6 +51,11 @@ axis_fold_kernel(const T *__restrict__ x, int64_t A, int64_t R, int64_t C,
 }
 
 // ---- TMA-fed strip kernel ------------------------------------------------------------------------------
+template <typename T, int BC> __host__ __device__ constexpr int af_rows()   // rows per tile (a box dimension is <= 256)
+{
+    return AF_TILE_BYTES / (BC * (int)sizeof(T)) > 256 ? 256 : AF_TILE_BYTES / (BC * (int)sizeof(T));
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
@@ -63,17 +70,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 }
 
 template <typename T, int BC>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(64)
 axis_fold_tma_kernel(const __grid_constant__ CUtensorMap tm, int64_t R, int64_t C, int strips, int rsplit,
                      int64_t rows_per_part, typename fold_acc<T>::type *__restrict__ out)
 {
     using ACC = typename fold_acc<T>::type;
-    constexpr int BR = AF_TILE_BYTES / (BC * (int)sizeof(T));
-    static_assert(BR >= 1 && BR <= 256, "tile rows");
+    constexpr int BR = af_rows<T, BC>();
+    constexpr int TILE = BR * BC * (int)sizeof(T);   // bytes one tensor copy delivers (<= AF_TILE_BYTES, the slot size)
     extern __shared__ __align__(128) unsigned char af_smem[];
     T *tiles = reinterpret_cast<T *>(af_smem);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(af_smem + AF_STAGES * AF_TILE_BYTES);
-    const int lane = threadIdx.x;
+    uint64_t *full = reinterpret_cast<uint64_t *>(af_smem + AF_STAGES * AF_TILE_BYTES);
+    uint64_t *empty = full + AF_STAGES;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     int64_t b = blockIdx.x;
     const int part = (int)(b % rsplit); b /= rsplit;
@@ -85,53 +93,66 @@ axis_fold_tma_kernel(const __grid_constant__ CUtensorMap tm, int64_t R, int64_t 
     const int c0 = strip * BC;
     const int ntiles = (int)((r1 - r0 + BR - 1) / BR);
 
-    if (lane == 0) {
-        for (int s = 0; s < AF_STAGES; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bars + s)));
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < AF_STAGES; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(full + s)));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(empty + s)));
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncwarp();
-    auto issue = [&](int t) {   // lane 0: tile t of this CTA's row range into ring slot t % STAGES
-        const int s = t % AF_STAGES;
-        const uint32_t bar = smem_u32(bars + s);
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(AF_TILE_BYTES) : "memory");
-        asm volatile(
-            "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-            ::"r"(smem_u32(af_smem + (size_t)s * AF_TILE_BYTES)), "l"(&tm), "r"(c0), "r"((int)(r0 + (int64_t)t * BR)), "r"(a),
-              "r"(bar)
-            : "memory");
-    };
-    if (lane == 0) {
-        const int pre = ntiles < AF_STAGES ? ntiles : AF_STAGES;
-        for (int t = 0; t < pre; ++t) issue(t);
+    __syncthreads();
+
+    if (warp == 1) {
+        // ---- producer: one thread keeps the ring full (a slot is refilled when the consumer has released it)
+        if (lane == 0) {
+            for (int t = 0; t < ntiles; ++t) {
+                const int s = t % AF_STAGES;
+                if (t >= AF_STAGES) mbar_wait(smem_u32(empty + s), (uint32_t)(t / AF_STAGES - 1) & 1u);
+                const uint32_t bar = smem_u32(full + s);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(TILE) : "memory");
+                asm volatile(
+                    "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                    ::"r"(smem_u32(af_smem + (size_t)s * AF_TILE_BYTES)), "l"(&tm), "r"(c0), "r"((int)(r0 + (int64_t)t * BR)),
+                      "r"(a), "r"(bar)
+                    : "memory");
+            }
+        }
+        return;
     }
 
+    // ---- consumer warp: lane = column; the chain of adds runs straight out of the tile (the loads of the next
+    // rows are issued between the dependent adds; staging blocks of rows in registers first measured slower),
+    // the slot goes back to the producer after its last row.  Integer sums are associative: four chains per lane.
     const bool live = lane < BC && c0 + lane < C;
     const int col = lane < BC ? lane : 0;
-    ACC acc = ACC(0);
+    // NumPy's add.reduce starts from the identity: acc = +0, then row 0, 1, ... (an all -0.0 column sums to +0.0)
+    ACC acc = ACC(0), acc1 = ACC(0), acc2 = ACC(0), acc3 = ACC(0);
     for (int t = 0; t < ntiles; ++t) {
         const int s = t % AF_STAGES;
-        mbar_wait(smem_u32(bars + s), (uint32_t)(t / AF_STAGES) & 1u);
-        const T *tile = tiles + (size_t)s * (AF_TILE_BYTES / sizeof(T)) + col;
-        const int64_t left = r1 - (r0 + (int64_t)t * BR);
-        int r = 0;
-        if (t == 0 && part == 0) { acc = (ACC)tile[0]; r = 1; }   // the fold starts FROM row 0 (keeps a leading -0.0)
+        mbar_wait(smem_u32(full + s), (uint32_t)(t / AF_STAGES) & 1u);
+        const T *src = tiles + (size_t)s * (AF_TILE_BYTES / sizeof(T)) + col;
+        const int64_t left = r1 - (r0 + (int64_t)t * BR);       // rows of this tile that exist
         if (left >= BR) {
-            if (r == 1) {
-#pragma unroll
-                for (int k = 1; k < BR; ++k) acc = t_add<ACC>(acc, (ACC)tile[k * BC]);
+            if constexpr (is_float_t<T>::value) {
+#pragma unroll 32
+                for (int k = 0; k < BR; ++k) acc = t_add<ACC>(acc, (ACC)src[k * BC]);
             } else {
-#pragma unroll
-                for (int k = 0; k < BR; ++k) acc = t_add<ACC>(acc, (ACC)tile[k * BC]);
+                static_assert(BR % 4 == 0, "tile rows");
+#pragma unroll 8
+                for (int k = 0; k < BR; k += 4) {
+                    acc += (ACC)src[k * BC];
+                    acc1 += (ACC)src[(k + 1) * BC];
+                    acc2 += (ACC)src[(k + 2) * BC];
+                    acc3 += (ACC)src[(k + 3) * BC];
+                }
             }
         } else {
-            for (; r < (int)left; ++r) acc = t_add<ACC>(acc, (ACC)tile[r * BC]);
+            for (int k = 0; k < (int)left; ++k) acc = t_add<ACC>(acc, (ACC)src[k * BC]);
         }
-        __syncwarp();   // every lane is done with slot s before the next tensor copy overwrites it
-        if (lane == 0 && t + AF_STAGES < ntiles) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            issue(t + AF_STAGES);
-        }
+        __syncwarp();   // every lane has read slot s
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(empty + s)) : "memory");
     }
+    if constexpr (!is_float_t<T>::value) acc = (ACC)(acc + acc1 + acc2 + acc3);
     if (live) {
         ACC *o = out + (int64_t)a * C + c0 + lane;
         if (rsplit == 1) *o = acc;
@@ -162,7 +183,7 @@ static cudaError_t launch_tma(const st_tree *t, const T *x, int64_t A, int64_t R
                               bool *done)
 {
     using ACC = typename fold_acc<T>::type;
-    constexpr int BR = AF_TILE_BYTES / (BC * (int)sizeof(T));
+    constexpr int BR = af_rows<T, BC>();
     *done = false;
     encode_tiled_fn enc = encode_tiled();
     if (!enc) return cudaSuccess;
@@ -191,7 +212,7 @@ static cudaError_t launch_tma(const st_tree *t, const T *x, int64_t A, int64_t R
     rsplit = (int)((R + rows_per_part - 1) / rows_per_part);
     const int64_t grid = A * strips * rsplit;
     if (grid > 0x7fffffffLL) return cudaSuccess;
-    const size_t smem = (size_t)AF_STAGES * AF_TILE_BYTES + AF_STAGES * sizeof(uint64_t);
+    const size_t smem = (size_t)AF_STAGES * AF_TILE_BYTES + 2 * AF_STAGES * sizeof(uint64_t);
     auto kern = axis_fold_tma_kernel<T, BC>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -200,7 +221,7 @@ static cudaError_t launch_tma(const st_tree *t, const T *x, int64_t A, int64_t R
         if (e != cudaSuccess) return e;
     }
     ++g_kernel_launches;
-    kern<<<(unsigned)grid, 32, smem, s>>>(tm, R, C, strips, rsplit, rows_per_part, (ACC *)out);
+    kern<<<(unsigned)grid, 64, smem, s>>>(tm, R, C, strips, rsplit, rows_per_part, (ACC *)out);
     *done = true;
     return cudaGetLastError();
 }
@@ -218,13 +239,15 @@ cudaError_t launch_axis_fold(const st_tree *t, int64_t A, int64_t R, int64_t C, 
         if (tma_ok) {
             // widest strip that still gives every SM a CTA; a strip row is never narrower than one 32-byte sector
             int bc = 32;
-            while (bc > 8 && bc / 2 * (int)sizeof(T) >= 32 && A * ((C + bc - 1) / bc) < t->sm_count) bc /= 2;
+            if constexpr (is_float_t<T>::value)   // (integer sums split the rows instead, see launch_tma)
+                while (bc > 8 && bc / 2 * (int)sizeof(T) >= 32 && A * ((C + bc - 1) / bc) < t->sm_count) bc /= 2;
             if (force_bc == 32 || force_bc == 16 || force_bc == 8) bc = force_bc;
             if (bc * (int)sizeof(T) < 16) bc = 16;
             bool done = false;
-            cudaError_t e = bc == 32 ? launch_tma<T, 32>(t, x, A, R, C, out, s, &done)
-                          : bc == 16 ? launch_tma<T, 16>(t, x, A, R, C, out, s, &done)
-                                     : launch_tma<T, 8>(t, x, A, R, C, out, s, &done);
+            cudaError_t e = cudaSuccess;
+            if (bc == 32) e = launch_tma<T, 32>(t, x, A, R, C, out, s, &done);
+            else if (bc == 16) e = launch_tma<T, 16>(t, x, A, R, C, out, s, &done);
+            else if constexpr (sizeof(T) >= 2) e = launch_tma<T, 8>(t, x, A, R, C, out, s, &done);
             if (e != cudaSuccess || done) return e;
         }
         ++g_kernel_launches;

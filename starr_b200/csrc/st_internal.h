@@ -51,6 +51,7 @@ struct st_tree {
     size_t cub_bytes = 0;
     int sm_count = 148;
     int coop_ok = 0;
+    int hy_attr = 0;           // hy_segment_kernel's dynamic shared memory limit has been raised
     int part_occ = 0;          // resident CTAs per SM of the cooperative partition kernel (0 = not queried yet)
     // The reference's functions hold the GIL (SURVEY 8b "Threading"); here every entry point that touches the
     // handle's host-side state or staging areas takes this lock, so concurrent callers on ONE tree serialise.

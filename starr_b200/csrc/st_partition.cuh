@@ -47,6 +47,9 @@ template <typename T> struct part_params {
     seg_entry *qret;       // short segments to retire (node unused): finished by retire_kernel after this kernel
     int *huge_off;   // first chunk record of every huge segment
     unsigned int *status;
+    int l0;          // first level to process.  0: the whole descent.  > 0: fallback of the hybrid partition
+                     // (st_partition_hybrid.cuh) -- lev_key[l0] / lev_d[l0] and the segment bounds of level l0 are
+                     // given, level l0 is already classified, and the kernel only runs if SW_NEED_COOP is set
 };
 
 // exclusive scan of `v` over the CTA; returns the prefix, *total gets the CTA sum (valid in all threads)
@@ -87,6 +90,7 @@ __global__ void __launch_bounds__(PART_THREADS) partition_levels_kernel(part_par
     cg::grid_group grid = cg::this_grid();
     PT_TICK(0);
     if (p.status[SW_STATUS]) return;  // uniform over the grid: a failed batch is skipped as a whole
+    if (p.l0 > 0 && !p.status[SW_NEED_COOP]) return;   // the per-segment kernel has done everything (grid-uniform)
     __shared__ unsigned int s_tpre[PART_MAX_TILES + 1];
     __shared__ unsigned int s_warp[PART_THREADS / 32];
     __shared__ unsigned int s_wk[PART_E * (PART_THREADS / 32)];
@@ -97,26 +101,40 @@ __global__ void __launch_bounds__(PART_THREADS) partition_levels_kernel(part_par
     const uint64_t two_n = 2ull * p.n;
 
     // ---- P0: zero counts of the first split bit per tile; clear the other counter set -----------
-    for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
-        unsigned int z = 0;
-        if (depth >= 2 && m > RETIRE_SEG) {
+    const int l0 = p.l0;
+    {
+        const int cur0 = l0 & 1;
+        const uint32_t *key = (l0 == 0) ? p.key0 : p.lev_key + (int64_t)l0 * p.lev_stride;
+        const int *sC = cur0 ? p.sA : p.sB, *eC = cur0 ? p.eA : p.eB;
+        for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+            unsigned int z = 0;
+            if (depth - l0 >= 2 && (l0 > 0 || m > RETIRE_SEG)) {
 #pragma unroll
-            for (int k = 0; k < PART_E; ++k) {
-                const int i = t * PART_TILE + k * PART_THREADS + tid;
-                if (i < m) z += ((p.key0[i] >> (depth - 1)) & 1u) ^ 1u;
+                for (int k = 0; k < PART_E; ++k) {
+                    const int i = t * PART_TILE + k * PART_THREADS + tid;
+                    if (i < m) {
+                        bool live = true;
+                        if (l0 > 0) {
+                            const int e = eC[i];
+                            live = !(e & SEG_DONE) && (e - sC[i] > RETIRE_SEG);
+                        }
+                        if (live) z += ((key[i] >> (depth - l0 - 1)) & 1u) ^ 1u;
+                    }
+                }
             }
-        }
-        unsigned int tot;
-        block_excl_scan(z, s_warp, &tot);
-        if (tid == 0) {
-            p.tilesum[t] = tot;
-            p.tilesum[PART_MAX_TILES + t] = 0;
+            unsigned int tot;
+            block_excl_scan(z, s_warp, &tot);
+            if (tid == 0) {
+                p.tilesum[cur0 * PART_MAX_TILES + t] = tot;
+                p.tilesum[(cur0 ^ 1) * PART_MAX_TILES + t] = 0;
+            }
         }
     }
     grid.sync();
     PT_TICK(1);
 
-    for (int l = 0; l < depth; ++l) {
+    for (int l = l0; l < depth; ++l) {
+        const bool classify = !(l0 > 0 && l == l0);   // level l0 of the hybrid fallback was classified by hy_scan_kernel
         const int cur = l & 1;
         const int sh = depth - l;            // node at this level = key >> sh
         const bool last = (l == depth - 1);
@@ -180,9 +198,9 @@ __global__ void __launch_bounds__(PART_THREADS) partition_levels_kernel(part_par
                     const int len = e - s;
                     const uint32_t ky = kyv[k];
                     if (len <= RETIRE_SEG) {
-                        if (i == s) cls[k] = 1;   // retire_kernel finishes it on all SMs
+                        if (i == s && classify) cls[k] = 1;   // retire_kernel finishes it on all SMs
                     } else {
-                        if (i == s && l < key_leaf_level(ky, two_n, depth)) {
+                        if (i == s && classify && l < key_leaf_level(ky, two_n, depth)) {
                             if (len > HUGE_SEG) {
                                 const unsigned int slot = atomicAdd(p.status + SW_QCOUNT_HUGE, 1u);
                                 p.qhuge[slot] = seg_entry{l, s, len, ky >> sh};

@@ -607,44 +607,4 @@ cudaError_t launch_strided_sum(const st_tree *t, int64_t stride, void *out, int6
     return cudaGetLastError();
 }
 
-// =========================================================================================
-// non-contiguous axis sum: sequential row-order fold (the order NumPy uses)
-// =========================================================================================
-template <typename T>
-__global__ void __launch_bounds__(128)
-axis_fold_kernel(const T *__restrict__ x, int64_t A, int64_t R, int64_t C,
-                 typename fold_acc<T>::type *__restrict__ out)
-{
-    using ACC = typename fold_acc<T>::type;
-    const int64_t total = A * C;
-    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t a = o / C, c = o - a * C;
-        const T *p = x + a * R * C + c;
-        ACC acc = (ACC)__ldg(p);
-        int64_t r = 1;
-        constexpr int U = 16;
-        for (; r + U <= R; r += U) {
-            T v[U];
-#pragma unroll
-            for (int k = 0; k < U; ++k) v[k] = __ldg(p + (r + k) * C);
-#pragma unroll
-            for (int k = 0; k < U; ++k) acc = t_add<ACC>(acc, (ACC)v[k]);
-        }
-        for (; r < R; ++r) acc = t_add<ACC>(acc, (ACC)__ldg(p + r * C));
-        out[o] = acc;
-    }
-}
-
-cudaError_t launch_axis_fold(const st_tree *t, int64_t A, int64_t R, int64_t C, void *out, cudaStream_t s)
-{
-    if (A * C <= 0) return cudaSuccess;
-    ST_DISPATCH(t->dtype, {
-        using ACC = typename fold_acc<T>::type;
-        ++g_kernel_launches;
-        axis_fold_kernel<T><<<grid_for(A * C, 128, (int64_t)t->sm_count * 16), 128, 0, s>>>(
-            (const T *)t->heap + t->n, A, R, C, (ACC *)out);
-    });
-    return cudaGetLastError();
-}
-
 }  // namespace st

@@ -39,7 +39,7 @@
 #include "st_common.cuh"
 #include "st_update_defs.cuh"
 #include "st_ordered_fold.cuh"
-#include "st_partition.cuh"
+#include "st_partition_hybrid.cuh"
 #include "st_update_small.cuh"
 
 namespace st {
@@ -62,6 +62,9 @@ struct update_ws {
     uint32_t *lev_key;
     seg_entry *queue_ret;
     unsigned int *tilesum;
+    unsigned int *hy_hist, *hy_bintotal;   // hybrid partition (st_partition_hybrid.cuh)
+    int *hy_segstart, *hy_seglen;
+    unsigned char *hy_segstate;
     void *cub_tmp;
     size_t cub_bytes;
     size_t total;
@@ -104,6 +107,11 @@ static update_ws carve(const st_tree *t, int64_t B, char *base)
         w.lev_key = (uint32_t *)take((size_t)(t->depth + 1) * B * 4);
         w.queue_ret = (seg_entry *)take((size_t)(B + 32) * sizeof(seg_entry));
         w.tilesum = (unsigned int *)take(2 * PART_MAX_TILES * sizeof(unsigned int));
+        w.hy_hist = (unsigned int *)take((size_t)HY_MAX_BINS * HY_MAX_TILES * sizeof(unsigned int));
+        w.hy_bintotal = (unsigned int *)take(HY_MAX_BINS * sizeof(unsigned int));
+        w.hy_segstart = (int *)take(2 * HY_MAX_BINS * sizeof(int));
+        w.hy_seglen = (int *)take(2 * HY_MAX_BINS * sizeof(int));
+        w.hy_segstate = (unsigned char *)take(2 * HY_MAX_BINS);
     }
     if (t->cub_cap != B) {
         // temp-storage queries are host-side work: do them once per capacity, not once per call
@@ -861,6 +869,36 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
         pp.qlong = w.queue; pp.qmed = w.queue_med; pp.qhuge = w.queue_huge; pp.huge_off = w.huge_off;
         pp.qret = w.queue_ret;
         pp.status = status;
+        pp.l0 = 0;
+        // hybrid partition: top levels by counting sort, the rest per segment in shared memory; the cooperative
+        // kernel below then only runs (from level LT) for batches too skewed for that
+        static const bool hybrid_off = getenv("ST_HYBRID") && atoi(getenv("ST_HYBRID")) == 0;   // A/B switch
+        const int LT = hy_top_levels(m);
+        if (!hybrid_off && depth >= LT + 2 && m > RETIRE_SEG) {
+            hybrid_params<T> hp;
+            hp.n = n; hp.depth = depth; hp.m = m; hp.ntiles = (m + HY_TILE - 1) / HY_TILE; hp.LT = LT;
+            hp.key0 = w.kj; hp.lev_key = w.lev_key; hp.lev_d = lev; hp.lev_stride = B;
+            hp.hist = w.hy_hist; hp.bintotal = w.hy_bintotal;
+            hp.segstart = w.hy_segstart; hp.seglen = w.hy_seglen; hp.segstate = w.hy_segstate;
+            hp.sC = (LT & 1) ? w.seg_sa : w.seg_sb;
+            hp.eC = (LT & 1) ? w.seg_ea : w.seg_eb;
+            hp.qlong = w.queue; hp.qmed = w.queue_med; hp.qhuge = w.queue_huge; hp.qret = w.queue_ret;
+            hp.huge_off = w.huge_off; hp.status = status;
+            const size_t seg_smem = hy_segment_smem<T>();
+            if (!t->hy_attr) {
+                e = cudaFuncSetAttribute(hy_segment_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seg_smem);
+                if (e != cudaSuccess) return e;
+                t->hy_attr = 1;
+            }
+            g_kernel_launches += 4;
+            hy_hist_kernel<<<hp.ntiles, HY_THREADS, 0, s>>>(w.kj, m, depth, LT, w.hy_hist, status);
+            hy_scan_kernel<T><<<1 << LT, HY_THREADS, 0, s>>>(hp);
+            hy_scatter_kernel<T><<<hp.ntiles, HY_THREADS, 0, s>>>(hp);
+            hy_segment_kernel<T><<<1 << LT, HY_B_THREADS, seg_smem, s>>>(hp);
+            e = cudaGetLastError();
+            if (e != cudaSuccess) return e;
+            pp.l0 = LT;
+        }
         if (t->part_occ < 1) {   // per tree (one dtype, one device); the caller holds the tree's lock
             int occ = 0;
             e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, partition_levels_kernel<T>, PART_THREADS, 0);

@@ -262,6 +262,31 @@ def test_axis_fold_matches_numpy(oracle_mod):
             h.close()
 
 
+def test_axis_fold_tma_strips_match_numpy(oracle_mod):
+    """Shapes that take the TMA strip kernel (st_axis_fold.cu): ragged column strips, row counts that are no
+    multiple of the tile, leading dims, integer row splits, a leading -0.0 row, every strip width."""
+    from starr_b200 import _lib
+    rng = np.random.default_rng(9)
+    cases = [(np.float32, (1, 1000, 1024)), (np.float32, (3, 200, 260)), (np.float64, (2, 777, 64)),
+             (np.int32, (1, 5000, 512)), (np.uint8, (1, 300, 4096)), (np.int16, (2, 1031, 136)),
+             (np.float32, (1, 4097, 36)), (np.uint64, (1, 2048, 40)), (np.float32, (1, 65, 6000)),
+             (np.float64, (1, 3000, 4098))]
+    for dt, (A, R, Cc) in cases:
+        x = _draw(rng, A * R * Cc, dt, "log").reshape(A, R, Cc)
+        if np.dtype(dt).itemsize == 1:
+            x = (x % 5).astype(dt)
+        if np.dtype(dt).kind == "f":
+            x[:, 0, ::3] = -0.0
+            x[:, 1:, 0] = 0.0          # column 0 stays -0.0 only if the fold starts from row 0 and adds +0.0 ... = +0.0
+            x[:, 1:, 3] = -0.0         # column 3: (-0.0) + (-0.0) stays -0.0
+        h = _lib.TreeHandle(x.size, dt)
+        h.build_from_host(x.ravel())
+        got = h.axis_fold_host(A, R, Cc)
+        want = x.sum(axis=1)
+        assert_bits_equal(got.reshape(want.shape), want, f"{np.dtype(dt).name} {(A, R, Cc)}")
+        h.close()
+
+
 # ---- the exact parallel ordered fold (st_ordered_fold.cuh) under adversarial inputs ------------
 def _adversarial_batches(rng, n, m, dt, kind):
     idx = rng.integers(0, n, m).astype(np.intp)
