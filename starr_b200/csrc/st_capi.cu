@@ -195,6 +195,9 @@ int st_create(int64_t n, int dtype, int device, void *external_heap, st_tree **o
         e = cudaHostAlloc(&t->h_pin, t->pin_bytes + kPlanSlots * kPlanSlotBytes, cudaHostAllocMapped);
         if (e == cudaSuccess) e = cudaHostGetDevicePointer(&t->d_pin, t->h_pin, 0);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t->plan_ev, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t->ev_fork, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t->ev_join, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&t->side, cudaStreamNonBlocking);
     }
     if (e == cudaSuccess) e = cudaMemset(t->d_status, 0, 64 * sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMemset(t->heap, 0, heap_bytes);
@@ -216,6 +219,9 @@ int st_destroy(st_tree *t)
     if (t->h_status) cudaFreeHost(t->h_status);
     if (t->h_pin) cudaFreeHost(t->h_pin);
     if (t->plan_ev) cudaEventDestroy(t->plan_ev);
+    if (t->ev_fork) cudaEventDestroy(t->ev_fork);
+    if (t->ev_join) cudaEventDestroy(t->ev_join);
+    if (t->side) cudaStreamDestroy(t->side);
     if (t->ws.base) cudaFree(t->ws.base);
     if (t->scratch.base) cudaFree(t->scratch.base);
     if (t->aux) cudaFree(t->aux);

@@ -51,7 +51,6 @@ struct st_tree {
     size_t cub_bytes = 0;
     int sm_count = 148;
     int coop_ok = 0;
-    int hy_attr = 0;           // hy_segment_kernel's dynamic shared memory limit has been raised
     int part_occ = 0;          // resident CTAs per SM of the cooperative partition kernel (0 = not queried yet)
     // The reference's functions hold the GIL (SURVEY 8b "Threading"); here every entry point that touches the
     // handle's host-side state or staging areas takes this lock, so concurrent callers on ONE tree serialise.
@@ -68,6 +67,10 @@ struct st_tree {
         int busy = 0;
     } hs[2];
     cudaStream_t hs_in = nullptr, hs_main = nullptr, hs_out = nullptr;
+    // update pipeline: retirement (ordered atomics on the deep nodes) runs on this stream beside the folds of
+    // the top nodes (disjoint node sets); forked / joined with the two events around every batch
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // optional per-phase timing of the update pipeline (st_set_profiling)
     int profile = 0;
     cudaEvent_t prof_ev[8] = {};

@@ -32,8 +32,8 @@ constexpr int HY_MAX_LT = 9;
 constexpr int HY_MAX_BINS = 1 << HY_MAX_LT;  // 512
 constexpr int HY_MAX_TILES = (int)(UPDATE_MAX_CHUNK / HY_TILE);   // 1024
 constexpr int HY_CAP = 6144;                 // longest level-LT segment a CTA takes (uniform batches: <= 4096 + noise)
-constexpr int HY_B_THREADS = 512;
-constexpr int HY_B_E = HY_CAP / HY_B_THREADS;   // 12
+constexpr int HY_B_THREADS = 1024;
+constexpr int HY_B_E = HY_CAP / HY_B_THREADS;   // 6
 constexpr int HY_SEG_LIVE = 0, HY_SEG_DONE = 1;
 
 template <typename T> struct hybrid_params {
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(HY_THREADS) hy_hist_kernel(const uint32_t *__r
     }
     __syncthreads();
     for (int b = tid; b < bins; b += HY_THREADS) hist[(size_t)b * HY_MAX_TILES + t] = h[b];
-    if (t == 0 && tid == 0) { status[SW_NEED_COOP] = 0; status[SW_HY_TICKET] = 0; }
+    if (t == 0 && tid == 0) { status[SW_NEED_COOP] = 0; status[SW_HY_TICKET] = 0; status[SW_HY_KEYLEVELS] = 0; }
 }
 
 // CTA b: exclusive prefix over the tiles of node b.  The last CTA to finish turns the node totals into the
@@ -145,6 +145,7 @@ __global__ void __launch_bounds__(HY_THREADS) hy_scan_kernel(hybrid_params<T> p)
         if (!above && len > 0) {
             if (len <= RETIRE_SEG) {
                 p.qret[atomicAdd(p.status + SW_QCOUNT_RET, 1u)] = seg_entry{l, s, len, 0u};
+                atomicOr(p.status + SW_HY_KEYLEVELS, 1u << l);   // retire_kernel reads lev_key[l] for this segment
             } else {
                 state = HY_SEG_LIVE;                 // l <= LT < leaf level: `node` is a proper ancestor
                 if (len > HUGE_SEG) {
@@ -219,6 +220,8 @@ __global__ void __launch_bounds__(HY_THREADS) hy_scatter_kernel(hybrid_params<T>
     const int lane = tid & 31, warp = tid >> 5;
     const int mt = p.m - t * HY_TILE < HY_TILE ? p.m - t * HY_TILE : HY_TILE;
     const bool need_coop = p.status[SW_NEED_COOP] != 0;
+    // keys of a top level are only read where a segment is retired (skewed batches) and at level LT
+    const unsigned int key_levels = p.status[SW_HY_KEYLEVELS] | (1u << LT);
 
     for (int b = tid; b < 2 * bins; b += HY_THREADS) s_cnt[b] = 0;
     __syncthreads();
@@ -313,7 +316,7 @@ __global__ void __launch_bounds__(HY_THREADS) hy_scatter_kernel(hybrid_params<T>
                 dv[k] = s_d[i];
                 const uint32_t node = ky[k] >> bit;
                 const unsigned int g = s_base[node] + ((unsigned int)i - s_cnt[node]);
-                gk[g] = ky[k];
+                if ((key_levels >> l) & 1u) gk[g] = ky[k];
                 gd[g] = dv[k];
                 if (l == LT && need_coop) {
                     const int s = p.segstart[node];

@@ -885,11 +885,11 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
             hp.qlong = w.queue; hp.qmed = w.queue_med; hp.qhuge = w.queue_huge; hp.qret = w.queue_ret;
             hp.huge_off = w.huge_off; hp.status = status;
             const size_t seg_smem = hy_segment_smem<T>();
-            if (!t->hy_attr) {
-                e = cudaFuncSetAttribute(hy_segment_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seg_smem);
-                if (e != cudaSuccess) return e;
-                t->hy_attr = 1;
-            }
+            static per_device_once hy_attr;   // function attributes are per device
+            e = hy_attr.run(t->device, [&] {
+                return cudaFuncSetAttribute(hy_segment_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seg_smem);
+            });
+            if (e != cudaSuccess) return e;
             g_kernel_launches += 4;
             hy_hist_kernel<<<hp.ntiles, HY_THREADS, 0, s>>>(w.kj, m, depth, LT, w.hy_hist, status);
             hy_scan_kernel<T><<<1 << LT, HY_THREADS, 0, s>>>(hp);
@@ -920,7 +920,22 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
         using REC = chunk_rec<typename fp_bits<T>::I>;
         mark(3);
         ++g_kernel_launches;
-        retire_kernel<T><<<t->sm_count * 8, 256, 0, s>>>(H, n, depth, w.kj, w.lev_key, lev, B, w.queue_ret, status);
+        // Retirement touches only the nodes of retired segments (and everything below them), the folds that follow
+        // only the nodes of longer segments: disjoint, both read lev_d / the queues only.  The retirement is bound
+        // by the L2 / HBM atomic units, the folds by integer math, so they run side by side: retirement on the
+        // tree's side stream with half of every SM's thread slots, the folds on the caller's stream.
+        static const bool overlap_off = getenv("ST_OVERLAP") && atoi(getenv("ST_OVERLAP")) == 0;   // A/B switch
+        const bool overlap = !overlap_off && !t->profile && t->side;
+        if (overlap) {
+            e = cudaEventRecord(t->ev_fork, s);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(t->side, t->ev_fork, 0);
+            if (e != cudaSuccess) return e;
+            retire_kernel<T><<<t->sm_count * 4, 256, 0, t->side>>>(H, n, depth, w.kj, w.lev_key, lev, B, w.queue_ret, status);
+            e = cudaEventRecord(t->ev_join, t->side);
+            if (e != cudaSuccess) return e;
+        } else {
+            retire_kernel<T><<<t->sm_count * 8, 256, 0, s>>>(H, n, depth, w.kj, w.lev_key, lev, B, w.queue_ret, status);
+        }
         g_kernel_launches += 4;
         mark(4);
         // huge segments: chunk summaries -> first-pass stitch (pure map composition; a segment whose
@@ -940,9 +955,13 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
             H, lev, B, w.queue, w.queue_med, status, retire_params<T>{nullptr, nullptr, nullptr, 0, 0},
             huge_params<T>{w.queue_huge, w.huge_off, (const REC *)w.huge_recs, (const REC *)w.huge_recs2, w.huge_redo,
                            redo_stride});
+        if (overlap) {
+            e = cudaStreamWaitEvent(s, t->ev_join, 0);
+            if (e != cudaSuccess) return e;
+        }
         mark(7);
         if (t->profile) {
-            // profiling mode is synchronous by design (bench.py's roofline leg only)
+            // profiling mode is synchronous by design (bench.py's roofline leg only); its phases run one after another
             cudaEventSynchronize(t->prof_ev[7]);
             for (int k = 0; k < 7; ++k) {
                 float ms = 0.f;

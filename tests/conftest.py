@@ -4,6 +4,10 @@ import sys
 import numpy as np
 import pytest
 
+# The thread-rank tests run several "ranks" on ONE GPU with spinning wait kernels (tests/_thread_group.py): a lazy
+# module load in the middle of a step would wait for the whole device, i.e. for a kernel that waits for this thread.
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 for p in (ROOT, GOLDEN):

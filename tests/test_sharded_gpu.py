@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, dt_name, logn, q):
+def _worker(rank, world, port, dt_name, logn, q, peer=True):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     import torch.distributed as dist
@@ -31,7 +31,7 @@ def _worker(rank, world, port, dt_name, logn, q):
         oracle.c.build_sumtree_from_array(ref_leaves, ref_tree)
         nl = n // world
         dev = torch.device("cuda", rank)
-        st = ShardedSumTree(n, tdt, local_leaves=torch.from_numpy(leaves[rank * nl:(rank + 1) * nl].copy()).to(dev))
+        st = ShardedSumTree(n, tdt, local_leaves=torch.from_numpy(leaves[rank * nl:(rank + 1) * nl].copy()).to(dev), peer=peer)
         ok = st.gather_sumtree().cpu().numpy().tobytes() == ref_tree.tobytes()
         for m, nv in ((1, 1), (4096, 4096), (100_000, 777), (1 << 18, 1 << 18)):
             idx = rng.integers(0, n, m).astype(np.int64)
@@ -46,13 +46,16 @@ def _worker(rank, world, port, dt_name, logn, q):
             got = st.sample_uniform(torch.from_numpy(u).to(dev)).cpu().numpy()
             ok &= bool(np.array_equal(got, want))
         st.poll()
+        ok &= (st._peer is not None) == bool(peer)
+        st.close()
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("peer", [True, False], ids=["peer", "allgather"])
 @pytest.mark.parametrize("dt_name", ["float32", "int32", "float64"])
-def test_sharded_nccl_equals_single_tree(dt_name):
+def test_sharded_nccl_equals_single_tree(dt_name, peer):
     world = min(torch.cuda.device_count(), 8)
     if world < 2:
         pytest.skip("needs >= 2 GPUs")
@@ -61,7 +64,7 @@ def test_sharded_nccl_equals_single_tree(dt_name):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29700 + (os.getpid() + len(dt_name)) % 1000
-    procs = [ctx.Process(target=_worker, args=(r, world, port, dt_name, 22, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port + (500 if peer else 0), dt_name, 22, q, peer)) for r in range(world)]
     for p in procs:
         p.start()
     results = [q.get(timeout=600) for _ in range(world)]
@@ -237,6 +240,23 @@ def test_sharded_cuda_path_on_one_gpu(world, dt_name, peer, monkeypatch):
         want = np.zeros(u.size, np.intp)
         oracle.c.get_prefix_sum_idx(want, (ref_tree[1] * u).astype(dt), ref_leaves, ref_tree)
         batches.append((idx, vals, u, ref_tree.copy(), ref_leaves.copy(), want))
+
+    if peer:
+        # Every kernel the steps use runs once BEFORE the ranks start (first-use work of the CUDA runtime -- module
+        # loading, function attributes -- may wait for the whole device, and in this harness the device then holds
+        # another rank's spinning wait kernel; separate processes on separate GPUs cannot get into that state).
+        from starr_b200 import DeviceSumTree
+        warm = DeviceSumTree(torch.from_numpy(leaves[:nl].copy()).to(dev))
+        warm.reserve(70_000)
+        for idx, vals, u, *_ in batches:
+            w_idx = torch.from_numpy(idx % nl).to(dev)
+            warm.update_(w_idx, torch.from_numpy(vals).to(dev))
+            warm.update_begin_(w_idx, torch.from_numpy(np.resize(vals, idx.size)).to(dev), torch.empty(idx.size, dtype=tdt, device=dev))
+            warm.update_finish_()
+            warm.sample_uniform(torch.from_numpy(u).to(dev))
+        warm.poll()
+        torch.cuda.synchronize()
+        del warm
 
     def rank_body(r):
         torch.cuda.set_device(0)
