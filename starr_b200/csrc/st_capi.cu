@@ -197,7 +197,6 @@ int st_create(int64_t n, int dtype, int device, void *external_heap, st_tree **o
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t->plan_ev, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t->ev_fork, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t->ev_join, cudaEventDisableTiming);
-        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&t->side, cudaStreamNonBlocking);
     }
     if (e == cudaSuccess) e = cudaMemset(t->d_status, 0, 64 * sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMemset(t->heap, 0, heap_bytes);

@@ -57,6 +57,7 @@ struct st_tree {
     std::recursive_mutex mu;
     int64_t pending_ni = 0;    // split update (st_update_begin_device): batch size waiting for st_update_finish_device
     int pending_split = 0;
+    int pending_gb = 0;        // leaf-group bits of the latest float batch (deep_red_kernel / retire_kernel)
     int64_t stat_updates = 0;  // updates submitted since the last st_update_counters(reset)
     // pipelined host step (st_per_step_host_submit / _wait): two slots of device staging + streams + events
     struct host_slot {

@@ -65,6 +65,8 @@ struct update_ws {
     unsigned int *hy_hist, *hy_bintotal;   // hybrid partition (st_partition_hybrid.cuh)
     int *hy_segstart, *hy_seglen;
     unsigned char *hy_segstate;
+    unsigned int *bigmap;      // bit per leaf group: more than DEEP_GROUP_MAX updates (ancestors not by deep_red_kernel)
+    size_t bigmap_bytes;
     void *cub_tmp;
     size_t cub_bytes;
     size_t total;
@@ -112,6 +114,9 @@ static update_ws carve(const st_tree *t, int64_t B, char *base)
         w.hy_segstart = (int *)take(2 * HY_MAX_BINS * sizeof(int));
         w.hy_seglen = (int *)take(2 * HY_MAX_BINS * sizeof(int));
         w.hy_segstate = (unsigned char *)take(2 * HY_MAX_BINS);
+        // groups: fewer than 4 * B when the group size is maximal, fewer than 2n >> 10 when it is capped (deep_group_bits)
+        w.bigmap_bytes = (size_t)(B / 2 + t->n / 4096 + 256);
+        w.bigmap = (unsigned int *)take(w.bigmap_bytes);
     }
     if (t->cub_cap != B) {
         // temp-storage queries are host-side work: do them once per capacity, not once per call
@@ -170,7 +175,7 @@ __global__ void __launch_bounds__(256) make_keys_kernel(const int64_t *__restric
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j == 0) { status[SW_QCOUNT] = 0; status[SW_QTAKE] = 0; status[SW_QCOUNT_MED] = 0; status[SW_QTAKE_MED] = 0;
                   status[SW_QCOUNT_HUGE] = 0; status[SW_HUGE_CHUNKS] = 0; status[SW_QTAKE_HUGE] = 0;
-                  status[SW_ANYLONG] = 0; status[SW_ANYLONG + 1] = 0; status[SW_QCOUNT_RET] = 0; status[SW_REDO_ANY] = 0; }
+                  status[SW_ANYLONG] = 0; status[SW_ANYLONG + 1] = 0; status[SW_QCOUNT_RET] = 0; status[SW_REDO_ANY] = 0; status[SW_ANYBIG] = 0; }
     if (j >= m) return;
     const uint32_t h = (uint32_t)idx[j] + n;
     const uint32_t key = h << (depth - heap_level(h));
@@ -215,14 +220,20 @@ __global__ void __launch_bounds__(256) leaf_pass_kernel(T *__restrict__ H, uint3
 }
 
 // Float path: the sort only has to bring the duplicates of one leaf together in batch order, so the
-// low `gb` key bits may be left unsorted (one radix pass less).  A group = the updates of 2^gb
-// neighbouring leaves, batch-ordered; its head thread walks it and keeps every leaf's running value
-// in memory (its own earlier stores are visible to its later loads).  Used when groups are sparse.
+// low `gb` key bits may be left unsorted.  A group = the updates of the 2^gb neighbouring leaves below one
+// level-(depth-gb) node, batch-ordered; its head thread walks it (the running value of the leaf it touched
+// last stays in a register, other leaves go through memory: its own earlier stores are visible to its
+// later loads).  gb is chosen so that a group holds at most one update on average.
+// Groups with more than DEEP_GROUP_MAX updates are flagged in `bigmap` (bit per group): their ancestors are
+// left to the partition / fold / retirement machinery; all other groups get theirs from deep_red_kernel.
+constexpr int DEEP_GROUP_MAX = 64;   // <= RETIRE_SEG, so that an unflagged group never holds a fold segment
+
 template <typename T>
 __global__ void __launch_bounds__(256) leaf_pass_grouped_kernel(T *H, uint32_t n, const uint32_t *__restrict__ keys,
                                                                 const int *__restrict__ js, int m,
                                                                 const T *__restrict__ vals, uint64_t nv, uint64_t j0,
-                                                                T *__restrict__ dj, int gb, unsigned int *status,
+                                                                T *__restrict__ dj, T *__restrict__ ds, int gb, int depth,
+                                                                unsigned int *__restrict__ bigmap, unsigned int *status,
                                                                 bool assign)
 {
     if (status[SW_STATUS]) return;
@@ -234,21 +245,60 @@ __global__ void __launch_bounds__(256) leaf_pass_grouped_kernel(T *H, uint32_t n
     int e = i;
     uint32_t key = keys[i];
     unsigned int nzero = 0;
+    uint32_t h_last = 0;      // 0 is never a leaf
+    T v_last = T(0);
     do {
         const uint32_t h = key_to_heap(key, two_n);
         const uint32_t j = (uint32_t)js[e];
         const uint64_t g = j0 + j;  // position in the whole batch (pyx:44: vals[i % nv])
         const T v = vals[g < nv ? g : g % nv];
-        const T cur = H[h];
+        const T cur = (h == h_last) ? v_last : H[h];
         const T d = t_sub<T>(v, cur);
-        H[h] = assign ? v : t_add<T>(cur, d);
+        v_last = assign ? v : t_add<T>(cur, d);
+        h_last = h;
+        H[h] = v_last;
         dj[j] = d;
+        ds[e] = d;
         nzero += (d == T(0));
         ++e;
         if (e >= m) break;
         key = keys[e];
     } while ((key >> gb) == grp);
+    if (bigmap && e - i > DEEP_GROUP_MAX) {
+        const uint32_t gi = grp - (1u << (depth - gb));
+        atomicOr(bigmap + (gi >> 5), 1u << (gi & 31));
+        status[SW_ANYBIG] = 1;
+    }
     if (nzero) atomicAdd(status + SW_STAT_ZERO_DELTA, nzero);
+}
+
+// Ancestors at the levels depth-gb .. leaf level - 1 ("deep" levels: the ones that do not fit the L2) of every
+// group the leaf pass did not flag: all updates of such a node belong to ONE group, so the group's head thread
+// adds them in batch order (ordered_add: same-thread same-address atomics keep program order).  Runs in
+// leaf-sorted order, so consecutive threads touch neighbouring sectors of every level (DRAM pages are reused),
+// which the batch-ordered retirement could not do for these levels.
+template <typename T>
+__global__ void __launch_bounds__(256) deep_red_kernel(T *__restrict__ H, uint32_t n, int depth, int gb,
+                                                       const uint32_t *__restrict__ keys, const T *__restrict__ ds, int m,
+                                                       const unsigned int *__restrict__ status)
+{
+    if (status[SW_STATUS]) return;
+    const uint64_t two_n = 2ull * n;
+    const int top = depth - gb;                          // level of the group's node
+    // grid-stride: the launch is kept small on purpose (it shares the SMs with the partition on the main stream)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+        uint32_t key = keys[i];
+        const uint32_t grp = key >> gb;
+        if (i > 0 && (keys[i - 1] >> gb) == grp) continue;  // not the head of its group
+        int len = 1;
+        while (len <= DEEP_GROUP_MAX && i + len < m && (keys[i + len] >> gb) == grp) ++len;
+        if (len > DEEP_GROUP_MAX) continue;                  // flagged group: not ours
+        for (int e = i; e < i + len; ++e) {
+            key = keys[e];
+            const T d = ds[e];
+            for (int l = key_leaf_level(key, two_n, depth) - 1; l >= top; --l) ordered_add<T>(H + (key >> (depth - l)), d);
+        }
+    }
 }
 
 // -----------------------------------------------------------------------------------------
@@ -328,7 +378,8 @@ template <typename T>
 __device__ __forceinline__ void retire_warps(T *__restrict__ H, uint32_t n, int depth, const uint32_t *__restrict__ key0,
                                              const uint32_t *__restrict__ lev_key, const T *__restrict__ lev_d,
                                              int64_t lev_stride, const seg_entry *__restrict__ qret, unsigned int total,
-                                             unsigned int warp_id, unsigned int warps);
+                                             unsigned int warp_id, unsigned int warps, int deep_level = 1 << 20,
+                                             int gb = 0, const unsigned int *__restrict__ bigmap = nullptr);
 
 // Queued segments: exact parallel ordered folds (st_ordered_fold.cuh).  CTAs first drain the
 // queue of long segments (one CTA each), then their warps drain the queue of medium segments
@@ -416,8 +467,11 @@ __device__ __forceinline__ void retire_warps(T *__restrict__ H, uint32_t n, int 
                                              const uint32_t *__restrict__ lev_key,
                                              const T *__restrict__ lev_d, int64_t lev_stride,
                                              const seg_entry *__restrict__ qret, unsigned int total,
-                                             unsigned int warp_id, unsigned int warps)
+                                             unsigned int warp_id, unsigned int warps, int deep_level, int gb,
+                                             const unsigned int *__restrict__ bigmap)
 {
+    // levels >= deep_level belong to deep_red_kernel, except below the groups the leaf pass flagged in bigmap
+    // (bigmap == nullptr: no group was flagged in this batch)
     const uint64_t two_n = 2ull * n;
     const int lane = threadIdx.x & 31;
     for (unsigned int w = warp_id; w < total; w += warps) {
@@ -441,7 +495,14 @@ __device__ __forceinline__ void retire_warps(T *__restrict__ H, uint32_t n, int 
                 T dx;
                 if constexpr (sizeof(T) == 8) dx = __longlong_as_double(__shfl_sync(0xffffffffu, __double_as_longlong(dv), x));
                 else dx = __shfl_sync(0xffffffffu, dv, x);
-                if (have_level && l2 < key_leaf_level(kx, two_n, depth)) ordered_add<T>(H + (kx >> sh), dx);
+                if (have_level && l2 < key_leaf_level(kx, two_n, depth)) {
+                    bool mine = l2 < deep_level;
+                    if (!mine && bigmap) {
+                        const uint32_t gi = (kx >> gb) - (1u << (depth - gb));
+                        mine = (bigmap[gi >> 5] >> (gi & 31)) & 1u;
+                    }
+                    if (mine) ordered_add<T>(H + (kx >> sh), dx);
+                }
             }
         }
     }
@@ -452,11 +513,13 @@ __global__ void __launch_bounds__(256) retire_kernel(T *__restrict__ H, uint32_t
                                                      const uint32_t *__restrict__ key0,
                                                      const uint32_t *__restrict__ lev_key,
                                                      const T *__restrict__ lev_d, int64_t lev_stride,
-                                                     const seg_entry *__restrict__ qret, const unsigned int *status)
+                                                     const seg_entry *__restrict__ qret, const unsigned int *status,
+                                                     int deep_level, int gb, const unsigned int *__restrict__ bigmap)
 {
     if (status[SW_STATUS]) return;
     retire_warps<T>(H, n, depth, key0, lev_key, lev_d, lev_stride, qret, status[SW_QCOUNT_RET],
-                    blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), gridDim.x * (blockDim.x >> 5));
+                    blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), gridDim.x * (blockDim.x >> 5), deep_level, gb,
+                    status[SW_ANYBIG] ? bigmap : nullptr);
 }
 
 // Huge segments, phase A: every CTA summarises chunks (see st_ordered_fold.cuh).
@@ -760,6 +823,15 @@ __global__ void __launch_bounds__(FOLD_THREADS) fold_top_maps_kernel(const T *__
 // -----------------------------------------------------------------------------------------
 // host driver
 // -----------------------------------------------------------------------------------------
+// group size (in key bits) of the float leaf pass / deep pass: the largest gb with m * 2^gb <= n, at most 10,
+// and never the whole tree (a group's node stays below the root)
+static int deep_group_bits(int m, int64_t n, int depth)
+{
+    int gb = 0;
+    while (gb < 10 && gb + 2 <= depth && ((int64_t)m << (gb + 1)) <= n) ++gb;
+    return gb;
+}
+
 template <typename T>
 static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *idx, int m, const T *vals,
                                 int64_t nv, int64_t j0, int64_t B, T *delta_out, const T *deltas_in,
@@ -819,23 +891,24 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
     make_keys_kernel<<<g, 256, 0, s>>>(idx, m, n, depth, w.keys_a, w.kj, w.j_a, status);
     }
     if (!deltas_in && phase != 2) {
-        // floats only need the duplicates of a leaf adjacent: drop the partial low radix digit when the
-        // groups this creates (2^gb neighbouring leaves) hold less than one update on average
+        // floats only need the duplicates of a leaf adjacent and batch-ordered: the low gb key bits stay unsorted,
+        // gb as large as keeps the groups this creates (2^gb neighbouring leaves) at <= 1 update on average
         int gb = 0;
-        if constexpr (is_float_t<T>::value) {
-            const int rem = (depth + 1) % 8;
-            if (rem && depth + 1 > 8 && ((int64_t)m << rem) <= (int64_t)n) gb = rem;
-        }
+        if constexpr (is_float_t<T>::value) gb = deep_group_bits(m, (int64_t)n, depth);
+        t->pending_gb = gb;
         e = cub::DeviceRadixSort::SortPairs(w.cub_tmp, cb, w.keys_a, w.keys_b, w.j_a, w.j_b, m, gb, depth + 1, s);
         if (e != cudaSuccess) return e;
         mark(1);
         ++g_kernel_launches;
-        if (gb)
+        if (gb) {
+            e = cudaMemsetAsync(w.bigmap, 0, (((size_t)1 << (depth - gb)) + 7) / 8 + 4, s);
+            if (e != cudaSuccess) return e;
             leaf_pass_grouped_kernel<T><<<g, 256, 0, s>>>(H, n, w.keys_b, w.j_b, m, vals, (uint64_t)nv, (uint64_t)j0,
-                                                         (T *)w.dj, gb, status, assign);
-        else
+                                                         (T *)w.dj, (T *)w.ds, gb, depth, w.bigmap, status, assign);
+        } else {
             leaf_pass_kernel<T><<<g, 256, 0, s>>>(H, n, w.keys_b, w.j_b, m, vals, (uint64_t)nv, (uint64_t)j0,
                                                   (T *)w.dj, (T *)w.ds, status, assign);
+        }
         d_batch = (const T *)w.dj;
         if (delta_out) {
             e = cudaMemcpyAsync(delta_out, w.dj, (size_t)m * sizeof(T), cudaMemcpyDeviceToDevice, s);
@@ -856,6 +929,31 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
         // the top l+1 key bits.  lev_d[l] keeps every level's ordered d for the long folds.
         T *lev = (T *)w.lev_d;
         mark(2);
+        // Side stream.  Three groups of nodes are written by three independent parts of the pipeline, all of which
+        // only read the batch arrays: (1) the deep levels below the leaf groups -- deep_red_kernel, in leaf-sorted
+        // order, needs nothing but the leaf pass; (2) the nodes of retired segments -- retire_kernel, needs the
+        // partition; (3) the nodes of longer segments -- the folds.  (1) and (2) are bound by the L2 / HBM atomic
+        // units, the partition and (3) by shared memory and integer math, so (1) + (2) run on the tree's side stream
+        // (retirement with half of every SM's thread slots) beside the partition and the folds on the caller's.
+        static const bool overlap_off = getenv("ST_OVERLAP") && atoi(getenv("ST_OVERLAP")) == 0;   // A/B switch
+        if (!overlap_off && !t->profile && !t->side) {   // created by the first large float batch (the caller holds the tree's lock)
+            e = cudaStreamCreateWithFlags(&t->side, cudaStreamNonBlocking);
+            if (e != cudaSuccess) return e;
+        }
+        const bool overlap = !overlap_off && !t->profile && t->side;
+        const int gbd = deltas_in ? 0 : t->pending_gb;            // leaf-group bits (0: no deep pass)
+        const int deep_level = gbd ? depth - gbd : (1 << 20);     // retirement stops here, except under flagged groups
+        cudaStream_t rs = overlap ? t->side : s;
+        if (overlap) {
+            e = cudaEventRecord(t->ev_fork, s);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(t->side, t->ev_fork, 0);
+            if (e != cudaSuccess) return e;
+            if (gbd) {
+                ++g_kernel_launches;
+                static const int deep_ctas = getenv("ST_DEEP_CTAS") ? atoi(getenv("ST_DEEP_CTAS")) : 2;   // per SM (tuning)
+                deep_red_kernel<T><<<t->sm_count * deep_ctas, 256, 0, rs>>>(H, n, depth, gbd, w.keys_b, (const T *)w.ds, m, status);
+            }
+        }
         e = cudaMemcpyAsync(lev, d_batch, (size_t)m * sizeof(T), cudaMemcpyDeviceToDevice, s);
         if (e != cudaSuccess) return e;
         if (!t->coop_ok) return cudaErrorCooperativeLaunchTooLarge;
@@ -920,21 +1018,21 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
         using REC = chunk_rec<typename fp_bits<T>::I>;
         mark(3);
         ++g_kernel_launches;
-        // Retirement touches only the nodes of retired segments (and everything below them), the folds that follow
-        // only the nodes of longer segments: disjoint, both read lev_d / the queues only.  The retirement is bound
-        // by the L2 / HBM atomic units, the folds by integer math, so they run side by side: retirement on the
-        // tree's side stream with half of every SM's thread slots, the folds on the caller's stream.
-        static const bool overlap_off = getenv("ST_OVERLAP") && atoi(getenv("ST_OVERLAP")) == 0;   // A/B switch
-        const bool overlap = !overlap_off && !t->profile && t->side;
-        if (overlap) {
+        // (retirement: see the note on the side stream above the partition)
+        if (overlap) {   // the side stream (already busy with deep_red_kernel) goes on once the partition is complete
             e = cudaEventRecord(t->ev_fork, s);
             if (e == cudaSuccess) e = cudaStreamWaitEvent(t->side, t->ev_fork, 0);
             if (e != cudaSuccess) return e;
-            retire_kernel<T><<<t->sm_count * 4, 256, 0, t->side>>>(H, n, depth, w.kj, w.lev_key, lev, B, w.queue_ret, status);
+        } else if (gbd) {
+            ++g_kernel_launches;
+            deep_red_kernel<T><<<g, 256, 0, s>>>(H, n, depth, gbd, w.keys_b, (const T *)w.ds, m, status);
+        }
+        static const int retire_ctas = getenv("ST_RETIRE_CTAS") ? atoi(getenv("ST_RETIRE_CTAS")) : 4;   // per SM beside the folds (tuning)
+        retire_kernel<T><<<t->sm_count * (overlap ? retire_ctas : 8), 256, 0, rs>>>(H, n, depth, w.kj, w.lev_key, lev, B, w.queue_ret,
+                                                                          status, deep_level, gbd, w.bigmap);
+        if (overlap) {
             e = cudaEventRecord(t->ev_join, t->side);
             if (e != cudaSuccess) return e;
-        } else {
-            retire_kernel<T><<<t->sm_count * 8, 256, 0, s>>>(H, n, depth, w.kj, w.lev_key, lev, B, w.queue_ret, status);
         }
         g_kernel_launches += 4;
         mark(4);

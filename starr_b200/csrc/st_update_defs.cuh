@@ -26,6 +26,7 @@ struct seg_entry {
 // status-word layout (unsigned int[64])
 enum { SW_STATUS = 0, SW_QCOUNT = 1, SW_QTAKE = 2, SW_QCOUNT_MED = 8, SW_QTAKE_MED = 9, SW_QCOUNT_HUGE = 10, SW_HUGE_CHUNKS = 11, SW_QTAKE_HUGE = 12, SW_REDO_ANY = 13, SW_ANYLONG = 14 /* and 15 */, SW_RETIRE_MASK = 16, SW_QCOUNT_RET = 19, SW_STAT_FAST = 4, SW_STAT_CHAINS = 5, SW_STAT_CHAIN_ELEMS = 6, SW_STAT_LONGEST = 7, SW_STAT_ZERO_DELTA = 20 /* updates whose difference was exactly 0 (cumulative) */,
        SW_NEED_COOP = 23 /* hybrid partition: a level-LT segment is too long for one CTA (21 = ST_SW_STICKY) */, SW_HY_TICKET = 24,
+       SW_ANYBIG = 26 /* the leaf pass flagged a group in bigmap */,
        SW_HY_KEYLEVELS = 25 /* bit l: lev_key[l] of a top level l is read (a segment is retired there) */ };
 
 // -----------------------------------------------------------------------------------------

@@ -108,6 +108,8 @@ class ShardedSumTree:
                 h.reserve_sharded(max_global_batch, self.world)
             else:
                 tree.reserve(max_global_batch)
+        if self._peer_wanted:       # collective, like every call on a sharded tree: the exchange area for this batch size
+            self._ensure_peer(mu=max_global_batch, ms=max_global_batch)
 
     def _mark(self, label: str) -> None:
         if self._marks is not None:

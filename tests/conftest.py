@@ -7,6 +7,9 @@ import pytest
 # The thread-rank tests run several "ranks" on ONE GPU with spinning wait kernels (tests/_thread_group.py): a lazy
 # module load in the middle of a step would wait for the whole device, i.e. for a kernel that waits for this thread.
 os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+# ... and every rank thread brings 3-4 streams: with the default of 8 hardware queues, one rank's signal kernel can end
+# up queued behind another rank's wait kernel (which waits for that signal).  One queue per stream avoids it.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
