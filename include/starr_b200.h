@@ -136,6 +136,9 @@ ST_API int st_update_host_ex(st_tree *t, const int64_t *idx_host, int64_t ni, co
  * for its host mirror: floats store fl(old + fl(val - old)), not val), in one staging round. */
 ST_API int st_update_gather_host(st_tree *t, const int64_t *idx_host, int64_t ni, const void *vals_host,
                           int64_t nv, void *leaves_out_host);
+/* the same, also returning the root after the update (the host layer's `sum()` then needs no call of its own) */
+ST_API int st_update_gather_root_host(st_tree *t, const int64_t *idx_host, int64_t ni, const void *vals_host, int64_t nv,
+                               void *leaves_out_host, void *root_out_host);
 
 /* ---- building blocks of the subtree-sharded tree (no reference counterpart: the reference is
  * single-process; these keep the sharded result bit-identical to ONE reference tree) -------- */
@@ -204,6 +207,10 @@ ST_API int st_search_counted_device(const st_tree *t, const void *vals_dev, int6
  *   indices: out[j] = shard[j] * leaves_per_shard + slabs[...]              (int32 slabs -> int64) */
 ST_API int st_shard_expand_values_device(const st_tree *t, const uint8_t *shard_dev, const int32_t *slot_dev, int64_t m,
                                   const void *slabs_dev, int64_t slab_stride, void *out_dev, void *stream);
+/* out[j] = cat[starts[shard[j]] + slot[j]]: the shards' slabs stored back to back (peer exchange); starts_host: `shards`
+ * element offsets, read during the call */
+ST_API int st_shard_expand_cat_device(const st_tree *t, const uint8_t *shard_dev, const int32_t *slot_dev, int64_t m,
+                               const void *cat_dev, const int64_t *starts_host, int shards, void *out_dev, void *stream);
 ST_API int st_shard_expand_indices_device(const st_tree *t, const uint8_t *shard_dev, const int32_t *slot_dev,
                                    int64_t m, const int32_t *slabs_dev, int64_t slab_stride,
                                    int64_t leaves_per_shard, int64_t *out_dev, void *stream);
@@ -240,6 +247,18 @@ ST_API int st_peer_broadcast(st_peer *p, int64_t offset, int64_t bytes, void *st
  * pos values must lie in [0, span_elems); count_dev may be NULL */
 ST_API int st_peer_scatter(st_peer *p, const void *src_dev, const int32_t *pos_dev, int64_t count,
                     const uint32_t *count_dev, int esize, int64_t offset, int64_t span_elems, void *stream);
+/* payload_q[dst_offset + k*esize] = src[k], k < min(count, *count_dev), on EVERY rank q: consecutive elements, so every
+ * warp store is one full-width NVLink write (the scattered stores of st_peer_scatter cost a packet per element).
+ * esize 4 or 8; count_dev nullable; count_offset >= 0: the number of elements also goes to payload_q[count_offset] (uint32) */
+ST_API int st_peer_put(st_peer *p, const void *src_dev, int64_t count, const uint32_t *count_dev, int esize,
+                int64_t dst_offset, int64_t count_offset, void *stream);
+/* out[pos] = q * leaves_per_shard + idx for the int32 (pos, idx) pairs every rank q has put into THIS rank's buffer: rank q's
+ * pairs start at payload[pairs_offset + q*slab_bytes], their number is the uint32 at payload[counts_offset + 4q] */
+ST_API int st_peer_scatter_pairs(st_peer *p, int64_t pairs_offset, int64_t slab_bytes, int64_t counts_offset,
+                          int64_t leaves_per_shard, int64_t *out_dev, int64_t m, void *stream);
+/* st_search_counted_device whose result k is stored as the int32 pair (pos[k], local leaf) in pairs_out[2k], [2k+1] */
+ST_API int st_search_pairs_device(const st_tree *t, const void *vals_dev, int64_t m_max, const uint32_t *m_dev,
+                           const int32_t *pos_dev, int32_t *pairs_out_dev, void *stream);
 /* release-store `value` into flags[channel][this rank] of every rank / spin until flags[channel][q] has
  * reached `value` for every q (wrap-safe compare; gives up after 20 s and records it for st_peer_status) */
 ST_API int st_peer_signal(st_peer *p, int channel, unsigned int value, void *stream);

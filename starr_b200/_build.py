@@ -22,6 +22,7 @@ FLAGS = [
     *(["-DST_SMALL_TIMING"] if os.environ.get("ST_SMALL_TIMING") else []),
     *([f"-DST_RETIRE_SEG={os.environ['ST_RETIRE_SEG']}"] if os.environ.get("ST_RETIRE_SEG") else []),
     *([f"-DST_HUGE_SEG={os.environ['ST_HUGE_SEG']}"] if os.environ.get("ST_HUGE_SEG") else []),
+    *([f"-DST_HY_SEG={os.environ['ST_HY_SEG']}"] if os.environ.get("ST_HY_SEG") else []),
     *([f"-DST_SMALL_RETIRE_SEG={os.environ['ST_SMALL_RETIRE_SEG']}"] if os.environ.get("ST_SMALL_RETIRE_SEG") else []),
     "-Xptxas", "-v" if os.environ.get("ST_PTXAS_V") else "-O3",
 ]

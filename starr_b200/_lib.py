@@ -100,6 +100,7 @@ _SIGNATURES = {
                                                c_void_p]),
     "st_route_uniform_device": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "st_update_gather_host": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
+    "st_update_gather_root_host": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
     "st_sample_root_host": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "st_search_device": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "st_search_host": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
@@ -132,6 +133,10 @@ _SIGNATURES = {
     "st_peer_payload_bytes": (c_int64, [c_void_p]),
     "st_peer_broadcast": (c_int, [c_void_p, c_int64, c_int64, c_void_p]),
     "st_peer_scatter": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int64, c_int64, c_void_p]),
+    "st_peer_put": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int64, c_int64, c_void_p]),
+    "st_peer_scatter_pairs": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p]),
+    "st_search_pairs_device": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "st_shard_expand_cat_device": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "st_peer_signal": (c_int, [c_void_p, c_int, ctypes.c_uint, c_void_p]),
     "st_peer_wait": (c_int, [c_void_p, c_int, ctypes.c_uint, c_void_p]),
     "st_peer_status": (c_int, [c_void_p, c_void_p]),
@@ -273,6 +278,14 @@ class TreeHandle:
         check(lib().st_update_gather_host(self.ptr, host_ptr(idx), idx.size, host_ptr(vals), vals.size,
                                           host_ptr(out)))
         return out
+
+    def update_gather_root_host(self, idx: np.ndarray, vals: np.ndarray):
+        """``update_gather_host`` that also returns the root after the update (same staging round, one sync)."""
+        out = np.empty(idx.size, dtype=self.dtype)
+        root = np.zeros(1, dtype=self.dtype)
+        check(lib().st_update_gather_root_host(self.ptr, host_ptr(idx), idx.size, host_ptr(vals), vals.size,
+                                               host_ptr(out), host_ptr(root)))
+        return out, root[0]
 
     def sample_root_host(self, u: np.ndarray, out: np.ndarray):
         root = np.zeros(1, dtype=self.dtype)
@@ -428,6 +441,18 @@ class TreeHandle:
                            payload_offset: int, span_elems: int, stream: int = 0) -> None:
         check(lib().st_search_push_device(self.ptr, c_void_p(vals_ptr), int(m_max), c_void_p(m_dev_ptr), c_void_p(pos_ptr),
                                           int(index_offset), peer.ptr, int(payload_offset), int(span_elems), c_void_p(stream)))
+
+    def search_pairs_device(self, vals_ptr: int, m_max: int, m_dev_ptr: int, pos_ptr: int, pairs_ptr: int, stream: int = 0) -> None:
+        status = lib().st_search_pairs_device(self.ptr, c_void_p(vals_ptr), int(m_max), c_void_p(m_dev_ptr), c_void_p(pos_ptr),
+                                              c_void_p(pairs_ptr), c_void_p(stream))
+        if status != ST_OK:
+            raise RuntimeError(lib().st_peer_last_error().decode("utf-8", "replace"))
+
+    def shard_expand_cat_device(self, shard_ptr: int, slot_ptr: int, m: int, cat_ptr: int, starts: list, out_ptr: int,
+                                stream: int = 0) -> None:
+        arr = (c_int64 * len(starts))(*[int(x) for x in starts])
+        check(lib().st_shard_expand_cat_device(self.ptr, c_void_p(shard_ptr), c_void_p(slot_ptr), int(m), c_void_p(cat_ptr), arr,
+                                               len(starts), c_void_p(out_ptr), c_void_p(stream)))
 
     def shard_plan_wait(self, result_slot: int, shards: int) -> list[int]:
         counts = (c_int64 * int(shards))()
@@ -589,6 +614,16 @@ class PeerArea:
         self._check(lib().st_peer_scatter(self.ptr, c_void_p(src_ptr), c_void_p(pos_ptr), int(count),
                                           c_void_p(count_dev_ptr) if count_dev_ptr else None, int(esize), int(offset),
                                           int(span_elems), c_void_p(stream)))
+
+    def put(self, src_ptr: int, count: int, esize: int, dst_offset: int, count_dev_ptr: int = 0, count_offset: int = -1,
+            stream: int = 0) -> None:
+        self._check(lib().st_peer_put(self.ptr, c_void_p(src_ptr), int(count), c_void_p(count_dev_ptr) if count_dev_ptr else None,
+                                      int(esize), int(dst_offset), int(count_offset), c_void_p(stream)))
+
+    def scatter_pairs(self, pairs_offset: int, slab_bytes: int, counts_offset: int, leaves_per_shard: int, out_ptr: int, m: int,
+                      stream: int = 0) -> None:
+        self._check(lib().st_peer_scatter_pairs(self.ptr, int(pairs_offset), int(slab_bytes), int(counts_offset),
+                                                int(leaves_per_shard), c_void_p(out_ptr), int(m), c_void_p(stream)))
 
     def signal(self, channel: int, value: int, stream: int = 0) -> None:
         self._check(lib().st_peer_signal(self.ptr, int(channel), int(value) & 0xffffffff, c_void_p(stream)))

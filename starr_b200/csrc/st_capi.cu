@@ -198,6 +198,14 @@ int st_create(int64_t n, int dtype, int device, void *external_heap, st_tree **o
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t->ev_fork, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t->ev_join, cudaEventDisableTiming);
     }
+    if (e == cudaSuccess) {
+        // search index (st_sidx.cuh): all zeros matches the all-zero tree
+        t->sidx_bytes = st::sidx_bytes_for(t->n, t->depth, t->esize, t->kind, &t->sidx_nb);
+        if (t->sidx_bytes) {
+            e = cudaMalloc(&t->sidx, t->sidx_bytes);
+            if (e == cudaSuccess) e = cudaMemset(t->sidx, 0, t->sidx_bytes);
+        }
+    }
     if (e == cudaSuccess) e = cudaMemset(t->d_status, 0, 64 * sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMemset(t->heap, 0, heap_bytes);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
@@ -218,6 +226,7 @@ int st_destroy(st_tree *t)
     if (t->h_status) cudaFreeHost(t->h_status);
     if (t->h_pin) cudaFreeHost(t->h_pin);
     if (t->plan_ev) cudaEventDestroy(t->plan_ev);
+    if (t->sidx) cudaFree(t->sidx);
     if (t->ev_fork) cudaEventDestroy(t->ev_fork);
     if (t->ev_join) cudaEventDestroy(t->ev_join);
     if (t->side) cudaStreamDestroy(t->side);
@@ -270,6 +279,11 @@ int st_load_host(st_tree *t, const void *leaves, const void *tree)
     const size_t half = (size_t)t->n * t->esize;
     if (tree) CU(cudaMemcpy(t->heap, tree, half, cudaMemcpyHostToDevice));
     if (leaves) CU(cudaMemcpy((char *)t->heap + half, leaves, half, cudaMemcpyHostToDevice));
+    if (tree && t->sidx) {   // the search index follows the tree that was just loaded
+        CU(cudaMemsetAsync(t->d_status, 0, sizeof(unsigned int), 0));
+        CU(st::launch_sidx_build(t, 0));
+        CU(cudaStreamSynchronize(0));
+    }
     return ST_OK;
 }
 
@@ -557,6 +571,17 @@ int st_shard_expand_values_device(const st_tree *t, const uint8_t *shard_dev, co
     return ST_OK;
 }
 
+int st_shard_expand_cat_device(const st_tree *t, const uint8_t *shard_dev, const int32_t *slot_dev, int64_t m,
+                               const void *cat_dev, const int64_t *starts_host, int shards, void *out_dev, void *stream)
+{
+    if (!t || m < 0 || shards < 1 || shards > 64 || !starts_host || (m > 0 && (!shard_dev || !slot_dev || !cat_dev || !out_dev)))
+        return fail(ST_ERR_ARG, "st_shard_expand_cat_device: bad argument");
+    tree_lock lk(t);
+    device_guard g(t->device);
+    CU(st::launch_shard_expand_cat(t, shard_dev, slot_dev, m, cat_dev, starts_host, shards, out_dev, (cudaStream_t)stream));
+    return ST_OK;
+}
+
 int st_shard_expand_indices_device(const st_tree *t, const uint8_t *shard_dev, const int32_t *slot_dev, int64_t m,
                                    const int32_t *slabs_dev, int64_t slab_stride, int64_t leaves_per_shard,
                                    int64_t *out_dev, void *stream)
@@ -584,6 +609,12 @@ int st_route_uniform_device(const st_tree *t, const double *u_dev, int64_t m, in
 int st_update_gather_host(st_tree *t, const int64_t *idx_host, int64_t ni, const void *vals_host, int64_t nv,
                           void *leaves_out_host)
 {
+    return st_update_gather_root_host(t, idx_host, ni, vals_host, nv, leaves_out_host, nullptr);
+}
+
+int st_update_gather_root_host(st_tree *t, const int64_t *idx_host, int64_t ni, const void *vals_host, int64_t nv,
+                               void *leaves_out_host, void *root_out_host)
+{
     if (!t || ni < 0 || nv < 0 || t->kind != 0) return fail(ST_ERR_ARG, "st_update_gather_host: bad argument");
     if (ni > 0 && nv == 0) return fail(ST_ERR_EMPTY_VALS, "%s", st_status_string(ST_ERR_EMPTY_VALS));
     if (ni == 0 && nv == 0) return ST_OK;
@@ -594,15 +625,16 @@ int st_update_gather_host(st_tree *t, const int64_t *idx_host, int64_t ni, const
         const size_t up = 256;
         auto rnd = [&](size_t b) { return (b + up - 1) / up * up; };
         const size_t o_idx = 0, o_val = o_idx + rnd(ni * sizeof(int64_t)), o_leaf = o_val + rnd(nv * t->esize);
-        const size_t o_stat = o_leaf + rnd(ni * t->esize), total = o_stat + up;
+        const size_t o_stat = o_leaf + rnd(ni * t->esize), o_root = o_stat + up, total = o_root + up;
         if (total <= t->pin_bytes) {
             char *hp = (char *)t->h_pin, *dp = (char *)t->d_pin;
             memcpy(hp + o_idx, idx_host, ni * sizeof(int64_t));
             memcpy(hp + o_val, vals_host, nv * t->esize);
             CU(st::launch_update(t, (const int64_t *)(dp + o_idx), ni, dp + o_val, nv, nullptr, nullptr, 0));
             if (ni && leaves_out_host) CU(st::launch_gather(t, (const int64_t *)(dp + o_idx), ni, dp + o_leaf, 0));
-            CU(st::launch_publish(t, dp + o_stat, nullptr, 0));
+            CU(st::launch_publish(t, dp + o_stat, root_out_host ? dp + o_root : nullptr, 0));   // flags (+ the new root)
             CU(cudaStreamSynchronize(0));
+            if (root_out_host) memcpy(root_out_host, hp + o_root, t->esize);
             const unsigned int f = *(volatile unsigned int *)(hp + o_stat);
             if (f) {
                 CU(clear_status_words(t, 0));
@@ -626,6 +658,7 @@ int st_update_gather_host(st_tree *t, const int64_t *idx_host, int64_t ni, const
     if (ni && leaves_out_host) CU(st::launch_gather(t, di, ni, dl, 0));
     CU(cudaMemcpyAsync(t->h_status, t->d_status, 32 * sizeof(unsigned int), cudaMemcpyDeviceToHost, 0));
     if (ni && leaves_out_host) CU(cudaMemcpyAsync(leaves_out_host, dl, ni * t->esize, cudaMemcpyDeviceToHost, 0));
+    if (root_out_host) CU(cudaMemcpyAsync(root_out_host, (const char *)t->heap + t->esize, t->esize, cudaMemcpyDeviceToHost, 0));
     CU(cudaStreamSynchronize(0));
     const unsigned int f = t->h_status[0] | t->h_status[ST_SW_STICKY];
     if (f) {
@@ -1066,6 +1099,12 @@ int st_min_create(int64_t n, int dtype, int device, void *external_heap, st_tree
     st_tree *t = *out;
     device_guard g(device);
     t->kind = 1;
+    if (t->sidx) {   // the search index belongs to sum trees
+        cudaFree(t->sidx);
+        t->sidx = nullptr;
+        t->sidx_bytes = 0;
+        t->sidx_nb = 0;
+    }
     cudaError_t e = cudaMalloc(&t->aux, (size_t)n * sizeof(int));
     if (e == cudaSuccess) e = st::launch_min_init(t, 0);
     if (e == cudaSuccess) e = cudaStreamSynchronize(0);

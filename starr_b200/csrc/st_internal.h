@@ -68,6 +68,11 @@ struct st_tree {
         int busy = 0;
     } hs[2];
     cudaStream_t hs_in = nullptr, hs_main = nullptr, hs_out = nullptr;
+    // sector-packed search index (st_sidx.cuh): copies of the left children below the staged levels, three levels
+    // per 32-byte record; nullptr when the tree is too small / not a 4-byte sum tree / ST_SEARCH_INDEX=0
+    void *sidx = nullptr;
+    size_t sidx_bytes = 0;
+    int sidx_nb = 0;
     // update pipeline: retirement (ordered atomics on the deep nodes) runs on this stream beside the folds of
     // the top nodes (disjoint node sets); forked / joined with the two events around every batch
     cudaStream_t side = nullptr;
@@ -88,6 +93,7 @@ struct search_push {
     int n = 0;                     // 0: no push (plain search)
     const int32_t *pos = nullptr;
     int64_t index_offset = 0;
+    int32_t *pairs = nullptr;      // != nullptr: result i goes to pairs[2i] = pos[i], pairs[2i+1] = local leaf (no push)
 };
 
 // process-wide count of kernels of THIS library that were launched (bench.py's gpu_launches)
@@ -112,7 +118,9 @@ struct per_device_once {
 
 cudaError_t launch_batch_begin(st_tree *t, cudaStream_t s);   // flags of the previous batch -> sticky word
 cudaError_t launch_check_leaves(st_tree *t, cudaStream_t s);  // sets STF_NEG_ARRAY
-cudaError_t launch_build(st_tree *t, cudaStream_t s);         // skipped on device if status != 0
+cudaError_t launch_build(st_tree *t, cudaStream_t s);         // skipped on device if status != 0; refreshes the search index
+cudaError_t launch_sidx_build(st_tree *t, cudaStream_t s);    // search index from the current heap (no-op without index)
+size_t sidx_bytes_for(int64_t n, int depth, int esize, int kind, int *nb_out);
 // m_dev (nullable): device-side query count, the launch covers min(m, *m_dev) queries
 cudaError_t launch_search(const st_tree *t, const void *vals, int64_t m, int64_t *out, cudaStream_t s,
                           const unsigned int *m_dev = nullptr, const search_push *push = nullptr);
@@ -160,6 +168,8 @@ cudaError_t launch_shard_plan(st_tree *t, const int64_t *ids, int64_t m, int shi
                               unsigned int *counts_out, cudaStream_t s, int32_t *own_pos_out = nullptr);
 cudaError_t launch_shard_expand_values(const st_tree *t, const uint8_t *shard, const int32_t *slot, int64_t m,
                                        const void *slabs, int64_t slab_stride, void *out, cudaStream_t s);
+cudaError_t launch_shard_expand_cat(const st_tree *t, const uint8_t *shard, const int32_t *slot, int64_t m, const void *cat,
+                                    const int64_t *starts_host, int shards, void *out, cudaStream_t s);
 cudaError_t launch_shard_expand_indices(const st_tree *t, const uint8_t *shard, const int32_t *slot, int64_t m,
                                         const int32_t *slabs, int64_t slab_stride, int64_t leaves_per_shard,
                                         int64_t *out, cudaStream_t s);

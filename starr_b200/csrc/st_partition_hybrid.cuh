@@ -28,12 +28,17 @@ namespace st {
 constexpr int HY_TILE = 2048;
 constexpr int HY_THREADS = 256;
 constexpr int HY_E = HY_TILE / HY_THREADS;   // 8
-constexpr int HY_MAX_LT = 9;
-constexpr int HY_MAX_BINS = 1 << HY_MAX_LT;  // 512
+constexpr int HY_MAX_LT = 10;
+constexpr int HY_MAX_BINS = 1 << HY_MAX_LT;  // 1024
 constexpr int HY_MAX_TILES = (int)(UPDATE_MAX_CHUNK / HY_TILE);   // 1024
-constexpr int HY_CAP = 6144;                 // longest level-LT segment a CTA takes (uniform batches: <= 4096 + noise)
-constexpr int HY_B_THREADS = 1024;
-constexpr int HY_B_E = HY_CAP / HY_B_THREADS;   // 6
+#ifndef ST_HY_SEG
+#define ST_HY_SEG 4096                       // level-LT segments of a uniform batch hold ST_HY_SEG/2+1 .. ST_HY_SEG updates
+                                             // (2048 measured the same: partition 113 vs 117 us)
+#endif
+constexpr int HY_SEG = ST_HY_SEG;
+constexpr int HY_CAP = HY_SEG + HY_SEG / 2;  // longest level-LT segment a CTA takes (uniform: <= HY_SEG + noise)
+constexpr int HY_B_E = 6;
+constexpr int HY_B_THREADS = HY_CAP / HY_B_E;   // 512 (HY_SEG 2048) or 1024 (HY_SEG 4096)
 constexpr int HY_SEG_LIVE = 0, HY_SEG_DONE = 1;
 
 template <typename T> struct hybrid_params {
@@ -330,8 +335,10 @@ __global__ void __launch_bounds__(HY_THREADS) hy_scatter_kernel(hybrid_params<T>
 }
 
 // One CTA per live level-LT segment: the rest of the partition in shared memory.
+// (48 registers: a CTA of 1024 threads must leave room on its SM for the side stream's kernels -- with the whole
+// register file it would wait for deep_red_kernel to drain, which serialised the two streams)
 template <typename T>
-__global__ void __launch_bounds__(HY_B_THREADS) hy_segment_kernel(hybrid_params<T> p)
+__global__ void __maxnreg__(48) hy_segment_kernel(hybrid_params<T> p)   // launched with HY_B_THREADS threads
 {
     if (p.status[SW_STATUS] || p.status[SW_NEED_COOP]) return;
     const int node0 = (1 << p.LT) + blockIdx.x;
@@ -476,11 +483,11 @@ __global__ void __launch_bounds__(HY_B_THREADS) hy_segment_kernel(hybrid_params<
 
 template <typename T> static inline size_t hy_segment_smem() { return (size_t)HY_CAP * (sizeof(T) + 4 + 2 + 2 + 2); }
 
-// number of top levels for a batch of m updates: level-LT segments of a uniform batch hold 2049 .. 4096 updates
+// number of top levels for a batch of m updates: level-LT segments of a uniform batch hold HY_SEG/2+1 .. HY_SEG updates
 static inline int hy_top_levels(int m)
 {
     int LT = 1;
-    while (LT < HY_MAX_LT && (m >> LT) > 4096) ++LT;
+    while (LT < HY_MAX_LT && (m >> LT) > HY_SEG) ++LT;
     return LT;
 }
 

@@ -117,6 +117,43 @@ __global__ void __launch_bounds__(256) peer_scatter_kernel(peer_ptrs pp, size_t 
     }
 }
 
+// payload_q[off + k * sizeof(T)] = src[k], k < count, for EVERY rank q: consecutive lanes store consecutive
+// elements, so every warp store is one full 128-byte (or 256-byte) write per peer -- the scattered 4 / 8-byte
+// stores of peer_scatter_kernel cost a whole NVLink packet each.  The element count goes to a header word.
+template <typename T>
+__global__ void __launch_bounds__(256) peer_put_kernel(peer_ptrs pp, size_t off, const T *__restrict__ src, int64_t count,
+                                                       const unsigned int *__restrict__ count_dev, int rank, int64_t count_off)
+{
+    if (count_dev) {
+        const int64_t c = (int64_t)*count_dev;
+        if (c < count) count = c;
+    }
+    if (count_off >= 0 && blockIdx.x == 0 && threadIdx.x < pp.n)
+        *reinterpret_cast<unsigned int *>(pp.base[threadIdx.x] + count_off) = (unsigned int)count;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += stride) {
+        const T v = src[k];
+        for (int q = 0; q < pp.n; ++q) reinterpret_cast<T *>(pp.base[q] + off)[k] = v;
+    }
+    (void)rank;
+}
+
+// out[pos] = q * leaves_per_shard + idx for the (pos, idx) pairs every rank q has put into this rank's buffer
+__global__ void __launch_bounds__(256) peer_scatter_pairs_kernel(const char *__restrict__ local, size_t pairs_off,
+                                                                 size_t slab_bytes, size_t counts_off, int world,
+                                                                 int64_t leaves_per_shard, int64_t *__restrict__ out, int64_t m)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int q = 0; q < world; ++q) {
+        const int64_t cnt = (int64_t)*reinterpret_cast<const unsigned int *>(local + counts_off + 4 * (size_t)q);
+        const int2 *pairs = reinterpret_cast<const int2 *>(local + pairs_off + (size_t)q * slab_bytes);
+        for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < cnt; k += stride) {
+            const int2 pr = pairs[k];
+            if (pr.x >= 0 && pr.x < m) out[pr.x] = (int64_t)q * leaves_per_shard + pr.y;
+        }
+    }
+}
+
 // Top-tree routing of a replicated query batch (the first g levels of the reference descent,
 // pyx:96-113, on the replicated top tree) fused with the selection of this rank's queries:
 // the queries whose descent ends in top leaf `rank` are appended (any order: every result is
@@ -329,6 +366,58 @@ int st_peer_scatter(st_peer *p, const void *src_dev, const int32_t *pos_dev, int
     default: st::peer_scatter_kernel<uint64_t><<<grid, 256, 0, s>>>(p->ptrs, off, (const uint64_t *)src_dev, pos_dev, count, count_dev); break;
     }
     PCU(cudaGetLastError());
+    return ST_OK;
+}
+
+int st_peer_put(st_peer *p, const void *src_dev, int64_t count, const uint32_t *count_dev, int esize, int64_t dst_offset,
+                int64_t count_offset, void *stream)
+{
+    if (!p || count < 0 || dst_offset < 0 || (dst_offset % esize) || (esize != 4 && esize != 8) || (count > 0 && !src_dev) ||
+        (size_t)(dst_offset + count * esize) > p->payload_bytes ||
+        (count_offset >= 0 && ((count_offset & 3) || (size_t)count_offset + 4 > p->payload_bytes)))
+        return pfail(ST_ERR_ARG, "st_peer_put: bad argument");
+    dev_guard g(p->device);
+    ++st::g_kernel_launches;
+    const unsigned grid = st::grid_for(count > 0 ? count : 1, 256, 1184);
+    const size_t off = st::PEER_FLAG_BYTES + (size_t)dst_offset;
+    const int64_t coff = count_offset >= 0 ? (int64_t)st::PEER_FLAG_BYTES + count_offset : -1;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (esize == 4)
+        st::peer_put_kernel<uint32_t><<<grid, 256, 0, s>>>(p->ptrs, off, (const uint32_t *)src_dev, count, count_dev, p->rank, coff);
+    else
+        st::peer_put_kernel<uint64_t><<<grid, 256, 0, s>>>(p->ptrs, off, (const uint64_t *)src_dev, count, count_dev, p->rank, coff);
+    PCU(cudaGetLastError());
+    return ST_OK;
+}
+
+int st_peer_scatter_pairs(st_peer *p, int64_t pairs_offset, int64_t slab_bytes, int64_t counts_offset,
+                          int64_t leaves_per_shard, int64_t *out_dev, int64_t m, void *stream)
+{
+    if (!p || pairs_offset < 0 || (pairs_offset & 7) || slab_bytes < 0 || (slab_bytes & 7) || counts_offset < 0 ||
+        (counts_offset & 3) || !out_dev || m < 0 ||
+        (size_t)(pairs_offset + slab_bytes * p->world) > p->payload_bytes ||
+        (size_t)(counts_offset + 4 * p->world) > p->payload_bytes)
+        return pfail(ST_ERR_ARG, "st_peer_scatter_pairs: bad argument");
+    if (m == 0) return ST_OK;
+    dev_guard g(p->device);
+    ++st::g_kernel_launches;
+    st::peer_scatter_pairs_kernel<<<st::grid_for(m / p->world + 1, 256, 1184), 256, 0, (cudaStream_t)stream>>>(
+        p->local, st::PEER_FLAG_BYTES + (size_t)pairs_offset, (size_t)slab_bytes, st::PEER_FLAG_BYTES + (size_t)counts_offset,
+        p->world, leaves_per_shard, out_dev, m);
+    PCU(cudaGetLastError());
+    return ST_OK;
+}
+
+int st_search_pairs_device(const st_tree *t, const void *vals_dev, int64_t m_max, const uint32_t *m_dev,
+                           const int32_t *pos_dev, int32_t *pairs_out_dev, void *stream)
+{
+    if (!t || m_max < 0 || !m_dev || (m_max > 0 && (!vals_dev || !pos_dev || !pairs_out_dev)))
+        return pfail(ST_ERR_ARG, "st_search_pairs_device: bad argument");
+    dev_guard g(t->device);
+    st::search_push push;
+    push.pos = pos_dev;
+    push.pairs = pairs_out_dev;
+    PCU(st::launch_search(t, vals_dev, m_max, nullptr, (cudaStream_t)stream, m_dev, &push));
     return ST_OK;
 }
 

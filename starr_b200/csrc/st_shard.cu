@@ -227,6 +227,22 @@ __global__ void __launch_bounds__(256) shard_expand_values_kernel(const uint8_t 
     }
 }
 
+struct shard_starts { int64_t v[SH_MAX]; };
+
+// out[j] = cat[starts[shard[j]] + slot[j]]: the slabs of all shards back to back (peer exchange, no padding)
+template <typename T>
+__global__ void __launch_bounds__(256) shard_expand_cat_kernel(const uint8_t *__restrict__ shard8,
+                                                               const int32_t *__restrict__ slot, int64_t m,
+                                                               const T *__restrict__ cat, const shard_starts starts,
+                                                               T *__restrict__ out)
+{
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += step) {
+        const int32_t s = slot[j];
+        out[j] = s >= 0 ? cat[starts.v[shard8[j]] + s] : T(0);
+    }
+}
+
 __global__ void __launch_bounds__(256) shard_expand_indices_kernel(const uint8_t *__restrict__ shard8,
                                                                    const int32_t *__restrict__ slot, int64_t m,
                                                                    const int32_t *__restrict__ slabs, int64_t stride,
@@ -288,6 +304,24 @@ cudaError_t launch_shard_expand_values(const st_tree *t, const uint8_t *shard, c
     case 2: shard_expand_values_kernel<uint16_t><<<g, 256, 0, s>>>(shard, slot, m, (const uint16_t *)slabs, slab_stride, (uint16_t *)out); break;
     case 4: shard_expand_values_kernel<uint32_t><<<g, 256, 0, s>>>(shard, slot, m, (const uint32_t *)slabs, slab_stride, (uint32_t *)out); break;
     default: shard_expand_values_kernel<uint64_t><<<g, 256, 0, s>>>(shard, slot, m, (const uint64_t *)slabs, slab_stride, (uint64_t *)out); break;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_shard_expand_cat(const st_tree *t, const uint8_t *shard, const int32_t *slot, int64_t m, const void *cat,
+                                    const int64_t *starts_host, int shards, void *out, cudaStream_t s)
+{
+    if (m <= 0) return cudaSuccess;
+    if (shards < 1 || shards > SH_MAX) return cudaErrorInvalidValue;
+    shard_starts st{};
+    for (int q = 0; q < shards; ++q) st.v[q] = starts_host[q];
+    ++g_kernel_launches;
+    const unsigned g = grid_for(m, 256, (int64_t)t->sm_count * 16);
+    switch (t->esize) {
+    case 1: shard_expand_cat_kernel<uint8_t><<<g, 256, 0, s>>>(shard, slot, m, (const uint8_t *)cat, st, (uint8_t *)out); break;
+    case 2: shard_expand_cat_kernel<uint16_t><<<g, 256, 0, s>>>(shard, slot, m, (const uint16_t *)cat, st, (uint16_t *)out); break;
+    case 4: shard_expand_cat_kernel<uint32_t><<<g, 256, 0, s>>>(shard, slot, m, (const uint32_t *)cat, st, (uint32_t *)out); break;
+    default: shard_expand_cat_kernel<uint64_t><<<g, 256, 0, s>>>(shard, slot, m, (const uint64_t *)cat, st, (uint64_t *)out); break;
     }
     return cudaGetLastError();
 }

@@ -11,6 +11,7 @@
 #include <cstring>
 
 #include "st_common.cuh"
+#include "st_sidx.cuh"
 
 namespace st {
 
@@ -165,6 +166,66 @@ build_pass_kernel(T *__restrict__ H, uint32_t n, int root_level, int k, const un
     }
 }
 
+// ---- search index (st_sidx.cuh) ------------------------------------------------------------------------
+size_t sidx_bytes_for(int64_t n, int depth, int esize, int kind, int *nb_out)
+{
+    // Opt-in (ST_SEARCH_INDEX=1).  Measured at 2^27 float32 leaves, 2^20 updates + 2^20 samples per step
+    // (profiles/r2_experiments.md): the search drops from 150 to 110 us (14 -> 6 dependent loads per query,
+    // 9.5e9 samples/s), but every update of a left child below level 13 becomes two atomics and the update grows
+    // from 0.61 to 0.92 ms -- the L2 atomic units are what bounds the update.  Worth it only for sample-heavy loads.
+    static const bool on = getenv("ST_SEARCH_INDEX") && atoi(getenv("ST_SEARCH_INDEX")) != 0;
+    int nb = 0;
+    if (on && esize == 4 && kind == 0 && 2 * n >= 16384) nb = (depth - 2 - SIDX_L0) / 3;
+    if (nb < 0) nb = 0;
+    if (nb > SIDX_MAX_BLOCK_LEVELS) nb = SIDX_MAX_BLOCK_LEVELS;
+    if (nb_out) *nb_out = nb;
+    size_t blocks = 0;
+    for (int i = 0; i < nb; ++i) blocks += (size_t)1 << (SIDX_L0 + 3 * i);
+    return blocks * 32;
+}
+
+sidx_ref sidx_of(const st_tree *t)
+{
+    sidx_ref sx;
+    if (!t->sidx) return sx;
+    sx.base = t->sidx;
+    sx.nb = t->sidx_nb;
+    uint32_t off = 0;
+    for (int i = 0; i < sx.nb; ++i) {
+        sx.off[i] = off;
+        off += 8u << (SIDX_L0 + 3 * i);
+    }
+    return sx;
+}
+
+// one thread per record: block root r of level L0 + 3i -> [0, H[2r], H[4r], H[4r+2], H[8r], H[8r+2], H[8r+4], H[8r+6]]
+__global__ void __launch_bounds__(256) sidx_build_kernel(const uint32_t *__restrict__ H, sidx_ref sx, const unsigned int *status)
+{
+    if (*status) return;   // failed validation: nothing was built (pyx:58-59)
+    uint32_t total = 0;
+    for (int i = 0; i < sx.nb; ++i) total += 1u << (SIDX_L0 + 3 * i);
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < total; g += gridDim.x * blockDim.x) {
+        int i = 0;
+        uint32_t b = g;
+        while (b >= (1u << (SIDX_L0 + 3 * i))) { b -= 1u << (SIDX_L0 + 3 * i); ++i; }
+        const uint32_t r = (1u << (SIDX_L0 + 3 * i)) + b;
+        uint4 lo, hi;
+        lo.x = 0u;        lo.y = H[2 * r];     lo.z = H[4 * r];     lo.w = H[4 * r + 2];
+        hi.x = H[8 * r];  hi.y = H[8 * r + 2]; hi.z = H[8 * r + 4]; hi.w = H[8 * r + 6];
+        uint4 *dst = reinterpret_cast<uint4 *>(reinterpret_cast<uint32_t *>(sx.base) + sx.off[i] + b * 8u);
+        dst[0] = lo;
+        dst[1] = hi;
+    }
+}
+
+cudaError_t launch_sidx_build(st_tree *t, cudaStream_t s)
+{
+    if (!t->sidx) return cudaSuccess;
+    ++g_kernel_launches;
+    sidx_build_kernel<<<t->sm_count * 8, 256, 0, s>>>((const uint32_t *)t->heap, sidx_of(t), t->d_status);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_build(st_tree *t, cudaStream_t s)
 {
     const uint32_t n = (uint32_t)t->n;
@@ -185,7 +246,9 @@ cudaError_t launch_build(st_tree *t, cudaStream_t s)
             top = root_level;
         }
     });
-    return cudaGetLastError();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    return launch_sidx_build(t, s);
 }
 
 // =========================================================================================
@@ -269,7 +332,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS)
 search_kernel(const T *__restrict__ H, uint32_t n, int depth, const void *__restrict__ in,
               int64_t m, int64_t *__restrict__ out, T *__restrict__ prio, T *__restrict__ resid,
               uint32_t stage_nodes, const unsigned int *__restrict__ m_dev,
-              typename prob_type<T>::type *__restrict__ prob, const search_push push)
+              typename prob_type<T>::type *__restrict__ prob, const search_push push, const sidx_ref sx)
 {
     if (m_dev) {   // the host did not know the count when it launched (sharded sample: st_shard_plan_device)
         const int64_t md = (int64_t)*m_dev;
@@ -302,7 +365,55 @@ search_kernel(const T *__restrict__ H, uint32_t n, int depth, const void *__rest
                 h[q] = n;  // inactive: already "at a leaf"
             }
         }
-        for (int lev = 0; lev < depth; ++lev) {
+        int lev = 0;
+        if constexpr (STAGE && sizeof(T) == 4) {
+            if (sx.base) {
+                // (a) the staged levels: every left child is in shared memory (L0 = 13 steps)
+                for (; lev < SIDX_L0; ++lev) {
+#pragma unroll
+                    for (int q = 0; q < SEARCH_Q; ++q) {
+                        if (h[q] < n) {
+                            const uint32_t c = 2u * h[q];
+                            const T lv = top[c];
+                            if (p[q] >= lv) { p[q] = t_sub<T>(p[q], lv); h[q] = c + 1; } else { h[q] = c; }
+                        }
+                    }
+                }
+                // (b) three levels per 32-byte index record (st_sidx.cuh); all nodes here are internal
+                for (int i = 0; i < sx.nb; ++i, lev += 3) {
+                    uint4 lo[SEARCH_Q], hi[SEARCH_Q];
+                    const uint4 *rec = reinterpret_cast<const uint4 *>(reinterpret_cast<const uint32_t *>(sx.base) + sx.off[i]);
+#pragma unroll
+                    for (int q = 0; q < SEARCH_Q; ++q) {
+                        lo[q] = make_uint4(0u, 0u, 0u, 0u);
+                        hi[q] = lo[q];
+                        if (h[q] < n) {
+                            const uint32_t b = h[q] - (1u << lev);
+                            lo[q] = __ldcg(rec + 2 * b);
+                            hi[q] = __ldcg(rec + 2 * b + 1);
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < SEARCH_Q; ++q) {
+                        if (h[q] < n) {
+                            auto as_t = [](uint32_t w) { T v; memcpy(&v, &w, 4); return v; };
+                            T lv = as_t(lo[q].y);
+                            uint32_t path = 0;
+                            if (p[q] >= lv) { p[q] = t_sub<T>(p[q], lv); path = 1; }
+                            lv = as_t(path ? lo[q].w : lo[q].z);
+                            path <<= 1;
+                            if (p[q] >= lv) { p[q] = t_sub<T>(p[q], lv); path |= 1; }
+                            const uint32_t w3 = (path & 2u) ? ((path & 1u) ? hi[q].w : hi[q].z) : ((path & 1u) ? hi[q].y : hi[q].x);
+                            lv = as_t(w3);
+                            path <<= 1;
+                            if (p[q] >= lv) { p[q] = t_sub<T>(p[q], lv); path |= 1; }
+                            h[q] = (h[q] << 3) + path;
+                        }
+                    }
+                }
+            }
+        }
+        for (; lev < depth; ++lev) {
             T lv[SEARCH_Q];
 #pragma unroll
             for (int q = 0; q < SEARCH_Q; ++q) {
@@ -327,7 +438,10 @@ search_kernel(const T *__restrict__ H, uint32_t n, int depth, const void *__rest
         for (int q = 0; q < SEARCH_Q; ++q) {
             const int64_t i = base + threadIdx.x + (int64_t)q * SEARCH_THREADS;
             if (i < m) {
-                if (push.n) {
+                if (push.pairs) {
+                    // sharded sample, coalesced exchange: (batch position, local leaf) in this rank's own order
+                    reinterpret_cast<int2 *>(push.pairs)[i] = make_int2(push.pos[i], (int)(h[q] - n));
+                } else if (push.n) {
                     // sharded sample: the global leaf index goes straight into every rank's result buffer
                     const int64_t g = (int64_t)h[q] - (int64_t)n + push.index_offset;
                     const int32_t at = push.pos[i];
@@ -375,13 +489,13 @@ static cudaError_t launch_search_cfg(const st_tree *t, const void *in, int64_t m
         unsigned g = grid_for(m, (int)per_block, (int64_t)t->sm_count * 3);
         ++g_kernel_launches;
         kern<<<g, THREADS, smem, s>>>(H, n, t->depth, in, m, out, (T *)prio, (T *)resid, stage_nodes, m_dev,
-                                      (typename prob_type<T>::type *)prob, push);
+                                      (typename prob_type<T>::type *)prob, push, sidx_of(t));
     } else {
         unsigned g = grid_for(m, (int)per_block, (int64_t)t->sm_count * 4);
         ++g_kernel_launches;
         search_kernel<T, false, UNIFORM, THREADS, Q><<<g, THREADS, 0, s>>>(H, n, t->depth, in, m, out, (T *)prio,
                                                                           (T *)resid, 0, m_dev,
-                                                                          (typename prob_type<T>::type *)prob, push);
+                                                                          (typename prob_type<T>::type *)prob, push, sidx_ref{});
     }
     return cudaGetLastError();
 }

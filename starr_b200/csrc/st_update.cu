@@ -38,6 +38,7 @@
 
 #include "st_common.cuh"
 #include "st_update_defs.cuh"
+#include "st_sidx.cuh"
 #include "st_ordered_fold.cuh"
 #include "st_partition_hybrid.cuh"
 #include "st_update_small.cuh"
@@ -277,10 +278,10 @@ __global__ void __launch_bounds__(256) leaf_pass_grouped_kernel(T *H, uint32_t n
 // adds them in batch order (ordered_add: same-thread same-address atomics keep program order).  Runs in
 // leaf-sorted order, so consecutive threads touch neighbouring sectors of every level (DRAM pages are reused),
 // which the batch-ordered retirement could not do for these levels.
-template <typename T>
+template <typename T, bool SIDX>
 __global__ void __launch_bounds__(256) deep_red_kernel(T *__restrict__ H, uint32_t n, int depth, int gb,
                                                        const uint32_t *__restrict__ keys, const T *__restrict__ ds, int m,
-                                                       const unsigned int *__restrict__ status)
+                                                       const unsigned int *__restrict__ status, const sidx_ref sx)
 {
     if (status[SW_STATUS]) return;
     const uint64_t two_n = 2ull * n;
@@ -296,7 +297,13 @@ __global__ void __launch_bounds__(256) deep_red_kernel(T *__restrict__ H, uint32
         for (int e = i; e < i + len; ++e) {
             key = keys[e];
             const T d = ds[e];
-            for (int l = key_leaf_level(key, two_n, depth) - 1; l >= top; --l) ordered_add<T>(H + (key >> (depth - l)), d);
+            for (int l = key_leaf_level(key, two_n, depth) - 1; l >= top; --l) {
+                const uint32_t v = key >> (depth - l);
+                ordered_add<T>(H + v, d);
+                if constexpr (SIDX) {
+                    if (T *c = sidx_slot<T>(sx, v, l)) ordered_add<T>(c, d);   // the search index copy: same adds, same order
+                }
+            }
         }
     }
 }
@@ -339,7 +346,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) int_propagate_kernel(T *__restrict__ H, uint32_t n, int depth,
                                                             const uint32_t *__restrict__ keys,
                                                             const T *__restrict__ ds, int m,
-                                                            const unsigned int *status)
+                                                            const unsigned int *status, const sidx_ref sx)
 {
     if (status[SW_STATUS]) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;  // blockDim multiple of 32; whole warps stay
@@ -367,19 +374,23 @@ __global__ void __launch_bounds__(256) int_propagate_kernel(T *__restrict__ H, u
         }
         const uint32_t nnext = __shfl_down_sync(0xffffffffu, node, 1);
         const bool tail = (lane == 31) || (nnext != node);
-        if (node && tail && sum != T(0)) atomic_add_wrap<T>(H + node, sum);
+        if (node && tail && sum != T(0)) {
+            atomic_add_wrap<T>(H + node, sum);
+            if (T *c = sidx_slot<T>(sx, node, l)) atomic_add_wrap<T>(c, sum);   // search index copy (modular adds commute)
+        }
     }
 }
 
 // -----------------------------------------------------------------------------------------
 // 3b. float propagation: ordered segment folds (segments come from st_partition.cuh)
 // -----------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, bool SIDX>
 __device__ __forceinline__ void retire_warps(T *__restrict__ H, uint32_t n, int depth, const uint32_t *__restrict__ key0,
                                              const uint32_t *__restrict__ lev_key, const T *__restrict__ lev_d,
                                              int64_t lev_stride, const seg_entry *__restrict__ qret, unsigned int total,
-                                             unsigned int warp_id, unsigned int warps, int deep_level = 1 << 20,
-                                             int gb = 0, const unsigned int *__restrict__ bigmap = nullptr);
+                                             unsigned int warp_id, unsigned int warps, const sidx_ref &sx,
+                                             int deep_level = 1 << 20, int gb = 0,
+                                             const unsigned int *__restrict__ bigmap = nullptr);
 
 // Queued segments: exact parallel ordered folds (st_ordered_fold.cuh).  CTAs first drain the
 // queue of long segments (one CTA each), then their warps drain the queue of medium segments
@@ -390,7 +401,7 @@ __device__ void huge_apply_body(T *__restrict__ H, const T *__restrict__ lev_d, 
                                 const chunk_rec<typename fp_bits<T>::I> *__restrict__ recs, unsigned int *status,
                                 const void *__restrict__ mleaf, int mleaf_bytes, int64_t mnleaves, int mleaf_level,
                                 const chunk_rec<typename fp_bits<T>::I> *__restrict__ recs2, int *__restrict__ redo,
-                                int redo_stride, T *s_seq);
+                                int redo_stride, T *s_seq, const sidx_ref &sx);
 
 // second-pass stitch of the huge segments, done by the same launch as the long / medium folds
 template <typename T> struct huge_params {
@@ -411,7 +422,7 @@ __global__ void __launch_bounds__(FOLD_THREADS) fold_scan_kernel(T *__restrict__
                                                                  const seg_entry *__restrict__ queue_long,
                                                                  const seg_entry *__restrict__ queue_med,
                                                                  unsigned int *status, retire_params<T> ret,
-                                                                 huge_params<T> hp)
+                                                                 huge_params<T> hp, const sidx_ref sx)
 {
     if (status[SW_STATUS]) return;
     using I = typename fp_bits<T>::I;
@@ -421,12 +432,12 @@ __global__ void __launch_bounds__(FOLD_THREADS) fold_scan_kernel(T *__restrict__
     __shared__ T s_stage[FOLD_THREADS / 32][FOLDW_PAD];
     if (hp.qhuge)
         huge_apply_body<T, false, true>(H, lev_d, level_stride, hp.qhuge, hp.huge_off, hp.recs, status, nullptr, 0, 0, 0,
-                                        hp.recs2, hp.redo, hp.redo_stride, &s_stage[0][0]);
+                                        hp.recs2, hp.redo, hp.redo_stride, &s_stage[0][0], sx);
     if (ret.qret) {
         // small-batch path: retire the segments the single-CTA kernel queued (st_update_small.cuh)
-        retire_warps<T>(H, ret.n, ret.depth, ret.key0, ret.lev_key, lev_d, level_stride, ret.qret,
+        retire_warps<T, true>(H, ret.n, ret.depth, ret.key0, ret.lev_key, lev_d, level_stride, ret.qret,
                         status[SW_QCOUNT_RET], blockIdx.x * (FOLD_THREADS >> 5) + (threadIdx.x >> 5),
-                        gridDim.x * (FOLD_THREADS >> 5));
+                        gridDim.x * (FOLD_THREADS >> 5), sx);
     }
     const unsigned int n_long = status[SW_QCOUNT];
     for (;;) {
@@ -438,7 +449,7 @@ __global__ void __launch_bounds__(FOLD_THREADS) fold_scan_kernel(T *__restrict__
         const seg_entry s = queue_long[slot];
         const T *src = lev_d + (int64_t)s.level * level_stride + s.start;
         const T r = ordered_fold_cta<T>(H[s.node], src, s.len, s_wtot, &s_mviol, &ctl, &s_stage[0][0]);
-        if (threadIdx.x == 0) H[s.node] = r;
+        if (threadIdx.x == 0) sidx_store<T>(H, sx, s.node, s.level, r);
     }
     const unsigned int n_med = status[SW_QCOUNT_MED];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -450,7 +461,7 @@ __global__ void __launch_bounds__(FOLD_THREADS) fold_scan_kernel(T *__restrict__
         const seg_entry s = queue_med[slot];
         const T *src = lev_d + (int64_t)s.level * level_stride + s.start;
         const T r = ordered_fold_warp<T>(H[s.node], src, s.len, s_stage[warp]);
-        if (lane == 0) H[s.node] = r;
+        if (lane == 0) sidx_store<T>(H, sx, s.node, s.level, r);
     }
 }
 
@@ -461,14 +472,14 @@ __global__ void __launch_bounds__(FOLD_THREADS) fold_scan_kernel(T *__restrict__
 // lane adds the update to its level's ancestor.  All adds to one node therefore come from one lane
 // in batch order (ordered_add); the random node updates of a 2^20 batch spread over every SM at
 // full occupancy instead of stalling the cooperative kernel.
-template <typename T>
+template <typename T, bool SIDX>
 __device__ __forceinline__ void retire_warps(T *__restrict__ H, uint32_t n, int depth,
                                              const uint32_t *__restrict__ key0,
                                              const uint32_t *__restrict__ lev_key,
                                              const T *__restrict__ lev_d, int64_t lev_stride,
                                              const seg_entry *__restrict__ qret, unsigned int total,
-                                             unsigned int warp_id, unsigned int warps, int deep_level, int gb,
-                                             const unsigned int *__restrict__ bigmap)
+                                             unsigned int warp_id, unsigned int warps, const sidx_ref &sx, int deep_level,
+                                             int gb, const unsigned int *__restrict__ bigmap)
 {
     // levels >= deep_level belong to deep_red_kernel, except below the groups the leaf pass flagged in bigmap
     // (bigmap == nullptr: no group was flagged in this batch)
@@ -501,24 +512,30 @@ __device__ __forceinline__ void retire_warps(T *__restrict__ H, uint32_t n, int 
                         const uint32_t gi = (kx >> gb) - (1u << (depth - gb));
                         mine = (bigmap[gi >> 5] >> (gi & 31)) & 1u;
                     }
-                    if (mine) ordered_add<T>(H + (kx >> sh), dx);
+                    if (mine) {
+                        ordered_add<T>(H + (kx >> sh), dx);
+                        if constexpr (SIDX) {
+                            if (T *c = sidx_slot<T>(sx, kx >> sh, l2)) ordered_add<T>(c, dx);   // search index copy
+                        }
+                    }
                 }
             }
         }
     }
 }
 
-template <typename T>
+template <typename T, bool SIDX>
 __global__ void __launch_bounds__(256) retire_kernel(T *__restrict__ H, uint32_t n, int depth,
                                                      const uint32_t *__restrict__ key0,
                                                      const uint32_t *__restrict__ lev_key,
                                                      const T *__restrict__ lev_d, int64_t lev_stride,
                                                      const seg_entry *__restrict__ qret, const unsigned int *status,
-                                                     int deep_level, int gb, const unsigned int *__restrict__ bigmap)
+                                                     int deep_level, int gb, const unsigned int *__restrict__ bigmap,
+                                                     const sidx_ref sx)
 {
     if (status[SW_STATUS]) return;
-    retire_warps<T>(H, n, depth, key0, lev_key, lev_d, lev_stride, qret, status[SW_QCOUNT_RET],
-                    blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), gridDim.x * (blockDim.x >> 5), deep_level, gb,
+    retire_warps<T, SIDX>(H, n, depth, key0, lev_key, lev_d, lev_stride, qret, status[SW_QCOUNT_RET],
+                          blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), gridDim.x * (blockDim.x >> 5), sx, deep_level, gb,
                     status[SW_ANYBIG] ? bigmap : nullptr);
 }
 
@@ -589,7 +606,7 @@ __device__ void huge_apply_body(T *__restrict__ H, const T *__restrict__ lev_d, 
                                 const chunk_rec<typename fp_bits<T>::I> *__restrict__ recs, unsigned int *status,
                                 const void *__restrict__ mleaf, int mleaf_bytes, int64_t mnleaves, int mleaf_level,
                                 const chunk_rec<typename fp_bits<T>::I> *__restrict__ recs2, int *__restrict__ redo,
-                                int redo_stride, T *s_seq /* FOLD_CHUNK elements of shared memory */)
+                                int redo_stride, T *s_seq /* FOLD_CHUNK elements of shared memory */, const sidx_ref &sx)
 {
     // First pass (REDO false): stitch with the summaries made for the binade eA the node starts in.
     //   redo == nullptr (the masked top fold): chunks that fail the check are folded exactly in place.
@@ -730,7 +747,7 @@ __device__ void huge_apply_body(T *__restrict__ H, const T *__restrict__ lev_d, 
                     if (redo) {
                         // hand over to the second pass, which has the time to fold exactly
                         if (tid == 0) {
-                            H[s.node] = ready ? value_of<T>(e_cur, m) : cur;
+                            sidx_store<T>(H, sx, s.node, s.level, ready ? value_of<T>(e_cur, m) : cur);
                             redo[slot] = c;
                             redo[redo_stride + slot] = eA;
                             redo[2 * redo_stride + slot] = other;
@@ -754,7 +771,7 @@ __device__ void huge_apply_body(T *__restrict__ H, const T *__restrict__ lev_d, 
                 ++exact_chunks;
             }
         }
-        if (!deferred && tid == 0) H[s.node] = ready ? value_of<T>(e_cur, m) : cur;
+        if (!deferred && tid == 0) sidx_store<T>(H, sx, s.node, s.level, ready ? value_of<T>(e_cur, m) : cur);
         if (tid == 0) {
             if (exact_chunks == 0 && !deferred) {
                 if (!REDO) atomicAdd(status + SW_STAT_FAST, 1u);
@@ -777,11 +794,11 @@ __global__ void __launch_bounds__(FOLD_THREADS) fold_huge_apply_kernel(T *__rest
                                                                        const void *__restrict__ mleaf, int mleaf_bytes, int64_t mnleaves,
                                                                        int mleaf_level,
                                                                        const chunk_rec<typename fp_bits<T>::I> *__restrict__ recs2,
-                                                                       int *__restrict__ redo, int redo_stride)
+                                                                       int *__restrict__ redo, int redo_stride, const sidx_ref sx)
 {
     __shared__ T s_seq[FOLD_CHUNK];
     huge_apply_body<T, MASKED, REDO>(H, lev_d, level_stride, qhuge, huge_off, recs, status, mleaf, mleaf_bytes, mnleaves,
-                                     mleaf_level, recs2, redo, redo_stride, s_seq);
+                                     mleaf_level, recs2, redo, redo_stride, s_seq, sx);
 }
 
 // Masked variant of phase A for the tiny top tree: records laid out [chunk][node-1] so that a rank's
@@ -832,6 +849,37 @@ static int deep_group_bits(int m, int64_t n, int depth)
     return gb;
 }
 
+// ST_TIMELINE=1 (debugging aid): one stderr line per large float batch with the completion times (us after the
+// start of the batch) of every stage on the caller's stream and on the side stream; synchronises after every batch.
+struct update_timeline {
+    bool on = false;
+    cudaEvent_t m[10] = {}, sd[3] = {};
+    update_timeline()
+    {
+        on = getenv("ST_TIMELINE") != nullptr;
+        if (on) {
+            for (auto &e : m) cudaEventCreate(&e);
+            for (auto &e : sd) cudaEventCreate(&e);
+        }
+    }
+    void main(int k, cudaStream_t s) { if (on) cudaEventRecord(m[k], s); }
+    void side(int k, cudaStream_t s) { if (on) cudaEventRecord(sd[k], s); }
+    void report()
+    {
+        if (!on) return;
+        cudaEventSynchronize(m[9]);
+        static const char *mn[10] = {"start", "keys", "sort", "leaf", "partition", "maps", "stitch+maps2", "fold_scan", "", "join"};
+        float v;
+        fprintf(stderr, "[timeline us] main:");
+        for (int k = 1; k < 10; ++k)
+            if (mn[k][0] && cudaEventElapsedTime(&v, m[0], m[k]) == cudaSuccess) fprintf(stderr, " %s=%.0f", mn[k], v * 1e3f);
+        fprintf(stderr, " | side:");
+        if (cudaEventElapsedTime(&v, m[0], sd[0]) == cudaSuccess) fprintf(stderr, " deep=%.0f", v * 1e3f);
+        if (cudaEventElapsedTime(&v, m[0], sd[1]) == cudaSuccess) fprintf(stderr, " retire=%.0f", v * 1e3f);
+        fprintf(stderr, "\n");
+    }
+};
+
 template <typename T>
 static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *idx, int m, const T *vals,
                                 int64_t nv, int64_t j0, int64_t B, T *delta_out, const T *deltas_in,
@@ -848,6 +896,7 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
     const unsigned g = (unsigned)((m + 255) / 256);
 
     auto mark = [&](int k) { if (t->profile) cudaEventRecord(t->prof_ev[k], s); };
+    static thread_local update_timeline tl;
     if constexpr (is_float_t<T>::value) {
         if (small && phase == 2) return cudaSuccess;
         if (small) {
@@ -877,7 +926,7 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
             }
             retire_params<T> rp{w.queue_ret, w.kj, w.lev_key, depth, n};
             fold_scan_kernel<T><<<t->sm_count, FOLD_THREADS, 0, s>>>(H, (const T *)w.lev_d, B, w.queue, w.queue_med,
-                                                                    status, rp, huge_params<T>{nullptr, nullptr, nullptr, nullptr, nullptr, 0});
+                                                                    status, rp, huge_params<T>{nullptr, nullptr, nullptr, nullptr, nullptr, 0}, sidx_of(t));
             return cudaGetLastError();
         }
     }
@@ -887,8 +936,10 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
     if (phase == 2) d_batch = (const T *)w.dj;
     if (phase != 2) {
     mark(0);
+    tl.main(0, s);
     ++g_kernel_launches;
     make_keys_kernel<<<g, 256, 0, s>>>(idx, m, n, depth, w.keys_a, w.kj, w.j_a, status);
+    tl.main(1, s);
     }
     if (!deltas_in && phase != 2) {
         // floats only need the duplicates of a leaf adjacent and batch-ordered: the low gb key bits stay unsorted,
@@ -899,6 +950,7 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
         e = cub::DeviceRadixSort::SortPairs(w.cub_tmp, cb, w.keys_a, w.keys_b, w.j_a, w.j_b, m, gb, depth + 1, s);
         if (e != cudaSuccess) return e;
         mark(1);
+        tl.main(2, s);
         ++g_kernel_launches;
         if (gb) {
             e = cudaMemsetAsync(w.bigmap, 0, (((size_t)1 << (depth - gb)) + 7) / 8 + 4, s);
@@ -920,15 +972,16 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
     if constexpr (!is_float_t<T>::value) {
         ++g_kernel_launches;
         if (deltas_in)   // unsorted keys: adjacent equal ancestors still merge, the rest use separate atomics
-            int_propagate_kernel<T><<<g, 256, 0, s>>>(H, n, depth, w.kj, deltas_in, m, status);
+            int_propagate_kernel<T><<<g, 256, 0, s>>>(H, n, depth, w.kj, deltas_in, m, status, sidx_of(t));
         else
-            int_propagate_kernel<T><<<g, 256, 0, s>>>(H, n, depth, w.keys_b, (const T *)w.ds, m, status);
+            int_propagate_kernel<T><<<g, 256, 0, s>>>(H, n, depth, w.keys_b, (const T *)w.ds, m, status, sidx_of(t));
         return cudaGetLastError();
     } else {
         // Level 0 order = batch order: (kj, dj).  Level l+1 order = stable sort of level l by
         // the top l+1 key bits.  lev_d[l] keeps every level's ordered d for the long folds.
         T *lev = (T *)w.lev_d;
         mark(2);
+        tl.main(3, s);
         // Side stream.  Three groups of nodes are written by three independent parts of the pipeline, all of which
         // only read the batch arrays: (1) the deep levels below the leaf groups -- deep_red_kernel, in leaf-sorted
         // order, needs nothing but the leaf pass; (2) the nodes of retired segments -- retire_kernel, needs the
@@ -944,15 +997,24 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
         const int gbd = deltas_in ? 0 : t->pending_gb;            // leaf-group bits (0: no deep pass)
         const int deep_level = gbd ? depth - gbd : (1 << 20);     // retirement stops here, except under flagged groups
         cudaStream_t rs = overlap ? t->side : s;
-        if (overlap) {
+        const sidx_ref sx = sidx_of(t);
+        // ST_DEEP_EARLY=1 starts deep_red_kernel beside the PARTITION instead of behind it.  Measured: the partition
+        // then takes 212 us instead of 118 (its shared-memory kernels stall behind the atomics' L2 misses), so the
+        // pairing is: partition alone, then deep pass + retirement (atomics) beside the folds (integer math).
+        static const bool deep_early = getenv("ST_DEEP_EARLY") && atoi(getenv("ST_DEEP_EARLY")) != 0;
+        auto launch_deep = [&](cudaStream_t ds, unsigned grid) {
+            if (!gbd) return;
+            ++g_kernel_launches;
+            if (sx.base) deep_red_kernel<T, true><<<grid, 256, 0, ds>>>(H, n, depth, gbd, w.keys_b, (const T *)w.ds, m, status, sx);
+            else deep_red_kernel<T, false><<<grid, 256, 0, ds>>>(H, n, depth, gbd, w.keys_b, (const T *)w.ds, m, status, sx);
+            tl.side(0, ds);
+        };
+        static const int deep_ctas = getenv("ST_DEEP_CTAS") ? atoi(getenv("ST_DEEP_CTAS")) : 4;   // per SM (tuning)
+        if (overlap && deep_early) {
             e = cudaEventRecord(t->ev_fork, s);
             if (e == cudaSuccess) e = cudaStreamWaitEvent(t->side, t->ev_fork, 0);
             if (e != cudaSuccess) return e;
-            if (gbd) {
-                ++g_kernel_launches;
-                static const int deep_ctas = getenv("ST_DEEP_CTAS") ? atoi(getenv("ST_DEEP_CTAS")) : 2;   // per SM (tuning)
-                deep_red_kernel<T><<<t->sm_count * deep_ctas, 256, 0, rs>>>(H, n, depth, gbd, w.keys_b, (const T *)w.ds, m, status);
-            }
+            launch_deep(rs, t->sm_count * 2);
         }
         e = cudaMemcpyAsync(lev, d_batch, (size_t)m * sizeof(T), cudaMemcpyDeviceToDevice, s);
         if (e != cudaSuccess) return e;
@@ -1017,19 +1079,26 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
         if (e != cudaSuccess) return e;
         using REC = chunk_rec<typename fp_bits<T>::I>;
         mark(3);
+        tl.main(4, s);
         ++g_kernel_launches;
         // (retirement: see the note on the side stream above the partition)
         if (overlap) {   // the side stream (already busy with deep_red_kernel) goes on once the partition is complete
             e = cudaEventRecord(t->ev_fork, s);
             if (e == cudaSuccess) e = cudaStreamWaitEvent(t->side, t->ev_fork, 0);
             if (e != cudaSuccess) return e;
-        } else if (gbd) {
-            ++g_kernel_launches;
-            deep_red_kernel<T><<<g, 256, 0, s>>>(H, n, depth, gbd, w.keys_b, (const T *)w.ds, m, status);
         }
+        if (!(overlap && deep_early)) launch_deep(rs, overlap ? t->sm_count * deep_ctas : g);
         static const int retire_ctas = getenv("ST_RETIRE_CTAS") ? atoi(getenv("ST_RETIRE_CTAS")) : 4;   // per SM beside the folds (tuning)
-        retire_kernel<T><<<t->sm_count * (overlap ? retire_ctas : 8), 256, 0, rs>>>(H, n, depth, w.kj, w.lev_key, lev, B, w.queue_ret,
-                                                                          status, deep_level, gbd, w.bigmap);
+        {
+            const unsigned rg = t->sm_count * (overlap ? retire_ctas : 8);
+            if (sx.base)
+                retire_kernel<T, true><<<rg, 256, 0, rs>>>(H, n, depth, w.kj, w.lev_key, lev, B, w.queue_ret, status, deep_level, gbd,
+                                                           w.bigmap, sx);
+            else
+                retire_kernel<T, false><<<rg, 256, 0, rs>>>(H, n, depth, w.kj, w.lev_key, lev, B, w.queue_ret, status, deep_level, gbd,
+                                                            w.bigmap, sx);
+        }
+        tl.side(1, rs);
         if (overlap) {
             e = cudaEventRecord(t->ev_join, t->side);
             if (e != cudaSuccess) return e;
@@ -1043,20 +1112,26 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
         fold_huge_maps_kernel<T, false><<<t->sm_count * 8, FOLD_THREADS, 0, s>>>(
             H, lev, B, w.queue_huge, w.huge_off, (REC *)w.huge_recs, status, nullptr, 0, 0, 0, nullptr, 0);
         mark(5);
+        tl.main(5, s);
         fold_huge_apply_kernel<T, false, false><<<t->sm_count, FOLD_THREADS, 0, s>>>(
             H, lev, B, w.queue_huge, w.huge_off, (const REC *)w.huge_recs, status, nullptr, 0, 0, 0, nullptr, w.huge_redo,
-            redo_stride);
+            redo_stride, sidx_of(t));
         fold_huge_maps_kernel<T, false><<<t->sm_count * 8, FOLD_THREADS, 0, s>>>(
             H, lev, B, w.queue_huge, w.huge_off, (REC *)w.huge_recs2, status, nullptr, 0, 0, 0, w.huge_redo, redo_stride);
         mark(6);
+        tl.main(6, s);
         fold_scan_kernel<T><<<t->sm_count * 8, FOLD_THREADS, 0, s>>>(
             H, lev, B, w.queue, w.queue_med, status, retire_params<T>{nullptr, nullptr, nullptr, 0, 0},
             huge_params<T>{w.queue_huge, w.huge_off, (const REC *)w.huge_recs, (const REC *)w.huge_recs2, w.huge_redo,
-                           redo_stride});
+                           redo_stride},
+            sidx_of(t));
+        tl.main(7, s);
         if (overlap) {
             e = cudaStreamWaitEvent(s, t->ev_join, 0);
             if (e != cudaSuccess) return e;
         }
+        tl.main(9, s);
+        tl.report();
         mark(7);
         if (t->profile) {
             // profiling mode is synchronous by design (bench.py's roofline leg only); its phases run one after another
@@ -1134,11 +1209,11 @@ cudaError_t launch_fold_by_leaf_apply(st_tree *t, const void *leaf, int leaf_byt
     if (t->dtype == ST_F32)
         fold_huge_apply_kernel<float, true, false><<<(unsigned)(t->n - 1), FOLD_THREADS, 0, s>>>(
             (float *)t->heap, (const float *)deltas, 0, q, nullptr, (const chunk_rec<int32_t> *)recs, t->d_status, leaf,
-            leaf_bytes, t->n, t->depth, nullptr, nullptr, 0);
+            leaf_bytes, t->n, t->depth, nullptr, nullptr, 0, sidx_ref{});
     else
         fold_huge_apply_kernel<double, true, false><<<(unsigned)(t->n - 1), FOLD_THREADS, 0, s>>>(
             (double *)t->heap, (const double *)deltas, 0, q, nullptr, (const chunk_rec<int64_t> *)recs, t->d_status, leaf,
-            leaf_bytes, t->n, t->depth, nullptr, nullptr, 0);
+            leaf_bytes, t->n, t->depth, nullptr, nullptr, 0, sidx_ref{});
     return cudaGetLastError();
 }
 

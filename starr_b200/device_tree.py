@@ -211,6 +211,24 @@ class DeviceSumTree:
             self._h.search_push_device(vals.data_ptr(), vals.numel(), count.data_ptr(), pos.data_ptr(), index_offset, peer,
                                        payload_offset, span_elems, _stream())
 
+    def search_pairs(self, prefix_sums: torch.Tensor, count: torch.Tensor, pos: torch.Tensor, pairs: torch.Tensor) -> None:
+        """``search`` over the first ``count[0]`` prefixes; result k goes to ``pairs[k] = (pos[k], local leaf)`` (int32 [m, 2])."""
+        vals = self._chk(prefix_sums, self.dtype, "prefix_sums")
+        if pairs.dtype != torch.int32 or not pairs.is_contiguous() or pairs.numel() < 2 * vals.numel() or pos.dtype != torch.int32:
+            raise TypeError("pairs must be a contiguous int32 tensor with two entries per prefix, pos an int32 tensor")
+        with torch.cuda.device(self.device):
+            self._h.search_pairs_device(vals.data_ptr(), vals.numel(), count.data_ptr(), pos.data_ptr(), pairs.data_ptr(), _stream())
+
+    def shard_expand_cat(self, shard: torch.Tensor, slot: torch.Tensor, cat: torch.Tensor, starts: list,
+                         out: torch.Tensor | None = None) -> torch.Tensor:
+        """``out[j] = cat[starts[shard[j]] + slot[j]]`` (the shards' slabs stored back to back)."""
+        cat = self._chk(cat, self.dtype, "cat")
+        out = self._chk_out(out, shard.numel(), self.dtype)
+        with torch.cuda.device(self.device):
+            self._h.shard_expand_cat_device(shard.data_ptr(), slot.data_ptr(), shard.numel(), cat.data_ptr(), starts,
+                                            out.data_ptr(), _stream())
+        return out[:shard.numel()]
+
     def apply_deltas_(self, idx: torch.Tensor, deltas: torch.Tensor) -> "DeviceSumTree":
         """For j in batch order add ``deltas[j]`` to every proper ancestor of leaf ``idx[j]``
         (ordered folds for floats); the leaves themselves are not touched."""

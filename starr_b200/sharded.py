@@ -31,13 +31,15 @@ Per batch (inputs are replicated on every rank, as a PER learner broadcasts them
 Peer exchange (``peer=True``, the default on CUDA when every rank can reach every other rank's memory):
 the three all-gathers and the passes that put slabs back into batch order are replaced by direct stores
 into an exchange buffer of EVERY rank (``csrc/st_peer.cu``, CUDA IPC over NVLink / NVSwitch):
-  update  the leaf pass of the local update emits the d_j, a scatter kernel stores each one at its batch
-          position j of ``d_all`` on every rank WHILE the local ancestors are still being updated
-          (side stream); shard roots and the rank's 1/G of the top-fold records follow the same way;
-          a release flag per rank + a spinning wait kernel replace the collective's implicit barrier.
+  update  the leaf pass of the local update emits the d_j; one coalesced copy per peer (``st_peer_put``) stores the
+          rank's slab behind the slabs of the lower ranks in every rank's buffer WHILE the local ancestors are
+          still being updated (side stream); shard roots and the rank's 1/G of the top-fold records follow the
+          same way; a release flag per rank + a spinning wait kernel replace the collective's implicit barrier.
   sample  routing on the top tree and the selection of the rank's queries are one kernel
-          (``st_route_compact_device``: no plan, no host round trip); the local descent stores the GLOBAL
-          index of each query at its batch position on every rank (``st_search_push_device``).
+          (``st_route_compact_device``: no plan, no host round trip); the local descent writes (batch position,
+          local leaf) pairs, which go to every rank as one coalesced copy; a scatter puts them in batch order.
+  (Storing every result straight at its batch position on every peer -- ``st_peer_scatter``,
+  ``st_search_push_device`` -- was measured first: a 4- or 8-byte remote store costs a whole NVLink packet.)
 """
 from __future__ import annotations
 
@@ -127,7 +129,10 @@ class ShardedSumTree:
         nodes = self.world - 1
         rb = self.top.top_fold_record_bytes() if hasattr(self.top, "top_fold_record_bytes") else 0
         per = ((mu + 1023) // 1024 + self.world - 1) // self.world
-        sizes = {"d": al(mu * es), "roots": al(self.world * es), "recs": al(per * self.world * nodes * rb), "out": al(ms * 8)}
+        # d: the shards' difference slabs back to back (exactly mu elements); pairs: one slab of (position, local leaf)
+        # int32 pairs per rank, each able to hold the whole batch (a skewed tree may route every query to one shard)
+        sizes = {"d": al(mu * es), "roots": al(self.world * es), "recs": al(per * self.world * nodes * rb),
+                 "pairs": al(ms * 8) * self.world, "cnt": 256}
         off, lay = 0, {}
         for name, size in sizes.items():
             lay[name] = (off, off + size)                                        # parity 0 / parity 1
@@ -158,6 +163,9 @@ class ShardedSumTree:
         self._ustep = self._sstep = 0
         self._rank_pos = torch.tensor([self.rank], dtype=torch.int32, device=self.device)
         self._own_count = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._pairs = torch.empty(2 * ms, dtype=torch.int32, device=self.device)
+        self._d_all = torch.empty(mu, dtype=self.dtype, device=self.device)
+        self._pair_slab = (ms * 8 + 255) // 256 * 256
         self._side = self._side or torch.cuda.Stream(device=self.device)
         return True
 
@@ -336,13 +344,16 @@ class ShardedSumTree:
         es = self.local.heap.element_size()
         main = torch.cuda.current_stream()
         d_own = buf["d_own"]
+        starts = [0] * self.world                  # slab of shard q inside every rank's "d" region (all ranks know all counts)
+        for q in range(1, self.world):
+            starts[q] = starts[q - 1] + plan.counts[q - 1]
         if c:
-            # leaf pass first: the differences exist, and travel (side stream) while the ancestors are updated
+            # leaf pass first: the differences exist, and travel (side stream, one coalesced copy per peer) while the
+            # ancestors are updated
             self.local.update_begin_(plan.own_idx[:c], plan.own_vals[:c], out=d_own)
             self._side.wait_stream(main)
             with torch.cuda.stream(self._side):
-                peer.scatter(d_own.data_ptr(), buf["pos"].data_ptr(), c, es, self._lay["d"][par], ni,
-                             stream=self._side.cuda_stream)
+                peer.put(d_own.data_ptr(), c, es, self._lay["d"][par] + starts[self.rank] * es, stream=self._side.cuda_stream)
             self.local.update_finish_()
             main.wait_stream(self._side)
         self._mark("update: local update (+ deltas to every rank)")
@@ -351,7 +362,9 @@ class ShardedSumTree:
         peer.signal(self.CH_DELTAS, step, main.cuda_stream)
         peer.wait(self.CH_DELTAS, step, main.cuda_stream)
         self._mark("update: wait for all ranks' deltas + roots")
-        d_all = self._region("d", par, self.dtype, ni)
+        d_all = self.local.shard_expand_cat(plan.shard, plan.slot, self._region("d", par, self.dtype, ni), starts,
+                                            out=self._d_all)
+        self._mark("update: deltas to batch order")
         self._fold_top(plan.shard, d_all, peer_step=(step, par))
         self.top.leaves.copy_(self._region("roots", par, self.dtype, self.world))
         ev = torch.cuda.Event()
@@ -449,14 +462,16 @@ class ShardedSumTree:
         own_resid, own_pos = bufs["out"][3], bufs["pos"]
         self.top.route_compact(u, self.rank, own_resid, own_pos, self._own_count)
         self._mark("sample: route + select")
-        self.local.search_push(own_resid, self._own_count, own_pos, self.offset, self._peer, self._lay["out"][par], m)
-        self._mark("sample: local search (indices to every rank)")
+        self.local.search_pairs(own_resid, self._own_count, own_pos, self._pairs)
+        self._mark("sample: local search")
         s = torch.cuda.current_stream().cuda_stream
+        self._peer.put(self._pairs.data_ptr(), m, 8, self._lay["pairs"][par] + self.rank * self._pair_slab,
+                       count_dev_ptr=self._own_count.data_ptr(), count_offset=self._lay["cnt"][par] + 4 * self.rank, stream=s)
         self._peer.signal(self.CH_SAMPLE, step, s)
         self._peer.wait(self.CH_SAMPLE, step, s)
-        self._mark("sample: wait for all ranks")
-        out.copy_(self._region("out", par, torch.int64, m))
-        self._mark("sample: copy out")
+        self._mark("sample: pairs to every rank + wait")
+        self._peer.scatter_pairs(self._lay["pairs"][par], self._pair_slab, self._lay["cnt"][par], self.n_local, out.data_ptr(), m, s)
+        self._mark("sample: indices to batch order")
         return out
 
     # ---- inspection -------------------------------------------------------------------------------

@@ -91,7 +91,10 @@ class _TreeState:
         try:
             # the device holds fl(old + fl(val - old)), which is not always `val` for floats, so the
             # host mirror is patched with what the device actually stored (same staging round)
-            written = self.handle.update_gather_host(flat_idx, values)
+            # ... and the new root comes back with it, so that sum() / the zero check of sample() need no call
+            written, root = self.handle.update_gather_root_host(flat_idx, values)
+            if flat_idx.size:
+                self._root = root
         finally:
             self.tree_stale = True
         if flat_idx.size:
