@@ -165,39 +165,59 @@ __global__ void __launch_bounds__(256) route_compact_kernel(const T *__restrict_
                                                             unsigned int *__restrict__ own_count)
 {
     __shared__ T top[2 * PEER_MAX];
+    __shared__ unsigned int s_wcount[8], s_base;
     for (int i = threadIdx.x; i < 2 * nleaves; i += blockDim.x) top[i] = H[i];
     __syncthreads();
     const T root = top[1];
     const int lane = threadIdx.x & 31;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const int64_t rounds = (m + stride - 1) / stride;
+    constexpr int K = 4;                               // queries per thread and round
+    const int64_t rounds = (m + stride * K - 1) / (stride * K);
+    const int warp = threadIdx.x >> 5;
     for (int64_t r = 0; r < rounds; ++r) {
-        const int64_t i = r * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-        bool mine = false;
-        T p = T(0);
-        if (i < m) {
-            // (root * u).astype(dtype), sumtree_array.py:420
-            if constexpr (sizeof(T) == 4 && is_float_t<T>::value) p = __double2float_rn(__dmul_rn((double)root, u[i]));
-            else if constexpr (is_float_t<T>::value) p = __dmul_rn(root, u[i]);
-            else p = (T)__dmul_rn((double)root, u[i]);
-            uint32_t h = 1;
-            for (int lev = 0; lev < depth; ++lev) {
-                const T lv = top[2 * h];
-                if (p >= lv) { p = t_sub<T>(p, lv); h = 2 * h + 1; } else { h = 2 * h; }
+        bool mine[K];
+        T p[K];
+        unsigned int bal[K], wc = 0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int64_t i = (r * K + k) * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+            mine[k] = false;
+            p[k] = T(0);
+            if (i < m) {
+                // (root * u).astype(dtype), sumtree_array.py:420
+                if constexpr (sizeof(T) == 4 && is_float_t<T>::value) p[k] = __double2float_rn(__dmul_rn((double)root, u[i]));
+                else if constexpr (is_float_t<T>::value) p[k] = __dmul_rn(root, u[i]);
+                else p[k] = (T)__dmul_rn((double)root, u[i]);
+                uint32_t h = 1;
+                for (int lev = 0; lev < depth; ++lev) {
+                    const T lv = top[2 * h];
+                    if (p[k] >= lv) { p[k] = t_sub<T>(p[k], lv); h = 2 * h + 1; } else { h = 2 * h; }
+                }
+                mine[k] = ((int)h - nleaves == rank);
             }
-            mine = ((int)h - nleaves == rank);
+            bal[k] = __ballot_sync(0xffffffffu, mine[k]);
+            wc += __popc(bal[k]);
         }
-        const unsigned int bal = __ballot_sync(0xffffffffu, mine);
-        if (bal) {
-            unsigned int base = 0;
-            if (lane == (__ffs(bal) - 1)) base = atomicAdd(own_count, (unsigned int)__popc(bal));
-            base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
-            if (mine) {
-                const unsigned int at = base + __popc(bal & ((1u << lane) - 1u));
-                own_resid[at] = p;
-                own_pos[at] = (int32_t)i;
+        // append: ONE atomic per CTA and round (a counter bumped by every warp serialised 2^16 atomics per 2^21 queries)
+        if (lane == 0) s_wcount[warp] = wc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned int tot = 0;
+            for (int w = 0; w < 8; ++w) { const unsigned int c = s_wcount[w]; s_wcount[w] = tot; tot += c; }
+            s_base = tot ? atomicAdd(own_count, tot) : 0u;
+        }
+        __syncthreads();
+        unsigned int at = s_base + s_wcount[warp];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            if (mine[k]) {
+                const unsigned int a = at + __popc(bal[k] & ((1u << lane) - 1u));
+                own_resid[a] = p[k];
+                own_pos[a] = (int32_t)((r * K + k) * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x);
             }
+            at += __popc(bal[k]);
         }
+        __syncthreads();   // s_wcount / s_base are reused by the next round
     }
 }
 
