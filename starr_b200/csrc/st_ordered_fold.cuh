@@ -68,11 +68,17 @@ template <typename I> __device__ __forceinline__ pmap<I> pmap_then(const pmap<I>
 
 // One update d seen from a node whose value has exponent field eT (ulp u = 2^(eT - bias - MB)):
 //   map  : the parity map of rne(m + d/u)
-//   flo  : floor(d/u)      (m + flo inside [2^MB, 2^(MB+1)) <=> the exact sum stays in the binade)
+//   flq  : floor(4 d/u).  The identity holds while the exact sum s = m + d/u stays inside
+//              [2^MB - 1/4, 2^(MB+1))   <=>   4 (m - 2^MB) + flq >= -1   and   m + (flq >> 2) < 2^(MB+1):
+//          inside the binade the rounding grid is u; in the quarter below it (grid u/2) both grids round
+//          to 2^MB itself -- s = 2^MB - 1/4 is a tie between 2^MB - 1/2 (odd) and 2^MB (even).  Without
+//          that quarter a node sitting EXACTLY on a power of two would fail on every tiny negative update
+//          (uniform priorities on a power-of-two tree put the upper nodes there, and the boundary is sticky:
+//          from 2^MB small positive updates are absorbed, small negative ones too).
 //   big  : |d/u| too large to represent / d is inf or nan  -> always handled by a real FADD
 template <typename T> struct upd_map {
     pmap<typename fp_bits<T>::I> map;
-    typename fp_bits<T>::I flo;
+    typename fp_bits<T>::I flq;
     bool big;
 };
 
@@ -89,14 +95,14 @@ template <typename T> __device__ __forceinline__ upd_map<T> decompose(T d, int e
     upd_map<T> r;
     r.map.a0 = 0;
     r.map.a1 = 0;
-    r.flo = 0;
+    r.flq = 0;
     r.big = (ef == F::EMASK);
     const U md = ef ? (mant | (U(1) << MB)) : mant;
     if (md == 0 || r.big) return r;  // +-0 changes nothing
     const int ed = ef ? (int)ef : 1;
     const int shift = ed - eT;
-    U q, g0, g1;
-    bool frac;
+    U q, g0, g1, q4;
+    bool frac4;
     if (shift >= 0) {
         if (shift >= 2) {
             r.big = true;
@@ -104,18 +110,18 @@ template <typename T> __device__ __forceinline__ upd_map<T> decompose(T d, int e
         }
         q = md << shift;
         g0 = g1 = q;
-        frac = false;
+        q4 = q << 2;
+        frac4 = false;
     } else {
         const int sh = -shift;
-        if (sh > MB + 2) {  // |x| < 1/2, not a tie
-            q = 0;
+        if (sh > MB + 2) {  // |x| < 1/4, not a tie
             g0 = g1 = 0;
-            frac = true;
+            q4 = 0;
+            frac4 = true;
         } else {
             q = md >> sh;
             const U rem = md & ((U(1) << sh) - 1);
             const U half = U(1) << (sh - 1);
-            frac = rem != 0;
             if (rem > half) {
                 g0 = g1 = q + 1;
             } else if (rem == half) {  // exact tie: the even neighbour of m + q + 1/2
@@ -124,16 +130,23 @@ template <typename T> __device__ __forceinline__ upd_map<T> decompose(T d, int e
             } else {
                 g0 = g1 = q;
             }
+            if (sh >= 2) {
+                q4 = md >> (sh - 2);
+                frac4 = (md & ((U(1) << (sh - 2)) - 1)) != 0;
+            } else {            // sh == 1: 4x = 2 md, an integer
+                q4 = md << 1;
+                frac4 = false;
+            }
         }
     }
     if (!neg) {
         r.map.a0 = (I)g0;
         r.map.a1 = (I)g1;
-        r.flo = (I)q;
+        r.flq = (I)q4;
     } else {
         r.map.a0 = -(I)g0;
         r.map.a1 = -(I)g1;
-        r.flo = -(I)q - (frac ? 1 : 0);
+        r.flq = -(I)q4 - (frac4 ? 1 : 0);
     }
     return r;
 }
@@ -212,8 +225,8 @@ __device__ __forceinline__ int walk_updates(const upd_map<T> (&um)[E], int first
     for (int k = 0; k < E; ++k) {
         const int i = first_idx + k;
         if (i >= pos && i < nc && viol == NO_VIOL) {
-            const I v = m + um[k].flo;
-            if (um[k].big || m < LO || m >= HI || v < LO || v >= HI) viol = i;
+            const I f = um[k].flq;
+            if (um[k].big || m < LO || m >= HI || 4 * (m - LO) + (f < 0 ? f : 0) < -1 || m + (f >> 2) >= HI) viol = i;
             else m += (m & 1) ? um[k].map.a1 : um[k].map.a0;
         }
     }
@@ -272,7 +285,8 @@ template <typename T> struct masked_src {
 
 template <typename I> struct chunk_rec {
     I a0, a1;        // parity map of the whole chunk
-    I min0, max0;    // extremes of (m_k - m_in) and (m_k + floor(x_k) - m_in), start parity even
+    I min0, max0;    // start parity even: min0 = min over k of 4 (m_k - m_in) + min(floor(4 x_k), 0)  (QUARTER units, see
+                     // upd_map::flq), max0 = max over k of (m_k - m_in) + max(floor(x_k), 0)
     I min1, max1;    // ... start parity odd
     int ok;          // 0: contains an update the identity never covers, or magnitudes too large
     int pad;
@@ -330,9 +344,9 @@ __device__ void chunk_summary_cta(SRC src, int nc, int eT, chunk_rec<typename fp
     for (int k = 0; k < FOLD_E; ++k) {
         const int i = tid * FOLD_E + k;
         if (i < nc) {
-            const I f = um[k].flo;
-            const I lo0 = f < 0 ? off0 + f : off0, hi0 = f > 0 ? off0 + f : off0;
-            const I lo1 = f < 0 ? off1 + f : off1, hi1 = f > 0 ? off1 + f : off1;
+            const I f = um[k].flq;
+            const I lo0 = 4 * off0 + (f < 0 ? f : 0), hi0 = f > 0 ? off0 + (f >> 2) : off0;
+            const I lo1 = 4 * off1 + (f < 0 ? f : 0), hi1 = f > 0 ? off1 + (f >> 2) : off1;
             mn0 = lo0 < mn0 ? lo0 : mn0;  mx0 = hi0 > mx0 ? hi0 : mx0;
             mn1 = lo1 < mn1 ? lo1 : mn1;  mx1 = hi1 > mx1 ? hi1 : mx1;
             off0 += (off0 & 1) ? um[k].map.a1 : um[k].map.a0;          // start parity even: m = m_in + off0

@@ -694,7 +694,7 @@ __device__ void huge_apply_body(T *__restrict__ H, const T *__restrict__ lev_d, 
                 const chunk_rec<I> r = recs[rec_base + c * rec_stride];
                 const bool odd = (mm & 1) != 0;
                 const I mn = odd ? r.min1 : r.min0, mx = odd ? r.max1 : r.max0;
-                if (!(r.ok && mm + mn >= LO && mm + mx < HI)) {
+                if (!(r.ok && 4 * (mm - LO) + mn >= -1 && mm + mx < HI)) {
                     bad = c;
                     m_bad = mm;
                     break;
@@ -734,12 +734,12 @@ __device__ void huge_apply_body(T *__restrict__ H, const T *__restrict__ lev_d, 
                         const chunk_rec<I> &r = s_rec[REDO ? which : 0][k];
                         const bool odd = (m & 1) != 0;
                         const I mn = odd ? r.min1 : r.min0, mx = odd ? r.max1 : r.max0;
-                        if (r.ok && m + mn >= LO && m + mx < HI) {
+                        if (r.ok && 4 * (m - LO) + mn >= -1 && m + mx < HI) {
                             m += odd ? r.a1 : r.a0;
                             continue;
                         }
                         hovering = r.ok != 0;
-                        if (hovering) other = (m + mn < LO) ? e_cur - 1 : e_cur + 1;
+                        if (hovering) other = (4 * (m - LO) + mn < -1) ? e_cur - 1 : e_cur + 1;
                     }
                 }
                 const int c = cb + k;

@@ -330,6 +330,38 @@ def test_ordered_fold_adversarial(oracle_mod, dt, kind):
         h.close()
 
 
+@pytest.mark.parametrize("dt", [np.float32, np.float64], ids=["f32", "f64"])
+def test_node_sitting_on_a_power_of_two(oracle_mod, dt):
+    """Upper nodes EXACTLY on a power of two whose updates are all a fraction of an ulp (uniform priorities on a
+    power-of-two tree: bench.py's fixed-2^30 leg had top node 3 == 2^28).  Tiny negative updates put the exact sum just
+    below the binade, where the finer grid still rounds to 2^k: the chunk summaries must cover that (no chunk folded
+    one add at a time), and the result stays bit-identical."""
+    from starr_b200 import _lib
+    C = oracle_mod.c
+    rng = np.random.default_rng(5)
+    n, m = 1 << 12, 200_000
+    big = 2.0 ** (30 if dt == np.float32 else 60)
+    leaves = np.full(n, big / n, dt)                      # every node is a power of two; ulp(root) = 2^7
+    tree = np.zeros(n, dt)
+    C.build_sumtree_from_array(leaves, tree)
+    h = _lib.TreeHandle(n, dt)
+    h.build_from_host(leaves)
+    before = h.update_stats()
+    for rep in range(2):
+        idx = rng.integers(0, n, m).astype(np.intp)
+        # differences of a few ulps of the LEAF = 2^-12 ulps of the root: absorbed by every node that sees a huge segment
+        vals = (leaves[idx] + rng.integers(-2, 3, m).astype(dt) * dt(np.spacing(dt(big / n)))).astype(dt)
+        C.update_sumtree(idx, vals, leaves, tree)
+        h.update_host(idx, vals)
+        gl, gt = _state(h)
+        assert_bits_equal(gl, leaves, f"rep={rep} leaves")
+        assert_bits_equal(gt, tree, f"rep={rep} tree")
+    after = h.update_stats()
+    assert after["huge_segments_maps_only"] > before["huge_segments_maps_only"]
+    assert after["chunks_folded_exactly"] == before["chunks_folded_exactly"], after
+    h.close()
+
+
 @pytest.mark.parametrize("dt", [np.float32, np.int32], ids=["f32", "i32"])
 def test_batches_larger_than_one_chunk(oracle_mod, dt):
     """Batches above 2^21 updates are applied chunk by chunk (2^20 + 1 is now ONE ragged chunk); `vals` keeps cycling over the position

@@ -36,7 +36,7 @@ def value_of(et, m, dt):
 
 
 def decompose(d, et, dt):
-    """(a0, a1, flo, big) of one update seen from a node with exponent field et."""
+    """(a0, a1, flq, big) of one update seen from a node with exponent field et; flq = floor(4 d / ulp)."""
     _, mb, emask, nbits = FMT[dt]
     b = bits(d, dt)
     neg = (b >> (nbits - 1)) != 0
@@ -53,26 +53,37 @@ def decompose(d, et, dt):
             return 0, 0, 0, True
         q = md << shift
         g0 = g1 = q
-        frac = False
+        q4, frac4 = q << 2, False
     else:
         sh = -shift
         if sh > mb + 2:
-            q = g0 = g1 = 0
-            frac = True
+            g0 = g1 = 0
+            q4, frac4 = 0, True
         else:
             q = md >> sh
             rem = md & ((1 << sh) - 1)
             half = 1 << (sh - 1)
-            frac = rem != 0
             if rem > half:
                 g0 = g1 = q + 1
             elif rem == half:                      # exact tie: round-half-even depends on the parity of m
                 g0, g1 = q + (q & 1), q + ((q + 1) & 1)
             else:
                 g0 = g1 = q
+            if sh >= 2:
+                q4, frac4 = md >> (sh - 2), (md & ((1 << (sh - 2)) - 1)) != 0
+            else:
+                q4, frac4 = md << 1, False
     if not neg:
-        return g0, g1, q, False
-    return -g0, -g1, -q - (1 if frac else 0), False
+        return g0, g1, q4, False
+    return -g0, -g1, -q4 - (1 if frac4 else 0), False
+
+
+def covered(m, flq, dt):
+    """walk_updates' test: the identity holds while the exact sum stays in [2^MB - 1/4, 2^(MB+1)) ulps -- the binade
+    itself plus the quarter below it, where the finer grid of the lower binade rounds to 2^MB as well."""
+    mb = FMT[dt][1]
+    lo, hi = 1 << mb, 1 << (mb + 1)
+    return lo <= m < hi and 4 * (m - lo) + min(flq, 0) >= -1 and m + (flq >> 2) < hi
 
 
 def then(f, g):
@@ -98,9 +109,9 @@ def fold_with_maps(t, ds, dt):
         pre = (0, 0)
         viol = None
         for k in range(pos, len(ds)):
-            a0, a1, flo, big = decompose(ds[k], et, dt)
+            a0, a1, flq, big = decompose(ds[k], et, dt)
             m = m0 + (pre[1] if m0 & 1 else pre[0])            # exact m in front of update k
-            if big or m < lo or m >= hi or m + flo < lo or m + flo >= hi:      # walk_updates' test
+            if big or not covered(m, flq, dt):                 # walk_updates' test
                 viol = (k, m)
                 break
             pre = then(pre, (a0, a1))
@@ -132,8 +143,13 @@ def test_single_update_map_equals_ieee_add(dt):
         ok, et, m = scan_ready(t, dt)
         assert ok
         ulp = float(value_of(et, m + 1, dt)) - float(t) if m + 1 < (1 << (mb + 1)) else float(t) - float(value_of(et, m - 1, dt))
-        kind = rng.integers(0, 4)
-        if kind == 0:
+        kind = rng.integers(0, 5)
+        if kind == 4:                                  # bottom of the binade, updates of a fraction of an ulp
+            t = value_of(et, (1 << mb) + int(rng.integers(0, 3)), dt)
+            ok, et, m = scan_ready(t, dt)
+            ulp = float(value_of(et, m + 1, dt)) - float(t)
+            d = dt(-ulp * rng.choice([0.125, 0.25, 0.2500001, 0.375, 0.5, 0.75, 1.0, 1.25, 2.25, 1e-6]) * rng.choice([1, 1, 1, -1]))
+        elif kind == 0:
             d = dt(rng.choice([-1, 1]) * ulp * rng.choice([0.5, 1.5, 2.5, 0.25, 0.75, 1.0, 3.0]))   # ties and near-ties
         elif kind == 1:
             d = dt(rng.choice([-1, 1]) * ulp * np.exp(rng.uniform(-30, 3)))
@@ -141,11 +157,10 @@ def test_single_update_map_equals_ieee_add(dt):
             d = dt(rng.choice([-1, 1]) * float(t) * rng.uniform(0, 0.4))
         else:
             d = dt(0.0)
-        a0, a1, flo, big = decompose(d, et, dt)
+        a0, a1, flq, big = decompose(d, et, dt)
         if big:
             continue
-        lo, hi = 1 << mb, 1 << (mb + 1)
-        if not (lo <= m + flo and m + flo + 1 <= hi):
+        if not covered(m, flq, dt):
             continue                                   # leaves the binade: the kernel uses a real add there
         got = value_of(et, m + (a1 if m & 1 else a0), dt)
         want = dt(t + d)
@@ -155,7 +170,7 @@ def test_single_update_map_equals_ieee_add(dt):
 
 
 @pytest.mark.parametrize("dt", [np.float32, np.float64], ids=["f32", "f64"])
-@pytest.mark.parametrize("kind", ["small", "ties", "hopping", "from_zero", "mixed"])
+@pytest.mark.parametrize("kind", ["small", "ties", "hopping", "on_power_of_two", "from_zero", "mixed"])
 def test_composed_maps_equal_sequential_fold(dt, kind):
     """Prefix composition + restart reproduces the sequential IEEE fold bit for bit, including runs that
     hop across binade boundaries, grow from zero, or consist of exact ties."""
@@ -171,6 +186,9 @@ def test_composed_maps_equal_sequential_fold(dt, kind):
         elif kind == "hopping":                       # sits on a power of two and walks across it
             t = 2.0 ** rng.integers(5, 15)
             ds = rng.normal(0, float(np.spacing(dt(t))) * 3, n)
+        elif kind == "on_power_of_two":               # every update is absorbed: the node never leaves 2^k
+            t = 2.0 ** rng.integers(5, 15)
+            ds = rng.uniform(-0.249, 0.49, n) * float(np.spacing(dt(t)))
         elif kind == "from_zero":
             t, ds = 0.0, np.exp(rng.uniform(-30, 5, n))
         else:
@@ -181,7 +199,7 @@ def test_composed_maps_equal_sequential_fold(dt, kind):
         got, real_adds = fold_with_maps(t, ds, dt)
         want = sequential(t, ds, dt)
         assert bits(got, dt) == bits(want, dt), (kind, rep, t)
-        if kind == "small":
+        if kind in ("small", "on_power_of_two"):
             assert real_adds == 0                     # the whole run is one composition
 
 
