@@ -275,6 +275,53 @@ ST_API int st_search_push_device(const st_tree *t, const void *vals_dev, int64_t
                           const int32_t *pos_dev, int64_t index_offset, st_peer *p, int64_t payload_offset,
                           int64_t span_elems, void *stream);
 
+/* ---- slices layout: the batch is DISTRIBUTED over the ranks (no reference counterpart) ----------
+ * Rank r holds elements [r m, (r+1) m) of the global batch (data-parallel learners: every rank updates the
+ * priorities of, and samples, its own 1/G of the batch), so nobody touches O(M_global) data.  One exchange:
+ *   st_shard_partition_device   owner (uint8) + stable slot of every slice element, the slice partitioned by owner
+ *                               (shard-local ids / payload, one contiguous run per destination) and a row of
+ *                               world counts + 1 word of validation flags -- all on the device, no host round trip
+ *   st_slices_rows              the row goes into the count matrix M[world][world + 1] of every rank, then the
+ *                               release flag (channel, value); st_peer_wait completes the matrix
+ *   st_slices_matrix_fetch/wait asynchronous host copy of the matrix (the local update needs its element count)
+ *   st_slices_send              up to two arrays of the partitioned slice go to their owners' receive areas, each
+ *                               owner receiving its elements in GLOBAL batch order (rank-major), contiguous;
+ *                               *total_out_dev = elements this rank receives
+ *   st_slices_return            the owner's results, in receive order, back to the source's return area at the
+ *                               position the element had in the source's partitioned slice
+ *   st_slices_unpermute         out[j] = ret[start[shard[j]] + slot[j]]  (leaves_per_shard > 0: ret holds int32 local
+ *                               leaves and out[j] = shard * leaves_per_shard + leaf as int64)
+ * Offsets are byte offsets into the payload; matrix_offset must be 4-byte, the others 8-byte aligned. */
+ST_API int st_shard_partition_device(st_tree *t, const int64_t *ids_dev, int64_t m, int shift, int shards,
+                              const void *payload_dev, int check_negative, uint8_t *shard_out_dev,
+                              int32_t *slot_out_dev, int64_t *part_ids_out_dev, void *part_payload_out_dev,
+                              uint32_t *row_out_dev, void *stream);
+ST_API int st_slices_rows(st_peer *p, const uint32_t *row_dev, int64_t matrix_offset, int channel, unsigned int value,
+                   void *stream);
+ST_API int st_slices_matrix_fetch(st_peer *p, int64_t matrix_offset, void *stream);
+ST_API int st_slices_matrix_wait(st_peer *p, uint32_t *matrix_out_host); /* world * (world + 1) words */
+ST_API int st_slices_send(st_peer *p, int64_t matrix_offset, const void *src0_dev, int esize0, int64_t dst_offset0,
+                   const void *src1_dev, int esize1, int64_t dst_offset1, int64_t m_max, uint32_t *total_out_dev,
+                   void *stream);
+ST_API int st_slices_return(st_peer *p, int64_t matrix_offset, const void *src_dev, int esize, int64_t dst_offset,
+                     int64_t total_max, void *stream);
+ST_API int st_slices_unpermute(st_peer *p, int64_t matrix_offset, const uint8_t *shard_dev, const int32_t *slot_dev,
+                        int64_t m, int64_t ret_offset, int esize, int64_t leaves_per_shard, void *out_dev,
+                        int64_t shard_copy_offset /* >= 0: shard ids are copied there too */, void *stream);
+/* Top fold over a distributed batch.  maps_slice: chunk summaries of THIS rank's slice (m_slice elements, nchunks =
+ * span / 1024 chunks, padding chunks are identities) into records [record_first, record_first + nchunks).
+ * st_slices_table(parity, d_offset, leaf_offset): where every rank keeps its slice's differences and shard ids (uint8)
+ * inside its exchange buffer; apply_slices stitches the records of all ranks and reads those arrays through peer
+ * memory only for chunks that must be folded one add at a time. */
+ST_API int st_top_fold_maps_slice_device(st_tree *t, const uint8_t *leaf_dev, const void *deltas_dev, int64_t m_slice,
+                                  int64_t record_first, int64_t nchunks, void *recs_dev, void *stream);
+ST_API int st_slices_table(st_peer *p, int parity, int64_t d_offset, int64_t leaf_offset);
+ST_API int st_top_fold_apply_slices_device(st_tree *t, st_peer *p, int parity, int64_t span, int64_t m_slice,
+                                    const void *recs_dev, void *stream);
+/* st_search_counted_device with 32-bit local leaves as the result (what travels back to the querying rank) */
+ST_API int st_search_leaf32_device(const st_tree *t, const void *vals_dev, int64_t m_max, const uint32_t *m_dev,
+                            int32_t *out_dev, void *stream);
+
 /* ---- prefix-sum search: replaces get_prefix_sum_idx, _sumtree_array.pyx:66-122 --- */
 ST_API int st_search_device(const st_tree *t, const void *vals_dev, int64_t m, int64_t *out_dev,
                      void *stream);

@@ -143,6 +143,19 @@ _SIGNATURES = {
     "st_route_compact_device": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "st_search_push_device": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64,
                                       c_void_p]),
+    "st_shard_partition_device": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                          c_void_p, c_void_p, c_void_p]),
+    "st_slices_rows": (c_int, [c_void_p, c_void_p, c_int64, c_int, ctypes.c_uint, c_void_p]),
+    "st_slices_matrix_fetch": (c_int, [c_void_p, c_int64, c_void_p]),
+    "st_slices_matrix_wait": (c_int, [c_void_p, c_void_p]),
+    "st_slices_send": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int64, c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p]),
+    "st_slices_return": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int64, c_int64, c_void_p]),
+    "st_slices_unpermute": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int64, c_void_p, c_int64,
+                                    c_void_p]),
+    "st_top_fold_maps_slice_device": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
+    "st_slices_table": (c_int, [c_void_p, c_int, c_int64, c_int64]),
+    "st_top_fold_apply_slices_device": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p]),
+    "st_search_leaf32_device": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "st_sample_weights_device": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "st_per_step_device": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p,
                                    c_void_p, c_void_p]),
@@ -454,6 +467,36 @@ class TreeHandle:
         check(lib().st_shard_expand_cat_device(self.ptr, c_void_p(shard_ptr), c_void_p(slot_ptr), int(m), c_void_p(cat_ptr), arr,
                                                len(starts), c_void_p(out_ptr), c_void_p(stream)))
 
+    # ---- slices layout (batch distributed over the ranks) -------------------------------------------------------
+    def shard_partition_device(self, ids_ptr: int, m: int, shift: int, shards: int, payload_ptr: int, check_negative: bool,
+                               shard_out_ptr: int, slot_out_ptr: int, part_ids_out_ptr: int, part_payload_out_ptr: int,
+                               row_out_ptr: int, stream: int = 0) -> None:
+        check(lib().st_shard_partition_device(self.ptr, c_void_p(ids_ptr), int(m), int(shift), int(shards),
+                                              c_void_p(payload_ptr) if payload_ptr else None, int(bool(check_negative)),
+                                              c_void_p(shard_out_ptr), c_void_p(slot_out_ptr),
+                                              c_void_p(part_ids_out_ptr) if part_ids_out_ptr else None,
+                                              c_void_p(part_payload_out_ptr) if part_payload_out_ptr else None,
+                                              c_void_p(row_out_ptr), c_void_p(stream)))
+
+    @staticmethod
+    def _pcheck(status: int) -> None:
+        if status != ST_OK:
+            raise RuntimeError(lib().st_peer_last_error().decode("utf-8", "replace"))
+
+    def top_fold_maps_slice_device(self, leaf_ptr: int, deltas_ptr: int, m_slice: int, record_first: int, nchunks: int,
+                                   recs_ptr: int, stream: int = 0) -> None:
+        self._pcheck(lib().st_top_fold_maps_slice_device(self.ptr, c_void_p(leaf_ptr), c_void_p(deltas_ptr), int(m_slice),
+                                                         int(record_first), int(nchunks), c_void_p(recs_ptr), c_void_p(stream)))
+
+    def top_fold_apply_slices_device(self, peer: "PeerArea", parity: int, span: int, m_slice: int, recs_ptr: int,
+                                     stream: int = 0) -> None:
+        self._pcheck(lib().st_top_fold_apply_slices_device(self.ptr, peer.ptr, int(parity), int(span), int(m_slice),
+                                                           c_void_p(recs_ptr), c_void_p(stream)))
+
+    def search_leaf32_device(self, vals_ptr: int, m_max: int, m_dev_ptr: int, out_ptr: int, stream: int = 0) -> None:
+        self._pcheck(lib().st_search_leaf32_device(self.ptr, c_void_p(vals_ptr), int(m_max), c_void_p(m_dev_ptr),
+                                                   c_void_p(out_ptr), c_void_p(stream)))
+
     def shard_plan_wait(self, result_slot: int, shards: int) -> list[int]:
         counts = (c_int64 * int(shards))()
         check(lib().st_shard_plan_wait(self.ptr, int(result_slot), int(shards), counts))
@@ -624,6 +667,40 @@ class PeerArea:
                       stream: int = 0) -> None:
         self._check(lib().st_peer_scatter_pairs(self.ptr, int(pairs_offset), int(slab_bytes), int(counts_offset),
                                                 int(leaves_per_shard), c_void_p(out_ptr), int(m), c_void_p(stream)))
+
+    # ---- slices layout (batch distributed over the ranks) -------------------------------------------------------
+    def slices_rows(self, row_ptr: int, matrix_offset: int, channel: int, value: int, stream: int = 0) -> None:
+        self._check(lib().st_slices_rows(self.ptr, c_void_p(row_ptr), int(matrix_offset), int(channel), int(value) & 0xffffffff,
+                                         c_void_p(stream)))
+
+    def slices_matrix_fetch(self, matrix_offset: int, stream: int = 0) -> None:
+        self._check(lib().st_slices_matrix_fetch(self.ptr, int(matrix_offset), c_void_p(stream)))
+
+    def slices_matrix_wait(self) -> list:
+        """The count matrix as ``world`` rows of ``world`` counts + 1 word of validation flags."""
+        w = self.world
+        out = (ctypes.c_uint32 * (w * (w + 1)))()
+        self._check(lib().st_slices_matrix_wait(self.ptr, out))
+        return [list(out[r * (w + 1):(r + 1) * (w + 1)]) for r in range(w)]
+
+    def slices_send(self, matrix_offset: int, src0: int, esize0: int, dst0: int, m_max: int, total_out_ptr: int = 0,
+                    src1: int = 0, esize1: int = 0, dst1: int = 0, stream: int = 0) -> None:
+        self._check(lib().st_slices_send(self.ptr, int(matrix_offset), c_void_p(src0), int(esize0), int(dst0),
+                                         c_void_p(src1) if src1 else None, int(esize1), int(dst1), int(m_max),
+                                         c_void_p(total_out_ptr) if total_out_ptr else None, c_void_p(stream)))
+
+    def slices_return(self, matrix_offset: int, src: int, esize: int, dst: int, total_max: int, stream: int = 0) -> None:
+        self._check(lib().st_slices_return(self.ptr, int(matrix_offset), c_void_p(src), int(esize), int(dst), int(total_max),
+                                           c_void_p(stream)))
+
+    def slices_unpermute(self, matrix_offset: int, shard_ptr: int, slot_ptr: int, m: int, ret_offset: int, esize: int,
+                         out_ptr: int, leaves_per_shard: int = 0, shard_copy_offset: int = -1, stream: int = 0) -> None:
+        self._check(lib().st_slices_unpermute(self.ptr, int(matrix_offset), c_void_p(shard_ptr), c_void_p(slot_ptr), int(m),
+                                              int(ret_offset), int(esize), int(leaves_per_shard), c_void_p(out_ptr),
+                                              int(shard_copy_offset), c_void_p(stream)))
+
+    def slices_table(self, parity: int, d_offset: int, leaf_offset: int) -> None:
+        self._check(lib().st_slices_table(self.ptr, int(parity), int(d_offset), int(leaf_offset)))
 
     def signal(self, channel: int, value: int, stream: int = 0) -> None:
         self._check(lib().st_peer_signal(self.ptr, int(channel), int(value) & 0xffffffff, c_void_p(stream)))

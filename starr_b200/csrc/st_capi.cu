@@ -531,6 +531,33 @@ int st_shard_plan_pos_device(st_tree *t, const int64_t *ids_dev, int64_t m, int 
     return st_shard_plan_wait(t, result_slot, shards, counts_out_host);
 }
 
+int st_shard_partition_device(st_tree *t, const int64_t *ids_dev, int64_t m, int shift, int shards, const void *payload_dev,
+                              int check_negative, uint8_t *shard_out_dev, int32_t *slot_out_dev, int64_t *part_ids_out_dev,
+                              void *part_payload_out_dev, uint32_t *row_out_dev, void *stream)
+{
+    if (!t || m <= 0 || m > 0x7fffffffLL || shards < 1 || shards > 64 || shift < 0 || shift > 62 || !ids_dev || !shard_out_dev ||
+        !slot_out_dev || !row_out_dev || ((part_payload_out_dev || check_negative) && !payload_dev))
+        return fail(ST_ERR_ARG, "st_shard_partition_device: bad argument");
+    if (((uintptr_t)shard_out_dev & 7) || ((uintptr_t)slot_out_dev & 15))
+        return fail(ST_ERR_ARG, "st_shard_partition_device: shard_out must be 8-byte and slot_out 16-byte aligned");
+    tree_lock lk(t);
+    device_guard g(t->device);
+    if (t->plan_pending) {   // the scratch area belongs to one plan at a time
+        CU(cudaEventSynchronize(t->plan_ev));
+        t->plan_pending = 0;
+    }
+    scratch_carver c(t);
+    const size_t bytes = st::shard_plan_scratch_bytes(m, shards);
+    c.add(bytes);
+    CU(c.commit());
+    void *scratch = c.take(bytes);
+    CU(st::launch_shard_partition(t, ids_dev, m, shift, shards, payload_dev, check_negative, shard_out_dev, slot_out_dev,
+                                  part_ids_out_dev, part_payload_out_dev, scratch, row_out_dev, (cudaStream_t)stream));
+    CU(cudaEventRecord(t->plan_ev, (cudaStream_t)stream));
+    t->plan_pending = 1;
+    return ST_OK;
+}
+
 int st_shard_plan_wait(st_tree *t, int result_slot, int shards, int64_t *counts_out_host)
 {
     if (!t || !counts_out_host || shards < 1 || shards > 64 || result_slot < 0 || result_slot >= kPlanSlots)

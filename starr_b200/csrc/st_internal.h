@@ -94,6 +94,7 @@ struct search_push {
     const int32_t *pos = nullptr;
     int64_t index_offset = 0;
     int32_t *pairs = nullptr;      // != nullptr: result i goes to pairs[2i] = pos[i], pairs[2i+1] = local leaf (no push)
+    int32_t *leaf32 = nullptr;     // != nullptr: result i goes to leaf32[i] as a 32-bit local leaf (slices layout)
 };
 
 // process-wide count of kernels of THIS library that were launched (bench.py's gpu_launches)
@@ -156,8 +157,11 @@ size_t fold_rec_bytes(const st_tree *t);
 // leaf ids are int64 (leaf_bytes 8) or uint8 (leaf_bytes 1)
 cudaError_t launch_fold_by_leaf_maps(st_tree *t, const void *leaf, int leaf_bytes, const void *deltas, int64_t m,
                                      int chunk_lo, int chunk_hi, void *recs, cudaStream_t s);
+// slice_d / slice_leaf (nullable, device arrays of per-rank pointers): the batch is distributed over the ranks, element i
+// lives on rank i / slice_span at position i % slice_span (positions >= slice_m are padding); leaf / deltas unused then
 cudaError_t launch_fold_by_leaf_apply(st_tree *t, const void *leaf, int leaf_bytes, const void *deltas, int64_t m,
-                                      const void *recs, cudaStream_t s);
+                                      const void *recs, cudaStream_t s, const void *const *slice_d = nullptr,
+                                      const void *const *slice_leaf = nullptr, int64_t slice_span = 0, int64_t slice_m = 0);
 
 // subtree-sharded layout helpers (st_shard.cu)
 size_t shard_plan_scratch_bytes(int64_t m, int shards);
@@ -166,6 +170,11 @@ cudaError_t launch_shard_plan(st_tree *t, const int64_t *ids, int64_t m, int shi
                               const void *payload, int64_t npayload, int check_negative, uint8_t *shard_out,
                               int32_t *slot_out, int64_t *own_ids_out, void *own_payload_out, void *scratch,
                               unsigned int *counts_out, cudaStream_t s, int32_t *own_pos_out = nullptr);
+// slices layout: stable G-way partition of a slice by owner (shard-local ids + payload in destination order);
+// row_out: [shards] counts, then one word of STF_* flags (device; nothing is read back)
+cudaError_t launch_shard_partition(st_tree *t, const int64_t *ids, int64_t m, int shift, int shards, const void *payload,
+                                   int check_negative, uint8_t *shard_out, int32_t *slot_out, int64_t *part_ids_out,
+                                   void *part_payload_out, void *scratch, unsigned int *row_out, cudaStream_t s);
 cudaError_t launch_shard_expand_values(const st_tree *t, const uint8_t *shard, const int32_t *slot, int64_t m,
                                        const void *slabs, int64_t slab_stride, void *out, cudaStream_t s);
 cudaError_t launch_shard_expand_cat(const st_tree *t, const uint8_t *shard, const int32_t *slot, int64_t m, const void *cat,

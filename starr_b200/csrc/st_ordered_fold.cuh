@@ -262,6 +262,16 @@ __device__ __forceinline__ T seq_until_ready(T cur, int &p, int nc, LOAD load)
 // element i counts for `node` iff node is an ancestor of leaf[i]; everything else reads as 0,
 // which is the identity of the fold (T + 0 == T).  Used for the replicated top tree of the
 // subtree-sharded layout, where all ranks' differences arrive as ONE batch-ordered vector.
+// Sliced variant (slices layout of the sharded tree): the batch is distributed over the ranks, element i of the
+// GLOBAL batch lives on rank i / span at local position i % span (positions >= m of a slice are padding and read as 0);
+// d[r] / leaf[r] point into rank r's exchange buffer (peer memory), leaf ids are uint8.  Only chunks that must be
+// folded one add at a time are ever read through it.
+struct slice_ref {
+    const void *const *d = nullptr;
+    const void *const *leaf = nullptr;
+    int64_t span = 0, m = 0;
+};
+
 template <typename T> struct masked_src {
     const T *d;
     const void *leaf;   // leaf (shard) id of every element: int64 (leaf_bytes 8) or uint8 (leaf_bytes 1)
@@ -269,16 +279,28 @@ template <typename T> struct masked_src {
     int64_t nleaves;
     uint32_t node;
     int rshift;   // leaf level - level(node)
+    slice_ref sl{};
+    int64_t off = 0;   // sliced: global index of element 0
     __device__ __forceinline__ T operator[](int64_t i) const
     {
+        if (sl.d) {
+            const int64_t gi = off + i, r = gi / sl.span, lo = gi - r * sl.span;
+            if (lo >= sl.m) return T(0);
+            const int64_t l = reinterpret_cast<const uint8_t *>(sl.leaf[r])[lo];
+            return ((uint32_t)((l + nleaves) >> rshift) == node) ? reinterpret_cast<const T *>(sl.d[r])[lo] : T(0);
+        }
         const int64_t l = leaf_bytes == 1 ? (int64_t)__ldg((const uint8_t *)leaf + i) : __ldg((const int64_t *)leaf + i);
         return ((uint32_t)((l + nleaves) >> rshift) == node) ? d[i] : T(0);
     }
-    __device__ __forceinline__ masked_src operator+(int64_t off) const
+    __device__ __forceinline__ masked_src operator+(int64_t o) const
     {
         masked_src r = *this;
-        r.d += off;
-        r.leaf = (const char *)leaf + off * leaf_bytes;
+        if (sl.d) {
+            r.off += o;
+        } else {
+            r.d += o;
+            r.leaf = (const char *)leaf + o * leaf_bytes;
+        }
         return r;
     }
 };

@@ -20,6 +20,7 @@
 //              spin (acquire loads, bounded by a timeout) until all sources reached the step.
 // All of it is stream-ordered; nothing synchronises with the host.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -46,6 +47,9 @@ struct st_peer {
     st::peer_ptrs ptrs{};
     unsigned int *d_err = nullptr;   // bit 0: a wait timed out
     unsigned int *h_err = nullptr;
+    unsigned int *h_mat = nullptr;   // pinned: host copy of the slices count matrix (st_slices_matrix_fetch / _wait)
+    cudaEvent_t mat_ev = nullptr;
+    const void **d_tab = nullptr;    // device: 2 parities x 2 arrays (differences, shard ids) x PEER_MAX slice pointers
 };
 
 namespace st {
@@ -150,6 +154,148 @@ __global__ void __launch_bounds__(256) peer_scatter_pairs_kernel(const char *__r
         for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < cnt; k += stride) {
             const int2 pr = pairs[k];
             if (pr.x >= 0 && pr.x < m) out[pr.x] = (int64_t)q * leaves_per_shard + pr.y;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Slices layout: the batch is DISTRIBUTED over the ranks (rank r holds elements [r m, (r+1) m) of the global batch, as
+// data-parallel learners produce it), so no rank ever touches more than its own 1/G of the batch plus the elements it
+// owns.  One exchange = count matrix first (M[r][q] = elements of rank r's slice that belong to shard q, plus rank r's
+// validation flags in column `world`), then every kernel derives its offsets from the matrix on the device:
+//   send    slice partitioned by owner (st_shard_partition_device) -> owner q's receive area at sum_{r' < r} M[r'][q]:
+//           the receive area is the owner's elements in GLOBAL batch order (rank-major = batch order), contiguous
+//   return  the owner's results (differences d_j / found leaves) in receive order -> source r's return area at
+//           sum_{q' < q} M[r][q'] = the position the element had in r's partitioned slice
+//   unpermute   result of slice element j = ret[start[shard[j]] + slot[j]]
+// ---------------------------------------------------------------------------------------------
+__global__ void slices_row_kernel(peer_ptrs pp, int rank, size_t mat_off, const unsigned int *__restrict__ row,
+                                  int channel, unsigned int value)
+{
+    // one CTA: row r of the matrix goes to every rank, then the release flag
+    const int w = pp.n;
+    for (int i = threadIdx.x; i < w * (w + 1); i += blockDim.x) {
+        const int q = i / (w + 1), c = i - q * (w + 1);
+        reinterpret_cast<unsigned int *>(pp.base[q] + mat_off)[rank * (w + 1) + c] = row[c];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < w) {
+        unsigned int *f = reinterpret_cast<unsigned int *>(pp.base[threadIdx.x]) + channel * PEER_MAX + rank;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(value) : "memory");
+    }
+}
+
+struct slices_arr {
+    const void *src[2];
+    size_t dst_off[2];
+    int esize[2];
+    int n;
+};
+
+template <typename V> __device__ __forceinline__ void copy_elem(char *dst, const void *src, int64_t di, int64_t si)
+{
+    reinterpret_cast<V *>(dst)[di] = reinterpret_cast<const V *>(src)[si];
+}
+__device__ __forceinline__ void copy_sized(char *dst, const void *src, int64_t di, int64_t si, int es)
+{
+    switch (es) {
+    case 1: copy_elem<uint8_t>(dst, src, di, si); break;
+    case 2: copy_elem<uint16_t>(dst, src, di, si); break;
+    case 4: copy_elem<uint32_t>(dst, src, di, si); break;
+    default: copy_elem<uint64_t>(dst, src, di, si); break;
+    }
+}
+
+// forward: element k of the partitioned slice (k in [0, sum_q M[rank][q])) belongs to destination q with
+// start[q] <= k < start[q + 1]; it lands at element base[q] + (k - start[q]) of q's receive area.
+__global__ void __launch_bounds__(256) slices_send_kernel(peer_ptrs pp, int rank, size_t mat_off, slices_arr a,
+                                                          unsigned int *__restrict__ total_out)
+{
+    __shared__ unsigned int s_start[PEER_MAX + 1], s_base[PEER_MAX];
+    const int w = pp.n;
+    const unsigned int *mat = reinterpret_cast<const unsigned int *>(pp.base[rank] + mat_off);
+    if (threadIdx.x == 0) {
+        unsigned int run = 0;
+        for (int q = 0; q < w; ++q) { s_start[q] = run; run += mat[rank * (w + 1) + q]; }
+        s_start[w] = run;
+    }
+    if (threadIdx.x < w) {
+        unsigned int b = 0;
+        for (int r = 0; r < rank; ++r) b += mat[r * (w + 1) + threadIdx.x];
+        s_base[threadIdx.x] = b;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 32 && total_out) {
+        unsigned int tot = 0;
+        for (int r = 0; r < w; ++r) tot += mat[r * (w + 1) + rank];
+        *total_out = tot;                       // elements this rank receives (it owns)
+    }
+    __syncthreads();
+    const int64_t total = s_start[w];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += stride) {
+        int q = 0;
+        while (k >= (int64_t)s_start[q + 1]) ++q;
+        const int64_t di = (int64_t)s_base[q] + (k - (int64_t)s_start[q]);
+        for (int i = 0; i < a.n; ++i) copy_sized(pp.base[q] + a.dst_off[i], a.src[i], di, k, a.esize[i]);
+    }
+}
+
+// backward: element k of the owner's receive order came from source r with rstart[r] <= k < rstart[r + 1]; its
+// result goes to element sum_{q' < rank} M[r][q'] + (k - rstart[r]) of r's return area.
+__global__ void __launch_bounds__(256) slices_return_kernel(peer_ptrs pp, int rank, size_t mat_off, const void *__restrict__ src,
+                                                            int esize, size_t dst_off)
+{
+    __shared__ unsigned int s_rstart[PEER_MAX + 1], s_base[PEER_MAX];
+    const int w = pp.n;
+    const unsigned int *mat = reinterpret_cast<const unsigned int *>(pp.base[rank] + mat_off);
+    if (threadIdx.x == 0) {
+        unsigned int run = 0;
+        for (int r = 0; r < w; ++r) { s_rstart[r] = run; run += mat[r * (w + 1) + rank]; }
+        s_rstart[w] = run;
+    }
+    if (threadIdx.x < w) {
+        unsigned int b = 0;
+        for (int q = 0; q < rank; ++q) b += mat[threadIdx.x * (w + 1) + q];
+        s_base[threadIdx.x] = b;
+    }
+    __syncthreads();
+    const int64_t total = s_rstart[w];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += stride) {
+        int r = 0;
+        while (k >= (int64_t)s_rstart[r + 1]) ++r;
+        copy_sized(pp.base[r] + dst_off, src, (int64_t)s_base[r] + (k - (int64_t)s_rstart[r]), k, esize);
+    }
+}
+
+// result of slice element j = ret[start[shard[j]] + slot[j]], start from this rank's own row of the matrix.
+// INDEX: ret holds int32 local leaves, out[j] = shard * leaves_per_shard + leaf (int64); otherwise a plain copy.
+template <typename V, bool INDEX>
+__global__ void __launch_bounds__(256) slices_unpermute_kernel(const unsigned int *__restrict__ row, int world,
+                                                               const uint8_t *__restrict__ shard8,
+                                                               const int32_t *__restrict__ slot, int64_t m,
+                                                               const V *__restrict__ ret, int64_t leaves_per_shard,
+                                                               void *__restrict__ out, uint8_t *__restrict__ shard_copy)
+{
+    __shared__ unsigned int s_start[PEER_MAX];
+    if (threadIdx.x == 0) {
+        unsigned int run = 0;
+        for (int q = 0; q < world; ++q) { s_start[q] = run; run += row[q]; }
+    }
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += stride) {
+        const int32_t sl = slot[j];
+        const int q = shard8[j];
+        if constexpr (INDEX) {
+            reinterpret_cast<int64_t *>(out)[j] =
+                sl >= 0 ? (int64_t)q * leaves_per_shard + (int64_t)ret[(size_t)s_start[q] + (size_t)sl] : (int64_t)-1;
+        } else {
+            V v{};
+            if (sl >= 0) v = ret[(size_t)s_start[q] + (size_t)sl];
+            reinterpret_cast<V *>(out)[j] = v;
+            if (shard_copy) shard_copy[j] = (uint8_t)q;   // next to the differences, where the other ranks can read it
         }
     }
 }
@@ -280,6 +426,9 @@ int st_peer_create(int device, int rank, int world, int64_t payload_bytes, st_pe
     if (e == cudaSuccess) e = cudaMalloc((void **)&p->d_err, sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMemset(p->d_err, 0, sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMallocHost((void **)&p->h_err, sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMallocHost((void **)&p->h_mat, sizeof(unsigned int) * st::PEER_MAX * (st::PEER_MAX + 1));
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->mat_ev, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&p->d_tab, sizeof(void *) * 4 * st::PEER_MAX);
     cudaIpcMemHandle_t h;
     if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p->local);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
@@ -340,6 +489,9 @@ int st_peer_destroy(st_peer *p)
     if (p->local) cudaFree(p->local);
     if (p->d_err) cudaFree(p->d_err);
     if (p->h_err) cudaFreeHost(p->h_err);
+    if (p->h_mat) cudaFreeHost(p->h_mat);
+    if (p->mat_ev) cudaEventDestroy(p->mat_ev);
+    if (p->d_tab) cudaFree(p->d_tab);
     delete p;
     return ST_OK;
 }
@@ -441,6 +593,167 @@ int st_search_pairs_device(const st_tree *t, const void *vals_dev, int64_t m_max
     return ST_OK;
 }
 
+// ---- slices layout (batch distributed over the ranks) ---------------------------------------------------------------
+namespace {
+bool region_ok(const st_peer *p, int64_t off, int64_t bytes, int align)
+{
+    return off >= 0 && bytes >= 0 && !(off % align) && (size_t)(off + bytes) <= p->payload_bytes;
+}
+int64_t matrix_bytes(const st_peer *p) { return (int64_t)p->world * (p->world + 1) * 4; }
+}  // namespace
+
+int st_slices_rows(st_peer *p, const uint32_t *row_dev, int64_t matrix_offset, int channel, unsigned int value, void *stream)
+{
+    if (!p || !row_dev || channel < 0 || channel >= st::PEER_CHANNELS || !region_ok(p, matrix_offset, matrix_bytes(p), 4))
+        return pfail(ST_ERR_ARG, "st_slices_rows: bad argument");
+    dev_guard g(p->device);
+    ++st::g_kernel_launches;
+    st::slices_row_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(p->ptrs, p->rank, st::PEER_FLAG_BYTES + (size_t)matrix_offset,
+                                                              row_dev, channel, value);
+    PCU(cudaGetLastError());
+    return ST_OK;
+}
+
+int st_slices_matrix_fetch(st_peer *p, int64_t matrix_offset, void *stream)
+{
+    if (!p || !region_ok(p, matrix_offset, matrix_bytes(p), 4)) return pfail(ST_ERR_ARG, "st_slices_matrix_fetch: bad argument");
+    dev_guard g(p->device);
+    PCU(cudaMemcpyAsync(p->h_mat, p->local + st::PEER_FLAG_BYTES + matrix_offset, (size_t)matrix_bytes(p), cudaMemcpyDeviceToHost,
+                        (cudaStream_t)stream));
+    PCU(cudaEventRecord(p->mat_ev, (cudaStream_t)stream));
+    return ST_OK;
+}
+
+int st_slices_matrix_wait(st_peer *p, uint32_t *matrix_out_host)
+{
+    if (!p || !matrix_out_host) return pfail(ST_ERR_ARG, "st_slices_matrix_wait: bad argument");
+    dev_guard g(p->device);
+    PCU(cudaEventSynchronize(p->mat_ev));     // the fetch only, not what was enqueued behind it
+    memcpy(matrix_out_host, p->h_mat, (size_t)matrix_bytes(p));
+    return ST_OK;
+}
+
+int st_slices_send(st_peer *p, int64_t matrix_offset, const void *src0_dev, int esize0, int64_t dst_offset0, const void *src1_dev,
+                   int esize1, int64_t dst_offset1, int64_t m_max, uint32_t *total_out_dev, void *stream)
+{
+    auto es_ok = [](int e) { return e == 1 || e == 2 || e == 4 || e == 8; };
+    if (!p || m_max < 0 || !region_ok(p, matrix_offset, matrix_bytes(p), 4) || !src0_dev || !es_ok(esize0) ||
+        !region_ok(p, dst_offset0, 0, 8) || (src1_dev && (!es_ok(esize1) || !region_ok(p, dst_offset1, 0, 8))))
+        return pfail(ST_ERR_ARG, "st_slices_send: bad argument");
+    dev_guard g(p->device);
+    st::slices_arr a{};
+    a.n = src1_dev ? 2 : 1;
+    a.src[0] = src0_dev; a.esize[0] = esize0; a.dst_off[0] = st::PEER_FLAG_BYTES + (size_t)dst_offset0;
+    a.src[1] = src1_dev; a.esize[1] = esize1; a.dst_off[1] = st::PEER_FLAG_BYTES + (size_t)dst_offset1;
+    ++st::g_kernel_launches;
+    st::slices_send_kernel<<<st::grid_for(m_max > 0 ? m_max : 1, 256, 1184), 256, 0, (cudaStream_t)stream>>>(
+        p->ptrs, p->rank, st::PEER_FLAG_BYTES + (size_t)matrix_offset, a, total_out_dev);
+    PCU(cudaGetLastError());
+    return ST_OK;
+}
+
+int st_slices_return(st_peer *p, int64_t matrix_offset, const void *src_dev, int esize, int64_t dst_offset, int64_t total_max,
+                     void *stream)
+{
+    if (!p || total_max < 0 || !region_ok(p, matrix_offset, matrix_bytes(p), 4) || !src_dev ||
+        (esize != 1 && esize != 2 && esize != 4 && esize != 8) || !region_ok(p, dst_offset, 0, 8))
+        return pfail(ST_ERR_ARG, "st_slices_return: bad argument");
+    dev_guard g(p->device);
+    ++st::g_kernel_launches;
+    st::slices_return_kernel<<<st::grid_for(total_max > 0 ? total_max : 1, 256, 1184), 256, 0, (cudaStream_t)stream>>>(
+        p->ptrs, p->rank, st::PEER_FLAG_BYTES + (size_t)matrix_offset, src_dev, esize, st::PEER_FLAG_BYTES + (size_t)dst_offset);
+    PCU(cudaGetLastError());
+    return ST_OK;
+}
+
+int st_slices_unpermute(st_peer *p, int64_t matrix_offset, const uint8_t *shard_dev, const int32_t *slot_dev, int64_t m,
+                        int64_t ret_offset, int esize, int64_t leaves_per_shard, void *out_dev, int64_t shard_copy_offset,
+                        void *stream)
+{
+    if (!p || m < 0 || (shard_copy_offset >= 0 && !region_ok(p, shard_copy_offset, m, 1)) || !region_ok(p, matrix_offset, matrix_bytes(p), 4) || !region_ok(p, ret_offset, m * (leaves_per_shard > 0 ? 4 : esize), 8) ||
+        (m > 0 && (!shard_dev || !slot_dev || !out_dev)) || (esize != 1 && esize != 2 && esize != 4 && esize != 8))
+        return pfail(ST_ERR_ARG, "st_slices_unpermute: bad argument");
+    if (m == 0) return ST_OK;
+    dev_guard g(p->device);
+    ++st::g_kernel_launches;
+    const unsigned int *row = reinterpret_cast<const unsigned int *>(p->local + st::PEER_FLAG_BYTES + matrix_offset) +
+                              (size_t)p->rank * (p->world + 1);
+    const char *ret = p->local + st::PEER_FLAG_BYTES + ret_offset;
+    uint8_t *sc = shard_copy_offset >= 0 ? (uint8_t *)(p->local + st::PEER_FLAG_BYTES + shard_copy_offset) : nullptr;
+    const unsigned grid = st::grid_for(m, 256, 1184);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (leaves_per_shard > 0)
+        st::slices_unpermute_kernel<int32_t, true><<<grid, 256, 0, s>>>(row, p->world, shard_dev, slot_dev, m, (const int32_t *)ret, leaves_per_shard, out_dev, nullptr);
+    else if (esize == 1)
+        st::slices_unpermute_kernel<uint8_t, false><<<grid, 256, 0, s>>>(row, p->world, shard_dev, slot_dev, m, (const uint8_t *)ret, 0, out_dev, sc);
+    else if (esize == 2)
+        st::slices_unpermute_kernel<uint16_t, false><<<grid, 256, 0, s>>>(row, p->world, shard_dev, slot_dev, m, (const uint16_t *)ret, 0, out_dev, sc);
+    else if (esize == 4)
+        st::slices_unpermute_kernel<uint32_t, false><<<grid, 256, 0, s>>>(row, p->world, shard_dev, slot_dev, m, (const uint32_t *)ret, 0, out_dev, sc);
+    else
+        st::slices_unpermute_kernel<uint64_t, false><<<grid, 256, 0, s>>>(row, p->world, shard_dev, slot_dev, m, (const uint64_t *)ret, 0, out_dev, sc);
+    PCU(cudaGetLastError());
+    return ST_OK;
+}
+
+int st_slices_table(st_peer *p, int parity, int64_t d_offset, int64_t leaf_offset)
+{
+    if (!p || (parity != 0 && parity != 1) || !region_ok(p, d_offset, 0, 8) || !region_ok(p, leaf_offset, 0, 8))
+        return pfail(ST_ERR_ARG, "st_slices_table: bad argument");
+    dev_guard g(p->device);
+    const void *tab[2 * st::PEER_MAX] = {};
+    for (int q = 0; q < p->world; ++q) {
+        if (!p->ptrs.base[q]) return pfail(ST_ERR_ARG, "st_slices_table: peers are not connected yet");
+        tab[q] = p->ptrs.base[q] + st::PEER_FLAG_BYTES + d_offset;
+        tab[st::PEER_MAX + q] = p->ptrs.base[q] + st::PEER_FLAG_BYTES + leaf_offset;
+    }
+    PCU(cudaMemcpy(p->d_tab + (size_t)parity * 2 * st::PEER_MAX, tab, sizeof(tab), cudaMemcpyHostToDevice));
+    return ST_OK;
+}
+
+int st_top_fold_maps_slice_device(st_tree *t, const uint8_t *leaf_dev, const void *deltas_dev, int64_t m_slice,
+                                  int64_t record_first, int64_t nchunks, void *recs_dev, void *stream)
+{
+    if (!t || m_slice < 0 || record_first < 0 || nchunks < 0 || !recs_dev || (m_slice > 0 && (!leaf_dev || !deltas_dev)) ||
+        nchunks * 1024 < m_slice || (record_first + nchunks) * 1024 > 0x7fffffffLL)
+        return pfail(ST_ERR_ARG, "st_top_fold_maps_slice_device: bad argument");
+    std::lock_guard<std::recursive_mutex> lk(t->mu);
+    dev_guard g(t->device);
+    // chunk c of the GLOBAL batch = chunk c - record_first of this slice: shift the array origins accordingly
+    const int64_t shift = record_first * 1024;
+    const char *leaf0 = (const char *)leaf_dev - shift;
+    const char *d0 = (const char *)deltas_dev - shift * t->esize;
+    PCU(st::launch_fold_by_leaf_maps(t, leaf0, 1, d0, shift + m_slice, (int)record_first, (int)(record_first + nchunks), recs_dev,
+                                     (cudaStream_t)stream));
+    return ST_OK;
+}
+
+int st_top_fold_apply_slices_device(st_tree *t, st_peer *p, int parity, int64_t span, int64_t m_slice, const void *recs_dev,
+                                    void *stream)
+{
+    if (!t || !p || (parity != 0 && parity != 1) || span <= 0 || (span % 1024) || m_slice < 0 || m_slice > span || !recs_dev ||
+        span * p->world > 0x7fffffffLL)
+        return pfail(ST_ERR_ARG, "st_top_fold_apply_slices_device: bad argument");
+    std::lock_guard<std::recursive_mutex> lk(t->mu);
+    dev_guard g(t->device);
+    const void *const *tab = p->d_tab + (size_t)parity * 2 * st::PEER_MAX;
+    PCU(st::launch_fold_by_leaf_apply(t, nullptr, 1, nullptr, span * p->world, recs_dev, (cudaStream_t)stream, tab,
+                                      tab + st::PEER_MAX, span, m_slice));
+    return ST_OK;
+}
+
+int st_search_leaf32_device(const st_tree *t, const void *vals_dev, int64_t m_max, const uint32_t *m_dev, int32_t *out_dev,
+                            void *stream)
+{
+    if (!t || m_max < 0 || !m_dev || (m_max > 0 && (!vals_dev || !out_dev)))
+        return pfail(ST_ERR_ARG, "st_search_leaf32_device: bad argument");
+    dev_guard g(t->device);
+    st::search_push push;
+    push.leaf32 = out_dev;
+    PCU(st::launch_search(t, vals_dev, m_max, nullptr, (cudaStream_t)stream, m_dev, &push));
+    return ST_OK;
+}
+
 int st_peer_signal(st_peer *p, int channel, unsigned int value, void *stream)
 {
     if (!p || channel < 0 || channel >= st::PEER_CHANNELS) return pfail(ST_ERR_ARG, "st_peer_signal: bad argument");
@@ -456,8 +769,13 @@ int st_peer_wait(st_peer *p, int channel, unsigned int value, void *stream)
     if (!p || channel < 0 || channel >= st::PEER_CHANNELS) return pfail(ST_ERR_ARG, "st_peer_wait: bad argument");
     dev_guard g(p->device);
     ++st::g_kernel_launches;
+    static const unsigned long long timeout_ns = [] {   // STARR_B200_WAIT_TIMEOUT_S: debugging aid (default 20 s)
+        const char *e = getenv("STARR_B200_WAIT_TIMEOUT_S");
+        const double sec = e ? atof(e) : 20.0;
+        return (unsigned long long)((sec > 0 ? sec : 20.0) * 1e9);
+    }();
     st::peer_wait_kernel<<<1, st::PEER_MAX, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned int *>(p->local), channel,
-                                                                      value, p->world, 20ull * 1000000000ull, p->d_err);
+                                                                      value, p->world, timeout_ns, p->d_err);
     PCU(cudaGetLastError());
     return ST_OK;
 }

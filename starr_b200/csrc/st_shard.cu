@@ -214,6 +214,86 @@ __global__ void __launch_bounds__(SH_THREADS, 3) shard_slot_kernel(const int64_t
     }
 }
 
+// Slices layout (the batch is DISTRIBUTED over the ranks, every rank holds 1/G of it): the same counts and slots, but
+// instead of compacting one shard the kernel writes the STABLE G-way partition of the whole slice -- the elements of
+// shard 0 in batch order, then those of shard 1, ... -- which is the order the slice travels in (one contiguous run
+// per destination rank) and the order its results come back in.  part_ids: shard-local ids; part_payload: payload.
+// Consecutive threads store consecutive elements of one destination run.
+template <typename T>
+__global__ void __launch_bounds__(SH_THREADS, 3) shard_partition_kernel(const int64_t *__restrict__ ids, int64_t m, int shift,
+                                                                        int shards, const T *__restrict__ payload,
+                                                                        const uint8_t *__restrict__ shard8,
+                                                                        const unsigned int *__restrict__ tile_off,
+                                                                        int64_t ntiles, const unsigned int *__restrict__ counts,
+                                                                        int32_t *__restrict__ slot_out,
+                                                                        int64_t *__restrict__ part_ids, T *__restrict__ part_payload)
+{
+    typedef cub::BlockScan<pk128, SH_THREADS> scan_t;
+    __shared__ typename scan_t::TempStorage tmp;
+    __shared__ unsigned int s_off[SH_MAX];            // elements of each shard before this tile
+    __shared__ unsigned int s_start[SH_MAX];          // first element of each shard's run in the partition
+    __shared__ unsigned int s_tpre[SH_MAX + 1];       // this tile: elements of the shards in front of shard q
+    __shared__ int32_t s_slot[SH_TILE];
+    __shared__ unsigned short s_order[SH_TILE];       // tile elements sorted by (shard, batch position)
+    const int tid = threadIdx.x;
+    if (tid < SH_MAX) s_off[tid] = tid < shards ? tile_off[(int64_t)tid * ntiles + blockIdx.x] : 0u;
+    if (tid == 0) {
+        unsigned int run = 0;
+        for (int q = 0; q < shards; ++q) { s_start[q] = run; run += counts[q]; }
+        s_tpre[0] = 0;
+    }
+    const int64_t tile0 = (int64_t)blockIdx.x * SH_TILE;
+    const int64_t j0 = tile0 + (int64_t)tid * SH_E;
+    const unsigned long long word = load_shard8(shard8, j0, m);
+#pragma unroll
+    for (int k = 0; k < SH_E; ++k) s_slot[k * SH_THREADS + tid] = -1;
+    __syncthreads();
+    unsigned int within_reg[SH_E];
+    for (int g0 = 0; g0 < shards; g0 += 8) {
+        pk128 c{0, 0};
+#pragma unroll
+        for (int k = 0; k < SH_E; ++k) {
+            const int b = (int)((word >> (8 * k)) & 0xff) - g0;
+            if (b >= 0 && b < 8) pk_inc(c, b);
+        }
+        pk128 pre, total;
+        scan_t(tmp).ExclusiveScan(c, pre, pk128{0, 0}, pk_add(), total);
+        if (tid == 0)
+            for (int b = 0; b < 8 && g0 + b < shards; ++b) s_tpre[g0 + b + 1] = s_tpre[g0 + b] + pk_get(total, b);
+#pragma unroll
+        for (int k = 0; k < SH_E; ++k) {
+            const int b = (int)((word >> (8 * k)) & 0xff) - g0;
+            if (b >= 0 && b < 8) {
+                within_reg[k] = pk_get(pre, b);
+                s_slot[tid * SH_E + k] = (int32_t)(s_off[b + g0] + within_reg[k]);
+                pk_inc(pre, b);
+            }
+        }
+        __syncthreads();   // tmp is reused by the next group; s_tpre[.. g0 + 8] complete
+    }
+#pragma unroll
+    for (int k = 0; k < SH_E; ++k) {
+        const int b = (int)((word >> (8 * k)) & 0xff);
+        if (b < shards) s_order[s_tpre[b] + within_reg[k]] = (unsigned short)(tid * SH_E + k);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < SH_E; ++r) {
+        const int i = r * SH_THREADS + tid;
+        if (tile0 + i < m) slot_out[tile0 + i] = s_slot[i];
+    }
+    if (!part_ids && !part_payload) return;
+    const unsigned int nvalid = s_tpre[shards];
+    for (unsigned int i = tid; i < nvalid; i += SH_THREADS) {
+        const unsigned int e = s_order[i];
+        const int64_t j = tile0 + e;
+        const int q = shard8[j];
+        const size_t at = (size_t)s_start[q] + (size_t)s_slot[e];
+        if (part_ids) part_ids[at] = ids[j] - ((int64_t)q << shift);
+        if (part_payload) part_payload[at] = payload[j];
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) shard_expand_values_kernel(const uint8_t *__restrict__ shard8,
                                                                   const int32_t *__restrict__ slot, int64_t m,
@@ -289,6 +369,33 @@ cudaError_t launch_shard_plan(st_tree *t, const int64_t *ids, int64_t m, int shi
         shard_slot_kernel<T><<<(unsigned)ntiles, SH_THREADS, 0, s>>>(ids, m, shift, shards, rank, (const T *)payload,
                                                                     npayload, shard_out, tile_counts, ntiles, slot_out,
                                                                     own_ids_out, (T *)own_payload_out, own_pos_out);
+    });
+    return cudaGetLastError();
+}
+
+cudaError_t launch_shard_partition(st_tree *t, const int64_t *ids, int64_t m, int shift, int shards, const void *payload,
+                                   int check_negative, uint8_t *shard_out, int32_t *slot_out, int64_t *part_ids_out,
+                                   void *part_payload_out, void *scratch, unsigned int *row_out, cudaStream_t s)
+{
+    if (shards < 1 || shards > SH_MAX || shift < 0 || shift > 62) return cudaErrorInvalidValue;
+    const int64_t ntiles = shard_tiles(m);
+    if (ntiles <= 0 || ntiles > 0x7fffffffLL) return cudaErrorInvalidValue;
+    unsigned int *tile_counts = (unsigned int *)scratch;
+    unsigned int *flags = tile_counts + (size_t)shards * ntiles;
+    cudaError_t e = cudaMemsetAsync(flags, 0, sizeof(unsigned int), s);
+    if (e != cudaSuccess) return e;
+    g_kernel_launches += 3;
+    ST_DISPATCH(t->dtype, {
+        if (check_negative)
+            shard_count_kernel<T, true><<<(unsigned)ntiles, SH_THREADS, 0, s>>>(
+                ids, m, shift, shards, (const T *)payload, m, shard_out, tile_counts, ntiles, flags);
+        else
+            shard_count_kernel<T, false><<<(unsigned)ntiles, SH_THREADS, 0, s>>>(
+                ids, m, shift, shards, (const T *)payload, m, shard_out, tile_counts, ntiles, flags);
+        shard_scan_kernel<<<(unsigned)shards, SH_THREADS, 0, s>>>(tile_counts, ntiles, row_out, flags);
+        shard_partition_kernel<T><<<(unsigned)ntiles, SH_THREADS, 0, s>>>(ids, m, shift, shards, (const T *)payload, shard_out,
+                                                                         tile_counts, ntiles, row_out, slot_out, part_ids_out,
+                                                                         (T *)part_payload_out);
     });
     return cudaGetLastError();
 }

@@ -438,7 +438,9 @@ search_kernel(const T *__restrict__ H, uint32_t n, int depth, const void *__rest
         for (int q = 0; q < SEARCH_Q; ++q) {
             const int64_t i = base + threadIdx.x + (int64_t)q * SEARCH_THREADS;
             if (i < m) {
-                if (push.pairs) {
+                if (push.leaf32) {
+                    push.leaf32[i] = (int32_t)(h[q] - n);
+                } else if (push.pairs) {
                     // sharded sample, coalesced exchange: (batch position, local leaf) in this rank's own order
                     reinterpret_cast<int2 *>(push.pairs)[i] = make_int2(push.pos[i], (int)(h[q] - n));
                 } else if (push.n) {

@@ -401,7 +401,7 @@ __device__ void huge_apply_body(T *__restrict__ H, const T *__restrict__ lev_d, 
                                 const chunk_rec<typename fp_bits<T>::I> *__restrict__ recs, unsigned int *status,
                                 const void *__restrict__ mleaf, int mleaf_bytes, int64_t mnleaves, int mleaf_level,
                                 const chunk_rec<typename fp_bits<T>::I> *__restrict__ recs2, int *__restrict__ redo,
-                                int redo_stride, T *s_seq, const sidx_ref &sx);
+                                int redo_stride, T *s_seq, const sidx_ref &sx, const slice_ref &sl = slice_ref{});
 
 // second-pass stitch of the huge segments, done by the same launch as the long / medium folds
 template <typename T> struct huge_params {
@@ -606,7 +606,8 @@ __device__ void huge_apply_body(T *__restrict__ H, const T *__restrict__ lev_d, 
                                 const chunk_rec<typename fp_bits<T>::I> *__restrict__ recs, unsigned int *status,
                                 const void *__restrict__ mleaf, int mleaf_bytes, int64_t mnleaves, int mleaf_level,
                                 const chunk_rec<typename fp_bits<T>::I> *__restrict__ recs2, int *__restrict__ redo,
-                                int redo_stride, T *s_seq /* FOLD_CHUNK elements of shared memory */, const sidx_ref &sx)
+                                int redo_stride, T *s_seq /* FOLD_CHUNK elements of shared memory */, const sidx_ref &sx,
+                                const slice_ref &sl)
 {
     // First pass (REDO false): stitch with the summaries made for the binade eA the node starts in.
     //   redo == nullptr (the masked top fold): chunks that fail the check are folded exactly in place.
@@ -760,7 +761,7 @@ __device__ void huge_apply_body(T *__restrict__ H, const T *__restrict__ lev_d, 
                 if (ready) cur = value_of<T>(e_cur, m);
                 const int nc = s.len - c * FOLD_CHUNK < FOLD_CHUNK ? s.len - c * FOLD_CHUNK : FOLD_CHUNK;
                 if constexpr (MASKED) {
-                    const masked_src<T> ms{lev_d, mleaf, mleaf_bytes, mnleaves, s.node, mleaf_level - s.level};
+                    const masked_src<T> ms{lev_d, mleaf, mleaf_bytes, mnleaves, s.node, mleaf_level - s.level, sl, 0};
                     cur = hovering ? sequential_fold_cta<T>(cur, ms + (int64_t)c * FOLD_CHUNK, nc, s_seq)
                                    : ordered_fold_cta<T>(cur, ms + (int64_t)c * FOLD_CHUNK, nc, s_wtot, &s_mviol, &ctl, s_seq);
                 } else {
@@ -794,11 +795,12 @@ __global__ void __launch_bounds__(FOLD_THREADS) fold_huge_apply_kernel(T *__rest
                                                                        const void *__restrict__ mleaf, int mleaf_bytes, int64_t mnleaves,
                                                                        int mleaf_level,
                                                                        const chunk_rec<typename fp_bits<T>::I> *__restrict__ recs2,
-                                                                       int *__restrict__ redo, int redo_stride, const sidx_ref sx)
+                                                                       int *__restrict__ redo, int redo_stride, const sidx_ref sx,
+                                                                       const slice_ref sl = slice_ref{})
 {
     __shared__ T s_seq[FOLD_CHUNK];
     huge_apply_body<T, MASKED, REDO>(H, lev_d, level_stride, qhuge, huge_off, recs, status, mleaf, mleaf_bytes, mnleaves,
-                                     mleaf_level, recs2, redo, redo_stride, s_seq, sx);
+                                     mleaf_level, recs2, redo, redo_stride, s_seq, sx, sl);
 }
 
 // Masked variant of phase A for the tiny top tree: records laid out [chunk][node-1] so that a rank's
@@ -1189,7 +1191,8 @@ cudaError_t launch_fold_by_leaf_maps(st_tree *t, const void *leaf, int leaf_byte
 }
 
 cudaError_t launch_fold_by_leaf_apply(st_tree *t, const void *leaf, int leaf_bytes, const void *deltas, int64_t m,
-                                      const void *recs, cudaStream_t s)
+                                      const void *recs, cudaStream_t s, const void *const *slice_d,
+                                      const void *const *slice_leaf, int64_t slice_span, int64_t slice_m)
 {
     if (!fold_by_leaf_ok(t, m) || (leaf_bytes != 1 && leaf_bytes != 8)) return cudaErrorInvalidValue;
     if (m <= 0) return cudaSuccess;
@@ -1204,16 +1207,18 @@ cudaError_t launch_fold_by_leaf_apply(st_tree *t, const void *leaf, int leaf_byt
         t->ws.bytes = need < 4096 ? 4096 : need;
     }
     seg_entry *q = (seg_entry *)t->ws.base;
+    slice_ref sl{};
+    if (slice_d) { sl.d = slice_d; sl.leaf = slice_leaf; sl.span = slice_span; sl.m = slice_m; }
     g_kernel_launches += 2;
     top_entries_kernel<<<1, 64, 0, s>>>(q, t->d_status, (int)t->n, (int)m);
     if (t->dtype == ST_F32)
         fold_huge_apply_kernel<float, true, false><<<(unsigned)(t->n - 1), FOLD_THREADS, 0, s>>>(
             (float *)t->heap, (const float *)deltas, 0, q, nullptr, (const chunk_rec<int32_t> *)recs, t->d_status, leaf,
-            leaf_bytes, t->n, t->depth, nullptr, nullptr, 0, sidx_ref{});
+            leaf_bytes, t->n, t->depth, nullptr, nullptr, 0, sidx_ref{}, sl);
     else
         fold_huge_apply_kernel<double, true, false><<<(unsigned)(t->n - 1), FOLD_THREADS, 0, s>>>(
             (double *)t->heap, (const double *)deltas, 0, q, nullptr, (const chunk_rec<int64_t> *)recs, t->d_status, leaf,
-            leaf_bytes, t->n, t->depth, nullptr, nullptr, 0, sidx_ref{});
+            leaf_bytes, t->n, t->depth, nullptr, nullptr, 0, sidx_ref{}, sl);
     return cudaGetLastError();
 }
 

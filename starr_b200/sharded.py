@@ -97,8 +97,13 @@ class ShardedSumTree:
         self._peer_cap = (0, 0)
         self._ustep = self._sstep = 0
         self._side = None
+        self._slices = None          # SlicesExchange (starr_b200/_slices.py), created by the first distributed batch
         if local_leaves is not None:
             self.build_(local_leaves)
+
+    @staticmethod
+    def _dist():
+        return dist
 
     # ---- helpers --------------------------------------------------------------------------------
     def reserve(self, max_global_batch: int) -> None:
@@ -179,6 +184,8 @@ class ShardedSumTree:
     def close(self) -> None:
         """Release the peer exchange area (collective; every rank calls it).  Without it the area is freed when the
         object is collected, which is only safe once every rank has finished with the tree."""
+        if self._slices is not None:
+            self._slices.close()
         if self._peer is not None:
             torch.cuda.synchronize(self.device)
             dist.barrier(group=self.group)
@@ -473,6 +480,76 @@ class ShardedSumTree:
         self._peer.scatter_pairs(self._lay["pairs"][par], self._pair_slab, self._lay["cnt"][par], self.n_local, out.data_ptr(), m, s)
         self._mark("sample: indices to batch order")
         return out
+
+    # ---- slices layout: the batch is distributed over the ranks (starr_b200/_slices.py) ---------------------------
+    def _slices_exchange(self):
+        if not self._peer_wanted:
+            return None
+        if self._slices is None:
+            from ._slices import SlicesExchange
+            self._slices = SlicesExchange(self)
+        return self._slices
+
+    def reserve_slices(self, max_slice: int, expected_local: int | None = None) -> None:
+        """Pre-size the exchange area for slices of up to ``max_slice`` elements per rank and the local update
+        workspace for ``expected_local`` owned elements per batch (default: twice the slice).  Collective."""
+        # update workspace + the partition's scratch area (local tree: update plans, top tree: sample plans), so that no
+        # stream-ordered call reallocates (= waits for the whole device) later
+        for tree, batch in ((self.local, int(expected_local or 2 * max_slice)), (self.top, int(max_slice))):
+            h = getattr(tree, "handle", None)
+            if h is not None and hasattr(h, "reserve_sharded"):
+                h.reserve_sharded(max(batch, int(max_slice)), self.world)
+            else:
+                tree.reserve(batch)
+        sx = self._slices_exchange()
+        if sx is not None:
+            sx.ensure(int(max_slice))
+
+    def plan_update_slices(self, idx: torch.Tensor, vals: torch.Tensor, stream=None):
+        """First half of ``update_slices_``: owner / slot of every element of this rank's slice and the exchange of
+        the slices (ids and values travel to their owners).  Reads nothing of the tree, so with ``stream`` (a side
+        stream; ``idx`` / ``vals`` must be complete on the device) it overlaps the batch that is being applied."""
+        sx = self._slices_exchange()
+        if sx is None:
+            return ("gathered", idx, vals)
+        return sx.plan_update(idx, vals, stream)
+
+    def update_slices_(self, idx: torch.Tensor | None = None, vals: torch.Tensor | None = None, plan=None) -> "ShardedSumTree":
+        """Distributed batch: rank r supplies elements ``[r m, (r+1) m)`` of the global batch -- ``idx`` are GLOBAL
+        leaf ids, ``vals`` one value per index, the same ``m`` on every rank.  Bit-identical to ONE reference tree
+        applying the concatenated batch in rank order (pyx:41-49).  A bad slice on any rank raises on every rank,
+        before anything is modified.  Without peer memory the slices are all-gathered and applied as a replicated batch."""
+        if plan is None:
+            plan = self.plan_update_slices(idx, vals)
+        if isinstance(plan, tuple):
+            _, idx, vals = plan
+            idx, vals = idx.reshape(-1).contiguous(), vals.reshape(-1).contiguous()
+            if vals.numel() != idx.numel():
+                raise TypeError("slices layout: vals must have one entry per index of the slice")
+            all_idx = torch.empty(self.world * idx.numel(), dtype=idx.dtype, device=idx.device)
+            all_vals = torch.empty(self.world * vals.numel(), dtype=vals.dtype, device=vals.device)
+            dist.all_gather_into_tensor(all_idx, idx, group=self.group)
+            dist.all_gather_into_tensor(all_vals, vals, group=self.group)
+            return self.update_(all_idx, all_vals)
+        self._slices.update(plan)
+        return self
+
+    def sample_slices(self, u: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """Global leaf indices for THIS rank's uniforms (float64; the same count on every rank): what the reference's
+        ``get_prefix_sum_id((root * u).astype(dtype))`` returns for them on the whole tree."""
+        u = u.reshape(-1)
+        m = u.numel()
+        if out is None:
+            out = torch.empty(m, dtype=torch.int64, device=u.device)
+        sx = self._slices_exchange()
+        if sx is None:
+            all_u = torch.empty(self.world * m, dtype=u.dtype, device=u.device)
+            dist.all_gather_into_tensor(all_u, u.contiguous(), group=self.group)
+            out.copy_(self.sample_uniform(all_u)[self.rank * m:(self.rank + 1) * m])
+            return out
+        if u.dtype != torch.float64 or not u.is_contiguous() or out.dtype != torch.int64 or not out.is_contiguous() or out.numel() < m:
+            raise TypeError("u must be a contiguous float64 tensor and out a contiguous int64 tensor of the same size")
+        return self._slices.sample(u, out)
 
     # ---- inspection -------------------------------------------------------------------------------
     def gather_sumtree(self) -> torch.Tensor:

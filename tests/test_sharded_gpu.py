@@ -306,3 +306,109 @@ def test_sharded_cuda_path_on_one_gpu(world, dt_name, peer, monkeypatch):
         return bad_steps
 
     assert group.run(rank_body) == [[]] * world
+
+
+@pytest.mark.parametrize("world,dt_name", [(2, "float32"), (8, "float32"), (4, "float64"), (4, "int32")])
+def test_sharded_slices_on_one_gpu(world, dt_name, monkeypatch):
+    """Slices layout (starr_b200/_slices.py): every rank supplies 1/G of the batch; the tree, the leaves and the sampled
+    indices must equal ONE oracle tree that applies the concatenated batch.  Ranks are threads on cuda:0, each on a stream
+    of its own; odd batches are planned ahead on a side stream."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle
+    from _thread_group import ThreadGroup
+
+    import starr_b200.sharded as sharded
+    group = ThreadGroup(world)
+    monkeypatch.setattr(sharded, "dist", group)
+    # 8 ranks on ONE device: one stream per rank (three each would share the device's hardware queues, and a spinning
+    # wait kernel at the head of a queue holds up whatever else was mapped to it -- separate processes on separate GPUs
+    # have the queues to themselves); the side-stream schedule is covered by the 2- and 4-rank cases
+    one_stream = world > 4
+    if one_stream:
+        monkeypatch.setenv("STARR_B200_SLICES_SERIAL", "1")
+    dev = torch.device("cuda", 0)
+    dt, tdt = np.dtype(dt_name), getattr(torch, dt_name)
+    n = 1 << 16
+    rng = np.random.default_rng(12)
+    draw = (lambda k: np.exp(rng.uniform(-8, 8, k)).astype(dt)) if dt.kind == "f" else \
+        (lambda k: rng.integers(0, 1000, k).astype(dt))
+    leaves = draw(n)
+    ref_leaves, ref_tree = leaves.copy(), np.zeros(n, dt)
+    oracle.c.build_sumtree_from_array(ref_leaves, ref_tree)
+    nl = n // world
+    batches = []
+    for m, mq in ((1, 3), (512, 100), (2500, 2500), (9000, 5000)):       # per rank
+        idx = rng.integers(0, n, m * world).astype(np.int64)
+        if m == 2500:
+            idx[rng.random(idx.size) < 0.7] = rng.integers(0, 64, 1)[0]    # skewed: most of the batch is ONE leaf of shard 0
+        if m == 9000:
+            idx[: m] = rng.integers(n - nl, n, m)                          # the first rank's slice all belongs to the last shard
+        vals, u = draw(m * world), rng.random(mq * world)
+        oracle.c.update_sumtree(idx.astype(np.intp), vals, ref_leaves, ref_tree)
+        want = np.zeros(u.size, np.intp)
+        oracle.c.get_prefix_sum_idx(want, (ref_tree[1] * u).astype(dt), ref_leaves, ref_tree)
+        batches.append((m, mq, idx, vals, u, ref_tree.copy(), ref_leaves.copy(), want))
+
+    # every kernel runs once BEFORE the ranks start (see test_sharded_cuda_path_on_one_gpu)
+    from starr_b200 import DeviceSumTree
+    warm = DeviceSumTree(torch.from_numpy(leaves[:nl].copy()).to(dev))
+    warm.reserve(9000 * world)
+    for m, mq, idx, vals, u, *_ in batches:
+        w_idx, w_vals = torch.from_numpy(idx % nl).to(dev), torch.from_numpy(vals).to(dev)
+        warm.update_begin_(w_idx, w_vals, torch.empty(idx.size, dtype=tdt, device=dev))
+        warm.update_finish_()
+        warm.sample_uniform(torch.from_numpy(u).to(dev))
+    warm.poll()
+    torch.cuda.synchronize()
+    del warm
+
+    def rank_body(r):
+        torch.cuda.set_device(0)
+        with torch.cuda.stream(torch.cuda.Stream()):
+            try:
+                return rank_steps(r)
+            finally:
+                torch.cuda.current_stream().synchronize()
+
+    def rank_steps(r):
+        st = sharded.ShardedSumTree(n, tdt, local_leaves=torch.from_numpy(leaves[r * nl:(r + 1) * nl].copy()).to(dev), peer=True)
+        st.reserve_slices(9000, expected_local=9000 * world)   # no workspace growth while another rank's wait kernel spins
+        bad_steps = []
+        side = torch.cuda.Stream()
+        for b, (m, mq, idx, vals, u, tree_after, leaves_after, want) in enumerate(batches):
+            d_idx = torch.from_numpy(idx[r * m:(r + 1) * m]).to(dev)
+            d_vals = torch.from_numpy(vals[r * m:(r + 1) * m]).to(dev)
+            if b % 2 and not one_stream:
+                torch.cuda.current_stream().synchronize()
+                st.update_slices_(plan=st.plan_update_slices(d_idx, d_vals, stream=side))
+            else:
+                st.update_slices_(d_idx, d_vals)
+            if st.gather_sumtree().cpu().numpy().tobytes() != tree_after.tobytes():
+                bad_steps.append((b, "tree"))
+            if st.gather_leaves().cpu().numpy().tobytes() != leaves_after.tobytes():
+                bad_steps.append((b, "leaves"))
+            got = st.sample_slices(torch.from_numpy(u[r * mq:(r + 1) * mq]).to(dev)).cpu().numpy()
+            if not np.array_equal(got, want[r * mq:(r + 1) * mq]):
+                bad_steps.append((b, "sample"))
+        # a bad slice on ONE rank raises on every rank, before anything is modified
+        before = st.gather_sumtree().cpu().numpy().tobytes()
+        m, _, idx, vals = batches[1][:4]
+        bad = torch.from_numpy(idx[r * m:(r + 1) * m]).to(dev).clone()
+        if r == world - 1:
+            bad[17] = n
+        try:
+            st.update_slices_(bad, torch.from_numpy(vals[r * m:(r + 1) * m]).to(dev))
+            bad_steps.append(("bad batch", "not reported"))
+        except IndexError:
+            pass
+        if st.gather_sumtree().cpu().numpy().tobytes() != before:
+            bad_steps.append(("bad batch", "tree modified"))
+        # and the tree keeps working afterwards
+        m, mq, idx, vals, u, *_ = batches[0]
+        st.update_slices_(torch.from_numpy(idx[r * m:(r + 1) * m]).to(dev), torch.from_numpy(vals[r * m:(r + 1) * m]).to(dev))
+        if st._slices is None or st._slices.area is None:
+            bad_steps.append(("slices", "exchange area was not used"))
+        st.close()
+        return bad_steps
+
+    assert group.run(rank_body) == [[]] * world
