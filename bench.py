@@ -34,6 +34,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# the sharded step keeps wait kernels spinning on up to three streams: one hardware queue per stream
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 LOG2_LEAVES = int(os.environ.get("ST_BENCH_LOG2_LEAVES", "27"))   # per GPU
 LOG2_BATCH = int(os.environ.get("ST_BENCH_LOG2_BATCH", "20"))     # per GPU
@@ -222,7 +224,12 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(world):
+def workload_config(world, layout="single"):
+    how = {"single": "single tree",
+           "slices": f"subtree shards x{world}; the batch is distributed (every rank supplies and samples its own 1/{world} "
+                     "of it); exchange over CUDA-IPC peer memory (NVLink), NCCL only for set-up",
+           "replicated": f"subtree shards x{world}; the whole batch is replicated on every rank; exchange of deltas / roots / "
+                         "results over peer memory"}[layout]
     return {
         "workload": f"SumTreeArray float32, 2^{LOG2_LEAVES} leaves per GPU ({world} GPU: 2^{LOG2_LEAVES + (world - 1).bit_length()} "
                     f"leaves{' sharded by subtree' if world > 1 else ''}), per step 2^{LOG2_BATCH} leaf updates + 2^{LOG2_BATCH} prefix-search samples per GPU "
@@ -232,7 +239,7 @@ def workload_config(world):
         "l2_policy": "inputs larger than L2: the tree is 1 GiB per GPU; every warm-up and timed step applies a batch "
                      "(indices, values, uniforms) that has never been applied before (zero_delta_frac reports the share "
                      "of updates whose difference was exactly 0)",
-        "parallelism": "single tree" if world == 1 else f"subtree shards x{world}, NCCL exchange of deltas / roots / results",
+        "parallelism": how,
     }
 
 
@@ -259,14 +266,15 @@ def parity_single(torch, dev, leaves_host, batches_host, cpu_state):
             "sampled_indices_equal": bool(ok_idx), "ok": bool(ok_tree and ok_leaves and ok_idx)}
 
 
-def parity_sharded(torch, dist, dev, world, rank):
+def parity_sharded(torch, dist, dev, world, rank, layout):
     """Reduced sharded case against the C oracle on EVERY rank, before the timed region: 2^22 leaves over the
-    ranks, float32 and int32, 3 replicated batches of 2^16 updates (with duplicates) and 50 000 samples."""
+    ranks, float32 and int32, 3 batches of 2^16 updates (with duplicates) and 50 000 samples, in the layout the
+    timed region uses (slices: every rank supplies 1/N of the batch; replicated: every rank holds all of it)."""
     import oracle
     from starr_b200 import ShardedSumTree
     oracle.build()
     C = oracle.c
-    n, m, q = 1 << 22, 1 << 16, 50000
+    n, m, q = 1 << 22, 1 << 16, 50000 // world * world
     n_local = n // world
     detail = {}
     ok = True
@@ -284,9 +292,16 @@ def parity_sharded(torch, dist, dev, world, rank):
             C.update_sumtree(idx.astype(np.intp), val, leaves, tree)
             want = np.zeros(q, np.intp)
             C.get_prefix_sum_idx(want, (tree[1] * u).astype(dt), leaves, tree)
-            sh.update_(torch.from_numpy(idx).to(dev), torch.from_numpy(val).to(dev))
-            got = sh.sample_uniform(torch.from_numpy(u).to(dev))
-            good = good and bool(np.array_equal(got.cpu().numpy(), want))
+            if layout == "slices":      # every rank supplies its 1/N of the same batch
+                ms, qs = m // world, q // world
+                sh.update_slices_(torch.from_numpy(idx[rank * ms:(rank + 1) * ms]).to(dev),
+                                  torch.from_numpy(val[rank * ms:(rank + 1) * ms]).to(dev))
+                got = sh.sample_slices(torch.from_numpy(u[rank * qs:(rank + 1) * qs]).to(dev))
+                good = good and bool(np.array_equal(got.cpu().numpy(), want[rank * qs:(rank + 1) * qs]))
+            else:
+                sh.update_(torch.from_numpy(idx).to(dev), torch.from_numpy(val).to(dev))
+                got = sh.sample_uniform(torch.from_numpy(u).to(dev))
+                good = good and bool(np.array_equal(got.cpu().numpy(), want))
         sh.poll()
         good = good and sh.gather_sumtree().cpu().numpy().tobytes() == tree.tobytes()
         good = good and sh.gather_leaves().cpu().numpy().tobytes() == leaves.tobytes()
@@ -297,7 +312,8 @@ def parity_sharded(torch, dist, dev, world, rank):
         sh.close()
         del sh
     torch.cuda.empty_cache()
-    return ok, {"leaves": n, "batches": 3, "updates_per_batch": m, "samples_per_batch": q, "checked_on": "every rank", **detail}
+    return ok, {"leaves": n, "batches": 3, "updates_per_batch": m, "samples_per_batch": q, "checked_on": "every rank",
+                "layout": layout, **detail}
 
 
 # --------------------------------------------------------------------------------------------
@@ -325,6 +341,7 @@ def run_ours(args):
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
+    layout = args.layout if world > 1 else "single"
     n_local = 1 << LOG2_LEAVES
     m_local = 1 << LOG2_BATCH
     n_global = n_local * world
@@ -339,7 +356,7 @@ def run_ours(args):
     # ---- sharded parity gate, before anything is timed -------------------------------------------
     par_sharded = None
     if world > 1:
-        ok, par_sharded = parity_sharded(torch, dist, dev, world, rank)
+        ok, par_sharded = parity_sharded(torch, dist, dev, world, rank, layout)
         if not ok:
             if rank == 0:
                 print(json.dumps({"metric": METRIC, "parity_sharded": False, "parity_sharded_detail": par_sharded}), flush=True)
@@ -358,7 +375,10 @@ def run_ours(args):
         else:
             from starr_b200 import ShardedSumTree
             t = ShardedSumTree(n_loc * world, torch.float32, local_leaves=leaves_dev)
-            t.reserve(m_res)
+            if layout == "slices":
+                t.reserve_slices(m_res // world, expected_local=m_res // world * 5 // 4)
+            else:
+                t.reserve(m_res)
         return t
 
     tree = build_tree(n_local, torch.from_numpy(leaves_host).to(dev), m_global)
@@ -366,9 +386,11 @@ def run_ours(args):
     # Batches are generated on the device with the same seed on every rank (replicated input, as a PER
     # learner broadcasts it): DISTINCT batches for every warm-up and timed step.
     gen = torch.Generator(device=dev)
-    gen.manual_seed(20260)
+    gen.manual_seed(20260 + (rank if layout == "slices" else 0))
 
     def gen_batch(n_tot, m_tot):
+        if layout == "slices":          # this rank's 1/N of the global batch (indices over the whole leaf range)
+            m_tot //= world
         return (torch.randint(0, n_tot, (m_tot,), generator=gen, device=dev, dtype=torch.int64),
                 torch.rand(m_tot, generator=gen, device=dev, dtype=torch.float32),
                 torch.rand(m_tot, generator=gen, device=dev, dtype=torch.float64))
@@ -379,12 +401,19 @@ def run_ours(args):
 
     def timed_leg(t, n_tot, m_tot, nsteps, nwarm):
         """W warm-up + exactly K timed steps on never-applied batches; returns per-rank times (ms)."""
-        per = m_tot * 20
+        m_mine = m_tot // world if layout == "slices" else m_tot
+        per = m_mine * 20
         distinct = max(2, min(nwarm + nsteps + 1, MAX_DISTINCT_BYTES // per))
         cycling = distinct < nwarm + nsteps + 1
         bat = [gen_batch(n_tot, m_tot) for _ in range(distinct)]
-        outb = torch.empty(m_tot, dtype=torch.int64, device=dev)
+        outb = torch.empty(m_mine, dtype=torch.int64, device=dev)
         s_plan = torch.cuda.Stream() if world > 1 else None
+        if layout == "slices":
+            upd, smp, mkplan = t.update_slices_, t.sample_slices, t.plan_update_slices
+        elif world > 1:
+            upd, smp, mkplan = t.update_, t.sample_uniform, t.plan_update
+        else:
+            upd, smp, mkplan = t.update_, t.sample_uniform, None
 
         def use(k):
             b = bat[k % distinct]
@@ -396,31 +425,31 @@ def run_ours(args):
 
         for w in range(nwarm):
             i, v, u = use(w)
-            t.update_(i, v)
-            t.sample_uniform(u, out=outb)
+            upd(i, v)
+            smp(u, out=outb)
             refresh(w)
         t.poll()
         barrier()
         counters(t)
         launches0 = int(_lib.lib().st_kernel_launches())
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * nsteps + 1)]
-        # Sharded runs plan ahead: owner / slot / compaction of batch k+1 (it reads nothing of the tree) is
-        # computed on a side stream while batch k is applied.  One plan per step inside the timed region.
-        plan = t.plan_update(*use(nwarm)[:2], stream=s_plan) if world > 1 else None
+        # Sharded runs plan ahead: owner / slot of batch k+1 and (slices layout) the exchange of its slices -- none of
+        # which reads the tree -- run on a side stream while batch k is applied.  One plan per step inside the timed region.
+        plan = mkplan(*use(nwarm)[:2], stream=s_plan) if world > 1 else None
         barrier()
         t_w0 = time.time()
         ev[0].record()
         for k in range(nsteps):
             i, v, u = use(nwarm + k)
             if world > 1:
-                t.update_(plan=plan)
+                upd(plan=plan)
                 ev[2 * k + 1].record()
                 if k + 1 < nsteps:
-                    plan = t.plan_update(*use(nwarm + k + 1)[:2], stream=s_plan)
+                    plan = mkplan(*use(nwarm + k + 1)[:2], stream=s_plan)
             else:
-                t.update_(i, v)
+                upd(i, v)
                 ev[2 * k + 1].record()
-            t.sample_uniform(u, out=outb)
+            smp(u, out=outb)
             ev[2 * k + 2].record()
             refresh(nwarm + k)
         barrier()
@@ -485,6 +514,72 @@ def run_ours(args):
                    "so copies of step k+1 / k-1 overlap the kernels of step k; timed with the host clock around the "
                    "blocking calls")
         del pins, outs
+    elif layout == "slices":
+        # Sharded, slices layout: every rank holds ITS 1/N of the batch in pinned host memory, uploads it (PCIe carries
+        # every byte once), hands it to update_slices_ / sample_slices as it is, and reads back its own indices.
+        pinned = [(torch.from_numpy(rng_e.integers(0, n_global, m_local).astype(np.int64)).pin_memory(),
+                   torch.from_numpy(rng_e.random(m_local, dtype=np.float32)).pin_memory(),
+                   torch.from_numpy(rng_e.random(m_local)).pin_memory()) for _ in range(e2e_distinct)]
+        host_out = torch.empty(m_local, dtype=torch.int64).pin_memory()
+        s_main = torch.cuda.current_stream()
+        s_in, s_out, s_plan = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
+        stage = [tuple(torch.empty_like(t, device=dev) for t in pinned[0]) for _ in range(2)]
+        obuf = [torch.empty(m_local, dtype=torch.int64, device=dev) for _ in range(2)]
+        ev_in = [torch.cuda.Event() for _ in range(2)]
+        ev_free = [torch.cuda.Event() for _ in range(2)]
+        ev_done = [torch.cuda.Event() for _ in range(2)]
+        ev_read = [torch.cuda.Event() for _ in range(2)]
+
+        def prefetch(first, k):
+            slot = k % 2
+            with torch.cuda.stream(s_in):
+                s_in.wait_event(ev_free[slot])
+                for dst, src in zip(stage[slot], pinned[(first + k) % e2e_distinct]):
+                    dst.copy_(src, non_blocking=True)
+                ev_in[slot].record(s_in)
+
+        def e2e_run(first, nsteps):
+            for slot in range(2):
+                ev_free[slot].record(s_main)
+                ev_read[slot].record(s_main)
+            prefetch(first, 0)
+            s_plan.wait_event(ev_in[0])
+            plan = tree.plan_update_slices(*stage[0][:2], stream=s_plan)
+            for k in range(nsteps):
+                slot = k % 2
+                if k + 1 < nsteps:
+                    prefetch(first, k + 1)
+                s_main.wait_event(ev_in[slot])
+                s_main.wait_event(ev_read[slot])
+                tree.update_slices_(plan=plan)
+                if k + 1 < nsteps:
+                    s_plan.wait_event(ev_in[(k + 1) % 2])
+                    plan = tree.plan_update_slices(*stage[(k + 1) % 2][:2], stream=s_plan)
+                tree.sample_slices(stage[slot][2], out=obuf[slot])
+                ev_free[slot].record(s_main)
+                ev_done[slot].record(s_main)
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(ev_done[slot])
+                    host_out.copy_(obuf[slot], non_blocking=True)
+                    ev_read[slot].record(s_out)
+            s_main.wait_stream(s_out)
+
+        e2e_run(0, 2)
+        barrier()
+        counters(tree)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_w0 = time.time()
+        e0.record()
+        e2e_run(2, steps)
+        e1.record()
+        barrier()
+        windows.append((t_w0, time.time()))
+        e2e_ms = e0.elapsed_time(e1)
+        cnt_e2e = counters(tree)
+        e2e_how = ("pinned host buffers; every rank uploads its 1/N of the batch, passes it to update_slices_ / sample_slices and "
+                   "reads back its own sampled indices (byte counts are totals over ranks); H2D of step k+1 and D2H of step k-1 "
+                   "overlap step k")
+        del pinned, stage, obuf
     else:
         # Sharded: every rank holds ITS 1/N slice of the batch in pinned host memory, uploads only that (PCIe
         # carries every byte once), the slices are all-gathered over NVLink, and every rank reads back its slice.
@@ -573,6 +668,7 @@ def run_ours(args):
     # ---- BASELINE config #4 as stated: a FIXED 2^30 leaves over the N GPUs, 2^20 + 2^20 per step -------------
     fixed = None
     if world > 1 and not args.no_fixed:
+        tree.close()        # collective: the exchange areas are released on every rank together
         del tree
         torch.cuda.empty_cache()
         nl = (1 << 30) // world
@@ -624,7 +720,7 @@ def run_ours(args):
             "metric": METRIC, "value": ops_per_step * steps / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": steps, "warmup": warmup, "ms_per_step": total_ms / steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(world),
+            "config": workload_config(world, layout),
             "updates_per_s": upd_rate, "samples_per_s": smp_rate,
             "update_ms_per_step": upd_ms / steps, "sample_ms_per_step": smp_ms / steps,
             "zero_delta_frac": cnt_dev["zero_delta"] / max(1, cnt_dev["updates"]),
@@ -674,6 +770,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg and the in-run parity gate (N=1)")
     ap.add_argument("--no-fixed", action="store_true", help="skip the fixed-2^30-leaf leg (N>1)")
+    ap.add_argument("--layout", default=os.environ.get("ST_BENCH_LAYOUT", "slices"), choices=["slices", "replicated"],
+                    help="N>1: 'slices' = every rank supplies 1/N of each batch (default), 'replicated' = every rank holds all of it")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -199,9 +199,10 @@ class ShardedSumTree:
         holder = type("_Region", (), {"__cuda_array_interface__": iface})()
         return torch.as_tensor(holder, device=self.device)[:nbytes].view(dtype)
 
-    def phase_times(self, next_batch, reps: int = 10):
+    def phase_times(self, next_batch, reps: int = 10, slices: bool = False):
         """Diagnostics (tools/sharded_breakdown.py): median device time in microseconds of every
-        phase of ``update_`` and ``sample_uniform``; ``next_batch()`` returns ``(idx, vals, u)``."""
+        phase of ``update_`` and ``sample_uniform`` (``slices``: of ``update_slices_`` and ``sample_slices``);
+        ``next_batch()`` returns ``(idx, vals, u)``."""
         import statistics
         acc: dict[str, list[float]] = {}
         for _ in range(reps):
@@ -210,9 +211,14 @@ class ShardedSumTree:
             torch.cuda.synchronize()
             self._marks = []
             self._mark("start")
-            self.update_(idx, vals)
-            self._mark("update: done")
-            self.sample_uniform(u)
+            if slices:
+                self.update_slices_(idx, vals)
+                self._mark("update: done")
+                self.sample_slices(u)
+            else:
+                self.update_(idx, vals)
+                self._mark("update: done")
+                self.sample_uniform(u)
             torch.cuda.synchronize()
             marks, self._marks = self._marks, None
             for (_, a), (label, b) in zip(marks, marks[1:]):

@@ -47,6 +47,22 @@ def _worker(rank, world, port, dt_name, logn, q, peer=True):
             ok &= bool(np.array_equal(got, want))
         st.poll()
         ok &= (st._peer is not None) == bool(peer)
+        # slices layout: every rank supplies its 1/world of the same batches (without peer memory the slices are
+        # all-gathered and applied as a replicated batch)
+        for ms, nq in ((1, 2), (3000, 1000), (1 << 16, 20_000)):
+            idx = rng.integers(0, n, ms * world).astype(np.int64)
+            vals = draw(ms * world)
+            oracle.c.update_sumtree(idx.astype(np.intp), vals, ref_leaves, ref_tree)
+            st.update_slices_(torch.from_numpy(idx[rank * ms:(rank + 1) * ms]).to(dev),
+                              torch.from_numpy(vals[rank * ms:(rank + 1) * ms]).to(dev))
+            ok &= st.gather_sumtree().cpu().numpy().tobytes() == ref_tree.tobytes()
+            ok &= st.gather_leaves().cpu().numpy().tobytes() == ref_leaves.tobytes()
+            u = rng.random(nq * world)
+            want = np.zeros(u.size, np.intp)
+            oracle.c.get_prefix_sum_idx(want, (ref_tree[1] * u).astype(dt), ref_leaves, ref_tree)
+            got = st.sample_slices(torch.from_numpy(u[rank * nq:(rank + 1) * nq]).to(dev)).cpu().numpy()
+            ok &= bool(np.array_equal(got, want[rank * nq:(rank + 1) * nq]))
+        st.poll()
         st.close()
         q.put((rank, bool(ok)))
     finally:

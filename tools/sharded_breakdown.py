@@ -13,6 +13,7 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 os.environ.setdefault("NCCL_DEBUG", "WARN")
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 
 def main():
@@ -29,7 +30,8 @@ def main():
     n = n_local * world
     leaves = torch.from_numpy(np.random.default_rng(1000 + rank).random(n_local, dtype=np.float32)).to(dev)
     tree = ShardedSumTree(n, torch.float32, local_leaves=leaves)
-    tree.reserve(m)
+    if os.environ.get("ST_LAYOUT", "slices") != "slices":
+        tree.reserve(m)
     rng = np.random.default_rng(0)
     batches = [(torch.from_numpy(rng.integers(0, n, m)).to(dev),
                 torch.from_numpy(rng.random(m, dtype=np.float32)).to(dev),
@@ -59,9 +61,27 @@ def main():
         k[0] += 1
         return batches[k[0] % len(batches)]
 
-    timed("update_ (whole)", lambda: tree.update_(*nxt()[:2]))
-    timed("sample_uniform (whole)", lambda: tree.sample_uniform(nxt()[2]))
-    if hasattr(tree, "phase_times"):
+    if os.environ.get("ST_LAYOUT", "slices") == "slices":
+        # slices layout: every rank supplies its own 1/N of the batch (ShardedSumTree.update_slices_ / sample_slices)
+        ml = 1 << lg_m
+        tree.reserve_slices(ml, expected_local=ml * 5 // 4)
+        rs = np.random.default_rng(100 + rank)
+        sl = [(torch.from_numpy(rs.integers(0, n, ml)).to(dev), torch.from_numpy(rs.random(ml, dtype=np.float32)).to(dev),
+               torch.from_numpy(rs.random(ml)).to(dev)) for _ in range(6)]
+        ks = [0]
+
+        def nxs():
+            ks[0] += 1
+            return sl[ks[0] % len(sl)]
+        timed("update_slices_ (whole)", lambda: tree.update_slices_(*nxs()[:2]))
+        timed("sample_slices (whole)", lambda: tree.sample_slices(nxs()[2]))
+        for name, us in tree.phase_times(nxs, reps=10, slices=True):
+            t = torch.tensor([us], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            rows.append(("  phase: " + name, float(t)))
+    else:
+        timed("update_ (whole)", lambda: tree.update_(*nxt()[:2]))
+        timed("sample_uniform (whole)", lambda: tree.sample_uniform(nxt()[2]))
         for name, us in tree.phase_times(nxt, reps=10):
             t = torch.tensor([us], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
