@@ -69,6 +69,20 @@ def _worker(rank, world, port, dt_name, n, q):
         st.update_(plan=plan)
         ok &= st.gather_sumtree().numpy().tobytes() == ref_tree.tobytes()
         ok &= float(st.total()) == float(ref_tree[1])
+        # slices layout (every rank supplies its 1/world of the batch); without peer memory -- here -- the slices are
+        # all-gathered and applied as one replicated batch in rank order
+        for ms, nq in ((1, 1), (300, 50)):
+            idx = rng.integers(0, n, ms * world).astype(np.int64)
+            vals = draw(ms * world)
+            oracle.c.update_sumtree(idx.astype(np.intp), vals, ref_leaves, ref_tree)
+            st.update_slices_(torch.from_numpy(idx[rank * ms:(rank + 1) * ms]), torch.from_numpy(vals[rank * ms:(rank + 1) * ms]))
+            ok &= st.gather_sumtree().numpy().tobytes() == ref_tree.tobytes()
+            ok &= st.gather_leaves().numpy().tobytes() == ref_leaves.tobytes()
+            u = rng.random(nq * world)
+            want = np.zeros(u.size, np.intp)
+            oracle.c.get_prefix_sum_idx(want, (ref_tree[1] * u).astype(dt), ref_leaves, ref_tree)
+            got = st.sample_slices(torch.from_numpy(u[rank * nq:(rank + 1) * nq])).numpy()
+            ok &= bool(np.array_equal(got, want[rank * nq:(rank + 1) * nq]))
         try:
             st.update_(torch.tensor([0]), torch.from_numpy(np.array([1], dt)) * -1 if dt.kind != "u" else torch.tensor([n]), check=True)
             raised = dt.kind == "u"
