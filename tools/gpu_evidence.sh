@@ -17,7 +17,7 @@ python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/plain_a.json
 echo "launch list rc=$?"
 python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/plain_b.json 2>/dev/null &&
   ncu --set full --clock-control none --import-source on \
-      -k regex:"partition_levels|retire_kernel|search_kernel|fold_huge_maps|fold_huge_apply|fold_scan|leaf_pass|build_pass" \
-      -s 11 -c 9 -f -o gpurun_out/prof_final python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_b.log 2>&1
+      -k regex:"hy_hist|hy_scan|hy_scatter|hy_segment|deep_red|retire_kernel|search_kernel|fold_huge_maps|fold_huge_apply|fold_scan|leaf_pass|build_pass|make_keys|RadixSortOnesweep" \
+      -c 24 -f -o gpurun_out/prof_final python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_b.log 2>&1
 echo "full capture rc=$?"
 python tools/config_bench.py > gpurun_out/configs_final.md 2> gpurun_out/configs_final.err; echo "per-config table rc=$?"
