@@ -25,6 +25,7 @@ Per update (all stream-ordered, one host read of the count matrix):
 from __future__ import annotations
 
 import os
+import weakref
 
 import torch
 
@@ -44,7 +45,9 @@ class SlicesExchange:
     CH_UROW, CH_UDATA, CH_DBACK, CH_RECS, CH_ROOTS, CH_SROW, CH_SDATA, CH_SBACK = range(8)
 
     def __init__(self, tree):
-        self.t = tree                       # the ShardedSumTree
+        # weak: the tree owns this object; a reference cycle would leave the trees' device memory to the cyclic collector,
+        # whose cudaFree (a device-wide wait) could then land in the middle of somebody's step
+        self.t = weakref.proxy(tree)
         self.area = None
         self.cap = 0
         self._pstep = self._ustep = self._sstep = 0

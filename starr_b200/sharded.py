@@ -186,6 +186,7 @@ class ShardedSumTree:
         object is collected, which is only safe once every rank has finished with the tree."""
         if self._slices is not None:
             self._slices.close()
+            self._slices = None
         if self._peer is not None:
             torch.cuda.synchronize(self.device)
             dist.barrier(group=self.group)

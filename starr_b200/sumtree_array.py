@@ -274,9 +274,26 @@ class SumTreeArray(np.ndarray):
     def put(self, indices, values):
         """Set ``self[indices] = values``; ``values`` cycles over the selected elements in
         C order (reference :229-233 -- not NumPy broadcasting)."""
-        flat = np.ascontiguousarray(self._indices[indices]).ravel()
+        flat = self._flat_ids(indices)
         vals = np.ascontiguousarray(values, dtype=self._state.leaves.dtype).ravel()
         self._state.update(flat, vals)
+
+    def _flat_ids(self, indices) -> np.ndarray:
+        """Flat leaf ids selected by an index expression, in C order (reference :231, ``self._indices[indices]``).
+        A 1-D array indexed by an integer array needs no lookup table (the ids ARE the indices, negatives wrapped):
+        that is the PER case, and it skips a random gather from an 8-byte-per-leaf arange.  Everything else -- and
+        any out-of-range index, so that NumPy raises its own IndexError -- goes through the table."""
+        if self.ndim == 1 and isinstance(indices, np.ndarray) and indices.dtype.kind in "iu" and indices.ndim >= 1:
+            n = self.shape[0]
+            ids = indices.astype(np.intp, copy=False).ravel()
+            if ids.size == 0:
+                return np.ascontiguousarray(ids)
+            lo, hi = int(ids.min()), int(ids.max())
+            if -n <= lo and hi < n:
+                if lo < 0:
+                    ids = np.where(ids < 0, ids + n, ids)
+                return np.ascontiguousarray(ids)
+        return np.ascontiguousarray(self._indices[indices]).ravel()
 
     @_guarded
     def fill(self, *args, **kwargs):

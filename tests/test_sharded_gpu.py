@@ -274,6 +274,9 @@ def test_sharded_cuda_path_on_one_gpu(world, dt_name, peer, monkeypatch):
         torch.cuda.synchronize()
         del warm
 
+    import gc
+    gc.collect()   # device memory of earlier tests is freed NOW (cudaFree waits for the whole device), not under a spinning wait kernel
+
     def rank_body(r):
         torch.cuda.set_device(0)
         if peer:        # a spinning wait kernel must not sit in front of another rank's signal on a shared stream
@@ -377,6 +380,9 @@ def test_sharded_slices_on_one_gpu(world, dt_name, monkeypatch):
     warm.poll()
     torch.cuda.synchronize()
     del warm
+
+    import gc
+    gc.collect()   # device memory of earlier tests is freed NOW (cudaFree waits for the whole device), not under a spinning wait kernel
 
     def rank_body(r):
         torch.cuda.set_device(0)

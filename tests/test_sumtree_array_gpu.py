@@ -103,6 +103,29 @@ def test_set_and_put_forms(STA):
     assert x.tolist()[1:3] == [[1, 2, 1], [2, 1, 2]]
 
 
+def test_integer_array_indices_fast_path(STA):
+    """1-D array indexed by an integer ndarray: the flat ids are the indices themselves (no lookup table); same result
+    as NumPy's own assignment semantics with the reference's value cycling -- negatives, 2-D index arrays, duplicates
+    (last write wins), unsigned dtypes, and NumPy's IndexError for anything out of range (nothing modified)."""
+    rng = np.random.default_rng(4)
+    base = rng.integers(0, 50, 1000).astype(np.float32)
+    x = STA(base.copy())
+    want = base.copy()
+    for idx in (np.array([3, -1, 7, -1000, 999]), rng.integers(-1000, 1000, (4, 25)), np.array([5, 5, 5]),
+                np.array([1, 2, 3], dtype=np.uint8), np.array([], dtype=np.int64), np.array([7], dtype=np.int32)):
+        vals = rng.integers(0, 50, max(idx.size, 1)).astype(np.float32)
+        x[idx] = vals
+        for j, i in enumerate(idx.ravel()):          # the reference's loop (pyx:41-49): in order, values cycle
+            want[int(i)] = vals[j % vals.size]
+        assert x.tolist() == want.tolist()
+        assert float(x.sum()) == float(np.asarray(x._sumtree)[1])
+    before = x.tolist()
+    for bad in (np.array([0, 1000]), np.array([-1001])):
+        with pytest.raises(IndexError):
+            x[bad] = 1.0
+        assert x.tolist() == before
+
+
 def test_get_returns_plain_arrays(STA):
     x = STA(np.array([0, 1, 2, 3, 4, 5]).astype("int32").reshape((3, 2)))
     y = x[1]
