@@ -318,6 +318,22 @@ ST_API int st_top_fold_maps_slice_device(st_tree *t, const uint8_t *leaf_dev, co
 ST_API int st_slices_table(st_peer *p, int parity, int64_t d_offset, int64_t leaf_offset);
 ST_API int st_top_fold_apply_slices_device(st_tree *t, st_peer *p, int parity, int64_t span, int64_t m_slice,
                                     const void *recs_dev, void *stream);
+/* sample() of the slices layout without a count matrix (one flag round trip each way):
+ *   st_route_push_device            routes this rank's own uniforms on the top tree and stores every left-over prefix,
+ *                                   with its slice position, straight into the owner's receive region of this source
+ *                                   (element [rank * cap + k], k from a local counter per owner; cnt_dev: world counters)
+ *   st_slices_counts                the counters go to the owners (cnt_offset + 4 * rank) and into this rank's own buffer
+ *                                   (sent_offset + 4 * owner), then the release flag (channel, value)
+ *   st_search_segments_push_device  the local descent over the world segments that arrived; result k of source r's
+ *                                   segment is stored as the pair (slice position, local leaf) at element
+ *                                   [rank * cap + k] of r's back region -- consecutive queries, consecutive stores
+ *   st_peer_scatter_pairs           (above) turns the pairs that came back into global indices in slice order */
+ST_API int st_route_push_device(const st_tree *top, const double *u_dev, int64_t m, st_peer *p, int64_t resid_offset,
+                         int64_t pos_offset, int64_t cap, uint32_t *cnt_dev, void *stream);
+ST_API int st_slices_counts(st_peer *p, const uint32_t *cnt_dev, int64_t cnt_offset, int64_t sent_offset, int channel,
+                     unsigned int value, void *stream);
+ST_API int st_search_segments_push_device(const st_tree *t, st_peer *p, int64_t resid_offset, int64_t pos_offset,
+                                   int64_t cnt_offset, int64_t cap, int64_t back_offset, void *stream);
 /* st_search_counted_device with 32-bit local leaves as the result (what travels back to the querying rank) */
 ST_API int st_search_leaf32_device(const st_tree *t, const void *vals_dev, int64_t m_max, const uint32_t *m_dev,
                             int32_t *out_dev, void *stream);

@@ -155,6 +155,9 @@ _SIGNATURES = {
     "st_top_fold_maps_slice_device": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
     "st_slices_table": (c_int, [c_void_p, c_int, c_int64, c_int64]),
     "st_top_fold_apply_slices_device": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p]),
+    "st_route_push_device": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
+    "st_slices_counts": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, ctypes.c_uint, c_void_p]),
+    "st_search_segments_push_device": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p]),
     "st_search_leaf32_device": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "st_sample_weights_device": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "st_per_step_device": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p,
@@ -493,6 +496,16 @@ class TreeHandle:
         self._pcheck(lib().st_top_fold_apply_slices_device(self.ptr, peer.ptr, int(parity), int(span), int(m_slice),
                                                            c_void_p(recs_ptr), c_void_p(stream)))
 
+    def route_push_device(self, u_ptr: int, m: int, peer: "PeerArea", resid_offset: int, pos_offset: int, cap: int,
+                          cnt_ptr: int, stream: int = 0) -> None:
+        self._pcheck(lib().st_route_push_device(self.ptr, c_void_p(u_ptr), int(m), peer.ptr, int(resid_offset), int(pos_offset),
+                                                int(cap), c_void_p(cnt_ptr), c_void_p(stream)))
+
+    def search_segments_push_device(self, peer: "PeerArea", resid_offset: int, pos_offset: int, cnt_offset: int, cap: int,
+                                    back_offset: int, stream: int = 0) -> None:
+        self._pcheck(lib().st_search_segments_push_device(self.ptr, peer.ptr, int(resid_offset), int(pos_offset), int(cnt_offset),
+                                                          int(cap), int(back_offset), c_void_p(stream)))
+
     def search_leaf32_device(self, vals_ptr: int, m_max: int, m_dev_ptr: int, out_ptr: int, stream: int = 0) -> None:
         self._pcheck(lib().st_search_leaf32_device(self.ptr, c_void_p(vals_ptr), int(m_max), c_void_p(m_dev_ptr),
                                                    c_void_p(out_ptr), c_void_p(stream)))
@@ -698,6 +711,10 @@ class PeerArea:
         self._check(lib().st_slices_unpermute(self.ptr, int(matrix_offset), c_void_p(shard_ptr), c_void_p(slot_ptr), int(m),
                                               int(ret_offset), int(esize), int(leaves_per_shard), c_void_p(out_ptr),
                                               int(shard_copy_offset), c_void_p(stream)))
+
+    def slices_counts(self, cnt_ptr: int, cnt_offset: int, sent_offset: int, channel: int, value: int, stream: int = 0) -> None:
+        self._check(lib().st_slices_counts(self.ptr, c_void_p(cnt_ptr), int(cnt_offset), int(sent_offset), int(channel),
+                                           int(value) & 0xffffffff, c_void_p(stream)))
 
     def slices_table(self, parity: int, d_offset: int, leaf_offset: int) -> None:
         self._check(lib().st_slices_table(self.ptr, int(parity), int(d_offset), int(leaf_offset)))

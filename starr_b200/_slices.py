@@ -57,6 +57,9 @@ class SlicesExchange:
         # beside them (A/B timing; and the thread-rank test at 8 ranks, where 8 x 3 streams with spinning wait kernels
         # would share the device's hardware queues)
         self.serial = os.environ.get("STARR_B200_SLICES_SERIAL", "0") == "1"
+        # STARR_B200_SLICES_SAMPLE=matrix: the first version of sample (stable partition + count matrix, three flag round
+        # trips) instead of the direct push (two); A/B timing only
+        self.sample_matrix = os.environ.get("STARR_B200_SLICES_SAMPLE", "push") == "matrix"
 
     # ---- exchange area ------------------------------------------------------------------------------------------
     def _layout(self, cap: int) -> dict:
@@ -71,6 +74,8 @@ class SlicesExchange:
             "dback": al(cap * es), "dslice": al(span * es), "shard": al(span),
             "roots": al(w * es), "recs": al(w * (span // 1024) * (w - 1) * rb),
             "recv_q": al(w * cap * es), "back_q": al(cap * 4),
+            # sample without a count matrix: one receive region per source rank, results come back as pairs
+            "rq_resid": al(w * cap * es), "rq_pos": al(w * cap * 4), "rq_cnt": 256, "sent_cnt": 256, "back": al(w * cap * 8),
         }
         off, lay = 0, {}
         for name, size in sizes.items():
@@ -111,6 +116,7 @@ class SlicesExchange:
         self.qowner, self.qresid = mk(cap, torch.int64), mk(cap, t.dtype)
         self.qrow = torch.zeros(w + 1, dtype=torch.int32, device=dev)
         self.qtotal = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.qcnt = torch.zeros(w, dtype=torch.int32, device=dev)
         self.found = mk(w * cap, torch.int32)
         self.rank_pos = torch.tensor([t.rank], dtype=torch.int32, device=dev)
         self._side = self._side or torch.cuda.Stream(device=dev)
@@ -243,6 +249,34 @@ class SlicesExchange:
 
     # ---- sample -------------------------------------------------------------------------------------------------
     def sample(self, u: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+        if self.sample_matrix:
+            return self._sample_matrix(u, out)
+        t = self.t
+        m = u.numel()
+        self.ensure(m)
+        area, lay, cap = self.area, self.lay, self.cap
+        self._sstep += 1
+        p, par = self._sstep, self._sstep & 1
+        s = torch.cuda.current_stream().cuda_stream
+        # every prefix goes straight into its owner's receive region of this source, the counts follow with the flag
+        t.top.handle.route_push_device(u.data_ptr(), m, area, lay["rq_resid"][par], lay["rq_pos"][par], cap, self.qcnt.data_ptr(), s)
+        area.slices_counts(self.qcnt.data_ptr(), lay["rq_cnt"][par], lay["sent_cnt"][par], self.CH_SDATA, p, s)
+        t._mark("sample: route + prefixes to their owners")
+        area.wait(self.CH_SDATA, p, s)
+        t._mark("sample: wait for every rank's prefixes")
+        # local descent over the segments that arrived; (slice position, leaf) pairs go straight back to their sources
+        t.local.handle.search_segments_push_device(area, lay["rq_resid"][par], lay["rq_pos"][par], lay["rq_cnt"][par], cap,
+                                                   lay["back"][par], s)
+        area.signal(self.CH_SBACK, p, s)
+        t._mark("sample: local search (+ results to the querying ranks)")
+        area.wait(self.CH_SBACK, p, s)
+        t._mark("sample: wait for every rank's results")
+        if m:
+            area.scatter_pairs(lay["back"][par], cap * 8, lay["sent_cnt"][par], t.n_local, out.data_ptr(), m, s)
+        t._mark("sample: indices to slice order")
+        return out
+
+    def _sample_matrix(self, u: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
         t = self.t
         m = u.numel()
         self.ensure(m)

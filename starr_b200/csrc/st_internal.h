@@ -95,6 +95,11 @@ struct search_push {
     int64_t index_offset = 0;
     int32_t *pairs = nullptr;      // != nullptr: result i goes to pairs[2i] = pos[i], pairs[2i+1] = local leaf (no push)
     int32_t *leaf32 = nullptr;     // != nullptr: result i goes to leaf32[i] as a 32-bit local leaf (slices layout)
+    // segmented input (slices layout, sample): the queries are n segments of seg_cnt[r] elements, segment r at
+    // in[r * seg_stride ..] / pos[r * seg_stride ..]; result k of segment r is stored as the pair (pos, local leaf) at
+    // element k of base[r] (peer memory: consecutive queries of a segment are consecutive 8-byte stores)
+    const unsigned int *seg_cnt = nullptr;
+    int64_t seg_stride = 0;
 };
 
 // process-wide count of kernels of THIS library that were launched (bench.py's gpu_launches)

@@ -300,6 +300,71 @@ __global__ void __launch_bounds__(256) slices_unpermute_kernel(const unsigned in
     }
 }
 
+// Slices layout, sample: route this rank's OWN queries on the top tree and push every left-over prefix straight into
+// its owner's receive region (one region per source rank, so the append position is a local counter; any order: the
+// slice position travels with the prefix).  Lanes of a warp that go to the same owner take consecutive places, so the
+// remote stores of a warp are a few full-width runs.  Region of source r on the owner: element [r * cap + k].
+template <typename T>
+__global__ void __launch_bounds__(256) route_push_kernel(const T *__restrict__ H, int nleaves, int depth,
+                                                         const double *__restrict__ u, int64_t m, int rank, peer_ptrs pp,
+                                                         size_t resid_off, size_t pos_off, int64_t cap,
+                                                         unsigned int *__restrict__ cnt)
+{
+    __shared__ T top[2 * PEER_MAX];
+    for (int i = threadIdx.x; i < 2 * nleaves; i += blockDim.x) top[i] = H[i];
+    __syncthreads();
+    const T root = top[1];
+    const int lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t rounds = (m + stride - 1) / stride;
+    for (int64_t r = 0; r < rounds; ++r) {
+        const int64_t i = r * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        int q = -1;
+        T p = T(0);
+        if (i < m) {
+            // (root * u).astype(dtype), sumtree_array.py:420
+            if constexpr (sizeof(T) == 4 && is_float_t<T>::value) p = __double2float_rn(__dmul_rn((double)root, u[i]));
+            else if constexpr (is_float_t<T>::value) p = __dmul_rn(root, u[i]);
+            else p = (T)__dmul_rn((double)root, u[i]);
+            uint32_t h = 1;
+            for (int lev = 0; lev < depth; ++lev) {
+                const T lv = top[2 * h];
+                if (p >= lv) { p = t_sub<T>(p, lv); h = 2 * h + 1; } else { h = 2 * h; }
+            }
+            q = (int)h - nleaves;
+        }
+        const unsigned int peers = __match_any_sync(0xffffffffu, q);
+        if (q >= 0) {
+            const int leader = __ffs(peers) - 1;
+            unsigned int base = 0;
+            if (lane == leader) base = atomicAdd(cnt + q, (unsigned int)__popc(peers));
+            base = __shfl_sync(peers, base, leader);
+            const size_t at = (size_t)rank * (size_t)cap + base + __popc(peers & ((1u << lane) - 1u));
+            reinterpret_cast<T *>(pp.base[q] + resid_off)[at] = p;
+            reinterpret_cast<int32_t *>(pp.base[q] + pos_off)[at] = (int32_t)i;
+        }
+    }
+}
+
+// the counts of what route_push_kernel appended go to the owners (cnt_off + 4 * rank on owner q) and, for the scatter
+// of the results, into this rank's own buffer (sent_off + 4 * q); then the release flag
+__global__ void slices_counts_kernel(peer_ptrs pp, int rank, const unsigned int *__restrict__ cnt, size_t cnt_off,
+                                     size_t sent_off, int channel, unsigned int value)
+{
+    const int q = threadIdx.x;
+    if (q < pp.n) {
+        const unsigned int c = cnt[q];
+        reinterpret_cast<unsigned int *>(pp.base[q] + cnt_off)[rank] = c;
+        reinterpret_cast<unsigned int *>(pp.base[rank] + sent_off)[q] = c;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (q < pp.n) {
+        unsigned int *f = reinterpret_cast<unsigned int *>(pp.base[q]) + channel * PEER_MAX + rank;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(value) : "memory");
+    }
+}
+
 // Top-tree routing of a replicated query batch (the first g levels of the reference descent,
 // pyx:96-113, on the replicated top tree) fused with the selection of this rank's queries:
 // the queries whose descent ends in top leaf `rank` are appended (any order: every result is
@@ -751,6 +816,62 @@ int st_search_leaf32_device(const st_tree *t, const void *vals_dev, int64_t m_ma
     st::search_push push;
     push.leaf32 = out_dev;
     PCU(st::launch_search(t, vals_dev, m_max, nullptr, (cudaStream_t)stream, m_dev, &push));
+    return ST_OK;
+}
+
+int st_route_push_device(const st_tree *top, const double *u_dev, int64_t m, st_peer *p, int64_t resid_offset, int64_t pos_offset,
+                         int64_t cap, uint32_t *cnt_dev, void *stream)
+{
+    if (!top || !p || m < 0 || m > cap || cap > 0x7fffffffLL || !cnt_dev || (m > 0 && !u_dev) || top->n != p->world ||
+        !region_ok(p, resid_offset, (int64_t)p->world * cap * top->esize, 8) || !region_ok(p, pos_offset, (int64_t)p->world * cap * 4, 8))
+        return pfail(ST_ERR_ARG, "st_route_push_device: bad argument");
+    if (top->n > st::PEER_MAX || (top->n & (top->n - 1))) return pfail(ST_ERR_ARG, "st_route_push_device: not a top tree");
+    dev_guard g(top->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    PCU(cudaMemsetAsync(cnt_dev, 0, sizeof(unsigned int) * p->world, s));
+    if (m == 0) return ST_OK;
+    ST_DISPATCH(top->dtype, {
+        ++st::g_kernel_launches;
+        st::route_push_kernel<T><<<st::grid_for(m, 256, (int64_t)top->sm_count * 8), 256, 0, s>>>(
+            (const T *)top->heap, (int)top->n, top->depth, u_dev, m, p->rank, p->ptrs, st::PEER_FLAG_BYTES + (size_t)resid_offset,
+            st::PEER_FLAG_BYTES + (size_t)pos_offset, cap, cnt_dev);
+    });
+    PCU(cudaGetLastError());
+    return ST_OK;
+}
+
+int st_slices_counts(st_peer *p, const uint32_t *cnt_dev, int64_t cnt_offset, int64_t sent_offset, int channel, unsigned int value,
+                     void *stream)
+{
+    if (!p || !cnt_dev || channel < 0 || channel >= st::PEER_CHANNELS || !region_ok(p, cnt_offset, 4 * p->world, 4) ||
+        !region_ok(p, sent_offset, 4 * p->world, 4))
+        return pfail(ST_ERR_ARG, "st_slices_counts: bad argument");
+    dev_guard g(p->device);
+    ++st::g_kernel_launches;
+    st::slices_counts_kernel<<<1, st::PEER_MAX, 0, (cudaStream_t)stream>>>(p->ptrs, p->rank, cnt_dev, st::PEER_FLAG_BYTES + (size_t)cnt_offset,
+                                                                          st::PEER_FLAG_BYTES + (size_t)sent_offset, channel, value);
+    PCU(cudaGetLastError());
+    return ST_OK;
+}
+
+int st_search_segments_push_device(const st_tree *t, st_peer *p, int64_t resid_offset, int64_t pos_offset, int64_t cnt_offset,
+                                   int64_t cap, int64_t back_offset, void *stream)
+{
+    if (!t || !p || cap <= 0 || cap > 0x7fffffffLL || !region_ok(p, resid_offset, (int64_t)p->world * cap * t->esize, 8) ||
+        !region_ok(p, pos_offset, (int64_t)p->world * cap * 4, 8) || !region_ok(p, cnt_offset, 4 * p->world, 4) ||
+        !region_ok(p, back_offset, (int64_t)p->world * cap * 8, 8))
+        return pfail(ST_ERR_ARG, "st_search_segments_push_device: bad argument");
+    dev_guard g(t->device);
+    st::search_push push;
+    push.n = p->world;
+    // result k of source r's segment goes to r's back region of THIS rank: [rank * cap + k] pairs of (slice position, leaf)
+    for (int q = 0; q < p->world; ++q)
+        push.base[q] = p->ptrs.base[q] + st::PEER_FLAG_BYTES + back_offset + (size_t)p->rank * (size_t)cap * 8;
+    push.pos = reinterpret_cast<const int32_t *>(p->local + st::PEER_FLAG_BYTES + pos_offset);
+    push.seg_cnt = reinterpret_cast<const unsigned int *>(p->local + st::PEER_FLAG_BYTES + cnt_offset);
+    push.seg_stride = cap;
+    PCU(st::launch_search(t, p->local + st::PEER_FLAG_BYTES + resid_offset, (int64_t)p->world * cap, nullptr, (cudaStream_t)stream,
+                          nullptr, &push));
     return ST_OK;
 }
 

@@ -338,6 +338,22 @@ search_kernel(const T *__restrict__ H, uint32_t n, int depth, const void *__rest
         const int64_t md = (int64_t)*m_dev;
         if (md < m) m = md;
     }
+    // segmented input (search_push::seg_cnt): query i is element i - s_seg[r] of the segment r with s_seg[r] <= i < s_seg[r + 1]
+    __shared__ unsigned int s_seg[65];
+    if (push.seg_cnt) {
+        if (threadIdx.x == 0) {
+            unsigned int run = 0;
+            for (int r = 0; r < push.n; ++r) { s_seg[r] = run; run += push.seg_cnt[r]; }
+            s_seg[push.n] = run;
+        }
+        __syncthreads();
+        m = (int64_t)s_seg[push.n];
+    }
+    auto seg_of = [&](int64_t i, int &r) -> int64_t {   // element index inside the strided segment layout
+        r = 0;
+        while (i >= (int64_t)s_seg[r + 1]) ++r;
+        return (int64_t)r * push.seg_stride + (i - (int64_t)s_seg[r]);
+    };
     extern __shared__ __align__(128) unsigned char smem_raw[];
     T *top = reinterpret_cast<T *>(smem_raw);
     __shared__ __align__(8) uint64_t bar;
@@ -359,8 +375,14 @@ search_kernel(const T *__restrict__ H, uint32_t n, int depth, const void *__rest
             h[q] = 1;
             p[q] = T(0);
             if (i < m) {
-                if constexpr (UNIFORM) p[q] = scale_uniform<T>(root, __ldg((const double *)in + i));
-                else p[q] = __ldg((const T *)in + i);
+                if constexpr (UNIFORM) {
+                    p[q] = scale_uniform<T>(root, __ldg((const double *)in + i));
+                } else if (push.seg_cnt) {
+                    int r;
+                    p[q] = __ldcg((const T *)in + seg_of(i, r));   // written by a peer a moment ago: not through the read-only path
+                } else {
+                    p[q] = __ldg((const T *)in + i);
+                }
             } else {
                 h[q] = n;  // inactive: already "at a leaf"
             }
@@ -438,7 +460,12 @@ search_kernel(const T *__restrict__ H, uint32_t n, int depth, const void *__rest
         for (int q = 0; q < SEARCH_Q; ++q) {
             const int64_t i = base + threadIdx.x + (int64_t)q * SEARCH_THREADS;
             if (i < m) {
-                if (push.leaf32) {
+                if (push.seg_cnt) {
+                    int r;
+                    const int64_t e = seg_of(i, r);
+                    reinterpret_cast<int2 *>(push.base[r])[e - (int64_t)r * push.seg_stride] =
+                        make_int2(__ldcg(push.pos + e), (int)(h[q] - n));
+                } else if (push.leaf32) {
                     push.leaf32[i] = (int32_t)(h[q] - n);
                 } else if (push.pairs) {
                     // sharded sample, coalesced exchange: (batch position, local leaf) in this rank's own order
