@@ -311,38 +311,64 @@ __global__ void __launch_bounds__(256) route_push_kernel(const T *__restrict__ H
                                                          unsigned int *__restrict__ cnt)
 {
     __shared__ T top[2 * PEER_MAX];
+    __shared__ unsigned int s_cnt[PEER_MAX], s_base[PEER_MAX];
     for (int i = threadIdx.x; i < 2 * nleaves; i += blockDim.x) top[i] = H[i];
+    if (threadIdx.x < PEER_MAX) s_cnt[threadIdx.x] = 0;
     __syncthreads();
     const T root = top[1];
     const int lane = threadIdx.x & 31;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const int64_t rounds = (m + stride - 1) / stride;
+    constexpr int K = 4;                               // queries per thread and round
+    const int64_t rounds = (m + stride * K - 1) / (stride * K);
     for (int64_t r = 0; r < rounds; ++r) {
-        const int64_t i = r * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-        int q = -1;
-        T p = T(0);
-        if (i < m) {
-            // (root * u).astype(dtype), sumtree_array.py:420
-            if constexpr (sizeof(T) == 4 && is_float_t<T>::value) p = __double2float_rn(__dmul_rn((double)root, u[i]));
-            else if constexpr (is_float_t<T>::value) p = __dmul_rn(root, u[i]);
-            else p = (T)__dmul_rn((double)root, u[i]);
-            uint32_t h = 1;
-            for (int lev = 0; lev < depth; ++lev) {
-                const T lv = top[2 * h];
-                if (p >= lv) { p = t_sub<T>(p, lv); h = 2 * h + 1; } else { h = 2 * h; }
+        int q[K];
+        T p[K];
+        unsigned int off[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int64_t i = (r * K + k) * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+            q[k] = -1;
+            p[k] = T(0);
+            off[k] = 0;
+            if (i < m) {
+                // (root * u).astype(dtype), sumtree_array.py:420
+                if constexpr (sizeof(T) == 4 && is_float_t<T>::value) p[k] = __double2float_rn(__dmul_rn((double)root, u[i]));
+                else if constexpr (is_float_t<T>::value) p[k] = __dmul_rn(root, u[i]);
+                else p[k] = (T)__dmul_rn((double)root, u[i]);
+                uint32_t h = 1;
+                for (int lev = 0; lev < depth; ++lev) {
+                    const T lv = top[2 * h];
+                    if (p[k] >= lv) { p[k] = t_sub<T>(p[k], lv); h = 2 * h + 1; } else { h = 2 * h; }
+                }
+                q[k] = (int)h - nleaves;
             }
-            q = (int)h - nleaves;
+            // place inside this CTA's run for owner q: one shared-memory atomic per (warp, owner)
+            const unsigned int peers = __match_any_sync(0xffffffffu, q[k]);
+            if (q[k] >= 0) {
+                const int leader = __ffs(peers) - 1;
+                unsigned int b = 0;
+                if (lane == leader) b = atomicAdd(&s_cnt[q[k]], (unsigned int)__popc(peers));
+                off[k] = __shfl_sync(peers, b, leader) + __popc(peers & ((1u << lane) - 1u));
+            }
         }
-        const unsigned int peers = __match_any_sync(0xffffffffu, q);
-        if (q >= 0) {
-            const int leader = __ffs(peers) - 1;
-            unsigned int base = 0;
-            if (lane == leader) base = atomicAdd(cnt + q, (unsigned int)__popc(peers));
-            base = __shfl_sync(peers, base, leader);
-            const size_t at = (size_t)rank * (size_t)cap + base + __popc(peers & ((1u << lane) - 1u));
-            reinterpret_cast<T *>(pp.base[q] + resid_off)[at] = p;
-            reinterpret_cast<int32_t *>(pp.base[q] + pos_off)[at] = (int32_t)i;
+        __syncthreads();
+        // ONE global atomic per (CTA, owner, round): a counter bumped by every warp serialises ~2^15 atomics per 2^20 queries
+        if (threadIdx.x < nleaves) {
+            const unsigned int c = s_cnt[threadIdx.x];
+            s_base[threadIdx.x] = c ? atomicAdd(cnt + threadIdx.x, c) : 0u;
+            s_cnt[threadIdx.x] = 0;
         }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            if (q[k] >= 0) {
+                const size_t at = (size_t)rank * (size_t)cap + s_base[q[k]] + off[k];
+                reinterpret_cast<T *>(pp.base[q[k]] + resid_off)[at] = p[k];
+                reinterpret_cast<int32_t *>(pp.base[q[k]] + pos_off)[at] =
+                    (int32_t)((r * K + k) * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x);
+            }
+        }
+        __syncthreads();   // s_base is reused by the next round
     }
 }
 
@@ -832,7 +858,7 @@ int st_route_push_device(const st_tree *top, const double *u_dev, int64_t m, st_
     if (m == 0) return ST_OK;
     ST_DISPATCH(top->dtype, {
         ++st::g_kernel_launches;
-        st::route_push_kernel<T><<<st::grid_for(m, 256, (int64_t)top->sm_count * 8), 256, 0, s>>>(
+        st::route_push_kernel<T><<<st::grid_for(m, 256 * 4, (int64_t)top->sm_count * 8), 256, 0, s>>>(
             (const T *)top->heap, (int)top->n, top->depth, u_dev, m, p->rank, p->ptrs, st::PEER_FLAG_BYTES + (size_t)resid_offset,
             st::PEER_FLAG_BYTES + (size_t)pos_offset, cap, cnt_dev);
     });
