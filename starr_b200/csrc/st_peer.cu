@@ -310,15 +310,18 @@ __global__ void __launch_bounds__(256) route_push_kernel(const T *__restrict__ H
                                                          size_t resid_off, size_t pos_off, int64_t cap,
                                                          unsigned int *__restrict__ cnt)
 {
+    constexpr int K = 4;                               // queries per thread and round
     __shared__ T top[2 * PEER_MAX];
-    __shared__ unsigned int s_cnt[PEER_MAX], s_base[PEER_MAX];
+    __shared__ unsigned int s_cnt[PEER_MAX], s_base[PEER_MAX], s_pre[PEER_MAX + 1];
+    __shared__ T s_res[256 * K];
+    __shared__ int32_t s_pos[256 * K];
+    __shared__ unsigned char s_dst[256 * K];
     for (int i = threadIdx.x; i < 2 * nleaves; i += blockDim.x) top[i] = H[i];
     if (threadIdx.x < PEER_MAX) s_cnt[threadIdx.x] = 0;
     __syncthreads();
     const T root = top[1];
     const int lane = threadIdx.x & 31;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    constexpr int K = 4;                               // queries per thread and round
     const int64_t rounds = (m + stride * K - 1) / (stride * K);
     for (int64_t r = 0; r < rounds; ++r) {
         int q[K];
@@ -356,19 +359,34 @@ __global__ void __launch_bounds__(256) route_push_kernel(const T *__restrict__ H
         if (threadIdx.x < nleaves) {
             const unsigned int c = s_cnt[threadIdx.x];
             s_base[threadIdx.x] = c ? atomicAdd(cnt + threadIdx.x, c) : 0u;
-            s_cnt[threadIdx.x] = 0;
+        }
+        if (threadIdx.x == 0) {
+            unsigned int run = 0;
+            for (int d = 0; d < nleaves; ++d) { s_pre[d] = run; run += s_cnt[d]; }
+            s_pre[nleaves] = run;
         }
         __syncthreads();
+        // stage the round's elements grouped by owner, so that consecutive threads store consecutive elements of ONE
+        // owner's run (with 8 owners a warp's own lanes would give 16-byte remote stores)
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             if (q[k] >= 0) {
-                const size_t at = (size_t)rank * (size_t)cap + s_base[q[k]] + off[k];
-                reinterpret_cast<T *>(pp.base[q[k]] + resid_off)[at] = p[k];
-                reinterpret_cast<int32_t *>(pp.base[q[k]] + pos_off)[at] =
-                    (int32_t)((r * K + k) * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x);
+                const unsigned int sl = s_pre[q[k]] + off[k];
+                s_res[sl] = p[k];
+                s_pos[sl] = (int32_t)((r * K + k) * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x);
+                s_dst[sl] = (unsigned char)q[k];
             }
         }
-        __syncthreads();   // s_base is reused by the next round
+        __syncthreads();
+        const unsigned int total = s_pre[nleaves];
+        for (unsigned int e = threadIdx.x; e < total; e += blockDim.x) {
+            const int d = s_dst[e];
+            const size_t at = (size_t)rank * (size_t)cap + s_base[d] + (e - s_pre[d]);
+            reinterpret_cast<T *>(pp.base[d] + resid_off)[at] = s_res[e];
+            reinterpret_cast<int32_t *>(pp.base[d] + pos_off)[at] = s_pos[e];
+        }
+        if (threadIdx.x < nleaves) s_cnt[threadIdx.x] = 0;
+        __syncthreads();   // the staging arrays and counters are reused by the next round
     }
 }
 
