@@ -93,6 +93,18 @@ for r in rows[2:]:
     wr = to_bytes(r[idx["dram__bytes_write.sum"]], units[idx["dram__bytes_write.sum"]])
     traffic[key] = {"dram_bytes_per_launch": rd + wr, "dram_read": rd, "dram_write": wr,
                     "source": f"profiles/{tag}_ncu_full.md"}
+# the whole update pipeline of one batch (bench.py's roofline.traffic for the update): every update kernel once, the
+# radix pass three times (sparse float batches sort 21 key bits), the huge-segment summaries twice (second binade)
+UPDATE_KERNELS = {"make_keys_kernel": 1, "cub::DeviceRadixSortOnesweepKernel": 3, "leaf_pass_grouped_kernel": 1, "hy_hist_kernel": 1,
+                  "hy_scan_kernel": 1, "hy_scatter_kernel": 1, "hy_segment_kernel": 1, "deep_red_kernel": 1, "retire_kernel": 1,
+                  "fold_huge_maps_kernel": 2, "fold_huge_apply_kernel": 1, "fold_scan_kernel": 1}
+if all(k in traffic for k in UPDATE_KERNELS):
+    tot = sum(traffic[k]["dram_bytes_per_launch"] * c for k, c in UPDATE_KERNELS.items())
+    traffic["update_pipeline"] = {"dram_bytes_per_launch": tot, "source": f"profiles/{tag}_ncu_full.md",
+                                  "note": "sum over the update kernels of one 2^20-update batch: " +
+                                          ", ".join(f"{k} x{c}" for k, c in UPDATE_KERNELS.items())}
+    md.append(f"\n## update pipeline, one batch\n\nDRAM traffic summed over its kernels: {tot / 1e6:.1f} MB "
+              f"(algorithmic: 236 B x 2^20 = 247.5 MB).")
 open(os.path.join(ROOT, "profiles", f"{tag}_ncu_full.md"), "w").write("\n".join(md) + "\n")
 json.dump({"note": "dram__bytes_read.sum + dram__bytes_write.sum per launch (ncu --set full), BASELINE config #3",
            "kernels": traffic}, open(os.path.join(ROOT, "profiles", "ncu_traffic.json"), "w"), indent=1)
