@@ -473,10 +473,11 @@ def run_ours(args):
 
     # ---- end-to-end: HOST buffers in, sampled indices back on the host -----------------------------
     rng_e = np.random.default_rng(555 + rank)
-    e2e_distinct = min(steps + 2, 64)
+    e2e_distinct = min(steps + 3, 64)
     if world == 1:
         # through the C ABI: st_per_step_host_submit / st_per_step_host_wait (pinned host buffers from
-        # st_host_alloc; two slots, so the H2D of step k+1 and the D2H of step k-1 overlap the kernels of step k)
+        # st_host_alloc; three slots in flight, so the H2D of step k+1 and the D2H of step k-1 overlap the kernels of step k
+        # and the copy stream never waits for the host)
         h = tree.handle
         pins = []
         for _ in range(e2e_distinct):
@@ -485,34 +486,35 @@ def run_ours(args):
             u = pb.array(np.float64, m_local, 12 * m_local)
             i[:] = rng_e.integers(0, n_local, m_local); v[:] = rng_e.random(m_local, dtype=np.float32); u[:] = rng_e.random(m_local)
             pins.append((pb, i, v, u))
+        NS = 3          # slots in flight (the library has ST_HOST_SLOTS = 4): step k is submitted before step k - 2 is collected
         outs = []
-        for _ in range(2):
+        for _ in range(NS):
             pb = _lib.PinnedBuffer(m_local * 8)
             outs.append((pb, pb.array(np.int64, m_local, 0)))
 
         def e2e_run(first, nsteps):
             for k in range(nsteps):
-                slot = k % 2
-                if k >= 2:
-                    h.per_step_host_wait(slot)
+                slot = k % NS
+                if k >= NS:
+                    h.per_step_host_wait(slot)       # its results are in outs[slot]; the slot is reused for step k
                 _, i, v, u = pins[(first + k) % e2e_distinct]
                 h.per_step_host_submit(slot, i, v, u, outs[slot][1])
-            for k in range(max(0, nsteps - 2), nsteps):
-                h.per_step_host_wait(k % 2)
+            for k in range(max(0, nsteps - NS), nsteps):
+                h.per_step_host_wait(k % NS)
 
         torch.cuda.synchronize()
-        e2e_run(0, 2)
+        e2e_run(0, NS)
         counters(tree)
         t_w0 = time.time()
         t0 = time.perf_counter()
-        e2e_run(2, steps)
+        e2e_run(NS, steps)
         e2e_ms = (time.perf_counter() - t0) * 1e3     # host clock: the call is synchronous at its ends (wait() blocks)
         windows.append((t_w0, time.time()))
         cnt_e2e = counters(tree)
         e2e_how = ("C ABI st_per_step_host_submit/_wait on pinned host buffers (st_host_alloc): every step's indices, "
-                   "values and uniforms are copied H2D and its sampled indices D2H inside the timed region; two slots, "
-                   "so copies of step k+1 / k-1 overlap the kernels of step k; timed with the host clock around the "
-                   "blocking calls")
+                   "values and uniforms are copied H2D and its sampled indices D2H inside the timed region; three slots in "
+                   "flight, so copies of step k+1 / k-1 overlap the kernels of step k; timed with the host clock around "
+                   "the blocking calls (the last wait returns when the last step's indices are on the host)")
         del pins, outs
     elif layout == "slices":
         # Sharded, slices layout: every rank holds ITS 1/N of the batch in pinned host memory, uploads it (PCIe carries

@@ -379,12 +379,15 @@ ST_API int st_sample_weights_device(const st_tree *t, const double *u_dev, int64
 ST_API int st_per_step_device(st_tree *t, const int64_t *idx_dev, int64_t ni, const void *vals_dev, int64_t nv,
                        const double *u_dev, int64_t m, int64_t *out_idx_dev, void *out_prio_dev,
                        void *out_prob_dev, void *stream);
-/* The same step for HOST buffers, pipelined over two slots: submit(slot) enqueues H2D of
+/* The same step for HOST buffers, pipelined over ST_HOST_SLOTS slots: submit(slot) enqueues H2D of
  * (idx, vals, u) on a copy stream, the step on the compute stream and D2H of the results on a third
  * stream, and returns; wait(slot) blocks until that slot's results are in the caller's buffers and
- * returns the batch's validation status.  With both slots in flight the copies of step k+1 / k-1
- * overlap the kernels of step k.  Buffers must stay valid until wait(); use st_host_alloc (pinned
- * memory) for truly asynchronous copies.  out_prio_host / out_prob_host may be NULL. */
+ * returns the batch's validation status.  Steps run in submission order.  With three or more slots in
+ * flight (submit step k before waiting for step k - 2) the upload of step k+1 and the read-back of step
+ * k-1 overlap the kernels of step k and the host never holds up the copy stream; with two, the next upload
+ * starts only after the host has collected a result.  Buffers must stay valid until wait(); use
+ * st_host_alloc (pinned memory) for truly asynchronous copies.  out_prio_host / out_prob_host may be NULL. */
+#define ST_HOST_SLOTS 4
 ST_API int st_per_step_host_submit(st_tree *t, int slot, const int64_t *idx_host, int64_t ni, const void *vals_host,
                             int64_t nv, const double *u_host, int64_t m, int64_t *out_idx_host,
                             void *out_prio_host, void *out_prob_host);

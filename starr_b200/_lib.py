@@ -360,7 +360,7 @@ class TreeHandle:
 
     def per_step_host_submit(self, slot: int, idx: np.ndarray, vals: np.ndarray, u: np.ndarray, out_idx: np.ndarray,
                              out_prio: np.ndarray | None = None, out_prob: np.ndarray | None = None) -> None:
-        """Pipelined host step (two slots); the arrays must stay alive and untouched until per_step_host_wait."""
+        """Pipelined host step (slots 0 .. 3); the arrays must stay alive and untouched until per_step_host_wait."""
         check(lib().st_per_step_host_submit(self.ptr, int(slot), host_ptr(idx), idx.size, host_ptr(vals), vals.size,
                                             host_ptr(u), u.size, host_ptr(out_idx),
                                             host_ptr(out_prio) if out_prio is not None else None,

@@ -1028,7 +1028,7 @@ int st_per_step_host_submit(st_tree *t, int slot, const int64_t *idx_host, int64
                             int64_t nv, const double *u_host, int64_t m, int64_t *out_idx_host,
                             void *out_prio_host, void *out_prob_host)
 {
-    if (!t || slot < 0 || slot > 1 || ni < 0 || nv < 0 || m < 0 || t->kind != 0 || (m > 0 && (!u_host || !out_idx_host)))
+    if (!t || slot < 0 || slot >= ST_HOST_SLOTS || ni < 0 || nv < 0 || m < 0 || t->kind != 0 || (m > 0 && (!u_host || !out_idx_host)))
         return fail(ST_ERR_ARG, "st_per_step_host_submit: bad argument");
     if (ni > 0 && nv == 0) return fail(ST_ERR_EMPTY_VALS, "%s", st_status_string(ST_ERR_EMPTY_VALS));
     tree_lock lk(t);
@@ -1084,7 +1084,7 @@ int st_per_step_host_submit(st_tree *t, int slot, const int64_t *idx_host, int64
 
 int st_per_step_host_wait(st_tree *t, int slot)
 {
-    if (!t || slot < 0 || slot > 1) return fail(ST_ERR_ARG, "st_per_step_host_wait: bad argument");
+    if (!t || slot < 0 || slot >= ST_HOST_SLOTS) return fail(ST_ERR_ARG, "st_per_step_host_wait: bad argument");
     tree_lock lk(t);
     device_guard g(t->device);
     st_tree::host_slot &h = t->hs[slot];

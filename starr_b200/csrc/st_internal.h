@@ -59,14 +59,14 @@ struct st_tree {
     int pending_split = 0;
     int pending_gb = 0;        // leaf-group bits of the latest float batch (deep_red_kernel / retire_kernel)
     int64_t stat_updates = 0;  // updates submitted since the last st_update_counters(reset)
-    // pipelined host step (st_per_step_host_submit / _wait): two slots of device staging + streams + events
+    // pipelined host step (st_per_step_host_submit / _wait): ST_HOST_SLOTS slots of device staging + streams + events
     struct host_slot {
         void *dev = nullptr;       // idx | vals | u | out_idx | out_prio | out_prob
         size_t bytes = 0;
         cudaEvent_t ev_in = nullptr, ev_free = nullptr, ev_done = nullptr, ev_read = nullptr;
         unsigned int *h_flag = nullptr;   // pinned: validation flags of the slot's batch
         int busy = 0;
-    } hs[2];
+    } hs[4];   // ST_HOST_SLOTS
     cudaStream_t hs_in = nullptr, hs_main = nullptr, hs_out = nullptr;
     // sector-packed search index (st_sidx.cuh): copies of the left children below the staged levels, three levels
     // per 32-byte record; nullptr when the tree is too small / not a 4-byte sum tree / ST_SEARCH_INDEX=0

@@ -115,8 +115,9 @@ def test_per_step_cuda_graph_library_call(torch_mod, oracle_mod):
     assert_bits_equal(_np(dev.tree), tree, "tree after graph replays")
 
 
-def test_host_pipeline_step(oracle_mod):
-    """st_per_step_host_submit / _wait: pinned host buffers in and out, two slots in flight."""
+@pytest.mark.parametrize("NS", [2, 4])
+def test_host_pipeline_step(oracle_mod, NS):
+    """st_per_step_host_submit / _wait: pinned host buffers in and out, NS slots in flight."""
     from starr_b200 import _lib
     C = oracle_mod.c
     n, m = 1 << 18, 1 << 14
@@ -127,7 +128,7 @@ def test_host_pipeline_step(oracle_mod):
     h = _lib.TreeHandle(n, np.float32)
     h.build_from_host(leaves)
     slots = []
-    for _ in range(2):
+    for _ in range(NS):
         pb = _lib.PinnedBuffer(m * (8 + 4 + 8 + 8 + 4 + 4))
         off = 0
         arrs = []
@@ -138,21 +139,21 @@ def test_host_pipeline_step(oracle_mod):
     steps = 7
     for k in range(steps + 1):
         if k < steps:
-            _, (idx, val, u, o_idx, o_prio, o_prob) = slots[k % 2]
-            if k >= 2:
-                h.per_step_host_wait(k % 2)
-                w_idx, w_prio, w_prob = wants.pop(k - 2)
-                assert np.array_equal(o_idx, w_idx), f"step {k - 2}"
+            _, (idx, val, u, o_idx, o_prio, o_prob) = slots[k % NS]
+            if k >= NS:
+                h.per_step_host_wait(k % NS)
+                w_idx, w_prio, w_prob = wants.pop(k - NS)
+                assert np.array_equal(o_idx, w_idx), f"step {k - NS}"
                 assert_bits_equal(o_prio, w_prio, "priorities"); assert_bits_equal(o_prob, w_prob, "probabilities")
             idx[:] = rng.integers(0, n, m); val[:] = rng.random(m, dtype=np.float32); u[:] = rng.random(m)
             C.update_sumtree(idx.astype(np.intp), val, leaves, tree)
             want = np.zeros(m, np.intp)
             C.get_prefix_sum_idx(want, (tree[1] * u).astype(np.float32), leaves, tree)
             wants[k] = (want, leaves[want].copy(), leaves[want] / tree[1])
-            h.per_step_host_submit(k % 2, idx, val, u, o_idx, o_prio, o_prob)
-    for k in (steps - 2, steps - 1):
-        h.per_step_host_wait(k % 2)
-        _, (_, _, _, o_idx, o_prio, o_prob) = slots[k % 2]
+            h.per_step_host_submit(k % NS, idx, val, u, o_idx, o_prio, o_prob)
+    for k in range(steps - NS, steps):
+        h.per_step_host_wait(k % NS)
+        _, (_, _, _, o_idx, o_prio, o_prob) = slots[k % NS]
         assert np.array_equal(o_idx, wants[k][0]), f"step {k}"
         assert_bits_equal(o_prob, wants[k][2], "probabilities")
     t = np.zeros(n, np.float32)
