@@ -197,6 +197,7 @@ int st_create(int64_t n, int dtype, int device, void *external_heap, st_tree **o
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t->plan_ev, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t->ev_fork, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t->ev_join, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t->ev_hy, cudaEventDisableTiming);
     }
     if (e == cudaSuccess) {
         // search index (st_sidx.cuh): all zeros matches the all-zero tree
@@ -229,6 +230,7 @@ int st_destroy(st_tree *t)
     if (t->sidx) cudaFree(t->sidx);
     if (t->ev_fork) cudaEventDestroy(t->ev_fork);
     if (t->ev_join) cudaEventDestroy(t->ev_join);
+    if (t->ev_hy) cudaEventDestroy(t->ev_hy);
     if (t->side) cudaStreamDestroy(t->side);
     if (t->ws.base) cudaFree(t->ws.base);
     if (t->scratch.base) cudaFree(t->scratch.base);

@@ -77,6 +77,8 @@ struct st_tree {
     // the top nodes (disjoint node sets); forked / joined with the two events around every batch
     cudaStream_t side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_hy = nullptr;   // histogram + scan of the hybrid partition, run ahead on the side stream beside sort + leaf pass
+    int hy_ahead = 0;              // ... for the batch whose first half is enqueued
     // optional per-phase timing of the update pipeline (st_set_profiling)
     int profile = 0;
     cudaEvent_t prof_ev[8] = {};

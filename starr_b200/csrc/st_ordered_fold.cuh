@@ -337,6 +337,46 @@ __device__ void chunk_summary_cta(SRC src, int nc, int eT, chunk_rec<typename fp
         mag += (float)a + 2.f;
         local = pmap_then<I>(local, um[k].map);
     }
+    // Every update absorbed (a0 == a1 == 0 for the whole chunk: the node is far larger than the differences, the usual
+    // case for the upper levels of a big tree and for the top tree of a sharded one)?  Then the chunk's map is the
+    // identity and the trajectory never moves: no scan, the record is two reductions.
+    {
+        bool moves = false;
+        I mnq = 0, mxf = 0;
+#pragma unroll
+        for (int k = 0; k < FOLD_E; ++k) {
+            moves |= (um[k].map.a0 | um[k].map.a1) != 0;
+            const I f = um[k].flq;
+            mnq = f < mnq ? f : mnq;
+            const I fx = f > 0 ? (f >> 2) : I(0);
+            mxf = fx > mxf ? fx : mxf;
+        }
+        if (!__syncthreads_or(moves)) {      // also the barrier that frees the shared buffers
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const I a = shfl_xor_i<I>(mnq, off), b = shfl_xor_i<I>(mxf, off);
+                mnq = a < mnq ? a : mnq;
+                mxf = b > mxf ? b : mxf;
+            }
+            const int bigs = __syncthreads_or(anybig);
+            if (lane == 0) { s_red[warp][0] = mnq; s_red[warp][1] = mxf; }
+            __syncthreads();
+            if (tid == 0) {
+                chunk_rec<I> r;
+                r.a0 = 0; r.a1 = 0;
+                r.min0 = s_red[0][0]; r.max0 = s_red[0][1];
+                for (int w = 1; w < NW; ++w) {
+                    r.min0 = s_red[w][0] < r.min0 ? s_red[w][0] : r.min0;
+                    r.max0 = s_red[w][1] > r.max0 ? s_red[w][1] : r.max0;
+                }
+                r.min1 = r.min0; r.max1 = r.max0;
+                r.ok = bigs ? 0 : 1;
+                r.pad = 0;
+                *out = r;
+            }
+            return;
+        }
+    }
     const pmap<I> incl = pmap_warp_scan<I>(local, lane);
     pmap<I> excl = pmap_shfl_up<I>(incl, 1);
     if (lane == 0) excl = pmap<I>{0, 0};

@@ -882,6 +882,30 @@ struct update_timeline {
     }
 };
 
+// hybrid partition (st_partition_hybrid.cuh): top levels by counting sort, the rest per segment in shared memory; the
+// cooperative kernel then only runs (from level LT) for batches too skewed for that.  ST_HYBRID=0: A/B switch.
+static bool hy_applies(int m, int depth)
+{
+    static const bool hybrid_off = getenv("ST_HYBRID") && atoi(getenv("ST_HYBRID")) == 0;
+    return !hybrid_off && depth >= hy_top_levels(m) + 2 && m > RETIRE_SEG;
+}
+
+template <typename T>
+static hybrid_params<T> hy_params(const st_tree *t, const update_ws &w, T *lev, int m, int64_t B)
+{
+    const int LT = hy_top_levels(m);
+    hybrid_params<T> hp;
+    hp.n = (uint32_t)t->n; hp.depth = t->depth; hp.m = m; hp.ntiles = (m + HY_TILE - 1) / HY_TILE; hp.LT = LT;
+    hp.key0 = w.kj; hp.lev_key = w.lev_key; hp.lev_d = lev; hp.lev_stride = B;
+    hp.hist = w.hy_hist; hp.bintotal = w.hy_bintotal;
+    hp.segstart = w.hy_segstart; hp.seglen = w.hy_seglen; hp.segstate = w.hy_segstate;
+    hp.sC = (LT & 1) ? w.seg_sa : w.seg_sb;
+    hp.eC = (LT & 1) ? w.seg_ea : w.seg_eb;
+    hp.qlong = w.queue; hp.qmed = w.queue_med; hp.qhuge = w.queue_huge; hp.qret = w.queue_ret;
+    hp.huge_off = w.huge_off; hp.status = t->d_status;
+    return hp;
+}
+
 template <typename T>
 static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *idx, int m, const T *vals,
                                 int64_t nv, int64_t j0, int64_t B, T *delta_out, const T *deltas_in,
@@ -942,6 +966,29 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
     ++g_kernel_launches;
     make_keys_kernel<<<g, 256, 0, s>>>(idx, m, n, depth, w.keys_a, w.kj, w.j_a, status);
     tl.main(1, s);
+    if constexpr (is_float_t<T>::value) {
+        // The histogram and the scan of the hybrid partition need nothing but the batch-ordered keys: they run on the
+        // tree's side stream beside the sort and the leaf pass (ST_HY_AHEAD=0: behind them, on the caller's stream).
+        t->hy_ahead = 0;
+        static const bool overlap_off0 = getenv("ST_OVERLAP") && atoi(getenv("ST_OVERLAP")) == 0;
+        static const bool hy_ahead_off = getenv("ST_HY_AHEAD") && atoi(getenv("ST_HY_AHEAD")) == 0;
+        if (!deltas_in && !overlap_off0 && !hy_ahead_off && !t->profile && hy_applies(m, depth)) {
+            if (!t->side) {
+                e = cudaStreamCreateWithFlags(&t->side, cudaStreamNonBlocking);
+                if (e != cudaSuccess) return e;
+            }
+            e = cudaEventRecord(t->ev_fork, s);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(t->side, t->ev_fork, 0);
+            if (e != cudaSuccess) return e;
+            const hybrid_params<T> hp = hy_params<T>(t, w, (T *)w.lev_d, m, B);
+            g_kernel_launches += 2;
+            hy_hist_kernel<<<hp.ntiles, HY_THREADS, 0, t->side>>>(w.kj, m, depth, hp.LT, w.hy_hist, status);
+            hy_scan_kernel<T><<<1 << hp.LT, HY_THREADS, 0, t->side>>>(hp);
+            e = cudaEventRecord(t->ev_hy, t->side);
+            if (e != cudaSuccess) return e;
+            t->hy_ahead = 1;
+        }
+    }
     }
     if (!deltas_in && phase != 2) {
         // floats only need the duplicates of a leaf adjacent and batch-ordered: the low gb key bits stay unsorted,
@@ -1034,32 +1081,29 @@ static cudaError_t update_chunk(st_tree *t, const update_ws &w, const int64_t *i
         pp.l0 = 0;
         // hybrid partition: top levels by counting sort, the rest per segment in shared memory; the cooperative
         // kernel below then only runs (from level LT) for batches too skewed for that
-        static const bool hybrid_off = getenv("ST_HYBRID") && atoi(getenv("ST_HYBRID")) == 0;   // A/B switch
-        const int LT = hy_top_levels(m);
-        if (!hybrid_off && depth >= LT + 2 && m > RETIRE_SEG) {
-            hybrid_params<T> hp;
-            hp.n = n; hp.depth = depth; hp.m = m; hp.ntiles = (m + HY_TILE - 1) / HY_TILE; hp.LT = LT;
-            hp.key0 = w.kj; hp.lev_key = w.lev_key; hp.lev_d = lev; hp.lev_stride = B;
-            hp.hist = w.hy_hist; hp.bintotal = w.hy_bintotal;
-            hp.segstart = w.hy_segstart; hp.seglen = w.hy_seglen; hp.segstate = w.hy_segstate;
-            hp.sC = (LT & 1) ? w.seg_sa : w.seg_sb;
-            hp.eC = (LT & 1) ? w.seg_ea : w.seg_eb;
-            hp.qlong = w.queue; hp.qmed = w.queue_med; hp.qhuge = w.queue_huge; hp.qret = w.queue_ret;
-            hp.huge_off = w.huge_off; hp.status = status;
+        if (hy_applies(m, depth)) {
+            const hybrid_params<T> hp = hy_params<T>(t, w, lev, m, B);
             const size_t seg_smem = hy_segment_smem<T>();
             static per_device_once hy_attr;   // function attributes are per device
             e = hy_attr.run(t->device, [&] {
                 return cudaFuncSetAttribute(hy_segment_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seg_smem);
             });
             if (e != cudaSuccess) return e;
-            g_kernel_launches += 4;
-            hy_hist_kernel<<<hp.ntiles, HY_THREADS, 0, s>>>(w.kj, m, depth, LT, w.hy_hist, status);
-            hy_scan_kernel<T><<<1 << LT, HY_THREADS, 0, s>>>(hp);
+            if (t->hy_ahead) {       // histogram + scan ran ahead on the side stream (first half of this batch)
+                e = cudaStreamWaitEvent(s, t->ev_hy, 0);
+                if (e != cudaSuccess) return e;
+                t->hy_ahead = 0;
+            } else {
+                g_kernel_launches += 2;
+                hy_hist_kernel<<<hp.ntiles, HY_THREADS, 0, s>>>(w.kj, m, depth, hp.LT, w.hy_hist, status);
+                hy_scan_kernel<T><<<1 << hp.LT, HY_THREADS, 0, s>>>(hp);
+            }
+            g_kernel_launches += 2;
             hy_scatter_kernel<T><<<hp.ntiles, HY_THREADS, 0, s>>>(hp);
-            hy_segment_kernel<T><<<1 << LT, HY_B_THREADS, seg_smem, s>>>(hp);
+            hy_segment_kernel<T><<<1 << hp.LT, HY_B_THREADS, seg_smem, s>>>(hp);
             e = cudaGetLastError();
             if (e != cudaSuccess) return e;
-            pp.l0 = LT;
+            pp.l0 = hp.LT;
         }
         if (t->part_occ < 1) {   // per tree (one dtype, one device); the caller holds the tree's lock
             int occ = 0;
