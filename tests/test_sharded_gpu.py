@@ -425,6 +425,12 @@ def test_sharded_slices_on_one_gpu(world, dt_name, monkeypatch):
             pass
         if st.gather_sumtree().cpu().numpy().tobytes() != before:
             bad_steps.append(("bad batch", "tree modified"))
+        # an empty batch and an empty query set are legal (every rank still takes part in the exchange)
+        st.update_slices_(torch.zeros(0, dtype=torch.int64, device=dev), torch.zeros(0, dtype=tdt, device=dev))
+        if st.sample_slices(torch.zeros(0, dtype=torch.float64, device=dev)).numel() != 0:
+            bad_steps.append(("empty", "sample"))
+        if st.gather_sumtree().cpu().numpy().tobytes() != before:
+            bad_steps.append(("empty batch", "tree modified"))
         # and the tree keeps working afterwards
         m, mq, idx, vals, u, *_ = batches[0]
         st.update_slices_(torch.from_numpy(idx[r * m:(r + 1) * m]).to(dev), torch.from_numpy(vals[r * m:(r + 1) * m]).to(dev))
