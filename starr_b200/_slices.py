@@ -73,7 +73,8 @@ class SlicesExchange:
             "recv_idx": al(w * cap * 8), "recv_val": al(w * cap * es),           # worst case: every element to one owner
             "dback": al(cap * es), "dslice": al(span * es), "shard": al(span),
             "roots": al(w * es), "recs": al(w * (span // 1024) * (w - 1) * rb),
-            "recv_q": al(w * cap * es), "back_q": al(cap * 4),
+            # first version of sample (count matrix; A/B timing only)
+            "recv_q": al(w * cap * es) if self.sample_matrix else 256, "back_q": al(cap * 4) if self.sample_matrix else 256,
             # sample without a count matrix: one receive region per source rank, results come back as pairs
             "rq_resid": al(w * cap * es), "rq_pos": al(w * cap * 4), "rq_cnt": 256, "sent_cnt": 256, "back": al(w * cap * 8),
         }
@@ -117,7 +118,7 @@ class SlicesExchange:
         self.qrow = torch.zeros(w + 1, dtype=torch.int32, device=dev)
         self.qtotal = torch.zeros(1, dtype=torch.int32, device=dev)
         self.qcnt = torch.zeros(w, dtype=torch.int32, device=dev)
-        self.found = mk(w * cap, torch.int32)
+        self.found = mk(w * cap if self.sample_matrix else 1, torch.int32)
         self.rank_pos = torch.tensor([t.rank], dtype=torch.int32, device=dev)
         self._side = self._side or torch.cuda.Stream(device=dev)
 
