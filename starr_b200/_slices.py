@@ -65,7 +65,7 @@ class SlicesExchange:
     def _layout(self, cap: int) -> dict:
         t = self.t
         w, es = t.world, torch.empty(0, dtype=t.dtype).element_size()
-        al = lambda x: (x + 255) // 256 * 256                                    # noqa: E731
+        al = lambda x: (max(x, 1) + 255) // 256 * 256                            # noqa: E731
         span = (cap + 1023) // 1024 * 1024
         rb = t.top.top_fold_record_bytes() if t.dtype.is_floating_point else 0
         sizes = {

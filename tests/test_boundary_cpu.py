@@ -125,3 +125,40 @@ def test_shard_geometry():
     for bad in ((1000, 2), (1 << 20, 3), (4, 4)):
         with pytest.raises(ValueError):
             shard_geometry(*bad)
+
+
+def test_slices_exchange_layout_is_aligned_and_disjoint():
+    """Host logic of the slices layout (starr_b200/_slices.py): every region of the exchange buffer is 256-byte
+    aligned, the two parities of all regions are pairwise disjoint, and the per-source receive regions hold the
+    worst case (every element of every rank going to one owner)."""
+    import types
+
+    import torch
+
+    from starr_b200._slices import SlicesExchange
+    for world, dtype, rb in ((2, torch.float32, 32), (8, torch.float32, 32), (4, torch.float64, 56), (4, torch.int32, 0)):
+        tree = types.SimpleNamespace(world=world, dtype=dtype, top=types.SimpleNamespace(top_fold_record_bytes=lambda rb=rb: rb))
+        sx = SlicesExchange.__new__(SlicesExchange)
+        sx.t, sx.sample_matrix = tree, False
+        cap = 5000
+        lay = sx._layout(cap)
+        es = torch.empty(0, dtype=dtype).element_size()
+        spans = []
+        names = [k for k in lay if k != "bytes"]
+        for i, name in enumerate(names):
+            a, b = lay[name]
+            assert a % 256 == 0 and b % 256 == 0 and a < b
+            nxt = lay[names[i + 1]][0] if i + 1 < len(names) else lay["bytes"]
+            size = b - a
+            assert b + size == nxt, name                   # parity 1 ends where the next region starts
+            spans += [(a, a + size), (b, b + size)]
+        spans.sort()
+        assert all(x[1] <= y[0] for x, y in zip(spans, spans[1:]))
+        size_of = lambda name: lay[name][1] - lay[name][0]   # noqa: E731
+        assert size_of("recv_idx") >= world * cap * 8 and size_of("recv_val") >= world * cap * es
+        assert size_of("rq_resid") >= world * cap * es and size_of("rq_pos") >= world * cap * 4 and size_of("back") >= world * cap * 8
+        assert size_of("mat_u") >= world * (world + 1) * 4
+        span = (cap + 1023) // 1024 * 1024
+        assert size_of("dslice") >= span * es and size_of("shard") >= span
+        if rb:
+            assert size_of("recs") >= world * (span // 1024) * (world - 1) * rb
