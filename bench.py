@@ -17,7 +17,8 @@ the measured HBM copy bandwidth (MEASURED_PEAKS.json).  `cpu_baseline` = the ref
 compiled Cython module (oracle/_ref) -- or the C oracle port if that is absent -- timed on one
 host core on the same inputs (the reference is single-threaded by construction).
 
-`--impl reference` times that CPU implementation as the whole arm (same metric / config).
+`--impl reference` times that CPU implementation as the whole arm (same metric / config; with --gpus N one tree over
+all N * 2^27 leaves, each step a bounded 2^20 + 2^20 sample of the sharded step, rank 0 only).
 The oracle is only ever the checker / the baseline here, never part of the measured GPU path.
 """
 from __future__ import annotations
@@ -141,7 +142,7 @@ def make_batches(rng, n_leaves_global, m_global, count):
 # --------------------------------------------------------------------------------------------
 # CPU baseline (reference module from oracle/_ref, else the C oracle port)
 # --------------------------------------------------------------------------------------------
-def cpu_arm(leaves, batches, steps, warmup, keep=False):
+def cpu_arm(leaves, batches, steps, warmup, keep=False, full_step=None):
     """Time the reference CPU path: per step update_sumtree(2^20) + get_prefix_sum_idx(2^20), every step on
     a batch it has not seen.  keep=True also returns the final (leaves, tree) and every step's sampled
     indices: the in-run parity gate replays the same batches on the GPU and compares bits."""
@@ -183,11 +184,14 @@ def cpu_arm(leaves, batches, steps, warmup, keep=False):
     total = t_upd + t_srch
     res = {
         "value": 2 * m * steps / total, "unit": UNIT, "cores": 1, "kind": kind,
-        "sample": f"{steps} full steps (2^{LOG2_BATCH} updates + 2^{LOG2_BATCH} samples each, a fresh batch per step) "
-                  f"on one pinned host core; tree built by the C oracle",
+        "sample": (f"{steps} full steps (2^{LOG2_BATCH} updates + 2^{LOG2_BATCH} samples each, a fresh batch per step) "
+                   f"on one pinned host core; tree built by the C oracle") if not full_step or full_step == m else
+                  (f"{steps} bounded steps on the {n}-leaf tree: {m} updates + {m} samples of each step's {full_step} + "
+                   f"{full_step} (a fresh batch per step) on one pinned host core; ms_per_step is scaled to the full step; "
+                   f"tree built by the C oracle"),
         "updates_per_s": m * steps / t_upd, "samples_per_s": m * steps / t_srch,
         "host_cores_available": avail,
-        "ms_per_step": 1e3 * total / steps,
+        "ms_per_step": 1e3 * total / steps * ((full_step / m) if full_step else 1.0),
     }
     if keep:
         res["_state"] = (arr, tree, sampled)
@@ -203,19 +207,22 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n = 1 << LOG2_LEAVES
+    # the arm's config is ours: at N > 1 ONE tree over all N * 2^27 leaves (what the N shards hold together), each step a
+    # bounded sample (2^20 + 2^20 operations) of the N * 2^20 + N * 2^20 a sharded step processes
+    world = max(1, int(args.gpus))
+    n = (1 << LOG2_LEAVES) * world
     m = 1 << LOG2_BATCH
     rng = np.random.default_rng(0)
     leaves = rng.random(n, dtype=np.float32)
     steps = max(1, min(args.steps, 8))
     warmup = max(1, min(args.warmup, 2))
     batches = make_batches(rng, n, m, steps + warmup)
-    base = cpu_arm(leaves, batches, steps, warmup)
+    base = cpu_arm(leaves, batches, steps, warmup, full_step=m * world)
     line = {
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": base["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(1),
+        "config": workload_config(world, "single" if world == 1 else args.layout),
         "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample", "updates_per_s",
                                               "samples_per_s", "host_cores_available")},
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
