@@ -83,7 +83,7 @@ typedef enum st_inplace_op {
     ST_OP_FILL = 4  /* x.fill(c) */
 } st_inplace_op;
 
-ST_API int st_abi_version(void);
+ST_API int st_abi_version(void); /* 4 */
 ST_API const char *st_status_string(int status);
 ST_API const char *st_last_error(void); /* detail of the last failure on this thread */
 ST_API int st_dtype_size(int dtype);     /* bytes, or -1 */

@@ -126,7 +126,7 @@ namespace st { std::atomic<unsigned long long> g_kernel_launches{0}; }
 
 extern "C" {
 
-int st_abi_version(void) { return 3; }
+int st_abi_version(void) { return 4; }   // 4: slices layout, sample push, ST_HOST_SLOTS = 4
 
 unsigned long long st_kernel_launches(void) { return st::g_kernel_launches.load(); }
 

@@ -35,7 +35,7 @@ def test_ctypes_binding_covers_header(built_lib):
     from starr_b200 import _lib
     assert sorted(_lib.EXPORTED_SYMBOLS) == _declared_symbols()
     lib = _lib.lib()
-    assert lib.st_abi_version() == 3
+    assert lib.st_abi_version() == 4
     assert [lib.st_dtype_size(c) for c in range(9)] == [2, 4, 8, 1, 2, 4, 8, 4, 8]
     assert lib.st_status_string(1) == b"vals must be non-negative"
     assert lib.st_status_string(2) == b"array elements must be non-negative"
