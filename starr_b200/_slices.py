@@ -197,6 +197,10 @@ class SlicesExchange:
             if flags & _FLAG_INDEX:
                 raise IndexError("Out of bounds on buffer access (axis 0)")
             raise ValueError("vals must be non-negative")
+        if any(sum(mat[r][:w]) != m for r in range(w)):       # the chunk numbering of the top fold assumes equal slices
+            area.wait(self.CH_UDATA, p, main.cuda_stream)
+            self._mark_free(par, main)
+            raise ValueError("slices layout: every rank must supply the same number of elements per batch")
         c = sum(mat[r][t.rank] for r in range(w))
         es = t.local.heap.element_size()
         s = main.cuda_stream
