@@ -213,3 +213,74 @@ def test_map_composition_is_associative():
         for m in (1000, 1001):
             step = lambda mm, p: mm + (p[1] if mm & 1 else p[0])
             assert step(step(step(m, f), g), h) == step(m, then(then(f, g), h))
+
+
+def chunk_record(ds, et, dt):
+    """chunk_summary_cta: parity map of the whole chunk plus, for either start parity, the extremes of
+    4 (m_k - m_in) + min(floor(4 x_k), 0)   (QUARTER units)   and   (m_k - m_in) + max(floor(x_k), 0)."""
+    rec = {"ok": True}
+    maps = []
+    for d in ds:
+        a0, a1, flq, big = decompose(d, et, dt)
+        rec["ok"] &= not big
+        maps.append((a0, a1, flq))
+    tot = (0, 0)
+    for a0, a1, _ in maps:
+        tot = then(tot, (a0, a1))
+    rec["a"] = tot
+    for parity in (0, 1):
+        off, mn, mx = 0, 0, 0
+        for a0, a1, flq in maps:
+            mn = min(mn, 4 * off + min(flq, 0))
+            mx = max(mx, off + (flq >> 2) if flq > 0 else off)
+            off += a1 if (off + parity) & 1 else a0
+        rec[parity] = (mn, mx)
+    return rec
+
+
+def absorbed_chunk_record(ds, et, dt):
+    """The early-out of chunk_summary_cta: every element's map is the identity -> no scan, two reductions."""
+    flqs = []
+    ok = True
+    for d in ds:
+        a0, a1, flq, big = decompose(d, et, dt)
+        assert a0 == 0 and a1 == 0
+        ok &= not big
+        flqs.append(flq)
+    mn = min([0] + [f for f in flqs if f < 0])
+    mx = max([0] + [f >> 2 for f in flqs if f > 0])
+    return {"ok": ok, "a": (0, 0), 0: (mn, mx), 1: (mn, mx)}
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64], ids=["f32", "f64"])
+def test_chunk_records_cover_exactly_what_the_element_walk_covers(dt):
+    """A chunk record accepts an incoming m (4 (m - LO) + min >= -1 and m + max < HI) exactly when walking its
+    elements one by one never meets an update the identity does not cover; then m_out = m + a[parity]; and the
+    absorbed-chunk shortcut produces the same record as the general path."""
+    rng = np.random.default_rng(11)
+    mb = FMT[dt][1]
+    lo, hi = 1 << mb, 1 << (mb + 1)
+    for rep in range(200):
+        t = dt(2.0 ** rng.integers(3, 12) * rng.choice([1.0, 1.0 + 2.0 ** -mb, 1.5, 2.0 - 2.0 ** -mb]))   # on / next to a boundary, mid-binade
+        ok, et, m0 = scan_ready(t, dt)
+        ulp = float(np.spacing(t))
+        scale = rng.choice([0.2, 0.6, 3.0])
+        ds = (rng.uniform(-1, 1, int(rng.integers(1, 64))) * ulp * scale).astype(dt)
+        rec = chunk_record(ds, et, dt)
+        if all(decompose(d, et, dt)[:2] == (0, 0) for d in ds):
+            assert absorbed_chunk_record(ds, et, dt) == rec
+        for m in (m0, lo, lo + 1, hi - 1, hi - 2, (lo + hi) // 2):
+            mn, mx = rec[m & 1]
+            accept = rec["ok"] and 4 * (m - lo) + mn >= -1 and m + mx < hi
+            mm, walk_ok = m, True
+            for d in ds:
+                a0, a1, flq, big = decompose(d, et, dt)
+                if big or not covered(mm, flq, dt):
+                    walk_ok = False
+                    break
+                mm += a1 if mm & 1 else a0
+            assert accept == walk_ok, (rep, m - lo)
+            if accept:
+                assert mm == m + (rec["a"][1] if m & 1 else rec["a"][0])
+                want = sequential(value_of(et, m, dt), ds, dt)
+                assert bits(value_of(et, mm, dt), dt) == bits(want, dt)
